@@ -1,0 +1,255 @@
+"""Eager SPMD op dispatch: ``DTensor.__torch_dispatch__`` lands here.
+
+unwrap → OpSchema → ShardingPropagator (cached) → redistribute inputs if the rule asks → local aten op
+on the shards → wrap.  Custom handlers short-circuit ops whose semantics are not "run locally":
+fused optimizers (unwrap lists and call once), amp found-inf (local op + MAX all-reduce), ragged
+vector norm, scalar extraction, equality.
+
+Parity: reference ``vescale/dtensor/_dispatch.py:247-383`` and legacy ``dtensor/dispatch.py:235-392``,
+``_dispatch_bypass.py``, ``_dispatch_patch.py``.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..layout import compute_local_shape
+from ..placement import Partial, RaggedShard, Replicate, Shard
+from ..spec import DTensorSpec, TensorMeta, contiguous_stride
+from .op_schema import OpSchema, OutputSharding
+from .redistribute import redistribute_local_tensor
+from .sharding_prop import propagator
+
+aten = torch.ops.aten
+
+__all__ = ["OpDispatcher", "dispatcher", "register_op_handler"]
+
+
+def _disable_redistribute() -> bool:
+    return os.environ.get("VESCALE_DISABLE_REDISTRIBUTE", "0") == "1"
+
+
+class OpDispatcher:
+    def __init__(self):
+        self.sharding_propagator = propagator
+        self._custom: Dict[Any, Callable] = {}
+        self._random_ops = set()
+        self._hooks: List[Callable] = []  # debug logger hooks: fn(op, schema, output_sharding)
+
+    def register_handler(self, ops, fn):
+        if not isinstance(ops, (list, tuple)):
+            ops = [ops]
+        for op in ops:
+            if isinstance(op, torch._ops.OpOverloadPacket):
+                for n in op.overloads():
+                    self._custom[getattr(op, n)] = fn
+            else:
+                self._custom[op] = fn
+
+    # ------------------------------------------------------------------ unwrap
+    def unwrap(self, op, args, kwargs):
+        from .api import DTensor, _IMPLICIT_REPLICATION
+
+        mesh = None
+        for a in args:
+            if type(a) is DTensor:
+                mesh = a._spec.mesh
+                break
+            if isinstance(a, (list, tuple)):
+                for x in a:
+                    if type(x) is DTensor:
+                        mesh = x._spec.mesh
+                        break
+                if mesh is not None:
+                    break
+        if mesh is None:
+            for a in kwargs.values():
+                if type(a) is DTensor:
+                    mesh = a._spec.mesh
+                    break
+        if mesh is None:
+            raise RuntimeError(f"{op}: no DTensor argument")
+
+        def conv(a):
+            if type(a) is DTensor:
+                if a._spec.mesh != mesh:
+                    raise RuntimeError(f"{op}: DTensor operands live on different meshes")
+                return a._spec, a._local_tensor
+            if isinstance(a, torch.Tensor):
+                if a.ndim == 0 or a.numel() == 1 or _IMPLICIT_REPLICATION[0] or op in _AUTO_WRAP_OPS:
+                    spec = DTensorSpec(mesh, tuple(Replicate() for _ in range(mesh.ndim)), TensorMeta(tuple(a.shape), tuple(a.stride()), a.dtype))
+                    return spec, a
+                raise RuntimeError(
+                    f"{op}: got mixed torch.Tensor and DTensor operands; wrap the tensor with DTensor.from_local "
+                    "or use vescale_b200.dtensor.implicit_replication()"
+                )
+            return a, a
+
+        args_s, args_l = [], []
+        for a in args:
+            if isinstance(a, (list, tuple)) and any(isinstance(x, torch.Tensor) for x in a):
+                ss, ll = zip(*(conv(x) for x in a))
+                args_s.append(tuple(ss))
+                args_l.append(list(ll))
+            else:
+                s, l = conv(a)
+                args_s.append(s)
+                args_l.append(l)
+        kw_s, kw_l = {}, {}
+        for k, a in kwargs.items():
+            s, l = conv(a)
+            kw_s[k] = s
+            kw_l[k] = l
+        return mesh, OpSchema(op, tuple(args_s), kw_s, mesh), args_l, kw_l
+
+    # ------------------------------------------------------------------ dispatch
+    def dispatch(self, op, args, kwargs):
+        h = self._custom.get(op)
+        if h is not None:
+            return h(op, args, kwargs)
+        mesh, schema, local_args, local_kwargs = self.unwrap(op, args, kwargs)
+        out_sh = self.sharding_propagator.propagate(schema)
+        for hook in self._hooks:
+            hook(op, schema, out_sh)
+        if mesh.get_coordinate() is None:
+            return self._wrap_no_participation(op, args, out_sh)
+
+        if out_sh.redistribute_specs is not None:
+            self._redistribute_inputs(schema, out_sh, local_args, local_kwargs)
+        if out_sh.local_args:
+            for i, v in out_sh.local_args.items():
+                if i < len(local_args):
+                    local_args[i] = v
+        if out_sh.local_kwargs:
+            local_kwargs.update(out_sh.local_kwargs)
+        if out_sh.pre is not None:
+            out_sh.pre(local_args, local_kwargs, mesh)
+
+        if op in _RANDOM_OPS:
+            from .random import rng_region
+
+            first = schema.tensor_specs()[0]
+            with rng_region(first):
+                local_out = op(*local_args, **local_kwargs)
+        else:
+            local_out = op(*local_args, **local_kwargs)
+        if out_sh.post is not None:
+            local_out = out_sh.post(local_out, local_args, mesh)
+        return self.wrap(op, args, kwargs, local_out, out_sh.output_spec)
+
+    def _redistribute_inputs(self, schema, out_sh, local_args, local_kwargs):
+        if _disable_redistribute():
+            raise RuntimeError(
+                f"{schema.op}: implicit redistribution is disabled (VESCALE_DISABLE_REDISTRIBUTE=1) but inputs "
+                f"{[s.placements for s in schema.tensor_specs()]} need {[None if s is None else s.placements for s in out_sh.redistribute_specs]}"
+            )
+        it = iter(out_sh.redistribute_specs)
+
+        def fix(spec, local):
+            tgt = next(it)
+            if tgt is None:
+                return local
+            return redistribute_local_tensor(local, spec, tgt)
+
+        for i, s in enumerate(schema.args_schema):
+            if isinstance(s, DTensorSpec):
+                local_args[i] = fix(s, local_args[i])
+            elif isinstance(s, tuple) and s and any(isinstance(x, DTensorSpec) for x in s):
+                local_args[i] = [fix(x, l) if isinstance(x, DTensorSpec) else l for x, l in zip(s, local_args[i])]
+        for k, s in schema.kwargs_schema.items():
+            if isinstance(s, DTensorSpec):
+                local_kwargs[k] = fix(s, local_kwargs[k])
+
+    # ------------------------------------------------------------------ wrap
+    def wrap(self, op, args, kwargs, local_out, out_spec):
+        from .api import DTensor
+
+        sch = op._schema
+        if sch.is_mutable:
+            name = sch.name
+            if "out" in kwargs and kwargs["out"] is not None:
+                return kwargs["out"]
+            if name.endswith("_") or any(a.alias_info is not None and a.alias_info.is_write for a in sch.arguments[:1]):
+                self_arg = args[0]
+                if isinstance(self_arg, DTensor):
+                    spec = out_spec[0] if isinstance(out_spec, tuple) and out_spec else out_spec
+                    if isinstance(spec, DTensorSpec) and spec.placements != self_arg._spec.placements:
+                        raise RuntimeError(
+                            f"{op}: in-place result would change placements {self_arg._spec.placements} -> {spec.placements}"
+                        )
+                    return self_arg
+                if isinstance(self_arg, (list, tuple)):  # foreach in-place ops return None
+                    return None
+        return self._wrap_out(local_out, out_spec)
+
+    def _wrap_out(self, local_out, out_spec):
+        from .api import DTensor
+
+        if isinstance(local_out, torch.Tensor):
+            spec = out_spec[0] if isinstance(out_spec, tuple) else out_spec
+            if spec is None:
+                return local_out
+            if spec.tensor_meta.dtype != local_out.dtype:
+                spec = spec.with_meta(TensorMeta(spec.shape, spec.stride, local_out.dtype))
+            return DTensor(local_out, spec, requires_grad=False)
+        if isinstance(local_out, (list, tuple)):
+            specs = out_spec if isinstance(out_spec, (list, tuple)) else [out_spec] * len(local_out)
+            res = [self._wrap_out(o, s) if isinstance(o, torch.Tensor) and s is not None else o for o, s in zip(local_out, specs)]
+            return type(local_out)(res) if isinstance(local_out, tuple) else res
+        return local_out
+
+    def _wrap_no_participation(self, op, args, out_sh):
+        from .api import DTensor
+
+        spec = out_sh.output_spec
+        if op._schema.is_mutable and isinstance(args[0], DTensor):
+            return args[0]
+
+        def mk(s):
+            if s is None:
+                return None
+            return DTensor(torch.empty(0, dtype=s.dtype, device=s.mesh.device_type if s.mesh.device_type != "meta" else "cpu"), s)
+
+        if isinstance(spec, tuple):
+            return tuple(mk(s) for s in spec)
+        return mk(spec)
+
+
+# ops for which plain tensors are silently treated as replicated (reference ``_dispatch.py:281-315``)
+_AUTO_WRAP_OPS = {
+    aten._foreach_mul_.Tensor,
+    aten._foreach_norm.Scalar,
+    aten.mul_.Tensor,
+    aten.index_put.default,
+    aten.index_put_.default,
+    aten._index_put_impl_.default,
+    aten.index.Tensor,
+    aten.eq.Tensor,
+    aten.scatter.src,
+    aten.scatter_.src,
+}
+
+_RANDOM_OPS = {
+    aten.native_dropout.default,
+    aten.normal_.default,
+    aten.uniform_.default,
+    aten.bernoulli.default,
+    aten.bernoulli_.float,
+    aten.rand_like.default,
+    aten.randn_like.default,
+    aten.randint_like.default,
+    aten.exponential_.default,
+}
+
+dispatcher = OpDispatcher()
+
+
+def register_op_handler(ops, fn=None):
+    def deco(f):
+        dispatcher.register_handler(ops, f)
+        return f
+
+    return deco(fn) if fn is not None else deco

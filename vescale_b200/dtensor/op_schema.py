@@ -1,0 +1,108 @@
+"""OpSchema / OutputSharding: what a sharding rule consumes and produces.
+
+A rule sees the op plus its arguments with every DTensor replaced by its ``DTensorSpec`` and returns
+the output placements together with (optionally) the input placements it needs; the propagator fills
+in tensor metadata and the dispatcher performs any redistribution.
+
+Parity: ``legacy/vescale/dtensor/op_schema.py`` (OpSchema:73, OutputSharding:268, RuntimeSchemaInfo:52),
+reference ``vescale/dtensor/_op_schema.py``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from ..placement import Placement
+from ..spec import DTensorSpec
+
+__all__ = ["OpSchema", "OutputSharding", "RuleResult", "PlacementList"]
+
+PlacementList = Tuple[Placement, ...]
+
+
+def _freeze(x):
+    """Hashable form of an op argument (lists -> tuples, tensors rejected by the caller)."""
+    if isinstance(x, (list, tuple)):
+        return tuple(_freeze(i) for i in x)
+    if isinstance(x, dict):
+        return tuple(sorted((k, _freeze(v)) for k, v in x.items()))
+    if isinstance(x, torch.Tensor):
+        raise TypeError("tensor in static args")
+    return x
+
+
+class OpSchema:
+    """``args_schema`` / ``kwargs_schema`` mirror the call with specs in place of DTensors.
+    Lists of DTensors (foreach ops, cat) become tuples of specs."""
+
+    __slots__ = ("op", "args_schema", "kwargs_schema", "_hash", "mesh")
+
+    def __init__(self, op, args_schema: Tuple[Any, ...], kwargs_schema: Dict[str, Any], mesh=None):
+        self.op = op
+        self.args_schema = args_schema
+        self.kwargs_schema = kwargs_schema
+        self.mesh = mesh
+        self._hash: Optional[int] = None
+
+    def __hash__(self) -> int:
+        if self._hash is None:
+            self._hash = hash((self.op, _freeze(self.args_schema), _freeze(self.kwargs_schema)))
+        return self._hash
+
+    def __eq__(self, other) -> bool:
+        return (
+            isinstance(other, OpSchema)
+            and self.op == other.op
+            and _freeze(self.args_schema) == _freeze(other.args_schema)
+            and _freeze(self.kwargs_schema) == _freeze(other.kwargs_schema)
+        )
+
+    def tensor_specs(self) -> List[DTensorSpec]:
+        """All specs in call order (lists flattened)."""
+        out: List[DTensorSpec] = []
+        for a in list(self.args_schema) + list(self.kwargs_schema.values()):
+            if isinstance(a, DTensorSpec):
+                out.append(a)
+            elif isinstance(a, (list, tuple)):
+                out.extend(x for x in a if isinstance(x, DTensorSpec))
+        return out
+
+    def arg(self, i: int, default=None):
+        return self.args_schema[i] if i < len(self.args_schema) else default
+
+    def __repr__(self) -> str:
+        return f"OpSchema({self.op}, {self.args_schema}, {self.kwargs_schema})"
+
+
+@dataclass
+class RuleResult:
+    """What a rule returns.
+
+    ``out``: placements for the single output, or a tuple/list of placements-or-None for multi-output
+    ops, or None for ops without tensor outputs.
+    ``ins``: required placements for each tensor input in ``tensor_specs()`` order; None = keep as is.
+    ``local_args`` / ``local_kwargs``: overrides for the *non-tensor* arguments of the local call
+    (index -> value / name -> value), e.g. the per-shard size for ``view``.
+    ``out_shapes``: explicit global output shape(s) when meta propagation cannot produce them.
+    """
+
+    out: Any
+    ins: Optional[Sequence[Optional[PlacementList]]] = None
+    local_args: Optional[Dict[int, Any]] = None
+    local_kwargs: Optional[Dict[str, Any]] = None
+    post: Optional[Callable] = None  # post-process local outputs (e.g. mask for vocab-parallel embedding)
+    pre: Optional[Callable] = None  # pre-process local tensor args (list) before the local call
+
+
+@dataclass
+class OutputSharding:
+    """Propagation result: output spec(s), and the input specs to redistribute to (if any)."""
+
+    output_spec: Any
+    redistribute_specs: Optional[List[Optional[DTensorSpec]]] = None
+    local_args: Optional[Dict[int, Any]] = None
+    local_kwargs: Optional[Dict[str, Any]] = None
+    post: Optional[Callable] = None
+    pre: Optional[Callable] = None

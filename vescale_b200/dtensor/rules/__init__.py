@@ -1,0 +1,2 @@
+"""Sharding rules.  Importing this package registers every rule with the propagator."""
+from . import common, pointwise, math, matrix, view, tensor  # noqa: F401
