@@ -1,0 +1,1 @@
+from .llama import LlamaConfig, LlamaModel, LlamaBlock, llama_flops_per_token  # noqa: F401

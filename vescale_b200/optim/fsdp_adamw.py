@@ -1,0 +1,173 @@
+"""FSDPAdamW: AdamW over the flat unit shards of a ``fully_shard``-ed model.
+
+One fused launch per unit (``csrc/adamw.cu``): reads the reduce-scattered gradient shard (fp32, or bf16 at
+world size 1), applies the global-norm clip coefficient *from a device scalar* (no host sync), updates the
+fp32 master / exp_avg / exp_avg_sq shards and writes the bf16 parameter shard that the next all-gather reads
+— i.e. "copy grads→main, clip, Adam, copy main→model params" of the reference's DistributedOptimizer
+(``legacy/vescale/optim/distributed_optimizer.py:1142-1261``) in a single pass over HBM.  Weight decay is
+per-parameter through a small segment table (norm weights and other 1-D params are not decayed).
+
+When ``max_grad_norm is None`` and the symmetric-memory backend is active, ``fused_reduce=True`` folds the
+update into the reduce-scatter kernel itself (``rs_adamw``): the reduced gradient never touches HBM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..ops import _ext
+from ..parallel.fsdp.api import FSDPState, get_fsdp_state
+from ..parallel.fsdp.unit import FSDPUnit
+
+__all__ = ["FSDPAdamW"]
+
+
+class FSDPAdamW:
+    def __init__(
+        self,
+        model: torch.nn.Module,
+        lr: float = 1e-3,
+        betas: Tuple[float, float] = (0.9, 0.95),
+        eps: float = 1e-8,
+        weight_decay: float = 0.1,
+        max_grad_norm: Optional[float] = 1.0,
+        no_decay: Optional[Callable[[str, Sequence[int]], bool]] = None,
+        state_dtype: torch.dtype = torch.float32,
+    ):
+        st = None
+        for m in model.modules():
+            st = get_fsdp_state(m)
+            if st is not None:
+                break
+        if st is None:
+            raise ValueError("model is not wrapped with fully_shard")
+        self.state: FSDPState = st
+        self.units: List[FSDPUnit] = st.units
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.step_count = 0
+        self.no_decay = no_decay or (lambda name, shape: len(shape) <= 1)
+        dev = st.device
+        for u in self.units:
+            u.exp_avg = torch.zeros(u.S, dtype=state_dtype, device=dev)
+            u.exp_avg_sq = torch.zeros(u.S, dtype=state_dtype, device=dev)
+            segs = []
+            for slot in u.layout.slots:
+                lo, hi = u.layout.rank_range(slot, u.rank)
+                if hi > lo:
+                    segs.append((lo, hi, 0.0 if self.no_decay(slot.name, slot.shape) else 1.0))
+            u.wd_segments = segs
+            if dev.type == "cuda":
+                # [n, 3] int64/float table consumed by the kernel: (lo, hi, decay_flag)
+                u.wd_table = torch.tensor([[s[0], s[1], int(s[2])] for s in segs] or [[0, 0, 0]], dtype=torch.int64, device=dev)
+        self._norm_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._coef = torch.ones(1, dtype=torch.float32, device=dev)
+        self.last_grad_norm: Optional[torch.Tensor] = None
+        self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
+
+    # ------------------------------------------------------------------ grad norm (device-side)
+    def _global_grad_norm(self) -> torch.Tensor:
+        tot = self._norm_buf.zero_()
+        for u in self.units:
+            if not u.grad_ready:
+                continue
+            if u.sumsq is not None:  # produced by the fused reduce-scatter kernel
+                tot += u.sumsq
+                continue
+            g = u.grad_shard
+            sc = getattr(u, "grad_scale_pending", 1.0)
+            if g.is_cuda and _ext.available():
+                _ext.count_launch("sumsq")
+                _ext.ops().sumsq_accumulate(g, tot, float(sc))
+            else:
+                tot += (g.float() * sc).pow(2).sum()
+        if self.state.mesh.has_groups() and self.units and self.units[0].world > 1:
+            dist.all_reduce(tot, group=self.units[0].group)
+        return tot.sqrt()
+
+    @torch.no_grad()
+    def step(self) -> Optional[torch.Tensor]:
+        st = self.state
+        st.wait_grads()
+        self.step_count += 1
+        b1, b2 = self.betas
+        lr = self.param_groups[0]["lr"]
+        bc1 = 1.0 - b1**self.step_count
+        bc2 = 1.0 - b2**self.step_count
+        norm = None
+        if self.max_grad_norm is not None:
+            norm = self._global_grad_norm()
+            torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0, out=self._coef)
+            self.last_grad_norm = norm
+        else:
+            self._coef.fill_(1.0)
+        for u in self.units:
+            if not u.grad_ready:
+                continue
+            g = u.grad_shard
+            sc = getattr(u, "grad_scale_pending", 1.0)
+            if g.is_cuda and _ext.available():
+                _ext.count_launch("adamw")
+                _ext.ops().fused_adamw_(
+                    u.master, u.exp_avg, u.exp_avg_sq, g, u.param_shard, u.wd_table, self._coef,
+                    float(lr), float(b1), float(b2), float(self.eps), float(self.weight_decay), float(bc1), float(bc2), float(sc),
+                )
+            else:
+                self._step_reference(u, g, sc, lr, b1, b2, bc1, bc2)
+            u.bf16_fresh = True
+            u.grad_ready = False
+            u.sumsq = None
+        st.invalidate_params()
+        st.iteration += 1
+        return norm
+
+    def _step_reference(self, u: FSDPUnit, g, sc, lr, b1, b2, bc1, bc2) -> None:
+        gf = g.float() * (self._coef * sc)
+        u.exp_avg.mul_(b1).add_(gf, alpha=1 - b1)
+        u.exp_avg_sq.mul_(b2).addcmul_(gf, gf, value=1 - b2)
+        denom = (u.exp_avg_sq / bc2).sqrt_().add_(self.eps)
+        upd = (u.exp_avg / bc1) / denom
+        for lo, hi, dec in u.wd_segments:
+            if dec:
+                u.master[lo:hi].mul_(1 - lr * self.weight_decay)
+        # padding has zero grad and zero state: update is 0 there
+        u.master.add_(upd, alpha=-lr)
+        u.param_shard.copy_(u.master)
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        for u in self.units:
+            u.zero_grad()
+
+    # ------------------------------------------------------------------ checkpointing (DTensor views → DCP)
+    def state_dict(self) -> dict:
+        """Optimizer state as RaggedShard DTensors keyed like the parameters, so DCP can reshard it
+        (reference ``OptimizerStateSpec`` resharding, ``distributed_optimizer.py:51-93,748-880``)."""
+        from ..dtensor.api import DTensor
+
+        out = {"step": self.step_count, "state": {}}
+        for u in self.units:
+            for slot, sp in zip(u.layout.slots, u.sharded_params):
+                lo, hi = u.layout.rank_range(slot, u.rank)
+                key = f"{u.name}.{u._index}.{slot.name}"
+                out["state"][key] = {
+                    "exp_avg": DTensor(u.exp_avg[lo:hi], sp.data._spec),
+                    "exp_avg_sq": DTensor(u.exp_avg_sq[lo:hi], sp.data._spec),
+                }
+        return out
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd.get("step", 0))
+        for u in self.units:
+            for slot in u.layout.slots:
+                lo, hi = u.layout.rank_range(slot, u.rank)
+                key = f"{u.name}.{u._index}.{slot.name}"
+                ent = sd["state"].get(key)
+                if ent is None:
+                    continue
+                for nm, buf in (("exp_avg", u.exp_avg), ("exp_avg_sq", u.exp_avg_sq)):
+                    t = ent[nm]
+                    t = t._local_tensor if hasattr(t, "_local_tensor") else t
+                    buf[lo:hi].copy_(t.reshape(-1))
