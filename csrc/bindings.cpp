@@ -1,0 +1,48 @@
+// TORCH_LIBRARY registration of every vescale_b200 native op (loaded with torch.ops.load_library).
+#include <ATen/ATen.h>
+#include <torch/library.h>
+
+#include <tuple>
+
+// elementwise.cu
+std::tuple<at::Tensor, at::Tensor> rms_norm_fwd(const at::Tensor& x, const at::Tensor& w, double eps);
+std::tuple<at::Tensor, at::Tensor, at::Tensor> add_rms_norm_fwd(const at::Tensor& a, const at::Tensor& b, const at::Tensor& w, double eps);
+std::tuple<at::Tensor, at::Tensor> rms_norm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& rstd);
+std::tuple<at::Tensor, at::Tensor> add_rms_norm_bwd(const at::Tensor& dy, const at::Tensor& dh, const at::Tensor& h, const at::Tensor& w, const at::Tensor& rstd);
+at::Tensor swiglu_fwd(const at::Tensor& gu);
+at::Tensor swiglu_bwd(const at::Tensor& dy, const at::Tensor& gu);
+void rope_qk_(at::Tensor qkv, const at::Tensor& cos, const at::Tensor& sin, int64_t S, int64_t n_q, int64_t n_kv, int64_t D, double sign);
+at::Tensor cross_entropy_fwd_bwd_(at::Tensor logits, const at::Tensor& target, const at::Tensor& n_valid, int64_t ignore_index);
+void sumsq_accumulate(const at::Tensor& g, at::Tensor out, double scale);
+void fused_adamw_(at::Tensor master, at::Tensor m, at::Tensor v, const at::Tensor& g, at::Tensor p_out, const at::Tensor& wd_table,
+                  const at::Tensor& coef, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, double gscale);
+// gemm_sm100.cu
+void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate);
+
+TORCH_LIBRARY(vescale_b200, m) {
+  m.def("rms_norm_fwd(Tensor x, Tensor w, float eps) -> (Tensor, Tensor)");
+  m.def("add_rms_norm_fwd(Tensor a, Tensor b, Tensor w, float eps) -> (Tensor, Tensor, Tensor)");
+  m.def("rms_norm_bwd(Tensor dy, Tensor x, Tensor w, Tensor rstd) -> (Tensor, Tensor)");
+  m.def("add_rms_norm_bwd(Tensor dy, Tensor dh, Tensor h, Tensor w, Tensor rstd) -> (Tensor, Tensor)");
+  m.def("swiglu_fwd(Tensor gu) -> Tensor");
+  m.def("swiglu_bwd(Tensor dy, Tensor gu) -> Tensor");
+  m.def("rope_qk_(Tensor(a!) qkv, Tensor cos, Tensor sin, int S, int n_q, int n_kv, int D, float sign) -> ()");
+  m.def("cross_entropy_fwd_bwd_(Tensor(a!) logits, Tensor target, Tensor n_valid, int ignore_index) -> Tensor");
+  m.def("sumsq_accumulate(Tensor g, Tensor(a!) out, float scale) -> ()");
+  m.def("fused_adamw_(Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor(d!) p_out, Tensor wd_table, Tensor coef, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) -> ()");
+  m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate) -> ()");
+}
+
+TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
+  m.impl("rms_norm_fwd", &rms_norm_fwd);
+  m.impl("add_rms_norm_fwd", &add_rms_norm_fwd);
+  m.impl("rms_norm_bwd", &rms_norm_bwd);
+  m.impl("add_rms_norm_bwd", &add_rms_norm_bwd);
+  m.impl("swiglu_fwd", &swiglu_fwd);
+  m.impl("swiglu_bwd", &swiglu_bwd);
+  m.impl("rope_qk_", &rope_qk_);
+  m.impl("cross_entropy_fwd_bwd_", &cross_entropy_fwd_bwd_);
+  m.impl("sumsq_accumulate", &sumsq_accumulate);
+  m.impl("fused_adamw_", &fused_adamw_);
+  m.impl("gemm_nt", &gemm_nt);
+}

@@ -1,0 +1,554 @@
+// Bandwidth-bound fused kernels for the transformer block and the optimizer (sm_100a).
+// Every kernel moves data with 16-byte vector accesses, keeps a row in registers between the reduction and
+// the normalisation pass (one HBM read + one write per tensor), and is sized so that the grid is a multiple
+// of the 148 SMs or row-parallel with >= 2 waves.
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+
+#include "common.cuh"
+
+using namespace vb;
+
+namespace {
+
+constexpr int kMaxVecPerThread = 2;  // NT threads * 8 elements * 2 vectors >= H ; NT in {128,256,512,1024} -> H <= 16384
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
+
+// =================================================================================================
+// RMSNorm forward (optionally fused with the residual add): one CTA per row, row kept in registers.
+//   ADD:  h = a + b (written), y = h * rstd * w        else: y = a * rstd * w
+// =================================================================================================
+template <bool ADD, int kNormThreads>
+__global__ void __launch_bounds__(kNormThreads) rms_norm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                                    const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ h_out,
+                                                                    __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int rows,
+                                                                    int H, float eps) {
+  __shared__ float red[33];
+  const int nvec = H / 8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const __nv_bfloat16* ar = a + (size_t)row * H;
+    float x[kMaxVecPerThread][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < kMaxVecPerThread; ++it) {
+      const int v = threadIdx.x + it * kNormThreads;
+      if (v < nvec) {
+        unpack8(ld8(ar + v * 8), x[it]);
+        if (ADD) {
+          float t[8];
+          unpack8(ld8(b + (size_t)row * H + v * 8), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[it][i] += t[i];
+          bf16x8 hv = pack8(x[it]);
+          st8(h_out + (size_t)row * H + v * 8, hv);
+          unpack8(hv, x[it]);  // normalise the rounded residual so fwd/bwd see the same h
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += x[it][i] * x[it][i];
+      }
+    }
+    ss = block_sum<kNormThreads>(ss, red);
+    const float rstd = rsqrtf(ss / (float)H + eps);
+    if (threadIdx.x == 0) rstd_out[row] = rstd;
+#pragma unroll
+    for (int it = 0; it < kMaxVecPerThread; ++it) {
+      const int v = threadIdx.x + it * kNormThreads;
+      if (v < nvec) {
+        float wv[8], o[8];
+        unpack8(ld8(w + v * 8), wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = x[it][i] * rstd * wv[i];
+        st8(y + (size_t)row * H + v * 8, pack8(o));
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// RMSNorm backward.  Persistent grid over rows; each CTA accumulates its dw partial in registers and
+// writes one [H] fp32 row of `dw_part`; a second tiny kernel reduces the partials.
+//   dx = rstd * (g - xhat * mean(g * xhat)),  g = dy * w, xhat = x * rstd;  (+ dh if ADD)
+// =================================================================================================
+template <bool ADD, int kNormThreads>
+__global__ void __launch_bounds__(kNormThreads) rms_norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dh,
+                                                                    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                                    const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
+                                                                    float* __restrict__ dw_part, int rows, int H) {
+  __shared__ float red[33];
+  const int nvec = H / 8;
+  float dwacc[kMaxVecPerThread][8];
+  float wv[kMaxVecPerThread][8];
+#pragma unroll
+  for (int it = 0; it < kMaxVecPerThread; ++it) {
+    const int v = threadIdx.x + it * kNormThreads;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dwacc[it][i] = 0.f;
+    if (v < nvec) unpack8(ld8(w + v * 8), wv[it]);
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float r = rstd[row];
+    float g[kMaxVecPerThread][8], xh[kMaxVecPerThread][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int it = 0; it < kMaxVecPerThread; ++it) {
+      const int v = threadIdx.x + it * kNormThreads;
+      if (v < nvec) {
+        float d[8];
+        unpack8(ld8(dy + (size_t)row * H + v * 8), d);
+        unpack8(ld8(x + (size_t)row * H + v * 8), xh[it]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[it][i] *= r;
+          dwacc[it][i] += d[i] * xh[it][i];
+          g[it][i] = d[i] * wv[it][i];
+          dot += g[it][i] * xh[it][i];
+        }
+      }
+    }
+    dot = block_sum<kNormThreads>(dot, red) / (float)H;
+#pragma unroll
+    for (int it = 0; it < kMaxVecPerThread; ++it) {
+      const int v = threadIdx.x + it * kNormThreads;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = r * (g[it][i] - xh[it][i] * dot);
+        if (ADD) {
+          float t[8];
+          unpack8(ld8(dh + (size_t)row * H + v * 8), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += t[i];
+        }
+        st8(dx + (size_t)row * H + v * 8, pack8(o));
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kMaxVecPerThread; ++it) {
+    const int v = threadIdx.x + it * kNormThreads;
+    if (v < nvec) {
+      float4* p = reinterpret_cast<float4*>(dw_part + (size_t)blockIdx.x * H + v * 8);
+      p[0] = make_float4(dwacc[it][0], dwacc[it][1], dwacc[it][2], dwacc[it][3]);
+      p[1] = make_float4(dwacc[it][4], dwacc[it][5], dwacc[it][6], dwacc[it][7]);
+    }
+  }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int H) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * H + c];
+  out[c] = s;
+}
+
+// =================================================================================================
+// SwiGLU on packed gate|up rows: y[t, j] = silu(g[t, j]) * u[t, j],  in: [T, 2F], out: [T, F]
+// =================================================================================================
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ y, size_t T, int F) {
+  const size_t nvec = T * (size_t)(F / 8);
+  const int fv = F / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / fv;
+    const int j = (int)(i % fv) * 8;
+    float g[8], u[8], o[8];
+    unpack8(ld8(gu + t * 2 * F + j), g);
+    unpack8(ld8(gu + t * 2 * F + F + j), u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = g[k] / (1.f + __expf(-g[k])) * u[k];
+    st8(y + t * F + j, pack8(o));
+  }
+}
+
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ gu,
+                                                         __nv_bfloat16* __restrict__ dgu, size_t T, int F) {
+  const size_t nvec = T * (size_t)(F / 8);
+  const int fv = F / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / fv;
+    const int j = (int)(i % fv) * 8;
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8(ld8(gu + t * 2 * F + j), g);
+    unpack8(ld8(gu + t * 2 * F + F + j), u);
+    unpack8(ld8(dy + t * F + j), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float s = 1.f / (1.f + __expf(-g[k]));
+      dg[k] = d[k] * u[k] * s * (1.f + g[k] * (1.f - s));
+      du[k] = d[k] * g[k] * s;
+    }
+    st8(dgu + t * 2 * F + j, pack8(dg));
+    st8(dgu + t * 2 * F + F + j, pack8(du));
+  }
+}
+
+// =================================================================================================
+// RoPE (rotate-half) in place on the q and k heads of a packed qkv activation [T, (nq+2nk)*D].
+// cos/sin: [S, D/2] fp32, position = t % S.  sign=-1 is the backward rotation.
+// =================================================================================================
+__global__ void __launch_bounds__(256) rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cs, const float* __restrict__ sn,
+                                                      size_t T, int S, int nheads, int D, int row_stride, float sign) {
+  const int hv = D / 16;  // 8-element vectors per half head
+  const size_t total = T * (size_t)nheads * hv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % hv);
+    const size_t th = i / hv;
+    const int h = (int)(th % nheads);
+    const size_t t = th / nheads;
+    const int pos = (int)(t % S);
+    __nv_bfloat16* base = qkv + t * row_stride + (size_t)h * D + v * 8;
+    float x1[8], x2[8], o1[8], o2[8];
+    unpack8(ld8(base), x1);
+    unpack8(ld8(base + D / 2), x2);
+    const float4* c4 = reinterpret_cast<const float4*>(cs + (size_t)pos * (D / 2) + v * 8);
+    const float4* s4 = reinterpret_cast<const float4*>(sn + (size_t)pos * (D / 2) + v * 8);
+    float c[8], s[8];
+    *reinterpret_cast<float4*>(c) = c4[0];
+    *reinterpret_cast<float4*>(c + 4) = c4[1];
+    *reinterpret_cast<float4*>(s) = s4[0];
+    *reinterpret_cast<float4*>(s + 4) = s4[1];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sk = s[k] * sign;
+      o1[k] = x1[k] * c[k] - x2[k] * sk;
+      o2[k] = x2[k] * c[k] + x1[k] * sk;
+    }
+    st8(base, pack8(o1));
+    st8(base + D / 2, pack8(o2));
+  }
+}
+
+// =================================================================================================
+// Cross-entropy forward + backward in place.  One CTA per row of logits [T, V] (bf16):
+//   pass 1: online max / sum-exp (row streams through L2, 256 KB per row stays L2-resident for pass 2)
+//   pass 2: logits <- (softmax - onehot) / n_valid ;  loss[row] = lse - logit[target]
+// =================================================================================================
+constexpr int kCEThreads = 1024;
+__global__ void __launch_bounds__(kCEThreads) cross_entropy_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
+                                                                   const float* __restrict__ n_valid, float* __restrict__ loss, int V,
+                                                                   int64_t ignore_index) {
+  __shared__ float red[33];
+  const size_t row = blockIdx.x;
+  __nv_bfloat16* x = logits + row * (size_t)V;
+  const int64_t tgt = target[row];
+  const int nvec = V / 8;
+  float m = -INFINITY, s = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += kCEThreads) {
+    float f[8];
+    unpack8(ld8(x + v * 8), f);
+    float lm = f[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) lm = fmaxf(lm, f[k]);
+    const float nm = fmaxf(m, lm);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += __expf(f[k] - nm);
+    s = s * __expf(m - nm) + acc;
+    m = nm;
+  }
+  for (int c = nvec * 8 + threadIdx.x; c < V; c += kCEThreads) {  // tail (V % 8)
+    const float f = __bfloat162float(x[c]);
+    const float nm = fmaxf(m, f);
+    s = s * __expf(m - nm) + __expf(f - nm);
+    m = nm;
+  }
+  const float gm = block_max<kCEThreads>(m, red);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+  const float gs = block_sum<kCEThreads>(s, red);
+  const bool valid = tgt != ignore_index;
+  const float inv = valid ? 1.f / (gs * n_valid[0]) : 0.f;
+  const float sub = valid ? 1.f / n_valid[0] : 0.f;
+  if (threadIdx.x == 0) loss[row] = valid ? (__logf(gs) + gm - __bfloat162float(x[tgt])) : 0.f;
+  __syncthreads();  // the target logit is read before anyone overwrites it
+  for (int v = threadIdx.x; v < nvec; v += kCEThreads) {
+    float f[8];
+    unpack8(ld8(x + v * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float g = __expf(f[k] - gm) * inv;
+      if ((int64_t)(v * 8 + k) == tgt) g -= sub;
+      f[k] = g;
+    }
+    st8(x + v * 8, pack8(f));
+  }
+  for (int c = nvec * 8 + threadIdx.x; c < V; c += kCEThreads) {
+    float g = __expf(__bfloat162float(x[c]) - gm) * inv;
+    if ((int64_t)c == tgt) g -= sub;
+    x[c] = __float2bfloat16(g);
+  }
+}
+
+// =================================================================================================
+// sum of squares of (scale * g) accumulated into a device scalar (global grad-norm without host sync)
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(512) sumsq_kernel(const T* __restrict__ g, float* __restrict__ out, size_t n, float scale) {
+  __shared__ float red[33];
+  float acc = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if constexpr (sizeof(T) == 4) {
+    const size_t n4 = n / 4;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = g4[i];
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) acc += (float)g[i] * (float)g[i];
+  } else {
+    const size_t n8 = n / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += stride) {
+      float f[8];
+      unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(g) + i * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += f[k] * f[k];
+    }
+    for (size_t i = n8 * 8 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[i]);
+      acc += f * f;
+    }
+  }
+  acc = block_sum<512>(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc * scale * scale);
+}
+
+// =================================================================================================
+// Fused AdamW over a flat shard: grad (fp32|bf16) -> clip/scale -> m, v, master (fp32) -> bf16 param shard.
+// Weight decay applies inside the segments of `wd_table` ([n,3] int64: lo, hi, flag).
+// =================================================================================================
+template <typename GT>
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, float* __restrict__ m, float* __restrict__ v,
+                                                    const GT* __restrict__ g, __nv_bfloat16* __restrict__ p_out,
+                                                    const int64_t* __restrict__ wd_table, int nseg, const float* __restrict__ coef, size_t n,
+                                                    float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
+  __shared__ int64_t seg[64 * 3];
+  for (int i = threadIdx.x; i < nseg * 3 && i < 64 * 3; i += blockDim.x) seg[i] = wd_table[i];
+  __syncthreads();
+  const float gs = gscale * coef[0];
+  const float inv_bc1 = 1.f / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    float decay = 0.f;
+    for (int s = 0; s < nseg; ++s)
+      if ((int64_t)e >= seg[3 * s] && (int64_t)e < seg[3 * s + 1]) decay = seg[3 * s + 2] ? wd : 0.f;
+    float4 pm = reinterpret_cast<float4*>(master)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float gg[4];
+    if constexpr (sizeof(GT) == 4) {
+      const float4 t = reinterpret_cast<const float4*>(g)[i];
+      gg[0] = t.x, gg[1] = t.y, gg[2] = t.z, gg[3] = t.w;
+    } else {
+      const uint2 t = reinterpret_cast<const uint2*>(g)[i];
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+      gg[0] = a.x, gg[1] = a.y, gg[2] = b.x, gg[3] = b.y;
+    }
+    float* pp = reinterpret_cast<float*>(&pm);
+    float* pmm = reinterpret_cast<float*>(&mm);
+    float* pvv = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gg[k] * gs;
+      pmm[k] = b1 * pmm[k] + (1.f - b1) * gk;
+      pvv[k] = b2 * pvv[k] + (1.f - b2) * gk * gk;
+      const float denom = sqrtf(pvv[k]) * inv_sqrt_bc2 + eps;
+      pp[k] = pp[k] * (1.f - lr * decay) - lr * (pmm[k] * inv_bc1) / denom;
+    }
+    reinterpret_cast<float4*>(master)[i] = pm;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    __nv_bfloat162 o0 = __floats2bfloat162_rn(pp[0], pp[1]), o1 = __floats2bfloat162_rn(pp[2], pp[3]);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&o0);
+    o.y = *reinterpret_cast<uint32_t*>(&o1);
+    reinterpret_cast<uint2*>(p_out)[i] = o;
+  }
+}
+
+int grid_for(size_t work_items, int threads, int max_waves = 8) {
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)sms * max_waves;
+  return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+}  // namespace
+
+#define VB_NORM_DISPATCH(H)        \
+  do {                             \
+    if ((H) <= 2048) {             \
+      VB_LAUNCH(128);              \
+    } else if ((H) <= 4096) {      \
+      VB_LAUNCH(256);              \
+    } else if ((H) <= 8192) {      \
+      VB_LAUNCH(512);              \
+    } else {                       \
+      VB_LAUNCH(1024);             \
+    }                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------- host API
+std::tuple<at::Tensor, at::Tensor> rms_norm_fwd(const at::Tensor& x, const at::Tensor& w, double eps) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous());
+  const int rows = x.size(0), H = x.size(1);
+  TORCH_CHECK(H % 8 == 0 && H <= 16384, "rms_norm: unsupported hidden size ", H);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({rows}, x.options().dtype(at::kFloat));
+  if (rows == 0) return {y, rstd};
+#define VB_LAUNCH(NT)                                                                                                             \
+  rms_norm_fwd_kernel<false, NT><<<rows, NT, 0, cur_stream()>>>((const __nv_bfloat16*)x.data_ptr(), nullptr,                      \
+                                                               (const __nv_bfloat16*)w.data_ptr(), nullptr,                      \
+                                                               (__nv_bfloat16*)y.data_ptr(), rstd.data_ptr<float>(), rows, H, (float)eps)
+  VB_NORM_DISPATCH(H);
+#undef VB_LAUNCH
+  return {y, rstd};
+}
+
+std::tuple<at::Tensor, at::Tensor, at::Tensor> add_rms_norm_fwd(const at::Tensor& a, const at::Tensor& b, const at::Tensor& w, double eps) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.is_contiguous() && b.is_contiguous());
+  const int rows = a.size(0), H = a.size(1);
+  TORCH_CHECK(H % 8 == 0 && H <= 16384, "add_rms_norm: unsupported hidden size ", H);
+  c10::cuda::CUDAGuard guard(a.device());
+  auto h = at::empty_like(a);
+  auto y = at::empty_like(a);
+  auto rstd = at::empty({rows}, a.options().dtype(at::kFloat));
+  if (rows == 0) return {h, y, rstd};
+#define VB_LAUNCH(NT)                                                                                                             \
+  rms_norm_fwd_kernel<true, NT><<<rows, NT, 0, cur_stream()>>>((const __nv_bfloat16*)a.data_ptr(), (const __nv_bfloat16*)b.data_ptr(), \
+                                                              (const __nv_bfloat16*)w.data_ptr(), (__nv_bfloat16*)h.data_ptr(),    \
+                                                              (__nv_bfloat16*)y.data_ptr(), rstd.data_ptr<float>(), rows, H, (float)eps)
+  VB_NORM_DISPATCH(H);
+#undef VB_LAUNCH
+  return {h, y, rstd};
+}
+
+static std::tuple<at::Tensor, at::Tensor> rms_bwd_impl(const at::Tensor& dy, const at::Tensor* dh, const at::Tensor& x, const at::Tensor& w,
+                                                       const at::Tensor& rstd) {
+  TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && dy.is_contiguous() && x.is_contiguous());
+  const int rows = x.size(0), H = x.size(1);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dx = at::empty_like(x);
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int nblk = std::max(1, std::min(rows, sms * 4));
+  auto part = at::empty({nblk, H}, x.options().dtype(at::kFloat));
+  auto dw = at::empty({H}, x.options().dtype(at::kFloat));
+  TORCH_CHECK(H % 8 == 0 && H <= 16384, "rms_norm_bwd: unsupported hidden size ", H);
+  if (dh) {
+#define VB_LAUNCH(NT)                                                                                                                   \
+  rms_norm_bwd_kernel<true, NT><<<nblk, NT, 0, cur_stream()>>>((const __nv_bfloat16*)dy.data_ptr(), (const __nv_bfloat16*)dh->data_ptr(), \
+                                                              (const __nv_bfloat16*)x.data_ptr(), (const __nv_bfloat16*)w.data_ptr(),   \
+                                                              rstd.data_ptr<float>(), (__nv_bfloat16*)dx.data_ptr(), part.data_ptr<float>(), rows, H)
+    VB_NORM_DISPATCH(H);
+#undef VB_LAUNCH
+  } else {
+#define VB_LAUNCH(NT)                                                                                                                   \
+  rms_norm_bwd_kernel<false, NT><<<nblk, NT, 0, cur_stream()>>>((const __nv_bfloat16*)dy.data_ptr(), nullptr,                            \
+                                                               (const __nv_bfloat16*)x.data_ptr(), (const __nv_bfloat16*)w.data_ptr(),  \
+                                                               rstd.data_ptr<float>(), (__nv_bfloat16*)dx.data_ptr(), part.data_ptr<float>(), rows, H)
+    VB_NORM_DISPATCH(H);
+#undef VB_LAUNCH
+  }
+  colsum_kernel<<<(H + 255) / 256, 256, 0, cur_stream()>>>(part.data_ptr<float>(), dw.data_ptr<float>(), nblk, H);
+  return {dx, dw};
+}
+
+std::tuple<at::Tensor, at::Tensor> rms_norm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& rstd) {
+  return rms_bwd_impl(dy, nullptr, x, w, rstd);
+}
+std::tuple<at::Tensor, at::Tensor> add_rms_norm_bwd(const at::Tensor& dy, const at::Tensor& dh, const at::Tensor& h, const at::Tensor& w,
+                                                    const at::Tensor& rstd) {
+  TORCH_CHECK(dh.is_contiguous());
+  return rms_bwd_impl(dy, &dh, h, w, rstd);
+}
+
+at::Tensor swiglu_fwd(const at::Tensor& gu) {
+  TORCH_CHECK(gu.is_cuda() && gu.scalar_type() == at::kBFloat16 && gu.dim() == 2 && gu.is_contiguous() && gu.size(1) % 16 == 0);
+  c10::cuda::CUDAGuard guard(gu.device());
+  const size_t T = gu.size(0);
+  const int F = gu.size(1) / 2;
+  auto y = at::empty({(int64_t)T, F}, gu.options());
+  if (T == 0) return y;
+  swiglu_fwd_kernel<<<grid_for(T * (F / 8), 256, 16), 256, 0, cur_stream()>>>((const __nv_bfloat16*)gu.data_ptr(), (__nv_bfloat16*)y.data_ptr(), T, F);
+  return y;
+}
+
+at::Tensor swiglu_bwd(const at::Tensor& dy, const at::Tensor& gu) {
+  TORCH_CHECK(dy.is_cuda() && dy.is_contiguous() && gu.is_contiguous() && dy.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(gu.device());
+  const size_t T = gu.size(0);
+  const int F = gu.size(1) / 2;
+  auto dgu = at::empty_like(gu);
+  if (T == 0) return dgu;
+  swiglu_bwd_kernel<<<grid_for(T * (F / 8), 256, 16), 256, 0, cur_stream()>>>((const __nv_bfloat16*)dy.data_ptr(), (const __nv_bfloat16*)gu.data_ptr(),
+                                                                              (__nv_bfloat16*)dgu.data_ptr(), T, F);
+  return dgu;
+}
+
+void rope_qk_(at::Tensor qkv, const at::Tensor& cos, const at::Tensor& sin, int64_t S, int64_t n_q, int64_t n_kv, int64_t D, double sign) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == at::kBFloat16 && qkv.dim() == 2 && qkv.is_contiguous());
+  TORCH_CHECK(cos.scalar_type() == at::kFloat && cos.is_contiguous() && sin.is_contiguous() && cos.size(0) >= S && cos.size(1) == D / 2);
+  TORCH_CHECK(D % 16 == 0 && qkv.size(1) == (n_q + 2 * n_kv) * D);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  const size_t T = qkv.size(0);
+  if (T == 0) return;
+  const int nheads = n_q + n_kv;
+  rope_qk_kernel<<<grid_for(T * nheads * (D / 16), 256, 16), 256, 0, cur_stream()>>>((__nv_bfloat16*)qkv.data_ptr(), cos.data_ptr<float>(),
+                                                                                    sin.data_ptr<float>(), T, (int)S, nheads, (int)D,
+                                                                                    (int)qkv.size(1), (float)sign);
+}
+
+at::Tensor cross_entropy_fwd_bwd_(at::Tensor logits, const at::Tensor& target, const at::Tensor& n_valid, int64_t ignore_index) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kBFloat16 && logits.dim() == 2 && logits.is_contiguous());
+  TORCH_CHECK(target.scalar_type() == at::kLong && target.is_contiguous() && n_valid.scalar_type() == at::kFloat);
+  TORCH_CHECK(logits.size(1) % 8 == 0 || true);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int T = logits.size(0), V = logits.size(1);
+  TORCH_CHECK(((size_t)V * 2) % 16 == 0, "cross_entropy: row pitch must be 16-byte aligned");
+  auto loss = at::empty({T}, logits.options().dtype(at::kFloat));
+  if (T == 0) return loss;
+  cross_entropy_kernel<<<T, kCEThreads, 0, cur_stream()>>>((__nv_bfloat16*)logits.data_ptr(), target.data_ptr<int64_t>(), n_valid.data_ptr<float>(),
+                                                          loss.data_ptr<float>(), V, ignore_index);
+  return loss;
+}
+
+void sumsq_accumulate(const at::Tensor& g, at::Tensor out, double scale) {
+  TORCH_CHECK(g.is_cuda() && g.is_contiguous() && out.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(g.device());
+  const size_t n = g.numel();
+  if (n == 0) return;
+  const int grid = grid_for(n / 8 + 1, 512, 4);
+  if (g.scalar_type() == at::kFloat)
+    sumsq_kernel<float><<<grid, 512, 0, cur_stream()>>>(g.data_ptr<float>(), out.data_ptr<float>(), n, (float)scale);
+  else if (g.scalar_type() == at::kBFloat16)
+    sumsq_kernel<__nv_bfloat16><<<grid, 512, 0, cur_stream()>>>((const __nv_bfloat16*)g.data_ptr(), out.data_ptr<float>(), n, (float)scale);
+  else
+    TORCH_CHECK(false, "sumsq: unsupported dtype");
+}
+
+void fused_adamw_(at::Tensor master, at::Tensor m, at::Tensor v, const at::Tensor& g, at::Tensor p_out, const at::Tensor& wd_table,
+                  const at::Tensor& coef, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, double gscale) {
+  TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat);
+  TORCH_CHECK(p_out.scalar_type() == at::kBFloat16 && wd_table.scalar_type() == at::kLong && coef.scalar_type() == at::kFloat);
+  const size_t n = master.numel();
+  TORCH_CHECK(n % 4 == 0 && (size_t)g.numel() == n && (size_t)p_out.numel() == n && wd_table.size(0) <= 64);
+  c10::cuda::CUDAGuard guard(master.device());
+  if (n == 0) return;
+  const int grid = grid_for(n / 4, 256, 16);
+  const int nseg = wd_table.size(0);
+  if (g.scalar_type() == at::kFloat)
+    adamw_kernel<float><<<grid, 256, 0, cur_stream()>>>(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), g.data_ptr<float>(),
+                                                       (__nv_bfloat16*)p_out.data_ptr(), wd_table.data_ptr<int64_t>(), nseg, coef.data_ptr<float>(),
+                                                       n, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+  else if (g.scalar_type() == at::kBFloat16)
+    adamw_kernel<__nv_bfloat16><<<grid, 256, 0, cur_stream()>>>(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                                                               (const __nv_bfloat16*)g.data_ptr(), (__nv_bfloat16*)p_out.data_ptr(),
+                                                               wd_table.data_ptr<int64_t>(), nseg, coef.data_ptr<float>(), n, lr, b1, b2, eps, wd,
+                                                               bc1, bc2, gscale);
+  else
+    TORCH_CHECK(false, "fused_adamw_: unsupported grad dtype");
+}

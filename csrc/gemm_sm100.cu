@@ -1,0 +1,270 @@
+// bf16 GEMM for sm_100a on the 5th-gen tensor cores:  C[M,N] (+)= A[M,K] * B[N,K]^T   (both K-major)
+//
+//   * operands staged global -> shared by TMA (cp.async.bulk.tensor, 128B swizzle), 4-stage mbarrier ring
+//   * tcgen05.mma (UMMA 128x256x16, kind::f16) issued by ONE thread, fp32 accumulators in TMEM
+//   * two TMEM accumulator stages (2 x 256 columns = all 512): the epilogue of tile i overlaps the MMAs of tile i+1
+//   * persistent grid (one CTA per SM), M-fastest tile order so concurrently running CTAs share B (weight) tiles in L2
+//   * warp roles: w0 = TMA producer, w1 = MMA issuer, w2 = TMEM allocator, w4..7 = epilogue (tcgen05.ld -> bf16 -> global)
+//
+// The same mainloop is reused by the fused communication kernels (ag_gemm: B tiles fetched from peer GPUs'
+// symmetric memory through per-peer tensor maps; gemm_rs: epilogue reduces into the owner rank's buffer).
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+
+using namespace vb;
+
+namespace vb {
+
+// ------------------------------------------------------------------------------------------------- tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    auto err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    TORCH_CHECK(err == cudaSuccess && qres == cudaDriverEntryPointSuccess && p != nullptr, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 2-D row-major [rows, cols] tensor of `elem_bytes`-wide elements, box = [box_rows, box_cols], 128B swizzle.
+CUtensorMap make_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols,
+                         int elem_bytes, bool swizzle128) {
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {row_pitch_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult r = get_encode_fn()(&m, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code ", (int)r, " (ptr=", ptr, " rows=", rows, " cols=", cols, ")");
+  return m;
+}
+
+}  // namespace vb
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------- the kernel
+template <int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, __nv_bfloat16* __restrict__ C, int M, int N,
+               int K, int ldc, int accumulate) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (kABytes + kBBytes));
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + kBM - 1) / kBM, num_n = (N + kBN - 1) / kBN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpilogueThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * kBM, n0 = (tile / num_m) * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+          tma_load_2d(smem_a + s * kABytes, &tma_a, &full_bar[s], kb * kBK, m0);
+          tma_load_2d(smem_b + s * kBBytes, &tma_b, &full_bar[s], kb * kBK, n0);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer (single thread) =====================
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(smem_u32(smem_a + s * kABytes));
+          const uint64_t b_desc = make_sw128_desc(smem_u32(smem_b + s * kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom: start-address field is in 16 B units
+            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete
+        if (++as == 2) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> bf16 -> global =====================
+    const int ew = warp - 4;  // TMEM lane quadrant = warp_id % 4
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * kBM, n0 = (tile / num_m) * kBN;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 32, r);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = n0 + c * 32 + q * 8;
+            if (col < N) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
+              if (accumulate) {
+                float o[8];
+                unpack8(ld8(crow + c * 32 + q * 8), o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += o[i];
+              }
+              st8(crow + c * 32 + q * 8, pack8(f));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct MapKey {
+  const void* p;
+  int64_t r, c, pitch;
+  int br;
+  bool operator==(const MapKey& o) const { return p == o.p && r == o.r && c == o.c && pitch == o.pitch && br == o.br; }
+};
+struct MapHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.p) ^ (std::hash<int64_t>()(k.r) * 31) ^ (std::hash<int64_t>()(k.c) * 131) ^ (std::hash<int64_t>()(k.pitch) * 7) ^ k.br;
+  }
+};
+
+}  // namespace
+
+namespace vb {
+
+const CUtensorMap& cached_tmap_bf16(const void* p, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+  static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  MapKey k{p, rows, cols, pitch_elems, box_rows};
+  auto it = cache.find(k);
+  if (it == cache.end()) {
+    if (cache.size() > 4096) cache.clear();
+    it = cache.emplace(k, make_tmap_2d(p, rows, cols, pitch_elems * 2, box_rows, kBK, 2, true)).first;
+  }
+  return it->second;
+}
+
+int gemm_smem_bytes(int stages) { return stages * (kABytes + kBBytes) + (2 * stages + 4) * 8 + 16 + 1024; }
+
+}  // namespace vb
+
+void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && c.is_cuda(), "gemm_nt: CUDA tensors required");
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && c.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1 && c.stride(1) == 1);
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && c.size(0) == M && c.size(1) == N, "gemm_nt: shape mismatch");
+  TORCH_CHECK(K % kBK == 0 && N % 8 == 0, "gemm_nt: K must be a multiple of 64 and N of 8");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) % 16 == 0) && (reinterpret_cast<uintptr_t>(b.data_ptr()) % 16 == 0) &&
+              (reinterpret_cast<uintptr_t>(c.data_ptr()) % 16 == 0) && a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0 && c.stride(0) % 8 == 0);
+  if (M == 0 || N == 0) return;
+  c10::cuda::CUDAGuard guard(a.device());
+  constexpr int STAGES = 4;
+  const CUtensorMap& ta = cached_tmap_bf16(a.data_ptr(), M, K, a.stride(0), kBM);
+  const CUtensorMap& tb = cached_tmap_bf16(b.data_ptr(), N, K, b.stride(0), kBN);
+  const int smem = gemm_smem_bytes(STAGES);
+  static bool attr_set = false;
+  if (!attr_set) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+  const int grid = std::min(sms, tiles);
+  gemm_nt_kernel<STAGES><<<grid, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, tb, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K,
+                                                                                         (int)c.stride(0), accumulate ? 1 : 0);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
