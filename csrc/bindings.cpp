@@ -17,7 +17,18 @@ void sumsq_accumulate(const at::Tensor& g, at::Tensor out, double scale);
 void fused_adamw_(at::Tensor master, at::Tensor m, at::Tensor v, const at::Tensor& g, at::Tensor p_out, const at::Tensor& wd_table,
                   const at::Tensor& coef, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, double gscale);
 // gemm_sm100.cu
-void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate);
+void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate, int64_t variant);
+
+// symm_comm.cu
+void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch);
+void symm_wait(int64_t my_pad, int64_t world, int64_t slot, int64_t epoch);
+void symm_all_gather(std::vector<int64_t> shard_ptrs, at::Tensor full, int64_t shard_bytes, int64_t rank, std::vector<int64_t> pad_ptrs,
+                     int64_t slot, int64_t epoch, int64_t num_ctas);
+void symm_reduce_scatter(std::vector<int64_t> grad_ptrs, at::Tensor out, c10::optional<at::Tensor> sumsq, int64_t shard_elems, int64_t rank,
+                         double scale, std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, int64_t multicast_ptr, int64_t num_ctas);
+void symm_rs_adamw(std::vector<int64_t> grad_ptrs, at::Tensor master, at::Tensor m, at::Tensor v, at::Tensor p_out, const at::Tensor& wd_table,
+                   const at::Tensor& coef, c10::optional<at::Tensor> sumsq, int64_t rank, double scale, std::vector<int64_t> pad_ptrs, int64_t slot,
+                   int64_t epoch, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, int64_t num_ctas);
 
 TORCH_LIBRARY(vescale_b200, m) {
   m.def("rms_norm_fwd(Tensor x, Tensor w, float eps) -> (Tensor, Tensor)");
@@ -30,7 +41,12 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("cross_entropy_fwd_bwd_(Tensor(a!) logits, Tensor target, Tensor n_valid, int ignore_index) -> Tensor");
   m.def("sumsq_accumulate(Tensor g, Tensor(a!) out, float scale) -> ()");
   m.def("fused_adamw_(Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor(d!) p_out, Tensor wd_table, Tensor coef, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) -> ()");
-  m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate) -> ()");
+  m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate, int variant=0) -> ()");
+  m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
+  m.def("symm_wait(int my_pad, int world, int slot, int epoch) -> ()", &symm_wait);
+  m.def("symm_all_gather(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int num_ctas) -> ()");
+  m.def("symm_reduce_scatter(int[] grad_ptrs, Tensor(a!) out, Tensor(b!)? sumsq, int shard_elems, int rank, float scale, int[] pad_ptrs, int slot, int epoch, int multicast_ptr, int num_ctas) -> ()");
+  m.def("symm_rs_adamw(int[] grad_ptrs, Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor(d!) p_out, Tensor wd_table, Tensor coef, Tensor(e!)? sumsq, int rank, float scale, int[] pad_ptrs, int slot, int epoch, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int num_ctas) -> ()");
 }
 
 TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
@@ -45,4 +61,7 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("sumsq_accumulate", &sumsq_accumulate);
   m.impl("fused_adamw_", &fused_adamw_);
   m.impl("gemm_nt", &gemm_nt);
+  m.impl("symm_all_gather", &symm_all_gather);
+  m.impl("symm_reduce_scatter", &symm_reduce_scatter);
+  m.impl("symm_rs_adamw", &symm_rs_adamw);
 }

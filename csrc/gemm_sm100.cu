@@ -208,6 +208,185 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------- 2-CTA kernel
+// CTA pair (cluster 2x1, cta_group::2): one UMMA 256x256x16 spans both SMs.  Each CTA stages its own 128 rows
+// of A and HALF of the B tile (128 of 256 rows), so per-SM shared-memory traffic (TMA writes + tensor-core
+// reads) halves for B — the 1-CTA kernel is smem-bandwidth bound at ~60% tensor-pipe utilisation (ncu,
+// profiles/gemm_v1_ncu.md).  The leader CTA's single MMA thread issues for the pair; completion is multicast
+// to both CTAs' barriers; both CTAs' epilogues drain their own 128 TMEM lanes.
+constexpr int kB2Bytes = (kBN / 2) * kBK * 2;  // half B tile per CTA
+constexpr int kStage2 = kABytes + kB2Bytes;    // 32 KB
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, __nv_bfloat16* __restrict__ C, int M,
+                    int N, int K, int ldc, int accumulate, int group_m) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage2);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  constexpr int BM2 = 2 * kBM;  // 256 rows per pair tile
+  const int num_m = (M + BM2 - 1) / BM2, num_n = (N + kBN - 1) / kBN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / kBK;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  // grouped rasterisation: `group_m` M-tiles x all N-tiles form a group, M fastest inside -> A and B slabs stay in L2
+  auto tile_coord = [&](int t, int& m_blk, int& n_blk) {
+    const int per_group = group_m * num_n;
+    const int g = t / per_group;
+    const int first_m = g * group_m;
+    const int gsize = min(group_m, num_m - first_m);
+    const int r = t - g * per_group;
+    m_blk = first_m + r % gsize;
+    n_blk = r / gsize;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kEpilogueThreads);  // both CTAs' epilogue threads release the pair's accumulator
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_holder, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs; bytes land on the leader's full barrier) =====================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        tile_coord(tile, m_blk, n_blk);
+        const int m0 = m_blk * BM2 + (int)cta * kBM;
+        const int n0 = n_blk * kBN + (int)cta * (kBN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t full_leader = mapa(smem_u32(&full_bar[s]), 0);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * kStage2);
+          tma_load_2d_2sm(smem_a + s * kABytes, &tma_a, full_leader, kb * kBK, m0);
+          tma_load_2d_2sm(smem_b + s * kB2Bytes, &tma_b, full_leader, kb * kBK, n0);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer: one thread of the leader CTA drives both tensor cores =====================
+      constexpr uint32_t idesc = make_idesc_bf16(BM2, kBN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(smem_u32(smem_a + s * kABytes));
+          const uint64_t b_desc = make_sw128_desc(smem_u32(smem_b + s * kB2Bytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit_2cta_mc(&empty_bar[s], 0b11);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit_2cta_mc(&tfull_bar[as], 0b11);
+        if (++as == 2) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
+    const int ew = warp - 4;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      tile_coord(tile, m_blk, n_blk);
+      const int m0 = m_blk * BM2 + (int)cta * kBM, n0 = n_blk * kBN;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 32, r);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = n0 + c * 32 + q * 8;
+            if (col < N) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
+              if (accumulate) {
+                float o[8];
+                unpack8(ld8(crow + c * 32 + q * 8), o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += o[i];
+              }
+              st8(crow + c * 32 + q * 8, pack8(f));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa(smem_u32(&tempty_bar[as]), 0));
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
 struct MapKey {
   const void* p;
   int64_t r, c, pitch;
@@ -241,7 +420,7 @@ int gemm_smem_bytes(int stages) { return stages * (kABytes + kBBytes) + (2 * sta
 
 }  // namespace vb
 
-void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate) {
+void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate, int64_t variant_arg) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && c.is_cuda(), "gemm_nt: CUDA tensors required");
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kBFloat16);
   TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && c.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1 && c.stride(1) == 1);
@@ -252,6 +431,33 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
               (reinterpret_cast<uintptr_t>(c.data_ptr()) % 16 == 0) && a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0 && c.stride(0) % 8 == 0);
   if (M == 0 || N == 0) return;
   c10::cuda::CUDAGuard guard(a.device());
+  static const int env_variant = [] {
+    const char* e = getenv("VESCALE_B200_GEMM_VARIANT");
+    return e ? atoi(e) : 2;
+  }();
+  const int variant = variant_arg > 0 ? (int)variant_arg : env_variant;
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  if (variant == 2) {
+    constexpr int STAGES2 = 6;
+    const CUtensorMap& ta2 = cached_tmap_bf16(a.data_ptr(), M, K, a.stride(0), kBM);
+    const CUtensorMap& tb2 = cached_tmap_bf16(b.data_ptr(), N, K, b.stride(0), kBN / 2);
+    const int smem2 = STAGES2 * kStage2 + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr2 = true;
+    }
+    const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN);
+    const int pairs = std::max(1, std::min(sms / 2, tiles2));
+    static const int group_m = [] {
+      const char* e = getenv("VESCALE_B200_GEMM_GROUP_M");
+      return e ? atoi(e) : 8;
+    }();
+    gemm_nt_2cta_kernel<STAGES2><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+        ta2, tb2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return;
+  }
   constexpr int STAGES = 4;
   const CUtensorMap& ta = cached_tmap_bf16(a.data_ptr(), M, K, a.stride(0), kBM);
   const CUtensorMap& tb = cached_tmap_bf16(b.data_ptr(), N, K, b.stride(0), kBN);
@@ -261,7 +467,6 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
     C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
   const int grid = std::min(sms, tiles);
   gemm_nt_kernel<STAGES><<<grid, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, tb, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K,

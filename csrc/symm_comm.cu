@@ -1,0 +1,303 @@
+// Symmetric-memory collectives over NVLink 5 / NVSwitch for the FSDP unit buffers (sm_100a).
+//
+// Every rank maps every peer's arena (cuMem fabric/fd handles exchanged at bootstrap) so a kernel can load
+// from / store to any peer with ordinary global instructions; NVSwitch gives each GPU 900 GB/s per direction
+// to any mix of peers, so the kernels are written as *pull* operations that stripe requests over all peers
+// at once.  Cross-GPU ordering uses 32-bit epoch flags in a per-rank signal pad with st.release.sys /
+// ld.acquire.sys — no host synchronisation, no NCCL kernel, no separate cast/scale/norm passes.
+//
+//   signal_all / wait_all    : one-sided flag barrier pieces (epoch-valued, monotonic, never reset)
+//   all_gather_pull          : full[p*S .. (p+1)*S) <- peer p's shard, all peers in flight together
+//   reduce_scatter_fused     : my fp32 grad shard = scale * sum_p peer_p.full_grad[my slice]  (+ sum of squares
+//                              for the global grad norm) — C4/C7 of SURVEY §2F fused with cast/scale/norm
+//   rs_adamw_fused           : the same reduction feeding AdamW directly (no gradient ever written to HBM)
+//   multimem variants        : NVLS in-switch reduction (multimem.ld_reduce) when a multicast mapping exists
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "common.cuh"
+
+using namespace vb;
+
+namespace {
+
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+  const void* p[kMaxPeers];
+};
+struct PeerFlags {
+  uint32_t* p[kMaxPeers];
+};
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
+
+// ------------------------------------------------------------------------------------------------- signalling
+// Pad layout (uint32): slot-major, [slot][src_rank].  Rank r signals slot s by writing `epoch` into
+// peer_pad[s*W + r] on every peer; waiting means spinning on my own pad until all W entries reach `epoch`.
+__global__ void signal_all_kernel(PeerFlags pads, int world, int rank, int slot, uint32_t epoch) {
+  const int p = threadIdx.x;
+  if (p < world) {
+    __threadfence_system();
+    st_release_sys(pads.p[p] + slot * world + rank, epoch);
+  }
+}
+
+__global__ void wait_all_kernel(const uint32_t* my_pad, int world, int slot, uint32_t epoch) {
+  const int p = threadIdx.x;
+  if (p < world) {
+    const uint32_t* f = my_pad + slot * world + p;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    }
+  }
+}
+
+VB_DEVICE void block_signal_then_wait(const PeerFlags& pads, const uint32_t* my_pad, int world, int rank, int slot, uint32_t epoch, bool do_signal) {
+  // every CTA waits; only CTA 0 signals (after making this GPU's prior writes visible system-wide)
+  if (do_signal && blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(pads.p[threadIdx.x] + slot * world + rank, epoch);
+  }
+  if (threadIdx.x < world) {
+    const uint32_t* f = my_pad + slot * world + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------- all-gather (pull)
+// Work item = 16-byte vector v of peer p's shard.  Items are interleaved peer-fastest so each CTA keeps
+// requests to all peers in flight.
+template <int UNROLL>
+__global__ void __launch_bounds__(512) all_gather_pull_kernel(PeerPtrs shards, uint4* __restrict__ full, size_t vec_per_shard, int world, int rank,
+                                                              PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch, int use_flags) {
+  if (use_flags) block_signal_then_wait(pads, my_pad, world, rank, slot, epoch, true);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int pi = 0; pi < world; ++pi) {
+    const int p = (rank + pi) % world;  // own shard first, then neighbours: spreads simultaneous requests over distinct owners
+    const uint4* src = reinterpret_cast<const uint4*>(shards.p[p]);
+    uint4* dst = full + (size_t)p * vec_per_shard;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < vec_per_shard; i += UNROLL * stride) {
+      uint4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(src + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) dst[i + u * stride] = v[u];
+    }
+    for (; i < vec_per_shard; i += stride) dst[i] = ld_stream(src + i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- reduce-scatter fused
+VB_DEVICE void acc8(float* acc, const uint4& v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    acc[2 * k] += f.x;
+    acc[2 * k + 1] += f.y;
+  }
+}
+
+struct AdamArgs {
+  float* master;
+  float* m;
+  float* v;
+  __nv_bfloat16* p_out;
+  const int64_t* wd_table;
+  int nseg;
+  const float* coef;
+  float lr, b1, b2, eps, wd, bc1, bc2;
+};
+
+// MODE 0: write fp32 grad shard + sumsq.   MODE 1: feed AdamW directly (grad never stored).
+template <int MODE, int WORLD>
+__global__ void __launch_bounds__(512) reduce_scatter_fused_kernel(PeerPtrs grads, size_t shard_off_vec, float* __restrict__ out, float* __restrict__ sumsq,
+                                                                   size_t nvec, int rank, float scale, PeerFlags pads, const uint32_t* my_pad,
+                                                                   int slot, uint32_t epoch, AdamArgs ad) {
+  __shared__ float red[33];
+  __shared__ int64_t seg[64 * 3];
+  // wait until every peer has finished producing this bucket's gradients (and tell them mine are done)
+  block_signal_then_wait(pads, my_pad, WORLD, rank, slot, epoch, true);
+  if (MODE == 1) {
+    for (int i = threadIdx.x; i < ad.nseg * 3 && i < 64 * 3; i += blockDim.x) seg[i] = ad.wd_table[i];
+    __syncthreads();
+  }
+  float ss = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 v[WORLD];
+#pragma unroll
+    for (int pi = 0; pi < WORLD; ++pi) {
+      const int p = (rank + pi) % WORLD;
+      v[pi] = ld_stream(reinterpret_cast<const uint4*>(grads.p[p]) + shard_off_vec + i);
+    }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int pi = 0; pi < WORLD; ++pi) acc8(acc, v[pi]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k] *= scale;
+      ss += acc[k] * acc[k];
+    }
+    if (MODE == 0) {
+      float4* o = reinterpret_cast<float4*>(out + i * 8);
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      const size_t e = i * 8;
+      float decay = 0.f;
+      for (int s = 0; s < ad.nseg; ++s)
+        if ((int64_t)e >= seg[3 * s] && (int64_t)e < seg[3 * s + 1]) decay = seg[3 * s + 2] ? ad.wd : 0.f;
+      const float gs = ad.coef[0];
+      const float inv_bc1 = 1.f / ad.bc1, inv_sqrt_bc2 = rsqrtf(ad.bc2);
+      float pm[8], mm[8], vv[8];
+      *reinterpret_cast<float4*>(pm) = reinterpret_cast<float4*>(ad.master + e)[0];
+      *reinterpret_cast<float4*>(pm + 4) = reinterpret_cast<float4*>(ad.master + e)[1];
+      *reinterpret_cast<float4*>(mm) = reinterpret_cast<float4*>(ad.m + e)[0];
+      *reinterpret_cast<float4*>(mm + 4) = reinterpret_cast<float4*>(ad.m + e)[1];
+      *reinterpret_cast<float4*>(vv) = reinterpret_cast<float4*>(ad.v + e)[0];
+      *reinterpret_cast<float4*>(vv + 4) = reinterpret_cast<float4*>(ad.v + e)[1];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float g = acc[k] * gs;
+        mm[k] = ad.b1 * mm[k] + (1.f - ad.b1) * g;
+        vv[k] = ad.b2 * vv[k] + (1.f - ad.b2) * g * g;
+        pm[k] = pm[k] * (1.f - ad.lr * decay) - ad.lr * (mm[k] * inv_bc1) / (sqrtf(vv[k]) * inv_sqrt_bc2 + ad.eps);
+      }
+      reinterpret_cast<float4*>(ad.master + e)[0] = *reinterpret_cast<float4*>(pm);
+      reinterpret_cast<float4*>(ad.master + e)[1] = *reinterpret_cast<float4*>(pm + 4);
+      reinterpret_cast<float4*>(ad.m + e)[0] = *reinterpret_cast<float4*>(mm);
+      reinterpret_cast<float4*>(ad.m + e)[1] = *reinterpret_cast<float4*>(mm + 4);
+      reinterpret_cast<float4*>(ad.v + e)[0] = *reinterpret_cast<float4*>(vv);
+      reinterpret_cast<float4*>(ad.v + e)[1] = *reinterpret_cast<float4*>(vv + 4);
+      st8(ad.p_out + e, pack8(pm));
+    }
+  }
+  ss = block_sum<512>(ss, red);
+  if (threadIdx.x == 0 && sumsq != nullptr) atomicAdd(sumsq, ss);
+}
+
+// NVLS: the switch performs the W-way reduction; each GPU receives only its reduced slice.
+__global__ void __launch_bounds__(512) reduce_scatter_multimem_kernel(const void* mc_base, size_t shard_off_vec, float* __restrict__ out,
+                                                                      float* __restrict__ sumsq, size_t nvec, int world, int rank, float scale,
+                                                                      PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch) {
+  __shared__ float red[33];
+  block_signal_then_wait(pads, my_pad, world, rank, slot, epoch, true);
+  float ss = 0.f;
+  const uint4* src = reinterpret_cast<const uint4*>(mc_base) + shard_off_vec;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(src + i)
+                 : "memory");
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    acc8(acc, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k] *= scale;
+      ss += acc[k] * acc[k];
+    }
+    float4* o = reinterpret_cast<float4*>(out + i * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  ss = block_sum<512>(ss, red);
+  if (threadIdx.x == 0 && sumsq != nullptr) atomicAdd(sumsq, ss);
+}
+
+PeerPtrs to_ptrs(const std::vector<int64_t>& v) {
+  TORCH_CHECK((int)v.size() <= kMaxPeers, "at most ", kMaxPeers, " peers");
+  PeerPtrs p{};
+  for (size_t i = 0; i < v.size(); ++i) p.p[i] = reinterpret_cast<const void*>(v[i]);
+  return p;
+}
+PeerFlags to_flags(const std::vector<int64_t>& v) {
+  PeerFlags p{};
+  for (size_t i = 0; i < v.size(); ++i) p.p[i] = reinterpret_cast<uint32_t*>(v[i]);
+  return p;
+}
+
+int comm_grid(int sms, int frac_num, int frac_den) { return std::max(1, sms * frac_num / frac_den); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------- host API
+void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch) {
+  const int world = pad_ptrs.size();
+  signal_all_kernel<<<1, 32, 0, cur_stream()>>>(to_flags(pad_ptrs), world, (int)rank, (int)slot, (uint32_t)epoch);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void symm_wait(int64_t my_pad, int64_t world, int64_t slot, int64_t epoch) {
+  wait_all_kernel<<<1, 32, 0, cur_stream()>>>(reinterpret_cast<const uint32_t*>(my_pad), (int)world, (int)slot, (uint32_t)epoch);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void symm_all_gather(std::vector<int64_t> shard_ptrs, at::Tensor full, int64_t shard_bytes, int64_t rank, std::vector<int64_t> pad_ptrs,
+                     int64_t slot, int64_t epoch, int64_t num_ctas) {
+  TORCH_CHECK(full.is_cuda() && full.is_contiguous() && shard_bytes % 16 == 0);
+  const int world = shard_ptrs.size();
+  TORCH_CHECK((int64_t)full.numel() * full.element_size() == shard_bytes * world, "all_gather: full buffer size mismatch");
+  c10::cuda::CUDAGuard guard(full.device());
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int grid = num_ctas > 0 ? (int)num_ctas : comm_grid(sms, 1, 4);
+  const bool use_flags = !pad_ptrs.empty();
+  PeerFlags pf = use_flags ? to_flags(pad_ptrs) : PeerFlags{};
+  all_gather_pull_kernel<4><<<grid, 512, 0, cur_stream()>>>(to_ptrs(shard_ptrs), reinterpret_cast<uint4*>(full.data_ptr()), (size_t)shard_bytes / 16, world,
+                                                           (int)rank, pf, use_flags ? pf.p[rank] : nullptr, (int)slot, (uint32_t)epoch, use_flags ? 1 : 0);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+#define VB_RS_DISPATCH(MODE)                                                                                                                   \
+  switch (world) {                                                                                                                              \
+    case 2: reduce_scatter_fused_kernel<MODE, 2><<<grid, 512, 0, cur_stream()>>>(gp, off_vec, outp, ssp, nvec, (int)rank, (float)scale, pf, pf.p[rank], (int)slot, (uint32_t)epoch, ad); break; \
+    case 4: reduce_scatter_fused_kernel<MODE, 4><<<grid, 512, 0, cur_stream()>>>(gp, off_vec, outp, ssp, nvec, (int)rank, (float)scale, pf, pf.p[rank], (int)slot, (uint32_t)epoch, ad); break; \
+    case 8: reduce_scatter_fused_kernel<MODE, 8><<<grid, 512, 0, cur_stream()>>>(gp, off_vec, outp, ssp, nvec, (int)rank, (float)scale, pf, pf.p[rank], (int)slot, (uint32_t)epoch, ad); break; \
+    default: TORCH_CHECK(false, "reduce_scatter_fused: world size must be 2, 4 or 8, got ", world);                                            \
+  }
+
+void symm_reduce_scatter(std::vector<int64_t> grad_ptrs, at::Tensor out, c10::optional<at::Tensor> sumsq, int64_t shard_elems, int64_t rank,
+                         double scale, std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, int64_t multicast_ptr, int64_t num_ctas) {
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kFloat && out.numel() == shard_elems && shard_elems % 8 == 0);
+  const int world = grad_ptrs.size();
+  c10::cuda::CUDAGuard guard(out.device());
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int grid = num_ctas > 0 ? (int)num_ctas : comm_grid(sms, 1, 2);
+  const size_t nvec = shard_elems / 8, off_vec = (size_t)rank * nvec;
+  float* outp = out.data_ptr<float>();
+  float* ssp = sumsq.has_value() ? sumsq->data_ptr<float>() : nullptr;
+  PeerFlags pf = to_flags(pad_ptrs);
+  if (multicast_ptr != 0) {
+    reduce_scatter_multimem_kernel<<<grid, 512, 0, cur_stream()>>>(reinterpret_cast<const void*>(multicast_ptr), off_vec, outp, ssp, nvec, world, (int)rank,
+                                                                  (float)scale, pf, pf.p[rank], (int)slot, (uint32_t)epoch);
+  } else {
+    PeerPtrs gp = to_ptrs(grad_ptrs);
+    AdamArgs ad{};
+    VB_RS_DISPATCH(0)
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void symm_rs_adamw(std::vector<int64_t> grad_ptrs, at::Tensor master, at::Tensor m, at::Tensor v, at::Tensor p_out, const at::Tensor& wd_table,
+                   const at::Tensor& coef, c10::optional<at::Tensor> sumsq, int64_t rank, double scale, std::vector<int64_t> pad_ptrs, int64_t slot,
+                   int64_t epoch, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, int64_t num_ctas) {
+  TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && p_out.scalar_type() == at::kBFloat16 && master.numel() % 8 == 0);
+  const int world = grad_ptrs.size();
+  c10::cuda::CUDAGuard guard(master.device());
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int grid = num_ctas > 0 ? (int)num_ctas : comm_grid(sms, 1, 2);
+  const size_t nvec = master.numel() / 8, off_vec = (size_t)rank * nvec;
+  float* outp = nullptr;
+  float* ssp = sumsq.has_value() ? sumsq->data_ptr<float>() : nullptr;
+  PeerFlags pf = to_flags(pad_ptrs);
+  PeerPtrs gp = to_ptrs(grad_ptrs);
+  AdamArgs ad{master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), (__nv_bfloat16*)p_out.data_ptr(), wd_table.data_ptr<int64_t>(),
+              (int)wd_table.size(0), coef.data_ptr<float>(), (float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)bc1, (float)bc2};
+  VB_RS_DISPATCH(1)
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}

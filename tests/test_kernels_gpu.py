@@ -19,12 +19,14 @@ def _bf(*shape, scale=1.0, seed=0):
     return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (1000, 264, 192), (4096, 6144, 4096), (8192, 4096, 14336), (77, 128256 // 8 * 8, 256), (8192, 28672, 4096)])
-def test_gemm_nt(M, N, K):
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (1000, 264, 192), (4096, 6144, 4096), (8192, 4096, 14336), (77, 128256 // 8 * 8, 256), (8192, 28672, 4096), (300, 136, 64)])
+def test_gemm_nt(M, N, K, variant):
+    """variant 1 = 1-CTA UMMA 128x256, variant 2 = CTA-pair (cta_group::2) UMMA 256x256."""
     ops = _ops()
     a, b = _bf(M, K, seed=1), _bf(N, K, seed=2)
     c = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    ops.gemm_nt(a, b, c, False)
+    ops.gemm_nt(a, b, c, False, variant)
     ref = a.float() @ b.float().t()
     err = (c.float() - ref).abs().max().item()
     tol = 0.02 * math.sqrt(K) + 0.01 * ref.abs().max().item()
@@ -34,7 +36,7 @@ def test_gemm_nt(M, N, K):
     assert (c.float() - cb).abs().max().item() <= 2 * (cb.abs().max().item() / 128 + 1e-3)
     # accumulate
     c2 = c.clone()
-    ops.gemm_nt(a, b, c2, True)
+    ops.gemm_nt(a, b, c2, True, variant)
     assert (c2.float() - 2 * ref).abs().max().item() < 3 * tol
 
 
