@@ -1,0 +1,108 @@
+"""Symmetric-memory kernels on >= 2 GPUs of one box: collectives vs NCCL, FSDP(symm) vs FSDP(nccl)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+from common import run_distributed
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _collectives(rank, world):
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.comm.symm import SymmUnitComm
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    dev = torch.device("cuda", rank)
+    mesh = init_device_mesh("cuda", (world,))
+    comm = SymmUnitComm(mesh, 0, dev, chunk_bytes=256 << 20)
+
+    class U:  # minimal stand-in for FSDPUnit
+        sumsq = None
+
+    u = U()
+    S = 64 * 4096 * 5
+    shard = comm.alloc(S, torch.bfloat16)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    shard.copy_(torch.randn(S, device=dev, generator=g).bfloat16())
+    full = torch.empty(S * world, dtype=torch.bfloat16, device=dev)
+    ref = torch.empty_like(full)
+    dist.all_gather_into_tensor(ref, shard)
+    for it in range(3):
+        full.zero_()
+        comm.all_gather(shard, full, u)
+        torch.cuda.synchronize()
+        assert torch.equal(full, ref), f"all_gather mismatch at iter {it}"
+    # reduce-scatter: fp32 accumulate of bf16 peers, scaled, + sum of squares
+    fg = comm.alloc(S * world, torch.bfloat16)
+    for use_mm in (False, True):
+        comm.use_multimem = use_mm
+        for it in range(2):
+            fg.copy_(torch.randn(S * world, device=dev, generator=g).bfloat16())
+            torch.cuda.synchronize()
+            dist.barrier()
+            gathered = [torch.empty_like(fg) for _ in range(world)]
+            dist.all_gather(gathered, fg)
+            want = sum(t[rank * S : (rank + 1) * S].float() for t in gathered) * 0.5
+            out = torch.empty(S, dtype=torch.float32, device=dev)
+            comm.wait_buffer_free(fg)
+            comm.reduce_scatter(fg, out, 0.5, u)
+            torch.cuda.synchronize()
+            tol = dict(rtol=1e-5, atol=1e-5) if not use_mm or comm.arena.multicast_ptr(fg) == 0 else dict(rtol=2e-2, atol=2e-2)
+            torch.testing.assert_close(out, want, **tol)
+            torch.testing.assert_close(u.sumsq[0], out.pow(2).sum(), rtol=1e-3, atol=1e-3)
+            dist.barrier()
+    if rank == 0:
+        print(f"multicast available: {comm.arena.multicast_ptr(fg) != 0}", flush=True)
+
+
+def _fsdp_backends(rank, world):
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.models import LlamaConfig, LlamaModel
+    from vescale_b200.optim import FSDPAdamW
+    from vescale_b200.parallel.fsdp import fully_shard
+
+    dev = torch.device("cuda", rank)
+    cfg = LlamaConfig(vocab_size=2048, hidden_size=512, intermediate_size=1024, num_layers=3, num_heads=8, num_kv_heads=2, head_dim=64, max_seq_len=256)
+    results = {}
+    for backend, clip, fused in (("nccl", 1.0, False), ("symm", 1.0, False), ("symm", None, True), ("nccl", None, False)):
+        mesh = init_device_mesh("cuda", (world,))
+        model = LlamaModel(cfg, device=dev).reset_parameters(seed=3)
+        for blk in model.layers:
+            fully_shard(blk, mesh, comm_backend=backend, reshard_after_forward=(backend == "nccl"))
+        fully_shard(model.embed, mesh, comm_backend=backend)
+        fully_shard(model.head, mesh, comm_backend=backend)
+        fully_shard(model, mesh, comm_backend=backend)
+        opt = FSDPAdamW(model, lr=1e-3, max_grad_norm=clip, fused_reduce=fused)
+        losses = []
+        for s in range(4):
+            g = torch.Generator().manual_seed(100 * s + rank)
+            tok = torch.randint(0, cfg.vocab_size, (2, 257), generator=g).to(dev)
+            loss = model(tok[:, :-1], tok[:, 1:])
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            losses.append(loss.item())
+        params = torch.cat([p.full_tensor().reshape(-1).float() for p in model.parameters()])
+        results[(backend, clip, fused)] = (losses, params)
+        del model, opt
+        torch.cuda.synchronize()
+        dist.barrier()
+    for a, b in ((("nccl", 1.0, False), ("symm", 1.0, False)), (("nccl", None, False), ("symm", None, True))):
+        la, pa = results[a]
+        lb, pb = results[b]
+        assert all(abs(x - y) < 3e-2 for x, y in zip(la, lb)), (a, b, la, lb)
+        rel = (pa - pb).norm() / pa.norm()
+        assert rel < 2e-3, (a, b, rel.item())
+        assert la[-1] < la[0]
+
+
+def test_symm_collectives_match_nccl():
+    run_distributed(_collectives, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+def test_fsdp_symm_matches_nccl():
+    run_distributed(_fsdp_backends, min(torch.cuda.device_count(), 8), backend="nccl")

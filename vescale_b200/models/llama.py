@@ -112,11 +112,7 @@ class LlamaBlock(nn.Module):
         hq, hk, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
         h, qkv = O.functional.add_norm_linear(h, delta, self.attn_norm, self.wqkv, cfg.rms_eps)
         qkv = O.rope_qk_(qkv, cos, sin, hq, hk, d)
-        q = qkv[..., : hq * d].unflatten(-1, (hq, d)).transpose(1, 2)
-        k = qkv[..., hq * d : (hq + hk) * d].unflatten(-1, (hk, d)).transpose(1, 2)
-        v = qkv[..., (hq + hk) * d :].unflatten(-1, (hk, d)).transpose(1, 2)
-        o = O.attention(q, k, v, causal=True)
-        o = o.transpose(1, 2).reshape(B, S, hq * d)
+        o = O.packed_attention(qkv, hq, hk, d, causal=True)
         a = O.linear(o, self.wo)
         h, gu = O.functional.add_norm_linear(h, a, self.mlp_norm, self.w_gate_up, cfg.rms_eps)
         delta = O.functional.swiglu_linear(gu, self.w_down)

@@ -22,6 +22,7 @@ __all__ = [
     "swiglu",
     "rope_qk_",
     "attention",
+    "packed_attention",
     "cross_entropy",
     "set_gemm_backend",
 ]
@@ -357,6 +358,46 @@ def attention(q, k, v, *, causal: bool = True) -> torch.Tensor:
         with sdpa_kernel(_sdpa_priority(), set_priority=True):
             return F.scaled_dot_product_attention(q, k, v, is_causal=causal, enable_gqa=gqa)
     return F.scaled_dot_product_attention(q, k, v, is_causal=causal, enable_gqa=gqa)
+
+
+class _PackedAttention(torch.autograd.Function):
+    """Causal GQA attention straight from / to the packed qkv activation [B, S, (Hq+2Hk)*D].
+
+    Autograd over three slices of one tensor materialises three zero-filled full-size gradients and adds them
+    (9 elementwise launches and ~0.6 GB of traffic per layer at 8k tokens); here the backward assembles dqkv with
+    one concatenation."""
+
+    @staticmethod
+    def forward(ctx, qkv, n_q, n_kv, head_dim, causal):
+        B, S, _ = qkv.shape
+        ctx.cfg = (n_q, n_kv, head_dim, causal)
+        with torch.enable_grad():
+            src = qkv.detach().requires_grad_(True)
+            q = src[..., : n_q * head_dim].unflatten(-1, (n_q, head_dim)).transpose(1, 2)
+            k = src[..., n_q * head_dim : (n_q + n_kv) * head_dim].unflatten(-1, (n_kv, head_dim)).transpose(1, 2)
+            v = src[..., (n_q + n_kv) * head_dim :].unflatten(-1, (n_kv, head_dim)).transpose(1, 2)
+            q, k, v = q.detach().requires_grad_(True), k.detach().requires_grad_(True), v.detach().requires_grad_(True)
+            o = attention(q, k, v, causal=causal)
+        ctx.graph = (q, k, v, o)
+        return o.detach().transpose(1, 2).reshape(B, S, n_q * head_dim)
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o = ctx.graph
+        ctx.graph = None
+        n_q, n_kv, head_dim, _ = ctx.cfg
+        B, S = do.shape[0], do.shape[1]
+        do4 = do.view(B, S, n_q, head_dim).transpose(1, 2)
+        dq, dk, dv = torch.autograd.grad(o, (q, k, v), do4)
+        dqkv = torch.cat(
+            [dq.transpose(1, 2).reshape(B, S, -1), dk.transpose(1, 2).reshape(B, S, -1), dv.transpose(1, 2).reshape(B, S, -1)], dim=-1
+        )
+        return dqkv, None, None, None, None
+
+
+def packed_attention(qkv: torch.Tensor, n_q: int, n_kv: int, head_dim: int, causal: bool = True) -> torch.Tensor:
+    """qkv [B, S, (Hq+2Hk)*D] (RoPE already applied) -> attention output [B, S, Hq*D]."""
+    return _PackedAttention.apply(qkv, n_q, n_kv, head_dim, causal)
 
 
 # =============================================================================== cross entropy

@@ -36,6 +36,7 @@ class FSDPAdamW:
         max_grad_norm: Optional[float] = 1.0,
         no_decay: Optional[Callable[[str, Sequence[int]], bool]] = None,
         state_dtype: torch.dtype = torch.float32,
+        fused_reduce: bool = False,
     ):
         st = None
         for m in model.modules():
@@ -67,6 +68,26 @@ class FSDPAdamW:
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
         self.last_grad_norm: Optional[torch.Tensor] = None
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
+        # fully fused mode: the update happens inside the reduce-scatter kernel during backward.  It needs the
+        # clip coefficient before the global norm of *this* step exists, so it is only legal without clipping.
+        self.fused_reduce = bool(fused_reduce)
+        if self.fused_reduce:
+            if max_grad_norm is not None:
+                raise ValueError("fused_reduce=True folds AdamW into the reduce-scatter kernel and cannot apply a global-norm clip; pass max_grad_norm=None")
+            if st.comm is None or not getattr(st.comm, "symmetric", False):
+                raise ValueError("fused_reduce=True needs the symmetric-memory comm backend")
+            st.fused_optimizer = self
+
+    def fused_update(self, u: FSDPUnit, scale: float) -> None:
+        """Called from post-backward on the reduce-scatter stream (see FSDPState.post_backward)."""
+        step = self.step_count + 1
+        b1, b2 = self.betas
+        hp = dict(coef=self._coef, lr=float(self.param_groups[0]["lr"]), b1=float(b1), b2=float(b2), eps=float(self.eps), wd=float(self.weight_decay),
+                  bc1=float(1.0 - b1**step), bc2=float(1.0 - b2**step))
+        u.comm.reduce_scatter_adamw(u.full_grad, u, scale, hp)
+        u.grad_ready = False
+        u.bf16_fresh = True
+        u._fused_done = True
 
     # ------------------------------------------------------------------ grad norm (device-side)
     def _global_grad_norm(self) -> torch.Tensor:
@@ -93,6 +114,19 @@ class FSDPAdamW:
         st = self.state
         st.wait_grads()
         self.step_count += 1
+        if self.fused_reduce:
+            # every unit was already updated by its reduce-scatter kernel; only book-keeping is left
+            tot = self._norm_buf.zero_()
+            for u in self.units:
+                if u.sumsq is not None:
+                    tot += u.sumsq
+                u._fused_done = False
+            if self.units and self.units[0].world > 1:
+                dist.all_reduce(tot, group=self.units[0].group)
+            self.last_grad_norm = tot.sqrt()
+            st.invalidate_params()
+            st.iteration += 1
+            return self.last_grad_norm
         b1, b2 = self.betas
         lr = self.param_groups[0]["lr"]
         bc1 = 1.0 - b1**self.step_count

@@ -172,6 +172,8 @@ class FSDPState:
             u.attach_grad_buffer(fg, accumulate=False)
             return
         fg = self.pool.get(u.S * u.world, u.param_dtype, self.cur_stream(), lambda: u._alloc_full(u.param_dtype, symmetric=sym), symmetric=sym)
+        if sym:
+            self.comm.wait_buffer_free(fg)  # peers may still be pull-reducing the previous tenant of this buffer
         u.attach_grad_buffer(fg, accumulate=False)
 
     def post_backward(self, u: FSDPUnit) -> None:
@@ -190,7 +192,11 @@ class FSDPState:
             return
         self.rs_stream.wait_stream(self.cur_stream())
         with self.on(self.rs_stream):
-            u.reduce_scatter(scale)
+            fused = getattr(self, "fused_optimizer", None)
+            if fused is not None and self.comm is not None and getattr(self.comm, "symmetric", False):
+                fused.fused_update(u, scale)  # reduce-scatter ⊕ AdamW ⊕ bf16 cast in one kernel
+            else:
+                u.reduce_scatter(scale)
             evt = make_event(self.device)
             evt.record(self.rs_stream if self.cuda else None)
         u.rs_event = evt
