@@ -43,13 +43,20 @@ __global__ void signal_all_kernel(PeerFlags pads, int world, int rank, int slot,
   }
 }
 
-__global__ void wait_all_kernel(const uint32_t* my_pad, int world, int slot, uint32_t epoch) {
-  const int p = threadIdx.x;
-  if (p < world) {
-    const uint32_t* f = my_pad + slot * world + p;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+// Spin with a watchdog: a protocol bug must surface as a trapped kernel with a message, not as a hung box.
+VB_DEVICE void spin_until(const uint32_t* f, uint32_t epoch, int slot, int peer) {
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    if (clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
+      printf("[vescale_b200] signal timeout: slot=%d peer=%d want epoch %u have %u\n", slot, peer, epoch, ld_relaxed_sys(f));
+      __trap();
     }
   }
+}
+
+__global__ void wait_all_kernel(const uint32_t* my_pad, int world, int slot, uint32_t epoch) {
+  const int p = threadIdx.x;
+  if (p < world) spin_until(my_pad + slot * world + p, epoch, slot, p);
 }
 
 VB_DEVICE void block_signal_then_wait(const PeerFlags& pads, const uint32_t* my_pad, int world, int rank, int slot, uint32_t epoch, bool do_signal) {
@@ -58,11 +65,7 @@ VB_DEVICE void block_signal_then_wait(const PeerFlags& pads, const uint32_t* my_
     __threadfence_system();
     st_release_sys(pads.p[threadIdx.x] + slot * world + rank, epoch);
   }
-  if (threadIdx.x < world) {
-    const uint32_t* f = my_pad + slot * world + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    }
-  }
+  if (threadIdx.x < world) spin_until(my_pad + slot * world + threadIdx.x, epoch, slot, threadIdx.x);
   __syncthreads();
 }
 

@@ -78,6 +78,8 @@ def _fsdp_backends(rank, world):
         fully_shard(model, mesh, comm_backend=backend)
         opt = FSDPAdamW(model, lr=1e-3, max_grad_norm=clip, fused_reduce=fused)
         losses = []
+        if rank == 0:
+            print(f"[fsdp-backends] {backend} clip={clip} fused={fused}", flush=True)
         for s in range(4):
             g = torch.Generator().manual_seed(100 * s + rank)
             tok = torch.randint(0, cfg.vocab_size, (2, 257), generator=g).to(dev)
@@ -86,6 +88,8 @@ def _fsdp_backends(rank, world):
             opt.step()
             opt.zero_grad()
             losses.append(loss.item())
+            if rank == 0:
+                print(f"   step {s} loss {losses[-1]:.4f}", flush=True)
         params = torch.cat([p.full_tensor().reshape(-1).float() for p in model.parameters()])
         results[(backend, clip, fused)] = (losses, params)
         del model, opt

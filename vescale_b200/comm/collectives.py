@@ -122,11 +122,11 @@ def mesh_all_gather_uneven(tensor: torch.Tensor, sizes: Sequence[int], mesh, mes
     _note("all_gather", flat, group, uneven=True)
     if n == 1:
         return [flat.clone()]
-    if _backend(group) == "nccl":
-        outs = [flat.new_empty(int(s)) for s in sizes]
-        dist.all_gather(outs, flat, group=group)
-        return outs
+    # One even all_gather_into_tensor of max-size padded pieces on every backend: the list form of
+    # dist.all_gather degrades to per-rank broadcasts for uneven sizes (and zero-size entries are fragile).
     mx = max(int(s) for s in sizes)
+    if mx == 0:
+        return [flat.new_empty(0) for _ in sizes]
     padded = flat.new_zeros(mx)
     padded[: flat.numel()] = flat
     buf = flat.new_empty(n * mx)

@@ -46,7 +46,7 @@ class _BufferPool:
         key = (numel, dtype, symmetric)
         lst = self.free.get(key)
         if lst:
-            buf, evt = lst.pop()
+            buf, evt = lst.pop(0)  # FIFO: the buffer that has been idle longest (its collectives are most likely done)
             if evt is not None and stream is not None:
                 stream.wait_event(evt) if hasattr(stream, "wait_event") else None
             return buf
@@ -171,7 +171,12 @@ class FSDPState:
                 fg = u._persistent_grad = torch.empty(u.S, dtype=u.param_dtype, device=u.device)
             u.attach_grad_buffer(fg, accumulate=False)
             return
-        fg = self.pool.get(u.S * u.world, u.param_dtype, self.cur_stream(), lambda: u._alloc_full(u.param_dtype, symmetric=sym), symmetric=sym)
+        def _alloc():
+            if sym and getattr(self, "symm_pool_frozen", False):
+                raise RuntimeError("symmetric gradient pool exhausted after lazy_init (would need a rendezvous mid-step)")
+            return u._alloc_full(u.param_dtype, symmetric=sym)
+
+        fg = self.pool.get(u.S * u.world, u.param_dtype, self.cur_stream(), _alloc, symmetric=sym)
         if sym:
             self.comm.wait_buffer_free(fg)  # peers may still be pull-reducing the previous tenant of this buffer
         u.attach_grad_buffer(fg, accumulate=False)
@@ -226,6 +231,27 @@ class FSDPState:
     def set_requires_gradient_sync(self, flag: bool) -> None:
         self.requires_gradient_sync = flag
 
+    def lazy_init(self) -> None:
+        """Before the first forward: allocate every *symmetric* pool buffer now.  Symmetric allocation is a
+        rendezvous (host-blocking collective, may synchronise the device); doing it later — while another rank
+        already sits in a kernel that spins on this rank's signal — can deadlock.  ``grad_pool_depth`` gradient
+        buffers per distinct unit size are enough for reduce-scatter to overlap the next unit's backward."""
+        if getattr(self, "_lazy_done", False):
+            return
+        self._lazy_done = True
+        sym = self.comm is not None and getattr(self.comm, "symmetric", False)
+        if not sym:
+            return
+        depth = getattr(self, "grad_pool_depth", 3)
+        sizes = {}
+        for u in self.units:
+            if u.world > 1:
+                sizes.setdefault((u.S * u.world, u.param_dtype), []).append(u)
+        for (numel, dtype), us in sizes.items():
+            for _ in range(min(depth, len(us))):
+                self.pool.put(us[0]._alloc_full(dtype, symmetric=True), None, symmetric=True)
+        self.symm_pool_frozen = True
+
 
 class _PostBackward(torch.autograd.Function):
     """Identity on the unit's inputs; its backward runs after every gradient of the unit was produced."""
@@ -247,6 +273,7 @@ def _unit_index(state: FSDPState, u: FSDPUnit) -> int:
 
 def _pre_forward(state: FSDPState, u: FSDPUnit, module, args, kwargs):
     idx = u._index
+    state.lazy_init()
     u._saw_forward = True
     u._post_backward_done = False
     state.wait_all_gather(u)
