@@ -353,6 +353,7 @@ def fsdp_units(module: nn.Module) -> List[FSDPUnit]:
 
 
 _STATES: Dict[int, FSDPState] = {}
+_COMM_CACHE: Dict[Tuple[int, Optional[int]], Any] = {}
 
 
 def fully_shard(
@@ -494,4 +495,9 @@ def _make_comm(backend: str, mesh: DeviceMesh, md: int, dev: torch.device):
         return None
     from ...comm.symm import SymmUnitComm
 
-    return SymmUnitComm(mesh, md, dev)
+    # one arena per (process group, device): every unit of every model on this mesh dim shares it
+    key = (id(mesh.get_group(md)), dev.index)
+    comm = _COMM_CACHE.get(key)
+    if comm is None:
+        comm = _COMM_CACHE[key] = SymmUnitComm(mesh, md, dev)
+    return comm
