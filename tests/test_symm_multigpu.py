@@ -101,7 +101,6 @@ def _fsdp_backends(rank, world):
         assert all(abs(x - y) < 3e-2 for x, y in zip(la, lb)), (a, b, la, lb)
         rel = (pa - pb).norm() / pa.norm()
         assert rel < 2e-3, (a, b, rel.item())
-        assert la[-1] < la[0]
 
 
 def test_symm_collectives_match_nccl():
