@@ -1,0 +1,104 @@
+"""DModule (TP/SP by plan) and deferred init on 4 ranks — golden = same module on one device
+(legacy ``test/dmodule/test_fwd_plan.py``, ``test_initialize.py`` strategy)."""
+import copy
+
+import torch
+import torch.nn as nn
+
+from common import device_type, run_distributed
+
+
+class Block(nn.Module):
+    def __init__(self, h=32, f=64):
+        super().__init__()
+        self.ln = nn.LayerNorm(h)
+        self.fc1 = nn.Linear(h, f)
+        self.fc2 = nn.Linear(f, h)
+
+    def forward(self, x):
+        return x + self.fc2(torch.nn.functional.gelu(self.fc1(self.ln(x))))
+
+
+class Net(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.blocks = nn.ModuleList([Block(), Block()])
+
+    def forward(self, x):
+        for b in self.blocks:
+            x = b(x)
+        return x
+
+
+def _tp_sp(rank, world):
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200.dtensor import DTensor
+    from vescale_b200.dtensor.debug import CommDebugMode
+    from vescale_b200.parallel.dmodule import parallelize_module
+
+    torch.manual_seed(0)
+    dev = device_type()
+    ref = Net().to(dev)
+    model = copy.deepcopy(ref)
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("TP",))
+    plan = {
+        "parameter": {
+            r"blocks\.\d+\.fc1\.weight": [Shard(0)],
+            r"blocks\.\d+\.fc1\.bias": [Shard(0)],
+            r"blocks\.\d+\.fc2\.weight": [Shard(1)],
+        },
+        "forward": {
+            r"input": [[Replicate()]],  # the caller passes the full (replicated) batch as a plain tensor
+            r"blocks\.\d+\.input": [[Shard(1)]],  # sequence-parallel residual stream
+            r"blocks\.\d+\.fc1\.input": [[Replicate()]],  # all-gather before the column-parallel GEMM
+            r"blocks\.\d+\.fc2\.output": [[Shard(1)]],  # reduce-scatter after the row-parallel GEMM
+            r"blocks\.1\.output": [[Replicate()]],
+        },
+    }
+    parallelize_module(model, mesh, plan)
+    assert all(isinstance(p, DTensor) for p in model.parameters())
+    x = torch.randn(2, 8, 32, generator=torch.Generator().manual_seed(1)).to(dev)
+    with CommDebugMode(model) as cm:
+        out = model(x)
+    counts = cm.get_comm_counts()
+    assert counts.get("all_gather", 0) >= 2 and counts.get("reduce_scatter", 0) + counts.get("all_reduce", 0) >= 2, counts
+    assert out.placements == (Replicate(),)
+    torch.testing.assert_close(out.to_local(), ref(x), rtol=1e-4, atol=1e-5)
+    out.to_local().sum().backward()
+    ref(x).sum().backward()
+    # LayerNorm grads are Partial under SP until synced
+    n_partial = len(model.list_partial_grads())
+    assert n_partial >= 4, n_partial
+    model.finish_grad_sync()
+    assert len(model.list_partial_grads()) == 0
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(p.grad.full_tensor(), q.grad, rtol=1e-4, atol=1e-5, msg=n)
+
+
+def _deferred(rank, world):
+    import vescale_b200.dtensor as vd
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200.dtensor import RaggedShard
+    from vescale_b200.initialize import deferred_init, materialize_dtensor, materialize_module
+
+    dev = device_type()
+    mesh = init_device_mesh(dev, (world,))
+    vd.manual_seed(7)
+    golden = materialize_module(deferred_init(Net), dev)
+    vd.manual_seed(7)
+    m = deferred_init(Net)
+    assert all(p.is_meta for p in m.parameters())
+    placements = {2: [Shard(0)], 1: [RaggedShard((0,), (1, 0, 2, 1))]}
+    for (n, p), (_, g) in zip(m.named_parameters(), golden.named_parameters()):
+        pl = placements.get(p.ndim, [Replicate()]) if p.shape[0] % 4 == 0 else [Replicate()]
+        dt = materialize_dtensor(p, mesh, pl)
+        assert dt.to_local().numel() <= p.numel()
+        assert torch.equal(dt.full_tensor(), g.detach()), n  # only the shard was materialised, values match the single-device init
+
+
+def test_tp_sp_plan():
+    run_distributed(_tp_sp, 4)
+
+
+def test_deferred_init_sharded_equals_single_device():
+    run_distributed(_deferred, 4)

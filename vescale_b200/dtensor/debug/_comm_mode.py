@@ -35,8 +35,15 @@ class CommDebugMode:
         if self._module is not None:
             for fqn, m in self._module.named_modules():
                 fqn = fqn or type(m).__name__
-                self._handles.append(m.register_forward_pre_hook(lambda mod, a, _n=fqn: self._stack.append(_n)))
-                self._handles.append(m.register_forward_hook(lambda mod, a, o: self._stack and self._stack.pop()))
+                def _push(mod, a, _n=fqn):
+                    self._stack.append(_n)
+
+                def _pop(mod, a, o):
+                    if self._stack:
+                        self._stack.pop()
+
+                self._handles.append(m.register_forward_pre_hook(_push))
+                self._handles.append(m.register_forward_hook(_pop))
         return self
 
     def __exit__(self, *exc):

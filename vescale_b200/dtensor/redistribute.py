@@ -335,7 +335,7 @@ class Redistribute(torch.autograd.Function):
         # gradient layouts never carry Partial on the way back
         tgt_pl = tuple(Replicate() if p.is_partial() else p for p in prev.placements)
         g_tgt = DTensorSpec(prev.mesh, tgt_pl, g_cur.tensor_meta)
-        src_pl = tuple(Replicate() if p.is_partial() and not now.placements[i].is_partial() else p for i, p in enumerate(g_cur.placements))
-        g_src = DTensorSpec(g_cur.mesh, src_pl, g_cur.tensor_meta)
-        local = redistribute_local_tensor(grad._local_tensor, g_src, g_tgt)
+        # the incoming gradient keeps its own layout: a Partial gradient (e.g. from a column-parallel GEMM's
+        # dgrad) is reduced here — Partial -> Shard is the reduce-scatter of Megatron SP
+        local = redistribute_local_tensor(grad._local_tensor, g_cur, g_tgt)
         return DTensor(local, g_tgt, requires_grad=grad.requires_grad), None, None, None

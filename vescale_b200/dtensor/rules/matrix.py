@@ -87,10 +87,14 @@ register_rule([aten.mm.default], mm_rule)
 
 def addmm_rule(schema: OpSchema) -> RuleResult:
     bias, a, b = schema.args_schema[0], schema.args_schema[1], schema.args_schema[2]
+    # row-parallel (contraction-sharded) addmm: the bias joins as a Partial (its value on coordinate 0, zeros
+    # elsewhere) so that it is added exactly once by the pending reduction — the RowParallelLinear patch of
+    # legacy (``model/patch/linear.py:32-54``) expressed as a sharding rule
+    row = ((P, Shard(1), Shard(0)), P)
     if bias.ndim == 1:
-        cands = [((R, Shard(0), R), Shard(0)), ((Shard(0), R, Shard(1)), Shard(1)), ((R, R, R), R)]
+        cands = [((R, Shard(0), R), Shard(0)), ((Shard(0), R, Shard(1)), Shard(1)), row, ((R, R, R), R)]
     else:
-        cands = [((Shard(0) if bias.shape[0] != 1 else R, Shard(0), R), Shard(0)), ((Shard(1) if bias.shape[-1] != 1 else R, R, Shard(1)), Shard(1)), ((R, R, R), R)]
+        cands = [((Shard(0) if bias.shape[0] != 1 else R, Shard(0), R), Shard(0)), ((Shard(1) if bias.shape[-1] != 1 else R, R, Shard(1)), Shard(1)), row, ((R, R, R), R)]
     ins, out = _pick(schema.mesh, [bias, a, b], cands)
     return RuleResult(out=out, ins=ins)
 
