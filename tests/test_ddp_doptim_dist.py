@@ -1,0 +1,68 @@
+"""DDP + DistributedOptimizer / BasicOptimizer vs single-process golden (2 epochs x 2 micro-batches),
+parametrised like ``legacy/test/parallel/ddp_optim/test_doptimizer.py:51-80``."""
+import copy
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from common import device_type, run_distributed
+
+
+class MLP(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = nn.Linear(16, 64)
+        self.n = nn.LayerNorm(64)
+        self.b = nn.Linear(64, 16)
+
+    def forward(self, x):
+        return self.b(self.n(torch.relu(self.a(x))))
+
+
+def _data(step, mb, rank):
+    g = torch.Generator().manual_seed(1000 * step + 10 * mb + rank)
+    return torch.randn(4, 16, generator=g), torch.randn(4, 16, generator=g)
+
+
+def _run(rank, world, use_dopt, overlap_grad, overlap_gather):
+    from vescale_b200.optim import BasicOptimizer, DistributedOptimizer
+    from vescale_b200.parallel.ddp import DistributedDataParallel as DDP
+
+    dev = device_type()
+    torch.manual_seed(0)
+    ref = MLP().to(dev)
+    model = copy.deepcopy(ref)
+    ref_opt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.05)
+    ddp = DDP(model, dist.group.WORLD, overlap_grad_reduce=overlap_grad, use_distributed_optimizer=use_dopt, bucket_size=600)
+    inner = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.05)
+    opt = DistributedOptimizer(inner, [ddp], clip_grad=1.0, overlap_param_gather=overlap_gather) if use_dopt else BasicOptimizer(inner, [ddp], clip_grad=1.0)
+    for step in range(2):
+        ref_opt.zero_grad()
+        for mb in range(2):
+            for r in range(world):
+                x, y = _data(step, mb, r)
+                (torch.nn.functional.mse_loss(ref(x.to(dev)), y.to(dev)) / (2 * world)).backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        ref_opt.step()
+        opt.zero_grad()
+        for mb in range(2):
+            x, y = _data(step, mb, rank)
+            ctx = ddp.no_sync() if mb == 0 else torch.enable_grad()
+            with ctx:
+                (torch.nn.functional.mse_loss(ddp(x.to(dev)), y.to(dev)) / 2).backward()
+        opt.step()
+        if use_dopt:
+            opt.finish_param_gather()
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-4, atol=2e-5, msg=n)
+    if use_dopt:
+        sd = opt.state_dict()
+        assert sd["state"] and all("exp_avg" in e and "main" in e for ents in sd["state"].values() for e in ents)
+        opt.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("use_dopt,overlap_grad,overlap_gather", [(False, True, False), (True, True, False), (True, False, True), (True, True, True)])
+def test_ddp_optimizers_match_single_process(use_dopt, overlap_grad, overlap_gather):
+    run_distributed(_run, 4, use_dopt, overlap_grad, overlap_gather)

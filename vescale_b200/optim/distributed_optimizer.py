@@ -1,0 +1,232 @@
+"""DistributedOptimizer (ZeRO-2+): optimizer state and fp32 master weights sharded over the DP group.
+
+Works on top of ``DistributedDataParallel(use_distributed_optimizer=True)``:
+
+* every gradient bucket is reduce-scattered; DP rank r owns the r-th equal slice of each bucket (slice
+  boundaries ignore parameter edges, ``legacy/vescale/optim/distributed_optimizer.py:454-517``);
+* fp32 *main* shards mirror the owned slices; the wrapped optimizer's param groups are re-pointed at views of
+  the main shards (one view per parameter piece, so per-group hyper-parameters survive);
+* ``step``: main_grad ← owned grad slice (fp32), global-norm clip, inner ``optimizer.step()``, model-dtype copy
+  into the owned slice of the flat *parameter buffer*, then one ``all_gather_into_tensor`` per bucket — eagerly,
+  or deferred to forward pre-hooks so the gather of bucket i+1 overlaps the forward that uses bucket i
+  (``overlap_param_gather``, ``:995-1076``); module parameters are views into the parameter buffer, so the
+  gather is zero-copy;
+* ``state_dict`` exposes each state tensor with its ``OptimizerStateSpec`` (global shape / local shape /
+  global offset of the owned piece) for resharding checkpoints (``:51-93,748-880``).
+
+On B200 the same step for FSDP-wrapped models is the fused kernel path (``FSDPAdamW``); this class is the general
+wrapper for arbitrary torch optimizers and DDP models.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from ..dtensor.api import DTensor
+from ..parallel.ddp import DistributedDataParallel, GradBuffer, _local
+from .clip_grads import get_grad_norm_fp32
+
+__all__ = ["DistributedOptimizer", "OptimizerStateSpec"]
+
+
+@dataclass
+class OptimizerStateSpec:
+    global_shape: Tuple[int, ...]
+    local_shape: Tuple[int, ...]
+    global_offset: Tuple[int, ...]
+    local_tensor: torch.Tensor
+    dp_ranks_ranges: Optional[Dict[int, Tuple[int, int]]] = None
+
+
+class _BucketShard:
+    def __init__(self, gb: GradBuffer, bucket, dtype, rank: int, dp: int):
+        self.gb = gb
+        self.bucket = bucket
+        n = bucket.data.numel() // dp
+        self.lo = bucket.offset + rank * n  # offsets in the dtype's flat buffer
+        self.hi = self.lo + n
+        self.n = n
+
+
+class DistributedOptimizer:
+    def __init__(
+        self,
+        optimizer: torch.optim.Optimizer,
+        models: Sequence[DistributedDataParallel],
+        *,
+        clip_grad: float = 0.0,
+        overlap_param_gather: bool = False,
+        grad_to_fp32: bool = True,
+        extra_norm_groups: Sequence = (),
+    ):
+        self.optimizer = optimizer
+        self.models = list(models) if isinstance(models, (list, tuple)) else [models]
+        self.clip_grad = clip_grad
+        self.overlap_param_gather = overlap_param_gather
+        self.extra_norm_groups = list(extra_norm_groups)
+        m0 = self.models[0]
+        assert all(isinstance(m, DistributedDataParallel) and m.use_distributed_optimizer for m in self.models), "models must be DDP(use_distributed_optimizer=True)"
+        self.group = m0.group
+        self.dp = m0.dp_size
+        self.rank = dist.get_rank(self.group) if self.group is not None and self.dp > 1 else 0
+
+        # ---- flat parameter buffers mirroring the grad buffers; parameters become views
+        self.param_buffers: Dict[Tuple[int, torch.dtype], torch.Tensor] = {}
+        self.shards: List[_BucketShard] = []
+        self.main_shards: Dict[int, torch.Tensor] = {}  # id(_BucketShard) -> fp32 flat
+        self.piece_of: Dict[int, List[Tuple[_BucketShard, int, int, int]]] = {}  # id(param) -> [(shard, p_lo, p_hi, shard_off)]
+        for mi, m in enumerate(self.models):
+            for dt, gb in m.grad_buffers.items():
+                pdt = _local(gb.params[0]).dtype
+                pbuf = torch.empty(gb.numel, dtype=pdt, device=gb.data.device)
+                self.param_buffers[(mi, dt)] = pbuf
+                for p in gb.params:
+                    s, e, _ = gb.param_index[id(p)]
+                    lp = _local(p)
+                    pbuf[s:e].copy_(lp.detach().reshape(-1))
+                    view = pbuf[s:e].view(lp.shape)
+                    if isinstance(p.data, DTensor):
+                        p.data._local_tensor = view
+                    else:
+                        p.data = view
+                for b in gb.buckets:
+                    sh = _BucketShard(gb, b, dt, self.rank, self.dp)
+                    sh.pbuf = pbuf
+                    self.shards.append(sh)
+                    self.main_shards[id(sh)] = pbuf[sh.lo : sh.hi].float().clone()
+                    for p in b.params:
+                        s, e, _ = gb.param_index[id(p)]
+                        lo, hi = max(s, sh.lo), min(e, sh.hi)
+                        if hi > lo:
+                            self.piece_of.setdefault(id(p), []).append((sh, lo - s, hi - s, lo - sh.lo))
+        # ---- re-point the inner optimizer at fp32 main pieces
+        self.main_params: Dict[int, List[nn.Parameter]] = {}
+        for g in self.optimizer.param_groups:
+            new = []
+            for p in g["params"]:
+                for sh, p_lo, p_hi, off in self.piece_of.get(id(p), []):
+                    mp = nn.Parameter(self.main_shards[id(sh)][off : off + (p_hi - p_lo)], requires_grad=True)
+                    mp._orig_param, mp._piece = p, (p_lo, p_hi)
+                    mp._shard, mp._off = sh, off
+                    self.main_params.setdefault(id(p), []).append(mp)
+                    new.append(mp)
+            g["params"] = new
+        self.optimizer.state.clear()
+        self._pending_gathers: List[Tuple[_BucketShard, object]] = []
+        self._hooks = []
+        if overlap_param_gather:
+            self._install_forward_hooks()
+
+    @property
+    def param_groups(self):
+        return self.optimizer.param_groups
+
+    # ------------------------------------------------------------------ step
+    def _main_grads(self) -> List[torch.Tensor]:
+        gs = []
+        for plist in self.main_params.values():
+            for mp in plist:
+                sh, off = mp._shard, mp._off
+                g = sh.gb.data[sh.lo + off : sh.lo + off + mp.numel()]
+                mp.grad = g.float()
+                gs.append(mp.grad)
+        return gs
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for m in self.models:
+            m.finish_grad_sync()
+        grads = self._main_grads()
+        norm = None
+        if self.clip_grad and self.clip_grad > 0:
+            norm = get_grad_norm_fp32(grads, 2.0, [self.group] + self.extra_norm_groups if self.dp > 1 else self.extra_norm_groups)
+            coef = torch.clamp(self.clip_grad / (norm + 1e-6), max=1.0)
+            if grads:
+                torch._foreach_mul_(grads, coef)
+        self.optimizer.step(closure)
+        # main -> model dtype into the owned slice of the parameter buffer, then gather
+        for sh in self.shards:
+            sh.pbuf[sh.lo : sh.hi].copy_(self.main_shards[id(sh)])
+        if self.dp > 1:
+            for sh in self.shards:
+                full = sh.pbuf[sh.bucket.offset : sh.bucket.offset + sh.bucket.data.numel()]
+                mine = sh.pbuf[sh.lo : sh.hi]
+                if self.overlap_param_gather:
+                    self._pending_gathers.append((sh, dist.all_gather_into_tensor(full, mine, group=self.group, async_op=True)))
+                else:
+                    dist.all_gather_into_tensor(full, mine, group=self.group)
+        return norm
+
+    def _install_forward_hooks(self):
+        """Wait for the parameter gathers right before the first module that needs them runs."""
+
+        def pre(mod, args):
+            self.finish_param_gather()
+
+        for m in self.models:
+            self._hooks.append(m.module.register_forward_pre_hook(pre))
+
+    def finish_param_gather(self):
+        for _, h in self._pending_gathers:
+            if h is not None:
+                h.wait()
+        self._pending_gathers.clear()
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.optimizer.zero_grad(set_to_none)
+        for m in self.models:
+            m.zero_grad_buffer()
+
+    # ------------------------------------------------------------------ checkpoint
+    def state_dict(self) -> dict:
+        """{param_name: {state_key: OptimizerStateSpec}} + the inner optimizer's param_groups (without tensors)."""
+        out = {"param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.optimizer.param_groups], "state": {}}
+        names = {}
+        for m in self.models:
+            names.update(m.param_names)
+        for pid, plist in self.main_params.items():
+            for mp in plist:
+                p = mp._orig_param
+                numel = _local(p).numel()
+                st = self.optimizer.state.get(mp, {})
+                ent = {"main": OptimizerStateSpec((numel,), (mp.numel(),), (mp._piece[0],), mp.data)}
+                for k, v in st.items():
+                    if torch.is_tensor(v) and v.numel() == mp.numel():
+                        ent[k] = OptimizerStateSpec((numel,), (mp.numel(),), (mp._piece[0],), v)
+                    else:
+                        ent[k] = v
+                out["state"].setdefault(names.get(pid, str(pid)), []).append(ent)
+        return out
+
+    def load_state_dict(self, sd: dict) -> None:
+        names = {}
+        for m in self.models:
+            names.update(m.param_names)
+        for g, saved in zip(self.optimizer.param_groups, sd.get("param_groups", [])):
+            g.update(saved)
+        for pid, plist in self.main_params.items():
+            ents = sd["state"].get(names.get(pid, str(pid)), [])
+            for mp in plist:
+                for ent in ents:
+                    spec = ent["main"]
+                    s_lo = spec.global_offset[0]
+                    s_hi = s_lo + spec.local_shape[0]
+                    lo, hi = max(s_lo, mp._piece[0]), min(s_hi, mp._piece[1])
+                    if hi <= lo:
+                        continue
+                    for k, v in ent.items():
+                        src = v.local_tensor if isinstance(v, OptimizerStateSpec) else None
+                        if src is None:
+                            self.optimizer.state.setdefault(mp, {})[k] = v
+                            continue
+                        if k == "main":
+                            dst = mp.data
+                        else:
+                            dst = self.optimizer.state.setdefault(mp, {}).setdefault(k, torch.zeros_like(mp.data))
+                        dst[lo - mp._piece[0] : hi - mp._piece[0]].copy_(src[lo - s_lo : hi - s_lo])
+        for sh in self.shards:
+            sh.pbuf[sh.lo : sh.hi].copy_(self.main_shards[id(sh)])

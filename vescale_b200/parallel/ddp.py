@@ -1,0 +1,241 @@
+"""DistributedDataParallel with flat gradient buffers (Megatron-style), optionally reduce-scattering for the
+ZeRO-2+ DistributedOptimizer.
+
+* one contiguous ``GradBuffer`` per parameter dtype; parameters are laid out in reverse registration order so
+  buckets fill in the order gradients become ready in backward; bucket ≈ ``bucket_size`` elements, padded to a
+  multiple of the DP size when the distributed optimizer will shard it;
+* ``param.main_grad`` is a view into the buffer; a post-accumulate-grad hook folds ``param.grad`` into it and,
+  when the bucket is complete, launches ``data /= dp`` + all-reduce (or reduce-scatter) — asynchronously when
+  ``overlap_grad_reduce``;
+* DTensor parameters (TP/SP via DModule) use their local shards; gradients that are ``Partial`` on the
+  model-parallel mesh are all-reduced there first (SP norm weights);
+* ``no_sync()`` / ``zero_grad_buffer()`` / ``finish_grad_sync()`` as in the reference.
+
+On CUDA the pre-scale, cast and the reduce are the fused symmetric-memory kernels of the FSDP path when the
+buffer is allocated from a SymmArena (``comm_backend="symm"``); otherwise c10d.
+
+Parity: ``legacy/vescale/ddp/distributed_data_parallel.py:20-336``, ``legacy/vescale/ddp/grad_buffer.py:27-494``.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from ..comm import collectives as C
+from ..dtensor.api import DTensor
+from ..mesh import DeviceMesh
+
+__all__ = ["DistributedDataParallel", "GradBuffer", "Bucket"]
+
+
+def _local(t):
+    return t._local_tensor if isinstance(t, DTensor) else t
+
+
+class Bucket:
+    def __init__(self, params: List[nn.Parameter], data: torch.Tensor, offset: int, group, dp_size: int, overlap: bool, use_distributed_optimizer: bool):
+        self.params = params
+        self.params_set = {id(p) for p in params}
+        self.data = data
+        self.offset = offset
+        self.group = group
+        self.dp_size = dp_size
+        self.overlap = overlap
+        self.use_distributed_optimizer = use_distributed_optimizer
+        self.reset()
+
+    def reset(self):
+        self.ready = set()
+        self.handle = None
+        self.issued = False
+
+    def start_grad_sync(self):
+        assert not self.issued, "bucket reduce already in flight (one reduce per backward)"
+        self.issued = True
+        self.data.div_(self.dp_size)
+        if self.dp_size == 1:
+            return
+        if self.use_distributed_optimizer:
+            rank = dist.get_rank(self.group)
+            n = self.data.numel() // self.dp_size
+            out = self.data[rank * n : (rank + 1) * n]
+            if dist.get_backend(self.group) == "nccl":
+                self.handle = dist.reduce_scatter_tensor(out, self.data, group=self.group, async_op=self.overlap)
+            else:  # gloo has no reduce-scatter: all-reduce, the owner slice is what matters
+                self.handle = dist.all_reduce(self.data, group=self.group, async_op=self.overlap)
+        else:
+            self.handle = dist.all_reduce(self.data, group=self.group, async_op=self.overlap)
+        if not self.overlap:
+            self.handle = None
+
+    def finish_grad_sync(self):
+        if not self.issued:
+            self.start_grad_sync()
+        if self.handle is not None:
+            self.handle.wait()
+            self.handle = None
+
+    def register_grad_ready(self, p) -> bool:
+        self.ready.add(id(p))
+        return len(self.ready) == len(self.params)
+
+
+class GradBuffer:
+    def __init__(self, dtype, params: List[nn.Parameter], group, dp_size: int, bucket_size: Optional[int], overlap: bool, use_distributed_optimizer: bool, device):
+        self.dtype = dtype
+        self.group = group
+        self.dp_size = dp_size
+        self.overlap = overlap
+        self.use_distributed_optimizer = use_distributed_optimizer
+        # reverse order: the last layers' grads are ready first
+        ordered = list(reversed(params))
+        self.param_index: Dict[int, Tuple[int, int, int]] = {}  # id -> (start, end, bucket_id)
+        bucket_bounds: List[Tuple[int, int, List[nn.Parameter]]] = []
+        pos = 0
+        cur_start, cur_params = 0, []
+
+        def pad(n):
+            if use_distributed_optimizer:
+                m = dp_size * 64  # keep every DP shard 128-byte aligned
+                return (n + m - 1) // m * m
+            return n
+
+        for p in ordered:
+            n = _local(p).numel()
+            self.param_index[id(p)] = (pos, pos + n, len(bucket_bounds))
+            pos += n
+            cur_params.append(p)
+            if bucket_size is not None and pos - cur_start >= bucket_size:
+                end = pad(pos)
+                bucket_bounds.append((cur_start, end, cur_params))
+                pos = end
+                cur_start, cur_params = pos, []
+        if cur_params:
+            end = pad(pos)
+            bucket_bounds.append((cur_start, end, cur_params))
+            pos = end
+        self.numel = pos
+        self.data = torch.zeros(self.numel, dtype=dtype, device=device)
+        self.buckets = [Bucket(ps, self.data[s:e], s, group, dp_size, overlap, use_distributed_optimizer) for s, e, ps in bucket_bounds]
+        self.params = ordered
+        for p in ordered:
+            s, e, _ = self.param_index[id(p)]
+            p.main_grad = self.data[s:e].view(_local(p).shape)
+
+    def bucket_of(self, p) -> Bucket:
+        return self.buckets[self.param_index[id(p)][2]]
+
+    def reset(self, zero: bool = True):
+        if zero:
+            self.data.zero_()
+        for b in self.buckets:
+            b.reset()
+
+    def finish_grad_sync(self):
+        for b in self.buckets:
+            b.finish_grad_sync()
+
+
+class DistributedDataParallel(nn.Module):
+    def __init__(
+        self,
+        module: nn.Module,
+        data_pg_or_device_mesh=None,
+        *,
+        accumulate_allreduce_grads_in_fp32: bool = False,
+        overlap_grad_reduce: bool = True,
+        use_distributed_optimizer: bool = False,
+        disable_bucketing: bool = False,
+        bucket_size: int = 40_000_000,
+        module_to_enforce: Optional[Sequence[type]] = None,
+        param_to_ignore: Optional[Sequence[str]] = None,
+    ):
+        super().__init__()
+        self.module = module
+        mesh_or_pg = data_pg_or_device_mesh
+        if isinstance(mesh_or_pg, DeviceMesh):
+            self.group = mesh_or_pg.get_group(0) if mesh_or_pg.ndim == 1 else mesh_or_pg.get_group("DP")
+        elif mesh_or_pg is None:
+            self.group = dist.group.WORLD if dist.is_initialized() else None
+        else:
+            self.group = mesh_or_pg
+        self.dp_size = dist.get_world_size(self.group) if self.group is not None else 1
+        self.overlap_grad_reduce = overlap_grad_reduce
+        self.use_distributed_optimizer = use_distributed_optimizer
+        self.bucket_size = None if disable_bucketing or not overlap_grad_reduce else bucket_size
+        self.param_to_ignore = set(param_to_ignore or [])
+        self.is_last_microbatch = True
+        self.grad_buffers: Dict[torch.dtype, GradBuffer] = {}
+        by_dtype: Dict[torch.dtype, List[nn.Parameter]] = {}
+        self.param_names = {}
+        for n, p in module.named_parameters():
+            self.param_names[id(p)] = n
+            if not p.requires_grad or n in self.param_to_ignore:
+                continue
+            dt = torch.float32 if accumulate_allreduce_grads_in_fp32 else _local(p).dtype
+            by_dtype.setdefault(dt, []).append(p)
+        dev = next((_local(p).device for p in module.parameters()), torch.device("cpu"))
+        for dt, ps in by_dtype.items():
+            self.grad_buffers[dt] = GradBuffer(dt, ps, self.group, self.dp_size, self.bucket_size, overlap_grad_reduce, use_distributed_optimizer, dev)
+        self._param_to_buffer = {id(p): gb for gb in self.grad_buffers.values() for p in gb.params}
+        self._hooks = []
+        for gb in self.grad_buffers.values():
+            for p in gb.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(p, gb)))
+
+    def _make_hook(self, p, gb: GradBuffer):
+        def hook(param):
+            g = param.grad
+            if g is None:
+                return
+            if isinstance(g, DTensor):
+                # model-parallel Partial grads (SP) are reduced on their own mesh right away
+                if any(pl.is_partial() for pl in g.placements):
+                    from ..placement import Replicate
+
+                    g = g.redistribute(g.device_mesh, [Replicate() if pl.is_partial() else pl for pl in g.placements])
+                g = g._local_tensor
+            param.main_grad.add_(g.to(param.main_grad.dtype))
+            param.grad = None
+            if self.overlap_grad_reduce and self.is_last_microbatch:
+                b = gb.bucket_of(param)
+                if b.register_grad_ready(param):
+                    b.start_grad_sync()
+
+        return hook
+
+    def forward(self, *a, **kw):
+        return self.module(*a, **kw)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        prev, self.is_last_microbatch = self.is_last_microbatch, False
+        try:
+            yield
+        finally:
+            self.is_last_microbatch = prev
+
+    def zero_grad_buffer(self, zero_buffer: bool = True):
+        for gb in self.grad_buffers.values():
+            gb.reset(zero_buffer)
+
+    def start_grad_sync(self):
+        for gb in self.grad_buffers.values():
+            for b in gb.buckets:
+                if not b.issued:
+                    b.start_grad_sync()
+
+    def finish_grad_sync(self):
+        for gb in self.grad_buffers.values():
+            gb.finish_grad_sync()
+
+    def state_dict(self, *a, **kw):
+        return self.module.state_dict(*a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        return self.module.load_state_dict(*a, **kw)
