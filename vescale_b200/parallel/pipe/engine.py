@@ -1,0 +1,191 @@
+"""PipeEngine: run one mini-batch through the pipeline schedule.
+
+    engine = PipeEngine(pipe_module, mesh, loss_fn, plan)
+    loss, outputs = engine(minibatch_inputs, minibatch_labels)      # list of micro-batches or a tensor to chunk
+
+The executor interprets this rank's instruction row (``schedule.build_schedule``): F / B / W with p2p receives
+right before and sends right after each op (``p2p.P2PContext``).  Backward of a chunk is
+``torch.autograd.backward`` on the stage outputs; when the schedule splits weight gradients (zero-bubble), B
+takes only the input gradients (``autograd.grad(..., inputs=stage_inputs)``) and W later produces the
+parameter gradients from the retained graph.  ``VESCALE_DUMP_INSTRUCTION=1`` writes the per-rank instruction
+files (``legacy/vescale/dtensor/_diff.py:25-71``).
+
+Parity: ``legacy/vescale/engine/pipe.py:33-237``, ``pipe/pipe_emmiter.py:132-343`` (ScheduleEngine).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .p2p import P2PContext
+from .plan import PipelineParallelPlan, PipelineScheduleType
+from .schedule import INSTRUCTION_REGISTRY, Instr, build_schedule, stage_placement
+from .stage import PipeModule
+
+__all__ = ["PipeEngine", "ScheduleEngine"]
+
+
+def _as_tuple(x):
+    if isinstance(x, tuple):
+        return x
+    if isinstance(x, list):
+        return tuple(x)
+    return (x,)
+
+
+class ScheduleEngine:
+    def __init__(self, module: PipeModule, plan: PipelineParallelPlan, pp_rank: int, pp_group, loss_fn: Optional[Callable], device):
+        self.module, self.plan, self.rank, self.group, self.loss_fn, self.device = module, plan, pp_rank, pp_group, loss_fn, device
+        self.P, self.V = plan.num_stages, plan.virtual_chunks
+        self.NV = self.P * self.V
+        self.place = stage_placement(self.P, self.V, plan.schedule_type)
+        self.split_w = plan.schedule_type in (PipelineScheduleType.ZERO_BUBBLE, PipelineScheduleType.ZERO_BUBBLE_V)
+        self._sched_cache: Dict[int, List[List[Instr]]] = {}
+        self._shape_cache: Dict = {}
+
+    def schedule(self, M: int) -> List[List[Instr]]:
+        if M not in self._sched_cache:
+            self._sched_cache[M] = build_schedule(self.plan, M)
+            if os.environ.get("VESCALE_DUMP_INSTRUCTION", "0") == "1":
+                with open(f"pipe_instructions_rank{self.rank}.txt", "w") as f:
+                    f.write("\n".join(repr(i) for i in self._sched_cache[M][self.rank]))
+        return self._sched_cache[M]
+
+    def _incoming_order(self, rows: List[List[Instr]]) -> Dict[int, List[Tuple[str, int, int]]]:
+        """For every peer: the messages it sends me, in its send order."""
+        order: Dict[int, List] = {}
+        for r, row in enumerate(rows):
+            if r == self.rank:
+                continue
+            for ins in row:
+                if ins.kind == "F" and ins.vstage + 1 < self.NV and self.place[ins.vstage + 1][0] == self.rank:
+                    order.setdefault(r, []).append(("F", ins.microbatch, ins.vstage))
+                if ins.kind == "B" and ins.vstage > 0 and self.place[ins.vstage - 1][0] == self.rank:
+                    order.setdefault(r, []).append(("B", ins.microbatch, ins.vstage))
+        return order
+
+    def execute(self, inputs: Sequence, labels: Optional[Sequence], forward_only: bool = False):
+        M = len(inputs)
+        rows = self.schedule(M)
+        p2p = P2PContext(self.group, self.rank, self._incoming_order(rows), self.device, self.plan.p2p_tensor_dtype, self.plan.reuse_p2p_tensor_shape)
+        p2p.shapes = self._shape_cache
+        acts: Dict[Tuple[int, int], Tuple] = {}  # (m, v) -> (stage_inputs, stage_outputs)
+        local_fwd: Dict[Tuple[int, int], Tuple] = {}
+        local_bwd: Dict[Tuple[int, int], Tuple] = {}
+        pending_w: Dict[Tuple[int, int], Tuple] = {}
+        losses: List[Optional[torch.Tensor]] = [None] * M
+        outputs: List = [None] * M
+        for ins in rows[self.rank]:
+            h = INSTRUCTION_REGISTRY.get(ins.kind)
+            if h is not None and h(self, ins) is not None:
+                continue
+            m, v, c = ins.microbatch, ins.vstage, ins.chunk
+            if ins.kind == "F":
+                if v == 0:
+                    xs = _as_tuple(inputs[m])
+                elif self.place[v - 1][0] == self.rank:
+                    xs = local_fwd.pop((m, v - 1))
+                else:
+                    xs = p2p.recv(("F", m, v - 1), self.place[v - 1][0])
+                xs = tuple(x.detach().requires_grad_(x.is_floating_point() and not forward_only) if isinstance(x, torch.Tensor) else x for x in xs)
+                with torch.set_grad_enabled(not forward_only):
+                    out = self.module(*xs, chunk_id=c)
+                    outs = _as_tuple(out)
+                    if v == self.NV - 1:
+                        outputs[m] = out
+                        if self.loss_fn is not None and labels is not None:
+                            loss = self.loss_fn(out, labels[m]) / M
+                            losses[m] = loss.detach()
+                            outs = (loss,)
+                acts[(m, v)] = (xs, outs)
+                if v + 1 < self.NV:
+                    if self.place[v + 1][0] == self.rank:
+                        local_fwd[(m, v)] = tuple(o.detach() for o in outs)
+                    else:
+                        p2p.send(("F", m, v), outs, self.place[v + 1][0])
+            elif ins.kind == "B":
+                xs, outs = acts[(m, v)]
+                if v == self.NV - 1:
+                    gouts = tuple(torch.ones_like(o) for o in outs)
+                elif self.place[v + 1][0] == self.rank:
+                    gouts = local_bwd.pop((m, v + 1))
+                else:
+                    gouts = p2p.recv(("B", m, v + 1), self.place[v + 1][0])
+                pairs = [(o, g) for o, g in zip(outs, gouts) if isinstance(o, torch.Tensor) and o.requires_grad]
+                o_t, g_t = [p[0] for p in pairs], [p[1] for p in pairs]
+                grad_inputs = [x for x in xs if isinstance(x, torch.Tensor) and x.requires_grad]
+                if self.split_w:
+                    gi = torch.autograd.grad(o_t, grad_inputs, g_t, retain_graph=True, allow_unused=True) if grad_inputs else ()
+                    pending_w[(m, v)] = (o_t, g_t)
+                else:
+                    torch.autograd.backward(o_t, g_t)
+                    gi = tuple(x.grad for x in grad_inputs)
+                    del acts[(m, v)]
+                if v > 0:
+                    gi = tuple(g if g is not None else torch.zeros_like(x) for g, x in zip(gi, grad_inputs))
+                    if self.place[v - 1][0] == self.rank:
+                        local_bwd[(m, v)] = gi
+                    else:
+                        p2p.send(("B", m, v), gi, self.place[v - 1][0])
+            elif ins.kind == "W":
+                o_t, g_t = pending_w.pop((m, v))
+                params = [p for p in self.module.chunk(c).parameters() if p.requires_grad]
+                gs = torch.autograd.grad(o_t, params, g_t, allow_unused=True)
+                for p, g in zip(params, gs):
+                    if g is not None:
+                        p.grad = g if p.grad is None else p.grad + g
+                del acts[(m, v)]
+        p2p.drain()
+        return losses, outputs
+
+
+class PipeEngine:
+    def __init__(self, module: PipeModule, global_mesh=None, loss_fn: Optional[Callable] = None, plan: Optional[PipelineParallelPlan] = None, *, pp_group=None, pp_rank: Optional[int] = None, device=None):
+        self.module = module
+        self.plan = plan or module.plan
+        self.loss_fn = loss_fn
+        if global_mesh is not None and pp_rank is None:
+            names = global_mesh.mesh_dim_names or ()
+            d = names.index("PP") if "PP" in names else 0
+            pp_rank = global_mesh.get_local_rank(d)
+            pp_group = global_mesh.get_group(d) if global_mesh.has_groups() else None
+            device = device or (torch.device("cuda", torch.cuda.current_device()) if global_mesh.device_type == "cuda" else torch.device("cpu"))
+        self.pp_rank = pp_rank if pp_rank is not None else module.pp_rank
+        self.pp_group = pp_group if pp_group is not None else module.pp_group
+        self.device = device or torch.device("cpu")
+        self.schedule_engine = ScheduleEngine(module, self.plan, self.pp_rank, self.pp_group, loss_fn, self.device)
+        os.environ["STAGE_ID"] = str(self.pp_rank)
+        if self.plan.reuse_p2p_tensor_shape:
+            os.environ["REUSE_COMM_SHAPE"] = "1"
+
+    @property
+    def is_last_rank(self) -> bool:
+        place = self.schedule_engine.place
+        return place[-1][0] == self.pp_rank
+
+    def forward_backward(self, minibatch, labels=None, forward_only: bool = False, num_microbatches: Optional[int] = None):
+        if isinstance(minibatch, torch.Tensor):
+            n = num_microbatches or self.plan.num_stages
+            minibatch = list(minibatch.chunk(n))
+            labels = list(labels.chunk(n)) if isinstance(labels, torch.Tensor) else labels
+        losses, outputs = self.schedule_engine.execute(minibatch, labels, forward_only or self.plan.forward_only)
+        loss = None
+        if any(l is not None for l in losses):
+            loss = torch.stack([l for l in losses if l is not None]).sum()
+        return loss, outputs
+
+    __call__ = forward_backward
+
+    def sync_shared_params(self, share_params: bool = True):
+        self.module.sync_shared_params(share_params)
+
+    def parameters(self):
+        return self.module.parameters()
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.module.parameters():
+            p.grad = None

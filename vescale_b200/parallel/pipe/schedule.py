@@ -1,0 +1,193 @@
+"""Pipeline schedules as explicit instruction streams produced by one deterministic list scheduler.
+
+Every rank simulates the whole pipeline (identical inputs → identical result) and keeps its own row.  An op is
+``F`` (forward of micro-batch m through virtual stage v), ``B`` (backward: input gradients — and weight
+gradients too unless the schedule splits them) or ``W`` (weight gradients).  Ops become *ready* when their
+producers have finished (+ a p2p latency); an idle rank takes its highest-priority ready op subject to an
+activation-memory bound on in-flight forwards.  Priorities and placement give the classic schedules:
+
+    GPipe              F before B, unbounded in-flight
+    1F1B               B before F, stage s keeps at most P - s forwards in flight
+    interleaved 1F1B   V chunks per rank (virtual stage v lives on rank v % P), B before F
+    zero-bubble (H1)   1F1B with backward split: B > F > W, W fills the bubbles
+    ZB-V               two chunks per rank placed in a V (v and 2P-1-v share a rank), B > F > W
+
+Parity: ``legacy/vescale/pipe/_schedules/{pipedream_flush,looping_bfs,zero_bubble_v,instruction_base}.py`` —
+the 1F1B / interleaved / ZB-V generators and the instruction registry; the greedy cost-driven construction
+mirrors ZB-V's ``CostGraph`` scheduler (``zero_bubble_v.py:198-600``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+from .plan import PipelineParallelPlan, PipelineScheduleType
+
+__all__ = ["Instr", "build_schedule", "stage_placement", "register_instruction", "INSTRUCTION_REGISTRY", "StageDeps"]
+
+
+@dataclass(frozen=True)
+class Instr:
+    kind: str  # "F" | "B" | "W"
+    microbatch: int
+    vstage: int  # virtual stage index in [0, P*V)
+    chunk: int  # local chunk index on the owning rank
+    start: float = 0.0
+    end: float = 0.0
+
+    def __repr__(self):
+        return f"{self.kind}{self.microbatch}@v{self.vstage}"
+
+
+INSTRUCTION_REGISTRY: Dict[str, Callable] = {}
+
+
+def register_instruction(name: str):
+    """User-extensible instruction set (legacy ``instruction_base.py:58``): handlers are looked up by the executor."""
+
+    def deco(fn):
+        INSTRUCTION_REGISTRY[name] = fn
+        return fn
+
+    return deco
+
+
+class StageDeps:
+    """Virtual-stage dependency table (legacy ``instruction_base.py:85``): a chain by default."""
+
+    def __init__(self, num_vstages: int):
+        self.n = num_vstages
+
+    def prev(self, v: int) -> Optional[int]:
+        return v - 1 if v > 0 else None
+
+    def next(self, v: int) -> Optional[int]:
+        return v + 1 if v + 1 < self.n else None
+
+
+def stage_placement(P: int, V: int, schedule: PipelineScheduleType) -> List[Tuple[int, int]]:
+    """virtual stage -> (rank, local chunk)."""
+    out = []
+    for v in range(P * V):
+        if schedule == PipelineScheduleType.ZERO_BUBBLE_V:
+            c = v // P
+            r = v % P if c % 2 == 0 else P - 1 - (v % P)
+        else:
+            c, r = v // P, v % P
+        out.append((r, c))
+    return out
+
+
+def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[List[Instr]]:
+    P, V, M = plan.num_stages, plan.virtual_chunks, num_microbatches
+    st = plan.schedule_type
+    NV = P * V
+    place = stage_placement(P, V, st)
+    split_w = st in (PipelineScheduleType.ZERO_BUBBLE, PipelineScheduleType.ZERO_BUBBLE_V) and not plan.forward_only
+    cF, cB, cW, cC = plan.costs.get("F", 1.0), plan.costs.get("B", 1.0), plan.costs.get("W", 1.0), plan.costs.get("comm", 0.0)
+    if not split_w:
+        cB = cB + cW
+    prio = {"F": 1, "B": 0, "W": 2} if st != PipelineScheduleType.GPIPE else {"F": 0, "B": 1, "W": 2}
+
+    def limit(rank: int) -> int:
+        if plan.max_inflight is not None:
+            return plan.max_inflight
+        if st == PipelineScheduleType.GPIPE or plan.forward_only:
+            return 10**9
+        if st == PipelineScheduleType.SIMPLE_1F1B or st == PipelineScheduleType.ZERO_BUBBLE:
+            return P - rank
+        if st == PipelineScheduleType.INTERLEAVED_1F1B:
+            return (P - rank - 1) * 2 + (V - 1) * P + 1
+        return 2 * P  # ZB-V: peak activation memory of 1F1B on the first stage
+
+    done: Dict[Tuple[str, int, int], float] = {}
+    remaining = set()
+    for m in range(M):
+        for v in range(NV):
+            remaining.add(("F", m, v))
+            if not plan.forward_only:
+                remaining.add(("B", m, v))
+                if split_w:
+                    remaining.add(("W", m, v))
+    rows: List[List[Instr]] = [[] for _ in range(P)]
+    free_at = [0.0] * P
+    inflight = [0] * P  # forwards whose backward has not run yet, per rank
+    next_f = [0] * NV  # micro-batches enter a virtual stage in order
+    next_b = [0] * NV
+
+    def ready_time(op) -> Optional[float]:
+        k, m, v = op
+        r = place[v][0]
+        if k == "F":
+            if m != next_f[v]:
+                return None
+            if v == 0:
+                return 0.0
+            t = done.get(("F", m, v - 1))
+            return None if t is None else t + (cC if place[v - 1][0] != r else 0.0)
+        if k == "B":
+            if m != next_b[v]:
+                return None
+            tf = done.get(("F", m, v))
+            if tf is None:
+                return None
+            if v == NV - 1:
+                return tf
+            t = done.get(("B", m, v + 1))
+            return None if t is None else max(tf, t + (cC if place[v + 1][0] != r else 0.0))
+        t = done.get(("B", m, v))
+        return t
+
+    now = 0.0
+    guard = 0
+    while remaining:
+        guard += 1
+        if guard > 10 * (len(remaining) + 10) * (P + 1) + 100000:
+            raise RuntimeError("pipeline scheduler did not converge (dependency cycle or memory bound too tight)")
+        progressed = False
+        for r in range(P):
+            if free_at[r] > now + 1e-12:
+                continue
+            cands = []
+            for op in remaining:
+                if place[op[2]][0] != r:
+                    continue
+                rt = ready_time(op)
+                if rt is None or rt > now + 1e-12:
+                    continue
+                if op[0] == "F" and inflight[r] >= limit(r):
+                    continue
+                cands.append(op)
+            if not cands:
+                continue
+            # priority, then older micro-batch, then (for F) deeper chunk first so the V/interleave drains
+            op = min(cands, key=lambda o: (prio[o[0]], o[1], -o[2] if o[0] == "F" else o[2]))
+            k, m, v = op
+            cost = cF if k == "F" else (cB if k == "B" else cW)
+            rows[r].append(Instr(k, m, v, place[v][1], now, now + cost))
+            done[op] = now + cost
+            remaining.discard(op)
+            free_at[r] = now + cost
+            if k == "F":
+                inflight[r] += 1
+                next_f[v] += 1
+            elif k == "B":
+                inflight[r] -= 1
+                next_b[v] += 1
+            progressed = True
+        if remaining:
+            # advance to the next time anything can change
+            future = [t for t in free_at if t > now + 1e-12] + [t for t in done.values() if t > now + 1e-12]
+            future += [t + cC for t in done.values() if t + cC > now + 1e-12]
+            if not progressed and not future:
+                raise RuntimeError(f"pipeline schedule deadlock at t={now} with {len(remaining)} ops left (in-flight limit too small?)")
+            if future:
+                now = min(future)
+    return rows
+
+
+def bubble_fraction(rows: List[List[Instr]]) -> float:
+    """Idle fraction of the schedule (max over ranks of makespan, summed busy time)."""
+    span = max((r[-1].end for r in rows if r), default=0.0)
+    busy = sum(i.end - i.start for r in rows for i in r)
+    return 1.0 - busy / (span * len(rows)) if span else 0.0

@@ -1,0 +1,193 @@
+"""Model splitting and per-rank stage modules.
+
+``construct_pipeline_stage(model, plan, mesh)`` splits the model into ``num_stages * virtual_chunks`` virtual
+stages and returns a ``PipeModule`` that holds only this rank's chunks.
+
+* STRUCTURAL tracer: the model is a chain of *units* — ``model.pipeline_units()`` if defined, else its direct
+  children in registration order; stage i is the ``nn.Sequential`` of its units.  Split by MANUAL split points,
+  UNIFORM unit count, or PARAMETERS (balanced parameter count).
+* FX tracer: ``torch.fx.symbolic_trace`` + ``split_module`` with call_module nodes assigned to stages by the same
+  unit→stage map (handles skip connections across stages as extra stage inputs/outputs).
+* tied parameters listed in ``plan.shared_modules`` get a process group spanning their owning ranks;
+  ``sync_shared_params`` all-reduces their values or gradients (legacy ``pipe_stage.py:200-247,311-500``).
+
+Parity: ``legacy/vescale/pipe/pipe_parser.py:46-652`` (split methods), ``pipe_stage.py:64-563``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .plan import PipelineParallelPlan, PipelineScheduleType, PipelineSplitMethodType, TracerType
+from .schedule import stage_placement
+
+__all__ = ["PipeModule", "construct_pipeline_stage", "split_units", "PipeParser"]
+
+
+def _units(model: nn.Module) -> List[Tuple[str, nn.Module]]:
+    if hasattr(model, "pipeline_units"):
+        return list(model.pipeline_units())
+    out = []
+    for n, m in model.named_children():
+        if isinstance(m, (nn.ModuleList, nn.Sequential)):
+            out += [(f"{n}.{k}", c) for k, c in m.named_children()]
+        else:
+            out.append((n, m))
+    return out
+
+
+def split_units(units: Sequence[Tuple[str, nn.Module]], plan: PipelineParallelPlan) -> List[List[int]]:
+    """Indices of the units of every virtual stage."""
+    n_vs = plan.num_stages * plan.virtual_chunks
+    n = len(units)
+    if n < n_vs:
+        raise ValueError(f"{n} units cannot fill {n_vs} virtual stages")
+    if plan.split_method == PipelineSplitMethodType.MANUAL:
+        names = [u[0] for u in units]
+        cuts = [names.index(p) + 1 for p in (plan.split_points or [])]
+        if len(cuts) != n_vs - 1:
+            raise ValueError(f"MANUAL split needs {n_vs - 1} split points, got {len(cuts)}")
+        bounds = [0] + cuts + [n]
+    elif plan.split_method == PipelineSplitMethodType.PARAMETERS:
+        sizes = [sum(p.numel() for p in u[1].parameters()) + 1 for u in units]
+        total = sum(sizes)
+        bounds, acc, tgt = [0], 0, total / n_vs
+        for i, s in enumerate(sizes):
+            acc += s
+            left_units, left_stages = n - (i + 1), n_vs - len(bounds)
+            if len(bounds) < n_vs and (acc >= tgt * len(bounds) or left_units == left_stages) and left_units >= left_stages:
+                bounds.append(i + 1)
+        bounds.append(n)
+    else:  # UNIFORM / AUTO
+        base, rem = divmod(n, n_vs)
+        bounds = [0]
+        for s in range(n_vs):
+            bounds.append(bounds[-1] + base + (1 if s < rem else 0))
+    return [list(range(bounds[s], bounds[s + 1])) for s in range(n_vs)]
+
+
+class _StageSeq(nn.Module):
+    def __init__(self, mods: Sequence[Tuple[str, nn.Module]]):
+        super().__init__()
+        self.names = [n for n, _ in mods]
+        self.mods = nn.ModuleList([m for _, m in mods])
+
+    def forward(self, *xs):
+        for m in self.mods:
+            xs = m(*xs) if isinstance(xs, tuple) else m(xs)
+            if not isinstance(xs, tuple):
+                xs = (xs,)
+        return xs if len(xs) > 1 else xs[0]
+
+
+class PipeParser:
+    """Splits a model into virtual-stage modules (all of them; the caller keeps its own)."""
+
+    def parse(self, model: nn.Module, plan: PipelineParallelPlan) -> List[nn.Module]:
+        units = _units(model)
+        groups = split_units(units, plan)
+        if plan.tracer_type == TracerType.FX:
+            return self._parse_fx(model, units, groups)
+        return [_StageSeq([units[i] for i in g]) for g in groups]
+
+    def _parse_fx(self, model, units, groups) -> List[nn.Module]:
+        import torch.fx as fx
+        from torch.fx.passes.split_module import split_module
+
+        unit_stage = {}
+        for s, g in enumerate(groups):
+            for i in g:
+                unit_stage[units[i][0]] = s
+        gm = fx.symbolic_trace(model)
+        cur = [0]
+
+        def part(node):
+            if node.op == "call_module":
+                t = str(node.target)
+                for name, s in unit_stage.items():
+                    if t == name or t.startswith(name + "."):
+                        cur[0] = max(cur[0], s)
+                        break
+            return cur[0]
+
+        split = split_module(gm, model, part)
+        return [getattr(split, f"submod_{s}") for s in range(len(groups)) if hasattr(split, f"submod_{s}")]
+
+
+class PipeModule(nn.Module):
+    """This rank's virtual stages.  ``forward(*inputs, chunk_id=c)`` runs local chunk c."""
+
+    def __init__(self, stage_modules: Dict[int, nn.Module], vstages: Dict[int, int], plan: PipelineParallelPlan, pp_rank: int, pp_group=None):
+        super().__init__()
+        self.stage_modules = nn.ModuleDict({str(c): m for c, m in stage_modules.items()})
+        self.vstage_of_chunk = dict(vstages)
+        self.plan = plan
+        self.pp_rank = pp_rank
+        self.pp_group = pp_group
+        self.shared_groups: List[Tuple[List[nn.Parameter], object]] = []
+
+    def chunk(self, c: int) -> nn.Module:
+        return self.stage_modules[str(c)]
+
+    def forward(self, *inputs, chunk_id: int = 0):
+        return self.chunk(chunk_id)(*inputs)
+
+    @property
+    def num_chunks(self) -> int:
+        return len(self.stage_modules)
+
+    def sync_shared_params(self, share_params: bool = True) -> None:
+        """All-reduce (average values / sum gradients) of parameters tied across stages, e.g. embeddings."""
+        for params, group in self.shared_groups:
+            for p in params:
+                if share_params:
+                    dist.all_reduce(p.data, group=group)
+                    p.data.div_(dist.get_world_size(group))
+                elif p.grad is not None:
+                    dist.all_reduce(p.grad, group=group)
+
+
+def construct_pipeline_stage(model: nn.Module, plan: PipelineParallelPlan, device_mesh=None, *, pp_rank: Optional[int] = None, pp_group=None, update_split_points: bool = False) -> PipeModule:
+    if device_mesh is not None and pp_rank is None:
+        names = device_mesh.mesh_dim_names or ()
+        d = names.index("PP") if "PP" in names else 0
+        pp_rank = device_mesh.get_local_rank(d)
+        pp_group = device_mesh.get_group(d) if device_mesh.has_groups() else None
+    pp_rank = pp_rank or 0
+    stages = PipeParser().parse(model, plan)
+    place = stage_placement(plan.num_stages, plan.virtual_chunks, plan.schedule_type)
+    mine, vmap = {}, {}
+    for v, (r, c) in enumerate(place):
+        if r == pp_rank:
+            mine[c] = stages[v]
+            vmap[c] = v
+    pm = PipeModule(mine, vmap, plan, pp_rank, pp_group)
+    # tied parameters: create one group per tie over the ranks that own a member
+    if plan.shared_modules and pp_group is not None:
+        all_names = [{n for n, _ in s.named_parameters()} for s in stages]
+        units = _units(model)
+        for tie in plan.shared_modules:
+            owners = sorted({place[v][0] for v, s in enumerate(stages) for t in tie if any(t in n or n in t for n in _stage_param_fqns(s, units))})
+            ranks = [dist.get_global_rank(pp_group, r) for r in owners] if len(owners) > 1 else None
+            grp = dist.new_group(ranks) if ranks else None
+            if grp is not None and pp_rank in owners:
+                ps = [p for c, m in mine.items() for n, p in m.named_parameters() if any(_match_tie(n, m, t) for t in tie)]
+                pm.shared_groups.append((ps, grp))
+    return pm
+
+
+def _stage_param_fqns(stage: nn.Module, units) -> List[str]:
+    if isinstance(stage, _StageSeq):
+        return [f"{un}.{pn}" for un, m in zip(stage.names, stage.mods) for pn, _ in m.named_parameters()]
+    return [n for n, _ in stage.named_parameters()]
+
+
+def _match_tie(local_name: str, stage: nn.Module, tie_fqn: str) -> bool:
+    if isinstance(stage, _StageSeq):
+        parts = local_name.split(".", 2)  # mods.<i>.<rest>
+        if len(parts) == 3 and parts[0] == "mods":
+            return f"{stage.names[int(parts[1])]}.{parts[2]}" == tie_fqn
+    return local_name == tie_fqn
