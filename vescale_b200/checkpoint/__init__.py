@@ -1,0 +1,16 @@
+"""vescale_b200.checkpoint — ``save`` / ``load`` of model + optimizer state with on-load resharding.
+
+Layout on disk is plain torch DCP (``.metadata`` + ``__{rank}_{i}.distcp``) under ``path/model`` and
+``path/optimizer`` (legacy ``vescale.checkpoint`` directory convention), produced through the DTensor
+``__create_write_items__ / __create_chunk_list__ / __get_tensor_shard__`` protocol, so RaggedShard tensors are
+saved *without communication* as a few axis-aligned boxes per rank and can be reloaded under any other
+placement, mesh shape or world size (reference ``vescale/dtensor/vescale_utils/checkpoint.py``,
+``docs/texts/raggedshard.md:93-95``).
+
+    vescale_b200.checkpoint.save(path, {"model": model, "optimizer": optimizer}, async_checkpoint=True)
+    vescale_b200.checkpoint.load(path, {"model": model, "optimizer": optimizer})
+
+Parity: ``legacy/vescale/checkpoint/__init__.py``, ``api/vescale_checkpointer.py:71-249``.
+"""
+from .api import VeScaleCheckpointer, load, save, wait_for_async  # noqa: F401
+from .pinned_pool import PinnedPool  # noqa: F401

@@ -1,0 +1,53 @@
+"""Pinned host staging pool for asynchronous checkpointing: device→host copies land in page-locked buffers
+(recycled across saves) on a side stream, so training resumes as soon as the copies are enqueued.
+Parity: ``legacy/vescale/checkpoint/utilities/mem_checkpoint.py:66-151`` (cudaHostRegister pool)."""
+from __future__ import annotations
+
+import threading
+from collections import defaultdict
+from typing import Dict, List, Tuple
+
+import torch
+
+__all__ = ["PinnedPool"]
+
+
+class PinnedPool:
+    def __init__(self):
+        self._free: Dict[Tuple[int, torch.dtype], List[torch.Tensor]] = defaultdict(list)
+        self._lock = threading.Lock()
+        self._stream = None
+        self.bytes_allocated = 0
+
+    def _get(self, numel: int, dtype) -> torch.Tensor:
+        with self._lock:
+            lst = self._free[(numel, dtype)]
+            if lst:
+                return lst.pop()
+        pin = torch.cuda.is_available()
+        t = torch.empty(numel, dtype=dtype, pin_memory=pin)
+        self.bytes_allocated += t.numel() * t.element_size()
+        return t
+
+    def release(self, t: torch.Tensor) -> None:
+        base = t._pool_base if hasattr(t, "_pool_base") else t
+        with self._lock:
+            self._free[(base.numel(), base.dtype)].append(base)
+
+    def stage(self, t: torch.Tensor) -> torch.Tensor:
+        """Asynchronous D2H of ``t`` into a pinned buffer; call ``synchronize()`` before reading."""
+        if not t.is_cuda:
+            return t.detach().clone()
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        buf = self._get(t.numel(), t.dtype)
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            view = buf.view(t.shape) if t.is_contiguous() else buf.view(-1)[: t.numel()].view(t.shape)
+            view.copy_(t.detach(), non_blocking=True)
+        view._pool_base = buf
+        return view
+
+    def synchronize(self) -> None:
+        if self._stream is not None:
+            self._stream.synchronize()
