@@ -1,1 +1,2 @@
 from .llama import LlamaConfig, LlamaModel, LlamaBlock, llama_flops_per_token  # noqa: F401
+from .mixtral import MixtralConfig, MixtralModel, MixtralBlock  # noqa: F401

@@ -1,0 +1,121 @@
+"""``parallelize_experts``: turn the expert modules of an existing model into an expert-parallel MoE.
+
+    parallelize_experts(model, experts_expr=r"layers\\.\\d+\\.moe", ep_mesh=mesh["EP"], config={...})
+
+The reference intercepts each expert's ``forward`` and ``Tensor.index_add_`` to batch all experts' work into one
+dispatch (``legacy/vescale/moe/_moe_tensor.py:42-99``); here matching ``MoELayer``s (or HF-style blocks exposing
+``gate`` + ``experts``) are rebuilt as :class:`MoELayer` over the EP group, their expert weights re-laid to the
+owning rank (``ExpertsAllocator``), and expert parameters are excluded from data-parallel gradient reduction
+across EP ranks (``param_to_ignore`` in DDP).  ``TokenDispatcher`` picks (expert, replica) per token copy.
+
+Parity: ``legacy/vescale/moe/api.py:29-49``, ``experts_allocator.py:63``, ``token_dispatcher.py:30``, ``moe_optimizer.py``.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .layer import MoEConfig, MoELayer
+
+__all__ = ["parallelize_experts", "ExpertsAllocator", "BasicExpertsAllocator", "TokenDispatcher", "BasicTokenDispatcher", "MoEOptimizer", "is_moe"]
+
+
+class ExpertsAllocator:
+    """expert id -> EP rank(s).  Replicas allow hot experts on several ranks."""
+
+    def __init__(self, num_experts: int, ep_size: int):
+        self.num_experts, self.ep_size = num_experts, ep_size
+
+    def allocate(self) -> List[List[int]]:
+        raise NotImplementedError
+
+
+class BasicExpertsAllocator(ExpertsAllocator):
+    def allocate(self) -> List[List[int]]:
+        per = self.num_experts // self.ep_size
+        return [[e // per] for e in range(self.num_experts)]
+
+
+class TokenDispatcher:
+    def dispatch_token(self, expert_id: torch.Tensor, placement: List[List[int]]) -> torch.Tensor:
+        raise NotImplementedError
+
+
+class BasicTokenDispatcher(TokenDispatcher):
+    """Random replica among the ranks hosting the expert (legacy ``token_dispatcher.py:46``)."""
+
+    def dispatch_token(self, expert_id, placement):
+        table = torch.tensor([p[0] for p in placement], device=expert_id.device)
+        return table[expert_id]
+
+
+def is_moe(module: nn.Module) -> bool:
+    return isinstance(module, MoELayer)
+
+
+def parallelize_experts(module: nn.Module, experts_expr: str = r".*moe.*", ep_mesh=None, experts_allocator: Optional[ExpertsAllocator] = None, token_dispatcher: Optional[TokenDispatcher] = None, config: Optional[Dict] = None) -> nn.Module:
+    rx = re.compile(experts_expr)
+    group = ep_mesh.get_group(0) if ep_mesh is not None and ep_mesh.has_groups() else None
+    W = dist.get_world_size(group) if group is not None else 1
+    rank = dist.get_rank(group) if group is not None else 0
+    for fqn, sub in list(module.named_modules()):
+        if not rx.fullmatch(fqn) or not isinstance(sub, MoELayer) or sub.ep_size == W:
+            continue
+        cfg = sub.cfg
+        alloc = (experts_allocator or BasicExpertsAllocator(cfg.num_experts, W)).allocate()
+        new = MoELayer(cfg, group, device=sub.router.weight.device)
+        new.router.weight.data.copy_(sub.router.weight.data)
+        mine = [e for e in range(cfg.num_experts) if rank in alloc[e]]
+        assert len(mine) == new.num_local, "allocator must give every rank E/W experts"
+        with torch.no_grad():
+            for le, e in enumerate(mine):
+                new.experts.w_gate_up[le].copy_(sub.experts.w_gate_up[e])
+                new.experts.w_down[le].copy_(sub.experts.w_down[e])
+        parent = module
+        parts = fqn.split(".")
+        for p in parts[:-1]:
+            parent = getattr(parent, p)
+        setattr(parent, parts[-1], new)
+        for p in new.experts.parameters():
+            p._is_expert_param = True
+    module._ep_group = group
+    return module
+
+
+class MoEOptimizer:
+    """Optimizer wrapper for EP models: expert grads are averaged over the *data-parallel replicas of that
+    expert* only (not over EP ranks); the grad-norm sums expert shards across EP (legacy ``moe_optimizer.py:40-107``)."""
+
+    def __init__(self, optimizer: torch.optim.Optimizer, model: nn.Module, dp_group=None, ep_group=None, clip_grad: float = 0.0):
+        self.optimizer, self.model, self.dp_group, self.ep_group, self.clip_grad = optimizer, model, dp_group, ep_group, clip_grad
+
+    def step(self):
+        dense = [p for p in self.model.parameters() if p.grad is not None and not getattr(p, "_is_expert_param", False)]
+        expert = [p for p in self.model.parameters() if p.grad is not None and getattr(p, "_is_expert_param", False)]
+        world_group = dist.group.WORLD if dist.is_initialized() else None
+        if world_group is not None and dist.get_world_size() > 1:
+            for p in dense:
+                dist.all_reduce(p.grad, group=world_group)
+                p.grad.div_(dist.get_world_size())
+            if self.dp_group is not None and dist.get_world_size(self.dp_group) > 1:
+                for p in expert:
+                    dist.all_reduce(p.grad, group=self.dp_group)
+            ep = dist.get_world_size(self.ep_group) if self.ep_group is not None else 1
+            for p in expert:  # the loss is averaged over all ranks' tokens; each expert saw tokens from every EP rank
+                p.grad.div_(dist.get_world_size())
+        if self.clip_grad > 0:
+            from ...optim.clip_grads import get_grad_norm_fp32
+
+            nd = get_grad_norm_fp32([p.grad for p in dense], 2.0)
+            ne = get_grad_norm_fp32([p.grad for p in expert], 2.0, [self.ep_group] if self.ep_group is not None else [])
+            total = (nd**2 + ne**2).sqrt()
+            coef = torch.clamp(self.clip_grad / (total + 1e-6), max=1.0)
+            torch._foreach_mul_([p.grad for p in dense + expert], coef)
+        self.optimizer.step()
+
+    def zero_grad(self, set_to_none=True):
+        self.optimizer.zero_grad(set_to_none)
