@@ -263,10 +263,11 @@ def redistribute_dtensor(dt: DTensor, device_mesh=None, placements=None, **kw) -
 
 # ------------------------------------------------------------------------------- distribute_tensor
 def _broadcast_from(tensor: torch.Tensor, mesh: DeviceMesh, src_rank: int) -> torch.Tensor:
-    flat = mesh.mesh.flatten().tolist()
-    if src_rank not in flat:
-        raise ValueError(f"src_data_rank {src_rank} is not in the mesh")
-    src_coord = [int(i) for i in torch.unravel_index(torch.tensor(flat.index(src_rank)), mesh.shape)]
+    # ``src_rank`` is the *mesh-local* rank (index into the flattened mesh), as in torch: a sub-mesh that does
+    # not contain global rank 0 still has a local rank 0
+    if not 0 <= src_rank < mesh.size():
+        raise ValueError(f"src_data_rank {src_rank} out of range for a mesh of {mesh.size()} ranks")
+    src_coord = [int(i) for i in torch.unravel_index(torch.tensor(src_rank), mesh.shape)]
     for d in range(mesh.ndim):
         C.mesh_broadcast(tensor, mesh, d, src_coord[d])
     return tensor

@@ -1,0 +1,141 @@
+"""NCCL algorithm emulation on lists of per-rank tensors (index = rank).
+
+Ring all-reduce follows ``all_reduce.h::runRing``: the buffer is processed in loops of ``nranks * chunk`` elements
+per channel; within a loop, chunk ``c`` starts its reduction at ring position ``c+1`` and is accumulated rank by
+rank around the ring, finishing at position ``c`` (so element e of chunk c is
+``(((x[c+1] + x[c+2]) + ...) + x[c])``), then the all-gather phase copies it around.  Tree all-reduce reduces up a
+binary tree (children first, then the local value) and broadcasts down.  Chunk boundaries decide which element
+falls into which chain, so ``nccl_chunking`` reproduces NCCL's split by channels / chunk size; pass the values of
+the run you compare against (``NCCL_DEBUG=INFO`` prints them; the legacy emulator reads the tuning from a graph
+dump, ``legacy/vescale/emulator/distributed.py:741-809``).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+__all__ = ["ring_all_reduce", "ring_reduce_scatter", "tree_all_reduce", "all_gather", "all_to_all", "EmulatorProcessGroup", "nccl_chunking"]
+
+
+def nccl_chunking(count: int, nranks: int, nchannels: int = 1, chunk_elems: Optional[int] = None) -> List[Tuple[int, int, int]]:
+    """[(channel, loop_offset, chunk_size)]: each entry is one ring loop covering ``nranks * chunk_size`` elements
+    (the last loop of a channel may be shorter; its chunk size shrinks, aligned to 4 elements as NCCL does for 16 B)."""
+    per_channel = (count + nchannels - 1) // nchannels
+    out = []
+    for ch in range(nchannels):
+        lo, hi = ch * per_channel, min(count, (ch + 1) * per_channel)
+        pos = lo
+        while pos < hi:
+            remaining = hi - pos
+            cs = chunk_elems if chunk_elems is not None else max(1, (remaining + nranks - 1) // nranks)
+            if remaining < nranks * cs:
+                cs = max(1, (remaining + nranks - 1) // nranks)
+                cs = (cs + 3) // 4 * 4 if remaining >= 4 * nranks else cs
+            out.append((ch, pos, cs))
+            pos += nranks * cs
+    return out
+
+
+def _op(a: torch.Tensor, b: torch.Tensor, op: str) -> torch.Tensor:
+    if op == "sum":
+        return a + b
+    if op == "max":
+        return torch.maximum(a, b)
+    if op == "min":
+        return torch.minimum(a, b)
+    if op == "product":
+        return a * b
+    raise ValueError(op)
+
+
+def ring_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum", ring: Optional[Sequence[int]] = None, nchannels: int = 1, chunk_elems: Optional[int] = None) -> List[torch.Tensor]:
+    n = len(inputs)
+    ring = list(ring) if ring is not None else list(range(n))
+    flat = [t.reshape(-1) for t in inputs]
+    count = flat[0].numel()
+    result = torch.empty_like(flat[0])
+    for _, off, cs in nccl_chunking(count, n, nchannels, chunk_elems):
+        for c in range(n):
+            lo, hi = off + c * cs, min(off + (c + 1) * cs, count)
+            if lo >= hi:
+                continue
+            acc = flat[ring[(c + 1) % n]][lo:hi].clone()
+            for j in range(2, n + 1):
+                acc = _op(acc, flat[ring[(c + j) % n]][lo:hi], op)
+            result[lo:hi] = acc
+    return [result.clone().view_as(inputs[r]) for r in range(n)]
+
+
+def ring_reduce_scatter(inputs: Sequence[torch.Tensor], op: str = "sum", ring: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
+    """``reduce_scatter.h::runRing``: rank r's output chunk r is accumulated starting at ring position r+1... and
+    finishing at r (same chain rule as the all-reduce's reduce-scatter phase)."""
+    n = len(inputs)
+    ring = list(ring) if ring is not None else list(range(n))
+    flat = [t.reshape(-1) for t in inputs]
+    per = flat[0].numel() // n
+    outs = []
+    for r in range(n):
+        lo, hi = r * per, (r + 1) * per
+        pos = ring.index(r)
+        acc = flat[ring[(pos + 1) % n]][lo:hi].clone()
+        for j in range(2, n + 1):
+            acc = _op(acc, flat[ring[(pos + j) % n]][lo:hi], op)
+        outs.append(acc)
+    return outs
+
+
+def tree_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum") -> List[torch.Tensor]:
+    """Binary-tree reduce (rank 0 root, children 2i+1 / 2i+2: child partial sums arrive first, the local value is
+    added last) followed by a broadcast."""
+    n = len(inputs)
+
+    def up(i):
+        acc = None
+        for c in (2 * i + 1, 2 * i + 2):
+            if c < n:
+                v = up(c)
+                acc = v if acc is None else _op(acc, v, op)
+        return inputs[i].clone() if acc is None else _op(acc, inputs[i], op)
+
+    total = up(0)
+    return [total.clone() for _ in range(n)]
+
+
+def all_gather(inputs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    cat = torch.cat([t.reshape(-1) for t in inputs])
+    return [cat.clone() for _ in inputs]
+
+
+def all_to_all(inputs: Sequence[Sequence[torch.Tensor]]) -> List[List[torch.Tensor]]:
+    n = len(inputs)
+    return [[inputs[src][dst].clone() for src in range(n)] for dst in range(n)]
+
+
+class EmulatorProcessGroup:
+    """Global-view process group: every call takes / returns one tensor per rank (legacy ``emulator/distributed.py``)."""
+
+    def __init__(self, world_size: int, algo: str = "ring", nchannels: int = 1, chunk_elems: Optional[int] = None, ring: Optional[Sequence[int]] = None):
+        self.world_size, self.algo, self.nchannels, self.chunk_elems, self.ring = world_size, algo, nchannels, chunk_elems, ring
+
+    def size(self) -> int:
+        return self.world_size
+
+    def all_reduce(self, tensors: Sequence[torch.Tensor], op: str = "sum") -> List[torch.Tensor]:
+        assert len(tensors) == self.world_size
+        if self.algo == "tree":
+            return tree_all_reduce(tensors, op)
+        return ring_all_reduce(tensors, op, self.ring, self.nchannels, self.chunk_elems)
+
+    def reduce_scatter(self, tensors, op: str = "sum"):
+        return ring_reduce_scatter(tensors, op, self.ring)
+
+    def all_gather(self, tensors):
+        return all_gather(tensors)
+
+    def all_to_all(self, tensors):
+        return all_to_all(tensors)
+
+    def broadcast(self, tensors, src: int = 0):
+        return [tensors[src].clone() for _ in tensors]

@@ -1,0 +1,96 @@
+"""Global-view DTensor API on lists of local tensors (one per rank), using the emulated collectives for every
+reduction so the result has real-NCCL summation order (legacy ``emulator/comm_api.py``, ``mesh_collectives.py``)."""
+from __future__ import annotations
+
+import itertools
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from ..layout import compute_local_shape_and_global_offset, local_boxes
+from ..mesh import DeviceMesh
+from ..placement import Partial, Placement, Replicate, Shard
+from .collectives import EmulatorProcessGroup
+
+__all__ = ["distribute_tensor", "redistribute_dtensor", "full_tensor", "mesh_all_reduce", "mesh_all_gather", "mesh_reduce_scatter"]
+
+
+def _coords(mesh: DeviceMesh):
+    return list(itertools.product(*[range(s) for s in mesh.shape]))
+
+
+def _rank_of(mesh: DeviceMesh, coord) -> int:
+    return int(mesh.mesh[tuple(coord)])
+
+
+def _groups_along(mesh: DeviceMesh, mesh_dim: int) -> List[List[int]]:
+    return [list(r) for r in mesh._ranks_along(mesh_dim)]
+
+
+def distribute_tensor(tensor: torch.Tensor, mesh: DeviceMesh, placements: Sequence[Placement]) -> List[torch.Tensor]:
+    """Full tensor -> list of local shards indexed by global rank."""
+    from ..dtensor.api import slice_local
+
+    out: List[Optional[torch.Tensor]] = [None] * mesh.size()
+    for c in _coords(mesh):
+        out[_rank_of(mesh, c)] = slice_local(tensor, mesh, tuple(placements), c)
+    return out
+
+
+def mesh_all_reduce(locals_: List[torch.Tensor], mesh: DeviceMesh, mesh_dim: int, op: str = "sum", pg_kw: Optional[dict] = None) -> List[torch.Tensor]:
+    out = list(locals_)
+    for ranks in _groups_along(mesh, mesh_dim):
+        pg = EmulatorProcessGroup(len(ranks), **(pg_kw or {}))
+        red = pg.all_reduce([locals_[r] for r in ranks], op)
+        for r, t in zip(ranks, red):
+            out[r] = t
+    return out
+
+
+def mesh_all_gather(locals_, mesh, mesh_dim, gather_dim: int = 0):
+    out = list(locals_)
+    for ranks in _groups_along(mesh, mesh_dim):
+        cat = torch.cat([locals_[r] for r in ranks], dim=gather_dim)
+        for r in ranks:
+            out[r] = cat.clone()
+    return out
+
+
+def mesh_reduce_scatter(locals_, mesh, mesh_dim, scatter_dim: int = 0, op: str = "sum", pg_kw=None):
+    red = mesh_all_reduce(locals_, mesh, mesh_dim, op, pg_kw)
+    out = list(red)
+    for ranks in _groups_along(mesh, mesh_dim):
+        for i, r in enumerate(ranks):
+            out[r] = red[r].chunk(len(ranks), dim=scatter_dim)[i].clone()
+    return out
+
+
+def full_tensor(locals_: List[torch.Tensor], shape: Sequence[int], mesh: DeviceMesh, placements: Sequence[Placement], pg_kw=None) -> torch.Tensor:
+    """Reassemble the global tensor; Partial mesh dims are reduced with the emulated all-reduce."""
+    cur = list(locals_)
+    pl = list(placements)
+    for i, p in enumerate(pl):
+        if p.is_partial():
+            cur = mesh_all_reduce(cur, mesh, i, p.reduce_op, pg_kw)
+            pl[i] = Replicate()
+    out = torch.zeros(tuple(shape), dtype=cur[0].dtype)
+    for c in _coords(mesh):
+        r = _rank_of(mesh, c)
+        boxes = local_boxes(tuple(shape), mesh, tuple(pl), c)
+        ragged = any(getattr(p, "is_ragged_shard", lambda: False)() for p in pl)
+        for off, sz, loc in boxes:
+            sl = tuple(slice(o, o + n) for o, n in zip(off, sz))
+            if ragged:
+                out[sl] = cur[r].reshape(-1)[loc[0] : loc[0] + math.prod(sz)].view(sz)
+            else:
+                t = cur[r]
+                for d, (o, n) in enumerate(zip(loc, sz)):
+                    t = t.narrow(d, o, n)
+                out[sl] = t
+    return out
+
+
+def redistribute_dtensor(locals_: List[torch.Tensor], shape: Sequence[int], mesh: DeviceMesh, src: Sequence[Placement], dst: Sequence[Placement], pg_kw=None) -> List[torch.Tensor]:
+    full = full_tensor(locals_, shape, mesh, src, pg_kw)
+    return distribute_tensor(full, mesh, dst)

@@ -1,0 +1,60 @@
+"""VocabParallelCrossEntropy: Megatron's algorithm on vocab-sharded logits with label smoothing
+(legacy ``model/patch/vp_cross_entropy.py:43-147``): local max → AR(MAX); masked target logit → AR(SUM);
+local sum-exp → AR(SUM).  ``loss_parallel`` is the DTensor-dispatch route to the same math."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ...comm import collectives as C
+from ...dtensor.api import DTensor
+from ...layout import compute_local_shape_and_global_offset
+from ...placement import Shard
+
+
+class _VPCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits_local, target, mesh, mesh_dim, vocab_start, label_smoothing, vocab_size):
+        lmax = logits_local.amax(-1)
+        gmax = C.mesh_all_reduce(lmax, mesh, "max", mesh_dim)
+        x = logits_local.float() - gmax.unsqueeze(-1)
+        n = x.shape[-1]
+        mask = (target < vocab_start) | (target >= vocab_start + n)
+        idx = (target - vocab_start).masked_fill(mask, 0)
+        picked = x.gather(-1, idx.unsqueeze(-1)).squeeze(-1).masked_fill(mask, 0.0)
+        picked = C.mesh_all_reduce(picked, mesh, "sum", mesh_dim)
+        ex = x.exp()
+        sumexp = C.mesh_all_reduce(ex.sum(-1), mesh, "sum", mesh_dim)
+        loss = sumexp.log() - picked
+        softmax = ex / sumexp.unsqueeze(-1)
+        if label_smoothing > 0:
+            s = label_smoothing * vocab_size / (vocab_size - 1)
+            mean_logp = C.mesh_all_reduce((x - sumexp.log().unsqueeze(-1)).sum(-1), mesh, "sum", mesh_dim) / vocab_size
+            loss = (1 - s) * loss - s * mean_logp
+        ctx.save_for_backward(softmax, mask, idx)
+        ctx.ls, ctx.V = label_smoothing, vocab_size
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        softmax, mask, idx = ctx.saved_tensors
+        grad = softmax.clone()
+        upd = (~mask).to(grad.dtype)
+        if ctx.ls > 0:
+            s = ctx.ls * ctx.V / (ctx.V - 1)
+            grad.scatter_add_(-1, idx.unsqueeze(-1), -(1 - s) * upd.unsqueeze(-1))
+            grad -= s / ctx.V
+        else:
+            grad.scatter_add_(-1, idx.unsqueeze(-1), -upd.unsqueeze(-1))
+        return grad * g.unsqueeze(-1), None, None, None, None, None, None
+
+
+class VocabParallelCrossEntropy:
+    @staticmethod
+    def apply(logits: DTensor, target, label_smoothing: float = 0.0) -> torch.Tensor:
+        """``logits``: DTensor sharded on the last (vocab) dim; ``target``: replicated tensor/DTensor. Per-token loss."""
+        mesh = logits.device_mesh
+        md = next(i for i, p in enumerate(logits.placements) if isinstance(p, Shard) and p.dim == logits.ndim - 1)
+        _, off = compute_local_shape_and_global_offset(logits.shape, mesh, logits.placements)
+        t = target._local_tensor if isinstance(target, DTensor) else target
+        return _VPCE.apply(logits.to_local(), t, mesh, md, off[-1], label_smoothing, logits.shape[-1])

@@ -1,0 +1,63 @@
+"""Record handlers: chrome/perfetto trace, raw dump, parser (aggregate stats), logging."""
+from __future__ import annotations
+
+import json
+import logging
+import os
+from collections import defaultdict
+from typing import Dict, List
+
+
+class NDHandler:
+    def __call__(self, records: List[dict], rank: int, step: int) -> None:
+        raise NotImplementedError
+
+
+class ChromeTraceNDHandler(NDHandler):
+    """One ``chrome://tracing`` / perfetto JSON per rank; timestamps are on the aligned global clock, so files
+    from all ranks can be concatenated into one timeline (legacy ``handlers/chrome_trace_event.py``)."""
+
+    def __init__(self, out_dir: str = ".", prefix: str = "ndtimeline"):
+        self.out_dir, self.prefix = out_dir, prefix
+        self.events: List[dict] = []
+
+    def __call__(self, records, rank, step):
+        for r in records:
+            self.events.append({"name": r["metric"], "ph": "X", "ts": r["start_us"], "dur": r["duration_us"], "pid": rank, "tid": r.get("stream", 0), "args": {"step": step, **r.get("tags", {})}})
+        os.makedirs(self.out_dir, exist_ok=True)
+        with open(os.path.join(self.out_dir, f"{self.prefix}_rank{rank}.json"), "w") as f:
+            json.dump({"traceEvents": self.events}, f)
+
+
+class LocalRawNDHandler(NDHandler):
+    def __init__(self, path: str):
+        self.path = path
+
+    def __call__(self, records, rank, step):
+        with open(f"{self.path}.rank{rank}", "a") as f:
+            for r in records:
+                f.write(json.dumps({"rank": rank, "step": step, **r}) + "\n")
+
+
+class ParserNDHandler(NDHandler):
+    """Aggregates per-metric count / total / mean durations (legacy ``handlers/parser_handler.py``)."""
+
+    def __init__(self):
+        self.stats: Dict[str, List[float]] = defaultdict(list)
+
+    def __call__(self, records, rank, step):
+        for r in records:
+            self.stats[r["metric"]].append(r["duration_us"])
+
+    def summary(self) -> Dict[str, dict]:
+        return {k: {"count": len(v), "total_us": sum(v), "mean_us": sum(v) / len(v)} for k, v in self.stats.items()}
+
+
+class LoggingNDHandler(NDHandler):
+    def __init__(self, logger=None, level=logging.INFO):
+        self.logger = logger or logging.getLogger("vescale_b200.ndtimeline")
+        self.level = level
+
+    def __call__(self, records, rank, step):
+        for r in records:
+            self.logger.log(self.level, "[rank %d step %d] %s: %.1f us", rank, step, r["metric"], r["duration_us"])
