@@ -228,6 +228,7 @@ _AUTO_WRAP_OPS = {
     aten._index_put_impl_.default,
     aten.index.Tensor,
     aten.eq.Tensor,
+    aten.embedding.default,
     aten.scatter.src,
     aten.scatter_.src,
 }

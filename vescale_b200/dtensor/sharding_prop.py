@@ -21,6 +21,7 @@ from .op_schema import OpSchema, OutputSharding, RuleResult
 __all__ = ["ShardingPropagator", "register_rule", "get_rule", "propagator"]
 
 _RULES: Dict[Any, Callable[[OpSchema], RuleResult]] = {}
+IN_META_PROPAGATION = [0]  # re-entrancy guard consulted by DModule's factory mode
 
 
 def register_rule(ops, fn: Optional[Callable] = None):
@@ -81,11 +82,15 @@ class ShardingPropagator:
         kwargs = {k: _to_meta(v) for k, v in schema.kwargs_schema.items()}
         if "device" in kwargs and kwargs["device"] is not None:
             kwargs["device"] = torch.device("meta")
+        IN_META_PROPAGATION[0] += 1
         try:
             with torch.no_grad():
                 out = schema.op(*args, **kwargs)
-        except Exception:
+        except Exception as e:  # noqa: BLE001
+            self.last_meta_error = f"{type(e).__name__}: {e}"
             return None
+        finally:
+            IN_META_PROPAGATION[0] -= 1
         return _collect_meta(out)
 
     # ------------------------------------------------------------------ propagate
@@ -139,7 +144,10 @@ class ShardingPropagator:
                 out_spec = tuple(mk(out, m) for m in metas)
             else:
                 if metas is None:
-                    raise RuntimeError(f"cannot infer output metadata of {schema.op} on the meta device; the rule must return specs")
+                    raise RuntimeError(
+                        f"cannot infer output metadata of {schema.op} on the meta device ({getattr(self, 'last_meta_error', '?')}); "
+                        f"inputs: {[(tuple(s.shape), s.placements) for s in in_specs]}"
+                    )
                 out_spec = mk(out, metas)
 
         redis = None

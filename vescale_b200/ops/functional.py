@@ -383,12 +383,11 @@ class _PackedAttention(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, do):
-        q, k, v, o = ctx.graph
-        ctx.graph = None
+        q, k, v, o = ctx.graph  # kept: the node may run again over a retained graph (zero-bubble W pass)
         n_q, n_kv, head_dim, _ = ctx.cfg
         B, S = do.shape[0], do.shape[1]
         do4 = do.view(B, S, n_q, head_dim).transpose(1, 2)
-        dq, dk, dv = torch.autograd.grad(o, (q, k, v), do4)
+        dq, dk, dv = torch.autograd.grad(o, (q, k, v), do4, retain_graph=True)
         dqkv = torch.cat(
             [dq.transpose(1, 2).reshape(B, S, -1), dk.transpose(1, 2).reshape(B, S, -1), dv.transpose(1, 2).reshape(B, S, -1)], dim=-1
         )
@@ -433,9 +432,13 @@ class _CrossEntropy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         grad = ctx.grad_buf
-        ctx.grad_buf = None
-        # dloss is 1.0 in ordinary training; the in-place scale keeps the 2 GB buffer single
-        return grad.mul_(dloss.to(grad.dtype)), None, None
+        # dloss is 1.0 in ordinary training; the in-place scale keeps the 2 GB buffer single.  The node may
+        # run twice (zero-bubble pipeline: input-gradient pass, then weight-gradient pass over the retained
+        # graph) — scale once only.
+        if not getattr(ctx, "scaled", False):
+            grad.mul_(dloss.to(grad.dtype))
+            ctx.scaled = True
+        return grad, None, None
 
 
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:

@@ -194,8 +194,12 @@ class DistributedDataParallel(nn.Module):
             if g is None:
                 return
             if isinstance(g, DTensor):
-                # model-parallel Partial grads (SP) are reduced on their own mesh right away
-                if any(pl.is_partial() for pl in g.placements):
+                # bring the gradient to the parameter's own layout on the model-parallel mesh: Partial grads
+                # (SP norm weights, vocab-parallel embeddings) are reduced right away, as legacy does
+                want = param.placements if isinstance(param, DTensor) else getattr(param.data, "placements", None)
+                if want is not None and g.placements != want:
+                    g = g.redistribute(g.device_mesh, want)
+                elif any(pl.is_partial() for pl in g.placements):
                     from ..placement import Replicate
 
                     g = g.redistribute(g.device_mesh, [Replicate() if pl.is_partial() else pl for pl in g.placements])

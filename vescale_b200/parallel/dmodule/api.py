@@ -229,10 +229,15 @@ def _factory_mode(mesh: DeviceMesh):
     """Inside forward, plain factory calls build replicated DTensors (legacy ``_factory.py:57-117``)."""
     saved = {n: getattr(torch, n) for n in _FACTORY_FNS}
 
+    from ...dtensor import sharding_prop as _sp
+
     def wrap(fn):
         def f(*a, **kw):
             t = fn(*a, **kw)
-            return DTensor.from_local(t, mesh, [Replicate()] * mesh.ndim) if isinstance(t, torch.Tensor) and not isinstance(t, DTensor) else t
+            # never inside the dispatcher's own meta-shape inference, never for meta tensors
+            if _sp.IN_META_PROPAGATION[0] or not isinstance(t, torch.Tensor) or isinstance(t, DTensor) or t.is_meta:
+                return t
+            return DTensor.from_local(t, mesh, [Replicate()] * mesh.ndim)
 
         return f
 
