@@ -30,6 +30,12 @@ void symm_rs_adamw(std::vector<int64_t> grad_ptrs, at::Tensor master, at::Tensor
                    const at::Tensor& coef, c10::optional<at::Tensor> sumsq, int64_t rank, double scale, std::vector<int64_t> pad_ptrs, int64_t slot,
                    int64_t epoch, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, int64_t num_ctas);
 
+// gemm_fused_tp.cu
+void ag_gemm(const at::Tensor& x_local, std::vector<int64_t> x_ptrs, const at::Tensor& w, at::Tensor x_full, at::Tensor y, at::Tensor arrive,
+             std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch);
+void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector<int64_t> staging_ptrs, at::Tensor done, std::vector<int64_t> flag_ptrs,
+             int64_t rank, int64_t epoch);
+
 TORCH_LIBRARY(vescale_b200, m) {
   m.def("rms_norm_fwd(Tensor x, Tensor w, float eps) -> (Tensor, Tensor)");
   m.def("add_rms_norm_fwd(Tensor a, Tensor b, Tensor w, float eps) -> (Tensor, Tensor, Tensor)");
@@ -42,6 +48,8 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("sumsq_accumulate(Tensor g, Tensor(a!) out, float scale) -> ()");
   m.def("fused_adamw_(Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor(d!) p_out, Tensor wd_table, Tensor coef, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) -> ()");
   m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate, int variant=0) -> ()");
+  m.def("ag_gemm(Tensor x_local, int[] x_ptrs, Tensor w, Tensor(a!) x_full, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch) -> ()");
+  m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
   m.def("symm_wait(int my_pad, int world, int slot, int epoch) -> ()", &symm_wait);
   m.def("symm_all_gather(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int num_ctas) -> ()");
@@ -61,6 +69,8 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("sumsq_accumulate", &sumsq_accumulate);
   m.impl("fused_adamw_", &fused_adamw_);
   m.impl("gemm_nt", &gemm_nt);
+  m.impl("ag_gemm", &ag_gemm);
+  m.impl("gemm_rs", &gemm_rs);
   m.impl("symm_all_gather", &symm_all_gather);
   m.impl("symm_reduce_scatter", &symm_reduce_scatter);
   m.impl("symm_rs_adamw", &symm_rs_adamw);

@@ -109,3 +109,68 @@ def test_symm_collectives_match_nccl():
 
 def test_fsdp_symm_matches_nccl():
     run_distributed(_fsdp_backends, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+def _fused_tp(rank, world):
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.comm.fused_tp import FusedTP
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    dev = torch.device("cuda", rank)
+    mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("TP",))
+    tp = FusedTP(mesh, "TP", dev)
+    g = torch.Generator(device=dev)
+    for (Ml, K, Nr) in ((256, 512, 256), (1024, 4096, 3072 // world * 2), (512, 1024, 264)):
+        M = Ml * world
+        for it in range(3):
+            g.manual_seed(1000 * it + rank)
+            x_local = (torch.randn(Ml, K, device=dev, generator=g) * 0.5).bfloat16()
+            w = (torch.randn(Nr, K, device=dev, generator=g) * 0.05).bfloat16()
+            xs = [torch.empty_like(x_local) for _ in range(world)]
+            dist.all_gather(xs, x_local)
+            ref = torch.cat(xs).float() @ w.float().t()
+            y, x_full = tp.ag_gemm(x_local, w)
+            torch.cuda.synchronize()
+            assert torch.equal(x_full, torch.cat(xs)), f"ag_gemm gathered buffer mismatch {Ml,K,Nr} it{it}"
+            err = (y.float() - ref).abs().max().item()
+            assert err < 0.02 * ref.abs().max().item() + 0.05, ("ag_gemm", Ml, K, Nr, it, err)
+    for (M, Kr, N) in ((256 * world, 512, 256), (2048 * world // 2, 2048, 4096), (512 * world, 1024, 264)):
+        for it in range(3):
+            g.manual_seed(77 * it + rank)
+            x = (torch.randn(M, Kr, device=dev, generator=g) * 0.5).bfloat16()
+            w = (torch.randn(N, Kr, device=dev, generator=g) * 0.05).bfloat16()
+            part = (x.float() @ w.float().t())
+            tot = part.clone()
+            dist.all_reduce(tot)
+            ref = tot[rank * (M // world) : (rank + 1) * (M // world)]
+            y = tp.gemm_rs(x, w)
+            torch.cuda.synchronize()
+            err = (y.float() - ref).abs().max().item()
+            assert err < 0.03 * ref.abs().max().item() + 0.05, ("gemm_rs", M, Kr, N, it, err)
+            dist.barrier()
+    # autograd: column-parallel then row-parallel MLP under SP equals the single-device MLP
+    H, F, Ml = 512, 1024, 256
+    g.manual_seed(5)
+    w1 = (torch.randn(F, H, device=dev, generator=g) * 0.05).bfloat16()
+    w2 = (torch.randn(H, F, device=dev, generator=g) * 0.05).bfloat16()
+    g.manual_seed(100 + rank)
+    x_local = torch.randn(Ml, H, device=dev, generator=g).bfloat16().requires_grad_()
+    w1s = w1[rank * F // world : (rank + 1) * F // world].clone().requires_grad_()
+    w2s = w2[:, rank * F // world : (rank + 1) * F // world].clone().requires_grad_()
+    out = tp.linear_rs(torch.relu(tp.ag_linear(x_local, w1s)), w2s)
+    out.float().pow(2).sum().backward()
+    xs = [torch.empty_like(x_local) for _ in range(world)]
+    dist.all_gather(xs, x_local.detach())
+    xf = torch.cat(xs).float().requires_grad_()
+    w1f, w2f = w1.float().requires_grad_(), w2.float().requires_grad_()
+    ref = torch.relu(xf @ w1f.t()) @ w2f.t()
+    ref.pow(2).sum().backward()
+    sl = slice(rank * Ml, (rank + 1) * Ml)
+    assert (out.float() - ref[sl]).abs().max().item() < 0.05 * ref.abs().max().item() + 0.05
+    assert (x_local.grad.float() - xf.grad[sl]).abs().max().item() < 0.08 * xf.grad.abs().max().item() + 0.05
+    assert (w1s.grad.float() - w1f.grad[rank * F // world : (rank + 1) * F // world]).abs().max().item() < 0.08 * w1f.grad.abs().max().item() + 0.05
+
+
+def test_fused_tp_kernels():
+    run_distributed(_fused_tp, min(torch.cuda.device_count(), 8), backend="nccl")
