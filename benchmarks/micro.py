@@ -67,6 +67,17 @@ def main():
         r = {"M": M, "N": N, "K": K, "tcgen05_1cta_ms": t_v1, "tcgen05_2cta_ms": t_ours, "cublas_ms": t_lib, "tcgen05_1cta_tflops": fl / t_v1 / 1e9,
              "tcgen05_2cta_tflops": fl / t_ours / 1e9, "cublas_tflops": fl / t_lib / 1e9,
              "frac_of_measured_burst": fl / t_ours / 1e9 / peaks["bf16_tflops"]}
+        # backward shapes of the same linear layer: dgrad [M,N]x[N,K] and wgrad [M,N]^T x [M,K]
+        if hasattr(ops, "gemm_nn") and N <= 32768:
+            dy = torch.randn(M, N, device=dev).bfloat16()
+            dx = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+            dw = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
+            t1, _ = timeit(lambda: ops.gemm_nn(dy, b, dx), flush=flush)
+            t1l, _ = timeit(lambda: torch.mm(dy, b, out=dx), flush=flush)
+            t2, _ = timeit(lambda: ops.gemm_tn(dy, a, dw, False), flush=flush)
+            t2l, _ = timeit(lambda: torch.mm(dy.t(), a, out=dw), flush=flush)
+            r.update(dgrad_tcgen05_tflops=fl / t1 / 1e9, dgrad_cublas_tflops=fl / t1l / 1e9, wgrad_tcgen05_tflops=fl / t2 / 1e9, wgrad_cublas_tflops=fl / t2l / 1e9)
+            del dy, dx, dw
         res["gemm"].append(r)
         print(r, flush=True)
         del a, b, c

@@ -18,6 +18,8 @@ void fused_adamw_(at::Tensor master, at::Tensor m, at::Tensor v, const at::Tenso
                   const at::Tensor& coef, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, double gscale);
 // gemm_sm100.cu
 void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate, int64_t variant);
+void gemm_nn(const at::Tensor& a, const at::Tensor& b, at::Tensor c);
+void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate);
 
 // symm_comm.cu
 void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch);
@@ -48,6 +50,8 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("sumsq_accumulate(Tensor g, Tensor(a!) out, float scale) -> ()");
   m.def("fused_adamw_(Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor(d!) p_out, Tensor wd_table, Tensor coef, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) -> ()");
   m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate, int variant=0) -> ()");
+  m.def("gemm_nn(Tensor a, Tensor b, Tensor(a!) c) -> ()");
+  m.def("gemm_tn(Tensor a, Tensor b, Tensor(a!) c, bool accumulate) -> ()");
   m.def("ag_gemm(Tensor x_local, int[] x_ptrs, Tensor w, Tensor(a!) x_full, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
@@ -69,6 +73,8 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("sumsq_accumulate", &sumsq_accumulate);
   m.impl("fused_adamw_", &fused_adamw_);
   m.impl("gemm_nt", &gemm_nt);
+  m.impl("gemm_nn", &gemm_nn);
+  m.impl("gemm_tn", &gemm_tn);
   m.impl("ag_gemm", &ag_gemm);
   m.impl("gemm_rs", &gemm_rs);
   m.impl("symm_all_gather", &symm_all_gather);

@@ -212,6 +212,22 @@ VB_DEVICE uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                              // [61,64) layout type = SWIZZLE_128B
   return d;
 }
+// MN-major operand tile (the MMA's M/N dimension is the contiguous one in global memory, e.g. W[K_contract, N_out]):
+// TMA boxes of [64 k-rows x 64 mn-elements] (128 B rows, 128B swizzle) are laid side by side, 8 KB apart.
+// Canonical form (CUTLASS make_umma_desc<Major::MN>, B128): ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units,
+// i.e. LBO = distance between consecutive 64-element MN groups (8192 B), SBO = distance between 8-row k groups (1024 B).
+VB_DEVICE uint64_t make_sw128_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+VB_DEVICE constexpr uint32_t make_idesc_bf16_major(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // instruction descriptor, kind::f16, bf16 x bf16 -> fp32, both operands K-major
 VB_DEVICE constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4)                 // c_format = F32
@@ -225,6 +241,26 @@ VB_DEVICE constexpr uint32_t make_idesc_e4m3(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
+// ---- coalesced epilogue: 32 rows x 64 bf16 columns per warp go through a 4 KB swizzled smem buffer and leave as
+// ONE TMA store (128-byte row segments; out-of-bounds rows/columns are clipped by the tensor map).  `lo`/`hi`
+// hold the fp32 accumulators of columns [0,32) and [32,64) of this lane's row.
+VB_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+VB_DEVICE uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+VB_DEVICE void epi_write_row_swizzled(uint8_t* buf, int lane, const float* v /*64 values*/) {
+  const uint32_t base = smem_u32(buf) + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float* f = v + j * 8;
+    st_shared_v4(base + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                 pack_bf16x2(f[6], f[7]));
+  }
+}
 
 // ---- cluster / CTA-pair (cta_group::2) helpers
 VB_DEVICE uint32_t cluster_ctarank() {

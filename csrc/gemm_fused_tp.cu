@@ -35,6 +35,7 @@ constexpr int STAGES = 5;                  // 160 KB ring + 32 KB copy staging
 constexpr int kCopyRows = 32, kCopyCols = 256;
 constexpr int kCopyBytes = kCopyRows * kCopyCols * 2;  // 16 KB box
 constexpr int kCopySlots = 2;
+constexpr int kEpiBytes = 4 * 2 * 4096;
 
 struct TmapArray {
   CUtensorMap m[kMaxW];
@@ -85,14 +86,15 @@ struct FusedArgs {
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a_local, const __grid_constant__ CUtensorMap tma_b,
-                const __grid_constant__ TmapArray peer_x, const __grid_constant__ CUtensorMap tma_full_store, __nv_bfloat16* __restrict__ C,
-                const FusedArgs fa) {
+                const __grid_constant__ TmapArray peer_x, const __grid_constant__ CUtensorMap tma_full_store, const __grid_constant__ CUtensorMap tma_c,
+                __nv_bfloat16* __restrict__ C, const FusedArgs fa) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * kABytes;
   uint8_t* smem_copy = smem + STAGES * kStage;  // kCopySlots x 16 KB
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_copy + kCopySlots * kCopyBytes);
+  uint8_t* smem_epi = smem_copy + kCopySlots * kCopyBytes;  // 4 warps x 2 buffers x 4 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -272,42 +274,65 @@ fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           peers_done = true;
         }
       }
-      __nv_bfloat16* crow;
+      // destination of this warp's 32 rows: my output, or the owner's staging slot [rank] (peer memory, TMA store)
+      const CUtensorMap* omap = &tma_c;
+      int orow = m0 + ew * 32;
       if (MODE == 2) {
-        const int lrow = row - owner * rows_per_rank;
-        if (owner == rank)
-          crow = C + (size_t)lrow * fa.ldc + n0;
-        else
-          crow = reinterpret_cast<__nv_bfloat16*>(fa.staging.p[owner]) + ((size_t)rank * rows_per_rank + lrow) * N + n0;
-      } else {
-        crow = C + (size_t)row * fa.ldc + n0;
+        const int lrow0 = orow - owner * rows_per_rank;
+        if (owner == rank) {
+          orow = lrow0;
+        } else {
+          omap = &peer_x.m[owner];
+          orow = rank * rows_per_rank + lrow0;
+        }
       }
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 32, r);
-        tmem_ld_wait();
+      for (int c = 0; c < kBN / 64; ++c) {
+        float v[64];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 64, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int col = n0 + c * 32 + q * 8;
-          if (col < N) {
-            float f[8];
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 64 + 32, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
-            if (MODE == 2 && owner == rank) {
-              const int lrow = row - rank * rows_per_rank;
-              const __nv_bfloat16* st = reinterpret_cast<const __nv_bfloat16*>(fa.staging.p[rank]);
-              for (int p = 0; p < W; ++p) {
-                if (p == rank) continue;
+          for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
+        }
+        if (MODE == 2 && owner == rank) {
+          // add the partial sums the peers pushed into my staging slots (fp32 accumulate)
+          const int lrow = row - rank * rows_per_rank;
+          const __nv_bfloat16* st = reinterpret_cast<const __nv_bfloat16*>(fa.staging.p[rank]);
+          for (int p = 0; p < W; ++p) {
+            if (p == rank) continue;
+            const __nv_bfloat16* src = st + ((size_t)p * rows_per_rank + lrow) * N + n0 + c * 64;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (n0 + c * 64 + q * 8 < N) {
                 float o[8];
-                unpack8(ld8(st + ((size_t)p * rows_per_rank + lrow) * N + col), o);
+                unpack8(ld8(src + q * 8), o);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] += o[i];
+                for (int i = 0; i < 8; ++i) v[q * 8 + i] += o[i];
               }
             }
-            st8(crow + c * 32 + q * 8, pack8(f));
           }
         }
+        uint8_t* buf = smem_epi + (ew * 2 + (c & 1)) * 4096;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        epi_write_row_swizzled(buf, lane, v);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && n0 + c * 64 < N) {
+          tma_store_2d(omap, buf, n0 + c * 64, orow);
+          tma_store_commit();
+        }
+      }
+      if (MODE == 2 && owner != rank) {
+        // the partial rows must have landed in the peer's memory before they are counted
+        if (lane == 0) tma_store_wait<0>();
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive_cluster(mapa(smem_u32(&tempty_bar[as]), 0));
@@ -329,6 +354,7 @@ fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
     }
   }
+  if (warp >= 4 && lane == 0) tma_store_wait<0>();
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) {
@@ -337,7 +363,7 @@ fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   }
 }
 
-int fused_smem_bytes() { return STAGES * kStage + kCopySlots * kCopyBytes + (2 * STAGES + 4 + kCopySlots) * 8 + 16 + 1024; }
+int fused_smem_bytes() { return STAGES * kStage + kCopySlots * kCopyBytes + kEpiBytes + (2 * STAGES + 4 + kCopySlots) * 8 + 16 + 1024; }
 
 PtrArray to_ptr_array(const std::vector<int64_t>& v) {
   PtrArray a{};
@@ -378,7 +404,8 @@ void ag_gemm(const at::Tensor& x_local, std::vector<int64_t> x_ptrs, const at::T
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   const int tiles = (M / (2 * kBM)) * ((Nr + kBN - 1) / kBN);
   const int pairs = std::max(1, std::min(sms / 2, tiles));
-  fused_tp_kernel<1><<<pairs * 2, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, tal, tb, px, tst, (__nv_bfloat16*)y.data_ptr(), fa);
+  const CUtensorMap tcy = make_tmap_2d(y.data_ptr(), M, Nr, y.stride(0) * 2, 32, 64, 2, true);
+  fused_tp_kernel<1><<<pairs * 2, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, tal, tb, px, tst, tcy, (__nv_bfloat16*)y.data_ptr(), fa);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -394,7 +421,8 @@ void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector
   c10::cuda::CUDAGuard guard(x.device());
   const CUtensorMap ta = make_tmap_2d(x.data_ptr(), M, K, x.stride(0) * 2, kBM, kBK, 2, true);
   const CUtensorMap tb = make_tmap_2d(w.data_ptr(), N, K, w.stride(0) * 2, kBN / 2, kBK, 2, true);
-  TmapArray px{};
+  TmapArray px{};  // store maps over every peer's staging buffer viewed as [W * M/W, N]
+  for (int p = 0; p < W; ++p) px.m[p] = make_tmap_2d(reinterpret_cast<void*>(staging_ptrs[p]), M, N, N * 2, 32, 64, 2, true);
   FusedArgs fa{};
   fa.M = M, fa.N = N, fa.K = K, fa.ldc = y.stride(0), fa.world = W, fa.rank = rank, fa.epoch = (uint32_t)epoch;
   fa.done = reinterpret_cast<uint32_t*>(done.data_ptr<int>());
@@ -409,6 +437,7 @@ void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   const int tiles = (M / (2 * kBM)) * ((N + kBN - 1) / kBN);
   const int pairs = std::max(1, std::min(sms / 2, tiles));
-  fused_tp_kernel<2><<<pairs * 2, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, ta, tb, px, ta, (__nv_bfloat16*)y.data_ptr(), fa);
+  const CUtensorMap tcy = make_tmap_2d(y.data_ptr(), M / W, N, y.stride(0) * 2, 32, 64, 2, true);
+  fused_tp_kernel<2><<<pairs * 2, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, ta, tb, px, ta, tcy, (__nv_bfloat16*)y.data_ptr(), fa);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

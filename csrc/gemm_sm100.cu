@@ -217,16 +217,18 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // to both CTAs' barriers; both CTAs' epilogues drain their own 128 TMEM lanes.
 constexpr int kB2Bytes = (kBN / 2) * kBK * 2;  // half B tile per CTA
 constexpr int kStage2 = kABytes + kB2Bytes;    // 32 KB
+constexpr int kEpiBytes = 4 * 2 * 4096;         // epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B)
 
-template <int STAGES>
+template <int STAGES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, __nv_bfloat16* __restrict__ C, int M,
-                    int N, int K, int ldc, int accumulate, int group_m) {
+gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
+                    __nv_bfloat16* __restrict__ C, int M, int N, int K, int ldc, int accumulate, int group_m) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage2);
+  uint8_t* smem_epi = smem + STAGES * kStage2;  // 4 warps x 2 buffers x 4 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -291,8 +293,18 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&empty_bar[s], ph ^ 1);
           const uint32_t full_leader = mapa(smem_u32(&full_bar[s]), 0);
           if (leader) mbar_expect_tx(&full_bar[s], 2 * kStage2);
-          tma_load_2d_2sm(smem_a + s * kABytes, &tma_a, full_leader, kb * kBK, m0);
-          tma_load_2d_2sm(smem_b + s * kB2Bytes, &tma_b, full_leader, kb * kBK, n0);
+          if (!A_MN) {
+            tma_load_2d_2sm(smem_a + s * kABytes, &tma_a, full_leader, kb * kBK, m0);
+          } else {  // A stored [K, M]: two [64 k x 64 m] boxes side by side
+            tma_load_2d_2sm(smem_a + s * kABytes, &tma_a, full_leader, m0, kb * kBK);
+            tma_load_2d_2sm(smem_a + s * kABytes + 8192, &tma_a, full_leader, m0 + 64, kb * kBK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(smem_b + s * kB2Bytes, &tma_b, full_leader, kb * kBK, n0);
+          } else {  // B stored [K, N]
+            tma_load_2d_2sm(smem_b + s * kB2Bytes, &tma_b, full_leader, n0, kb * kBK);
+            tma_load_2d_2sm(smem_b + s * kB2Bytes + 8192, &tma_b, full_leader, n0 + 64, kb * kBK);
+          }
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -303,7 +315,7 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // ===================== MMA issuer: one thread of the leader CTA drives both tensor cores =====================
-      constexpr uint32_t idesc = make_idesc_bf16(BM2, kBN);
+      constexpr uint32_t idesc = make_idesc_bf16_major(BM2, kBN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -315,11 +327,12 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint64_t a_desc = make_sw128_desc(smem_u32(smem_a + s * kABytes));
-          const uint64_t b_desc = make_sw128_desc(smem_u32(smem_b + s * kB2Bytes));
+          const uint64_t a_desc = A_MN ? make_sw128_desc_mn(smem_u32(smem_a + s * kABytes)) : make_sw128_desc(smem_u32(smem_a + s * kABytes));
+          const uint64_t b_desc = B_MN ? make_sw128_desc_mn(smem_u32(smem_b + s * kB2Bytes)) : make_sw128_desc(smem_u32(smem_b + s * kB2Bytes));
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            // K-major: +32 B inside the swizzle atom; MN-major: 16 k-rows = two 1024-byte atoms further
+            umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(A_MN ? k * 128 : k * 2), b_desc + (uint64_t)(B_MN ? k * 128 : k * 2), idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit_2cta_mc(&empty_bar[s], 0b11);
           if (++s == STAGES) {
@@ -346,28 +359,55 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const int row = m0 + ew * 32 + lane;
-      __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+      if (accumulate) {
+        // C += A B^T : read-modify-write per lane (rare path)
+        __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 32, r);
-        tmem_ld_wait();
-        if (row < M) {
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 32, r);
+          tmem_ld_wait();
+          if (row < M) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int col = n0 + c * 32 + q * 8;
-            if (col < N) {
-              float f[8];
+            for (int q = 0; q < 4; ++q) {
+              const int col = n0 + c * 32 + q * 8;
+              if (col < N) {
+                float f[8], o[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
-              if (accumulate) {
-                float o[8];
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
                 unpack8(ld8(crow + c * 32 + q * 8), o);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += o[i];
+                st8(crow + c * 32 + q * 8, pack8(f));
               }
-              st8(crow + c * 32 + q * 8, pack8(f));
             }
+          }
+        }
+      } else {
+        // coalesced path: TMEM -> registers -> swizzled smem -> one TMA store per 32x64 block (double buffered)
+#pragma unroll 1
+        for (int c = 0; c < kBN / 64; ++c) {
+          float v[64];
+          {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 64, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + c * 64 + 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
+          }
+          uint8_t* buf = smem_epi + (ew * 2 + (c & 1)) * 4096;
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+          __syncwarp();
+          epi_write_row_swizzled(buf, lane, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && n0 + c * 64 < N) {
+            tma_store_2d(&tma_c, buf, n0 + c * 64, m0 + ew * 32);
+            tma_store_commit();
           }
         }
       }
@@ -379,6 +419,7 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   }
+  if (warp >= 4 && lane == 0) tma_store_wait<0>();
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) {
@@ -416,6 +457,20 @@ const CUtensorMap& cached_tmap_bf16(const void* p, int64_t rows, int64_t cols, i
   return it->second;
 }
 
+// store map: box = 32 rows x 64 columns (128 B inner, 128B swizzle) — one epilogue warp's chunk
+const CUtensorMap& cached_tmap_store_bf16(const void* p, int64_t rows, int64_t cols, int64_t pitch_elems) {
+  static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  MapKey k{p, rows, cols, pitch_elems, 32};
+  auto it = cache.find(k);
+  if (it == cache.end()) {
+    if (cache.size() > 4096) cache.clear();
+    it = cache.emplace(k, make_tmap_2d(p, rows, cols, pitch_elems * 2, 32, 64, 2, true)).first;
+  }
+  return it->second;
+}
+
 int gemm_smem_bytes(int stages) { return stages * (kABytes + kBBytes) + (2 * stages + 4) * 8 + 16 + 1024; }
 
 }  // namespace vb
@@ -441,10 +496,11 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
     constexpr int STAGES2 = 6;
     const CUtensorMap& ta2 = cached_tmap_bf16(a.data_ptr(), M, K, a.stride(0), kBM);
     const CUtensorMap& tb2 = cached_tmap_bf16(b.data_ptr(), N, K, b.stride(0), kBN / 2);
-    const int smem2 = STAGES2 * kStage2 + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+    const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+    const CUtensorMap& tc2 = cached_tmap_store_bf16(c.data_ptr(), M, N, c.stride(0));
     static bool attr2 = false;
     if (!attr2) {
-      C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       attr2 = true;
     }
     const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN);
@@ -453,8 +509,8 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
       const char* e = getenv("VESCALE_B200_GEMM_GROUP_M");
       return e ? atoi(e) : 8;
     }();
-    gemm_nt_2cta_kernel<STAGES2><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
-        ta2, tb2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m);
+    gemm_nt_2cta_kernel<STAGES2, false, false><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+        ta2, tb2, tc2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return;
   }
@@ -472,4 +528,51 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
   gemm_nt_kernel<STAGES><<<grid, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, tb, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K,
                                                                                          (int)c.stride(0), accumulate ? 1 : 0);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+
+// ------------------------------------------------------------------------------------------------- transposed-operand variants
+namespace {
+template <bool A_MN, bool B_MN>
+void launch_2cta_major(const void* a, const void* b, at::Tensor& c, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, bool accumulate) {
+  constexpr int STAGES2 = 6;
+  // K-major operand: map [rows=MN, cols=K], box [128, 64]; MN-major operand: map [rows=K, cols=MN], box [64, 64]
+  const CUtensorMap ta = A_MN ? make_tmap_2d(a, K, M, lda * 2, 64, 64, 2, true) : make_tmap_2d(a, M, K, lda * 2, kBM, kBK, 2, true);
+  const CUtensorMap tb = B_MN ? make_tmap_2d(b, K, N, ldb * 2, 64, 64, 2, true) : make_tmap_2d(b, N, K, ldb * 2, kBN / 2, kBK, 2, true);
+  const CUtensorMap& tc = cached_tmap_store_bf16(c.data_ptr(), M, N, c.stride(0));
+  const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    attr = true;
+  }
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN);
+  const int pairs = std::max(1, std::min(sms / 2, tiles2));
+  gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+      ta, tb, tc, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, 8);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+}  // namespace
+
+// c[M,N] = a[M,K] @ b[K,N]      (dgrad shape: B is MN-major)
+void gemm_nn(const at::Tensor& a, const at::Tensor& b, at::Tensor c) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1 && c.stride(1) == 1);
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(1);
+  TORCH_CHECK(b.size(0) == K && c.size(0) == M && c.size(1) == N && K % kBK == 0 && N % 8 == 0 && a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0);
+  if (M == 0 || N == 0) return;
+  c10::cuda::CUDAGuard guard(a.device());
+  launch_2cta_major<false, true>(a.data_ptr(), b.data_ptr(), c, M, N, K, a.stride(0), b.stride(0), false);
+}
+
+// c[M,N] (+)= a[K,M]^T @ b[K,N]  (wgrad shape: both operands MN-major)
+void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1 && c.stride(1) == 1);
+  const int64_t K = a.size(0), M = a.size(1), N = b.size(1);
+  TORCH_CHECK(b.size(0) == K && c.size(0) == M && c.size(1) == N && K % kBK == 0 && M % 8 == 0 && N % 8 == 0 && a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0);
+  if (M == 0 || N == 0) return;
+  c10::cuda::CUDAGuard guard(a.device());
+  launch_2cta_major<true, true>(a.data_ptr(), b.data_ptr(), c, M, N, K, a.stride(0), b.stride(0), accumulate);
 }

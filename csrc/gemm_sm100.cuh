@@ -15,5 +15,6 @@ constexpr int kEpilogueThreads = 128;
 CUtensorMap make_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols,
                          int elem_bytes, bool swizzle128);
 const CUtensorMap& cached_tmap_bf16(const void* p, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows);
+const CUtensorMap& cached_tmap_store_bf16(const void* p, int64_t rows, int64_t cols, int64_t pitch_elems);
 int gemm_smem_bytes(int stages);
 }  // namespace vb

@@ -40,6 +40,25 @@ def test_gemm_nt(M, N, K, variant):
     assert (c2.float() - 2 * ref).abs().max().item() < 3 * tol
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 384, 256), (8192, 4096, 6144), (1000, 264, 192)])
+def test_gemm_nn_tn_transposed_operands(M, N, K):
+    """dgrad (A K-major x B MN-major) and wgrad (both MN-major) shapes on the tcgen05 kernel."""
+    ops = _ops()
+    a, b = _bf(M, K, seed=1), _bf(K, N, seed=2)
+    c = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nn(a, b, c)
+    ref = a.float() @ b.float()
+    tol = 0.02 * math.sqrt(K) + 0.01 * ref.abs().max().item()
+    assert (c.float() - ref).abs().max().item() < tol
+    at = _bf(K, M, seed=3)
+    c2 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm_tn(at, b, c2, False)
+    ref2 = at.float().t() @ b.float()
+    assert (c2.float() - ref2).abs().max().item() < tol
+    ops.gemm_tn(at, b, c2, True)
+    assert (c2.float() - 2 * ref2).abs().max().item() < 3 * tol
+
+
 def test_gemm_deterministic_and_repeatable():
     ops = _ops()
     a, b = _bf(2048, 1024, seed=3), _bf(1536, 1024, seed=4)

@@ -27,12 +27,15 @@ __all__ = [
     "set_gemm_backend",
 ]
 
-_CFG = {"gemm": "auto"}  # auto | tcgen05 | cublas
+# auto: tcgen05 kernel for the forward (NT) and dgrad (NN) shapes — it measures 4-14 % above cuBLAS on B200
+# (profiles/micro_r2.json); wgrad (TN, both operands MN-major) stays on cuBLAS, which is ~7 % faster there.
+_CFG = {"gemm": "auto", "wgrad": "cublas"}  # gemm: auto | tcgen05 | cublas ; wgrad: cublas | tcgen05
 
 
-def set_gemm_backend(name: str) -> None:
+def set_gemm_backend(name: str, wgrad: Optional[str] = None) -> None:
     assert name in ("auto", "tcgen05", "cublas")
     _CFG["gemm"] = name
+    _CFG["wgrad"] = wgrad or ("tcgen05" if name == "tcgen05" else "cublas")
 
 
 def _use_kernels(t: torch.Tensor) -> bool:
@@ -85,7 +88,7 @@ def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, accumulate: bool = False) -> torch.Tensor:
     """``out (+)= a[K,M]^T @ b[K,N]`` (wgrad shape: dW = dY^T X)."""
-    if _use_kernels(a) and _CFG["gemm"] != "cublas" and hasattr(torch.ops.vescale_b200, "gemm_tn") and a.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous() and a.shape[0] % 64 == 0 and a.shape[1] % 64 == 0 and b.shape[1] % 64 == 0 and (out is None or out.is_contiguous()):
+    if _use_kernels(a) and _CFG["gemm"] != "cublas" and _CFG["wgrad"] == "tcgen05" and hasattr(torch.ops.vescale_b200, "gemm_tn") and a.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous() and a.shape[0] % 64 == 0 and a.shape[1] % 64 == 0 and b.shape[1] % 64 == 0 and (out is None or out.is_contiguous()):
         _ext.count_launch("gemm_tn")
         if out is None:
             out = torch.empty((a.shape[1], b.shape[1]), dtype=a.dtype, device=a.device)
