@@ -38,6 +38,18 @@ void ag_gemm(const at::Tensor& x_local, std::vector<int64_t> x_ptrs, const at::T
 void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector<int64_t> staging_ptrs, at::Tensor done, std::vector<int64_t> flag_ptrs,
              int64_t rank, int64_t epoch);
 
+void grouped_gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, const at::Tensor& tile_expert, int64_t expert_n);
+// moe_dispatch.cu
+void moe_exchange_counts(const at::Tensor& my_counts, std::vector<int64_t> counts_all_ptrs, std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch);
+void moe_plan(const at::Tensor& counts_all, at::Tensor recv_seg_start, at::Tensor send_off, at::Tensor tile_expert, at::Tensor expert_rows,
+              at::Tensor total_rows, int64_t rank, int64_t tile_rows);
+void moe_dispatch_put(const at::Tensor& rows, const at::Tensor& row_expert, const at::Tensor& row_pos, const at::Tensor& send_off,
+                      std::vector<int64_t> recv_ptrs, std::vector<int64_t> flag_ptrs, at::Tensor done_counter, int64_t E, int64_t rank, int64_t epoch);
+void moe_wait(int64_t my_flags, int64_t W, int64_t base, int64_t epoch);
+void moe_signal(std::vector<int64_t> flag_ptrs, int64_t base, int64_t rank, int64_t epoch);
+void moe_combine_get(at::Tensor out, c10::optional<at::Tensor> gate, const at::Tensor& slot_rank, const at::Tensor& slot_row, std::vector<int64_t> src_ptrs,
+                     int64_t k);
+
 TORCH_LIBRARY(vescale_b200, m) {
   m.def("rms_norm_fwd(Tensor x, Tensor w, float eps) -> (Tensor, Tensor)");
   m.def("add_rms_norm_fwd(Tensor a, Tensor b, Tensor w, float eps) -> (Tensor, Tensor, Tensor)");
@@ -51,6 +63,13 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("fused_adamw_(Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor(d!) p_out, Tensor wd_table, Tensor coef, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) -> ()");
   m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate, int variant=0) -> ()");
   m.def("gemm_nn(Tensor a, Tensor b, Tensor(a!) c) -> ()");
+  m.def("grouped_gemm_nt(Tensor a, Tensor b, Tensor(a!) c, Tensor tile_expert, int expert_n) -> ()");
+  m.def("moe_exchange_counts(Tensor my_counts, int[] counts_all_ptrs, int[] flag_ptrs, int rank, int epoch) -> ()");
+  m.def("moe_plan(Tensor counts_all, Tensor(a!) recv_seg_start, Tensor(b!) send_off, Tensor(c!) tile_expert, Tensor(d!) expert_rows, Tensor(e!) total_rows, int rank, int tile_rows) -> ()");
+  m.def("moe_dispatch_put(Tensor rows, Tensor row_expert, Tensor row_pos, Tensor send_off, int[] recv_ptrs, int[] flag_ptrs, Tensor(a!) done_counter, int E, int rank, int epoch) -> ()");
+  m.def("moe_wait(int my_flags, int W, int base, int epoch) -> ()", &moe_wait);
+  m.def("moe_signal(int[] flag_ptrs, int base, int rank, int epoch) -> ()", &moe_signal);
+  m.def("moe_combine_get(Tensor(a!) out, Tensor? gate, Tensor slot_rank, Tensor slot_row, int[] src_ptrs, int k) -> ()");
   m.def("gemm_tn(Tensor a, Tensor b, Tensor(a!) c, bool accumulate) -> ()");
   m.def("ag_gemm(Tensor x_local, int[] x_ptrs, Tensor w, Tensor(a!) x_full, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
@@ -74,6 +93,11 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("fused_adamw_", &fused_adamw_);
   m.impl("gemm_nt", &gemm_nt);
   m.impl("gemm_nn", &gemm_nn);
+  m.impl("grouped_gemm_nt", &grouped_gemm_nt);
+  m.impl("moe_exchange_counts", &moe_exchange_counts);
+  m.impl("moe_plan", &moe_plan);
+  m.impl("moe_dispatch_put", &moe_dispatch_put);
+  m.impl("moe_combine_get", &moe_combine_get);
   m.impl("gemm_tn", &gemm_tn);
   m.impl("ag_gemm", &ag_gemm);
   m.impl("gemm_rs", &gemm_rs);

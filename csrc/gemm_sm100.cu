@@ -222,7 +222,10 @@ constexpr int kEpiBytes = 4 * 2 * 4096;         // epilogue staging: 4 warps x 2
 template <int STAGES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
-                    __nv_bfloat16* __restrict__ C, int M, int N, int K, int ldc, int accumulate, int group_m) {
+                    __nv_bfloat16* __restrict__ C, int M, int N, int K, int ldc, int accumulate, int group_m, const int* __restrict__ tile_expert,
+                    int expert_n) {
+  // grouped mode (MoE): `tile_expert[m_blk]` names the expert whose weights (rows [e*expert_n, (e+1)*expert_n) of B)
+  // multiply the 256-row block m_blk of A; -1 skips the block.  All roles evaluate it identically.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -287,8 +290,10 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         int m_blk, n_blk;
         tile_coord(tile, m_blk, n_blk);
+        const int ex = tile_expert ? tile_expert[m_blk] : 0;
+        if (ex < 0) continue;
         const int m0 = m_blk * BM2 + (int)cta * kBM;
-        const int n0 = n_blk * kBN + (int)cta * (kBN / 2);
+        const int n0 = ex * expert_n + n_blk * kBN + (int)cta * (kBN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           const uint32_t full_leader = mapa(smem_u32(&full_bar[s]), 0);
@@ -321,6 +326,11 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int as = 0;
       uint32_t aph = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        if (tile_expert) {
+          int m_blk, n_blk;
+          tile_coord(tile, m_blk, n_blk);
+          if (tile_expert[m_blk] < 0) continue;
+        }
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kBN;
@@ -355,6 +365,7 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       tile_coord(tile, m_blk, n_blk);
+      if (tile_expert && tile_expert[m_blk] < 0) continue;
       const int m0 = m_blk * BM2 + (int)cta * kBM, n0 = n_blk * kBN;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
@@ -510,7 +521,7 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
       return e ? atoi(e) : 8;
     }();
     gemm_nt_2cta_kernel<STAGES2, false, false><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
-        ta2, tb2, tc2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m);
+        ta2, tb2, tc2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m, nullptr, 0);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return;
   }
@@ -550,7 +561,7 @@ void launch_2cta_major(const void* a, const void* b, at::Tensor& c, int64_t M, i
   const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN);
   const int pairs = std::max(1, std::min(sms / 2, tiles2));
   gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
-      ta, tb, tc, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, 8);
+      ta, tb, tc, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, 8, nullptr, 0);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 }  // namespace
@@ -575,4 +586,29 @@ void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
   if (M == 0 || N == 0) return;
   c10::cuda::CUDAGuard guard(a.device());
   launch_2cta_major<true, true>(a.data_ptr(), b.data_ptr(), c, M, N, K, a.stride(0), b.stride(0), accumulate);
+}
+
+
+// Grouped GEMM for MoE experts: c[r, :] = a[r, :] @ b[e(r)]^T where e(r) is constant per 256-row block
+// (`tile_expert`, device-resident, -1 = skip): no host knowledge of the token counts is needed.
+// a [C, K], b [E_local * N, K] (stacked expert weights), c [C, N].
+void grouped_gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, const at::Tensor& tile_expert, int64_t expert_n) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && c.stride(1) == 1 && tile_expert.scalar_type() == at::kInt);
+  const int64_t M = a.size(0), K = a.size(1), N = expert_n;
+  TORCH_CHECK(M % (2 * kBM) == 0 && tile_expert.numel() >= M / (2 * kBM) && b.size(0) % N == 0 && c.size(0) == M && c.size(1) == N && K % kBK == 0 && N % 8 == 0);
+  if (M == 0) return;
+  c10::cuda::CUDAGuard guard(a.device());
+  constexpr int STAGES2 = 6;
+  const CUtensorMap ta = make_tmap_2d(a.data_ptr(), M, K, a.stride(0) * 2, kBM, kBK, 2, true);
+  const CUtensorMap tb = make_tmap_2d(b.data_ptr(), b.size(0), K, b.stride(0) * 2, kBN / 2, kBK, 2, true);
+  const CUtensorMap tcm = make_tmap_2d(c.data_ptr(), M, N, c.stride(0) * 2, 32, 64, 2, true);
+  const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+  C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int tiles2 = (M / (2 * kBM)) * ((N + kBN - 1) / kBN);
+  const int pairs = std::max(1, std::min(sms / 2, tiles2));
+  gemm_nt_2cta_kernel<STAGES2, false, false><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+      ta, tb, tcm, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), 0, 8, tile_expert.data_ptr<int>(), (int)N);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
