@@ -150,6 +150,8 @@ def _fused_tp(rank, world):
             assert err < 0.03 * ref.abs().max().item() + 0.05, ("gemm_rs", M, Kr, N, it, err)
             dist.barrier()
     # autograd: column-parallel then row-parallel MLP under SP equals the single-device MLP
+    if rank == 0:
+        print("[fused_tp] kernels ok; autograd section", flush=True)
     H, F, Ml = 512, 1024, 256
     g.manual_seed(5)
     w1 = (torch.randn(F, H, device=dev, generator=g) * 0.05).bfloat16()
@@ -159,7 +161,13 @@ def _fused_tp(rank, world):
     w1s = w1[rank * F // world : (rank + 1) * F // world].clone().requires_grad_()
     w2s = w2[:, rank * F // world : (rank + 1) * F // world].clone().requires_grad_()
     out = tp.linear_rs(torch.relu(tp.ag_linear(x_local, w1s)), w2s)
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("[fused_tp] forward done", flush=True)
     out.float().pow(2).sum().backward()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("[fused_tp] backward done", flush=True)
     xs = [torch.empty_like(x_local) for _ in range(world)]
     dist.all_gather(xs, x_local.detach())
     xf = torch.cat(xs).float().requires_grad_()
@@ -174,3 +182,46 @@ def _fused_tp(rank, world):
 
 def test_fused_tp_kernels():
     run_distributed(_fused_tp, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+def _symm_moe(rank, world):
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.ops import _ext
+    from vescale_b200.parallel.moe import MoEConfig, MoELayer
+    from vescale_b200.parallel.moe.symm_dispatch import SymmMoEDispatcher
+
+    _ext.load(required=True)
+    dev = torch.device("cuda", rank)
+    mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("EP",))
+    H, F, E, k, T = 512, 1024, 2 * world, 2, 384
+    cfg = MoEConfig(H, F, E, k, dtype=torch.bfloat16)
+    g = torch.Generator(device=dev).manual_seed(11)
+    layer = MoELayer(cfg, mesh.get_group(0), device=dev)
+    layer.reset_parameters(g)
+    disp = SymmMoEDispatcher(mesh, E, H, F, max_tokens=T, top_k=k, capacity_factor=float(world), device=dev)
+    for it in range(3):
+        gx = torch.Generator(device=dev).manual_seed(100 * it + rank)
+        x = torch.randn(T, H, device=dev, generator=gx).bfloat16()
+        xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+        layer.symm_dispatcher = None
+        ya = layer(xa)  # NCCL all_to_all_single path (baseline)
+        ya.float().pow(2).sum().backward()
+        ga = {n: p.grad.clone() for n, p in layer.named_parameters()}
+        layer.zero_grad()
+        layer.use_symmetric_dispatch(disp)
+        yb = layer(xb)
+        yb.float().pow(2).sum().backward()
+        torch.cuda.synchronize()
+        scale = ya.float().abs().max().item()
+        assert (ya.float() - yb.float()).abs().max().item() < 0.03 * scale + 1e-3, (it, "fwd")
+        assert (xa.grad.float() - xb.grad.float()).abs().max().item() < 0.05 * xa.grad.float().abs().max().item() + 1e-3, (it, "dx")
+        for n, p in layer.named_parameters():
+            ref = ga[n].float()
+            assert (p.grad.float() - ref).abs().max().item() < 0.06 * ref.abs().max().item() + 1e-3, (it, n)
+        layer.zero_grad()
+        dist.barrier()
+
+
+@pytest.mark.timeout(240)
+def test_symm_moe_dispatch_matches_nccl():
+    run_distributed(_symm_moe, min(torch.cuda.device_count(), 8), backend="nccl")
