@@ -50,6 +50,10 @@ void moe_signal(std::vector<int64_t> flag_ptrs, int64_t base, int64_t rank, int6
 void moe_combine_get(at::Tensor out, c10::optional<at::Tensor> gate, const at::Tensor& slot_rank, const at::Tensor& slot_row, std::vector<int64_t> src_ptrs,
                      int64_t k);
 
+// philox_shard.cu
+void philox_fill_box(at::Tensor local, std::vector<int64_t> size, std::vector<int64_t> goff, std::vector<int64_t> gstride, std::vector<int64_t> lstride,
+                     int64_t lbase, int64_t seed, int64_t offset, bool normal, double a, double b);
+
 TORCH_LIBRARY(vescale_b200, m) {
   m.def("rms_norm_fwd(Tensor x, Tensor w, float eps) -> (Tensor, Tensor)");
   m.def("add_rms_norm_fwd(Tensor a, Tensor b, Tensor w, float eps) -> (Tensor, Tensor, Tensor)");
@@ -63,6 +67,7 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("fused_adamw_(Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor(d!) p_out, Tensor wd_table, Tensor coef, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) -> ()");
   m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate, int variant=0) -> ()");
   m.def("gemm_nn(Tensor a, Tensor b, Tensor(a!) c) -> ()");
+  m.def("philox_fill_box(Tensor(a!) local, int[] size, int[] goff, int[] gstride, int[] lstride, int lbase, int seed, int offset, bool normal, float a, float b) -> ()");
   m.def("grouped_gemm_nt(Tensor a, Tensor b, Tensor(a!) c, Tensor tile_expert, int expert_n) -> ()");
   m.def("moe_exchange_counts(Tensor my_counts, int[] counts_all_ptrs, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("moe_plan(Tensor counts_all, Tensor(a!) recv_seg_start, Tensor(b!) send_off, Tensor(c!) tile_expert, Tensor(d!) expert_rows, Tensor(e!) total_rows, int rank, int tile_rows) -> ()");
@@ -93,6 +98,7 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("fused_adamw_", &fused_adamw_);
   m.impl("gemm_nt", &gemm_nt);
   m.impl("gemm_nn", &gemm_nn);
+  m.impl("philox_fill_box", &philox_fill_box);
   m.impl("grouped_gemm_nt", &grouped_gemm_nt);
   m.impl("moe_exchange_counts", &moe_exchange_counts);
   m.impl("moe_plan", &moe_plan);

@@ -189,3 +189,36 @@ def test_llama_block_kernels_vs_reference():
     for a, p in zip(g1, m.parameters()):
         denom = p.grad.float().abs().max().item() + 1e-6
         assert (a - p.grad.float()).abs().max().item() / denom < 0.1
+
+
+def test_sharded_philox_matches_cpu_specification():
+    """CUDA counter-based Philox fill == the pure-torch specification, for plain, sharded and ragged layouts."""
+    import vescale_b200.dtensor as vd
+    from vescale_b200 import DeviceMesh, Shard
+    from vescale_b200.dtensor import RaggedShard
+    from vescale_b200.dtensor.random import philox_normal_reference, philox_uniform_reference, sharded_random_fill
+    from vescale_b200.spec import DTensorSpec, TensorMeta, contiguous_stride
+    from vescale_b200.layout import compute_local_shape
+
+    _ops()
+    shape = (12, 10)
+    idx = torch.arange(120).view(shape)
+    for world, pl, coord in ((1, None, None), (4, [Shard(0)], (1,)), (4, [Shard(1)], (3,)), (4, [RaggedShard((0,), (1, 0, 4, 1))], (2,))):
+        mesh = DeviceMesh("cuda", list(range(world)), _init_process_groups=False, _rank=(coord[0] if coord else 0))
+        from vescale_b200 import Replicate
+        placements = tuple(pl) if pl else (Replicate(),)
+        spec = DTensorSpec(mesh, placements, TensorMeta(shape, contiguous_stride(shape), torch.float32))
+        for kind in ("uniform", "normal"):
+            vd.manual_seed(321)
+            local = torch.empty(compute_local_shape(shape, mesh, placements), device="cuda")
+            sharded_random_fill(local, spec, kind)
+            vd.manual_seed(321)
+            full = torch.empty(shape)
+            fspec = DTensorSpec(DeviceMesh("cpu", [0], _init_process_groups=False, _rank=0), (Replicate(),), spec.tensor_meta)
+            sharded_random_fill(full, fspec, kind)
+            from vescale_b200.dtensor.api import slice_local
+            want = slice_local(full, mesh, placements, coord if coord else (0,))
+            if kind == "uniform":
+                assert torch.equal(local.cpu().reshape(-1), want.reshape(-1)), (world, pl, kind)
+            else:
+                torch.testing.assert_close(local.cpu().reshape(-1), want.reshape(-1), rtol=1e-5, atol=1e-6)
