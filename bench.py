@@ -240,13 +240,16 @@ def main():
     _ext.LAUNCH_COUNTER.update(n=0, enabled=True, by_op={})
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
     last = None
     for i in range(args.steps):
         last = step_device(i)
+        marks[i].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    step_ms = [round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(args.steps)]
     launches = _ext.LAUNCH_COUNTER["n"]
     by_op = dict(_ext.LAUNCH_COUNTER["by_op"])
     _ext.LAUNCH_COUNTER["enabled"] = False
@@ -310,6 +313,7 @@ def main():
         "model_tflops_per_gpu": tps / world * flops_tok / 1e12,
         "peak_mem_gb": mem_gb,
         "final_loss": final_loss,
+        "step_ms": step_ms,
         "gpu_launches": launches,
         "gpu_launches_by_op": by_op,
         "clocks": clocks,
