@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--reshard", default="auto", choices=["auto", "yes", "no"])
     p.add_argument("--max-grad-norm", type=float, default=1.0)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--profile", default=None, help="after the timed regions, run ONE extra step under torch.profiler and write the per-kernel table here")
     return p.parse_args()
 
 
@@ -266,6 +267,18 @@ def main():
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         _ = float(loss_host[0])
+
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_device(0)
+            torch.cuda.synchronize()
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile)), exist_ok=True)
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+    elif args.profile:
+        step_device(0)
 
     t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0, mem_gb], device=dev, dtype=torch.float64)
     if world > 1:
