@@ -25,12 +25,23 @@ void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
 void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch);
 void symm_wait(int64_t my_pad, int64_t world, int64_t slot, int64_t epoch);
 void symm_all_gather(std::vector<int64_t> shard_ptrs, at::Tensor full, int64_t shard_bytes, int64_t rank, std::vector<int64_t> pad_ptrs,
-                     int64_t slot, int64_t epoch, int64_t num_ctas);
+                     int64_t slot, int64_t epoch, int64_t num_ctas, int64_t range_mode, int64_t range_lo_bytes, int64_t range_hi_bytes);
 void symm_reduce_scatter(std::vector<int64_t> grad_ptrs, at::Tensor out, c10::optional<at::Tensor> sumsq, int64_t shard_elems, int64_t rank,
                          double scale, std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, int64_t multicast_ptr, int64_t num_ctas);
 void symm_rs_adamw(std::vector<int64_t> grad_ptrs, at::Tensor master, at::Tensor m, at::Tensor v, at::Tensor p_out, const at::Tensor& wd_table,
                    const at::Tensor& coef, c10::optional<at::Tensor> sumsq, int64_t rank, double scale, std::vector<int64_t> pad_ptrs, int64_t slot,
                    int64_t epoch, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, int64_t num_ctas);
+
+// symm_collectives.cu
+void symm_all_reduce(std::vector<int64_t> buf_ptrs, int64_t multicast_ptr, c10::optional<at::Tensor> out, int64_t numel, int64_t dtype_code, double scale,
+                     int64_t rank, std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, at::Tensor counter, int64_t num_ctas);
+void symm_a2a_permute(const at::Tensor& src, std::vector<int64_t> dst_ptrs, std::vector<int64_t> n, std::vector<int64_t> ss, std::vector<int64_t> ds,
+                      int64_t src_peer_stride, int64_t dst_rank_stride, int64_t vec_bytes, int64_t rank, std::vector<int64_t> pad_ptrs, int64_t slot,
+                      int64_t epoch, at::Tensor counter, int64_t num_ctas);
+void symm_put_segments(const at::Tensor& src, std::vector<int64_t> dst_ptrs, const at::Tensor& table, int64_t vec_bytes, int64_t total_vecs, int64_t rank,
+                       std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, at::Tensor counter, int64_t num_ctas);
+at::Tensor symm_vocab_ce_(at::Tensor logits, const at::Tensor& target, const at::Tensor& n_valid, int64_t vocab_start, int64_t ignore_index,
+                          std::vector<int64_t> stats_ptrs, int64_t rank, int64_t epoch, int64_t max_rows, int64_t max_ctas);
 
 // gemm_fused_tp.cu
 void ag_gemm(const at::Tensor& x_local, std::vector<int64_t> x_ptrs, const at::Tensor& w, at::Tensor x_full, at::Tensor y, at::Tensor arrive,
@@ -38,6 +49,8 @@ void ag_gemm(const at::Tensor& x_local, std::vector<int64_t> x_ptrs, const at::T
 void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector<int64_t> staging_ptrs, at::Tensor done, std::vector<int64_t> flag_ptrs,
              int64_t rank, int64_t epoch);
 
+void wag_gemm(const at::Tensor& x, at::Tensor w_full, std::vector<int64_t> shard_ptrs, std::vector<int64_t> row_bounds, at::Tensor y, at::Tensor arrive,
+              std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch);
 void grouped_gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, const at::Tensor& tile_expert, int64_t expert_n);
 // moe_dispatch.cu
 void moe_exchange_counts(const at::Tensor& my_counts, std::vector<int64_t> counts_all_ptrs, std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch);
@@ -80,12 +93,22 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
   m.def("symm_wait(int my_pad, int world, int slot, int epoch) -> ()", &symm_wait);
-  m.def("symm_all_gather(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int num_ctas) -> ()");
+  m.def("symm_all_gather(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int num_ctas, int range_mode=0, int range_lo_bytes=0, int range_hi_bytes=0) -> ()");
   m.def("symm_reduce_scatter(int[] grad_ptrs, Tensor(a!) out, Tensor(b!)? sumsq, int shard_elems, int rank, float scale, int[] pad_ptrs, int slot, int epoch, int multicast_ptr, int num_ctas) -> ()");
   m.def("symm_rs_adamw(int[] grad_ptrs, Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor(d!) p_out, Tensor wd_table, Tensor coef, Tensor(e!)? sumsq, int rank, float scale, int[] pad_ptrs, int slot, int epoch, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int num_ctas) -> ()");
+  m.def("wag_gemm(Tensor x, Tensor(a!) w_full, int[] shard_ptrs, int[] row_bounds, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch) -> ()");
+  m.def("symm_all_reduce(int[] buf_ptrs, int multicast_ptr, Tensor(a!)? out, int numel, int dtype_code, float scale, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(b!) counter, int num_ctas) -> ()");
+  m.def("symm_a2a_permute(Tensor src, int[] dst_ptrs, int[] n, int[] ss, int[] ds, int src_peer_stride, int dst_rank_stride, int vec_bytes, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(a!) counter, int num_ctas) -> ()");
+  m.def("symm_put_segments(Tensor src, int[] dst_ptrs, Tensor table, int vec_bytes, int total_vecs, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(a!) counter, int num_ctas) -> ()");
+  m.def("symm_vocab_ce_(Tensor(a!) logits, Tensor target, Tensor n_valid, int vocab_start, int ignore_index, int[] stats_ptrs, int rank, int epoch, int max_rows, int max_ctas) -> Tensor");
 }
 
 TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
+  m.impl("wag_gemm", &wag_gemm);
+  m.impl("symm_all_reduce", &symm_all_reduce);
+  m.impl("symm_a2a_permute", &symm_a2a_permute);
+  m.impl("symm_put_segments", &symm_put_segments);
+  m.impl("symm_vocab_ce_", &symm_vocab_ce_);
   m.impl("rms_norm_fwd", &rms_norm_fwd);
   m.impl("add_rms_norm_fwd", &add_rms_norm_fwd);
   m.impl("rms_norm_bwd", &rms_norm_bwd);

@@ -2,6 +2,7 @@
 //
 //   ag_gemm   :  Y[M, Nr]  = allgather_rows(X)[M, K] * Wr[Nr, K]^T           (SP -> column-parallel linear, C9)
 //   gemm_rs   :  Y[M/W, N] = reduce_scatter_rows( Xr[M, Kr] * Wr[N, Kr]^T )  (row-parallel linear -> SP, C10)
+//   wag_gemm  :  Y[M, N]   = X[M, K] * allgather_rows(Wshards)[N, K]^T        (FSDP unit all-gather ⊕ first GEMM, C1/C8)
 //
 // Both reuse the plain GEMM's mainloop (TMA -> 6-stage smem ring -> tcgen05.mma.cta_group::2 -> TMEM -> epilogue);
 // the collective is done by the same kernel, tile by tile, so transfer and math overlap:
@@ -11,6 +12,12 @@
 //   local gathered buffer (a few MB in flight per GPU from one thread per CTA), then bumps a per-row-block
 //   arrival counter.  The producer of a tile that needs remote rows acquires that counter before issuing its TMA
 //   loads (reads then hit local HBM/L2: every remote byte crosses NVLink exactly once).
+//
+// wag_gemm: the B operand is an FSDP-sharded weight: rank p owns the contiguous row range [rb[p], rb[p+1]) of W inside its
+//   symmetric parameter shard (RaggedShard: uneven, possibly empty).  The copy engine gathers all W row ranges (own rows
+//   first) into the unit's gathered buffer, n-blocks are visited in arrival order, and the producer of a tile acquires its
+//   n-block's arrival counter before loading B.  The first GEMM of the unit therefore starts after ~one n-block (2 MB) has
+//   arrived instead of after the whole unit's all-gather.
 //
 // gemm_rs: tiles whose output rows belong to a peer run first; their epilogue stores the bf16 partial tile
 //   straight into that peer's staging slot (st.global to peer memory) and the last CTA to finish a peer's rows
@@ -80,9 +87,11 @@ struct FusedArgs {
   uint32_t* done;        // [W] finished-CTA counters (local), monotonically increasing
   PtrArray staging;      // peer p's staging buffer base: [W slots][M/W rows][N] bf16
   PtrArray flags;        // peer p's flag array: [W] uint32 "slot src complete" ; entry [W + src] = "entered"
+  // wag_gemm
+  int rb[kMaxW + 1];     // weight-row ownership boundaries: rank p owns rows [rb[p], rb[p+1])
 };
 
-// MODE 1 = ag_gemm, MODE 2 = gemm_rs
+// MODE 1 = ag_gemm, MODE 2 = gemm_rs, MODE 3 = wag_gemm
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a_local, const __grid_constant__ CUtensorMap tma_b,
@@ -114,7 +123,14 @@ fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   // owner order: ag_gemm consumes its own rows first; gemm_rs produces its own rows last
+  const int first_nblk = MODE == 3 ? fa.rb[rank] / kBN : 0;
   auto tile_coord = [&](int t, int& m_blk, int& n_blk, int& owner) {
+    if (MODE == 3) {  // n-blocks in the order their rows arrive (own rows first), all row blocks of X per n-block
+      owner = rank;
+      m_blk = t % num_m;
+      n_blk = (t / num_m + first_nblk) % num_n;
+      return;
+    }
     const int oi = t / tiles_per_owner;
     owner = MODE == 1 ? (rank + oi) % W : (rank + 1 + oi) % W;
     const int within = t - oi * tiles_per_owner;
@@ -172,6 +188,10 @@ fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             fence_proxy_async_all();
           }
         }
+        if (MODE == 3) {
+          spin_ge_gpu(fa.arrive + n_blk, fa.epoch * (uint32_t)fa.copy_units_per_blk);
+          fence_proxy_async_all();
+        }
         const int n0 = n_blk * kBN + (int)cta * (kBN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -217,6 +237,34 @@ fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
     }
   } else if (warp == 3) {
+    if (MODE == 3 && lane == 0) {
+      // ===================== TMA copy engine: every rank's weight rows -> local gathered weight =====================
+      for (int p = 0; p < W; ++p) spin_ge_sys(my_flags + W + p, fa.epoch);
+      const int boxes_per_row = K / kCopyCols;
+      const int row_boxes = N / kCopyRows;
+      const int rot = fa.rb[rank] / kCopyRows;
+      const int total = row_boxes * boxes_per_row;
+      int slot = 0;
+      uint32_t cph = 0;
+      for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        const int rbx = (u / boxes_per_row + rot) % row_boxes, cb = u % boxes_per_row;
+        const int r = rbx * kCopyRows;
+        int p = 0;
+        while (p + 1 < W && r >= fa.rb[p + 1]) ++p;
+        mbar_expect_tx(&copy_bar[slot], kCopyBytes);
+        tma_load_2d(smem_copy + slot * kCopyBytes, &peer_x.m[p], &copy_bar[slot], cb * kCopyCols, r - fa.rb[p]);
+        mbar_wait(&copy_bar[slot], cph);
+        tma_store_2d(&tma_full_store, smem_copy + slot * kCopyBytes, cb * kCopyCols, r);
+        tma_store_commit();
+        tma_store_wait<0>();
+        __threadfence();
+        atomicAdd(fa.arrive + r / kBN, 1u);
+        if (++slot == kCopySlots) {
+          slot = 0;
+          cph ^= 1;
+        }
+      }
+    }
     if (MODE == 1 && lane == 0) {
       // ===================== TMA copy engine: peers' X shards -> local gathered buffer =====================
       // wait until every peer has entered this call (its X shard is final)
@@ -439,5 +487,48 @@ void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector
   const int pairs = std::max(1, std::min(sms / 2, tiles));
   const CUtensorMap tcy = make_tmap_2d(y.data_ptr(), M / W, N, y.stride(0) * 2, 32, 64, 2, true);
   fused_tp_kernel<2><<<pairs * 2, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, ta, tb, px, ta, tcy, (__nv_bfloat16*)y.data_ptr(), fa);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// x [M, K]; w_full [N, K] = the weight's slice of the unit's gathered buffer (filled by this kernel); shard_ptrs[p] = address
+// of the first row rank p owns (inside its symmetric parameter shard); row_bounds[W+1] = ownership boundaries.
+void wag_gemm(const at::Tensor& x, at::Tensor w_full, std::vector<int64_t> shard_ptrs, std::vector<int64_t> row_bounds, at::Tensor y, at::Tensor arrive,
+              std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch) {
+  const int W = shard_ptrs.size();
+  TORCH_CHECK(W >= 1 && W <= kMaxW && (int)row_bounds.size() == W + 1);
+  const int64_t M = x.size(0), K = x.size(1), N = w_full.size(0);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w_full.scalar_type() == at::kBFloat16 && x.is_contiguous() && w_full.is_contiguous() && w_full.size(1) == K);
+  TORCH_CHECK(M % (2 * kBM) == 0 && K % kCopyCols == 0 && N % kBN == 0, "wag_gemm: M and N must be multiples of 256, K of 256");
+  TORCH_CHECK(y.size(0) == M && y.size(1) == N && y.stride(1) == 1 && arrive.scalar_type() == at::kInt && arrive.numel() >= N / kBN);
+  TORCH_CHECK(row_bounds[0] == 0 && row_bounds[W] == N);
+  c10::cuda::CUDAGuard guard(x.device());
+  FusedArgs fa{};
+  for (int p = 0; p <= W; ++p) {
+    TORCH_CHECK(row_bounds[p] % kCopyRows == 0 && (p == 0 || row_bounds[p] >= row_bounds[p - 1]), "wag_gemm: ownership boundaries must be multiples of 32 rows");
+    fa.rb[p] = (int)row_bounds[p];
+  }
+  const CUtensorMap ta = make_tmap_2d(x.data_ptr(), M, K, x.stride(0) * 2, kBM, kBK, 2, true);
+  const CUtensorMap tb = make_tmap_2d(w_full.data_ptr(), N, K, K * 2, kBN / 2, kBK, 2, true);
+  TmapArray px{};
+  for (int p = 0; p < W; ++p) {
+    const int64_t rows = row_bounds[p + 1] - row_bounds[p];
+    px.m[p] = rows > 0 ? make_tmap_2d(reinterpret_cast<void*>(shard_ptrs[p]), rows, K, K * 2, kCopyRows, kCopyCols, 2, false) : ta;
+  }
+  const CUtensorMap tst = make_tmap_2d(w_full.data_ptr(), N, K, K * 2, kCopyRows, kCopyCols, 2, false);
+  fa.M = M, fa.N = N, fa.K = K, fa.ldc = y.stride(0), fa.world = W, fa.rank = rank, fa.epoch = (uint32_t)epoch;
+  fa.arrive = reinterpret_cast<uint32_t*>(arrive.data_ptr<int>());
+  fa.copy_units_per_blk = (kBN / kCopyRows) * (K / kCopyCols);
+  fa.flags = to_ptr_array(flag_ptrs);
+  const int smem = fused_smem_bytes();
+  static bool attr = false;
+  if (!attr) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(fused_tp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int tiles = (M / (2 * kBM)) * (N / kBN);
+  const int pairs = std::max(1, std::min(sms / 2, tiles));
+  const CUtensorMap tcy = make_tmap_2d(y.data_ptr(), M, N, y.stride(0) * 2, 32, 64, 2, true);
+  fused_tp_kernel<3><<<pairs * 2, kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(ta, ta, tb, px, tst, tcy, (__nv_bfloat16*)y.data_ptr(), fa);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

@@ -73,23 +73,43 @@ VB_DEVICE void block_signal_then_wait(const PeerFlags& pads, const uint32_t* my_
 // Work item = 16-byte vector v of peer p's shard.  Items are interleaved peer-fastest so each CTA keeps
 // requests to all peers in flight.
 template <int UNROLL>
-__global__ void __launch_bounds__(512) all_gather_pull_kernel(PeerPtrs shards, uint4* __restrict__ full, size_t vec_per_shard, int world, int rank,
-                                                              PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch, int use_flags) {
-  if (use_flags) block_signal_then_wait(pads, my_pad, world, rank, slot, epoch, true);
+VB_DEVICE void pull_range(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t begin, size_t end) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + (UNROLL - 1) * stride < end; i += UNROLL * stride) {
+    uint4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) dst[i + u * stride] = v[u];
+  }
+  for (; i < end; i += stride) dst[i] = ld_stream(src + i);
+}
+
+// range_mode 0: whole unit.  1: only global vectors [range_lo, range_hi) (small parameters needed before the fused first
+// GEMM).  2: everything except that range (the weight the fused AG⊕GEMM kernel gathers itself).
+template <int UNROLL>
+__global__ void __launch_bounds__(512) all_gather_pull_kernel(PeerPtrs shards, uint4* __restrict__ full, size_t vec_per_shard, int world, int rank,
+                                                              PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch, int use_flags,
+                                                              int range_mode, size_t range_lo, size_t range_hi) {
+  if (use_flags) block_signal_then_wait(pads, my_pad, world, rank, slot, epoch, true);
   for (int pi = 0; pi < world; ++pi) {
     const int p = (rank + pi) % world;  // own shard first, then neighbours: spreads simultaneous requests over distinct owners
     const uint4* src = reinterpret_cast<const uint4*>(shards.p[p]);
     uint4* dst = full + (size_t)p * vec_per_shard;
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    for (; i + (UNROLL - 1) * stride < vec_per_shard; i += UNROLL * stride) {
-      uint4 v[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(src + i + u * stride);
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) dst[i + u * stride] = v[u];
+    if (range_mode == 0) {
+      pull_range<UNROLL>(src, dst, 0, vec_per_shard);
+    } else {
+      const size_t base = (size_t)p * vec_per_shard;
+      const size_t a = range_lo > base ? min(range_lo - base, vec_per_shard) : 0;
+      const size_t b = range_hi > base ? min(range_hi - base, vec_per_shard) : 0;
+      if (range_mode == 1) {
+        pull_range<UNROLL>(src, dst, a, b);
+      } else {
+        pull_range<UNROLL>(src, dst, 0, a);
+        pull_range<UNROLL>(src, dst, max(a, b), vec_per_shard);
+      }
     }
-    for (; i < vec_per_shard; i += stride) dst[i] = ld_stream(src + i);
   }
 }
 
@@ -242,17 +262,19 @@ void symm_wait(int64_t my_pad, int64_t world, int64_t slot, int64_t epoch) {
 }
 
 void symm_all_gather(std::vector<int64_t> shard_ptrs, at::Tensor full, int64_t shard_bytes, int64_t rank, std::vector<int64_t> pad_ptrs,
-                     int64_t slot, int64_t epoch, int64_t num_ctas) {
+                     int64_t slot, int64_t epoch, int64_t num_ctas, int64_t range_mode, int64_t range_lo_bytes, int64_t range_hi_bytes) {
   TORCH_CHECK(full.is_cuda() && full.is_contiguous() && shard_bytes % 16 == 0);
   const int world = shard_ptrs.size();
   TORCH_CHECK((int64_t)full.numel() * full.element_size() == shard_bytes * world, "all_gather: full buffer size mismatch");
   c10::cuda::CUDAGuard guard(full.device());
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  const int grid = num_ctas > 0 ? (int)num_ctas : comm_grid(sms, 1, 4);
+  int grid = num_ctas > 0 ? (int)num_ctas : comm_grid(sms, 1, 4);
+  if (range_mode == 1) grid = std::max<int>(1, std::min<int64_t>(grid, (range_hi_bytes - range_lo_bytes) / (16 * 512) + 1));
   const bool use_flags = !pad_ptrs.empty();
   PeerFlags pf = use_flags ? to_flags(pad_ptrs) : PeerFlags{};
   all_gather_pull_kernel<4><<<grid, 512, 0, cur_stream()>>>(to_ptrs(shard_ptrs), reinterpret_cast<uint4*>(full.data_ptr()), (size_t)shard_bytes / 16, world,
-                                                           (int)rank, pf, use_flags ? pf.p[rank] : nullptr, (int)slot, (uint32_t)epoch, use_flags ? 1 : 0);
+                                                           (int)rank, pf, use_flags ? pf.p[rank] : nullptr, (int)slot, (uint32_t)epoch, use_flags ? 1 : 0,
+                                                           (int)range_mode, (size_t)range_lo_bytes / 16, (size_t)(range_hi_bytes + 15) / 16);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

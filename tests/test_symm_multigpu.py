@@ -68,18 +68,27 @@ def _fsdp_backends(rank, world):
     dev = torch.device("cuda", rank)
     cfg = LlamaConfig(vocab_size=2048, hidden_size=512, intermediate_size=1024, num_layers=3, num_heads=8, num_kv_heads=2, head_dim=64, max_seq_len=256)
     results = {}
-    for backend, clip, fused in (("nccl", 1.0, False), ("symm", 1.0, False), ("symm", None, True), ("nccl", None, False)):
+    from vescale_b200.ops import _ext
+
+    for backend, clip, fused in (("nccl", 1.0, False), ("symm", 1.0, False), ("symm", None, True), ("nccl", None, False), ("symm-wag", 1.0, False)):
         mesh = init_device_mesh("cuda", (world,))
         model = LlamaModel(cfg, device=dev).reset_parameters(seed=3)
+        wag = backend == "symm-wag"  # exposed all-gathers (prefetch=0) with the unit's first GEMM gathering its own weight
+        if wag:
+            backend = "symm"
+            _ext.LAUNCH_COUNTER.update(n=0, enabled=True, by_op={})
         for blk in model.layers:
+            if wag:
+                fully_shard(blk, mesh, comm_backend="symm", reshard_after_forward=True, prefetch=0, fuse_first_gemm=True)
+                continue
             fully_shard(blk, mesh, comm_backend=backend, reshard_after_forward=(backend == "nccl"))
         fully_shard(model.embed, mesh, comm_backend=backend)
         fully_shard(model.head, mesh, comm_backend=backend)
-        fully_shard(model, mesh, comm_backend=backend)
+        fully_shard(model, mesh, comm_backend=backend, **({"prefetch": 0} if wag else {}))
         opt = FSDPAdamW(model, lr=1e-3, max_grad_norm=clip, fused_reduce=fused)
         losses = []
         if rank == 0:
-            print(f"[fsdp-backends] {backend} clip={clip} fused={fused}", flush=True)
+            print(f"[fsdp-backends] {backend} clip={clip} fused={fused} wag={wag}", flush=True)
         for s in range(4):
             g = torch.Generator().manual_seed(100 * s + rank)
             tok = torch.randint(0, cfg.vocab_size, (2, 257), generator=g).to(dev)
@@ -91,11 +100,15 @@ def _fsdp_backends(rank, world):
             if rank == 0:
                 print(f"   step {s} loss {losses[-1]:.4f}", flush=True)
         params = torch.cat([p.full_tensor().reshape(-1).float() for p in model.parameters()])
-        results[(backend, clip, fused)] = (losses, params)
+        results[("symm-wag" if wag else backend, clip, fused)] = (losses, params)
+        if wag:
+            n_wag = _ext.LAUNCH_COUNTER["by_op"].get("wag_gemm", 0)
+            _ext.LAUNCH_COUNTER["enabled"] = False
+            assert n_wag == 4 * cfg.num_layers, f"fused all-gather⊕GEMM ran {n_wag} times"
         del model, opt
         torch.cuda.synchronize()
         dist.barrier()
-    for a, b in ((("nccl", 1.0, False), ("symm", 1.0, False)), (("nccl", None, False), ("symm", None, True))):
+    for a, b in ((("nccl", 1.0, False), ("symm", 1.0, False)), (("nccl", None, False), ("symm", None, True)), (("nccl", 1.0, False), ("symm-wag", 1.0, False))):
         la, pa = results[a]
         lb, pb = results[b]
         assert all(abs(x - y) < 3e-2 for x, y in zip(la, lb)), (a, b, la, lb)
@@ -225,3 +238,84 @@ def _symm_moe(rank, world):
 @pytest.mark.timeout(240)
 def test_symm_moe_dispatch_matches_nccl():
     run_distributed(_symm_moe, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+def _tensor_collectives(rank, world):
+    """csrc/symm_collectives.cu: all-reduce (one-shot / two-shot / NVLS), a2a with folded permutes, ragged puts, vocab CE —
+    each against NCCL / a single-device fp32 reference — and DTensor.redistribute routed through them."""
+    from vescale_b200 import DTensor, Replicate, Shard, init_device_mesh
+    from vescale_b200.comm import collectives as C
+    from vescale_b200.comm.symm_collectives import disable_symmetric_collectives, enable_symmetric_collectives
+    from vescale_b200.dtensor import RaggedShard
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    dev = torch.device("cuda", rank)
+    mesh = init_device_mesh("cuda", (world,))
+    (sc,) = enable_symmetric_collectives(mesh, reserve_bytes=64 << 20)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+
+    # ---- all-reduce
+    for dtype in (torch.float32, torch.bfloat16):
+        for n in (7, 4096, 1 << 20, (1 << 22) + 24):
+            for mm in (False, True):
+                sc.use_multimem = mm
+                x = torch.randn(n, device=dev, generator=g).to(dtype)
+                want = x.clone().float()
+                dist.all_reduce(want)
+                got = sc.all_reduce(x.clone())
+                torch.cuda.synchronize()
+                tol = dict(rtol=2e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=1e-5, atol=1e-5)
+                torch.testing.assert_close(got.float(), want, **tol)
+    x = torch.randn(3, 1000, device=dev, generator=g)
+    want = x.clone()
+    dist.all_reduce(want)
+    torch.testing.assert_close(C.mesh_all_reduce(x, mesh, "avg", 0), want / world, rtol=1e-5, atol=1e-5)
+
+    # ---- Shard(i) -> Shard(j) with the permutes folded into the put
+    for shape, i, j, dtype in (((4 * world, 6, 8 * world), 0, 2, torch.bfloat16), ((3, 2 * world, 5, 4 * world, 8), 3, 1, torch.float32), ((2 * world, 3 * world), 1, 0, torch.bfloat16)):
+        full = torch.arange(int(torch.tensor(shape).prod()), device=dev, dtype=torch.float32).reshape(shape).to(dtype)
+        mine = full.chunk(world, dim=i)[rank].contiguous()
+        got = sc.all_to_all_permute(mine, i, j)
+        torch.cuda.synchronize()
+        assert torch.equal(got, full.chunk(world, dim=j)[rank]), (shape, i, j)
+        dt = DTensor.from_local(mine, mesh, [Shard(i)])
+        assert torch.equal(dt.redistribute(mesh, [Shard(j)]).to_local(), full.chunk(world, dim=j)[rank])
+
+    # ---- ragged interval exchange (RaggedShard -> RaggedShard, gather to root)
+    numel = 512 * world * (world + 1)
+    full = torch.randn(numel, device=dev, generator=torch.Generator(device=dev).manual_seed(5)).bfloat16()
+    src_units = tuple(range(1, world + 1))
+    dst_units = tuple(reversed(src_units))
+    root_units = tuple(1 if r == world - 1 else 0 for r in range(world))
+    a = DTensor.from_local(full[slice(*RaggedShard((0,), src_units).flat_range(numel, rank))].clone(), mesh, [RaggedShard((0,), src_units)], shape=(numel,), stride=(1,))
+    for units in (dst_units, root_units, src_units):
+        b = a.redistribute(mesh, [RaggedShard((0,), units)])
+        lo, hi = RaggedShard((0,), units).flat_range(numel, rank)
+        torch.cuda.synchronize()
+        assert torch.equal(b.to_local().reshape(-1), full[lo:hi]), units
+
+    # ---- vocab-parallel cross entropy: one launch vs the fp32 single-device reference
+    T, V = 1000, 1024 * world
+    logits = torch.randn(T, V, device=dev, generator=torch.Generator(device=dev).manual_seed(9)).mul(3).bfloat16()
+    target = torch.randint(0, V, (T,), device=dev, generator=torch.Generator(device=dev).manual_seed(10))
+    target[::17] = -100
+    ref_logits = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_logits, target, ignore_index=-100)
+    ref.backward()
+    for it in range(3):
+        shard = logits[:, rank * (V // world) : (rank + 1) * (V // world)].contiguous().requires_grad_(True)
+        buf = shard * 1.0  # non-leaf buffer the kernel may consume
+        loss = sc.vocab_parallel_cross_entropy(buf, target)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - ref.item()) < 2e-3, (it, loss.item(), ref.item())
+        want = ref_logits.grad[:, rank * (V // world) : (rank + 1) * (V // world)]
+        assert (shard.grad.float() - want).abs().max().item() < 2e-5 + 0.01 * want.abs().max().item()
+    disable_symmetric_collectives()
+    dist.barrier()
+
+
+@pytest.mark.timeout(300)
+def test_symm_tensor_collectives():
+    run_distributed(_tensor_collectives, min(torch.cuda.device_count(), 8), backend="nccl")

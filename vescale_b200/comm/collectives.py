@@ -23,6 +23,7 @@ __all__ = [
     "mesh_reduce_scatter",
     "mesh_all_to_all_single",
     "mesh_all_to_all_uneven",
+    "mesh_ragged_exchange",
     "mesh_broadcast",
     "mesh_scatter",
     "mesh_scatter_ragged",
@@ -76,6 +77,15 @@ def _group_rank(group) -> int:
     return dist.get_rank(group)
 
 
+def _symm(group, tensor):
+    """The symmetric-memory backend registered for this group (``enable_symmetric_collectives``), if the tensor qualifies."""
+    if not tensor.is_cuda:
+        return None
+    from .symm_collectives import symm_backend_for
+
+    return symm_backend_for(group, tensor)
+
+
 def mesh_all_reduce(tensor: torch.Tensor, mesh, reduce_op: str = "sum", mesh_dim: int = 0, *, inplace: bool = False) -> torch.Tensor:
     group = mesh.get_group(mesh_dim)
     n = _group_size(group)
@@ -83,6 +93,10 @@ def mesh_all_reduce(tensor: torch.Tensor, mesh, reduce_op: str = "sum", mesh_dim
     _note("all_reduce", out, group, op=reduce_op)
     if n == 1:
         return out
+    if reduce_op in ("sum", "avg") and out.dtype in (torch.float32, torch.bfloat16) and out.is_contiguous():
+        sc = _symm(group, out)
+        if sc is not None:
+            return sc.all_reduce(out, reduce_op)
     if reduce_op == "avg" and (_backend(group) != "nccl" or not out.is_floating_point()):
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
         return out.div_(n) if out.is_floating_point() else out.div_(n, rounding_mode="floor")
@@ -189,6 +203,28 @@ def mesh_all_to_all_uneven(ins: List[torch.Tensor], out_sizes: Sequence[int], me
     return outs
 
 
+def mesh_ragged_exchange(local: torch.Tensor, src_ranges: Sequence, dst_ranges: Sequence, mesh, mesh_dim: int = 0) -> torch.Tensor:
+    """Flat interval exchange: ``local`` holds flat range ``src_ranges[me]`` of a global buffer, the result holds
+    ``dst_ranges[me]`` (RaggedShard -> RaggedShard; one-hot destinations = gather-to-root).  Symmetric-memory put kernel
+    when enabled, else the uneven list all-to-all of the reference (``placement_types.py:152-192``)."""
+    group = mesh.get_group(mesh_dim)
+    n, me = _group_size(group), mesh.get_local_rank(mesh_dim)
+    local = local.contiguous().view(-1)
+    sc = _symm(group, local) if n > 1 else None
+    if sc is not None:
+        _note("all_to_all", local, group, uneven=True, backend="symm")
+        return sc.ragged_exchange(local, src_ranges, dst_ranges)
+    s_lo, s_hi = src_ranges[me]
+    d_lo, d_hi = dst_ranges[me]
+    ins, out_sizes = [], []
+    for j in range(n):
+        lo, hi = max(s_lo, dst_ranges[j][0]), min(s_hi, dst_ranges[j][1])
+        ins.append(local.narrow(0, lo - s_lo, hi - lo) if hi > lo else local.new_empty(0))
+        out_sizes.append(max(0, min(src_ranges[j][1], d_hi) - max(src_ranges[j][0], d_lo)))
+    outs = mesh_all_to_all_uneven(ins, out_sizes, mesh, mesh_dim)
+    return torch.cat(outs) if outs else local.new_empty(0)
+
+
 def mesh_all_to_all_single(tensor: torch.Tensor, mesh, mesh_dim: int, split_dim: int, concat_dim: int) -> torch.Tensor:
     """Even Shard(concat_dim) -> Shard(split_dim): split my tensor on ``split_dim`` into n pieces, piece j
     goes to coordinate j, received pieces are concatenated on ``concat_dim``."""
@@ -199,6 +235,10 @@ def mesh_all_to_all_single(tensor: torch.Tensor, mesh, mesh_dim: int, split_dim:
         return tensor.clone()
     if tensor.shape[split_dim] % n != 0:
         raise ValueError("all_to_all_single needs an evenly divisible split dim")
+    if tensor.element_size() >= 2:
+        sc = _symm(group, tensor)
+        if sc is not None:
+            return sc.all_to_all_permute(tensor, concat_dim, split_dim)
     pieces = [p.contiguous() for p in tensor.chunk(n, dim=split_dim)]
     if _backend(group) == "nccl":
         send = torch.stack(pieces, 0)

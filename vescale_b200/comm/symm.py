@@ -24,7 +24,7 @@ import torch.distributed as dist
 
 from ..ops import _ext
 
-__all__ = ["SymmArena", "SymmUnitComm", "symm_available"]
+__all__ = ["SymmArena", "SymmUnitComm", "symm_available", "get_unit_comm"]
 
 _MAX_SLOTS = 2048  # signal slots per rank
 
@@ -143,6 +143,7 @@ class SymmUnitComm:
         self.use_multimem = os.environ.get("VESCALE_B200_MULTIMEM", "1") == "1"
         self.ops = _ext.ops()
         self._unit_slots: Dict[int, Tuple[int, int, int]] = {}
+        self._fused_sites: Dict[Tuple[int, str], dict] = {}
         self._epochs: Dict[Tuple[int, str], int] = {}
         self.ag_ctas = int(os.environ.get("VESCALE_B200_AG_CTAS", "0"))
         self.rs_ctas = int(os.environ.get("VESCALE_B200_RS_CTAS", "0"))
@@ -166,13 +167,70 @@ class SymmUnitComm:
         return self._epochs[k]
 
     # ------------------------------------------------------------------ collectives (launch on the current stream)
-    def all_gather(self, shard: torch.Tensor, full: torch.Tensor, unit) -> None:
+    def all_gather(self, shard: torch.Tensor, full: torch.Tensor, unit, *, only: Optional[Tuple[int, int]] = None, skip: Optional[Tuple[int, int]] = None) -> None:
+        """Pull all-gather of the unit.  ``only=(lo, hi)`` gathers just that element range of the flat unit (small parameters
+        needed before a fused first GEMM); ``skip=(lo, hi)`` gathers everything else (the fused kernel gathers that range)."""
         ag_slot, _, _ = self._slots(unit)
         epoch = self._bump(unit, "ag")
+        esz = shard.element_size()
+        mode, lo, hi = (1, *only) if only is not None else (2, *skip) if skip is not None else (0, 0, 0)
+        if mode == 2 and (lo * esz) % 16:
+            raise ValueError("skip range must start on a 16-byte boundary")
+        if mode == 2:
+            hi = hi * esz // 16 * 16 // esz  # never skip a partially covered vector
         _ext.count_launch("symm_all_gather")
         self.ops.symm_all_gather(
-            self.arena.peer_ptrs(shard), full, shard.numel() * shard.element_size(), self.rank, self.arena.pad_ptrs, ag_slot, epoch, self.ag_ctas
+            self.arena.peer_ptrs(shard), full, shard.numel() * esz, self.rank, self.arena.pad_ptrs, ag_slot, epoch, self.ag_ctas, mode, lo * esz // 16 * 16, hi * esz
         )
+
+    # ------------------------------------------------------------------ all-gather ⊕ first GEMM of the unit (SURVEY §2F C1/C8)
+    def fusable_slot(self, unit, name: str):
+        """The layout slot of weight ``name`` if the fused kernel can gather it: 2-D bf16, N % 256 == 0, K % 256 == 0 and every
+        rank boundary inside it on a multiple of 32 rows (``fully_shard(..., block_rows=32)``)."""
+        slot = unit.layout.slot(name)
+        if len(slot.shape) != 2 or unit.param_dtype != torch.bfloat16:
+            return None
+        N, K = slot.shape
+        if N % 256 or K % 256 or slot.offset % 8:
+            return None
+        S = unit.layout.shard_size
+        for p in range(self.world + 1):
+            b = min(max(p * S, slot.offset), slot.end) - slot.offset
+            if b % (32 * K):
+                return None
+        return slot
+
+    def fused_first_linear(self, x: torch.Tensor, unit, slot, full: torch.Tensor) -> torch.Tensor:
+        """y = x @ W^T where W (``slot``) is gathered from the peers' parameter shards *by the GEMM kernel itself*, straight into
+        its place in ``full``; the math starts as soon as the first 256 rows have arrived."""
+        N, K = slot.shape
+        M = x.shape[0]
+        if x.dtype != torch.bfloat16 or not x.is_contiguous() or M % 256:
+            raise ValueError("fused_first_linear needs a contiguous bf16 activation with a multiple of 256 rows")
+        S, W = unit.layout.shard_size, self.world
+        key = (id(unit), slot.name)
+        st = self._fused_sites.get(key)
+        if st is None:
+            s0 = self.arena.new_slots(2)
+            bounds, ptrs = [0], []
+            base = self.arena.peer_ptrs(unit.param_shard)
+            for p in range(W):
+                lo, hi = min(max(p * S, slot.offset), slot.end), min(max((p + 1) * S, slot.offset), slot.end)
+                bounds.append((hi - slot.offset) // K)
+                ptrs.append(base[p] + (lo - p * S) * 2 if hi > lo else base[p])
+            st = self._fused_sites[key] = {
+                "epoch": 0,
+                "flag_ptrs": [q + s0 * W * 4 for q in self.arena.pad_ptrs],
+                "arrive": torch.zeros(N // 256, dtype=torch.int32, device=self.device),
+                "bounds": bounds,
+                "ptrs": ptrs,
+            }
+        st["epoch"] += 1
+        w_full = full[slot.offset : slot.end].view(N, K)
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+        _ext.count_launch("wag_gemm")
+        self.ops.wag_gemm(x, w_full, st["ptrs"], st["bounds"], y, st["arrive"], st["flag_ptrs"], self.rank, st["epoch"])
+        return y
 
     def wait_buffer_free(self, buf: torch.Tensor) -> None:
         """Before a symmetric gradient buffer is reused: every peer must have finished reading it."""
@@ -217,3 +275,15 @@ class SymmUnitComm:
         _ext.count_launch("symm_signal")
         self.ops.symm_signal(self.arena.pad_ptrs, self.rank, done_slot, epoch)
         full_grad._symm_last_use = (done_slot, epoch)
+
+
+# one arena per (process group, device): FSDP units, fused TP layers, MoE dispatch and the tensor collectives all share it
+_COMM_CACHE: Dict[Tuple[int, Optional[int]], "SymmUnitComm"] = {}
+
+
+def get_unit_comm(mesh, mesh_dim: int, device: torch.device) -> "SymmUnitComm":
+    key = (id(mesh.get_group(mesh_dim)), device.index)
+    comm = _COMM_CACHE.get(key)
+    if comm is None:
+        comm = _COMM_CACHE[key] = SymmUnitComm(mesh, mesh_dim, device)
+    return comm

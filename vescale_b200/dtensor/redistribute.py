@@ -121,20 +121,8 @@ def _ragged_to_replicate(local: torch.Tensor, mesh, i: int, rp: RaggedShard, bef
 def _ragged_to_ragged(local: torch.Tensor, mesh, i: int, src: RaggedShard, dst: RaggedShard, numel: int, coord) -> torch.Tensor:
     """Uneven all-to-all by intersecting source and destination flat intervals
     (reference ``placement_types.py:152-192``)."""
-    n, me = mesh.size(i), coord[i]
-    s_lo, s_hi = src.flat_range(numel, me)
-    ins = []
-    for j in range(n):
-        d_lo, d_hi = dst.flat_range(numel, j)
-        lo, hi = max(s_lo, d_lo), min(s_hi, d_hi)
-        ins.append(local.narrow(0, lo - s_lo, hi - lo) if hi > lo else local.new_empty(0))
-    d_lo, d_hi = dst.flat_range(numel, me)
-    out_sizes = []
-    for j in range(n):
-        lo, hi = src.flat_range(numel, j)
-        out_sizes.append(max(0, min(hi, d_hi) - max(lo, d_lo)))
-    outs = C.mesh_all_to_all_uneven(ins, out_sizes, mesh, i)
-    return torch.cat(outs) if outs else local.new_empty(0)
+    n = mesh.size(i)
+    return C.mesh_ragged_exchange(local, [src.flat_range(numel, j) for j in range(n)], [dst.flat_range(numel, j) for j in range(n)], mesh, i)
 
 
 # --------------------------------------------------------------------------- planner / executor

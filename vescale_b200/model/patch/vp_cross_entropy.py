@@ -58,3 +58,23 @@ class VocabParallelCrossEntropy:
         _, off = compute_local_shape_and_global_offset(logits.shape, mesh, logits.placements)
         t = target._local_tensor if isinstance(target, DTensor) else target
         return _VPCE.apply(logits.to_local(), t, mesh, md, off[-1], label_smoothing, logits.shape[-1])
+
+    @staticmethod
+    def mean(logits: DTensor, target, ignore_index: int = -100) -> torch.Tensor:
+        """Mean token loss.  When the symmetric-memory collectives are enabled on the vocab mesh dim (and the logits are an
+        evenly sharded bf16 CUDA tensor) this is ONE kernel launch — local max/sum-exp, a W-way statistics exchange through
+        peer memory and the gradient written in place — and it CONSUMES the logits buffer.  Otherwise the
+        three-all-reduce algorithm above."""
+        from ...comm.symm_collectives import symm_backend_for
+
+        mesh = logits.device_mesh
+        md = next(i for i, p in enumerate(logits.placements) if isinstance(p, Shard) and p.dim == logits.ndim - 1)
+        t = target._local_tensor if isinstance(target, DTensor) else target
+        local = logits.to_local()
+        sc = symm_backend_for(mesh.get_group(md), local) if mesh.size(md) > 1 else None
+        V, W = logits.shape[-1], mesh.size(md)
+        if sc is not None and local.dtype == torch.bfloat16 and local.is_contiguous() and V % (8 * W) == 0:
+            return sc.vocab_parallel_cross_entropy(local, t, ignore_index)
+        per_tok = VocabParallelCrossEntropy.apply(logits, t.clamp(min=0))
+        valid = (t != ignore_index).to(per_tok.dtype)
+        return (per_tok * valid).sum() / valid.sum().clamp(min=1)

@@ -79,6 +79,8 @@ def llama_flops_per_token(cfg: LlamaConfig, seq_len: int) -> float:
 
 
 class LlamaBlock(nn.Module):
+    fsdp_first_gemm_param = "wqkv"  # fully_shard(..., fuse_first_gemm=True): the weight of the block's first GEMM
+
     def __init__(self, cfg: LlamaConfig, layer_idx: int, device=None):
         super().__init__()
         self.cfg = cfg

@@ -95,6 +95,9 @@ def _tcgen05_ok(a: torch.Tensor, b: torch.Tensor) -> bool:
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, accumulate: bool = False) -> torch.Tensor:
     """``out (+)= a[M,K] @ b[N,K]^T`` — both operands K-major (the nn.Linear forward shape).
     tcgen05/TMA/TMEM kernel on sm_100a (``csrc/gemm_sm100.cu``); cuBLAS otherwise."""
+    pending = getattr(b, "_vb_pending_gather", None)
+    if pending is not None:  # FSDP: this weight is gathered by the GEMM kernel itself (all-gather ⊕ first GEMM of the unit)
+        return pending(a, out)
     if _tcgen05_ok(a, b) and (out is None or out.is_contiguous()):
         use = True
         if _CFG["gemm"] == "auto" and not accumulate:

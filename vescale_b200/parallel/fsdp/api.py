@@ -122,8 +122,67 @@ class FSDPState:
         u._ag_full = full
         u._ag_direct = False
 
+    def launch_fused_gather(self, u: FSDPUnit) -> bool:
+        """Exposed (not prefetched) forward all-gather of a unit whose first GEMM weight is known: the GEMM kernel gathers
+        that weight itself (``SymmUnitComm.fused_first_linear``), small parameters are pulled first by a tiny launch, and the
+        rest of the unit streams in on the all-gather stream *behind* the first GEMM."""
+        comm = u.comm
+        name = getattr(u, "fused_first", None)
+        if not name or comm is None or not getattr(comm, "symmetric", False) or u.world == 1 or self.in_backward:
+            return False
+        slot = getattr(u, "_fused_slot", False)
+        if slot is False:
+            slot = u._fused_slot = comm.fusable_slot(u, name) if name in u.param_names else None
+        if slot is None:
+            return False
+        persistent = not self.reshard_after_forward
+        if persistent and getattr(u, "_persistent_full", None) is not None:
+            full = u._persistent_full
+        else:
+            full = self.pool.get(u.S * u.world, u.param_dtype, self.ag_stream, lambda: u._alloc_full(u.param_dtype))
+            if persistent:
+                u._persistent_full = full
+        u.refresh_param_shard()
+        for s in u.layout.slots:  # norm weights / biases: needed before the first GEMM, a few KB each
+            if s is not slot and s.numel <= 65536:
+                comm.all_gather(u.param_shard, full, u, only=(s.offset, s.end))
+        self.ag_stream.wait_stream(self.cur_stream())
+        with self.on(self.ag_stream):
+            comm.all_gather(u.param_shard, full, u, skip=(slot.offset, slot.end))
+            evt = make_event(self.device)
+            evt.record(self.ag_stream)
+        u.use_full(full)
+        u._params_valid = True
+        u._ag_direct = False
+        param = u.params[u.param_names.index(name)]
+        state = self
+
+        def pending(a: torch.Tensor, out=None):
+            del param._vb_pending_gather
+            u._pending_param = None
+            a2 = a.reshape(-1, a.shape[-1])
+            if a2.dtype == torch.bfloat16 and a2.is_contiguous() and a2.shape[0] % 256 == 0:
+                y = comm.fused_first_linear(a2, u, slot, full)
+                state.cur_stream().wait_event(evt)
+            else:  # shape the kernel does not take: gather the weight the ordinary way
+                comm.all_gather(u.param_shard, full, u, only=(slot.offset, slot.end))
+                state.cur_stream().wait_event(evt)
+                from ...ops import functional as Fn
+
+                y = Fn.gemm_nt(a2, param)
+            if out is not None:
+                return out.copy_(y.view(out.shape))
+            return y.view(*a.shape[:-1], y.shape[-1])
+
+        param._vb_pending_gather = pending
+        u._pending_param = param
+        u._pending_evt = evt
+        return True
+
     def wait_all_gather(self, u: FSDPUnit) -> None:
         if u.unsharded:
+            return
+        if u.ag_event is None and self.launch_fused_gather(u):
             return
         if u.ag_event is None:
             self.launch_all_gather(u)
@@ -136,6 +195,15 @@ class FSDPState:
         u._params_valid = True
 
     def reshard(self, u: FSDPUnit) -> None:
+        pend = getattr(u, "_pending_param", None)
+        if pend is not None:
+            # the module never ran the GEMM that was meant to gather this weight: finish the gather the ordinary way
+            del pend._vb_pending_gather
+            u._pending_param = None
+            slot = u._fused_slot
+            u.comm.all_gather(u.param_shard, u.full_param, u, only=(slot.offset, slot.end))
+            self.cur_stream().wait_event(u._pending_evt)
+            raise RuntimeError(f"FSDP unit {u.name}: fuse_first_gemm={u.fused_first!r} but that weight was not the first GEMM of the forward")
         if not u.unsharded or u.world == 1:
             return
         if not self.reshard_after_forward:
@@ -353,7 +421,7 @@ def fsdp_units(module: nn.Module) -> List[FSDPUnit]:
 
 
 _STATES: Dict[int, FSDPState] = {}
-_COMM_CACHE: Dict[Tuple[int, Optional[int]], Any] = {}
+from ...comm.symm import _COMM_CACHE  # noqa: E402  (shared arena cache; re-exported for FusedTP / MoE)
 
 
 def fully_shard(
@@ -369,13 +437,23 @@ def fully_shard(
     granularity_fn=None,
     init_fn: Optional[Callable[[nn.Module], None]] = None,
     state: Optional[FSDPState] = None,
+    fuse_first_gemm: bool | str | None = None,
 ) -> nn.Module:
     """Shard the parameters of ``module`` that are not already managed by an inner ``fully_shard``.
 
     Call bottom-up (inner blocks first, root last), like torch's FSDP2.  ``comm_backend``: ``"nccl"`` (c10d
     collectives; also what CPU/gloo tests use), ``"symm"`` (sm_100a symmetric-memory kernels) or ``"auto"``
     (symm on CUDA when the world has more than one rank and the extension is loaded).
+
+    ``fuse_first_gemm``: name of the weight consumed by the module's first GEMM (``True`` = the module's
+    ``fsdp_first_gemm_param`` attribute).  When this unit's forward all-gather is *exposed* (not prefetched), that weight
+    is gathered by the GEMM kernel itself and the rest of the unit streams in behind it; needs ``comm_backend="symm"``
+    and ``block_rows`` a multiple of 32 (forced to 32 when left at 1).
     """
+    if fuse_first_gemm is True:
+        fuse_first_gemm = getattr(module, "fsdp_first_gemm_param", None)
+    if fuse_first_gemm and block_rows % 32:
+        block_rows = 32 * block_rows
     if mesh is None:
         mesh = init_device_mesh("cuda" if torch.cuda.is_available() else "cpu", (dist.get_world_size() if dist.is_initialized() else 1,))
     md = mesh._dim_index(mesh_dim)
@@ -440,6 +518,7 @@ def fully_shard(
     u = FSDPUnit(module, uniq, mesh, md, mp_policy, name=type(module).__name__, comm=state.comm, block_rows=block_rows, granularity_fn=granularity_fn)
     u._swap = _ParamSwap(u, owners)
     u._state = state
+    u.fused_first = fuse_first_gemm or None
     module._fsdp_unit = u
     # keep units in module-traversal order of the outermost wrapped module seen so far
     state.units.append(u)
