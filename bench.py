@@ -44,6 +44,8 @@ def parse():
     p.add_argument("--reshard", default="auto", choices=["auto", "yes", "no"])
     p.add_argument("--max-grad-norm", type=float, default=1.0)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--prefetch", type=int, default=1, help="FSDP all-gather prefetch depth (0 = every all-gather exposed: the memory-lean mode)")
+    p.add_argument("--fuse-first-gemm", action="store_true", help="exposed all-gathers: the unit's first GEMM gathers its own weight (wag_gemm)")
     p.add_argument("--profile", default=None, help="after the timed regions, run ONE extra step under torch.profiler and write the per-kernel table here")
     return p.parse_args()
 
@@ -188,10 +190,10 @@ def main():
                 mod.norm.fill_(1.0)
                 mod.weight.normal_(0, cfg.init_std, generator=g)
 
-    kw = dict(comm_backend=args.comm, reshard_after_forward=reshard, init_fn=init_fn)
+    kw = dict(comm_backend=args.comm, reshard_after_forward=reshard, init_fn=init_fn, prefetch=args.prefetch)
     fully_shard(model.embed, mesh, **kw)
     for blk in model.layers:
-        fully_shard(blk, mesh, **kw)
+        fully_shard(blk, mesh, fuse_first_gemm=bool(args.fuse_first_gemm and world > 1), **kw)
     fully_shard(model.head, mesh, **kw)
     fully_shard(model, mesh, **kw)
     opt = FSDPAdamW(model, lr=3e-4, betas=(0.9, 0.95), weight_decay=0.1, max_grad_norm=args.max_grad_norm)
@@ -318,6 +320,8 @@ def main():
             "comm_backend": comm_name,
             "gemm_backend": args.gemm,
             "reshard_after_forward": bool(reshard),
+            "prefetch": args.prefetch,
+            "fuse_first_gemm": bool(args.fuse_first_gemm),
             "optimizer": "AdamW fp32 master/m/v, global-norm clip 1.0" if args.max_grad_norm else "AdamW fp32 master/m/v, no clip",
             "activation_memory": "selective recompute (norm and SwiGLU outputs recomputed)",
             "l2_policy": "no explicit flush: per-step working set (>100 GB of weights/optimizer state/activations) is ~1000x the 126 MB L2",

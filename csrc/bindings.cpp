@@ -50,7 +50,7 @@ void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector
              int64_t rank, int64_t epoch);
 
 void wag_gemm(const at::Tensor& x, at::Tensor w_full, std::vector<int64_t> shard_ptrs, std::vector<int64_t> row_bounds, at::Tensor y, at::Tensor arrive,
-              std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch);
+              std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch, bool wait_peers);
 void grouped_gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, const at::Tensor& tile_expert, int64_t expert_n);
 // moe_dispatch.cu
 void moe_exchange_counts(const at::Tensor& my_counts, std::vector<int64_t> counts_all_ptrs, std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch);
@@ -96,7 +96,7 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("symm_all_gather(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int num_ctas, int range_mode=0, int range_lo_bytes=0, int range_hi_bytes=0) -> ()");
   m.def("symm_reduce_scatter(int[] grad_ptrs, Tensor(a!) out, Tensor(b!)? sumsq, int shard_elems, int rank, float scale, int[] pad_ptrs, int slot, int epoch, int multicast_ptr, int num_ctas) -> ()");
   m.def("symm_rs_adamw(int[] grad_ptrs, Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor(d!) p_out, Tensor wd_table, Tensor coef, Tensor(e!)? sumsq, int rank, float scale, int[] pad_ptrs, int slot, int epoch, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int num_ctas) -> ()");
-  m.def("wag_gemm(Tensor x, Tensor(a!) w_full, int[] shard_ptrs, int[] row_bounds, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch) -> ()");
+  m.def("wag_gemm(Tensor x, Tensor(a!) w_full, int[] shard_ptrs, int[] row_bounds, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch, bool wait_peers=True) -> ()");
   m.def("symm_all_reduce(int[] buf_ptrs, int multicast_ptr, Tensor(a!)? out, int numel, int dtype_code, float scale, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(b!) counter, int num_ctas) -> ()");
   m.def("symm_a2a_permute(Tensor src, int[] dst_ptrs, int[] n, int[] ss, int[] ds, int src_peer_stride, int dst_rank_stride, int vec_bytes, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(a!) counter, int num_ctas) -> ()");
   m.def("symm_put_segments(Tensor src, int[] dst_ptrs, Tensor table, int vec_bytes, int total_vecs, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(a!) counter, int num_ctas) -> ()");

@@ -89,6 +89,7 @@ struct FusedArgs {
   PtrArray flags;        // peer p's flag array: [W] uint32 "slot src complete" ; entry [W + src] = "entered"
   // wag_gemm
   int rb[kMaxW + 1];     // weight-row ownership boundaries: rank p owns rows [rb[p], rb[p+1])
+  int wait_peers;        // 0: the caller knows every peer's shard is already final (a handshake happened earlier this step)
 };
 
 // MODE 1 = ag_gemm, MODE 2 = gemm_rs, MODE 3 = wag_gemm
@@ -239,7 +240,8 @@ fused_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   } else if (warp == 3) {
     if (MODE == 3 && lane == 0) {
       // ===================== TMA copy engine: every rank's weight rows -> local gathered weight =====================
-      for (int p = 0; p < W; ++p) spin_ge_sys(my_flags + W + p, fa.epoch);
+      if (fa.wait_peers)
+        for (int p = 0; p < W; ++p) spin_ge_sys(my_flags + W + p, fa.epoch);
       const int boxes_per_row = K / kCopyCols;
       const int row_boxes = N / kCopyRows;
       const int rot = fa.rb[rank] / kCopyRows;
@@ -493,7 +495,7 @@ void gemm_rs(const at::Tensor& x, const at::Tensor& w, at::Tensor y, std::vector
 // x [M, K]; w_full [N, K] = the weight's slice of the unit's gathered buffer (filled by this kernel); shard_ptrs[p] = address
 // of the first row rank p owns (inside its symmetric parameter shard); row_bounds[W+1] = ownership boundaries.
 void wag_gemm(const at::Tensor& x, at::Tensor w_full, std::vector<int64_t> shard_ptrs, std::vector<int64_t> row_bounds, at::Tensor y, at::Tensor arrive,
-              std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch) {
+              std::vector<int64_t> flag_ptrs, int64_t rank, int64_t epoch, bool wait_peers) {
   const int W = shard_ptrs.size();
   TORCH_CHECK(W >= 1 && W <= kMaxW && (int)row_bounds.size() == W + 1);
   const int64_t M = x.size(0), K = x.size(1), N = w_full.size(0);
@@ -519,6 +521,7 @@ void wag_gemm(const at::Tensor& x, at::Tensor w_full, std::vector<int64_t> shard
   fa.arrive = reinterpret_cast<uint32_t*>(arrive.data_ptr<int>());
   fa.copy_units_per_blk = (kBN / kCopyRows) * (K / kCopyCols);
   fa.flags = to_ptr_array(flag_ptrs);
+  fa.wait_peers = wait_peers ? 1 : 0;
   const int smem = fused_smem_bytes();
   static bool attr = false;
   if (!attr) {

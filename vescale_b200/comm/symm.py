@@ -167,7 +167,8 @@ class SymmUnitComm:
         return self._epochs[k]
 
     # ------------------------------------------------------------------ collectives (launch on the current stream)
-    def all_gather(self, shard: torch.Tensor, full: torch.Tensor, unit, *, only: Optional[Tuple[int, int]] = None, skip: Optional[Tuple[int, int]] = None) -> None:
+    def all_gather(self, shard: torch.Tensor, full: torch.Tensor, unit, *, only: Optional[Tuple[int, int]] = None, skip: Optional[Tuple[int, int]] = None,
+                   handshake: bool = True) -> None:
         """Pull all-gather of the unit.  ``only=(lo, hi)`` gathers just that element range of the flat unit (small parameters
         needed before a fused first GEMM); ``skip=(lo, hi)`` gathers everything else (the fused kernel gathers that range)."""
         ag_slot, _, _ = self._slots(unit)
@@ -180,7 +181,8 @@ class SymmUnitComm:
             hi = hi * esz // 16 * 16 // esz  # never skip a partially covered vector
         _ext.count_launch("symm_all_gather")
         self.ops.symm_all_gather(
-            self.arena.peer_ptrs(shard), full, shard.numel() * esz, self.rank, self.arena.pad_ptrs, ag_slot, epoch, self.ag_ctas, mode, lo * esz // 16 * 16, hi * esz
+            self.arena.peer_ptrs(shard), full, shard.numel() * esz, self.rank, self.arena.pad_ptrs if handshake else [], ag_slot, epoch, self.ag_ctas, mode,
+            lo * esz // 16 * 16, hi * esz,
         )
 
     # ------------------------------------------------------------------ all-gather ⊕ first GEMM of the unit
@@ -200,7 +202,7 @@ class SymmUnitComm:
                 return None
         return slot
 
-    def fused_first_linear(self, x: torch.Tensor, unit, slot, full: torch.Tensor) -> torch.Tensor:
+    def fused_first_linear(self, x: torch.Tensor, unit, slot, full: torch.Tensor, handshake: bool = True) -> torch.Tensor:
         """y = x @ W^T where W (``slot``) is gathered from the peers' parameter shards *by the GEMM kernel itself*, straight into
         its place in ``full``; the math starts as soon as the first 256 rows have arrived."""
         N, K = slot.shape
@@ -229,7 +231,7 @@ class SymmUnitComm:
         w_full = full[slot.offset : slot.end].view(N, K)
         y = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
         _ext.count_launch("wag_gemm")
-        self.ops.wag_gemm(x, w_full, st["ptrs"], st["bounds"], y, st["arrive"], st["flag_ptrs"], self.rank, st["epoch"])
+        self.ops.wag_gemm(x, w_full, st["ptrs"], st["bounds"], y, st["arrive"], st["flag_ptrs"], self.rank, st["epoch"], handshake)
         return y
 
     def wait_buffer_free(self, buf: torch.Tensor) -> None:

@@ -62,14 +62,39 @@ class SymmCollectives:
         self.epoch += 1
         return self.epoch
 
+    def empty(self, shape, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        """A tensor in symmetric memory (same call sequence on every rank).  Collectives on such tensors are zero-copy: no
+        staging pass in, none out."""
+        shape = tuple(shape) if not isinstance(shape, int) else (shape,)
+        return self.arena.alloc(math.prod(shape), dtype).view(shape)
+
+    def _is_symmetric(self, x: torch.Tensor) -> bool:
+        try:
+            self.arena._locate(x)
+            return True
+        except ValueError:
+            return False
+
     # ------------------------------------------------------------------ all-reduce
     def all_reduce(self, x: torch.Tensor, op: str = "sum") -> torch.Tensor:
-        """In-place sum / avg of a contiguous bf16 or fp32 CUDA tensor over the mesh dim."""
+        """Sum / avg of a contiguous bf16 or fp32 CUDA tensor over the mesh dim; returns the reduced tensor (``x`` itself, reduced
+        in place, except for small tensors that already live in symmetric memory: those are reduced one-shot into a new tensor)."""
         if x.dtype not in _DT or not x.is_contiguous() or op not in ("sum", "avg"):
             raise ValueError("symmetric all_reduce handles contiguous bf16/fp32 sum/avg")
         if x.numel() == 0:
             return x
         nbytes = x.numel() * x.element_size()
+        if nbytes % 16 == 0 and x.data_ptr() % 16 == 0 and self._is_symmetric(x):  # zero-copy
+            scale = 1.0 / self.world if op == "avg" else 1.0
+            ptrs = self.arena.peer_ptrs(x)
+            _ext.count_launch("symm_all_reduce")
+            if nbytes <= _ONESHOT_BYTES:
+                out = torch.empty_like(x)
+                self.ops.symm_all_reduce(ptrs, 0, out, x.numel(), _DT[x.dtype], scale, self.rank, self.arena.pad_ptrs, self.slot, self._next(), self.counter, self.num_ctas)
+                return out
+            mc = self.arena.multicast_ptr(x) if self.use_multimem else 0
+            self.ops.symm_all_reduce(ptrs, mc, None, x.numel(), _DT[x.dtype], scale, self.rank, self.arena.pad_ptrs, self.slot, self._next(), self.counter, self.num_ctas)
+            return x
         padded = (nbytes + 15) // 16 * 16
         st = self._stage(padded)
         flat = x.view(-1).view(torch.uint8)

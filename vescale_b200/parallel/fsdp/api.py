@@ -83,6 +83,7 @@ class FSDPState:
         self.exposed_wait_ms = 0.0
         self.comm = None
         self.iteration = 0
+        self._handshake_iter = -1  # iteration in which a gather already exchanged "my shards are final" flags
 
     # ------------------------------------------------------------------ stream helpers
     def cur_stream(self):
@@ -95,6 +96,13 @@ class FSDPState:
                 yield
         else:
             yield
+
+    def _need_handshake(self) -> bool:
+        """One flag exchange per optimizer step is enough: a peer's signal follows its whole optimizer step in stream order, so
+        every one of its shards is final; later gathers of the same step (forward and backward) skip the exchange."""
+        need = self._handshake_iter != self.iteration
+        self._handshake_iter = self.iteration
+        return need
 
     # ------------------------------------------------------------------ unshard / reshard
     def launch_all_gather(self, u: FSDPUnit) -> None:
@@ -114,8 +122,9 @@ class FSDPState:
                 u._persistent_full = full
         # the shard may have just been written by the optimizer on the compute stream
         self.ag_stream.wait_stream(self.cur_stream())
+        hs = self._need_handshake()
         with self.on(self.ag_stream):
-            u.all_gather(full)
+            u.all_gather(full, handshake=hs)
             evt = make_event(self.device)
             evt.record(self.ag_stream if self.cuda else None)
         u.ag_event = evt
@@ -142,13 +151,14 @@ class FSDPState:
             full = self.pool.get(u.S * u.world, u.param_dtype, self.ag_stream, lambda: u._alloc_full(u.param_dtype))
             if persistent:
                 u._persistent_full = full
-        u.refresh_param_shard()
+        hs = u.refresh_param_shard() or self._need_handshake()
         for s in u.layout.slots:  # norm weights / biases: needed before the first GEMM, a few KB each
             if s is not slot and s.numel <= 65536:
-                comm.all_gather(u.param_shard, full, u, only=(s.offset, s.end))
+                comm.all_gather(u.param_shard, full, u, only=(s.offset, s.end), handshake=hs)
+                hs = False
         self.ag_stream.wait_stream(self.cur_stream())
         with self.on(self.ag_stream):
-            comm.all_gather(u.param_shard, full, u, skip=(slot.offset, slot.end))
+            comm.all_gather(u.param_shard, full, u, skip=(slot.offset, slot.end), handshake=hs)
             evt = make_event(self.device)
             evt.record(self.ag_stream)
         u.use_full(full)
@@ -162,10 +172,10 @@ class FSDPState:
             u._pending_param = None
             a2 = a.reshape(-1, a.shape[-1])
             if a2.dtype == torch.bfloat16 and a2.is_contiguous() and a2.shape[0] % 256 == 0:
-                y = comm.fused_first_linear(a2, u, slot, full)
+                y = comm.fused_first_linear(a2, u, slot, full, handshake=False)
                 state.cur_stream().wait_event(evt)
             else:  # shape the kernel does not take: gather the weight the ordinary way
-                comm.all_gather(u.param_shard, full, u, only=(slot.offset, slot.end))
+                comm.all_gather(u.param_shard, full, u, only=(slot.offset, slot.end), handshake=False)
                 state.cur_stream().wait_event(evt)
                 from ...ops import functional as Fn
 

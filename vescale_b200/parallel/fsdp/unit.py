@@ -166,21 +166,23 @@ class FSDPUnit:
         return self.S * self.world * torch.empty((), dtype=self.param_dtype).element_size()
 
     # ------------------------------------------------------------------ parameter (un)sharding
-    def refresh_param_shard(self) -> None:
+    def refresh_param_shard(self) -> bool:
         """bf16 shard <- master (needed when a foreign optimizer updated the fp32 DTensor params)."""
         if not self.bf16_fresh:
             self.param_shard.copy_(self.master)
             self.bf16_fresh = True
+            return True
+        return False
 
-    def all_gather(self, full: torch.Tensor) -> None:
+    def all_gather(self, full: torch.Tensor, handshake: bool = True) -> None:
         """Launch the all-gather of the unit into ``full`` on the current stream."""
-        self.refresh_param_shard()
+        handshake = self.refresh_param_shard() or handshake
         if self.world == 1:
             if full.data_ptr() != self.param_shard.data_ptr():
                 full.copy_(self.param_shard)
             return
         if self.comm is not None:
-            self.comm.all_gather(self.param_shard, full, self)
+            self.comm.all_gather(self.param_shard, full, self, handshake=handshake)
         else:
             dist.all_gather_into_tensor(full, self.param_shard, group=self.group)
 
