@@ -44,6 +44,8 @@ def parse():
     p.add_argument("--reshard", default="auto", choices=["auto", "yes", "no"])
     p.add_argument("--max-grad-norm", type=float, default=1.0)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--tp", type=int, default=1, help="tensor/sequence-parallel degree (2-D: FSDP over world/tp x TP over tp, fused TP kernels)")
+    p.add_argument("--tp-impl", default="fused", choices=["fused", "plain"], help="fused = ag_gemm/gemm_rs sm_100a kernels; plain = NCCL + library GEMMs")
     p.add_argument("--prefetch", type=int, default=1, help="FSDP all-gather prefetch depth (0 = every all-gather exposed: the memory-lean mode)")
     p.add_argument("--fuse-first-gemm", action="store_true", help="exposed all-gathers: the unit's first GEMM gathers its own weight (wag_gemm)")
     p.add_argument("--profile", default=None, help="after the timed regions, run ONE extra step under torch.profiler and write the per-kernel table here")
@@ -166,20 +168,33 @@ def main():
         invalid = f"layers overridden to {args.layers}"
     S, B = args.seq_len, args.micro_batch
     cfg.max_seq_len = max(cfg.max_seq_len, S)
-    mesh = init_device_mesh("cuda", (world,), **({} if world > 1 else {"_init_process_groups": False}))
+    tp_size = args.tp
+    if world % tp_size:
+        raise SystemExit("--tp must divide the number of GPUs")
+    dp_size = world // tp_size
+    tp = None
+    if tp_size > 1:
+        from vescale_b200.comm.fused_tp import FusedTP, PlainTP
+        from vescale_b200.models.llama_tp import LlamaTPModel
+
+        mesh = init_device_mesh("cuda", (dp_size, tp_size), mesh_dim_names=("dp", "tp"))
+        tp = FusedTP(mesh, "tp", dev) if args.tp_impl == "fused" else PlainTP(mesh, "tp")
+    else:
+        mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("dp",), **({} if world > 1 else {"_init_process_groups": False}))
+    dp_rank = mesh.get_local_rank("dp") if world > 1 else 0
 
     # ---- build: meta-device model, materialised unit by unit straight into the sharded master weights
     torch.manual_seed(1234)
     with torch.device("meta"):
-        model = LlamaModel(cfg)
+        model = LlamaModel(cfg) if tp is None else LlamaTPModel(cfg, tp)
     reshard = {"auto": None, "yes": True, "no": False}[args.reshard]
     if reshard is None:
         # keep gathered bf16 weights resident when they fit comfortably (ZeRO-2-style): saves the backward all-gather
-        reshard = not (world > 1 and cfg.num_params() * 2 < 40e9)
+        reshard = not (dp_size > 1 and cfg.num_params() * 2 / tp_size < 40e9)
     gens = {}
 
     def init_fn(mod):
-        g = gens.setdefault("g", torch.Generator(device=dev).manual_seed(1234))
+        g = gens.setdefault("g", torch.Generator(device=dev).manual_seed(1234 + 7 * (mesh.get_local_rank("tp") if tp is not None else 0)))
         if hasattr(mod, "reset_parameters"):
             mod.reset_parameters(g) if isinstance(mod, type(model.layers[0])) else None
         if mod is model.embed:
@@ -190,19 +205,19 @@ def main():
                 mod.norm.fill_(1.0)
                 mod.weight.normal_(0, cfg.init_std, generator=g)
 
-    kw = dict(comm_backend=args.comm, reshard_after_forward=reshard, init_fn=init_fn, prefetch=args.prefetch)
+    kw = dict(comm_backend=args.comm, reshard_after_forward=reshard, init_fn=init_fn, prefetch=args.prefetch, mesh_dim="dp")
     fully_shard(model.embed, mesh, **kw)
     for blk in model.layers:
-        fully_shard(blk, mesh, fuse_first_gemm=bool(args.fuse_first_gemm and world > 1), **kw)
+        fully_shard(blk, mesh, fuse_first_gemm=bool(args.fuse_first_gemm and dp_size > 1 and tp is None), **kw)
     fully_shard(model.head, mesh, **kw)
     fully_shard(model, mesh, **kw)
-    opt = FSDPAdamW(model, lr=3e-4, betas=(0.9, 0.95), weight_decay=0.1, max_grad_norm=args.max_grad_norm)
+    opt = FSDPAdamW(model, lr=3e-4, betas=(0.9, 0.95), weight_decay=0.1, max_grad_norm=args.max_grad_norm, tp_group=mesh.get_group("tp") if tp is not None else None)
     state = model._fsdp_state
-    comm_name = type(state.comm).__name__ if state.comm is not None else ("none" if world == 1 else "nccl")
+    comm_name = type(state.comm).__name__ if state.comm is not None else ("none" if dp_size == 1 else "nccl")
 
     # ---- synthetic data: pinned host batches (e2e) and device-resident copies (kernel-timed)
     n_batches = max(args.steps, 4)
-    g = torch.Generator().manual_seed(1000 + rank)
+    g = torch.Generator().manual_seed(1000 + dp_rank)  # the ranks of one TP group see the same batch
     host_tok = [torch.randint(0, cfg.vocab_size, (B, S + 1), generator=g).pin_memory() for _ in range(n_batches)]
     dev_tok = [t.to(dev) for t in host_tok[:4]]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -257,7 +272,7 @@ def main():
     by_op = dict(_ext.LAUNCH_COUNTER["by_op"])
     _ext.LAUNCH_COUNTER["enabled"] = False
     clocks = sampler.stop() if rank == 0 else None
-    final_loss = float(last.item())
+    final_loss = float(last.item()) * tp_size  # TP: the model returns this rank's share (local mean / tp)
 
     # ---- timed region 2: end to end through the public API (pinned H2D of the batch + D2H of the loss every step)
     e2e_ms = None
@@ -286,7 +301,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms_max, mem_gb = t.tolist()
-    tokens_per_step = world * B * S
+    tokens_per_step = dp_size * B * S
     tps = tokens_per_step * args.steps / (ms / 1e3)
     flops_tok = llama_flops_per_token(cfg, S)
     peak = 1462.2e12
@@ -313,10 +328,10 @@ def main():
             "model": args.model,
             "layers": cfg.num_layers,
             "params_b": round(cfg.num_params() / 1e9, 3),
-            "global_batch": world * B,
+            "global_batch": dp_size * B,
             "seq_len": S,
-            "tokens_per_gpu_per_step": B * S,
-            "parallelism": f"fsdp{world}",
+            "tokens_per_gpu_per_step": B * S // tp_size,
+            "parallelism": f"fsdp{world}" if tp is None else f"fsdp{dp_size}xtp{tp_size}({args.tp_impl})",
             "comm_backend": comm_name,
             "gemm_backend": args.gemm,
             "reshard_after_forward": bool(reshard),

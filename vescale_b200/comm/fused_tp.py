@@ -17,11 +17,16 @@ import torch.distributed as dist
 
 from ..ops import _ext
 
-__all__ = ["FusedTP"]
+__all__ = ["FusedTP", "PlainTP"]
 
 
 class FusedTP:
-    def __init__(self, mesh, mesh_dim=0, device=None):
+    """``fused_backward=True`` (default) also runs the backward duals on the fused kernels: d(ag_linear)/dx is
+    ``gemm_rs(dy, W^T)`` and d(linear_rs)/dx is ``ag_gemm(dy_local, W^T)``; the transposed weight copy is a
+    few tens of microseconds per layer."""
+
+    def __init__(self, mesh, mesh_dim=0, device=None, fused_backward: bool = True):
+        self.fused_backward = fused_backward
         from ..parallel.fsdp.api import _COMM_CACHE
         from .symm import SymmUnitComm
 
@@ -107,9 +112,12 @@ class _AGLinear(torch.autograd.Function):
         x_full, w = ctx.saved_tensors
         tp = ctx.tp
         dy = dy.contiguous()
-        dx_full = dy @ w  # [M, K] partial over the TP group
-        dx = torch.empty(dx_full.shape[0] // tp.world, dx_full.shape[1], dtype=dx_full.dtype, device=dx_full.device)
-        dist.reduce_scatter_tensor(dx, dx_full, group=tp.group)
+        if tp.fused_backward and dy.shape[0] % (256 * tp.world) == 0 and dy.shape[1] % 64 == 0 and w.shape[1] % 8 == 0:
+            dx = tp.gemm_rs(dy, w.t().contiguous())  # GEMM ⊕ reduce-scatter: [M/W, K]
+        else:
+            dx_full = dy @ w  # [M, K] partial over the TP group
+            dx = torch.empty(dx_full.shape[0] // tp.world, dx_full.shape[1], dtype=dx_full.dtype, device=dx_full.device)
+            dist.reduce_scatter_tensor(dx, dx_full, group=tp.group)
         mg = getattr(w, "main_grad", None)
         if mg is not None:
             from ..ops.functional import gemm_tn
@@ -135,9 +143,12 @@ class _LinearRS(torch.autograd.Function):
         x2, w = ctx.saved_tensors
         tp = ctx.tp
         dy_local = dy_local.contiguous()
-        dy = torch.empty(dy_local.shape[0] * tp.world, dy_local.shape[1], dtype=dy_local.dtype, device=dy_local.device)
-        dist.all_gather_into_tensor(dy, dy_local, group=tp.group)
-        dx = dy @ w
+        if tp.fused_backward and dy_local.shape[0] % 256 == 0 and dy_local.shape[1] % 256 == 0 and w.shape[1] % 8 == 0:
+            dx, dy = tp.ag_gemm(dy_local, w.t().contiguous())  # all-gather ⊕ GEMM; the gathered dy feeds the wgrad
+        else:
+            dy = torch.empty(dy_local.shape[0] * tp.world, dy_local.shape[1], dtype=dy_local.dtype, device=dy_local.device)
+            dist.all_gather_into_tensor(dy, dy_local, group=tp.group)
+            dx = dy @ w
         mg = getattr(w, "main_grad", None)
         if mg is not None:
             from ..ops.functional import gemm_tn
@@ -148,3 +159,72 @@ class _LinearRS(torch.autograd.Function):
         else:
             dw = dy.t() @ x2
         return dx.view(ctx.shape), dw, None
+
+
+class PlainTP:
+    """The same two tensor-parallel linears on ordinary collectives (NCCL / gloo) + library GEMMs: the measured baseline of
+    ``FusedTP`` and the CPU-testable implementation (legacy ``redistribute.py:122,341`` → ``mm`` call pattern)."""
+
+    def __init__(self, mesh, mesh_dim=0):
+        md = mesh._dim_index(mesh_dim)
+        self.mesh, self.md = mesh, md
+        self.group = mesh.get_group(md)
+        self.world = mesh.size(md)
+        self.rank = mesh.get_local_rank(md)
+
+    def ag_linear(self, x_local: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        return _PlainAGLinear.apply(x_local, w, self)
+
+    def linear_rs(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        return _PlainLinearRS.apply(x, w, self)
+
+
+def _wgrad_into(w, dy2, x2):
+    from ..ops.functional import gemm_tn
+
+    mg = getattr(w, "main_grad", None)
+    if mg is not None:
+        gemm_tn(dy2, x2, out=mg, accumulate=getattr(w, "_main_grad_initialised", False))
+        w._main_grad_initialised = True
+        return None
+    return dy2.t() @ x2
+
+
+class _PlainAGLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, w, tp: PlainTP):
+        from . import collectives as C
+
+        x2 = x_local.reshape(-1, x_local.shape[-1]).contiguous()
+        x_full = C.mesh_all_gather(x2, tp.mesh, tp.md, 0)
+        ctx.save_for_backward(x_full, w)
+        ctx.tp, ctx.shape = tp, x_local.shape
+        return x_full @ w.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import collectives as C
+
+        x_full, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = C.mesh_reduce_scatter(dy @ w, ctx.tp.mesh, "sum", ctx.tp.md, 0)
+        return dx.view(ctx.shape), _wgrad_into(w, dy, x_full), None
+
+
+class _PlainLinearRS(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, tp: PlainTP):
+        from . import collectives as C
+
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        ctx.save_for_backward(x2, w)
+        ctx.tp, ctx.shape = tp, x.shape
+        return C.mesh_reduce_scatter(x2 @ w.t(), tp.mesh, "sum", tp.md, 0)
+
+    @staticmethod
+    def backward(ctx, dy_local):
+        from . import collectives as C
+
+        x2, w = ctx.saved_tensors
+        dy = C.mesh_all_gather(dy_local.contiguous(), ctx.tp.mesh, ctx.tp.md, 0)
+        return (dy @ w).view(ctx.shape), _wgrad_into(w, dy, x2), None

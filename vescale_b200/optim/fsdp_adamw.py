@@ -37,6 +37,8 @@ class FSDPAdamW:
         no_decay: Optional[Callable[[str, Sequence[int]], bool]] = None,
         state_dtype: torch.dtype = torch.float32,
         fused_reduce: bool = False,
+        tp_group=None,
+        tp_sharded: Optional[Callable[[str], bool]] = None,
     ):
         st = None
         for m in model.modules():
@@ -64,7 +66,27 @@ class FSDPAdamW:
             if dev.type == "cuda":
                 # [n, 3] int64/float table consumed by the kernel: (lo, hi, decay_flag)
                 u.wd_table = torch.tensor([[s[0], s[1], int(s[2])] for s in segs] or [[0, 0, 0]], dtype=torch.int64, device=dev)
+        # ---- 2-D (FSDP x TP): parameters that are replicated over the TP group (norms, embedding, lm-head under sequence
+        # parallelism) carry partial gradients; they are summed over ``tp_group`` once per step, and the global grad norm
+        # counts TP-sharded parameters over all TP ranks but replicated ones once (legacy ``_grad_sync.py:98-101``,
+        # ``clip_grads.py:60-110``).
+        self.tp_group = tp_group if (tp_group is not None and dist.get_world_size(tp_group) > 1) else None
+        if self.tp_group is not None:
+            if fused_reduce:
+                raise ValueError("fused_reduce cannot be combined with tp_group (replicated gradients need a TP all-reduce first)")
+            from ..models.llama_tp import TP_SHARDED_PARAMS
+
+            is_sharded = tp_sharded or (lambda name: name.rsplit(".", 1)[-1] in TP_SHARDED_PARAMS)
+            for u in self.units:
+                u.tp_replicated_segments = []
+                for slot in u.layout.slots:
+                    lo, hi = u.layout.rank_range(slot, u.rank)
+                    if hi > lo and not is_sharded(slot.name):
+                        u.tp_replicated_segments.append((lo, hi))
+                real = sum(hi - lo for lo, hi, _ in u.layout.segments(u.rank))
+                u.tp_all_replicated = sum(hi - lo for lo, hi in u.tp_replicated_segments) == real
         self._norm_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._norm_rep = torch.zeros(1, dtype=torch.float32, device=dev)
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
         self.last_grad_norm: Optional[torch.Tensor] = None
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
@@ -89,8 +111,58 @@ class FSDPAdamW:
         u.bf16_fresh = True
         u._fused_done = True
 
+    # ------------------------------------------------------------------ 2-D: TP-replicated gradients
+    def _grad_view(self, u: FSDPUnit) -> torch.Tensor:
+        g = u.grad_shard
+        return g[u.rank * u.S : (u.rank + 1) * u.S] if g.numel() != u.S else g
+
+    def _sync_tp_replicated_grads(self) -> None:
+        small: List[torch.Tensor] = []
+        for u in self.units:
+            if not u.grad_ready or not u.tp_replicated_segments:
+                continue
+            g = self._grad_view(u)
+            if u.tp_all_replicated:
+                dist.all_reduce(g, group=self.tp_group)
+            else:
+                small.extend(g[lo:hi] for lo, hi in u.tp_replicated_segments)
+        if small:  # norm weights of every block: one flat bucket
+            flat = torch.cat([t.reshape(-1) for t in small])
+            dist.all_reduce(flat, group=self.tp_group)
+            off = 0
+            for t in small:
+                t.copy_(flat[off : off + t.numel()])
+                off += t.numel()
+
+    def _sumsq_into(self, g: torch.Tensor, out: torch.Tensor, sc: float) -> None:
+        if g.numel() == 0:
+            return
+        if g.is_cuda and _ext.available() and g.data_ptr() % 16 == 0:
+            _ext.count_launch("sumsq")
+            _ext.ops().sumsq_accumulate(g, out, float(sc))
+        else:
+            out += (g.float() * sc).pow(2).sum()
+
+    def _global_grad_norm_2d(self) -> torch.Tensor:
+        tot, rep = self._norm_buf.zero_(), self._norm_rep.zero_()
+        for u in self.units:
+            if not u.grad_ready:
+                continue
+            g, sc = self._grad_view(u), getattr(u, "grad_scale_pending", 1.0)
+            self._sumsq_into(g, tot, sc)
+            for lo, hi in u.tp_replicated_segments:
+                self._sumsq_into(g[lo:hi], rep, sc)
+        tot -= rep  # TP-sharded part only
+        dist.all_reduce(tot, group=self.tp_group)
+        tot += rep
+        if self.units and self.units[0].world > 1:
+            dist.all_reduce(tot, group=self.units[0].group)
+        return tot.clamp_(min=0).sqrt()
+
     # ------------------------------------------------------------------ grad norm (device-side)
     def _global_grad_norm(self) -> torch.Tensor:
+        if self.tp_group is not None:
+            return self._global_grad_norm_2d()
         tot = self._norm_buf.zero_()
         for u in self.units:
             if not u.grad_ready:
@@ -132,6 +204,8 @@ class FSDPAdamW:
         bc1 = 1.0 - b1**self.step_count
         bc2 = 1.0 - b2**self.step_count
         norm = None
+        if self.tp_group is not None:
+            self._sync_tp_replicated_grads()
         if self.max_grad_norm is not None:
             norm = self._global_grad_norm()
             torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0, out=self._coef)
