@@ -166,6 +166,16 @@ class FSDPState:
         u._ag_direct = False
         param = u.params[u.param_names.index(name)]
         state = self
+        others = [p for s, p in zip(u.layout.slots, u.params) if s is not slot and s.numel > 65536]
+
+        def rest_arrived():
+            """The first use of any other large weight of the unit waits for the rest of the all-gather — by then it has
+            been streaming in behind the first GEMM and whatever followed it (RoPE, attention, ...)."""
+            if u._pending_rest:
+                u._pending_rest = False
+                state.cur_stream().wait_event(evt)
+                for q in others:
+                    q.__dict__.pop("_vb_pending_gather", None)
 
         def pending(a: torch.Tensor, out=None):
             del param._vb_pending_gather
@@ -173,10 +183,9 @@ class FSDPState:
             a2 = a.reshape(-1, a.shape[-1])
             if a2.dtype == torch.bfloat16 and a2.is_contiguous() and a2.shape[0] % 256 == 0:
                 y = comm.fused_first_linear(a2, u, slot, full, handshake=False)
-                state.cur_stream().wait_event(evt)
             else:  # shape the kernel does not take: gather the weight the ordinary way
                 comm.all_gather(u.param_shard, full, u, only=(slot.offset, slot.end), handshake=False)
-                state.cur_stream().wait_event(evt)
+                rest_arrived()
                 from ...ops import functional as Fn
 
                 y = Fn.gemm_nt(a2, param)
@@ -184,8 +193,21 @@ class FSDPState:
                 return out.copy_(y.view(out.shape))
             return y.view(*a.shape[:-1], y.shape[-1])
 
+        def make_other(q):
+            def other(a: torch.Tensor, out=None):
+                rest_arrived()
+                from ...ops import functional as Fn
+
+                return Fn.gemm_nt(a, q, out)
+
+            return other
+
         param._vb_pending_gather = pending
+        for q in others:
+            q._vb_pending_gather = make_other(q)
         u._pending_param = param
+        u._pending_rest = True
+        u._pending_rest_fn = rest_arrived
         u._pending_evt = evt
         return True
 
@@ -214,6 +236,8 @@ class FSDPState:
             u.comm.all_gather(u.param_shard, u.full_param, u, only=(slot.offset, slot.end))
             self.cur_stream().wait_event(u._pending_evt)
             raise RuntimeError(f"FSDP unit {u.name}: fuse_first_gemm={u.fused_first!r} but that weight was not the first GEMM of the forward")
+        if getattr(u, "_pending_rest", False):
+            u._pending_rest_fn()  # no other large weight was touched: the gather must still complete before the buffer is recycled
         if not u.unsharded or u.world == 1:
             return
         if not self.reshard_after_forward:
