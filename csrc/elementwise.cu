@@ -88,17 +88,36 @@ __global__ void __launch_bounds__(kNormThreads) rms_norm_bwd_kernel(const __nv_b
     for (int i = 0; i < 8; ++i) dwacc[it][i] = 0.f;
     if (v < nvec) unpack8(ld8(w + v * 8), wv[it]);
   }
+  // software pipeline: the raw vectors of the CTA's next row are requested before the current row's block reduction, so two
+  // rows of loads are in flight per CTA (the reduction's two barriers otherwise drain the memory pipeline every row)
+  bf16x8 ndy[kMaxVecPerThread], nx[kMaxVecPerThread], ndh[kMaxVecPerThread];
+  float nr = 0.f;
+  auto fetch = [&](int row) {
+    if (row >= rows) return;
+    nr = rstd[row];
+#pragma unroll
+    for (int it = 0; it < kMaxVecPerThread; ++it) {
+      const int v = threadIdx.x + it * kNormThreads;
+      if (v < nvec) {
+        ndy[it] = ld8(dy + (size_t)row * H + v * 8);
+        nx[it] = ld8(x + (size_t)row * H + v * 8);
+        if (ADD) ndh[it] = ld8(dh + (size_t)row * H + v * 8);
+      }
+    }
+  };
+  fetch(blockIdx.x);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const float r = rstd[row];
-    float g[kMaxVecPerThread][8], xh[kMaxVecPerThread][8];
+    const float r = nr;
+    float g[kMaxVecPerThread][8], xh[kMaxVecPerThread][8], t[kMaxVecPerThread][8];
     float dot = 0.f;
 #pragma unroll
     for (int it = 0; it < kMaxVecPerThread; ++it) {
       const int v = threadIdx.x + it * kNormThreads;
       if (v < nvec) {
         float d[8];
-        unpack8(ld8(dy + (size_t)row * H + v * 8), d);
-        unpack8(ld8(x + (size_t)row * H + v * 8), xh[it]);
+        unpack8(ndy[it], d);
+        unpack8(nx[it], xh[it]);
+        if (ADD) unpack8(ndh[it], t[it]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           xh[it][i] *= r;
@@ -108,6 +127,7 @@ __global__ void __launch_bounds__(kNormThreads) rms_norm_bwd_kernel(const __nv_b
         }
       }
     }
+    fetch(row + gridDim.x);
     dot = block_sum<kNormThreads>(dot, red) / (float)H;
 #pragma unroll
     for (int it = 0; it < kMaxVecPerThread; ++it) {
@@ -117,10 +137,8 @@ __global__ void __launch_bounds__(kNormThreads) rms_norm_bwd_kernel(const __nv_b
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = r * (g[it][i] - xh[it][i] * dot);
         if (ADD) {
-          float t[8];
-          unpack8(ld8(dh + (size_t)row * H + v * 8), t);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += t[i];
+          for (int i = 0; i < 8; ++i) o[i] += t[it][i];
         }
         st8(dx + (size_t)row * H + v * 8, pack8(o));
       }
@@ -434,7 +452,12 @@ static std::tuple<at::Tensor, at::Tensor> rms_bwd_impl(const at::Tensor& dy, con
   c10::cuda::CUDAGuard guard(x.device());
   auto dx = at::empty_like(x);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  const int nblk = std::max(1, std::min(rows, sms * 4));
+  // persistent grid = exactly the resident capacity (register-limited), two rows in flight per CTA
+  int occ = 2;
+#define VB_LAUNCH(NT) C10_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rms_norm_bwd_kernel<true, NT>, NT, 0))
+  VB_NORM_DISPATCH(H);
+#undef VB_LAUNCH
+  const int nblk = std::max(1, std::min(rows, sms * std::max(1, occ)));
   auto part = at::empty({nblk, H}, x.options().dtype(at::kFloat));
   auto dw = at::empty({H}, x.options().dtype(at::kFloat));
   TORCH_CHECK(H % 8 == 0 && H <= 16384, "rms_norm_bwd: unsupported hidden size ", H);
