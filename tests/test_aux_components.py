@@ -114,3 +114,38 @@ def test_vescale_alias_package():
     import vescale.checkpoint as ck
 
     assert vescale.DTensor is DTensor and hasattr(ck, "save") and hasattr(vescale, "init_device_mesh")
+
+
+def _make_stream_handlers():
+    import os
+
+    from vescale_b200.profiler import LocalTimelineNDHandler
+
+    return [LocalTimelineNDHandler(os.environ["NDTL_TEST_OUT"])]
+
+
+def test_profiler_socket_streamer(tmp_path):
+    """Binary framing round-trip + records of two 'ranks' streamed over a unix socket into one per-host timeline."""
+    import json
+    import os
+
+    from vescale_b200.profiler import NDtimelineStreamer, SockNDHandler, decode_frames, encode_frame
+
+    recs = [{"metric": "forward-compute", "start_us": 10.0, "duration_us": 5.0, "stream": 7, "tags": {"mb": 1}}]
+    buf = bytearray(encode_frame(recs, 3, 42) + encode_frame(recs, 4, 43)[:10])
+    got = list(decode_frames(buf))
+    assert got == [(0, 3, 42, recs)] and len(buf) == 10  # partial second frame stays buffered
+    out = str(tmp_path / "host_timeline.json")
+    os.environ["NDTL_TEST_OUT"] = out
+    sock = str(tmp_path / "ndtl.sock")
+    streamer = NDtimelineStreamer.start(sock, _make_stream_handlers, expected_clients=2)
+    hs = [SockNDHandler(sock) for _ in range(2)]
+    for step in range(3):
+        for rank, h in enumerate(hs):
+            h(recs, rank, step)
+    for rank, h in enumerate(hs):
+        h.close(rank)
+    streamer.join(30)
+    ev = json.load(open(out))["traceEvents"]
+    spans = [e for e in ev if e["ph"] == "X"]
+    assert len(spans) == 6 and {e["pid"] for e in spans} == {0, 1} and all(e["tid"] == 7 for e in spans)

@@ -13,5 +13,6 @@ from .timer import (  # noqa: F401
     set_global_step,
     wait,
 )
-from .handlers import ChromeTraceNDHandler, LocalRawNDHandler, LoggingNDHandler, NDHandler, ParserNDHandler  # noqa: F401
+from .handlers import ChromeTraceNDHandler, LocalRawNDHandler, LocalTimelineNDHandler, LoggingNDHandler, NDHandler, ParserNDHandler  # noqa: F401
+from .sock_streamer import NDtimelineStreamer, SockNDHandler, decode_frames, encode_frame  # noqa: F401
 from . import predefined  # noqa: F401

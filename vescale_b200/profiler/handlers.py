@@ -61,3 +61,27 @@ class LoggingNDHandler(NDHandler):
     def __call__(self, records, rank, step):
         for r in records:
             self.logger.log(self.level, "[rank %d step %d] %s: %.1f us", rank, step, r["metric"], r["duration_us"])
+
+
+class LocalTimelineNDHandler(NDHandler):
+    """One merged perfetto/chrome trace per *host*: every rank of the host is a process row, every CUDA stream a thread row
+    (legacy ``handlers/local_timeline_handler.py``).  Meant to run inside the ``NDtimelineStreamer`` collector, where records
+    of all local ranks arrive; rewrites the file atomically on every flush."""
+
+    def __init__(self, path: str = "ndtimeline_host.json"):
+        self.path = path
+        self.events: List[dict] = []
+        self._named = set()
+
+    def __call__(self, records, rank, step):
+        if rank not in self._named:
+            self._named.add(rank)
+            self.events.append({"name": "process_name", "ph": "M", "pid": rank, "args": {"name": f"rank {rank}"}})
+        for r in records:
+            self.events.append({"name": r["metric"], "cat": "ndtimeline", "ph": "X", "ts": r["start_us"], "dur": r["duration_us"], "pid": rank,
+                                "tid": r.get("stream", 0), "args": {"step": step, **r.get("tags", {})}})
+        tmp = self.path + ".tmp"
+        os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
+        with open(tmp, "w") as f:
+            json.dump({"traceEvents": self.events, "displayTimeUnit": "ms"}, f)
+        os.replace(tmp, self.path)

@@ -1,0 +1,136 @@
+"""Unix-socket streaming of timeline records to one collector process per host.
+
+``SockNDHandler`` (in every training rank) frames each flush with a small binary header and sends it to the
+``NDtimelineStreamer`` process, which hands decoded records to ordinary ``NDHandler``s (e.g. one merged perfetto file per
+host) — so trace serialisation and file I/O never run inside a training process.
+
+Capability parity: legacy ``ndtimeline/sock_streamer.py:94-132`` (streamer process), ``handlers/sock_handler.py`` and
+``binary_protocol.py`` (length-prefixed frames with a magic and a version); the framing here is our own:
+
+    frame := magic "NDTL" | u8 version | u8 kind | u16 rank | u32 step | u32 payload_len | payload (UTF-8 JSON array)
+"""
+from __future__ import annotations
+
+import json
+import multiprocessing as mp
+import os
+import socket
+import struct
+import threading
+from typing import Callable, List, Optional, Sequence
+
+from .handlers import NDHandler
+
+__all__ = ["encode_frame", "decode_frames", "SockNDHandler", "NDtimelineStreamer"]
+
+_MAGIC = b"NDTL"
+_VERSION = 1
+_HDR = struct.Struct("<4sBBHII")
+KIND_RECORDS, KIND_CLOSE = 0, 1
+
+
+def encode_frame(records: List[dict], rank: int, step: int, kind: int = KIND_RECORDS) -> bytes:
+    payload = json.dumps(records, separators=(",", ":")).encode()
+    return _HDR.pack(_MAGIC, _VERSION, kind, rank & 0xFFFF, step & 0xFFFFFFFF, len(payload)) + payload
+
+
+def decode_frames(buf: bytearray):
+    """Yield (kind, rank, step, records) for every complete frame at the head of ``buf`` and consume it."""
+    while len(buf) >= _HDR.size:
+        magic, ver, kind, rank, step, n = _HDR.unpack_from(buf, 0)
+        if magic != _MAGIC or ver != _VERSION:
+            raise ValueError("ndtimeline stream: bad frame header")
+        if len(buf) < _HDR.size + n:
+            return
+        payload = bytes(buf[_HDR.size : _HDR.size + n])
+        del buf[: _HDR.size + n]
+        yield kind, rank, step, json.loads(payload)
+
+
+class SockNDHandler(NDHandler):
+    def __init__(self, sock_path: str, connect_timeout: float = 10.0):
+        self.sock_path = sock_path
+        self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self.sock.settimeout(connect_timeout)
+        self.sock.connect(sock_path)
+        self.sock.settimeout(None)
+        self._lock = threading.Lock()
+
+    def __call__(self, records, rank, step):
+        clean = [{k: v for k, v in r.items() if k not in ("e0", "e1")} for r in records]
+        with self._lock:
+            self.sock.sendall(encode_frame(clean, rank, step))
+
+    def close(self, rank: int = 0):
+        with self._lock:
+            try:
+                self.sock.sendall(encode_frame([], rank, 0, KIND_CLOSE))
+            finally:
+                self.sock.close()
+
+
+def _serve(sock_path: str, make_handlers: Callable[[], Sequence[NDHandler]], expected_clients: int, ready) -> None:
+    handlers = list(make_handlers())
+    if os.path.exists(sock_path):
+        os.unlink(sock_path)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(sock_path)
+    srv.listen(max(8, expected_clients))
+    ready.set()
+    lock = threading.Lock()
+    closed = [0]
+
+    def client(conn):
+        buf = bytearray()
+        try:
+            while True:
+                chunk = conn.recv(1 << 16)
+                if not chunk:
+                    break
+                buf += chunk
+                for kind, rank, step, recs in decode_frames(buf):
+                    if kind == KIND_CLOSE:
+                        return
+                    with lock:
+                        for h in handlers:
+                            h(recs, rank, step)
+        finally:
+            conn.close()
+            with lock:
+                closed[0] += 1
+
+    threads = []
+    for _ in range(expected_clients):
+        conn, _addr = srv.accept()
+        t = threading.Thread(target=client, args=(conn,), daemon=True)
+        t.start()
+        threads.append(t)
+    for t in threads:
+        t.join()
+    srv.close()
+    if os.path.exists(sock_path):
+        os.unlink(sock_path)
+
+
+class NDtimelineStreamer:
+    """Collector process: ``NDtimelineStreamer.start(path, make_handlers, n_clients)`` on local rank 0, then every rank adds a
+    ``SockNDHandler(path)`` to ``init_ndtimers``.  ``make_handlers`` must be picklable (it runs in the child)."""
+
+    def __init__(self, proc, sock_path: str):
+        self.proc, self.sock_path = proc, sock_path
+
+    @classmethod
+    def start(cls, sock_path: str, make_handlers: Callable[[], Sequence[NDHandler]], expected_clients: int = 1, timeout: float = 20.0) -> "NDtimelineStreamer":
+        ctx = mp.get_context("spawn")
+        ready = ctx.Event()
+        proc = ctx.Process(target=_serve, args=(sock_path, make_handlers, expected_clients, ready), daemon=True)
+        proc.start()
+        if not ready.wait(timeout):
+            proc.terminate()
+            raise RuntimeError("ndtimeline streamer did not come up")
+        return cls(proc, sock_path)
+
+    def join(self, timeout: Optional[float] = 30.0) -> None:
+        self.proc.join(timeout)
+        if self.proc.is_alive():
+            self.proc.terminate()
