@@ -99,7 +99,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -111,7 +117,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        t0, t1 = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
+        inside = [(ts, l) for ts, l in self.lines if t0 <= ts <= t1 + 0.25]  # samples taken while the timed region was running
+        for ts, l in inside or self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 8:
                 continue
@@ -246,15 +254,18 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    # the clock sampler is started before the warm-up: spawning nvidia-smi (NVML init over all GPUs) stalls kernel launches for
+    # a few hundred ms, which must not land inside the timed region; only samples taken during the region are reported
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step_device(i)
     barrier()
     mem_gb = torch.cuda.max_memory_allocated() / 2**30
 
     # ---- timed region 1: device-timed
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     _ext.LAUNCH_COUNTER.update(n=0, enabled=True, by_op={})
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,6 +282,7 @@ def main():
     launches = _ext.LAUNCH_COUNTER["n"]
     by_op = dict(_ext.LAUNCH_COUNTER["by_op"])
     _ext.LAUNCH_COUNTER["enabled"] = False
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(last.item()) * tp_size  # TP: the model returns this rank's share (local mean / tp)
 
