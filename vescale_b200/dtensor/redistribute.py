@@ -44,7 +44,7 @@ def _gather_shard(local: torch.Tensor, mesh, i: int, d: int, full: int) -> torch
         shp[d] = pad
         local = torch.cat([local, local.new_zeros(shp)], dim=d)
     out = C.mesh_all_gather(local, mesh, i, gather_dim=d)
-    return out.narrow(d, 0, full)
+    return out.narrow(d, 0, full).contiguous()  # views downstream assume the contiguous strides of the global metadata
 
 
 def _gather_interleaved(local: torch.Tensor, mesh, i: int, p: InterleavedShard) -> torch.Tensor:

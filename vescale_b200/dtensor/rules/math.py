@@ -39,7 +39,11 @@ def _reduction(schema: OpSchema, reduce_op: str, dims_arg: int = 1, keepdim_arg:
         n = mesh.size(i)
         if isinstance(p, RaggedShard):
             rd = set(p.dims)
-            if reduce_op in ("sum", "max", "min", "product") and rd <= red:
+            if reduce_op in ("max", "min") and any(u == 0 for u in p.local_units):
+                # amax/amin of an empty local shard raises in aten: reduce a replicated copy instead
+                ins.append(R)
+                out.append(R)
+            elif reduce_op in ("sum", "max", "min", "product") and rd <= red:
                 # every ragged dim is reduced away: flat local reduce + pending reduction
                 ins.append(p)
                 out.append(Partial(reduce_op))
@@ -49,7 +53,13 @@ def _reduction(schema: OpSchema, reduce_op: str, dims_arg: int = 1, keepdim_arg:
         elif isinstance(p, Shard):
             if p.dim in red:
                 even = spec.shape[p.dim] % n == 0
+                size = spec.shape[p.dim]
+                some_rank_empty = (-(-size // n)) * (n - 1) >= size
                 if reduce_op == "avg" and not even:
+                    ins.append(R)
+                    out.append(R)
+                elif reduce_op in ("max", "min") and some_rank_empty:
+                    # amax/amin/max/min of an empty local shard raises in aten: reduce a replicated copy instead
                     ins.append(R)
                     out.append(R)
                 elif type(p) is not Shard and reduce_op not in ("sum", "max", "min", "avg", "product"):
