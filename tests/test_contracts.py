@@ -1,0 +1,112 @@
+"""Single-process contract tests (no process group): hash / equality of meshes, placements, specs and op schemas (the
+sharding-propagation cache key; reference ``legacy/test/dtensor/hash/test_hash.py``), storage aliasing of ``from_local`` /
+``to_local`` (``legacy/test/dtensor/memory/test_memory.py``), propagator cache behaviour, and the env-flag switches
+(SURVEY §5.6)."""
+import os
+
+import pytest
+import torch
+
+
+def _mesh(shape=(4,), names=None, rank=0):
+    from vescale_b200 import init_device_mesh
+
+    return init_device_mesh("cpu", shape, mesh_dim_names=names, _rank=rank, _init_process_groups=False)
+
+
+def test_hash_and_equality_contracts():
+    from vescale_b200 import Partial, Replicate, Shard
+    from vescale_b200.dtensor import InterleavedShard, RaggedShard
+    from vescale_b200.dtensor.op_schema import OpSchema
+    from vescale_b200.spec import DTensorSpec, TensorMeta
+
+    # placements: value semantics, usable as dict keys, distinct kinds never collide
+    pls = [Replicate(), Shard(0), Shard(1), Partial(), Partial("max"), RaggedShard((0,), (1, 2, 0, 1)), RaggedShard((0,), (1, 2, 1, 0)), RaggedShard((0, 1), (1, 2, 0, 1)),
+           InterleavedShard(0, 2), InterleavedShard(0, 4)]
+    for i, a in enumerate(pls):
+        for j, b in enumerate(pls):
+            assert (a == b) == (i == j), (a, b)
+            if i == j:
+                assert hash(a) == hash(type(a)(**a.__dict__)) if hasattr(a, "__dict__") and a.__dict__ else True
+    assert len({p: k for k, p in enumerate(pls)}) == len(pls)
+    assert Shard(1) == Shard(dim=1) and hash(Shard(1)) == hash(Shard(dim=1))
+    assert Shard(0) != InterleavedShard(0, 2) and InterleavedShard(0, 2) != Shard(0)
+    # meshes: equal iff same layout of ranks (and names); sub-meshes hash like an explicitly built mesh
+    m1, m2, m3 = _mesh((2, 2), ("a", "b")), _mesh((2, 2), ("a", "b")), _mesh((4,))
+    assert m1 == m2 and hash(m1) == hash(m2) and m1 != m3
+    # specs: placements + tensor meta
+    tm, tm2 = TensorMeta((8, 4), (4, 1), torch.float32), TensorMeta((8, 4), (4, 1), torch.bfloat16)
+    s1, s2, s3, s4 = DTensorSpec(m3, (Shard(0),), tm), DTensorSpec(m3, (Shard(0),), tm), DTensorSpec(m3, (Shard(1),), tm), DTensorSpec(m3, (Shard(0),), tm2)
+    assert s1 == s2 and hash(s1) == hash(s2) and s1 != s3 and s1 != s4
+    # op schemas (cache keys): same op + specs + static args hash equal; a different static arg is a different key
+    aten = torch.ops.aten
+    k1 = OpSchema(aten.sum.dim_IntList, (s1, [0], False), {})
+    k2 = OpSchema(aten.sum.dim_IntList, (s2, [0], False), {})
+    k3 = OpSchema(aten.sum.dim_IntList, (s1, [1], False), {})
+    k4 = OpSchema(aten.sum.dim_IntList, (s3, [0], False), {})
+    assert k1 == k2 and hash(k1) == hash(k2) and k1 != k3 and k1 != k4
+    assert len({k1: 0, k2: 1, k3: 2, k4: 3}) == 3
+
+
+def test_from_local_to_local_alias_storage_and_cache():
+    from vescale_b200 import Replicate, Shard
+    from vescale_b200.dtensor import DTensor
+    from vescale_b200.dtensor.sharding_prop import propagator
+
+    mesh = _mesh((4,), rank=1)
+    local = torch.arange(12.0).reshape(3, 4)
+    dt = DTensor.from_local(local, mesh, [Shard(0)], run_check=False)
+    assert dt.shape == (12, 4) and dt.to_local().data_ptr() == local.data_ptr()  # no copy either way
+    dt.to_local().mul_(2)
+    assert local[0, 1].item() == 2.0
+    y = dt * 3  # pointwise on shards: local result, no communication needed on a fake mesh
+    assert isinstance(y, DTensor) and y.placements == (Shard(0),) and torch.equal(y.to_local(), local * 3)
+    v = dt.view(12, 2, 2)
+    assert v.to_local().data_ptr() == local.data_ptr()  # views stay views
+    before = propagator.cache_info()
+    for _ in range(5):
+        _ = dt + dt
+    after = propagator.cache_info()
+    assert after["hits"] - before["hits"] >= 4 and after["misses"] - before["misses"] <= 1
+    # detach / clone semantics
+    assert dt.detach().to_local().data_ptr() == local.data_ptr() and dt.clone().to_local().data_ptr() != local.data_ptr()
+    r = DTensor.from_local(torch.ones(2, 2), mesh, [Replicate()], run_check=False)
+    assert r.shape == (2, 2) and r.full_tensor().data_ptr() == r.to_local().data_ptr()
+
+
+def test_submesh_and_coordinates():
+    m = _mesh((2, 3), ("dp", "tp"), rank=4)
+    assert list(m.get_coordinate()) == [1, 1] and m.get_local_rank("tp") == 1 and m.get_local_rank("dp") == 1
+    tp, dp = m["tp"], m["dp"]
+    assert tp.size() == 3 and dp.size() == 2 and tp.mesh_dim_names == ("tp",)
+    assert tp.mesh.tolist() == [3, 4, 5] and dp.mesh.tolist() == [1, 4]
+    assert m.size(0) == 2 and m.size("tp") == 3 and m.ndim == 2 and m.size() == 6
+    with pytest.raises((KeyError, ValueError)):
+        m["pp"]
+
+
+def test_env_flags(monkeypatch):
+    """VESCALE_STRICT_RULES refuses the replicate fallback; VESCALE_DISABLE_REDISTRIBUTE forbids implicit resharding in
+    dispatch (legacy ``dtensor/_diff.py:24``)."""
+    from vescale_b200 import Shard
+    from vescale_b200.dtensor import DTensor
+
+    mesh = _mesh((1,))
+    a = DTensor.from_local(torch.randn(4, 4), mesh, [Shard(0)], run_check=False)
+    b = DTensor.from_local(torch.randn(4, 4), mesh, [Shard(1)], run_check=False)
+    monkeypatch.setenv("VESCALE_DISABLE_REDISTRIBUTE", "1")
+    import importlib
+
+    import vescale_b200.dtensor.dispatch as disp
+
+    if hasattr(disp, "_redistribute_disabled"):
+        assert disp._redistribute_disabled() is True
+    monkeypatch.setenv("VESCALE_DISABLE_REDISTRIBUTE", "0")
+    out = a + b  # placements differ: one operand must be resharded (a no-op on a 1-rank mesh, but it goes through the planner)
+    assert torch.allclose(out.full_tensor(), a.full_tensor() + b.full_tensor())
+    monkeypatch.setenv("VESCALE_STRICT_RULES", "1")
+    from vescale_b200.dtensor.sharding_prop import ShardingPropagator, _replicate_fallback
+    from vescale_b200.dtensor.op_schema import OpSchema
+
+    with pytest.raises(NotImplementedError):
+        _replicate_fallback(OpSchema(torch.ops.aten.frac.default, (a._spec,), {}))

@@ -63,6 +63,8 @@ _OPS = {
 
 
 def _backend(group) -> str:
+    if group is _SOLO:
+        return "solo"
     try:
         return dist.get_backend(group)
     except Exception:
@@ -70,16 +72,33 @@ def _backend(group) -> str:
 
 
 def _group_size(group) -> int:
-    return dist.get_world_size(group)
+    return 1 if group is _SOLO else dist.get_world_size(group)
+
+
+class _Solo:
+    """Stand-in group of a size-1 mesh dim: every collective is the identity and needs no process group (fake / single
+    process meshes built with ``_init_process_groups=False``)."""
+
+    def __repr__(self):
+        return "<solo group>"
+
+
+_SOLO = _Solo()
+
+
+def _group_of(mesh, mesh_dim):
+    if mesh.size(mesh_dim) == 1:
+        return _SOLO
+    return mesh.get_group(mesh_dim)
 
 
 def _group_rank(group) -> int:
-    return dist.get_rank(group)
+    return 0 if group is _SOLO else dist.get_rank(group)
 
 
 def _symm(group, tensor):
     """The symmetric-memory backend registered for this group (``enable_symmetric_collectives``), if the tensor qualifies."""
-    if not tensor.is_cuda:
+    if group is _SOLO or not tensor.is_cuda:
         return None
     from .symm_collectives import symm_backend_for
 
@@ -87,7 +106,7 @@ def _symm(group, tensor):
 
 
 def mesh_all_reduce(tensor: torch.Tensor, mesh, reduce_op: str = "sum", mesh_dim: int = 0, *, inplace: bool = False) -> torch.Tensor:
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n = _group_size(group)
     out = tensor if inplace else tensor.clone(memory_format=torch.contiguous_format)
     _note("all_reduce", out, group, op=reduce_op)
@@ -110,7 +129,7 @@ def mesh_all_reduce(tensor: torch.Tensor, mesh, reduce_op: str = "sum", mesh_dim
 
 def mesh_all_gather(tensor: torch.Tensor, mesh, mesh_dim: int = 0, gather_dim: int = 0) -> torch.Tensor:
     """Even all-gather: every rank contributes the same shape; result concatenated on ``gather_dim``."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n = _group_size(group)
     tensor = tensor.contiguous()
     _note("all_gather", tensor, group)
@@ -130,7 +149,7 @@ def mesh_all_gather(tensor: torch.Tensor, mesh, mesh_dim: int = 0, gather_dim: i
 def mesh_all_gather_uneven(tensor: torch.Tensor, sizes: Sequence[int], mesh, mesh_dim: int = 0) -> List[torch.Tensor]:
     """All-gather of 1-D pieces with per-rank lengths ``sizes`` (zeros allowed).  Returns the list.
     NCCL takes the list form directly; elsewhere pieces are padded to the max length."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n = _group_size(group)
     flat = tensor.reshape(-1).contiguous()
     _note("all_gather", flat, group, uneven=True)
@@ -150,7 +169,7 @@ def mesh_all_gather_uneven(tensor: torch.Tensor, sizes: Sequence[int], mesh, mes
 
 def mesh_reduce_scatter(tensor: torch.Tensor, mesh, reduce_op: str = "sum", mesh_dim: int = 0, scatter_dim: int = 0) -> torch.Tensor:
     """Even reduce-scatter along ``scatter_dim`` (size divisible by the group size)."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n = _group_size(group)
     _note("reduce_scatter", tensor, group, op=reduce_op)
     if n == 1:
@@ -189,7 +208,7 @@ def _p2p_all_to_all(outs: List[torch.Tensor], ins: List[torch.Tensor], group) ->
 
 def mesh_all_to_all_uneven(ins: List[torch.Tensor], out_sizes: Sequence[int], mesh, mesh_dim: int = 0) -> List[torch.Tensor]:
     """List all-to-all of 1-D pieces: send ``ins[j]`` to coordinate ``j``; receive ``out_sizes[j]`` elements from it."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     ref = ins[0]
     outs = [ref.new_empty(int(s)) for s in out_sizes]
     _note("all_to_all", torch.cat([i.reshape(-1) for i in ins]) if ins else None, group, uneven=True)
@@ -207,7 +226,7 @@ def mesh_ragged_exchange(local: torch.Tensor, src_ranges: Sequence, dst_ranges: 
     """Flat interval exchange: ``local`` holds flat range ``src_ranges[me]`` of a global buffer, the result holds
     ``dst_ranges[me]`` (RaggedShard -> RaggedShard; one-hot destinations = gather-to-root).  Symmetric-memory put kernel
     when enabled, else the uneven list all-to-all of the reference (``placement_types.py:152-192``)."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n, me = _group_size(group), mesh.get_local_rank(mesh_dim)
     local = local.contiguous().view(-1)
     sc = _symm(group, local) if n > 1 else None
@@ -228,7 +247,7 @@ def mesh_ragged_exchange(local: torch.Tensor, src_ranges: Sequence, dst_ranges: 
 def mesh_all_to_all_single(tensor: torch.Tensor, mesh, mesh_dim: int, split_dim: int, concat_dim: int) -> torch.Tensor:
     """Even Shard(concat_dim) -> Shard(split_dim): split my tensor on ``split_dim`` into n pieces, piece j
     goes to coordinate j, received pieces are concatenated on ``concat_dim``."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n = _group_size(group)
     _note("all_to_all", tensor, group)
     if n == 1:
@@ -252,7 +271,7 @@ def mesh_all_to_all_single(tensor: torch.Tensor, mesh, mesh_dim: int, split_dim:
 
 
 def mesh_broadcast(tensor: torch.Tensor, mesh, mesh_dim: int = 0, group_src: int = 0) -> torch.Tensor:
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     _note("broadcast", tensor, group)
     if _group_size(group) == 1:
         return tensor
@@ -262,7 +281,7 @@ def mesh_broadcast(tensor: torch.Tensor, mesh, mesh_dim: int = 0, group_src: int
 
 def mesh_scatter(output: torch.Tensor, scatter_list: Optional[List[torch.Tensor]], mesh, mesh_dim: int = 0, group_src: int = 0) -> torch.Tensor:
     """Even scatter from coordinate ``group_src``."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n, me = _group_size(group), _group_rank(group)
     _note("scatter", output, group)
     if n == 1:
@@ -279,7 +298,7 @@ def mesh_scatter(output: torch.Tensor, scatter_list: Optional[List[torch.Tensor]
 def mesh_scatter_ragged(output: torch.Tensor, scatter_list: Optional[List[torch.Tensor]], mesh, mesh_dim: int = 0, group_src: int = 0) -> torch.Tensor:
     """Uneven scatter.  The reference serialises blocking sends (``_collective_utils.py:83-94``, with a TODO);
     here all sends are posted at once and waited together."""
-    group = mesh.get_group(mesh_dim)
+    group = _group_of(mesh, mesh_dim)
     n, me = _group_size(group), _group_rank(group)
     _note("scatter", output, group, uneven=True)
     if me == group_src:

@@ -144,8 +144,8 @@ class DeviceMesh:
     def shape(self) -> Tuple[int, ...]:
         return self._shape
 
-    def size(self, mesh_dim: Optional[int] = None) -> int:
-        return math.prod(self._shape) if mesh_dim is None else self._shape[mesh_dim]
+    def size(self, mesh_dim: Union[int, str, None] = None) -> int:
+        return math.prod(self._shape) if mesh_dim is None else self._shape[self._dim_index(mesh_dim)]
 
     def get_rank(self) -> int:
         return self._rank
