@@ -149,3 +149,48 @@ def test_profiler_socket_streamer(tmp_path):
     ev = json.load(open(out))["traceEvents"]
     spans = [e for e in ev if e["ph"] == "X"]
     assert len(spans) == 6 and {e["pid"] for e in spans} == {0, 1} and all(e["tid"] == 7 for e in spans)
+
+
+def _emulator_vs_real(rank, world):
+    """The emulator's global-view collectives against the real process group on the same inputs, side by side
+    (``legacy/test/emulator/test_distributed.py:72-101`` strategy).  Integer-valued floats make the sums order-independent,
+    so the comparison is bitwise on gloo as well as NCCL."""
+    import torch.distributed as dist
+
+    from vescale_b200.emulator import EmulatorProcessGroup
+
+    dev = device_type()
+    pg = EmulatorProcessGroup(world, algo="ring")
+    gens = [torch.Generator().manual_seed(7 + r) for r in range(world)]
+    all_inputs = [torch.randint(-50, 50, (4 * world, 5), generator=g).float() for g in gens]  # every rank can build every input
+    mine = all_inputs[rank].clone().to(dev)
+    # all_reduce
+    emu = pg.all_reduce(all_inputs)
+    real = mine.clone()
+    dist.all_reduce(real)
+    assert torch.equal(real.cpu(), emu[rank])
+    for algo in ("tree",):
+        assert torch.equal(EmulatorProcessGroup(world, algo=algo).all_reduce(all_inputs)[rank], emu[rank])
+    # all_gather
+    emu = pg.all_gather(all_inputs)
+    outs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    assert torch.equal(torch.cat(outs).cpu(), emu[rank].reshape(-1, 5))
+    # reduce_scatter (gloo has no native one: all_reduce + slice is the definition)
+    emu = pg.reduce_scatter(all_inputs)
+    want = sum(all_inputs).chunk(world, 0)[rank]
+    assert torch.equal(emu[rank].reshape(want.shape), want)
+    # all_to_all
+    pieces = [list(t.chunk(world, 0)) for t in all_inputs]
+    emu = pg.all_to_all(pieces)
+    want = [all_inputs[src].chunk(world, 0)[rank] for src in range(world)]
+    assert all(torch.equal(a, b) for a, b in zip(emu[rank], want))
+    # broadcast
+    emu = pg.broadcast(all_inputs, src=2)
+    b = mine.clone()
+    dist.broadcast(b, src=2)
+    assert torch.equal(b.cpu(), emu[rank])
+
+
+def test_emulator_matches_real_collectives():
+    run_distributed(_emulator_vs_real, 4)

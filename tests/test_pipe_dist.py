@@ -105,3 +105,61 @@ def test_scheduler_properties():
     assert [len(x) for x in g] == [2, 4, 4]
     g = split_units(units, PipelineParallelPlan(num_stages=5, split_method=PipelineSplitMethodType.PARAMETERS))
     assert sum(len(x) for x in g) == 10 and all(len(x) >= 1 for x in g)
+
+
+class _Emb(nn.Module):
+    def __init__(self, v, h):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(v, h) * 0.1)
+
+    def forward(self, ids):
+        return torch.nn.functional.embedding(ids, self.weight)
+
+
+class _Head(nn.Module):
+    def __init__(self, v, h):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(v, h) * 0.1)
+
+    def forward(self, x):
+        return x @ self.weight.t()
+
+
+def _pp_shared(rank, world):
+    """Tied embedding / lm-head living on the first and last stage: values are synchronised once, gradients are summed over
+    the owning ranks every step (legacy ``test_shared_params.py`` / ``pipe_stage.py:200-247``)."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.pipe import PipeEngine, PipelineParallelPlan, PipelineScheduleType, construct_pipeline_stage
+
+    dev = device_type()
+    V, H = 11, 16
+    torch.manual_seed(0)
+    mods = [_Emb(V, H)] + [Blk(H) for _ in range(6)] + [_Head(V, H)]
+    mods[-1].weight.data.copy_(mods[0].weight.data)
+    ref = nn.Sequential(*mods).to(dev)
+    ref[7].weight = ref[0].weight  # really tied in the golden model
+    model = copy.deepcopy(nn.Sequential(*mods)).to(dev)
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("PP",))
+    plan = PipelineParallelPlan(num_stages=world, schedule_type=PipelineScheduleType.SIMPLE_1F1B, shared_modules=[["0.weight", "7.weight"]])
+    pm = construct_pipeline_stage(model, plan, mesh)
+    assert (len(pm.shared_groups) == 1) == (rank in (0, world - 1))
+    engine = PipeEngine(pm, mesh, lambda out, y: torch.nn.functional.cross_entropy(out, y), plan)
+    engine.sync_shared_params(share_params=True)
+    M = 4
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randint(0, V, (3,), generator=g).to(dev) for _ in range(M)]
+    ys = [torch.randint(0, V, (3,), generator=g).to(dev) for _ in range(M)]
+    loss, _ = engine(xs, ys)
+    engine.sync_shared_params(share_params=False)  # sum the two partial gradients of the tied weight
+    ref_loss = sum(torch.nn.functional.cross_entropy(ref(x), y) / M for x, y in zip(xs, ys))
+    ref_loss.backward()
+    if engine.is_last_rank:
+        torch.testing.assert_close(loss, ref_loss.detach(), rtol=1e-5, atol=1e-6)
+    if rank in (0, world - 1):
+        (params, _grp), = pm.shared_groups
+        assert len(params) == 1
+        torch.testing.assert_close(params[0].grad, ref[0].weight.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_pipeline_shared_params():
+    run_distributed(_pp_shared, 4)
