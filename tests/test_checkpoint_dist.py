@@ -106,3 +106,82 @@ def test_ragged_checkpoint_resharding():
 
 def test_fsdp_model_optimizer_roundtrip():
     run_distributed(_fsdp_roundtrip, 4)
+
+
+def test_mem_file_server_roundtrip(tmp_path):
+    """In-memory file server: write / read / rename / listdir / persist / report (single process)."""
+    from vescale_b200.checkpoint import MemFileClient, MemFileServer
+
+    srv = MemFileServer().start()
+    try:
+        c = MemFileClient(srv.address)
+        big = os.urandom(9 << 20)  # > 2 chunks
+        assert c.write("ck/a.bin", big) == len(big) and c.write("ck/empty", b"") == 0
+        assert c.read("ck/a.bin") == big and c.read("ck/empty") == b""
+        assert c.exists("ck/a.bin") and c.exists("ck") and not c.exists("ck/zzz")
+        c.rename("ck/a.bin", "ck/b.bin")
+        assert c.listdir("ck") == ["ck/b.bin", "ck/empty"]
+        assert c.persist("ck", str(tmp_path / "out")) == 2
+        assert open(tmp_path / "out" / "b.bin", "rb").read() == big
+        rep = c.report(who=3, status="saved", step=7)
+        assert rep["reports"]["3"]["status"] == "saved" and rep["reports"]["3"]["step"] == 7 and rep["files"] == 2
+        c.remove("ck/b.bin")
+        try:
+            c.read("ck/b.bin")
+            raise AssertionError("expected FileNotFoundError")
+        except FileNotFoundError:
+            pass
+    finally:
+        srv.stop()
+
+
+def _mem_ckpt(rank, world):
+    """Save into the memory server (``mem://``), reload from it under another layout, persist to disk and reload from
+    the persisted directory; second save of the same structure hits the plan cache; broadcast-on-load of replicated entries."""
+    import vescale_b200.checkpoint as ckpt
+    from vescale_b200 import Replicate, Shard, distribute_tensor, init_device_mesh
+    from vescale_b200.checkpoint import MemFileClient, MemFileServer
+    from vescale_b200.checkpoint.api import _PLANNERS
+    from vescale_b200.dtensor import RaggedShard, zeros
+
+    dev = device_type()
+    mesh = init_device_mesh(dev, (world,))
+    srv = MemFileServer().start() if rank == 0 else None
+    box = [srv.address if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    addr = box[0]
+    g = torch.Generator().manual_seed(0)
+    full = {"w": torch.randn(12, 10, generator=g).to(dev), "b": torch.randn(7, generator=g).to(dev)}
+
+    def make_state(scale):
+        return {"w": distribute_tensor(full["w"] * scale, mesh, [RaggedShard((0,), (1, 5, 0, 6))]), "b": (full["b"] * scale).clone(), "step": int(scale)}
+
+    for step in (1, 2):  # same structure twice: the second save re-uses the cached plan
+        ckpt.save(f"mem://{addr}/run/step{step}", {"model": make_state(float(step))})
+    dist.barrier()
+    pl = _PLANNERS["model"]
+    assert getattr(pl, "_enable_plan_caching", True)
+    client = MemFileClient(addr)
+    names = client.listdir("run/step2/model")
+    assert any(n.endswith(".metadata") for n in names) and sum(n.endswith(".distcp") for n in names) >= 1
+    # reload from memory under another layout
+    target = {"w": zeros(12, 10, device_mesh=mesh, placements=[Shard(1)]), "b": torch.zeros(7, device=dev), "step": 0}
+    ckpt.load(f"mem://{addr}/run/step2", {"model": target})
+    assert torch.equal(target["w"].full_tensor(), full["w"] * 2) and torch.equal(target["b"], full["b"] * 2)
+    # background persistence, then an ordinary file-system load with broadcast of the replicated entries
+    path = _shared_dir(rank)
+    dist.barrier()
+    if rank == 0:
+        assert client.persist("run/step1", path) >= 2
+    dist.barrier()
+    target = {"w": zeros(12, 10, device_mesh=mesh, placements=[Replicate()]), "b": torch.zeros(7, device=dev), "step": 0}
+    ckpt.load(path, {"model": target}, broadcast_checkpoint=True)
+    assert torch.equal(target["w"].full_tensor(), full["w"]) and torch.equal(target["b"], full["b"])
+    dist.barrier()
+    if rank == 0:
+        srv.stop()
+        shutil.rmtree(path, ignore_errors=True)
+
+
+def test_mem_checkpoint_plan_cache_broadcast_load():
+    run_distributed(_mem_ckpt, 4)

@@ -10,7 +10,13 @@ placement, mesh shape or world size (reference ``vescale/dtensor/vescale_utils/c
     vescale_b200.checkpoint.save(path, {"model": model, "optimizer": optimizer}, async_checkpoint=True)
     vescale_b200.checkpoint.load(path, {"model": model, "optimizer": optimizer})
 
-Parity: ``legacy/vescale/checkpoint/__init__.py``, ``api/vescale_checkpointer.py:71-249``.
+``path`` may be ``mem://host:port/dir``: the shards then land in a ``MemFileServer`` (gRPC, node-local memory) that persists
+them to disk in the background and serves fast restarts.  ``load(..., broadcast_checkpoint=True)`` makes one rank read the
+replicated entries and broadcast them.
+
+Parity: ``legacy/vescale/checkpoint/__init__.py``, ``api/vescale_checkpointer.py:71-249``, planner cache / balanced dedup
+``planner/common.py:65-132``, ``utilities/server/*`` (in-memory file server, report service).
 """
 from .api import VeScaleCheckpointer, load, save, wait_for_async  # noqa: F401
 from .pinned_pool import PinnedPool  # noqa: F401
+from .mem_server import MemFileClient, MemFileServer  # noqa: F401

@@ -19,6 +19,36 @@ __all__ = ["save", "load", "VeScaleCheckpointer", "wait_for_async"]
 _POOL = PinnedPool()
 _PENDING: List[Future] = []
 _ASYNC_PG = {"pg": None}
+_PLANNERS: Dict[str, Any] = {}
+
+
+def _save_planner(key: str):
+    """One planner per checkpoint key, kept across saves: torch DCP caches the local/global plan and the metadata when the
+    state-dict structure is unchanged (the legacy plan LRU cache, ``planner/common.py:65-89``) and spreads replicated items
+    over the ranks by accumulated bytes instead of writing them all from rank 0 (load-balanced dedup, ``:92-132``)."""
+    import torch.distributed.checkpoint as dcp
+
+    pl = _PLANNERS.get(key)
+    if pl is None:
+        try:
+            pl = dcp.DefaultSavePlanner(dedup_save_to_lowest_rank=False, enable_plan_caching=True)
+        except TypeError:  # older torch: no plan caching switch
+            pl = dcp.DefaultSavePlanner()
+        _PLANNERS[key] = pl
+    return pl
+
+
+def _storage(sub: str, write: bool):
+    """``mem://host:port/dir`` checkpoints go to the in-memory file server (``mem_server.py``); anything else is a path."""
+    from .mem_server import make_mem_reader, make_mem_writer, parse_mem_uri
+
+    if parse_mem_uri(sub) is None:
+        return {"checkpoint_id": sub}
+    return {"storage_writer": make_mem_writer(sub)} if write else {"storage_reader": make_mem_reader(sub)}
+
+
+def _join(path: str, key: str) -> str:
+    return f"{path.rstrip('/')}/{key}" if path.startswith("mem://") else os.path.join(path, key)
 
 
 def _flatten(prefix: str, obj, out: Dict[str, Any]) -> None:
@@ -80,8 +110,8 @@ class VeScaleCheckpointer:
 
         futures = []
         for key, obj in checkpoint_state.items():
-            sub = os.path.join(path, key)
-            if not dist.is_initialized() or dist.get_rank() == 0:
+            sub = _join(path, key)
+            if not path.startswith("mem://") and (not dist.is_initialized() or dist.get_rank() == 0):
                 os.makedirs(sub, exist_ok=True)
             sd = _state_of(obj)
             tensors = {k: v for k, v in sd.items() if isinstance(v, torch.Tensor)}
@@ -95,7 +125,7 @@ class VeScaleCheckpointer:
 
                 def work(host=host, sub=sub, pg=pg, fut=fut):
                     try:
-                        dcp.save(host, checkpoint_id=sub, process_group=pg)
+                        dcp.save(host, process_group=pg, planner=_save_planner("async/" + key), **_storage(sub, True))
                         fut.set_result(sub)
                     except Exception as e:  # noqa: BLE001
                         fut.set_exception(e)
@@ -109,7 +139,7 @@ class VeScaleCheckpointer:
                 _PENDING.append(fut)
                 futures.append(fut)
             else:
-                dcp.save(tensors, checkpoint_id=sub)
+                dcp.save(tensors, planner=_save_planner(key), **_storage(sub, True))
         return futures or None
 
     @classmethod
@@ -117,14 +147,37 @@ class VeScaleCheckpointer:
         import torch.distributed.checkpoint as dcp
 
         for key, obj in checkpoint_state.items():
-            sub = os.path.join(path, key)
+            sub = _join(path, key)
             sd = _state_of(obj)
             tensors = {k: v for k, v in sd.items() if isinstance(v, torch.Tensor)}
             extras_keys = [k for k, v in sd.items() if not isinstance(v, torch.Tensor)]
             req = dict(tensors)
             if extras_keys:
                 req["__extras__"] = {k: sd[k] for k in extras_keys}
-            dcp.load(req, checkpoint_id=sub)  # in place: DTensor/ tensor storages are filled with the resharded data
+            if broadcast_checkpoint and dist.is_initialized() and dist.get_world_size() > 1:
+                # replicated (non-DTensor) entries: one rank reads the files, everyone else gets them over the network
+                # (legacy ``storage/filesystem.py:817-865`` read_data_with_broadcast); sharded entries are read by their owners
+                plain = {k: v for k, v in req.items() if not isinstance(v, DTensor)}
+                sharded = {k: v for k, v in req.items() if isinstance(v, DTensor)}
+                if sharded:
+                    dcp.load(sharded, **_storage(sub, False))
+                if plain:
+                    if dist.get_rank() == 0:
+                        dcp.load(plain, no_dist=True, **_storage(sub, False))
+                    box = [plain.get("__extras__")]
+                    dist.broadcast_object_list(box, src=0)
+                    if "__extras__" in plain:
+                        plain["__extras__"] = req["__extras__"] = box[0]
+                    for k in sorted(k for k in plain if k != "__extras__"):
+                        t = plain[k]
+                        if dist.get_backend() == "nccl" and not t.is_cuda:
+                            tmp = t.cuda()
+                            dist.broadcast(tmp, src=0)
+                            t.copy_(tmp)
+                        else:
+                            dist.broadcast(t, src=0)
+            else:
+                dcp.load(req, **_storage(sub, False))  # in place: DTensor / tensor storages are filled with the resharded data
             if isinstance(obj, nn.Module):
                 pass  # state_dict tensors alias the module's parameters/buffers
             elif hasattr(obj, "load_state_dict") and not isinstance(obj, dict):
