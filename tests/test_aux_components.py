@@ -194,3 +194,60 @@ def _emulator_vs_real(rank, world):
 
 def test_emulator_matches_real_collectives():
     run_distributed(_emulator_vs_real, 4)
+
+
+def test_emulator_topology_tuning_primitives():
+    """Double binary tree structure, tuning-model monotonicity, chunk sizes, transition primitives and instrumentation."""
+    from vescale_b200 import DeviceMesh
+    from vescale_b200.emulator import (P2R, P2S, R2P, R2S, S2R, S2S, EmulatorInstrumentation, EmulatorProcessGroup, btree, calculate_chunk_size, double_tree,
+                                       double_tree_all_reduce, parse_graph_dump, select_algorithm)
+
+    for n in (2, 3, 4, 7, 8, 16):
+        t0, t1 = double_tree(n).trees
+        for t in (t0, t1):
+            assert sorted(t.parent) == list(range(n)) and sum(1 for p in t.parent.values() if p == -1) == 1
+            assert all(len(c) <= 2 for c in t.children.values())
+            seen, stack = set(), [t.root]
+            while stack:  # connected, acyclic
+                r = stack.pop()
+                assert r not in seen
+                seen.add(r)
+                stack += t.children[r]
+            assert seen == set(range(n))
+        if n > 2:  # leaves of one tree are inner nodes of the other (that is the point of the double tree)
+            leaves0 = {r for r in range(n) if not t0.children[r]}
+            leaves1 = {r for r in range(n) if not t1.children[r]}
+            assert len(leaves0 & leaves1) <= 1
+    xs = [torch.randn(50) * 10 ** (i - 3) for i in range(8)]
+    out = double_tree_all_reduce(xs)
+    torch.testing.assert_close(out[0], sum(xs), rtol=1e-5, atol=1e-3)
+    assert all(torch.equal(out[0], o) for o in out)
+    # tuning: small messages pick a low-latency protocol, large ones 'simple'; predicted time grows with size
+    small, big = select_algorithm("all_reduce", 1024, 8), select_algorithm("all_reduce", 256 << 20, 8)
+    assert small.proto in ("ll", "ll128") and big.proto == "simple" and big.time_us > small.time_us
+    assert select_algorithm("all_gather", 64 << 20, 8).algo == "ring"
+    assert calculate_chunk_size(256 << 20, 8, 16, "simple", "ring") >= calculate_chunk_size(64 << 10, 8, 16, "simple", "ring") >= 512
+    assert calculate_chunk_size(1 << 20, 8, 4, "ll", "ring") % 16 == 0
+    auto = EmulatorProcessGroup(8, algo="auto").all_reduce(xs)
+    torch.testing.assert_close(auto[0], sum(xs), rtol=1e-5, atol=1e-3)
+    xml = '<graphs version="1"><graph id="0" pattern="4" nchannels="2"><channel><net dev="0"/><gpu dev="0"/><gpu dev="2"/><gpu dev="1"/></channel><channel><gpu dev="1"/><gpu dev="0"/><gpu dev="2"/></channel></graph></graphs>'
+    assert parse_graph_dump(xml)["ring"] == [[0, 2, 1], [1, 0, 2]]
+    # primitives on a 2 x 2 mesh
+    mesh = DeviceMesh("meta", torch.arange(4).reshape(2, 2), mesh_dim_names=("a", "b"), _rank=0)
+    full = torch.arange(48.0).reshape(8, 6)
+    rep = [full.clone() for _ in range(4)]
+    sh = R2S(rep, mesh, 1, 0)
+    assert torch.equal(sh[1], full[4:]) and torch.equal(sh[2], full[:4])
+    assert all(torch.equal(t, full) for t in S2R(sh, mesh, 1, 0))
+    s2 = S2S(sh, mesh, 1, 0, 1)
+    assert torch.equal(s2[0], full[:, :3]) and torch.equal(s2[3], full[:, 3:])
+    part = R2P(rep, mesh, 0)
+    assert torch.equal(part[0], full) and torch.equal(part[2], torch.zeros_like(full))
+    assert all(torch.equal(t, full) for t in P2R(part, mesh, 0))
+    ps = P2S(part, mesh, 0, 1)
+    assert torch.equal(ps[0], full[:, :3]) and torch.equal(ps[2], full[:, 3:])
+    # instrumentation: ordinary torch code on per-rank lists
+    with EmulatorInstrumentation(4, [(torch, "add"), (torch, "relu")]):
+        y = torch.relu(torch.add(sh, 1.0))
+    assert isinstance(y, list) and torch.equal(y[1], torch.relu(full[4:] + 1))
+    assert torch.equal(torch.add(full, 1.0), full + 1)  # restored

@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-__all__ = ["ring_all_reduce", "ring_reduce_scatter", "tree_all_reduce", "all_gather", "all_to_all", "EmulatorProcessGroup", "nccl_chunking"]
+__all__ = ["ring_all_reduce", "ring_reduce_scatter", "tree_all_reduce", "double_tree_all_reduce", "all_gather", "all_to_all", "EmulatorProcessGroup", "nccl_chunking"]
 
 
 def nccl_chunking(count: int, nranks: int, nchannels: int = 1, chunk_elems: Optional[int] = None) -> List[Tuple[int, int, int]]:
@@ -103,6 +103,37 @@ def tree_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum") -> List[tor
     return [total.clone() for _ in range(n)]
 
 
+def double_tree_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum", chunk_elems: Optional[int] = None) -> List[torch.Tensor]:
+    """NCCL's tree all-reduce: the buffer alternates between the two trees of ``topo.double_tree`` chunk by chunk; within a
+    tree a node receives its children's partial results in child order, adds its own value last (``reduce`` up), and the
+    root's total is broadcast down.  The association order therefore depends on (tree, position) — which is exactly what
+    differs from a ring and what this function reproduces."""
+    from .topo import double_tree
+
+    n = len(inputs)
+    flat = [t.reshape(-1) for t in inputs]
+    count = flat[0].numel()
+    trees = double_tree(n).trees
+    cs = chunk_elems or max(1, (count + 1) // 2)
+    result = torch.empty_like(flat[0])
+
+    def up(tree, r, lo, hi):
+        acc = None
+        for c in tree.children.get(r, []):
+            v = up(tree, c, lo, hi)
+            acc = v if acc is None else _op(acc, v, op)
+        mine = flat[r][lo:hi]
+        return mine.clone() if acc is None else _op(acc, mine, op)
+
+    pos, k = 0, 0
+    while pos < count:
+        hi = min(count, pos + cs)
+        tree = trees[k % 2]
+        result[pos:hi] = up(tree, tree.root, pos, hi)
+        pos, k = hi, k + 1
+    return [result.clone().view_as(inputs[r]) for r in range(n)]
+
+
 def all_gather(inputs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     cat = torch.cat([t.reshape(-1) for t in inputs])
     return [cat.clone() for _ in inputs]
@@ -126,6 +157,15 @@ class EmulatorProcessGroup:
         assert len(tensors) == self.world_size
         if self.algo == "tree":
             return tree_all_reduce(tensors, op)
+        if self.algo == "double_tree":
+            return double_tree_all_reduce(tensors, op, self.chunk_elems)
+        if self.algo == "auto":  # let the tuning model pick, as NCCL would for this message size
+            from .tuning import select_algorithm
+
+            t = select_algorithm("all_reduce", tensors[0].numel() * tensors[0].element_size(), self.world_size)
+            if t.algo == "tree":
+                return double_tree_all_reduce(tensors, op, max(1, t.chunk_bytes // tensors[0].element_size()))
+            return ring_all_reduce(tensors, op, self.ring, t.nchannels, max(1, t.chunk_bytes // tensors[0].element_size()))
         return ring_all_reduce(tensors, op, self.ring, self.nchannels, self.chunk_elems)
 
     def reduce_scatter(self, tensors, op: str = "sum"):
