@@ -42,3 +42,53 @@ def _ep(rank, world):
 
 def test_expert_parallel_matches_local_experts():
     run_distributed(_ep, 4)
+
+
+def _realloc(rank, world):
+    """Experts (weights + Adam state) migrate between EP ranks mid-training; the function computed and the optimizer
+    trajectory are unchanged (legacy ``_moe_param_buffer.py:183-337`` dynamic re-allocation)."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.moe import MoEConfig, MoELayer
+    from vescale_b200.parallel.moe.api import balanced_allocation, reallocate_experts
+
+    dev = device_type()
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("EP",))
+    cfg = MoEConfig(32, 64, 8, 2, dtype=torch.float32)
+    layers, opts = [], []
+    for _ in range(2):  # twin A is re-allocated, twin B is not
+        l = MoELayer(cfg, mesh.get_group(0), device=dev)
+        l.reset_parameters(torch.Generator().manual_seed(4))
+        layers.append(l)
+        opts.append(torch.optim.Adam(l.parameters(), lr=1e-2))
+
+    def step(l, o, s):
+        x = torch.randn(24, 32, generator=torch.Generator().manual_seed(100 * s + rank)).to(dev)
+        y = l(x)
+        o.zero_grad()
+        y.pow(2).mean().backward()
+        for p in l.parameters():  # data-parallel part of the step: the router is replicated over EP ranks
+            if not getattr(p, "_is_expert_param", False):
+                dist.all_reduce(p.grad)
+        o.step()
+        return y.detach()
+
+    for s in range(2):
+        ya, yb = step(layers[0], opts[0], s), step(layers[1], opts[1], s)
+        assert torch.equal(ya, yb)
+    load = [5, 1, 9, 2, 7, 3, 8, 4]
+    slots = balanced_allocation(load, world)
+    assert sorted(slots) == list(range(8))
+    per_rank = [sum(load[e] for e in range(8) if slots[e] // 2 == r) for r in range(world)]
+    assert max(per_rank) - min(per_rank) <= 2
+    reallocate_experts(layers[0], slots, opts[0])
+    assert layers[0].slot_of_expert.tolist() == slots
+    for s in range(2, 5):
+        ya, yb = step(layers[0], opts[0], s), step(layers[1], opts[1], s)
+        torch.testing.assert_close(ya, yb, rtol=1e-5, atol=1e-6)
+    # and back to the identity layout: weights return to their original owners bit for bit
+    reallocate_experts(layers[0], list(range(8)), opts[0])
+    torch.testing.assert_close(layers[0].experts.w_down, layers[1].experts.w_down, rtol=1e-5, atol=1e-6)
+
+
+def test_dynamic_expert_reallocation():
+    run_distributed(_realloc, 4)

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .layer import MoEConfig, MoELayer
 
-__all__ = ["parallelize_experts", "ExpertsAllocator", "BasicExpertsAllocator", "TokenDispatcher", "BasicTokenDispatcher", "MoEOptimizer", "is_moe"]
+__all__ = ["parallelize_experts", "ExpertsAllocator", "BasicExpertsAllocator", "TokenDispatcher", "BasicTokenDispatcher", "MoEOptimizer", "is_moe", "reallocate_experts", "balanced_allocation"]
 
 
 class ExpertsAllocator:
@@ -119,3 +119,71 @@ class MoEOptimizer:
 
     def zero_grad(self, set_to_none=True):
         self.optimizer.zero_grad(set_to_none)
+
+
+def balanced_allocation(load_per_expert, ep_size: int) -> List[int]:
+    """Greedy load balancing: experts in decreasing load order go to the least-loaded rank that still has a free slot.
+    Returns ``slot_of_expert`` (global slot = rank * E/W + local index)."""
+    loads = [float(x) for x in load_per_expert]
+    E = len(loads)
+    per = E // ep_size
+    rank_load, rank_free = [0.0] * ep_size, [per] * ep_size
+    slot = [0] * E
+    for e in sorted(range(E), key=lambda i: -loads[i]):
+        r = min((r for r in range(ep_size) if rank_free[r] > 0), key=lambda r: rank_load[r])
+        slot[e] = r * per + (per - rank_free[r])
+        rank_free[r] -= 1
+        rank_load[r] += loads[e]
+    return slot
+
+
+@torch.no_grad()
+def reallocate_experts(layer: MoELayer, new_slot_of_expert, optimizer: Optional[torch.optim.Optimizer] = None) -> None:
+    """Move experts between EP ranks while training: weights *and* the optimizer state of every moved expert migrate to the
+    new owner, and the layer's routing table is updated (legacy ``MoELayerParamBuffer.refresh_buffer``,
+    ``_moe_param_buffer.py:183-337``).  ``new_slot_of_expert[e]`` is the global slot (rank * E/W + local index) expert ``e``
+    moves to; it must be a permutation of ``range(E)``.  One all-to-all per tensor; collective over the EP group."""
+    from ...comm.collectives import _p2p_all_to_all
+
+    E, W, El, me, group = layer.cfg.num_experts, layer.ep_size, layer.num_local, layer.ep_rank, layer.ep_group
+    new = [int(x) for x in (new_slot_of_expert.tolist() if isinstance(new_slot_of_expert, torch.Tensor) else new_slot_of_expert)]
+    if sorted(new) != list(range(E)):
+        raise ValueError("new_slot_of_expert must be a permutation of range(num_experts)")
+    old = [int(x) for x in layer.slot_of_expert.tolist()]
+    expert_at_old = {s: e for e, s in enumerate(old)}
+    expert_at_new = {s: e for e, s in enumerate(new)}
+    # my outgoing experts per destination rank (ordered by their new local index), incoming per source rank likewise
+    send = [[] for _ in range(W)]
+    for i in range(El):
+        e = expert_at_old[me * El + i]
+        send[new[e] // El].append((new[e] % El, i))
+    recv = [[] for _ in range(W)]
+    for j in range(El):
+        e = expert_at_new[me * El + j]
+        recv[old[e] // El].append(j)
+    for lst in send:
+        lst.sort()
+
+    def move(t: torch.Tensor) -> None:  # t: [El, ...] stacked per local slot
+        ins = [torch.stack([t[i] for _, i in send[d]]) if send[d] else t.new_empty((0, *t.shape[1:])) for d in range(W)]
+        outs = [t.new_empty((len(recv[s]), *t.shape[1:])) for s in range(W)]
+        if W == 1:
+            outs[0].copy_(ins[0])
+        elif dist.get_backend(group) == "nccl":
+            dist.all_to_all(outs, ins, group=group)
+        else:
+            _p2p_all_to_all(outs, ins, group)
+        for s in range(W):
+            for k, j in enumerate(sorted(recv[s])):
+                t[j].copy_(outs[s][k])
+
+    for p in (layer.experts.w_gate_up, layer.experts.w_down):
+        move(p.data)
+        if optimizer is not None:
+            st = optimizer.state.get(p, {})
+            for v in st.values():
+                if isinstance(v, torch.Tensor) and v.shape == p.shape:
+                    move(v)
+        if getattr(p, "main_grad", None) is not None and p.main_grad.shape == p.shape:
+            move(p.main_grad)
+    layer.slot_of_expert.copy_(torch.tensor(new, device=layer.slot_of_expert.device))

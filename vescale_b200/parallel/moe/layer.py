@@ -124,6 +124,9 @@ class MoELayer(nn.Module):
         self.experts = GroupedExperts(cfg, self.num_local, device)
         self.last_aux_loss: Optional[torch.Tensor] = None
         self.last_tokens_per_rank: Optional[List[int]] = None
+        # global slot (= ep_rank * num_local + local index) that currently hosts each expert; identity until
+        # ``reallocate_experts`` moves experts between ranks (dynamic load balancing)
+        self.register_buffer("slot_of_expert", torch.arange(cfg.num_experts, device=device), persistent=True)
         self.symm_dispatcher = None  # set by ``use_symmetric_dispatch`` (sm_100a kernels, no host sync in forward)
 
     def use_symmetric_dispatch(self, dispatcher) -> None:
@@ -146,15 +149,16 @@ class MoELayer(nn.Module):
         x2 = x.reshape(-1, shape[-1])
         T, k, E, W, El = x2.shape[0], self.cfg.top_k, self.cfg.num_experts, self.ep_size, self.num_local
         topv, topi, probs = self.router(x2)
+        slots = self.slot_of_expert[topi]  # where each chosen expert lives now
         if self.symm_dispatcher is not None and x2.is_cuda and W > 1:
             from .symm_dispatch import symm_moe_forward
 
-            out = symm_moe_forward(x2.contiguous(), topv, topi, self.experts.w_gate_up, self.experts.w_down, self.symm_dispatcher)
+            out = symm_moe_forward(x2.contiguous(), topv, slots, self.experts.w_gate_up, self.experts.w_down, self.symm_dispatcher)
             return out.view(shape)
         if self.cfg.aux_loss_coef > 0:
             frac = torch.zeros(E, device=x.device).index_add_(0, topi.reshape(-1), torch.ones(T * k, device=x.device)) / (T * k)
             self.last_aux_loss = self.cfg.aux_loss_coef * E * (frac * probs.mean(0)).sum()
-        flat_e = topi.reshape(-1)
+        flat_e = slots.reshape(-1)
         order = torch.argsort(flat_e, stable=True)
         token_of = order // k
         xs = x2[token_of]
