@@ -131,7 +131,18 @@ __global__ void __launch_bounds__(512) all_reduce_kernel(Peers bufs, void* mc, u
   if (MODE == 2) {
     for (size_t i = tid; i < nvec; i += stride) {
       float acc[Vec16<T>::N] = {};
-      for (int pi = 0; pi < world; ++pi) Vec16<T>::add(acc, ld_stream(reinterpret_cast<const uint4*>(bufs.p[(rank + pi) % world]) + i));
+      uint4 v[kMaxPeers / 2];  // all peer loads are issued before the first add: one NVLink round trip, not W of them
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int k = 0; k < kMaxPeers / 2; ++k) {
+          const int pi = half * (kMaxPeers / 2) + k;
+          if (pi < world) v[k] = ld_stream(reinterpret_cast<const uint4*>(bufs.p[(rank + pi) % world]) + i);
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxPeers / 2; ++k)
+          if (half * (kMaxPeers / 2) + k < world) Vec16<T>::add(acc, v[k]);
+      }
 #pragma unroll
       for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;
       out[i] = Vec16<T>::pack(acc);
@@ -144,7 +155,18 @@ __global__ void __launch_bounds__(512) all_reduce_kernel(Peers bufs, void* mc, u
       if (MODE == 1) {
         Vec16<T>::add(acc, Vec16<T>::mc_ld_reduce(reinterpret_cast<const uint4*>(mc) + i));
       } else {
-        for (int pi = 0; pi < world; ++pi) Vec16<T>::add(acc, ld_stream(reinterpret_cast<const uint4*>(bufs.p[(rank + pi) % world]) + i));
+        uint4 v[kMaxPeers / 2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int k = 0; k < kMaxPeers / 2; ++k) {
+            const int pi = half * (kMaxPeers / 2) + k;
+            if (pi < world) v[k] = ld_stream(reinterpret_cast<const uint4*>(bufs.p[(rank + pi) % world]) + i);
+          }
+#pragma unroll
+          for (int k = 0; k < kMaxPeers / 2; ++k)
+            if (half * (kMaxPeers / 2) + k < world) Vec16<T>::add(acc, v[k]);
+        }
       }
 #pragma unroll
       for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;

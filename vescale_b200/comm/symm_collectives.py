@@ -37,7 +37,9 @@ class SymmCollectives:
         self.mesh, self.md, self.device = mesh, md, dev
         self.arena: SymmArena = comm.arena
         self.world, self.rank = comm.world, comm.rank
-        self.use_multimem = comm.use_multimem
+        # NVLS two-shot wins from 4 ranks up (profiles/coll_bench_w8_r1.json: 1.2-1.6x NCCL at >= 2 MB); between two GPUs the
+        # P2P two-shot is faster than going through the switch (coll_bench_w2_r1.json)
+        self.use_multimem = comm.use_multimem and self.world > 2
         self.ops = _ext.ops()
         self.slot = self.arena.new_slots(2)
         self.epoch = 0

@@ -27,8 +27,8 @@ __all__ = [
     "set_gemm_backend",
 ]
 
-# auto: tcgen05 kernel for the forward (NT) and dgrad (NN) shapes — it measures 4-14 % above cuBLAS on B200
-# (profiles/micro_r2.json); wgrad (TN, both operands MN-major) stays on cuBLAS, which is ~7 % faster there.
+# auto: the tcgen05 kernel and cuBLAS are timed once per (kind, M, N, K) and the faster one is kept (see ``_autotune``);
+# tcgen05 / cublas force one back end.  wgrad (TN, both operands MN-major) stays on cuBLAS, which is ~7 % faster there.
 _CFG = {"gemm": "auto", "wgrad": "cublas"}  # gemm: auto | tcgen05 | cublas ; wgrad: cublas | tcgen05
 
 
