@@ -110,3 +110,36 @@ def test_env_flags(monkeypatch):
 
     with pytest.raises(NotImplementedError):
         _replicate_fallback(OpSchema(torch.ops.aten.frac.default, (a._spec,), {}))
+
+
+def test_utils_package():
+    """monkey-patch helper (reference ``vescale/utils/monkey_patch.py``), env-flag registry covers every flag in the tree."""
+    import re
+    import subprocess
+
+    from vescale_b200.utils import FLAGS, describe_flags, flag, patch_method, unpatch_all
+
+    class T:
+        def f(self):
+            return 1
+
+    @patch_method(T, "f")
+    def f2(self):
+        return 2
+
+    @patch_method(T, "g")
+    def g(self):
+        return 3
+
+    assert T().f() == 2 and T().g() == 3 and f2.__wrapped_original__(T()) == 1
+    unpatch_all()
+    assert T().f() == 1 and not hasattr(T, "g")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    used = set()
+    for dp, _, fs in os.walk(os.path.join(root, "vescale_b200")):
+        for fn in fs:
+            if fn.endswith(".py"):
+                used |= set(re.findall(r"VESCALE_[A-Z0-9_]+", open(os.path.join(dp, fn)).read()))
+    used -= {"VESCALE_DEVICE_MESH"} - set(FLAGS)  # the global VeDeviceMesh object shares the prefix
+    assert used <= set(FLAGS), f"flags missing from utils.env.FLAGS: {sorted(used - set(FLAGS))}"
+    assert "VESCALE_STRICT_RULES" in describe_flags() and flag("VESCALE_B200_SYMM_CHUNK_MB") == 2048

@@ -192,6 +192,16 @@ def _factories_random(rank, world):
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
     assert abs(outs[0].mean().item()) < 0.5 and 0.5 < outs[0].std().item() < 1.5
+    # cross-rank equality helpers: a mismatch on one rank makes every rank say False
+    from vescale_b200.dtensor import allclose, equal
+
+    a = vd.ones(8, 6, device_mesh=mesh, placements=[Shard(0)])
+    b = vd.ones(8, 6, device_mesh=mesh, placements=[Shard(0)])
+    assert equal(a, b) and allclose(a, b)
+    if rank == 2:
+        b.to_local()[0, 0] = 1.0 + 1e-7
+    assert not equal(a, b) and allclose(a, b, rtol=1e-5)
+    assert not equal(a, vd.ones(8, 6, device_mesh=mesh, placements=[Shard(1)]))
     # dropout on a sharded tensor: replicas agree, shards differ
     vd.manual_seed(7, mesh)
     x = vd.ones(8, 64, device_mesh=mesh, placements=[Shard(0)])

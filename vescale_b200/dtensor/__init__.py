@@ -19,6 +19,8 @@ from ..mesh import DeviceMesh, init_device_mesh  # noqa: F401
 from .api import (  # noqa: F401
     DTensor,
     arange,
+    equal,
+    allclose,
     distribute_tensor,
     empty,
     from_local,
@@ -41,7 +43,7 @@ from .cross_mesh import cross_mesh_redistribute  # noqa: F401
 
 __all__ = [
     "DTensor", "DeviceMesh", "init_device_mesh", "distribute_tensor", "from_local", "to_local", "redistribute_dtensor",
-    "ones", "empty", "full", "rand", "randn", "zeros", "arange", "DTensorSpec", "TensorMeta", "Placement", "Shard",
+    "ones", "empty", "full", "rand", "randn", "zeros", "arange", "equal", "allclose", "DTensorSpec", "TensorMeta", "Placement", "Shard",
     "Replicate", "Partial", "_Partial", "RaggedShard", "_StridedRaggedShard", "_StridedShard", "InterleavedShard",
     "is_ragged_shard", "implicit_replication", "manual_seed", "loss_parallel", "get_sub_spec",
     "vescale_all_gather", "vescale_all_reduce", "vescale_reduce_scatter", "cross_mesh_redistribute",

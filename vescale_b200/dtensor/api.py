@@ -41,6 +41,8 @@ __all__ = [
     "rand",
     "randn",
     "arange",
+    "equal",
+    "allclose",
     "implicit_replication",
 ]
 
@@ -399,3 +401,33 @@ def arange(*args, dtype=None, device_mesh=None, placements=None, requires_grad=F
     local = slice_local(full_t, mesh, placements)
     spec = DTensorSpec(mesh, placements, TensorMeta(tuple(full_t.shape), contiguous_stride(full_t.shape), full_t.dtype))
     return DTensor(local.requires_grad_(requires_grad), spec, requires_grad=requires_grad)
+
+
+def _all_ranks_agree(ok: bool, mesh) -> bool:
+    """AND of a per-rank boolean over every rank of ``mesh`` (one tiny all-reduce per mesh dim)."""
+    from ..comm import collectives as C
+
+    t = torch.tensor([1.0 if ok else 0.0], device=mesh.device_type if mesh.device_type != "meta" else "cpu")
+    for d in range(mesh.ndim):
+        if mesh.size(d) > 1:
+            t = C.mesh_all_reduce(t, mesh, "min", d)
+    return bool(t.item() > 0.5)
+
+
+def equal(a: DTensor, b: DTensor) -> bool:
+    """True on every rank iff the two DTensors have the same mesh, placements, global shape and bitwise-equal local shards on
+    *all* ranks (legacy ``dtensor/_utils.py:326-411`` ``equal``; a local mismatch anywhere makes every rank return False)."""
+    if not (isinstance(a, DTensor) and isinstance(b, DTensor)):
+        raise TypeError("equal() compares two DTensors")
+    if a.device_mesh != b.device_mesh or tuple(a.placements) != tuple(b.placements) or tuple(a.shape) != tuple(b.shape):
+        return False
+    return _all_ranks_agree(torch.equal(a._local_tensor, b._local_tensor), a.device_mesh)
+
+
+def allclose(a: DTensor, b: DTensor, rtol: float = 1e-5, atol: float = 1e-8, equal_nan: bool = False) -> bool:
+    """``torch.allclose`` over all shards of two identically laid out DTensors, agreed on by every rank."""
+    if not (isinstance(a, DTensor) and isinstance(b, DTensor)):
+        raise TypeError("allclose() compares two DTensors")
+    if a.device_mesh != b.device_mesh or tuple(a.placements) != tuple(b.placements) or tuple(a.shape) != tuple(b.shape):
+        return False
+    return _all_ranks_agree(torch.allclose(a._local_tensor, b._local_tensor, rtol=rtol, atol=atol, equal_nan=equal_nan), a.device_mesh)

@@ -1,0 +1,40 @@
+"""Every environment switch the framework reads, in one table (name, default, meaning).  ``flag(name)`` returns the parsed
+value; modules may still read ``os.environ`` directly on hot paths, but each name used anywhere must be listed here
+(``tests/test_contracts.py`` greps for strays)."""
+from __future__ import annotations
+
+import os
+from typing import Dict, Tuple
+
+__all__ = ["FLAGS", "flag", "describe_flags"]
+
+# name -> (default, description)
+FLAGS: Dict[str, Tuple[str, str]] = {
+    "VESCALE_DISABLE_REDISTRIBUTE": ("0", "1 = op dispatch raises instead of resharding operands implicitly (legacy default was 1)"),
+    "VESCALE_DISABLE_RUN_CHECK": ("0", "1 = DTensor.from_local skips the cross-rank metadata check"),
+    "VESCALE_STRICT_RULES": ("0", "1 = ops without a sharding rule raise instead of falling back to replicated execution"),
+    "VESCALE_DEBUG_MODE": ("", "non-empty = DebugLogger prints every dispatched op and mesh collective (rank filter after ':')"),
+    "VESCALE_DUMMY_P2P": ("0", "1 = pipeline p2p ops are logged, not executed (schedule dry run)"),
+    "VESCALE_DUMP_INSTRUCTION": ("0", "1 = the pipeline engine dumps each rank's instruction list to a file"),
+    "VESCALE_DEVICE_MESH": ("", "internal: name of the global VeDeviceMesh registry entry"),
+    "VESCALE_B200_ALLOW_FALLBACK": ("0", "1 = allow PyTorch fallbacks on a CUDA device when vescale_b200/_C.so is missing (default: fail loudly)"),
+    "VESCALE_B200_MULTIMEM": ("1", "0 = never use NVLS multimem instructions in the symmetric-memory kernels"),
+    "VESCALE_B200_SYMM_CHUNK_MB": ("2048", "size of one symmetric-memory arena chunk (one rendezvous per chunk)"),
+    "VESCALE_B200_AG_CTAS": ("0", "CTAs of the FSDP pull all-gather kernel (0 = a quarter of the SMs)"),
+    "VESCALE_B200_RS_CTAS": ("0", "CTAs of the fused reduce-scatter kernels (0 = half of the SMs)"),
+}
+
+
+def flag(name: str):
+    default, _ = FLAGS[name]
+    v = os.environ.get(name, default)
+    if default in ("0", "1"):
+        return v == "1"
+    if default.isdigit():
+        return int(v)
+    return v
+
+
+def describe_flags() -> str:
+    w = max(len(k) for k in FLAGS)
+    return "\n".join(f"{k.ljust(w)}  default={d!r:8}  {doc}" for k, (d, doc) in FLAGS.items())
