@@ -143,3 +143,22 @@ def test_utils_package():
     used -= {"VESCALE_DEVICE_MESH"} - set(FLAGS)  # the global VeDeviceMesh object shares the prefix
     assert used <= set(FLAGS), f"flags missing from utils.env.FLAGS: {sorted(used - set(FLAGS))}"
     assert "VESCALE_STRICT_RULES" in describe_flags() and flag("VESCALE_B200_SYMM_CHUNK_MB") == 2048
+
+
+def test_root_level_api_surface():
+    """SURVEY §7.5 checklist: the reference's root-level names resolve on ``vescale_b200`` and on the ``vescale`` alias."""
+    import vescale
+    import vescale_b200 as v
+
+    for name in ("DTensor DeviceMesh init_device_mesh Placement Shard Replicate Partial InterleavedShard RaggedShard distribute_tensor redistribute_dtensor "
+                 "from_local to_local normalize_placements parallelize_module is_dmodule PlacementsInterface auto_parallelize_module "
+                 "set_plan_overriding_policy get_plan_overriding_policy DistributedDataParallel DistributedOptimizer BasicOptimizer BasicOptimizerHook "
+                 "deferred_init is_deferred materialize_dtensor materialize_dparameter vescale_all_gather vescale_all_reduce vescale_reduce_scatter "
+                 "checkpoint loss_parallel manual_seed fully_shard FSDPAdamW PipeEngine PipelineParallelPlan parallelize_experts").split():
+        assert getattr(v, name) is not None, name
+        assert getattr(vescale, name) is getattr(v, name), name
+    import vescale_b200.dtensor as d
+
+    for name in "distribute_tensor ones empty full rand randn zeros arange DTensorSpec TensorMeta RaggedShard _StridedRaggedShard _StridedShard _Partial is_ragged_shard equal allclose".split():
+        assert hasattr(d, name), name
+    assert repr(d.RaggedShard((0,), (1, 2))) == "RaggedShard(dims=(0,), local_units=(1, 2))"

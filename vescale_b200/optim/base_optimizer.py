@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from ..dtensor.api import DTensor
 
-__all__ = ["BasicOptimizer", "GradOptimizerHookBase"]
+__all__ = ["BasicOptimizer", "GradOptimizerHookBase", "BasicOptimizerHook"]
 
 
 class GradOptimizerHookBase:
@@ -21,6 +21,26 @@ class GradOptimizerHookBase:
     @staticmethod
     def step_post_hook(optim, *a, **kw):
         raise NotImplementedError
+
+
+class BasicOptimizerHook(GradOptimizerHookBase):
+    """Before ``optimizer.step``: parameters whose gradient lives only in a DDP/FSDP ``main_grad`` view get a ``.grad`` over
+    that same storage (wrapped as a DTensor with the parameter's placements when the parameter is one), so any
+    ``torch.optim`` optimizer can consume it (legacy ``optim/base_optimizer.py:45-70``)."""
+
+    @staticmethod
+    def step_pre_hook(optim, *a, **kw):
+        for group in optim.param_groups:
+            for p in group["params"]:
+                mg = getattr(p, "main_grad", None)
+                if p.grad is not None or mg is None:
+                    continue
+                data = p.data if isinstance(p.data, DTensor) else (p if isinstance(p, DTensor) else None)
+                p.grad = DTensor(mg.to(p.dtype), data._spec) if data is not None else mg.to(p.dtype)
+
+    @staticmethod
+    def step_post_hook(optim, *a, **kw):
+        return None
 
 
 class BasicOptimizer:
