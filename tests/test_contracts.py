@@ -162,3 +162,19 @@ def test_root_level_api_surface():
     for name in "distribute_tensor ones empty full rand randn zeros arange DTensorSpec TensorMeta RaggedShard _StridedRaggedShard _StridedShard _Partial is_ragged_shard equal allclose".split():
         assert hasattr(d, name), name
     assert repr(d.RaggedShard((0,), (1, 2))) == "RaggedShard(dims=(0,), local_units=(1, 2))"
+
+
+def test_defer_resharding_toggle():
+    """Partial + Partial stays Partial (one reduction later) by default; ``defer_resharding(False)`` reduces each operand
+    first, the legacy order (``DeferReshardMode``, legacy ``_dispatch_patch.py:134``)."""
+    from vescale_b200 import Partial, Replicate
+    from vescale_b200.dtensor import DTensor, defer_resharding
+
+    mesh = _mesh((1,))
+    mk = lambda: DTensor.from_local(torch.ones(2, 2), mesh, [Partial()], run_check=False, shape=(2, 2))  # noqa: E731
+    assert (mk() + mk()).placements == (Partial(),)
+    with defer_resharding(False):
+        assert (mk() + mk()).placements == (Replicate(),)
+        with defer_resharding(True):
+            assert (mk() + mk()).placements == (Partial(),)
+    assert (mk() + mk() - mk()).placements == (Partial(),)

@@ -202,6 +202,24 @@ def _factories_random(rank, world):
         b.to_local()[0, 0] = 1.0 + 1e-7
     assert not equal(a, b) and allclose(a, b, rtol=1e-5)
     assert not equal(a, vd.ones(8, 6, device_mesh=mesh, placements=[Shard(1)]))
+    # single-device-equivalent aten random ops (ThreadBasedRNGTracker): the mask / values do not depend on the sharding
+    from vescale_b200.dtensor.random import OffsetBasedRNGTracker, TensorParallelRNGTracker, ThreadBasedRNGTracker, set_rng_tracker
+
+    set_rng_tracker(ThreadBasedRNGTracker())
+    base = torch.arange(48.0).reshape(8, 6).to(z.device) + 1
+    outs_d, outs_n = [], []
+    for pl in ([Replicate()], [Shard(0)], [Shard(1)], [RaggedShard((0,), (1, 0, 2, 1))]):
+        vd.manual_seed(99, mesh)
+        dt = vd.distribute_tensor(base, mesh, pl, src_data_rank=None)
+        outs_d.append(torch.nn.functional.dropout(dt, 0.4, training=True).full_tensor())
+        outs_n.append(torch.empty_like(dt).normal_(1.0, 2.0).full_tensor() if not isinstance(pl[0], RaggedShard) else None)
+    assert all(torch.equal(o, outs_d[0]) for o in outs_d[1:]) and 0.15 < (outs_d[0] == 0).float().mean().item() < 0.65
+    assert all(torch.equal(o, outs_n[0]) for o in outs_n[1:] if o is not None)
+    set_rng_tracker(TensorParallelRNGTracker(tp_mesh_dim=0))
+    vd.manual_seed(5, mesh)
+    y = torch.nn.functional.dropout(vd.ones(8, 64, device_mesh=mesh, placements=[Shard(0)]), 0.5, training=True).full_tensor()
+    assert not torch.equal(y[:2], y[2:4])  # TP ranks draw different streams
+    set_rng_tracker(OffsetBasedRNGTracker())
     # dropout on a sharded tensor: replicas agree, shards differ
     vd.manual_seed(7, mesh)
     x = vd.ones(8, 64, device_mesh=mesh, placements=[Shard(0)])

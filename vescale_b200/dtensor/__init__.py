@@ -26,6 +26,7 @@ from .api import (  # noqa: F401
     from_local,
     full,
     implicit_replication,
+    defer_resharding,
     ones,
     rand,
     randn,

@@ -44,6 +44,7 @@ __all__ = [
     "equal",
     "allclose",
     "implicit_replication",
+    "defer_resharding",
 ]
 
 
@@ -100,6 +101,33 @@ class _ToLocal(torch.autograd.Function):
 
 
 _IMPLICIT_REPLICATION = [False]
+
+
+class defer_resharding:
+    """``with defer_resharding(False): ...`` — inside, ``Partial + Partial`` is reduced operand by operand before the add (the
+    legacy package's default order); outside (and with ``True``) it stays ``Partial`` and is reduced once, later
+    (legacy ``DeferReshardMode``, ``dtensor/_dispatch_patch.py:134``).  Clears the propagation cache on entry and exit because
+    the choice changes rule outputs."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = bool(enabled)
+
+    def __enter__(self):
+        from .rules import pointwise
+        from .sharding_prop import propagator
+
+        self._prev = pointwise.DEFER_RESHARD[0]
+        pointwise.DEFER_RESHARD[0] = self.enabled
+        propagator._cache.clear()
+        return self
+
+    def __exit__(self, *exc):
+        from .rules import pointwise
+        from .sharding_prop import propagator
+
+        pointwise.DEFER_RESHARD[0] = self._prev
+        propagator._cache.clear()
+        return False
 
 
 class implicit_replication:

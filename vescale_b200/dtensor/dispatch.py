@@ -129,11 +129,14 @@ class OpDispatcher:
             out_sh.pre(local_args, local_kwargs, mesh)
 
         if op in _RANDOM_OPS:
-            from .random import rng_region
+            from .random import get_rng_tracker
 
             first = schema.tensor_specs()[0]
-            with rng_region(first):
-                local_out = op(*local_args, **local_kwargs)
+            tracker = get_rng_tracker()
+            local_out = tracker.run(op, local_args, local_kwargs, first)
+            if local_out is NotImplemented:
+                with tracker.region(first):
+                    local_out = op(*local_args, **local_kwargs)
         else:
             local_out = op(*local_args, **local_kwargs)
         if out_sh.post is not None:

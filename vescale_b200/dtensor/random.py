@@ -27,7 +27,8 @@ from ..layout import compute_local_shape_and_global_offset, local_boxes
 from ..placement import RaggedShard, Shard
 from ..spec import DTensorSpec
 
-__all__ = ["manual_seed", "rng_region", "sharded_random_fill", "philox_uniform_reference", "get_rng_state", "set_rng_state"]
+__all__ = ["manual_seed", "rng_region", "sharded_random_fill", "philox_uniform_reference", "get_rng_state", "set_rng_state", "RNGStateTracker",
+           "OffsetBasedRNGTracker", "ThreadBasedRNGTracker", "TensorParallelRNGTracker", "get_rng_tracker", "set_rng_tracker"]
 
 _STATE = {"seed": 0, "offset": 0, "initialised": False}
 
@@ -208,3 +209,98 @@ def rng_region(spec: DTensorSpec):
             finally:
                 pass
         _STATE["offset"] += (nshards * window) // 4
+
+
+# ------------------------------------------------------------------------------- tracker objects (legacy API shape)
+class RNGStateTracker:
+    """How aten random ops (dropout, ``uniform_``, ``normal_``, ``rand_like`` ...) behave on shards.  ``run`` returns
+    ``NotImplemented`` for ops the tracker does not special-case; the dispatcher then runs the op inside ``region``."""
+
+    single_device_equivalent = False
+
+    def manual_seed(self, seed: int, device_mesh=None) -> None:
+        manual_seed(seed, device_mesh)
+
+    def region(self, spec: DTensorSpec):
+        return rng_region(spec)
+
+    def run(self, op, local_args, local_kwargs, spec: DTensorSpec):
+        return NotImplemented
+
+
+class OffsetBasedRNGTracker(RNGStateTracker):
+    """Same seed everywhere; each distinct shard draws from its own Philox offset window, replicas share one
+    (legacy ``dtensor/random.py:167``; torch DTensor's scheme).  Results depend on the sharding."""
+
+
+class ThreadBasedRNGTracker(RNGStateTracker):
+    """Single-device-equivalent randomness: the value at a global position does not depend on how the tensor is sharded
+    (legacy ``dtensor/random.py:340-518`` — there by packing the shard geometry into the CUDA generator state for patched
+    aten kernels; here the counter-based Philox of ``sharded_random_fill`` is evaluated per global index)."""
+
+    single_device_equivalent = True
+
+    def run(self, op, local_args, local_kwargs, spec: DTensorSpec):
+        aten = torch.ops.aten
+        x = local_args[0]
+        if op is aten.native_dropout.default:
+            p, train = float(local_args[1]), local_args[2]
+            if not train or p == 0.0:
+                return x.clone(), torch.ones_like(x, dtype=torch.bool)
+            u = sharded_random_fill(torch.empty(x.shape, dtype=torch.float32, device=x.device), spec, "uniform")
+            mask = u >= p
+            return x * mask.to(x.dtype) * (1.0 / (1.0 - p)), mask
+        if op is aten.uniform_.default:
+            lo = float(local_args[1]) if len(local_args) > 1 else float(local_kwargs.get("from", 0.0))
+            hi = float(local_args[2]) if len(local_args) > 2 else float(local_kwargs.get("to", 1.0))
+            return sharded_random_fill(x, spec, "uniform", low=lo, high=hi)
+        if op is aten.normal_.default:
+            mean = float(local_args[1]) if len(local_args) > 1 else float(local_kwargs.get("mean", 0.0))
+            std = float(local_args[2]) if len(local_args) > 2 else float(local_kwargs.get("std", 1.0))
+            return sharded_random_fill(x, spec, "normal", mean=mean, std=std)
+        if op is aten.rand_like.default:
+            return sharded_random_fill(torch.empty_like(x), spec, "uniform")
+        if op is aten.randn_like.default:
+            return sharded_random_fill(torch.empty_like(x), spec, "normal")
+        if op is aten.bernoulli_.float:
+            p = float(local_args[1]) if len(local_args) > 1 else float(local_kwargs.get("p", 0.5))
+            u = sharded_random_fill(torch.empty(x.shape, dtype=torch.float32, device=x.device), spec, "uniform")
+            return x.copy_((u < p).to(x.dtype))
+        if op is aten.bernoulli.default:
+            u = sharded_random_fill(torch.empty(x.shape, dtype=torch.float32, device=x.device), spec, "uniform")
+            return (u < x.float()).to(x.dtype)
+        return NotImplemented
+
+
+class TensorParallelRNGTracker(RNGStateTracker):
+    """Megatron-style: ranks of the tensor-parallel mesh dim draw from *different* streams (dropout inside a TP region),
+    every other mesh dim shares one (legacy ``dtensor/random.py:521``)."""
+
+    def __init__(self, tp_mesh_dim=-1, offset: int = 2718):
+        self.tp_mesh_dim, self.offset = tp_mesh_dim, offset
+
+    @contextlib.contextmanager
+    def region(self, spec: DTensorSpec):
+        d = self.tp_mesh_dim if self.tp_mesh_dim >= 0 else spec.mesh.ndim + self.tp_mesh_dim
+        tp_rank = spec.mesh.get_coordinate()[d]
+        devices = [torch.cuda.current_device()] if (spec.mesh.device_type == "cuda" and torch.cuda.is_available()) else []
+        with torch.random.fork_rng(devices=devices):
+            torch.manual_seed((_STATE["seed"] + self.offset + tp_rank + 1000003 * _STATE["offset"]) & 0x7FFFFFFFFFFF)
+            yield
+        _STATE["offset"] += 1
+
+
+_TRACKER = {"t": None}
+
+
+def get_rng_tracker() -> RNGStateTracker:
+    if _TRACKER["t"] is None:
+        import os
+
+        # the legacy default: VESCALE_SINGLE_DEVICE_RAND=1 selects the thread-based (single-device-equivalent) tracker
+        _TRACKER["t"] = ThreadBasedRNGTracker() if os.environ.get("VESCALE_SINGLE_DEVICE_RAND", "0") == "1" else OffsetBasedRNGTracker()
+    return _TRACKER["t"]
+
+
+def set_rng_tracker(tracker: Optional[RNGStateTracker]) -> None:
+    _TRACKER["t"] = tracker

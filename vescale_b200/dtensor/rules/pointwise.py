@@ -138,8 +138,17 @@ def _numel(s: DTensorSpec) -> int:
     return n
 
 
+# Deferred resharding (legacy ``_dispatch_patch.py:134`` ``DeferReshardMode``): ``Partial + Partial`` stays ``Partial`` so a
+# chain of additions costs one all-reduce at the end instead of one per operand.  It is on by default here (the legacy
+# package needed a context manager to turn it on); ``defer_resharding(False)`` restores the eager reduce-then-add order,
+# e.g. to reproduce the legacy summation order bit for bit.
+DEFER_RESHARD = [True]
+
+
 def _partial_passthrough(base: str, specs, i, scalar_other: bool = False) -> Optional[Placement]:
     ps = [s.placements[i] for s in specs]
+    if not DEFER_RESHARD[0] and base in _LINEAR_ADD and sum(1 for p in ps if p.is_partial()) > 1:
+        return None
     partials = [p for p in ps if p.is_partial()]
     op0 = partials[0]
     if any(p != op0 for p in partials):

@@ -13,6 +13,7 @@ FLAGS: Dict[str, Tuple[str, str]] = {
     "VESCALE_DISABLE_REDISTRIBUTE": ("0", "1 = op dispatch raises instead of resharding operands implicitly (legacy default was 1)"),
     "VESCALE_DISABLE_RUN_CHECK": ("0", "1 = DTensor.from_local skips the cross-rank metadata check"),
     "VESCALE_STRICT_RULES": ("0", "1 = ops without a sharding rule raise instead of falling back to replicated execution"),
+    "VESCALE_SINGLE_DEVICE_RAND": ("0", "1 = aten random ops on DTensors (dropout, uniform_, normal_, rand_like) are single-device-equivalent (ThreadBasedRNGTracker)"),
     "VESCALE_DEBUG_MODE": ("", "non-empty = DebugLogger prints every dispatched op and mesh collective (rank filter after ':')"),
     "VESCALE_DUMMY_P2P": ("0", "1 = pipeline p2p ops are logged, not executed (schedule dry run)"),
     "VESCALE_DUMP_INSTRUCTION": ("0", "1 = the pipeline engine dumps each rank's instruction list to a file"),
