@@ -13,7 +13,13 @@ __all__ = ["PinnedPool"]
 
 
 class PinnedPool:
-    def __init__(self):
+    """``shared=True``: buffers live in POSIX shared memory (so checkpoint worker *processes* can serialise them without a
+    copy) and are page-locked in place with ``cudaHostRegister`` — the legacy pool's design; the default allocates ordinary
+    pinned memory for in-process writer threads."""
+
+    def __init__(self, shared: bool = False):
+        self.shared = shared
+        self._registered: List[torch.Tensor] = []
         self._free: Dict[Tuple[int, torch.dtype], List[torch.Tensor]] = defaultdict(list)
         self._lock = threading.Lock()
         self._stream = None
@@ -25,9 +31,28 @@ class PinnedPool:
             if lst:
                 return lst.pop()
         pin = torch.cuda.is_available()
-        t = torch.empty(numel, dtype=dtype, pin_memory=pin)
+        if self.shared:
+            t = torch.empty(numel, dtype=dtype).share_memory_()
+            if pin and t.numel():
+                try:  # page-lock the shared segment in place (cudaHostRegisterDefault)
+                    err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+                    if int(err) == 0:
+                        self._registered.append(t)
+                except Exception:  # noqa: BLE001  — staging still works through pageable memory
+                    pass
+        else:
+            t = torch.empty(numel, dtype=dtype, pin_memory=pin)
         self.bytes_allocated += t.numel() * t.element_size()
         return t
+
+    def close(self) -> None:
+        """Unregister shared segments (process exit does it implicitly)."""
+        for t in self._registered:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+            except Exception:  # noqa: BLE001
+                pass
+        self._registered.clear()
 
     def release(self, t: torch.Tensor) -> None:
         base = t._pool_base if hasattr(t, "_pool_base") else t
