@@ -588,6 +588,15 @@ def _materialize(module: nn.Module, names: List[str], device: torch.device, init
             m = getattr(m, a)
         old = m._parameters[parts[-1]]
         m._parameters[parts[-1]] = nn.Parameter(torch.empty(old.shape, dtype=old.dtype, device=device), requires_grad=old.requires_grad)
+    # meta buffers (routing tables, rope caches ...): allocate, then let the owning module fill them (``reset_buffers``)
+    for sub in module.modules():
+        touched = False
+        for bn, b in list(sub._buffers.items()):
+            if b is not None and b.device.type == "meta":
+                sub._buffers[bn] = torch.zeros(b.shape, dtype=b.dtype, device=device)
+                touched = True
+        if touched and hasattr(sub, "reset_buffers"):
+            sub.reset_buffers()
     if init_fn is not None:
         init_fn(module)
     elif hasattr(module, "reset_parameters"):

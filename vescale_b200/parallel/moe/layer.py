@@ -129,6 +129,10 @@ class MoELayer(nn.Module):
         self.register_buffer("slot_of_expert", torch.arange(cfg.num_experts, device=device), persistent=True)
         self.symm_dispatcher = None  # set by ``use_symmetric_dispatch`` (sm_100a kernels, no host sync in forward)
 
+    def reset_buffers(self) -> None:
+        """(Re)initialise non-parameter state after a meta-device materialisation: experts start at their home slots."""
+        self.slot_of_expert.copy_(torch.arange(self.cfg.num_experts, device=self.slot_of_expert.device))
+
     def use_symmetric_dispatch(self, dispatcher) -> None:
         self.symm_dispatcher = dispatcher
 
