@@ -46,6 +46,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--tp", type=int, default=1, help="tensor/sequence-parallel degree (2-D: FSDP over world/tp x TP over tp, fused TP kernels)")
     p.add_argument("--tp-impl", default="fused", choices=["fused", "plain"], help="fused = ag_gemm/gemm_rs sm_100a kernels; plain = NCCL + library GEMMs")
+    p.add_argument("--fp8", action="store_true", help="block-scaled e4m3 forward GEMMs in the decoder blocks (BASELINE config 5; use with --model llama3_70b)")
     p.add_argument("--prefetch", type=int, default=1, help="FSDP all-gather prefetch depth (0 = every all-gather exposed: the memory-lean mode)")
     p.add_argument("--fuse-first-gemm", action="store_true", help="exposed all-gathers: the unit's first GEMM gathers its own weight (wag_gemm)")
     p.add_argument("--profile", default=None, help="after the timed regions, run ONE extra step under torch.profiler and write the per-kernel table here")
@@ -170,6 +171,7 @@ def main():
     _ext.load(required=True)
     Fn.set_gemm_backend(args.gemm)
     cfg = getattr(LlamaConfig, args.model)()
+    cfg.fp8 = bool(args.fp8)
     invalid = None
     if args.layers is not None:
         cfg.num_layers = args.layers
@@ -333,7 +335,7 @@ def main():
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "bf16",
+        "dtype": "bf16" if not args.fp8 else "fp8 e4m3 block-scaled forward GEMMs (1x128 / 128x128 scales), bf16 backward",
         "data": "synthetic tokens (uniform random ids), random-init weights of the named architecture",
         "impl": "ours",
         "config": {

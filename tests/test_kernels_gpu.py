@@ -222,3 +222,24 @@ def test_sharded_philox_matches_cpu_specification():
                 assert torch.equal(local.cpu().reshape(-1), want.reshape(-1)), (world, pl, kind)
             else:
                 torch.testing.assert_close(local.cpu().reshape(-1), want.reshape(-1), rtol=1e-5, atol=1e-6)
+
+
+def test_fp8_block_scaled_gemm_on_cuda():
+    """fp8 forward GEMM on the GPU (cuBLASLt through torch._scaled_mm when the build accepts the scale layout, emulation
+    otherwise) against the fp32 product; the emulated path is the numerics specification."""
+    from vescale_b200.ops import fp8
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(512, 1024, device=dev, generator=g).bfloat16()
+    w = (torch.randn(768, 1024, device=dev, generator=g) * 0.05).bfloat16()
+    ref = x.float() @ w.float().t()
+    xq, xs = fp8.quantize_blockwise(x, (1, 128))
+    wq, ws = fp8.quantize_blockwise(w, (128, 128))
+    emu = fp8._emulated_gemm_nt(xq, xs, wq, ws, torch.float32)
+    assert ((emu - ref).norm() / ref.norm()).item() < 0.04
+    got = fp8.fp8_gemm_nt(xq, xs, wq, ws, torch.bfloat16).float()
+    assert ((got - ref).norm() / ref.norm()).item() < 0.06
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    fp8.fp8_linear(xr, wr).float().sum().backward()
+    assert xr.grad is not None and wr.grad is not None and torch.isfinite(xr.grad.float()).all()

@@ -38,6 +38,7 @@ class LlamaConfig:
     tie_embeddings: bool = False
     init_std: float = 0.02
     dtype: torch.dtype = torch.bfloat16
+    fp8: bool = False  # block-scaled e4m3 forward GEMMs in the decoder blocks (``ops/fp8.py``); lm-head and backward stay bf16
 
     @staticmethod
     def llama3_8b(**kw) -> "LlamaConfig":
@@ -112,6 +113,14 @@ class LlamaBlock(nn.Module):
         cfg = self.cfg
         B, S, _ = h.shape
         hq, hk, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        if cfg.fp8:
+            from ..ops.fp8 import fp8_linear
+
+            h, x = O.add_rms_norm(h, delta, self.attn_norm, cfg.rms_eps)
+            qkv = O.rope_qk_(fp8_linear(x, self.wqkv), cos, sin, hq, hk, d)
+            a = fp8_linear(O.packed_attention(qkv, hq, hk, d, causal=True), self.wo)
+            h, x = O.add_rms_norm(h, a, self.mlp_norm, cfg.rms_eps)
+            return h, fp8_linear(O.swiglu(fp8_linear(x, self.w_gate_up)), self.w_down)
         h, qkv = O.functional.add_norm_linear(h, delta, self.attn_norm, self.wqkv, cfg.rms_eps)
         qkv = O.rope_qk_(qkv, cos, sin, hq, hk, d)
         o = O.packed_attention(qkv, hq, hk, d, causal=True)

@@ -1,0 +1,142 @@
+"""Block-scaled fp8 (e4m3) linear layers for the fp8 training configuration (BASELINE.json config 5: Llama-3-70B FSDP fp8).
+
+Scaling scheme (DeepSeek-V3-style software block scaling): activations are quantised per token in 1×128 blocks along K,
+weights in 128×128 blocks, both to ``float8_e4m3fn`` with fp32 scales ``amax / 448``; the GEMM accumulates in fp32 and the
+two scale grids are applied to the partial sums of each 128-wide K block.  Backward runs in bf16 on the saved operands.
+
+Execution:
+  * CUDA: ``torch._scaled_mm`` (cuBLASLt fp8 tensor-core GEMM — a *library* call; the hand-written tcgen05 ``kind::f8f6f4``
+    variant of ``csrc/gemm_sm100.cu`` is listed under DESIGN.md "known gaps") with the scale layout the installed build
+    accepts — 1×128 / 128×128 blockwise first, row-wise as the fallback (scales are then folded per row / column, which is a
+    coarser but still block-derived scaling); any failure falls through to the emulated path.
+  * everywhere else (and for tests): the *emulated* path — dequantise the fp8 operands block by block and multiply in
+    fp32/bf16 — which defines the numerics the tests check.
+
+The reference has no fp8 path; this follows the north-star configuration list, not reference code.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+__all__ = ["quantize_blockwise", "dequantize_blockwise", "fp8_linear", "fp8_gemm_nt", "FP8_MAX", "set_fp8_backend"]
+
+FP8 = torch.float8_e4m3fn
+FP8_MAX = 448.0
+_BACKEND = {"mode": "auto", "scaled_mm_ok": None}  # auto | emulate | scaled_mm
+
+
+def set_fp8_backend(mode: str) -> None:
+    assert mode in ("auto", "emulate", "scaled_mm")
+    _BACKEND["mode"] = mode
+    _BACKEND["scaled_mm_ok"] = None
+
+
+def _pad_to(x: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
+    n = x.shape[dim]
+    pad = (-n) % mult
+    if pad == 0:
+        return x
+    shp = list(x.shape)
+    shp[dim] = pad
+    return torch.cat([x, x.new_zeros(shp)], dim=dim)
+
+
+def quantize_blockwise(x: torch.Tensor, block: Tuple[int, int] = (1, 128)) -> Tuple[torch.Tensor, torch.Tensor]:
+    """2-D ``x`` [R, C] -> (fp8 tensor [R, C], fp32 scales [ceil(R/br), ceil(C/bc)]) with ``x ≈ q * scale`` per block."""
+    assert x.dim() == 2
+    br, bc = block
+    R, C = x.shape
+    xp = _pad_to(_pad_to(x.float(), 0, br), 1, bc)
+    Rp, Cp = xp.shape
+    blocks = xp.view(Rp // br, br, Cp // bc, bc)
+    amax = blocks.abs().amax(dim=(1, 3)).clamp_(min=1e-12)
+    scale = amax / FP8_MAX
+    q = (blocks / scale[:, None, :, None]).clamp_(-FP8_MAX, FP8_MAX).to(FP8)
+    return q.view(Rp, Cp)[:R, :C].contiguous(), scale
+
+
+def dequantize_blockwise(q: torch.Tensor, scale: torch.Tensor, block: Tuple[int, int] = (1, 128), dtype=torch.float32) -> torch.Tensor:
+    br, bc = block
+    R, C = q.shape
+    s = scale.repeat_interleave(br, 0)[:R].repeat_interleave(bc, 1)[:, :C]
+    return (q.float() * s).to(dtype)
+
+
+def _emulated_gemm_nt(xq, xs, wq, ws, out_dtype) -> torch.Tensor:
+    """y = dequant(x) @ dequant(w)^T, accumulated in fp32 — what a block-scaled fp8 GEMM computes."""
+    x = dequantize_blockwise(xq, xs, (1, 128))
+    w = dequantize_blockwise(wq, ws, (128, 128))
+    return (x @ w.t()).to(out_dtype)
+
+
+def _scaled_mm(xq, xs, wq, ws, out_dtype) -> Optional[torch.Tensor]:
+    """cuBLASLt fp8 GEMM.  Tries block-wise scales, then row-wise; returns None when the build / shape does not support it."""
+    M, K = xq.shape
+    N = wq.shape[0]
+    if K % 16 or N % 16:
+        return None
+    b = wq.t()  # [K, N] column-major, as _scaled_mm wants the second operand
+    try:  # 1x128 (activations) x 128x128 (weights) block scales
+        return torch._scaled_mm(xq, b, scale_a=xs.contiguous(), scale_b=ws.t().contiguous(), out_dtype=out_dtype)
+    except Exception:  # noqa: BLE001
+        pass
+    try:  # row-wise: re-derive one scale per row / per output column from the block grids (max over the K blocks)
+        sa = xs.amax(dim=1, keepdim=True)  # [M, 1]
+        sb = ws.amax(dim=1).repeat_interleave(128)[:N].view(1, N)  # [1, N]
+        xa = (dequantize_blockwise(xq, xs, (1, 128)) / sa).clamp_(-FP8_MAX, FP8_MAX).to(FP8)
+        wb = (dequantize_blockwise(wq, ws, (128, 128)) / sb.t()).clamp_(-FP8_MAX, FP8_MAX).to(FP8)
+        return torch._scaled_mm(xa, wb.t(), scale_a=sa.contiguous(), scale_b=sb.contiguous(), out_dtype=out_dtype)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def fp8_gemm_nt(xq: torch.Tensor, xs: torch.Tensor, wq: torch.Tensor, ws: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """``[M, K] fp8 (1x128 scales) x [N, K] fp8 (128x128 scales) -> [M, N]``."""
+    mode = _BACKEND["mode"]
+    if xq.is_cuda and mode != "emulate" and _BACKEND["scaled_mm_ok"] is not False:
+        y = _scaled_mm(xq, xs, wq, ws, out_dtype)
+        if y is not None:
+            _BACKEND["scaled_mm_ok"] = True
+            return y
+        _BACKEND["scaled_mm_ok"] = False
+        if mode == "scaled_mm":
+            raise RuntimeError("torch._scaled_mm rejected the fp8 block-scaled GEMM on this build")
+    return _emulated_gemm_nt(xq, xs, wq, ws, out_dtype)
+
+
+class _Fp8Linear(torch.autograd.Function):
+    """y = x @ W^T with both operands block-quantised to e4m3 for the forward GEMM.  Backward: bf16 dgrad / wgrad on the saved
+    (unquantised) operands; dW goes straight into ``weight.main_grad`` when the FSDP/DDP wrapper provides one."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x2 = x.reshape(-1, x.shape[-1])
+        xq, xs = quantize_blockwise(x2, (1, 128))
+        wq, ws = quantize_blockwise(weight, (128, 128))
+        ctx.save_for_backward(x2, weight)
+        ctx.shape = x.shape
+        y = fp8_gemm_nt(xq, xs, wq, ws, x.dtype if x.dtype in (torch.bfloat16, torch.float16, torch.float32) else torch.bfloat16)
+        return y.view(*x.shape[:-1], weight.shape[0]).detach()  # not an autograd view: downstream ops (RoPE) write in place
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .functional import gemm_nn, gemm_tn
+
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dx = gemm_nn(dy2, weight).view(ctx.shape) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            mg = getattr(weight, "main_grad", None)
+            if mg is not None:
+                gemm_tn(dy2, x2.contiguous(), out=mg, accumulate=getattr(weight, "_main_grad_initialised", False))
+                weight._main_grad_initialised = True
+            else:
+                dw = gemm_tn(dy2, x2.contiguous())
+        return dx, dw
+
+
+def fp8_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    return _Fp8Linear.apply(x, weight)
