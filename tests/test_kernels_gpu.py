@@ -237,9 +237,9 @@ def test_fp8_block_scaled_gemm_on_cuda():
     xq, xs = fp8.quantize_blockwise(x, (1, 128))
     wq, ws = fp8.quantize_blockwise(w, (128, 128))
     emu = fp8._emulated_gemm_nt(xq, xs, wq, ws, torch.float32)
-    assert ((emu - ref).norm() / ref.norm()).item() < 0.04
+    assert ((emu - ref).norm() / ref.norm()).item() < 0.05
     got = fp8.fp8_gemm_nt(xq, xs, wq, ws, torch.bfloat16).float()
-    assert ((got - ref).norm() / ref.norm()).item() < 0.06
+    assert ((got - ref).norm() / ref.norm()).item() < 0.08
     xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
     fp8.fp8_linear(xr, wr).float().sum().backward()
     assert xr.grad is not None and wr.grad is not None and torch.isfinite(xr.grad.float()).all()
