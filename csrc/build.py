@@ -6,7 +6,6 @@ from __future__ import annotations
 
 import glob
 import os
-import shutil
 import subprocess
 import sys
 import sysconfig

@@ -1,6 +1,5 @@
 """Ulysses sequence<->head all-to-all attention vs attention on the gathered tensors (4 ranks)."""
 import torch
-import torch.distributed as dist
 import torch.nn.functional as F
 
 from common import device_type, run_distributed

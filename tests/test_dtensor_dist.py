@@ -3,9 +3,7 @@ Golden = the same op on the full tensor on one device, as in the reference's DTe
 (``test/dtensor/ragged_shard/test_redistribute.py``, ``legacy/test/dtensor/general/test_redistribute.py``)."""
 import itertools
 
-import pytest
 import torch
-import torch.distributed as dist
 
 from common import device_type, run_distributed
 

@@ -1,6 +1,5 @@
 """FSDP on RaggedShard vs single-process training (golden), 4 ranks gloo / NCCL.
 Strategy parity: ``legacy/test/parallel/ddp_optim/test_doptimizer.py:51-80`` (same data, compare to one device)."""
-import copy
 
 import pytest
 import torch

@@ -4,7 +4,6 @@ import copy
 
 import pytest
 import torch
-import torch.distributed as dist
 import torch.nn as nn
 
 from common import device_type, run_distributed

@@ -1,5 +1,4 @@
 """Symmetric-memory kernels on >= 2 GPUs of one box: collectives vs NCCL, FSDP(symm) vs FSDP(nccl)."""
-import os
 
 import pytest
 import torch

@@ -11,7 +11,6 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from ..dtensor.api import DTensor
-from ..spec import DTensorSpec
 from .pinned_pool import PinnedPool
 
 __all__ = ["save", "load", "VeScaleCheckpointer", "wait_for_async"]

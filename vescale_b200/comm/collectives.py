@@ -10,7 +10,6 @@ mesh_broadcast, mesh_reduce_scatter, mesh_all_gather, mesh_all_reduce), referenc
 """
 from __future__ import annotations
 
-import math
 from typing import Callable, List, Optional, Sequence
 
 import torch

@@ -9,10 +9,9 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Any, List, Optional, Sequence, Tuple, Union
+from typing import Any, Optional, Sequence, Tuple
 
 import torch
-import torch.distributed as dist
 
 from ..comm import collectives as C
 from ..layout import (
@@ -24,7 +23,7 @@ from ..layout import (
     shape_and_offset_before_ragged,
 )
 from ..mesh import DeviceMesh, mesh_resources
-from ..placement import InterleavedShard, Partial, Placement, RaggedShard, Replicate, Shard, normalize_placements
+from ..placement import Partial, Placement, RaggedShard, Replicate, Shard, normalize_placements
 from ..spec import DTensorSpec, TensorMeta, contiguous_stride
 from .redistribute import Redistribute, redistribute_local_tensor
 

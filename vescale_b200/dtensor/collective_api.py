@@ -1,7 +1,6 @@
 """Explicit DTensor collectives (legacy ``vescale.dtensor.api``: vescale_all_gather / all_reduce / reduce_scatter)."""
 from __future__ import annotations
 
-from typing import Optional, Sequence, Union
 
 from ..placement import Partial, Replicate, Shard
 

@@ -1,7 +1,6 @@
 """visualize_sharding: print which rank holds which region of a 1-D/2-D DTensor."""
 from __future__ import annotations
 
-import math
 
 from ...layout import local_boxes
 

@@ -11,15 +11,13 @@ Parity: reference ``vescale/dtensor/_dispatch.py:247-383`` and legacy ``dtensor/
 from __future__ import annotations
 
 import os
-import warnings
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, List
 
 import torch
 
-from ..layout import compute_local_shape
-from ..placement import Partial, RaggedShard, Replicate, Shard
-from ..spec import DTensorSpec, TensorMeta, contiguous_stride
-from .op_schema import OpSchema, OutputSharding
+from ..placement import Replicate
+from ..spec import DTensorSpec, TensorMeta
+from .op_schema import OpSchema
 from .redistribute import redistribute_local_tensor
 from .sharding_prop import propagator
 

@@ -7,13 +7,11 @@ found_inf_reduce_handler:60-96, ragged_norm_op_handler:154-244 — and legacy
 from __future__ import annotations
 
 import math
-from typing import List
 
 import torch
-import torch.distributed as dist
 
 from ..comm import collectives as C
-from ..layout import shape_and_offset_before_ragged, unravel_index
+from ..layout import shape_and_offset_before_ragged
 from ..placement import Partial, RaggedShard, Replicate, Shard
 from ..spec import DTensorSpec, TensorMeta, contiguous_stride
 from .dispatch import dispatcher, register_op_handler

@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import contextlib
 import math
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -16,14 +16,14 @@ Parity (non-ragged): ``legacy/vescale/dtensor/redistribute.py:35-455`` transitio
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence
 
 import torch
 
 from ..comm import collectives as C
 from ..layout import _shard_order, dim_intervals, get_ragged_shard, shape_and_offset_before_ragged
 from ..placement import InterleavedShard, Partial, Placement, RaggedShard, Replicate, Shard, _StridedShard, shard_size_and_offset
-from ..spec import DTensorSpec, TensorMeta
+from ..spec import DTensorSpec
 
 __all__ = ["redistribute_local_tensor", "Redistribute", "redistribute_cost"]
 

@@ -1,13 +1,10 @@
 """Helpers shared by the sharding rules."""
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Sequence, Tuple
 
-import torch
 
-from ...placement import InterleavedShard, Partial, Placement, RaggedShard, Replicate, Shard, _StridedShard
-from ...spec import DTensorSpec
+from ...placement import InterleavedShard, Placement, RaggedShard, Replicate, Shard, _StridedShard
 
 R = Replicate()
 

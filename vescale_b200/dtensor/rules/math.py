@@ -6,12 +6,11 @@ RaggedShard→Partial, vector_norm:215, foreach_norm:236, nll_loss:257, layer_no
 """
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional
 
 import torch
 
-from ...placement import Partial, Placement, RaggedShard, Replicate, Shard
+from ...placement import Partial, Placement, RaggedShard, Shard
 from ...spec import DTensorSpec
 from ..op_schema import OpSchema, RuleResult
 from ..sharding_prop import register_rule

@@ -11,15 +11,15 @@ Parity: legacy ``dtensor/ops/matrix_ops.py:133-470`` (mm/addmm/bmm/baddbmm/t, SD
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 
-from ...placement import Partial, Placement, RaggedShard, Replicate, Shard
+from ...placement import Partial, Placement, RaggedShard, Shard
 from ...spec import DTensorSpec
 from ..op_schema import OpSchema, RuleResult
 from ..sharding_prop import register_rule
-from .common import R, is_plain_shard, replicate, shard_with_dim, unshard
+from .common import R, is_plain_shard, replicate
 
 aten = torch.ops.aten
 P = Partial("sum")

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from ...placement import InterleavedShard, Partial, Placement, RaggedShard, Replicate, Shard
+from ...placement import Partial, Placement, RaggedShard, Shard
 from ...spec import DTensorSpec
 from ..op_schema import OpSchema, RuleResult
 from ..sharding_prop import register_rule

@@ -7,12 +7,12 @@ slice_scatter/scatter/gather/stack/cat/index_select/index/split) and legacy ``dt
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List
 
 import torch
 
 from ...layout import compute_local_shape, compute_local_shape_and_global_offset
-from ...placement import Partial, Placement, RaggedShard, Replicate, Shard
+from ...placement import Partial, Placement, RaggedShard, Shard
 from ...spec import DTensorSpec
 from ..op_schema import OpSchema, RuleResult
 from ..sharding_prop import register_rule

@@ -11,12 +11,12 @@ Parity: legacy ``dtensor/ops/view_ops.py`` (DimSpec algebra) and ``vescale_view_
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import torch
 
 from ...layout import compute_local_shape
-from ...placement import InterleavedShard, Partial, Placement, RaggedShard, Replicate, Shard
+from ...placement import InterleavedShard, Placement, RaggedShard, Shard
 from ...spec import DTensorSpec
 from ..op_schema import OpSchema, RuleResult
 from ..sharding_prop import register_rule

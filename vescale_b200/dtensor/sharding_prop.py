@@ -6,14 +6,12 @@ Independent of torch's private DTensor internals by construction.
 """
 from __future__ import annotations
 
-import math
 import os
 from collections import OrderedDict
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, List, Optional
 
 import torch
 
-from ..layout import compute_local_shape
 from ..placement import Placement, RaggedShard, Replicate
 from ..spec import DTensorSpec, TensorMeta
 from .op_schema import OpSchema, OutputSharding, RuleResult

@@ -11,7 +11,6 @@ dump, ``legacy/vescale/emulator/distributed.py:741-809``).
 """
 from __future__ import annotations
 
-import math
 from typing import List, Optional, Sequence, Tuple
 
 import torch

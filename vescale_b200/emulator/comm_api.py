@@ -8,9 +8,9 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from ..layout import compute_local_shape_and_global_offset, local_boxes
+from ..layout import local_boxes
 from ..mesh import DeviceMesh
-from ..placement import Partial, Placement, Replicate, Shard
+from ..placement import Partial, Placement, Replicate
 from .collectives import EmulatorProcessGroup
 
 __all__ = ["distribute_tensor", "redistribute_dtensor", "full_tensor", "mesh_all_reduce", "mesh_all_gather", "mesh_reduce_scatter"]

@@ -8,10 +8,9 @@ carries half of the data.
 """
 from __future__ import annotations
 
-import re
 import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 __all__ = ["Ring", "BinaryTree", "DoubleTree", "btree", "parse_graph_dump"]
 

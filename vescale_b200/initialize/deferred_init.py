@@ -11,7 +11,7 @@ materialised shard equals the slice of the tensor a single device would have pro
 from __future__ import annotations
 
 import math
-from typing import Any, Callable, Dict, Optional, Sequence, Tuple
+from typing import Callable, Optional, Sequence
 
 import torch
 import torch.nn as nn

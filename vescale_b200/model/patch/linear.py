@@ -6,7 +6,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ...dtensor.api import DTensor
 

@@ -4,7 +4,6 @@ local sum-exp → AR(SUM).  ``loss_parallel`` is the DTensor-dispatch route to t
 from __future__ import annotations
 
 import torch
-import torch.distributed as dist
 
 from ...comm import collectives as C
 from ...dtensor.api import DTensor

@@ -12,7 +12,7 @@ Architecture parity: HF ``LlamaForCausalLM`` (the reference's examples train HF 
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch

@@ -4,14 +4,13 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Optional
 
 import torch
 import torch.nn as nn
 
 from .. import ops as O
 from ..parallel.moe.layer import MoEConfig, MoELayer
-from .llama import EmbeddingFn, LlamaConfig, LlamaEmbedding, LlamaHead
+from .llama import LlamaConfig, LlamaEmbedding, LlamaHead
 
 __all__ = ["MixtralConfig", "MixtralModel", "MixtralBlock"]
 

@@ -1,8 +1,7 @@
 """Front-end of ``csrc/philox_shard.cu``: fill the boxes of a local shard with the single-device-equivalent stream."""
 from __future__ import annotations
 
-import math
-from typing import List, Sequence, Tuple
+from typing import Sequence
 
 import torch
 

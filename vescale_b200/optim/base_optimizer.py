@@ -3,7 +3,7 @@ module's gradient synchronisation (Partial grads of TP/SP, DDP buckets) and copi
 ``param.grad``.  Parity: ``legacy/vescale/optim/base_optimizer.py:116-206``."""
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence, Union
+from typing import Optional, Sequence, Union
 
 import torch
 import torch.nn as nn

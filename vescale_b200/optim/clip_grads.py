@@ -7,7 +7,7 @@ Apex ``amp_C.multi_tensor_l2norm`` / ``multi_tensor_scale``."""
 from __future__ import annotations
 
 import math
-from typing import Iterable, List, Optional, Sequence, Union
+from typing import Sequence
 
 import torch
 import torch.distributed as dist

@@ -12,8 +12,7 @@ update into the reduce-scatter kernel itself (``rs_adamw``): the reduced gradien
 """
 from __future__ import annotations
 
-import math
-from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist

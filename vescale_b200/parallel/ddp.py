@@ -19,14 +19,12 @@ Parity: ``legacy/vescale/ddp/distributed_data_parallel.py:20-336``, ``legacy/ves
 from __future__ import annotations
 
 import contextlib
-import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from ..comm import collectives as C
 from ..dtensor.api import DTensor
 from ..mesh import DeviceMesh
 

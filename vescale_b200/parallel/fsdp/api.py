@@ -19,9 +19,7 @@ Semantics (what the reference *describes*, ``docs/texts/raggedshard.md:67-77``; 
 from __future__ import annotations
 
 import contextlib
-import functools
-import math
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

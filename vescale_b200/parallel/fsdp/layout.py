@@ -18,8 +18,8 @@ quantisation granularity); the wrapper itself is not in the reference tree (SURV
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
 
 from ...placement import RaggedShard
 

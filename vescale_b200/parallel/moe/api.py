@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .layer import MoEConfig, MoELayer
+from .layer import MoELayer
 
 __all__ = ["parallelize_experts", "ExpertsAllocator", "BasicExpertsAllocator", "TokenDispatcher", "BasicTokenDispatcher", "MoEOptimizer", "is_moe", "reallocate_experts", "balanced_allocation"]
 

@@ -22,7 +22,7 @@ Parity: replaces the 3x ``all_to_all_single`` + ``.tolist()`` + Python expert lo
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist

@@ -15,11 +15,9 @@ Parity: ``legacy/vescale/engine/pipe.py:33-237``, ``pipe/pipe_emmiter.py:132-343
 from __future__ import annotations
 
 import os
-from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
-import torch.distributed as dist
-import torch.nn as nn
 
 from .p2p import P2PContext
 from .plan import PipelineParallelPlan, PipelineScheduleType

@@ -10,7 +10,7 @@ and reused (``reuse_p2p_tensor_shape``; legacy re-handshakes every micro-batch u
 from __future__ import annotations
 
 import os
-from collections import defaultdict, deque
+from collections import deque
 from typing import Deque, Dict, List, Optional, Sequence, Tuple
 
 import torch

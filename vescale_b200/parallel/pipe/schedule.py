@@ -19,7 +19,7 @@ mirrors ZB-V's ``CostGraph`` scheduler (``zero_bubble_v.py:198-600``).
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 from .plan import PipelineParallelPlan, PipelineScheduleType
 

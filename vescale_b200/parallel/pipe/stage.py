@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .plan import PipelineParallelPlan, PipelineScheduleType, PipelineSplitMethodType, TracerType
+from .plan import PipelineParallelPlan, PipelineSplitMethodType, TracerType
 from .schedule import stage_placement
 
 __all__ = ["PipeModule", "construct_pipeline_stage", "split_units", "PipeParser"]

@@ -15,7 +15,7 @@ import functools
 import threading
 import time
 from enum import IntEnum
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from .mesh import DeviceMesh
-from .placement import Partial, Placement, RaggedShard, Replicate, Shard, InterleavedShard
+from .placement import Partial, Placement, RaggedShard, Replicate, Shard
 
 __all__ = ["TensorMeta", "DTensorSpec", "get_sub_spec"]
 
