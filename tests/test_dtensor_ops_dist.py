@@ -141,6 +141,25 @@ def _op_table():
         add(f"gather/{tag}", lambda a, i: a.gather(1, i), x, idx)
         add(f"inplace/{tag}", lambda a, b: a.clone().add_(b).mul_(2).sub_(1).div_(2), x, y)
         add(f"copy_fill/{tag}", lambda a, b: (a.clone().copy_(b), a.clone().fill_(1.5), a.clone().zero_()), x, y)
+    # ---- data-dependent output shapes (run replicated, spec from the result), in-place ops that need a reshard, misc
+    x, y = _t((8, 12), 1), _t((8, 12), 2)
+    idx = _t((8, 4), 7, torch.int64)
+    add("topk_sort", lambda a: tuple(a.topk(3, dim=1)) + tuple(a.sort(dim=0)) + (a.argsort(dim=1),), x)
+    add("unique", lambda a: (a > 0).to(torch.int64).sum(1).unique(), x)
+    add("nonzero", lambda a: (a > 0.5).nonzero(), x)
+    add("masked_select", lambda a, b: a.masked_select(b > 0), x, y)
+    add("scatter_add", lambda a, i: torch.zeros_like(a).scatter_add(1, i, a[:, :4]), x, idx)
+    add("scatter_inplace", lambda a, i: a.clone().scatter_(1, i, 1.0), x, idx)
+    add("index_put_inplace", lambda a, i: a.clone().index_put_((i[:, 0],), a * 0 + 1.0, accumulate=True), x, idx)
+    add("adv_index", lambda a, i: a[i[:, 0]], x, idx)
+    add("pad_roll_repeat", lambda a: (F.pad(a, (1, 2, 3, 0)), a.roll(2, 0) + a.roll(-1, 1), a.repeat(2, 3), a.repeat_interleave(2, dim=0)), x)
+    add("one_hot", lambda i: F.one_hot(i, 6), idx)
+    add("conv1d", lambda a, w: F.conv1d(a.unsqueeze(0), w[:4, :8].reshape(4, 8, 1).contiguous()), x, y)
+    add("cdist_outer_dot", lambda a, b: (torch.cdist(a, b), torch.outer(a[:, 0], b[:, 1]), torch.dot(a[:, 0], b[:, 0])), x, y)
+    add("var_mean_median", lambda a: tuple(torch.var_mean(a, dim=1)) + (a.median(1)[0], a.kthvalue(2, 0)[0], a.cummax(1)[0], a.cumprod(0)), x)
+    add("group_norm", lambda a: F.group_norm(a.view(8, 4, 3), 2), x)
+    add("activations", lambda a: F.gelu(a, approximate="tanh") + F.leaky_relu(a) + F.elu(a) + F.softplus(a) + F.hardtanh(a), x)
+    add("losses", lambda a, b: F.l1_loss(a, b) + F.smooth_l1_loss(a, b) + F.binary_cross_entropy_with_logits(a, (b > 0).float()), x, y)
     # ---- view / reshape (shape arguments must be localised)
     v = _t((8, 12), 4)
     add("view_split", lambda a: a.view(2, 4, 12), v)

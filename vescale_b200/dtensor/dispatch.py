@@ -18,6 +18,7 @@ import torch
 from ..placement import Replicate
 from ..spec import DTensorSpec, TensorMeta
 from .op_schema import OpSchema
+from .sharding_prop import DynamicReplicate
 from .redistribute import redistribute_local_tensor
 from .sharding_prop import propagator
 
@@ -178,9 +179,15 @@ class OpDispatcher:
                 if isinstance(self_arg, DTensor):
                     spec = out_spec[0] if isinstance(out_spec, tuple) and out_spec else out_spec
                     if isinstance(spec, DTensorSpec) and spec.placements != self_arg._spec.placements:
-                        raise RuntimeError(
-                            f"{op}: in-place result would change placements {self_arg._spec.placements} -> {spec.placements}"
-                        )
+                        # the op needed ``self`` in another layout (e.g. scatter_ along the sharded dim): it ran on a resharded
+                        # copy; bring the result back to self's own placements and write it into self's storage
+                        res = local_out[0] if isinstance(local_out, (list, tuple)) else local_out
+                        if not isinstance(res, torch.Tensor) or any(p.is_partial() for p in self_arg._spec.placements):
+                            raise RuntimeError(f"{op}: in-place result would change placements {self_arg._spec.placements} -> {spec.placements}")
+                        if _disable_redistribute():
+                            raise RuntimeError(f"{op}: in-place update needs a reshard {spec.placements} -> {self_arg._spec.placements} but VESCALE_DISABLE_REDISTRIBUTE=1")
+                        back = redistribute_local_tensor(res, spec, self_arg._spec)
+                        self_arg._local_tensor.copy_(back)
                     return self_arg
                 if isinstance(self_arg, (list, tuple)):  # foreach in-place ops return None
                     return None
@@ -189,6 +196,19 @@ class OpDispatcher:
     def _wrap_out(self, local_out, out_spec):
         from .api import DTensor
 
+        if isinstance(out_spec, DynamicReplicate):  # data-dependent output shape: the spec comes from the result itself
+            mesh = out_spec.mesh
+            rep = tuple(Replicate() for _ in range(mesh.ndim))
+
+            def mk(t):
+                if not isinstance(t, torch.Tensor):
+                    return t
+                return DTensor(t, DTensorSpec(mesh, rep, TensorMeta(tuple(t.shape), tuple(t.stride()), t.dtype)), requires_grad=False)
+
+            if isinstance(local_out, (list, tuple)):
+                res = [mk(t) for t in local_out]
+                return tuple(res) if isinstance(local_out, tuple) else res
+            return mk(local_out)
         if isinstance(local_out, torch.Tensor):
             spec = out_spec[0] if isinstance(out_spec, tuple) else out_spec
             if spec is None:

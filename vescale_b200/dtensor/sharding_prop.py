@@ -19,6 +19,16 @@ from .op_schema import OpSchema, OutputSharding, RuleResult
 __all__ = ["ShardingPropagator", "register_rule", "get_rule", "propagator"]
 
 _RULES: Dict[Any, Callable[[OpSchema], RuleResult]] = {}
+
+
+class DynamicReplicate:
+    """Output spec of ops whose output *shape* depends on the data (``unique``, ``nonzero``, ``masked_select`` ...): no meta
+    kernel exists, so the op runs on replicated inputs and the spec is built from the actual local result (identical on every
+    rank because the inputs are).  Legacy handles ``nonzero`` / ``_unique2`` with bypass handlers (``_dispatch_bypass.py``)."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+
 IN_META_PROPAGATION = [0]  # re-entrancy guard consulted by DModule's factory mode
 
 
@@ -141,6 +151,11 @@ class ShardingPropagator:
             if isinstance(metas, tuple):  # op returns a list of tensors all sharing one placement
                 out_spec = tuple(mk(out, m) for m in metas)
             else:
+                if metas is None and all(isinstance(p, Replicate) for p in out) and res.ins is not None and all(
+                    w is not None and all(isinstance(p, Replicate) for p in w) for w in res.ins
+                ):
+                    redis_dyn = [None if tuple(w) == h.placements else h.with_placements(tuple(w)) for w, h in zip(res.ins, in_specs)]
+                    return OutputSharding(DynamicReplicate(mesh), redis_dyn if any(r is not None for r in redis_dyn) else None, res.local_args, res.local_kwargs, res.post, res.pre)
                 if metas is None:
                     raise RuntimeError(
                         f"cannot infer output metadata of {schema.op} on the meta device ({getattr(self, 'last_meta_error', '?')}); "
