@@ -288,6 +288,14 @@ VB_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t 
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same, multicast: the box lands at this smem offset in every CTA of `mask` (cluster ranks) and each destination pair's
+// leader barrier (the address's peer bit is kept as given: pass the barrier of an even-ranked CTA) is credited.
+VB_DEVICE void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int32_t c0, int32_t c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 VB_DEVICE void tmem_alloc_2cta(uint32_t* smem_holder, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
 }

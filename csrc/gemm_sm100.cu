@@ -439,6 +439,183 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 }
 
+// =================================================================================================
+// Variant 3 (experimental, opt-in: VESCALE_B200_GEMM_VARIANT=3 or variant=3): 2x2 cluster.  Two CTA pairs share one
+// cluster and compute vertically adjacent 256x256 tiles of the same n-block, so the B tile is identical for both pairs:
+// each of the 4 CTAs loads one quarter of it (64 rows x 64 k) and TMA-multicasts it to the CTA of the same parity in the
+// other pair.  L2->SM traffic per 512x256x64 step: 64 KB of A + 32 KB of B instead of 128 KB (-25 %), which is what limits
+// *sustained* throughput under the power cap (profiles/gemm_2cta_ncu_r1.md).  Not yet validated on hardware: the default
+// path and the autotune never select it.
+//   ranks: pair p = rank >> 1 (m-block 2*super_m + p), c = rank & 1 (upper / lower 128 rows of the pair tile, B half c)
+//   slot reuse: a CTA's B slot is written by both pairs' producers, so `empty` needs the MMA commits of *both* pairs (count 2,
+//   commit multicast to all four CTAs)
+// =================================================================================================
+template <int STAGES>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_nt_4cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_bq, const __grid_constant__ CUtensorMap tma_c,
+                    int M, int N, int K, int group_m) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * kABytes;
+  uint8_t* smem_epi = smem + STAGES * kStage2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pr = rank >> 1, c = rank & 1;  // pair in cluster, CTA in pair
+  const uint32_t lead = rank & ~1u;             // cluster rank of my pair's leader
+  const bool leader = c == 0;
+  constexpr int BM2 = 2 * kBM;
+  const int num_m = (M + BM2 - 1) / BM2, num_n = (N + kBN - 1) / kBN;
+  const int num_sm = (num_m + 1) / 2;  // super tiles along M (512 rows)
+  const int num_tiles = num_sm * num_n;
+  const int num_kb = K / kBK;
+  const int cl = blockIdx.x >> 2, num_cl = gridDim.x >> 2;
+
+  auto tile_coord = [&](int t, int& sm_blk, int& n_blk) {
+    const int per_group = group_m * num_n;
+    const int g = t / per_group;
+    const int first = g * group_m;
+    const int gsize = min(group_m, num_sm - first);
+    const int r = t - g * per_group;
+    sm_blk = first + r % gsize;
+    n_blk = r / gsize;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_bq);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);  // both pairs must have consumed the slot before anyone overwrites it
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kEpilogueThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_holder, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint16_t bmask = (uint16_t)((1u << c) | (1u << (c + 2)));  // same-parity CTA of both pairs
+      for (int tile = cl; tile < num_tiles; tile += num_cl) {
+        int sm_blk, n_blk;
+        tile_coord(tile, sm_blk, n_blk);
+        const int m0 = (sm_blk * 2 + (int)pr) * BM2 + (int)c * kBM;           // rows past M are zero-filled by TMA
+        const int nq = n_blk * kBN + (int)c * (kBN / 2) + (int)pr * (kBN / 4);  // my quarter of the shared B tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t full_lead = mapa(smem_u32(&full_bar[s]), lead);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * kStage2);
+          tma_load_2d_2sm(smem_a + s * kABytes, &tma_a, full_lead, kb * kBK, m0);
+          tma_load_2d_2sm_mc(smem_b + s * kB2Bytes + pr * (kB2Bytes / 2), &tma_bq, full_lead, kb * kBK, nq, bmask);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_major(BM2, kBN, false, false);
+      const uint16_t pair_mask = (uint16_t)(0b11u << lead);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = cl; tile < num_tiles; tile += num_cl) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(smem_u32(smem_a + s * kABytes));
+          const uint64_t b_desc = make_sw128_desc(smem_u32(smem_b + s * kB2Bytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2cta_mc(&empty_bar[s], 0b1111);  // every CTA of the cluster learns that this pair is done with slot s
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit_2cta_mc(&tfull_bar[as], pair_mask);
+        if (++as == 2) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = cl; tile < num_tiles; tile += num_cl) {
+      int sm_blk, n_blk;
+      tile_coord(tile, sm_blk, n_blk);
+      const int m0 = (sm_blk * 2 + (int)pr) * BM2 + (int)c * kBM, n0 = n_blk * kBN;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < kBN / 64; ++cc) {
+        float v[64];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + cc * 64, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * kBN + cc * 64 + 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
+        }
+        uint8_t* buf = smem_epi + (ew * 2 + (cc & 1)) * 4096;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        epi_write_row_swizzled(buf, lane, v);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && n0 + cc * 64 < N && m0 + ew * 32 < M) {
+          tma_store_2d(&tma_c, buf, n0 + cc * 64, m0 + ew * 32);  // rows / columns past the edge are clipped by the tensor map
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa(smem_u32(&tempty_bar[as]), lead));
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  }
+  if (warp >= 4 && lane == 0) tma_store_wait<0>();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
 struct MapKey {
   const void* p;
   int64_t r, c, pitch;
@@ -503,7 +680,41 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
   }();
   const int variant = variant_arg > 0 ? (int)variant_arg : env_variant;
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  if (variant == 2) {
+  if (variant == 3 && !accumulate) {
+    constexpr int STAGES3 = 6;
+    const CUtensorMap& ta3 = cached_tmap_bf16(a.data_ptr(), M, K, a.stride(0), kBM);
+    const CUtensorMap& tb3 = cached_tmap_bf16(b.data_ptr(), N, K, b.stride(0), kBN / 4);  // quarter-tile boxes (64 rows)
+    const CUtensorMap& tc3 = cached_tmap_store_bf16(c.data_ptr(), M, N, c.stride(0));
+    const int smem3 = STAGES3 * kStage2 + kEpiBytes + (2 * STAGES3 + 4) * 8 + 16 + 1024;
+    static int max_clusters = 0;
+    if (!max_clusters) {
+      C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_4cta_kernel<STAGES3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(sms / 4 * 4);
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = smem3;
+      cudaLaunchAttribute at_[1];
+      at_[0].id = cudaLaunchAttributeClusterDimension;
+      at_[0].val.clusterDim.x = 4;
+      at_[0].val.clusterDim.y = 1;
+      at_[0].val.clusterDim.z = 1;
+      cfg.attrs = at_;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_nt_4cta_kernel<STAGES3>, &cfg) != cudaSuccess || n <= 0) n = sms / 4;
+      max_clusters = n;
+    }
+    const int tiles3 = (((M + 2 * kBM - 1) / (2 * kBM) + 1) / 2) * ((N + kBN - 1) / kBN);
+    const int clusters = std::max(1, std::min(max_clusters, tiles3));
+    static const int group_m3 = [] {
+      const char* e = getenv("VESCALE_B200_GEMM_GROUP_M");
+      return e ? std::max(1, atoi(e) / 2) : 4;
+    }();
+    gemm_nt_4cta_kernel<STAGES3><<<clusters * 4, kGemmThreads, smem3, at::cuda::getCurrentCUDAStream()>>>(ta3, tb3, tc3, (int)M, (int)N, (int)K, group_m3);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return;
+  }
+  if (variant == 2 || variant == 3) {
     constexpr int STAGES2 = 6;
     const CUtensorMap& ta2 = cached_tmap_bf16(a.data_ptr(), M, K, a.stride(0), kBM);
     const CUtensorMap& tb2 = cached_tmap_bf16(b.data_ptr(), N, K, b.stride(0), kBN / 2);

@@ -21,6 +21,8 @@ FLAGS: Dict[str, Tuple[str, str]] = {
     "VESCALE_B200_ALLOW_FALLBACK": ("0", "1 = allow PyTorch fallbacks on a CUDA device when vescale_b200/_C.so is missing (default: fail loudly)"),
     "VESCALE_B200_MULTIMEM": ("1", "0 = never use NVLS multimem instructions in the symmetric-memory kernels"),
     "VESCALE_B200_SYMM_CHUNK_MB": ("2048", "size of one symmetric-memory arena chunk (one rendezvous per chunk)"),
+    "VESCALE_B200_GEMM_VARIANT": ("2", "read by csrc/gemm_sm100.cu: 1 = 1-CTA tcgen05 kernel, 2 = CTA pairs (default), 3 = experimental 2x2 cluster with TMA multicast of B"),
+    "VESCALE_B200_GEMM_GROUP_M": ("8", "read by csrc/gemm_sm100.cu: M-tiles per rasterisation group (L2 locality)"),
     "VESCALE_B200_AG_CTAS": ("0", "CTAs of the FSDP pull all-gather kernel (0 = a quarter of the SMs)"),
     "VESCALE_B200_RS_CTAS": ("0", "CTAs of the fused reduce-scatter kernels (0 = half of the SMs)"),
 }
