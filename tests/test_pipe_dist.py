@@ -31,7 +31,8 @@ def _pp(rank, world, sched_name, tracer):
     ref = make_model().to(dev)
     model = copy.deepcopy(ref)
     mesh = init_device_mesh(dev, (world,), mesh_dim_names=("PP",))
-    plan = PipelineParallelPlan(num_stages=world, schedule_type=PipelineScheduleType[sched_name], tracer_type=TracerType[tracer])
+    plan = PipelineParallelPlan(num_stages=world, schedule_type=PipelineScheduleType[sched_name], tracer_type=TracerType[tracer],
+                                example_inputs=(torch.randn(3, 16).to(dev),) if tracer == "EXPORT" else None)
     pm = construct_pipeline_stage(model, plan, mesh)
     M = 8
     g = torch.Generator().manual_seed(5)
@@ -61,7 +62,7 @@ def _pp(rank, world, sched_name, tracer):
                 continue
             torch.testing.assert_close(p.grad, ref_params[fq].grad, rtol=1e-4, atol=1e-6, msg=fq)
             checked += 1
-    assert checked > 0 or tracer == "FX"
+    assert checked > 0 or tracer in ("FX", "EXPORT")
 
 
 @pytest.mark.parametrize("sched", ["GPIPE", "SIMPLE_1F1B", "INTERLEAVED_1F1B", "ZERO_BUBBLE", "ZERO_BUBBLE_V"])
@@ -71,6 +72,10 @@ def test_pipeline_schedules_match_single_process(sched):
 
 def test_pipeline_fx_tracer():
     run_distributed(_pp, 2, "SIMPLE_1F1B", "FX")
+
+
+def test_pipeline_export_tracer():
+    run_distributed(_pp, 2, "SIMPLE_1F1B", "EXPORT")
 
 
 def test_scheduler_properties():

@@ -33,6 +33,7 @@ class PipelineScheduleType(Enum):
 class TracerType(Enum):
     STRUCTURAL = "structural"  # split along the model's declared unit list
     FX = "fx"  # torch.fx symbolic trace + split_module
+    EXPORT = "export"  # torch.export (dynamo) graph capture, unflattened back to the module hierarchy, split on unit boundaries
 
 
 @dataclass
@@ -55,6 +56,7 @@ class PipelineParallelPlan:
     p2p_tensor_dtype: Optional[torch.dtype] = None  # None = whatever the stage produces
     schedule_type: PipelineScheduleType = PipelineScheduleType.SIMPLE_1F1B
     tracer_type: TracerType = TracerType.STRUCTURAL
+    example_inputs: Optional[tuple] = None  # example arguments of the whole model (TracerType.EXPORT captures with them)
     shared_modules: List[List[str]] = field(default_factory=list)  # groups of parameter fqns tied across stages
     costs: Dict[str, float] = field(default_factory=lambda: {"F": 1.0, "B": 1.0, "W": 1.0, "comm": 0.0})
     max_inflight: Optional[int] = None

@@ -91,7 +91,25 @@ class PipeParser:
         groups = split_units(units, plan)
         if plan.tracer_type == TracerType.FX:
             return self._parse_fx(model, units, groups)
+        if plan.tracer_type == TracerType.EXPORT:
+            return self._parse_export(model, units, groups, plan)
         return [_StageSeq([units[i] for i in g]) for g in groups]
+
+    def _parse_export(self, model, units, groups, plan) -> List[nn.Module]:
+        """Dynamo-export tracer (legacy ``pipe/tracer.py`` "dynamo export" mode): ``torch.export.export`` captures an aten-level
+        graph with the parameters lifted; ``unflatten`` restores one graph module per original sub-module (same FQNs, same
+        parameter names), and the stages are cut on the unit boundaries of that captured hierarchy.  Needs
+        ``plan.example_inputs`` (a tuple of example arguments for the whole model)."""
+        ex = getattr(plan, "example_inputs", None)
+        if ex is None:
+            raise ValueError("TracerType.EXPORT needs plan.example_inputs")
+        ep = torch.export.export(model, tuple(ex))
+        um = torch.export.unflatten(ep)
+        captured = dict(um.named_children())
+        missing = [n for n, _ in units if n.split(".")[0] not in captured]
+        if missing:
+            raise RuntimeError(f"export tracer: units {missing} are not top-level sub-modules of the captured graph")
+        return [_StageSeq([(units[i][0], captured[units[i][0]]) for i in g]) for g in groups]
 
     def _parse_fx(self, model, units, groups) -> List[nn.Module]:
         import torch.fx as fx
