@@ -268,6 +268,8 @@ def main():
 
     # ---- timed region 1: device-timed
     sampler.mark_begin()
+    state.measure_exposed = True
+    state._exposed_events = []
     _ext.LAUNCH_COUNTER.update(n=0, enabled=True, by_op={})
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,6 +282,8 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    exposed_ms = state.exposed_comm_ms() / args.steps  # compute-stream stalls on all-gather / reduce-scatter completion
+    state.measure_exposed = False
     step_ms = [round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(args.steps)]
     launches = _ext.LAUNCH_COUNTER["n"]
     by_op = dict(_ext.LAUNCH_COUNTER["by_op"])
@@ -311,10 +315,10 @@ def main():
     elif args.profile:
         step_device(0)
 
-    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0, mem_gb], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0, mem_gb, exposed_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms_max, mem_gb = t.tolist()
+    ms, e2e_ms_max, mem_gb, exposed_ms = t.tolist()
     tokens_per_step = dp_size * B * S
     tps = tokens_per_step * args.steps / (ms / 1e3)
     flops_tok = llama_flops_per_token(cfg, S)
@@ -357,6 +361,7 @@ def main():
         },
         "mfu_of_measured_cublas_sustained": tps / world * flops_tok / peak,
         "model_tflops_per_gpu": tps / world * flops_tok / 1e12,
+        "exposed_comm_ms_per_step": exposed_ms,  # device-timed stall of the compute stream on FSDP collectives, max over ranks
         "peak_mem_gb": mem_gb,
         "final_loss": final_loss,
         "step_ms": step_ms,

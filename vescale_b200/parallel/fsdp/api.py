@@ -40,13 +40,16 @@ class _BufferPool:
         self.free: Dict[Tuple[int, torch.dtype, bool], List[Tuple[torch.Tensor, Any]]] = {}
         self.allocated_bytes = 0
 
-    def get(self, numel: int, dtype, stream, alloc: Callable[[], torch.Tensor], symmetric: bool = False) -> torch.Tensor:
+    def get(self, numel: int, dtype, stream, alloc: Callable[[], torch.Tensor], symmetric: bool = False, wait=None) -> torch.Tensor:
         key = (numel, dtype, symmetric)
         lst = self.free.get(key)
         if lst:
             buf, evt = lst.pop(0)  # FIFO: the buffer that has been idle longest (its collectives are most likely done)
             if evt is not None and stream is not None:
-                stream.wait_event(evt) if hasattr(stream, "wait_event") else None
+                if wait is not None:
+                    wait(evt)  # the caller's (timed) wait on its compute stream
+                elif hasattr(stream, "wait_event"):
+                    stream.wait_event(evt)
             return buf
         buf = alloc()
         self.allocated_bytes += buf.numel() * buf.element_size()
@@ -82,6 +85,35 @@ class FSDPState:
         self.comm = None
         self.iteration = 0
         self._handshake_iter = -1  # iteration in which a gather already exchanged "my shards are final" flags
+        # exposed-communication accounting: when on, every wait of the compute stream on a communication event is bracketed
+        # by two timing events; their elapsed time is the stall (≈ 0 when the collective had already finished)
+        self.measure_exposed = False
+        self._exposed_events: List[Tuple[Any, Any]] = []
+
+    # ------------------------------------------------------------------ exposed communication
+    def wait_comm_event(self, event) -> None:
+        """Make the current (compute) stream wait for a communication event, timing the stall when ``measure_exposed``."""
+        if not self.cuda or event is None:
+            return
+        s = self.cur_stream()
+        if not self.measure_exposed:
+            s.wait_event(event)
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s)
+        s.wait_event(event)
+        b.record(s)
+        self._exposed_events.append((a, b))
+
+    def exposed_comm_ms(self, reset: bool = True) -> float:
+        """Device time the compute stream spent stalled on all-gather / reduce-scatter completion since the last reset
+        (the "exposed communication" of BASELINE.json's metric).  Call after a device synchronize."""
+        tot = 0.0
+        for a, b in self._exposed_events:
+            tot += a.elapsed_time(b)
+        if reset:
+            self._exposed_events = []
+        return tot
 
     # ------------------------------------------------------------------ stream helpers
     def cur_stream(self):
@@ -171,7 +203,7 @@ class FSDPState:
             been streaming in behind the first GEMM and whatever followed it (RoPE, attention, ...)."""
             if u._pending_rest:
                 u._pending_rest = False
-                state.cur_stream().wait_event(evt)
+                state.wait_comm_event(evt)
                 for q in others:
                     q.__dict__.pop("_vb_pending_gather", None)
 
@@ -218,8 +250,7 @@ class FSDPState:
             self.launch_all_gather(u)
         if u.unsharded:
             return
-        if self.cuda:
-            self.cur_stream().wait_event(u.ag_event)
+        self.wait_comm_event(u.ag_event)
         u.ag_event = None
         u.use_full(u._ag_full)
         u._params_valid = True
@@ -276,7 +307,7 @@ class FSDPState:
                 raise RuntimeError("symmetric gradient pool exhausted after lazy_init (would need a rendezvous mid-step)")
             return u._alloc_full(u.param_dtype, symmetric=sym)
 
-        fg = self.pool.get(u.S * u.world, u.param_dtype, self.cur_stream(), _alloc, symmetric=sym)
+        fg = self.pool.get(u.S * u.world, u.param_dtype, self.cur_stream(), _alloc, symmetric=sym, wait=self.wait_comm_event)
         if sym:
             self.comm.wait_buffer_free(fg)  # peers may still be pull-reducing the previous tenant of this buffer
         u.attach_grad_buffer(fg, accumulate=False)
@@ -325,7 +356,7 @@ class FSDPState:
         if self.cuda:
             for u in self.units:
                 if u.rs_event is not None:
-                    self.cur_stream().wait_event(u.rs_event)
+                    self.wait_comm_event(u.rs_event)
                     u.rs_event = None
 
     def set_requires_gradient_sync(self, flag: bool) -> None:
