@@ -123,8 +123,8 @@ VB_DEVICE void mc_st(void* p, const uint4& v) {
 // MODE 0: P2P two-shot (reduce my slice from all peers, write it to all peers).  MODE 1: NVLS two-shot.
 // MODE 2: one-shot (every rank reduces everything into a private output; no peer writes).
 template <typename T, int MODE>
-__global__ void __launch_bounds__(512) all_reduce_kernel(Peers bufs, void* mc, uint4* __restrict__ out, size_t nvec, int world, int rank, float scale,
-                                                         Flags pads, const uint32_t* my_pad, int slot, uint32_t epoch, uint32_t* counter) {
+__global__ void __launch_bounds__(512) all_reduce_kernel(const __grid_constant__ Peers bufs, void* mc, uint4* __restrict__ out, size_t nvec, int world, int rank, float scale,
+                                                         const __grid_constant__ Flags pads, const uint32_t* my_pad, int slot, uint32_t epoch, uint32_t* counter) {
   start_barrier(pads, my_pad, world, rank, slot, epoch);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -193,7 +193,7 @@ struct A2AArgs {
 };
 
 template <typename V>
-__global__ void __launch_bounds__(512) a2a_permute_kernel(const V* __restrict__ src, Peers dst, A2AArgs a, int world, int rank, Flags pads,
+__global__ void __launch_bounds__(512) a2a_permute_kernel(const V* __restrict__ src, const __grid_constant__ Peers dst, const __grid_constant__ A2AArgs a, int world, int rank, const __grid_constant__ Flags pads,
                                                           const uint32_t* my_pad, int slot, uint32_t epoch, uint32_t* counter) {
   start_barrier(pads, my_pad, world, rank, slot, epoch);
   const int64_t total = a.n[0] * a.n[1] * a.n[2] * a.n[3] * a.n[4];
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(512) a2a_permute_kernel(const V* __restrict__ 
 // ------------------------------------------------------------------------------------------------- one-sided segment puts
 // table[n][4] (int64, units of VEC bytes): src_off, dst_peer, dst_off, count
 template <typename V>
-__global__ void __launch_bounds__(512) put_segments_kernel(const V* __restrict__ src, Peers dst, const int64_t* __restrict__ table, int nseg, int world,
-                                                           int rank, Flags pads, const uint32_t* my_pad, int slot, uint32_t epoch, uint32_t* counter) {
+__global__ void __launch_bounds__(512) put_segments_kernel(const V* __restrict__ src, const __grid_constant__ Peers dst, const int64_t* __restrict__ table, int nseg, int world,
+                                                           int rank, const __grid_constant__ Flags pads, const uint32_t* my_pad, int slot, uint32_t epoch, uint32_t* counter) {
   start_barrier(pads, my_pad, world, rank, slot, epoch);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int s = 0; s < nseg; ++s) {
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(512) put_segments_kernel(const V* __restrict__
 constexpr int kVCEThreads = 512;
 __global__ void __launch_bounds__(kVCEThreads) vocab_ce_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
                                                                const float* __restrict__ n_valid, float* __restrict__ loss, int T, int Vloc, int64_t v0,
-                                                               int64_t ignore_index, Peers stats, int world, int rank, uint32_t epoch, int max_rows,
+                                                               int64_t ignore_index, const __grid_constant__ Peers stats, int world, int rank, uint32_t epoch, int max_rows,
                                                                int max_ctas) {
   __shared__ float red[33];
   const int parity = epoch & 1;
