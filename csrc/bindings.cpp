@@ -67,7 +67,11 @@ void moe_combine_get(at::Tensor out, c10::optional<at::Tensor> gate, const at::T
 void philox_fill_box(at::Tensor local, std::vector<int64_t> size, std::vector<int64_t> goff, std::vector<int64_t> gstride, std::vector<int64_t> lstride,
                      int64_t lbase, int64_t seed, int64_t offset, bool normal, double a, double b);
 
+void philox_dropout_box(const at::Tensor& x, at::Tensor out, at::Tensor mask, std::vector<int64_t> size, std::vector<int64_t> goff, std::vector<int64_t> gstride,
+                        std::vector<int64_t> lstride, int64_t lbase, int64_t seed, int64_t offset, double p);
+
 TORCH_LIBRARY(vescale_b200, m) {
+  m.def("philox_dropout_box(Tensor x, Tensor(a!) out, Tensor(b!) mask, int[] size, int[] goff, int[] gstride, int[] lstride, int lbase, int seed, int offset, float p) -> ()");
   m.def("rms_norm_fwd(Tensor x, Tensor w, float eps) -> (Tensor, Tensor)");
   m.def("add_rms_norm_fwd(Tensor a, Tensor b, Tensor w, float eps) -> (Tensor, Tensor, Tensor)");
   m.def("rms_norm_bwd(Tensor dy, Tensor x, Tensor w, Tensor rstd) -> (Tensor, Tensor)");
@@ -104,6 +108,7 @@ TORCH_LIBRARY(vescale_b200, m) {
 }
 
 TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
+  m.impl("philox_dropout_box", &philox_dropout_box);
   m.impl("wag_gemm", &wag_gemm);
   m.impl("symm_all_reduce", &symm_all_reduce);
   m.impl("symm_a2a_permute", &symm_a2a_permute);

@@ -243,3 +243,36 @@ def test_fp8_block_scaled_gemm_on_cuda():
     xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
     fp8.fp8_linear(xr, wr).float().sum().backward()
     assert xr.grad is not None and wr.grad is not None and torch.isfinite(xr.grad.float()).all()
+
+
+def test_fused_sharded_dropout_matches_composite():
+    """The fused Philox dropout kernel draws the same mask and values as the specification path (uniform fill, compare,
+    scale), for a full tensor and for a shard of it viewed through a fake 4-rank mesh."""
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200.dtensor import DTensor
+    from vescale_b200.dtensor import random as R
+    from vescale_b200.ops import philox
+
+    if not philox.dropout_available():
+        pytest.skip("extension built without philox_dropout_box")
+    dev = torch.device("cuda")
+    full = torch.randn(64, 96, device=dev).bfloat16()
+    outs = {}
+    for rank in (0, 2):
+        mesh = init_device_mesh("cuda", (4,), _rank=rank, _init_process_groups=False)
+        for pl in ([Replicate()], [Shard(0)], [Shard(1)]):
+            local = full if isinstance(pl[0], Replicate) else full.chunk(4, dim=pl[0].dim)[rank].contiguous()
+            spec = DTensor.from_local(local, mesh, pl, run_check=False)._spec
+            tr = R.ThreadBasedRNGTracker()
+            R.manual_seed(123)
+            fused_out, fused_mask = tr.run(torch.ops.aten.native_dropout.default, [local, 0.3, True], {}, spec)
+            R.manual_seed(123)
+            u = R.sharded_random_fill(torch.empty(local.shape, dtype=torch.float32, device=dev), spec, "uniform")
+            mask = u >= 0.3
+            ref = local * mask.to(local.dtype) * (1.0 / 0.7)
+            assert torch.equal(fused_mask, mask) and torch.equal(fused_out, ref), (rank, pl)
+            outs[(rank, str(pl))] = (fused_out, fused_mask)
+    # shards agree with the replicated result at their global positions
+    rep_out, rep_mask = outs[(0, str([Replicate()]))]
+    assert torch.equal(outs[(2, str([Shard(0)]))][0], rep_out.chunk(4, 0)[2]) and torch.equal(outs[(2, str([Shard(1)]))][1], rep_mask.chunk(4, 1)[2])
+    assert 0.2 < (~rep_mask).float().mean().item() < 0.4

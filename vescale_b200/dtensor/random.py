@@ -247,6 +247,14 @@ class ThreadBasedRNGTracker(RNGStateTracker):
             p, train = float(local_args[1]), local_args[2]
             if not train or p == 0.0:
                 return x.clone(), torch.ones_like(x, dtype=torch.bool)
+            if x.is_cuda and x.is_contiguous() and x.numel() and p < 1.0:
+                from ..ops import philox as _ph
+
+                if _ph.dropout_available():  # one fused pass: Philox + mask + scale (csrc/philox_shard.cu)
+                    seed, offset = _STATE["seed"], _STATE["offset"]
+                    _STATE["offset"] = offset + (math.prod(spec.shape) + 3) // 4
+                    boxes = local_boxes(tuple(spec.shape), spec.mesh, spec.placements)
+                    return _ph.philox_dropout_boxes(x, tuple(spec.shape), boxes, seed, offset, p, ragged=spec.is_ragged_shard())
             u = sharded_random_fill(torch.empty(x.shape, dtype=torch.float32, device=x.device), spec, "uniform")
             mask = u >= p
             return x * mask.to(x.dtype) * (1.0 / (1.0 - p)), mask
