@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--reshard", default="auto", choices=["auto", "yes", "no"])
     p.add_argument("--max-grad-norm", type=float, default=1.0)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--device", default="cuda", choices=["cuda", "cpu"], help="cpu = control-flow smoke test of this script on gloo (marks the record invalid)")
     p.add_argument("--tp", type=int, default=1, help="tensor/sequence-parallel degree (2-D: FSDP over world/tp x TP over tp, fused TP kernels)")
     p.add_argument("--tp-impl", default="fused", choices=["fused", "plain"], help="fused = ag_gemm/gemm_rs sm_100a kernels; plain = NCCL + library GEMMs")
     p.add_argument("--fp8", action="store_true", help="block-scaled e4m3 forward GEMMs in the decoder blocks (BASELINE config 5; use with --model llama3_70b)")
@@ -156,11 +157,25 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    cuda = args.device == "cuda"
+    if cuda:
+        torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank) if cuda else torch.device("cpu")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev) if cuda else dist.init_process_group("gloo")
+
+    class _WallEvent:  # CPU stand-in for torch.cuda.Event (perf_counter based)
+        def __init__(self, enable_timing=True):
+            self.t = 0.0
+
+        def record(self, stream=None):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    Event = torch.cuda.Event if cuda else _WallEvent
 
     from vescale_b200 import init_device_mesh
     from vescale_b200.models import LlamaConfig, LlamaModel, llama_flops_per_token
@@ -168,7 +183,8 @@ def main():
     from vescale_b200.optim import FSDPAdamW
     from vescale_b200.parallel.fsdp import fully_shard
 
-    _ext.load(required=True)
+    if cuda:
+        _ext.load(required=True)
     Fn.set_gemm_backend(args.gemm)
     cfg = getattr(LlamaConfig, args.model)()
     cfg.fp8 = bool(args.fp8)
@@ -177,6 +193,9 @@ def main():
         cfg.num_layers = args.layers
         invalid = f"layers overridden to {args.layers}"
     S, B = args.seq_len, args.micro_batch
+    if not cuda:
+        invalid = "cpu control-flow smoke test"
+        cfg.dtype = torch.float32
     cfg.max_seq_len = max(cfg.max_seq_len, S)
     tp_size = args.tp
     if world % tp_size:
@@ -187,10 +206,10 @@ def main():
         from vescale_b200.comm.fused_tp import FusedTP, PlainTP
         from vescale_b200.models.llama_tp import LlamaTPModel
 
-        mesh = init_device_mesh("cuda", (dp_size, tp_size), mesh_dim_names=("dp", "tp"))
-        tp = FusedTP(mesh, "tp", dev) if args.tp_impl == "fused" else PlainTP(mesh, "tp")
+        mesh = init_device_mesh(args.device, (dp_size, tp_size), mesh_dim_names=("dp", "tp"))
+        tp = FusedTP(mesh, "tp", dev) if (args.tp_impl == "fused" and cuda) else PlainTP(mesh, "tp")
     else:
-        mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("dp",), **({} if world > 1 else {"_init_process_groups": False}))
+        mesh = init_device_mesh(args.device, (world,), mesh_dim_names=("dp",), **({} if world > 1 else {"_init_process_groups": False}))
     dp_rank = mesh.get_local_rank("dp") if world > 1 else 0
 
     # ---- build: meta-device model, materialised unit by unit straight into the sharded master weights
@@ -228,9 +247,10 @@ def main():
     # ---- synthetic data: pinned host batches (e2e) and device-resident copies (kernel-timed)
     n_batches = max(args.steps, 4)
     g = torch.Generator().manual_seed(1000 + dp_rank)  # the ranks of one TP group see the same batch
-    host_tok = [torch.randint(0, cfg.vocab_size, (B, S + 1), generator=g).pin_memory() for _ in range(n_batches)]
+    host_tok = [torch.randint(0, cfg.vocab_size, (B, S + 1), generator=g) for _ in range(n_batches)]
+    host_tok = [t.pin_memory() for t in host_tok] if cuda else host_tok
     dev_tok = [t.to(dev) for t in host_tok[:4]]
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory() if cuda else torch.zeros(1, dtype=torch.float32)
     h2d_bytes = host_tok[0].numel() * host_tok[0].element_size()
     d2h_bytes = 4
 
@@ -253,8 +273,9 @@ def main():
 
     def barrier():
         if world > 1:
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize()
+            dist.barrier(device_ids=[local_rank]) if cuda else dist.barrier()
+        if cuda:
+            torch.cuda.synchronize()
 
     # the clock sampler is started before the warm-up: spawning nvidia-smi (NVML init over all GPUs) stalls kernel launches for
     # a few hundred ms, which must not land inside the timed region; only samples taken during the region are reported
@@ -264,7 +285,7 @@ def main():
     for i in range(args.warmup):
         step_device(i)
     barrier()
-    mem_gb = torch.cuda.max_memory_allocated() / 2**30
+    mem_gb = torch.cuda.max_memory_allocated() / 2**30 if cuda else 0.0
 
     # ---- timed region 1: device-timed
     sampler.mark_begin()
@@ -272,8 +293,8 @@ def main():
     state._exposed_events = []
     _ext.LAUNCH_COUNTER.update(n=0, enabled=True, by_op={})
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e0, e1 = Event(enable_timing=True), Event(enable_timing=True)
+    marks = [Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
     last = None
     for i in range(args.steps):
@@ -349,7 +370,7 @@ def main():
             "global_batch": dp_size * B,
             "seq_len": S,
             "tokens_per_gpu_per_step": B * S // tp_size,
-            "parallelism": f"fsdp{world}" if tp is None else f"fsdp{dp_size}xtp{tp_size}({args.tp_impl})",
+            "parallelism": f"fsdp{world}" if tp is None else f"fsdp{dp_size}xtp{tp_size}({type(tp).__name__})",
             "comm_backend": comm_name,
             "gemm_backend": args.gemm,
             "reshard_after_forward": bool(reshard),

@@ -211,3 +211,23 @@ def test_fp8_block_scaled_linear():
     loss.backward()
     ref_loss = LlamaModel(LlamaConfig.tiny()).reset_parameters(seed=1)(tok[:, :-1], tok[:, 1:])
     assert abs(loss.item() - ref_loss.item()) < 0.05 and all(p.grad is not None for p in m.parameters())
+
+
+def test_bench_script_control_flow_on_cpu():
+    """``bench.py --device cpu`` walks the whole script (build, warm-up, both timed regions, JSON contract) on the tiny model;
+    the record is marked invalid.  Guards the driver-facing entry point against regressions that only a GPU run would show."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--device", "cpu", "--model", "tiny", "--seq-len", "64", "--micro-batch", "2", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=240, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e",
+              "gpu_launches", "exposed_comm_ms_per_step", "step_ms"):
+        assert k in rec, k
+    assert rec["invalid"] and rec["steps"] == 2 and rec["e2e"]["h2d_bytes_per_step"] == 2 * 65 * 8 and rec["e2e"]["d2h_bytes_per_step"] == 4
+    ref = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], capture_output=True, text=True, timeout=120, cwd=root)
+    assert ref.returncode == 0 and json.loads(ref.stdout.strip().splitlines()[-1])["impl"] == "reference"
