@@ -58,6 +58,17 @@ class _BufferPool:
     def put(self, buf: torch.Tensor, event, symmetric: bool = False) -> None:
         self.free.setdefault((buf.numel(), buf.dtype, symmetric), []).append((buf, event))
 
+    def poison_free(self, stream=None) -> None:
+        """Debug (``VESCALE_B200_SYMM_DEBUG=1``): NaN-fill every idle buffer once its last collective has finished, so a
+        consumer that reads a pooled buffer before its producer has written it cannot go unnoticed."""
+        from ...comm.symm_debug import poison
+
+        for lst in self.free.values():
+            for buf, evt in lst:
+                if evt is not None and hasattr(evt, "synchronize"):
+                    evt.synchronize()
+                poison(buf)
+
 
 class FSDPState:
     """Root-level state shared by all units of one ``fully_shard``-ed model."""

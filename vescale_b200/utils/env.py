@@ -19,6 +19,7 @@ FLAGS: Dict[str, Tuple[str, str]] = {
     "VESCALE_DUMP_INSTRUCTION": ("0", "1 = the pipeline engine dumps each rank's instruction list to a file"),
     "VESCALE_DEVICE_MESH": ("", "internal: name of the global VeDeviceMesh registry entry"),
     "VESCALE_B200_ALLOW_FALLBACK": ("0", "1 = allow PyTorch fallbacks on a CUDA device when vescale_b200/_C.so is missing (default: fail loudly)"),
+    "VESCALE_B200_SYMM_DEBUG": ("0", "1 = poison symmetric buffers when they return to a pool and validate signal epochs (comm/symm_debug.py)"),
     "VESCALE_B200_MULTIMEM": ("1", "0 = never use NVLS multimem instructions in the symmetric-memory kernels"),
     "VESCALE_B200_SYMM_CHUNK_MB": ("2048", "size of one symmetric-memory arena chunk (one rendezvous per chunk)"),
     "VESCALE_B200_GEMM_VARIANT": ("2", "read by csrc/gemm_sm100.cu: 1 = 1-CTA tcgen05 kernel, 2 = CTA pairs (default), 3 = experimental 2x2 cluster with TMA multicast of B"),
