@@ -231,3 +231,28 @@ def test_bench_script_control_flow_on_cpu():
     assert rec["invalid"] and rec["steps"] == 2 and rec["e2e"]["h2d_bytes_per_step"] == 2 * 65 * 8 and rec["e2e"]["d2h_bytes_per_step"] == 4
     ref = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], capture_output=True, text=True, timeout=120, cwd=root)
     assert ref.returncode == 0 and json.loads(ref.stdout.strip().splitlines()[-1])["impl"] == "reference"
+
+
+def test_symm_debug_tooling():
+    """Poisoning and the epoch-invariant checker (on a stand-in arena; the real one needs peer-mapped GPU memory)."""
+    from vescale_b200.comm.symm_debug import check_epochs, poison
+
+    assert poison(torch.zeros(4)).isnan().all() and poison(torch.zeros(2, dtype=torch.int32))[0].item() == 0x5A5A5A5A
+
+    class Arena:
+        pad = torch.zeros(8 * 2, dtype=torch.int32)
+        world = 2
+        device = torch.device("cpu")
+        group = None
+
+    a = Arena()
+    s0 = check_epochs(a, quiescent=False)
+    a.pad[0], a.pad[1] = 3, 3
+    s1 = check_epochs(a, s0, quiescent=False)
+    a.pad[1] = 2  # an epoch flag must never go backwards
+    with pytest.raises(AssertionError):
+        check_epochs(a, s1, quiescent=False)
+    a.pad[1] = 3
+    a.pad[2], a.pad[3] = 7, 5  # sources of one slot two epochs apart at a quiescent point: a lost signal
+    with pytest.raises(AssertionError):
+        torch.distributed.is_initialized() or check_epochs(a, s1, quiescent=True)
