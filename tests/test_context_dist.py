@@ -27,6 +27,15 @@ def _ulysses(rank, world):
     torch.testing.assert_close(out, ref[:, sl], rtol=1e-4, atol=1e-5)
     for a, b in ((ql, qf), (kl, kf), (vl, vf)):
         torch.testing.assert_close(a.grad, b.grad[:, sl], rtol=1e-4, atol=1e-5)
+    # all-gather-KV context parallelism: same result, dK/dV come back through a reduce-scatter
+    from vescale_b200.parallel.context import allgather_kv_attention
+
+    ql2, kl2, vl2 = (t[:, sl].clone().requires_grad_(True) for t in (q, k, v))
+    out2 = allgather_kv_attention(ql2, kl2, vl2, mesh, "cp", causal=True)
+    (out2 * w[:, sl]).sum().backward()
+    torch.testing.assert_close(out2, ref[:, sl], rtol=1e-4, atol=1e-5)
+    for a, b in ((ql2, qf), (kl2, kf), (vl2, vf)):
+        torch.testing.assert_close(a.grad, b.grad[:, sl], rtol=1e-4, atol=1e-5)
 
 
 def test_ulysses_attention_matches_full():
