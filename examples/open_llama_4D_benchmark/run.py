@@ -72,8 +72,8 @@ class Model(nn.Module):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--dp", type=int, default=1)
-    ap.add_argument("--tp", type=int, default=1)
+    ap.add_argument("--dp", type=int, default=None, help="default: world size / tp")
+    ap.add_argument("--tp", type=int, default=None, help="default: 2 when the world size is even, else 1")
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--hidden", type=int, default=4096)
     ap.add_argument("--ffn", type=int, default=11008)
@@ -89,6 +89,9 @@ def main():
     if cuda:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     dev = "cuda" if cuda else "cpu"
+    ws = dist.get_world_size()
+    args.tp = args.tp or (2 if ws % 2 == 0 else 1)
+    args.dp = args.dp or ws // args.tp
     mesh = init_device_mesh(dev, (args.dp, args.tp), mesh_dim_names=("DP", "TP"))
     torch.manual_seed(0)
     model = Model(args.vocab, args.hidden, args.ffn, args.heads, args.layers).to(dev).to(torch.bfloat16 if cuda else torch.float32)
