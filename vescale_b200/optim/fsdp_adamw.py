@@ -38,6 +38,7 @@ class FSDPAdamW:
         fused_reduce: bool = False,
         tp_group=None,
         tp_sharded: Optional[Callable[[str], bool]] = None,
+        replicate_group=None,
     ):
         st = None
         for m in model.modules():
@@ -84,6 +85,11 @@ class FSDPAdamW:
                         u.tp_replicated_segments.append((lo, hi))
                 real = sum(hi - lo for lo, hi, _ in u.layout.segments(u.rank))
                 u.tp_all_replicated = sum(hi - lo for lo, hi in u.tp_replicated_segments) == real
+        # ---- HSDP (replicate x shard): the model is sharded over the FSDP mesh dim and replicated over ``replicate_group``
+        # (each replica sees different data); reduce-scattered gradient shards are averaged over the replicas once per step.
+        self.replicate_group = replicate_group if (replicate_group is not None and dist.get_world_size(replicate_group) > 1) else None
+        if self.replicate_group is not None and fused_reduce:
+            raise ValueError("fused_reduce cannot be combined with replicate_group (gradients need the replica average first)")
         self._norm_buf = torch.zeros(1, dtype=torch.float32, device=dev)
         self._norm_rep = torch.zeros(1, dtype=torch.float32, device=dev)
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
@@ -203,6 +209,14 @@ class FSDPAdamW:
         bc1 = 1.0 - b1**self.step_count
         bc2 = 1.0 - b2**self.step_count
         norm = None
+        if self.replicate_group is not None:
+            n_rep = dist.get_world_size(self.replicate_group)
+            for u in self.units:
+                if u.grad_ready:
+                    g = self._grad_view(u)
+                    dist.all_reduce(g, group=self.replicate_group)
+                    g.div_(n_rep)
+                    u.sumsq = None  # the reduce-scatter kernel's partial norm predates the replica average
         if self.tp_group is not None:
             self._sync_tp_replicated_grads()
         if self.max_grad_norm is not None:
