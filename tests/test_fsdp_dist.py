@@ -159,3 +159,57 @@ def _hsdp(rank, world):
 
 def test_hsdp_replicate_x_shard_matches_single_process():
     run_distributed(_hsdp, 4)
+
+
+def _grad_accum(rank, world):
+    """Two micro-batches per step with the reduce-scatter deferred to the last one (``set_requires_gradient_sync(False)``)
+    must equal one step on the concatenated batch."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.models import LlamaConfig, LlamaModel
+    from vescale_b200.optim import FSDPAdamW
+    from vescale_b200.parallel.fsdp import MixedPrecisionPolicy, fully_shard
+
+    dev = device_type()
+    cfg = LlamaConfig.tiny()
+    mesh = init_device_mesh(dev, (world,))
+    mp = MixedPrecisionPolicy(param_dtype=torch.float32, reduce_dtype=torch.float32)
+
+    def build():
+        m = LlamaModel(cfg).reset_parameters(seed=1).to(dev)
+        for blk in m.layers:
+            fully_shard(blk, mesh, mp_policy=mp)
+        fully_shard(m, mesh, mp_policy=mp)
+        return m, FSDPAdamW(m, lr=1e-2, max_grad_norm=1.0)
+
+    ma, oa = build()  # accumulates over two micro-batches
+    mb, ob = build()  # sees both at once
+    for s in range(2):
+        g = torch.Generator().manual_seed(10 * s + rank)
+        tok = torch.randint(0, cfg.vocab_size, (4, 17), generator=g).to(dev)
+        st = ma._fsdp_state
+        st.set_requires_gradient_sync(False)
+        (ma(tok[:2, :-1], tok[:2, 1:]) / 2).backward()
+        assert all(u.full_grad is not None and not u.grad_ready for u in st.units)  # nothing reduced yet
+        st.set_requires_gradient_sync(True)
+        (ma(tok[2:, :-1], tok[2:, 1:]) / 2).backward()
+        mb(tok[:, :-1], tok[:, 1:]).backward()
+        st.wait_grads()
+        mb._fsdp_state.wait_grads()
+        # compare the reduce-scattered gradient shards (comparing weights after Adam would amplify fp32 summation-order noise
+        # on near-zero gradients into +-lr differences)
+        for ua, ub in zip(st.units, mb._fsdp_state.units):
+            torch.testing.assert_close(ua.grad_shard, ub.grad_shard, rtol=1e-4, atol=1e-7, msg=ua.name)
+        na, nb = oa.step(), ob.step()
+        torch.testing.assert_close(na, nb, rtol=1e-5, atol=1e-7)
+        oa.zero_grad()
+        ob.zero_grad()
+        # keep the twins in lock-step for the next iteration: copy B's weights and moments into A
+        for ua, ub in zip(st.units, mb._fsdp_state.units):
+            ua.master.copy_(ub.master)
+            ua.exp_avg.copy_(ub.exp_avg)
+            ua.exp_avg_sq.copy_(ub.exp_avg_sq)
+            ua.param_shard.copy_(ub.param_shard)
+
+
+def test_fsdp_gradient_accumulation():
+    run_distributed(_grad_accum, 4)
