@@ -68,8 +68,9 @@ def _autotune(kind: str, M: int, N: int, K: int, run_ours, run_lib) -> bool:
         e1.synchronize()
         return e0.elapsed_time(e1)
 
-    ours, lib = t(run_ours), t(run_lib)
-    ours2, lib2 = t(run_ours), t(run_lib)  # second pass under warmed-up clocks/power
+    with torch.no_grad():  # the timing launches write into ``out=`` buffers, which autograd would reject for tracked inputs
+        ours, lib = t(run_ours), t(run_lib)
+        ours2, lib2 = t(run_ours), t(run_lib)  # second pass under warmed-up clocks/power
     use = min(ours, ours2) <= min(lib, lib2)
     _AUTOTUNE[key] = use
     return use
