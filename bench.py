@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--device", default="cuda", choices=["cuda", "cpu"], help="cpu = control-flow smoke test of this script on gloo (marks the record invalid)")
     p.add_argument("--tp", type=int, default=1, help="tensor/sequence-parallel degree (2-D: FSDP over world/tp x TP over tp, fused TP kernels)")
     p.add_argument("--tp-impl", default="fused", choices=["fused", "plain"], help="fused = ag_gemm/gemm_rs sm_100a kernels; plain = NCCL + library GEMMs")
+    p.add_argument("--ac", default="selective", choices=["selective", "full"], help="selective = recompute norm / SwiGLU outputs only (default); full = checkpoint every block (70B-class models)")
     p.add_argument("--fp8", action="store_true", help="block-scaled e4m3 forward GEMMs in the decoder blocks (BASELINE config 5; use with --model llama3_70b)")
     p.add_argument("--prefetch", type=int, default=1, help="FSDP all-gather prefetch depth (0 = every all-gather exposed: the memory-lean mode)")
     p.add_argument("--fuse-first-gemm", action="store_true", help="exposed all-gathers: the unit's first GEMM gathers its own weight (wag_gemm)")
@@ -237,6 +238,10 @@ def main():
     kw = dict(comm_backend=args.comm, reshard_after_forward=reshard, init_fn=init_fn, prefetch=args.prefetch, mesh_dim="dp")
     fully_shard(model.embed, mesh, **kw)
     for blk in model.layers:
+        if args.ac == "full":
+            from vescale_b200.parallel.fsdp import checkpoint_module
+
+            checkpoint_module(blk)
         fully_shard(blk, mesh, fuse_first_gemm=bool(args.fuse_first_gemm and dp_size > 1 and tp is None), **kw)
     fully_shard(model.head, mesh, **kw)
     fully_shard(model, mesh, **kw)
@@ -377,7 +382,7 @@ def main():
             "prefetch": args.prefetch,
             "fuse_first_gemm": bool(args.fuse_first_gemm),
             "optimizer": "AdamW fp32 master/m/v, global-norm clip 1.0" if args.max_grad_norm else "AdamW fp32 master/m/v, no clip",
-            "activation_memory": "selective recompute (norm and SwiGLU outputs recomputed)",
+            "activation_memory": "selective recompute (norm and SwiGLU outputs recomputed)" if args.ac == "selective" else "full activation checkpointing per block",
             "l2_policy": "no explicit flush: per-step working set (>100 GB of weights/optimizer state/activations) is ~1000x the 126 MB L2",
         },
         "mfu_of_measured_cublas_sustained": tps / world * flops_tok / peak,

@@ -213,3 +213,51 @@ def _grad_accum(rank, world):
 
 def test_fsdp_gradient_accumulation():
     run_distributed(_grad_accum, 4)
+
+
+def _act_ckpt(rank, world):
+    """Full activation checkpointing of every block under FSDP: same loss, gradient shards and grad norm as without it."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.models import LlamaConfig, LlamaModel
+    from vescale_b200.optim import FSDPAdamW
+    from vescale_b200.parallel.fsdp import MixedPrecisionPolicy, checkpoint_module, fully_shard
+
+    dev = device_type()
+    cfg = LlamaConfig.tiny()
+    mesh = init_device_mesh(dev, (world,))
+    mp = MixedPrecisionPolicy(param_dtype=torch.float32, reduce_dtype=torch.float32)
+
+    def build(ac):
+        m = LlamaModel(cfg).reset_parameters(seed=1).to(dev)
+        for blk in m.layers:
+            if ac:
+                checkpoint_module(blk)
+            fully_shard(blk, mesh, mp_policy=mp)
+        fully_shard(m, mesh, mp_policy=mp)
+        return m, FSDPAdamW(m, lr=1e-2, max_grad_norm=1.0)
+
+    (ma, oa), (mb, ob) = build(True), build(False)
+    for s in range(2):
+        g = torch.Generator().manual_seed(10 * s + rank)
+        tok = torch.randint(0, cfg.vocab_size, (2, 17), generator=g).to(dev)
+        la = ma(tok[:, :-1], tok[:, 1:])
+        la.backward()
+        lb = mb(tok[:, :-1], tok[:, 1:])
+        lb.backward()
+        assert la.item() == lb.item()
+        ma._fsdp_state.wait_grads()
+        mb._fsdp_state.wait_grads()
+        for ua, ub in zip(ma._fsdp_state.units, mb._fsdp_state.units):
+            torch.testing.assert_close(ua.grad_shard, ub.grad_shard, rtol=1e-4, atol=1e-7, msg=ua.name)
+        torch.testing.assert_close(oa.step(), ob.step(), rtol=1e-5, atol=1e-7)
+        oa.zero_grad()
+        ob.zero_grad()
+        for ua, ub in zip(ma._fsdp_state.units, mb._fsdp_state.units):  # keep the twins in lock-step (see _grad_accum)
+            ua.master.copy_(ub.master)
+            ua.exp_avg.copy_(ub.exp_avg)
+            ua.exp_avg_sq.copy_(ub.exp_avg_sq)
+            ua.param_shard.copy_(ub.param_shard)
+
+
+def test_fsdp_with_activation_checkpointing():
+    run_distributed(_act_ckpt, 4)

@@ -28,7 +28,7 @@ import torch.nn as nn
 from ...mesh import DeviceMesh, init_device_mesh
 from .unit import FSDPUnit, MixedPrecisionPolicy, make_event, _NullStream
 
-__all__ = ["fully_shard", "FSDPState", "MixedPrecisionPolicy", "get_fsdp_state", "fsdp_units"]
+__all__ = ["checkpoint_module", "fully_shard", "FSDPState", "MixedPrecisionPolicy", "get_fsdp_state", "fsdp_units"]
 
 
 class _BufferPool:
@@ -479,6 +479,30 @@ class _ParamSwap:
     def to_unsharded(self):
         for (m, n), p in zip(self.owners, self.u.params):
             m._parameters[n] = p
+
+
+def checkpoint_module(module: nn.Module) -> nn.Module:
+    """Full activation checkpointing of ``module`` (non-reentrant ``torch.utils.checkpoint``): call *before* ``fully_shard`` so
+    that the FSDP hooks sit outside the checkpointed region — the recomputation then runs while the unit is already
+    unsharded by the pre-backward hook and never triggers a gather of its own.  The Llama blocks additionally do selective
+    recomputation of their cheap elementwise intermediates inside ``ops.functional``; use this for memory-bound configurations
+    (e.g. 70B on 8 GPUs)."""
+    from torch.utils.checkpoint import checkpoint
+
+    if getattr(module, "_vb_checkpointed", False):
+        return module
+    if getattr(module, "_fsdp_unit", None) is not None:
+        raise RuntimeError("checkpoint_module must be applied before fully_shard")
+    orig = module.forward
+
+    def forward(*args, **kwargs):
+        if not torch.is_grad_enabled():
+            return orig(*args, **kwargs)
+        return checkpoint(orig, *args, use_reentrant=False, **kwargs)
+
+    module.forward = forward
+    module._vb_checkpointed = True
+    return module
 
 
 def get_fsdp_state(module: nn.Module) -> Optional[FSDPState]:
