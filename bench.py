@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--device", default="cuda", choices=["cuda", "cpu"], help="cpu = control-flow smoke test of this script on gloo (marks the record invalid)")
     p.add_argument("--tp", type=int, default=1, help="tensor/sequence-parallel degree (2-D: FSDP over world/tp x TP over tp, fused TP kernels)")
     p.add_argument("--tp-impl", default="fused", choices=["fused", "plain"], help="fused = ag_gemm/gemm_rs sm_100a kernels; plain = NCCL + library GEMMs")
+    p.add_argument("--fused-reduce", action="store_true", help="reduce-scatter ⊕ AdamW in one kernel (no gradient shard is ever stored; implies no global-norm clip; symm backend, N > 1) — the memory-lean optimizer path for 70B-class models")
     p.add_argument("--ac", default="selective", choices=["selective", "full"], help="selective = recompute norm / SwiGLU outputs only (default); full = checkpoint every block (70B-class models)")
     p.add_argument("--fp8", action="store_true", help="block-scaled e4m3 forward GEMMs in the decoder blocks (BASELINE config 5; use with --model llama3_70b)")
     p.add_argument("--prefetch", type=int, default=1, help="FSDP all-gather prefetch depth (0 = every all-gather exposed: the memory-lean mode)")
@@ -245,7 +246,11 @@ def main():
         fully_shard(blk, mesh, fuse_first_gemm=bool(args.fuse_first_gemm and dp_size > 1 and tp is None), **kw)
     fully_shard(model.head, mesh, **kw)
     fully_shard(model, mesh, **kw)
-    opt = FSDPAdamW(model, lr=3e-4, betas=(0.9, 0.95), weight_decay=0.1, max_grad_norm=args.max_grad_norm, tp_group=mesh.get_group("tp") if tp is not None else None)
+    fused_reduce = bool(args.fused_reduce and dp_size > 1 and tp is None)
+    if fused_reduce:
+        args.max_grad_norm = 0.0
+    opt = FSDPAdamW(model, lr=3e-4, betas=(0.9, 0.95), weight_decay=0.1, max_grad_norm=args.max_grad_norm or None, fused_reduce=fused_reduce,
+                    tp_group=mesh.get_group("tp") if tp is not None else None)
     state = model._fsdp_state
     comm_name = type(state.comm).__name__ if state.comm is not None else ("none" if dp_size == 1 else "nccl")
 
@@ -381,7 +386,7 @@ def main():
             "reshard_after_forward": bool(reshard),
             "prefetch": args.prefetch,
             "fuse_first_gemm": bool(args.fuse_first_gemm),
-            "optimizer": "AdamW fp32 master/m/v, global-norm clip 1.0" if args.max_grad_norm else "AdamW fp32 master/m/v, no clip",
+            "optimizer": ("AdamW fp32 master/m/v, global-norm clip 1.0" if args.max_grad_norm else "AdamW fp32 master/m/v, no clip") + (", fused into the reduce-scatter kernel" if fused_reduce else ""),
             "activation_memory": "selective recompute (norm and SwiGLU outputs recomputed)" if args.ac == "selective" else "full activation checkpointing per block",
             "l2_policy": "no explicit flush: per-step working set (>100 GB of weights/optimizer state/activations) is ~1000x the 126 MB L2",
         },
