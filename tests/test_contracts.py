@@ -256,3 +256,27 @@ def test_symm_debug_tooling():
     a.pad[2], a.pad[3] = 7, 5  # sources of one slot two epochs apart at a quiescent point: a lost signal
     with pytest.raises(AssertionError):
         torch.distributed.is_initialized() or check_epochs(a, s1, quiescent=True)
+
+
+def test_mxfp8_quantisation():
+    """OCP MX (1x32 blocks, E8M0 power-of-two scales, e4m3 elements): round trip and emulated GEMM accuracy."""
+    from vescale_b200.ops.fp8 import FP8_MAX, dequantize_mx, mxfp8_gemm_nt, quantize_mx
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(40, 200, generator=g) * torch.logspace(-3, 3, 200)
+    q, s = quantize_mx(x)
+    assert q.dtype == torch.float8_e4m3fn and s.dtype == torch.uint8 and s.shape == (40, 7)
+    back = dequantize_mx(q, s)
+    blk_amax = torch.nn.functional.pad(x, (0, 24)).view(40, 7, 32).abs().amax(2).repeat_interleave(32, 1)[:, :200]
+    assert ((back - x).abs() <= blk_amax * 2.0**-3 + 1e-12).all()  # 3 mantissa bits relative to the block's top binade
+    assert (q.float().abs() <= FP8_MAX).all()
+    # power-of-two scales: dequantised values of exact powers of two are exact
+    p2 = torch.tensor([[2.0**k for k in range(-10, 22)]])
+    qp, sp = quantize_mx(p2)
+    assert torch.equal(dequantize_mx(qp, sp)[:, -9:], p2[:, -9:])  # within e4m3's dynamic range of the block maximum
+    w = torch.randn(64, 200, generator=g) * 0.05
+    xq, xs = quantize_mx(x)
+    wq, ws = quantize_mx(w)
+    y = mxfp8_gemm_nt(xq, xs, wq, ws, torch.float32)
+    ref = x @ w.t()
+    assert (y - ref).norm() / ref.norm() < 0.05

@@ -20,7 +20,7 @@ from typing import Optional, Tuple
 
 import torch
 
-__all__ = ["quantize_blockwise", "dequantize_blockwise", "fp8_linear", "fp8_gemm_nt", "FP8_MAX", "set_fp8_backend"]
+__all__ = ["quantize_blockwise", "dequantize_blockwise", "fp8_linear", "fp8_gemm_nt", "FP8_MAX", "set_fp8_backend", "quantize_mx", "dequantize_mx", "mxfp8_gemm_nt"]
 
 FP8 = torch.float8_e4m3fn
 FP8_MAX = 448.0
@@ -140,3 +140,38 @@ class _Fp8Linear(torch.autograd.Function):
 
 def fp8_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return _Fp8Linear.apply(x, weight)
+
+
+# ------------------------------------------------------------------------------- MXFP8 (the tensor cores' native block scaling)
+# OCP microscaling: 1x32 blocks along K, one power-of-two scale (E8M0, a biased exponent byte) per block, e4m3 elements.  This
+# is the format ``tcgen05.mma.kind::mxf8f6f4.block_scale`` consumes (scale factors staged in TMEM), so the quantiser and the
+# emulated GEMM below are the numerics specification for the hand-written kernel that is still to be written
+# (DESIGN.md "known gaps"); they already let a model be evaluated under MX numerics.
+MX_BLOCK = 32
+
+
+def quantize_mx(x: torch.Tensor):
+    """[R, C] -> (e4m3 [R, C], E8M0 scales as uint8 [R, ceil(C/32)]).  scale = 2^(floor(log2(amax)) - 8) so that the block's
+    largest element lands in e4m3's top binade (448 = 1.75 * 2^8); zero blocks get the smallest scale."""
+    assert x.dim() == 2
+    R, C = x.shape
+    xp = _pad_to(x.float(), 1, MX_BLOCK)
+    blocks = xp.view(R, -1, MX_BLOCK)
+    amax = blocks.abs().amax(dim=2)
+    exp = torch.floor(torch.log2(amax.clamp(min=2.0**-127))) - 8.0
+    exp = exp.clamp(-127.0, 127.0)
+    scale = torch.exp2(exp)
+    q = (blocks / scale[:, :, None]).clamp_(-FP8_MAX, FP8_MAX).to(FP8)
+    e8m0 = (exp + 127.0).to(torch.uint8)  # biased exponent byte
+    return q.view(R, -1)[:, :C].contiguous(), e8m0
+
+
+def dequantize_mx(q: torch.Tensor, e8m0: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    R, C = q.shape
+    scale = torch.exp2(e8m0.float() - 127.0).repeat_interleave(MX_BLOCK, dim=1)[:, :C]
+    return (q.float() * scale).to(dtype)
+
+
+def mxfp8_gemm_nt(xq, xs, wq, ws, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """Emulated MXFP8 GEMM: both operands carry 1x32 scales along K; fp32 accumulation."""
+    return (dequantize_mx(xq, xs) @ dequantize_mx(wq, ws).t()).to(out_dtype)
