@@ -99,7 +99,9 @@ class _ToLocal(torch.autograd.Function):
         return DTensor(grad, gspec, requires_grad=grad.requires_grad), None
 
 
-_IMPLICIT_REPLICATION = [False]
+from . import dispatch as _dispatch_mod  # noqa: E402
+
+_IMPLICIT_REPLICATION = _dispatch_mod._IMPLICIT_REPLICATION  # one shared flag cell
 
 
 class defer_resharding:
@@ -179,9 +181,7 @@ class DTensor(torch.Tensor):
 
     @classmethod
     def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
-        from .dispatch import dispatcher
-
-        return dispatcher.dispatch(func, args, kwargs or {})
+        return _dispatch_mod.dispatcher.dispatch(func, args, kwargs or {})
 
     # ------------------------------------------------------------------ properties
     @property
@@ -277,6 +277,9 @@ class DTensor(torch.Tensor):
                 return t
         raise ValueError(f"no local shard at offset {want} for {self._spec}")
 
+
+
+_dispatch_mod.DTensor = DTensor  # late binding for the dispatcher's hot path
 
 def from_local(local_tensor, device_mesh=None, placements=None, **kw) -> DTensor:
     return DTensor.from_local(local_tensor, device_mesh, placements, **kw)

@@ -37,7 +37,7 @@ class OpSchema:
     """``args_schema`` / ``kwargs_schema`` mirror the call with specs in place of DTensors.
     Lists of DTensors (foreach ops, cat) become tuples of specs."""
 
-    __slots__ = ("op", "args_schema", "kwargs_schema", "_hash", "mesh")
+    __slots__ = ("op", "args_schema", "kwargs_schema", "_hash", "_key", "mesh")
 
     def __init__(self, op, args_schema: Tuple[Any, ...], kwargs_schema: Dict[str, Any], mesh=None):
         self.op = op
@@ -45,19 +45,23 @@ class OpSchema:
         self.kwargs_schema = kwargs_schema
         self.mesh = mesh
         self._hash: Optional[int] = None
+        self._key = None
+
+    def _frozen(self):
+        """(op, hashable args, hashable kwargs), computed once: this is the propagation-cache key and sits on the eager
+        dispatch hot path (one hash + one equality per op)."""
+        k = self._key
+        if k is None:
+            k = self._key = (self.op, _freeze(self.args_schema), _freeze(self.kwargs_schema) if self.kwargs_schema else ())
+        return k
 
     def __hash__(self) -> int:
         if self._hash is None:
-            self._hash = hash((self.op, _freeze(self.args_schema), _freeze(self.kwargs_schema)))
+            self._hash = hash(self._frozen())
         return self._hash
 
     def __eq__(self, other) -> bool:
-        return (
-            isinstance(other, OpSchema)
-            and self.op == other.op
-            and _freeze(self.args_schema) == _freeze(other.args_schema)
-            and _freeze(self.kwargs_schema) == _freeze(other.kwargs_schema)
-        )
+        return isinstance(other, OpSchema) and (self is other or self._frozen() == other._frozen())
 
     def tensor_specs(self) -> List[DTensorSpec]:
         """All specs in call order (lists flattened)."""
