@@ -51,6 +51,7 @@ class _Chunk:
 
 
 class SymmArena:
+    """Growable pool of peer-mapped device memory with a signal pad (see the module docstring)."""
     def __init__(self, group, device: torch.device, chunk_bytes: int = 1 << 30):
         import torch.distributed._symmetric_memory as symm_mem
 

@@ -30,6 +30,7 @@ _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
 class SymmCollectives:
+    """Tensor collectives of one mesh dim over the shared symmetric arena (see the module docstring)."""
     def __init__(self, mesh, mesh_dim=0, device: Optional[torch.device] = None):
         md = mesh._dim_index(mesh_dim)
         dev = device or torch.device("cuda", torch.cuda.current_device())

@@ -17,6 +17,7 @@ __all__ = ["DebugLogger", "set_vescale_debug_mode"]
 
 
 class DebugLogger:
+    """Logs every mesh collective and every dispatched DTensor op (legacy ``debug/debug_log.py:40-361``)."""
     enabled = False
     ranks: Optional[Sequence[int]] = None
     logger: Optional[logging.Logger] = None

@@ -12,6 +12,7 @@ __all__ = ["VeDeviceMesh", "VESCALE_DEVICE_MESH"]
 
 
 class VeDeviceMesh:
+    """Singleton nD mesh registry with strategy-name lookups (PP / DP / TP ...), legacy ``devicemesh_api/api.py:36-475``."""
     def __init__(self):
         self._mesh: Optional[DeviceMesh] = None
         self._names: Tuple[str, ...] = ()

@@ -144,6 +144,9 @@ class implicit_replication:
 
 
 class DTensor(torch.Tensor):
+    """A tensor distributed over a ``DeviceMesh`` according to one ``Placement`` per mesh dim.  Wrapper subclass
+    (``_make_wrapper_subclass``) around the local shard with its own ``__torch_dispatch__`` → ``OpDispatcher`` → sharding rules;
+    no torch-private DTensor machinery.  Parity: reference ``vescale/dtensor/_api.py:221-586`` and legacy ``dtensor/dtensor.py:268-558``."""
     _local_tensor: torch.Tensor
     _spec: DTensorSpec
     __slots__ = ["_local_tensor", "_spec"]

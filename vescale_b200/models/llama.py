@@ -80,6 +80,10 @@ def llama_flops_per_token(cfg: LlamaConfig, seq_len: int) -> float:
 
 
 class LlamaBlock(nn.Module):
+    """Pre-norm decoder block with packed q|k|v and gate|up weights: four GEMMs, fused add+norm+GEMM and SwiGLU+GEMM autograd
+    nodes, RoPE in place, cuDNN attention.  Takes and returns ``(h, delta)`` — the residual stream and the branch output not yet
+    added — so the residual add fuses into the next norm."""
+
     fsdp_first_gemm_param = "wqkv"  # fully_shard(..., fuse_first_gemm=True): the weight of the block's first GEMM
 
     def __init__(self, cfg: LlamaConfig, layer_idx: int, device=None):
@@ -131,6 +135,7 @@ class LlamaBlock(nn.Module):
 
 
 class LlamaEmbedding(nn.Module):
+    """Token embedding whose backward scatters straight into the FSDP gradient buffer (``EmbeddingFn``)."""
     def __init__(self, cfg: LlamaConfig, device=None):
         super().__init__()
         self.cfg = cfg
@@ -187,6 +192,7 @@ class LlamaHead(nn.Module):
 
 
 class LlamaModel(nn.Module):
+    """Llama-3 decoder stack; ``forward(tokens, labels)`` returns the mean token loss (or logits without labels)."""
     def __init__(self, cfg: LlamaConfig, device=None):
         super().__init__()
         self.cfg = cfg

@@ -35,6 +35,7 @@ class MixtralConfig(LlamaConfig):
 
 
 class MixtralBlock(nn.Module):
+    """Llama attention half-block + MoE feed-forward (``parallel.moe.MoELayer``)."""
     def __init__(self, cfg: MixtralConfig, layer_idx: int, ep_group=None, device=None):
         super().__init__()
         self.cfg = cfg
@@ -64,6 +65,7 @@ class MixtralBlock(nn.Module):
 
 
 class MixtralModel(nn.Module):
+    """Mixtral-style sparse decoder; experts are expert-parallel over ``ep_group``."""
     def __init__(self, cfg: MixtralConfig, ep_group=None, device=None):
         super().__init__()
         self.cfg = cfg

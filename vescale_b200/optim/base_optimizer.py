@@ -14,6 +14,7 @@ __all__ = ["BasicOptimizer", "GradOptimizerHookBase", "BasicOptimizerHook"]
 
 
 class GradOptimizerHookBase:
+    """Hooks run before / after ``optimizer.step`` (legacy ``optim/base_optimizer.py:30-43``)."""
     @staticmethod
     def step_pre_hook(optim, *a, **kw):
         raise NotImplementedError
@@ -44,6 +45,8 @@ class BasicOptimizerHook(GradOptimizerHookBase):
 
 
 class BasicOptimizer:
+    """Thin wrapper that finishes DModule / DDP gradient synchronisation, exposes ``main_grad`` as ``.grad``, clips, and steps the
+    inner ``torch.optim`` optimizer (legacy ``optim/base_optimizer.py:116-206``)."""
     def __init__(self, optimizer: torch.optim.Optimizer, models: Union[nn.Module, Sequence[nn.Module]], grad_hook: Optional[GradOptimizerHookBase] = None, clip_grad: float = 0.0):
         self.optimizer = optimizer
         self.models = [models] if isinstance(models, nn.Module) else list(models)

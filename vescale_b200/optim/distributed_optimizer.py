@@ -53,6 +53,9 @@ class _BucketShard:
 
 
 class DistributedOptimizer:
+    """ZeRO-2+ wrapper: every DDP bucket is sharded evenly over the DP group, fp32 main-parameter shards are updated by the inner
+    optimizer and all-gathered back into the (aliased) parameter buffer, optionally overlapped with the next forward; the state
+    dict is expressed as ``OptimizerStateSpec``s so it reshards on load.  Parity: legacy ``optim/distributed_optimizer.py:131-1296``."""
     def __init__(
         self,
         optimizer: torch.optim.Optimizer,

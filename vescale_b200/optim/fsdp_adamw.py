@@ -25,6 +25,7 @@ __all__ = ["FSDPAdamW"]
 
 
 class FSDPAdamW:
+    """See the module docstring.  ``tp_group`` / ``replicate_group`` add the 2-D cases (FSDP × TP, HSDP)."""
     def __init__(
         self,
         model: torch.nn.Module,

@@ -36,6 +36,7 @@ def _local(t):
 
 
 class Bucket:
+    """A contiguous slice of a ``GradBuffer``: the unit of gradient all-reduce / reduce-scatter (legacy ``ddp/grad_buffer.py:27-200``)."""
     def __init__(self, params: List[nn.Parameter], data: torch.Tensor, offset: int, group, dp_size: int, overlap: bool, use_distributed_optimizer: bool):
         self.params = params
         self.params_set = {id(p) for p in params}
@@ -84,6 +85,8 @@ class Bucket:
 
 
 class GradBuffer:
+    """One flat gradient buffer per dtype; parameters get ``main_grad`` views laid out in reverse order so buckets fill in backward
+    order (legacy ``ddp/grad_buffer.py:226-494``)."""
     def __init__(self, dtype, params: List[nn.Parameter], group, dp_size: int, bucket_size: Optional[int], overlap: bool, use_distributed_optimizer: bool, device):
         self.dtype = dtype
         self.group = group
@@ -140,6 +143,9 @@ class GradBuffer:
 
 
 class DistributedDataParallel(nn.Module):
+    """Megatron-style data parallelism over a flat ``GradBuffer``: backward hooks accumulate into ``main_grad``, full buckets are
+    all-reduced (or reduce-scattered for ``DistributedOptimizer``) as soon as they are complete when ``overlap_grad_reduce``;
+    ``no_sync()`` for accumulation.  Parity: legacy ``ddp/distributed_data_parallel.py:20-336``."""
     def __init__(
         self,
         module: nn.Module,

@@ -34,6 +34,7 @@ __all__ = ["FSDPUnit", "MixedPrecisionPolicy"]
 
 
 class MixedPrecisionPolicy:
+    """dtypes of the gathered compute parameters, the reduced gradients and the sharded master weights."""
     def __init__(self, param_dtype: Optional[torch.dtype] = torch.bfloat16, reduce_dtype: Optional[torch.dtype] = torch.float32, master_dtype: torch.dtype = torch.float32):
         self.param_dtype = param_dtype
         self.reduce_dtype = reduce_dtype
@@ -70,6 +71,9 @@ def make_event(device: torch.device):
 
 
 class FSDPUnit:
+    """One FSDP unit = the parameters of one wrapped module in a flat ``UnitLayout`` buffer: fp32 master shard (exposed as
+    RaggedShard DTensor parameters), bf16 shard in symmetric memory (all-gather source), gathered compute views, flat gradient
+    buffer with ``main_grad`` views."""
     def __init__(
         self,
         module: nn.Module,

@@ -65,12 +65,14 @@ def ragged_token_placement(tokens_per_rank: Sequence[int]) -> RaggedShard:
 
 
 class MoEConfig:
+    """Sizes and routing hyper-parameters of one MoE layer (Mixtral: 8 experts, top-2)."""
     def __init__(self, hidden_size: int, ffn_size: int, num_experts: int = 8, top_k: int = 2, ep_size: int = 1, dtype=torch.bfloat16, init_std: float = 0.02, comm_backend: str = "nccl", aux_loss_coef: float = 0.0):
         self.hidden_size, self.ffn_size, self.num_experts, self.top_k = hidden_size, ffn_size, num_experts, top_k
         self.ep_size, self.dtype, self.init_std, self.comm_backend, self.aux_loss_coef = ep_size, dtype, init_std, comm_backend, aux_loss_coef
 
 
 class TopKRouter(nn.Module):
+    """Softmax router returning (top-k weights renormalised, top-k expert ids, full probabilities)."""
     def __init__(self, cfg: MoEConfig, device=None):
         super().__init__()
         self.cfg = cfg
@@ -112,6 +114,8 @@ class GroupedExperts(nn.Module):
 
 
 class MoELayer(nn.Module):
+    """Expert-parallel MoE layer: route → dispatch (NCCL all-to-all with host-side split sizes, or the device-side symmetric
+    dispatcher) → grouped expert GEMMs → combine.  Parity: legacy ``moe/_scheduler.py:162-277``."""
     def __init__(self, cfg: MoEConfig, ep_group=None, device=None):
         super().__init__()
         self.cfg = cfg

@@ -36,6 +36,8 @@ def _as_tuple(x):
 
 
 class ScheduleEngine:
+    """Interprets this rank's row of the global instruction schedule: receives right before, sends right after each F / B / W
+    instruction (legacy ``pipe/pipe_emmiter.py:132-343``)."""
     def __init__(self, module: PipeModule, plan: PipelineParallelPlan, pp_rank: int, pp_group, loss_fn: Optional[Callable], device):
         self.module, self.plan, self.rank, self.group, self.loss_fn, self.device = module, plan, pp_rank, pp_group, loss_fn, device
         self.P, self.V = plan.num_stages, plan.virtual_chunks
@@ -142,6 +144,8 @@ class ScheduleEngine:
 
 
 class PipeEngine:
+    """``engine(minibatch, labels) -> (loss, outputs)``: runs one pipeline-parallel mini-batch under the plan's schedule (legacy
+    ``engine/pipe.py:33-237``)."""
     def __init__(self, module: PipeModule, global_mesh=None, loss_fn: Optional[Callable] = None, plan: Optional[PipelineParallelPlan] = None, *, pp_group=None, pp_rank: Optional[int] = None, device=None):
         self.module = module
         self.plan = plan or module.plan

@@ -26,6 +26,7 @@ __all__ = ["NDTimerManager", "NDMetricLevel", "init_ndtimers", "ndtimeit", "ndti
 
 
 class NDMetricLevel(IntEnum):
+    """Verbosity filter of timed regions (legacy ``ndtimeline/timer.py:154``)."""
     FRAMEWORK_INFO = 2
     USER_INFO = 3
     INFO = 4
@@ -49,6 +50,7 @@ class _EventPool:
 
 
 class NDTimerManager:
+    """Pooled CUDA-event timers on a cross-rank aligned clock with asynchronous flush to handlers (legacy ``ndtimeline/timer.py:410-665``)."""
     def __init__(self, rank: int = 0, world_size: int = 1, handlers: Sequence[NDHandler] = (), level: NDMetricLevel = NDMetricLevel.TRACE, group=None):
         self.rank, self.world_size = rank, world_size
         self.handlers = list(handlers)
