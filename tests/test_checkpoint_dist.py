@@ -259,3 +259,72 @@ def test_checkpoint_reshards_across_world_sizes(tmp_path):
     """Save on 4 ranks, resume on 2 (reference ``checkpoint/open_llama/test_open_llama_dp_reshard.py`` strategy)."""
     run_distributed(_save_ws, 4, str(tmp_path))
     run_distributed(_load_ws, 2, str(tmp_path))
+
+
+class _MLP(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(16, 48)
+        self.n = torch.nn.LayerNorm(48)
+        self.b = torch.nn.Linear(48, 16)
+
+    def forward(self, x):
+        return self.b(self.n(torch.relu(self.a(x))))
+
+
+def _dopt_batch(step):
+    g = torch.Generator().manual_seed(step)
+    return torch.randn(8, 16, generator=g), torch.randn(8, 16, generator=g)
+
+
+def _dopt_build(dev, bucket):
+    from vescale_b200.optim import DistributedOptimizer
+    from vescale_b200.parallel.ddp import DistributedDataParallel as DDP
+
+    torch.manual_seed(0)
+    model = _MLP().to(dev)
+    ddp = DDP(model, dist.group.WORLD, overlap_grad_reduce=False, use_distributed_optimizer=True, bucket_size=bucket)
+    opt = DistributedOptimizer(torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.05), [ddp])
+    return model, ddp, opt
+
+
+def _dopt_step(ddp, opt, step, dev):
+    x, y = _dopt_batch(step)  # same batch on every rank: the trajectory does not depend on the DP size
+    opt.zero_grad()
+    torch.nn.functional.mse_loss(ddp(x.to(dev)), y.to(dev)).backward()
+    opt.step()
+
+
+def _dopt_save(rank, world, path):
+    import vescale_b200.checkpoint as ckpt
+
+    dev = device_type()
+    model, ddp, opt = _dopt_build(dev, bucket=500)
+    for s in range(2):
+        _dopt_step(ddp, opt, s, dev)
+    ckpt.save(os.path.join(path, "ckpt"), {"model": model, "optimizer": opt})
+    _dopt_step(ddp, opt, 2, dev)
+    if rank == 0:
+        torch.save({n: p.detach().cpu() for n, p in model.named_parameters()}, os.path.join(path, "golden.pt"))
+
+
+def _dopt_load(rank, world, path):
+    """Different DP size *and* bucket size: every parameter's moments are split over the ranks differently than when saved."""
+    import vescale_b200.checkpoint as ckpt
+
+    dev = device_type()
+    model, ddp, opt = _dopt_build(dev, bucket=1300)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(1.0)  # make sure the load really restores the weights
+    ckpt.load(os.path.join(path, "ckpt"), {"model": model, "optimizer": opt})
+    _dopt_step(ddp, opt, 2, dev)
+    gold = torch.load(os.path.join(path, "golden.pt"))
+    for n, p in model.named_parameters():
+        torch.testing.assert_close(p.detach().cpu(), gold[n], rtol=1e-5, atol=1e-6, msg=n)
+
+
+def test_distributed_optimizer_state_reshards_across_dp_sizes(tmp_path):
+    """ZeRO-2+ optimizer state saved on 4 DP ranks resumes on 2 (legacy ``test_open_llama_dp_reshard.py`` strategy)."""
+    run_distributed(_dopt_save, 4, str(tmp_path))
+    run_distributed(_dopt_load, 2, str(tmp_path))

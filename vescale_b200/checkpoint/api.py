@@ -64,6 +64,10 @@ def _flatten(prefix: str, obj, out: Dict[str, Any]) -> None:
 def _state_of(obj) -> Dict[str, Any]:
     if isinstance(obj, nn.Module):
         return dict(obj.state_dict())
+    if hasattr(obj, "checkpoint_state"):  # objects that expose a resharding (DTensor) view of their state, e.g. DistributedOptimizer
+        flat: Dict[str, Any] = {}
+        _flatten("", obj.checkpoint_state(), flat)
+        return flat
     if hasattr(obj, "state_dict"):
         flat: Dict[str, Any] = {}
         _flatten("", obj.state_dict(), flat)
@@ -179,6 +183,10 @@ class VeScaleCheckpointer:
                 dcp.load(req, **_storage(sub, False))  # in place: DTensor / tensor storages are filled with the resharded data
             if isinstance(obj, nn.Module):
                 pass  # state_dict tensors alias the module's parameters/buffers
+            elif hasattr(obj, "load_checkpoint_state"):
+                ex = req.get("__extras__", {}) or {}
+                steps = {k[len("__steps__.") :]: v for k, v in ex.items() if k.startswith("__steps__.")}
+                obj.load_checkpoint_state({**{k: v for k, v in req.items() if k != "__extras__"}, "__steps__": steps})
             elif hasattr(obj, "load_state_dict") and not isinstance(obj, dict):
                 full = obj.state_dict()
                 _assign(full, req)
