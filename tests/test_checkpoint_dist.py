@@ -328,3 +328,55 @@ def test_distributed_optimizer_state_reshards_across_dp_sizes(tmp_path):
     """ZeRO-2+ optimizer state saved on 4 DP ranks resumes on 2 (legacy ``test_open_llama_dp_reshard.py`` strategy)."""
     run_distributed(_dopt_save, 4, str(tmp_path))
     run_distributed(_dopt_load, 2, str(tmp_path))
+
+
+class _GPTBlock(torch.nn.Module):
+    def __init__(self, h=32):
+        super().__init__()
+        self.ln_1 = torch.nn.LayerNorm(h)
+        self.c_fc = torch.nn.Linear(h, 4 * h)
+        self.c_proj = torch.nn.Linear(4 * h, h)
+
+    def forward(self, x):
+        return x + self.c_proj(torch.nn.functional.gelu(self.c_fc(self.ln_1(x))))
+
+
+def _tp_model(dev, seed):
+    from vescale_b200 import Replicate, init_device_mesh
+    from vescale_b200.parallel.dmp import auto_parallelize_module
+
+    mesh = init_device_mesh(dev, (dist.get_world_size(),), mesh_dim_names=("TP",))
+    torch.manual_seed(seed)
+    model = torch.nn.Sequential(_GPTBlock(), _GPTBlock()).to(dev)
+    for blk in model:
+        auto_parallelize_module(blk, mesh, "MEGATRON", plan_override={"forward": {r"input": [[Replicate()]], r"c_proj\.output": [[Replicate()]]}})
+    return model
+
+
+def _tp_save(rank, world, path):
+    import vescale_b200.checkpoint as ckpt
+
+    dev = device_type()
+    model = _tp_model(dev, seed=0)
+    x = torch.randn(3, 5, 32, generator=torch.Generator().manual_seed(1)).to(dev)
+    y = model(x)
+    ckpt.save(os.path.join(path, "ckpt"), {"model": model})
+    if rank == 0:
+        torch.save(y.full_tensor().detach().cpu(), os.path.join(path, "y.pt"))
+
+
+def _tp_load(rank, world, path):
+    import vescale_b200.checkpoint as ckpt
+
+    dev = device_type()
+    model = _tp_model(dev, seed=123)  # different weights, different TP degree
+    ckpt.load(os.path.join(path, "ckpt"), {"model": model})
+    x = torch.randn(3, 5, 32, generator=torch.Generator().manual_seed(1)).to(dev)
+    torch.testing.assert_close(model(x).full_tensor().detach().cpu(), torch.load(os.path.join(path, "y.pt")), rtol=1e-5, atol=1e-6)
+
+
+def test_dmodule_checkpoint_reshards_across_tp_degrees(tmp_path):
+    """A DModule (auto-planned TP/SP) saved at TP=4 reloads at TP=2 and computes the same function
+    (legacy ``dmodule/test_saveload.py`` + ``checkpoint/open_llama/test_open_llama_tp_reshard.py``)."""
+    run_distributed(_tp_save, 4, str(tmp_path))
+    run_distributed(_tp_load, 2, str(tmp_path))
