@@ -66,3 +66,55 @@ def _run(rank, world, use_dopt, overlap_grad, overlap_gather):
 @pytest.mark.parametrize("use_dopt,overlap_grad,overlap_gather", [(False, True, False), (True, True, False), (True, False, True), (True, True, True)])
 def test_ddp_optimizers_match_single_process(use_dopt, overlap_grad, overlap_gather):
     run_distributed(_run, 4, use_dopt, overlap_grad, overlap_gather)
+
+
+class Tied(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.emb = nn.Embedding(20, 16)
+        self.mid = nn.Linear(16, 16)
+        self.head = nn.Linear(16, 20, bias=False)
+        self.head.weight = self.emb.weight
+
+    def forward(self, ids):
+        return self.head(torch.tanh(self.mid(self.emb(ids))))
+
+
+def _tied(rank, world):
+    """Tied embedding / lm-head under DDP with BasicOptimizer and with DistributedOptimizer (legacy ``test_shared_weight.py``)."""
+    from vescale_b200.optim import BasicOptimizer, DistributedOptimizer
+    from vescale_b200.parallel.ddp import DistributedDataParallel as DDP
+
+    dev = device_type()
+    for use_dopt in (False, True):
+        torch.manual_seed(0)
+        ref = Tied().to(dev)
+        model = copy.deepcopy(ref)
+        assert model.head.weight is model.emb.weight
+        ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+        ddp = DDP(model, dist.group.WORLD, overlap_grad_reduce=True, use_distributed_optimizer=use_dopt, bucket_size=300)
+        inner = torch.optim.SGD(model.parameters(), lr=0.1)
+        opt = DistributedOptimizer(inner, [ddp]) if use_dopt else BasicOptimizer(inner, [ddp])
+        for step in range(2):
+            ref_opt.zero_grad()
+            for r in range(world):
+                g = torch.Generator().manual_seed(10 * step + r)
+                ids = torch.randint(0, 20, (4, 6), generator=g).to(dev)
+                tgt = torch.randint(0, 20, (4, 6), generator=g).to(dev)
+                (torch.nn.functional.cross_entropy(ref(ids).view(-1, 20), tgt.view(-1)) / world).backward()
+            ref_opt.step()
+            g = torch.Generator().manual_seed(10 * step + rank)
+            ids = torch.randint(0, 20, (4, 6), generator=g).to(dev)
+            tgt = torch.randint(0, 20, (4, 6), generator=g).to(dev)
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(ddp(ids).view(-1, 20), tgt.view(-1)).backward()
+            opt.step()
+            if use_dopt:
+                opt.finish_param_gather()
+        for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-4, atol=1e-6, msg=f"{use_dopt} {n}")
+        assert model.head.weight.data_ptr() == model.emb.weight.data_ptr()
+
+
+def test_ddp_tied_weights():
+    run_distributed(_tied, 4)
