@@ -75,6 +75,35 @@ def _tp_sp(rank, world):
         torch.testing.assert_close(p.grad.full_tensor(), q.grad, rtol=1e-4, atol=1e-5, msg=n)
 
 
+    # ---- factory mode: tensors created inside forward become DTensors; modules may return dicts / tuples of DTensors
+    # (legacy ``dmodule/test_dfactory.py``, ``test_obj_return.py``)
+    class WithFactory(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(32, 32)
+
+        def forward(self, x):
+            y = self.fc(x)
+            bias = torch.ones(y.shape[-1], device=y.device if not isinstance(y, DTensor) else None)  # created inside forward
+            return {"out": y + bias, "aux": (y * 2, 3)}
+
+    torch.manual_seed(1)
+    ref2 = WithFactory().to(dev)
+    m2 = copy.deepcopy(ref2)
+    parallelize_module(
+        m2, mesh,
+        {"parameter": {r"fc\.weight": [Shard(0)], r"fc\.bias": [Shard(0)]}, "forward": {r"input": [[Replicate()]], r"fc\.output": [[Replicate()]]}},
+        factory=True,
+    )
+    res = m2(x)
+    want = ref2(x)
+    assert isinstance(res, dict) and isinstance(res["aux"], tuple) and res["aux"][1] == 3
+    got_out = res["out"].full_tensor() if isinstance(res["out"], DTensor) else res["out"]
+    got_aux = res["aux"][0].full_tensor() if isinstance(res["aux"][0], DTensor) else res["aux"][0]
+    torch.testing.assert_close(got_out, want["out"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got_aux, want["aux"][0], rtol=1e-4, atol=1e-5)
+
+
 def _deferred(rank, world):
     import vescale_b200.dtensor as vd
     from vescale_b200 import Replicate, Shard, init_device_mesh
