@@ -35,7 +35,7 @@ inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
 // ------------------------------------------------------------------------------------------------- signalling
 // Pad layout (uint32): slot-major, [slot][src_rank].  Rank r signals slot s by writing `epoch` into
 // peer_pad[s*W + r] on every peer; waiting means spinning on my own pad until all W entries reach `epoch`.
-__global__ void signal_all_kernel(const __grid_constant__ PeerFlags pads, int world, int rank, int slot, uint32_t epoch) {
+__global__ void signal_all_kernel(PeerFlags pads, int world, int rank, int slot, uint32_t epoch) {
   const int p = threadIdx.x;
   if (p < world) {
     __threadfence_system();
@@ -89,8 +89,8 @@ VB_DEVICE void pull_range(const uint4* __restrict__ src, uint4* __restrict__ dst
 // range_mode 0: whole unit.  1: only global vectors [range_lo, range_hi) (small parameters needed before the fused first
 // GEMM).  2: everything except that range (the weight the fused AG⊕GEMM kernel gathers itself).
 template <int UNROLL>
-__global__ void __launch_bounds__(512) all_gather_pull_kernel(const __grid_constant__ PeerPtrs shards, uint4* __restrict__ full, size_t vec_per_shard, int world, int rank,
-                                                              const __grid_constant__ PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch, int use_flags,
+__global__ void __launch_bounds__(512) all_gather_pull_kernel(PeerPtrs shards, uint4* __restrict__ full, size_t vec_per_shard, int world, int rank,
+                                                              PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch, int use_flags,
                                                               int range_mode, size_t range_lo, size_t range_hi) {
   if (use_flags) block_signal_then_wait(pads, my_pad, world, rank, slot, epoch, true);
   for (int pi = 0; pi < world; ++pi) {
@@ -137,9 +137,9 @@ struct AdamArgs {
 
 // MODE 0: write fp32 grad shard + sumsq.   MODE 1: feed AdamW directly (grad never stored).
 template <int MODE, int WORLD>
-__global__ void __launch_bounds__(512) reduce_scatter_fused_kernel(const __grid_constant__ PeerPtrs grads, size_t shard_off_vec, float* __restrict__ out, float* __restrict__ sumsq,
-                                                                   size_t nvec, int rank, float scale, const __grid_constant__ PeerFlags pads, const uint32_t* my_pad,
-                                                                   int slot, uint32_t epoch, const __grid_constant__ AdamArgs ad) {
+__global__ void __launch_bounds__(512) reduce_scatter_fused_kernel(PeerPtrs grads, size_t shard_off_vec, float* __restrict__ out, float* __restrict__ sumsq,
+                                                                   size_t nvec, int rank, float scale, PeerFlags pads, const uint32_t* my_pad,
+                                                                   int slot, uint32_t epoch, AdamArgs ad) {
   __shared__ float red[33];
   __shared__ int64_t seg[64 * 3];
   // wait until every peer has finished producing this bucket's gradients (and tell them mine are done)
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(512) reduce_scatter_fused_kernel(const __grid_
 // NVLS: the switch performs the W-way reduction; each GPU receives only its reduced slice.
 __global__ void __launch_bounds__(512) reduce_scatter_multimem_kernel(const void* mc_base, size_t shard_off_vec, float* __restrict__ out,
                                                                       float* __restrict__ sumsq, size_t nvec, int world, int rank, float scale,
-                                                                      const __grid_constant__ PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch) {
+                                                                      PeerFlags pads, const uint32_t* my_pad, int slot, uint32_t epoch) {
   __shared__ float red[33];
   block_signal_then_wait(pads, my_pad, world, rank, slot, epoch, true);
   float ss = 0.f;

@@ -59,3 +59,12 @@ def dropout_provider(fqn, module, root):
     if isinstance(module, nn.Dropout):
         return {"parameter": {}, "forward": {}}
     return None
+
+
+@register_provider("MEGATRON")
+def conv_provider(fqn, module, root):
+    """Convolutions stay replicated under the MEGATRON policy (empty plan; their parameters become Replicate
+    DTensors through the default-placement pass)."""
+    if "conv" in type(module).__name__.lower():
+        return {"parameter": {}, "forward": {}}
+    return None
