@@ -1,0 +1,150 @@
+"""GPU tests added after the last hardware session of round 1 (fp8 GEMM path, fused sharded dropout kernel, world-size-1
+run of the symmetric-memory kernels).  Kept in a file that sorts after the others so that ``pytest -x`` reaches every
+hardware-validated test first; same conventions as ``test_kernels_gpu.py``."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fp8_block_scaled_gemm_on_cuda():
+    """fp8 forward GEMM on the GPU (cuBLASLt through torch._scaled_mm when the build accepts the scale layout, emulation
+    otherwise) against the fp32 product; the emulated path is the numerics specification."""
+    from vescale_b200.ops import fp8
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(512, 1024, device=dev, generator=g).bfloat16()
+    w = (torch.randn(768, 1024, device=dev, generator=g) * 0.05).bfloat16()
+    ref = x.float() @ w.float().t()
+    xq, xs = fp8.quantize_blockwise(x, (1, 128))
+    wq, ws = fp8.quantize_blockwise(w, (128, 128))
+    emu = fp8._emulated_gemm_nt(xq, xs, wq, ws, torch.float32)
+    assert ((emu - ref).norm() / ref.norm()).item() < 0.05
+    got = fp8.fp8_gemm_nt(xq, xs, wq, ws, torch.bfloat16).float()
+    assert ((got - ref).norm() / ref.norm()).item() < 0.08
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    fp8.fp8_linear(xr, wr).float().sum().backward()
+    assert xr.grad is not None and wr.grad is not None and torch.isfinite(xr.grad.float()).all()
+
+
+def test_fused_sharded_dropout_matches_composite():
+    """The fused Philox dropout kernel draws the same mask and values as the specification path (uniform fill, compare,
+    scale), for a full tensor and for a shard of it viewed through a fake 4-rank mesh."""
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200.dtensor import DTensor
+    from vescale_b200.dtensor import random as R
+    from vescale_b200.ops import philox
+
+    if not philox.dropout_available():
+        pytest.skip("extension built without philox_dropout_box")
+    dev = torch.device("cuda")
+    full = torch.randn(64, 96, device=dev).bfloat16()
+    outs = {}
+    for rank in (0, 2):
+        mesh = init_device_mesh("cuda", (4,), _rank=rank, _init_process_groups=False)
+        for pl in ([Replicate()], [Shard(0)], [Shard(1)]):
+            local = full if isinstance(pl[0], Replicate) else full.chunk(4, dim=pl[0].dim)[rank].contiguous()
+            spec = DTensor.from_local(local, mesh, pl, run_check=False)._spec
+            tr = R.ThreadBasedRNGTracker()
+            R.manual_seed(123)
+            fused_out, fused_mask = tr.run(torch.ops.aten.native_dropout.default, [local, 0.3, True], {}, spec)
+            R.manual_seed(123)
+            u = R.sharded_random_fill(torch.empty(local.shape, dtype=torch.float32, device=dev), spec, "uniform")
+            mask = u >= 0.3
+            ref = local * mask.to(local.dtype) * (1.0 / 0.7)
+            assert torch.equal(fused_mask, mask) and torch.equal(fused_out, ref), (rank, pl)
+            outs[(rank, str(pl))] = (fused_out, fused_mask)
+    # shards agree with the replicated result at their global positions
+    rep_out, rep_mask = outs[(0, str([Replicate()]))]
+    assert torch.equal(outs[(2, str([Shard(0)]))][0], rep_out.chunk(4, 0)[2]) and torch.equal(outs[(2, str([Shard(1)]))][1], rep_mask.chunk(4, 1)[2])
+    assert 0.2 < (~rep_mask).float().mean().item() < 0.4
+
+
+def test_symmetric_memory_kernels_single_rank(tmp_path):
+    """World-size-1 run of the symmetric-memory / fused-collective kernels on one GPU: every peer table has one entry (this
+    GPU), so the flag protocols, copy engines and epilogues execute end to end and must reproduce the plain single-device
+    result.  (The multi-GPU behaviour is covered by tests/test_symm_multigpu.py on >= 2 GPUs.)"""
+    import torch.distributed as dist
+
+    from vescale_b200 import init_device_mesh
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    created = False
+    try:
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", init_method=f"file://{tmp_path}/store", rank=0, world_size=1, device_id=dev)
+            created = True
+        mesh = init_device_mesh("cuda", (1,))
+        from vescale_b200.comm.fused_tp import FusedTP
+        from vescale_b200.comm.symm_collectives import SymmCollectives
+
+        sc = SymmCollectives(mesh, 0, dev)
+        tp = FusedTP(mesh, 0, dev)
+    except Exception as e:  # noqa: BLE001  — symmetric memory unavailable in this environment
+        if created:
+            dist.destroy_process_group()
+        pytest.skip(f"symmetric memory not available for a single-rank group: {type(e).__name__}: {e}")
+    try:
+        g = torch.Generator(device=dev).manual_seed(0)
+        # all-reduce: one-shot, two-shot P2P, two-shot NVLS (if a multicast mapping exists), zero-copy
+        for n in (1000, 1 << 20):
+            x = torch.randn(n, device=dev, generator=g).bfloat16()
+            for mm in (False, True):
+                sc.use_multimem = mm
+                torch.testing.assert_close(sc.all_reduce(x.clone(), "sum").float(), x.float(), rtol=1e-2, atol=1e-2)
+            xs = sc.empty(n)
+            xs.copy_(x)
+            torch.testing.assert_close(sc.all_reduce(xs, "avg").float(), x.float(), rtol=1e-2, atol=1e-2)
+        # Shard(i) -> Shard(j) with one rank is the identity; ragged exchange likewise
+        t = torch.randn(4, 6, 8, device=dev, generator=g).bfloat16()
+        assert torch.equal(sc.all_to_all_permute(t, 0, 2), t) and torch.equal(sc.all_to_all_permute(t, 2, 1), t)
+        flat = torch.randn(4096, device=dev, generator=g)
+        assert torch.equal(sc.ragged_exchange(flat, [(0, 4096)], [(0, 4096)]), flat)
+        # vocab-parallel CE with the whole vocabulary local == ordinary CE
+        T, V = 300, 1024
+        logits = (torch.randn(T, V, device=dev, generator=g) * 3).bfloat16()
+        target = torch.randint(0, V, (T,), device=dev, generator=g)
+        target[::7] = -100
+        ref_l = logits.float().requires_grad_()
+        ref = torch.nn.functional.cross_entropy(ref_l, target, ignore_index=-100)
+        ref.backward()
+        buf = logits.clone()
+        loss = sc.vocab_parallel_cross_entropy(buf.requires_grad_() * 1.0, target)
+        assert abs(loss.item() - ref.item()) < 2e-3
+        # fused TP kernels: all-gather(x) @ W^T and reduce-scatter(x @ W^T) degenerate to the plain product
+        x = (torch.randn(512, 1024, device=dev, generator=g) * 0.5).bfloat16()
+        w = (torch.randn(768, 1024, device=dev, generator=g) * 0.05).bfloat16()
+        want = x.float() @ w.float().t()
+        y, x_full = tp.ag_gemm(x, w)
+        assert torch.equal(x_full, x)
+        assert (y.float() - want).abs().max().item() < 0.02 * want.abs().max().item() + 0.05
+        y2 = tp.gemm_rs(x, w)
+        assert (y2.float() - want).abs().max().item() < 0.02 * want.abs().max().item() + 0.05
+        # FSDP all-gather ⊕ first GEMM: the kernel copies the (single) shard into the gathered buffer while multiplying
+        from vescale_b200.models import LlamaConfig
+        from vescale_b200.models.llama import LlamaBlock
+        from vescale_b200.parallel.fsdp.unit import FSDPUnit, MixedPrecisionPolicy
+
+        cfg = LlamaConfig(vocab_size=2048, hidden_size=512, intermediate_size=1024, num_layers=1, num_heads=8, num_kv_heads=2, head_dim=64, max_seq_len=256)
+        blk = LlamaBlock(cfg, 0, device=dev)
+        blk.reset_parameters(g)
+        wq = blk.wqkv.detach().clone()
+        from vescale_b200.comm.symm import get_unit_comm
+
+        comm = get_unit_comm(mesh, 0, dev)
+        unit = FSDPUnit(blk, list(blk.named_parameters()), mesh, 0, MixedPrecisionPolicy(), name="blk", comm=comm, block_rows=32)
+        slot = comm.fusable_slot(unit, "wqkv")
+        assert slot is not None
+        full = torch.full((unit.S,), float("nan"), dtype=torch.bfloat16, device=dev)
+        xin = (torch.randn(512, 512, device=dev, generator=g) * 0.5).bfloat16()
+        yq = comm.fused_first_linear(xin, unit, slot, full)
+        torch.cuda.synchronize()
+        assert torch.equal(full[slot.offset : slot.end].view(slot.shape), wq)
+        wantq = xin.float() @ wq.float().t()
+        assert (yq.float() - wantq).abs().max().item() < 0.02 * wantq.abs().max().item() + 0.05
+    finally:
+        torch.cuda.synchronize()
+        if created:
+            dist.destroy_process_group()

@@ -11,6 +11,7 @@ mkdir -p gpurun_out
 step() { local name="$1" t="$2"; shift 2; echo "== $name"; timeout "$t" "$@" > "gpurun_out/validate_$name.log" 2>&1; echo "   rc=$? (log: gpurun_out/validate_$name.log)"; tail -2 "gpurun_out/validate_$name.log" | cut -c1-300; }
 
 step kernels 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu
+step late_kernels 600 python -m pytest tests/test_z_late_gpu.py -q -m gpu
 step bench_n1 400 python bench.py --steps 4 --warmup 3
 step gemm_v3 150 python benchmarks/gemm_variant3_check.py
 if [ "$N" -gt 1 ]; then
