@@ -40,7 +40,8 @@ def main():
     from vescale_b200.comm.fused_tp import FusedTP
 
     mesh = init_device_mesh("cuda", (W,), mesh_dim_names=("TP",))
-    tp = FusedTP(mesh, "TP", dev)
+    tp = FusedTP(mesh, "TP", dev, rs_impl="staged")
+    tp_nvls = FusedTP(mesh, "TP", dev, rs_impl="nvls") if os.environ.get("TP_BENCH_NVLS", "1") == "1" else None
     peak, link = 1462.2e12, 770e9
     T, H, F, QKV = 8192, 4096, 14336, 6144
     res = []
@@ -73,10 +74,16 @@ def main():
         t_f = timeit(lambda: tp.gemm_rs(x, w))
         t_b = timeit(base)
         t_mm = timeit(lambda: x @ w.t())
+        t_n, err = None, None
+        if tp_nvls is not None:  # GEMM into symmetric memory + switch-reduced pull (one multimem.ld_reduce per 16 bytes)
+            ref = base().float()
+            err = (tp_nvls.gemm_rs(x, w).float() - ref).abs().max().item() / ref.abs().max().item()
+            t_n = timeit(lambda: tp_nvls.gemm_rs(x, w))
         fl = 2.0 * M * Kr * N
         nv = (W - 1) * (M // W) * N * 2
         roof = max(fl / peak, nv / link) * 1e3
-        res.append({"op": name, "shape": [M, N, Kr], "fused_ms": t_f, "nccl_cublas_ms": t_b, "cublas_only_ms": t_mm, "roofline_ms": roof, "frac_of_roofline": roof / t_f, "speedup_vs_nccl": t_b / t_f})
+        res.append({"op": name, "shape": [M, N, Kr], "fused_ms": t_f, "nccl_cublas_ms": t_b, "cublas_only_ms": t_mm, "roofline_ms": roof, "frac_of_roofline": roof / t_f, "speedup_vs_nccl": t_b / t_f,
+                    "nvls_rs_ms": t_n, "nvls_rs_rel_err": err, "nvls_rs_speedup_vs_nccl": (t_b / t_n) if t_n else None})
     if rank == 0:
         for r in res:
             print(json.dumps(r), flush=True)

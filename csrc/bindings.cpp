@@ -33,6 +33,9 @@ void symm_rs_adamw(std::vector<int64_t> grad_ptrs, at::Tensor master, at::Tensor
                    int64_t epoch, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, int64_t num_ctas);
 
 // symm_collectives.cu
+void symm_reduce_scatter_t(std::vector<int64_t> buf_ptrs, int64_t multicast_ptr, at::Tensor out, int64_t slice_numel, int64_t row_numel, int64_t out_row_stride,
+                           int64_t dtype_code, double scale, int64_t rank, std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, at::Tensor counter,
+                           int64_t num_ctas);
 void symm_all_reduce(std::vector<int64_t> buf_ptrs, int64_t multicast_ptr, c10::optional<at::Tensor> out, int64_t numel, int64_t dtype_code, double scale,
                      int64_t rank, std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, at::Tensor counter, int64_t num_ctas);
 void symm_a2a_permute(const at::Tensor& src, std::vector<int64_t> dst_ptrs, std::vector<int64_t> n, std::vector<int64_t> ss, std::vector<int64_t> ds,
@@ -102,6 +105,7 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("symm_rs_adamw(int[] grad_ptrs, Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor(d!) p_out, Tensor wd_table, Tensor coef, Tensor(e!)? sumsq, int rank, float scale, int[] pad_ptrs, int slot, int epoch, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int num_ctas) -> ()");
   m.def("wag_gemm(Tensor x, Tensor(a!) w_full, int[] shard_ptrs, int[] row_bounds, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch, bool wait_peers=True) -> ()");
   m.def("symm_all_reduce(int[] buf_ptrs, int multicast_ptr, Tensor(a!)? out, int numel, int dtype_code, float scale, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(b!) counter, int num_ctas) -> ()");
+  m.def("symm_reduce_scatter_t(int[] buf_ptrs, int multicast_ptr, Tensor(a!) out, int slice_numel, int row_numel, int out_row_stride, int dtype_code, float scale, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(b!) counter, int num_ctas) -> ()");
   m.def("symm_a2a_permute(Tensor src, int[] dst_ptrs, int[] n, int[] ss, int[] ds, int src_peer_stride, int dst_rank_stride, int vec_bytes, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(a!) counter, int num_ctas) -> ()");
   m.def("symm_put_segments(Tensor src, int[] dst_ptrs, Tensor table, int vec_bytes, int total_vecs, int rank, int[] pad_ptrs, int slot, int epoch, Tensor(a!) counter, int num_ctas) -> ()");
   m.def("symm_vocab_ce_(Tensor(a!) logits, Tensor target, Tensor n_valid, int vocab_start, int ignore_index, int[] stats_ptrs, int rank, int epoch, int max_rows, int max_ctas) -> Tensor");
@@ -111,6 +115,7 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("philox_dropout_box", &philox_dropout_box);
   m.impl("wag_gemm", &wag_gemm);
   m.impl("symm_all_reduce", &symm_all_reduce);
+  m.impl("symm_reduce_scatter_t", &symm_reduce_scatter_t);
   m.impl("symm_a2a_permute", &symm_a2a_permute);
   m.impl("symm_put_segments", &symm_put_segments);
   m.impl("symm_vocab_ce_", &symm_vocab_ce_);

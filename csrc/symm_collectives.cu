@@ -2,6 +2,7 @@
 //
 // SURVEY §2F rows served here (the FSDP unit collectives are in symm_comm.cu, the GEMM-fused ones in gemm_fused_tp.cu):
 //   C11/C17/C19  all_reduce      : NVLS two-shot (multimem.ld_reduce + multimem.st), P2P two-shot, or one-shot for small messages
+//   C5/C10/C18   reduce_scatter  : NVLS (one multimem.ld_reduce per vector) or P2P pull of my slice, strided private output
 //   C12          a2a_permute     : Shard(i) -> Shard(j) all-to-all with the two permutes folded into the strided put
 //   C2/C3/C21    put_segments    : ragged->ragged interval exchange, scatter-from-source, gather-to-root (Muon) as one-sided puts
 //   C20          vocab_ce        : vocab-parallel cross entropy, local max/sumexp + W-way stats exchange + grad in ONE launch
@@ -176,6 +177,64 @@ __global__ void __launch_bounds__(512) all_reduce_kernel(const __grid_constant__
       } else {
         for (int pi = 0; pi < world; ++pi) reinterpret_cast<uint4*>(bufs.p[(rank + pi) % world])[i] = r;
       }
+    }
+  }
+  end_barrier(counter, pads, my_pad, world, rank, slot + 1, epoch);
+}
+
+// ------------------------------------------------------------------------------------------------- reduce-scatter
+// Rank r receives the sum over ranks of slice r of a symmetric buffer (slice_vecs 16-byte vectors starting at r * slice_vecs)
+// into the private tensor `out`.  The slice is a [rows, row_vecs] matrix and `out` may have a row stride, so column chunks of
+// a wider result can be reduced separately.  MODE 0: P2P loads of every peer's copy, all in flight before the first add.
+// MODE 1: one multimem.ld_reduce per vector -- the NVSwitch adds, this GPU receives 1/W of what the P2P form pulls.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(512) reduce_scatter_kernel(const __grid_constant__ Peers bufs, const void* mc, uint4* __restrict__ out, size_t slice_vecs, size_t row_vecs,
+                                                             size_t out_stride_vecs, int world, int rank, float scale, const __grid_constant__ Flags pads,
+                                                             const uint32_t* my_pad, int slot, uint32_t epoch, uint32_t* counter) {
+  start_barrier(pads, my_pad, world, rank, slot, epoch);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t lo = slice_vecs * (size_t)rank;
+  auto store = [&](size_t i, float* acc) {
+#pragma unroll
+    for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;
+    out[(i / row_vecs) * out_stride_vecs + i % row_vecs] = Vec16<T>::pack(acc);
+  };
+  if (MODE == 1) {
+    constexpr int U = 4;  // switch round trips in flight per thread
+    for (size_t base = tid; base < slice_vecs; base += stride * U) {
+      uint4 r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = base + u * stride;
+        if (i < slice_vecs) r[u] = Vec16<T>::mc_ld_reduce(reinterpret_cast<const uint4*>(mc) + lo + i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = base + u * stride;
+        if (i < slice_vecs) {
+          float acc[Vec16<T>::N] = {};
+          Vec16<T>::add(acc, r[u]);
+          store(i, acc);
+        }
+      }
+    }
+  } else {
+    for (size_t i = tid; i < slice_vecs; i += stride) {
+      float acc[Vec16<T>::N] = {};
+      uint4 v[kMaxPeers / 2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int k = 0; k < kMaxPeers / 2; ++k) {
+          const int pi = half * (kMaxPeers / 2) + k;
+          if (pi < world) v[k] = ld_stream(reinterpret_cast<const uint4*>(bufs.p[(rank + pi) % world]) + lo + i);
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxPeers / 2; ++k)
+          if (half * (kMaxPeers / 2) + k < world) Vec16<T>::add(acc, v[k]);
+      }
+      store(i, acc);
     }
   }
   end_barrier(counter, pads, my_pad, world, rank, slot + 1, epoch);
@@ -365,6 +424,39 @@ void symm_all_reduce(std::vector<int64_t> buf_ptrs, int64_t multicast_ptr, c10::
     else VB_AR(__nv_bfloat16, 0);
   }
 #undef VB_AR
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// out[rows, row] (row stride out_row_stride elements) = scale * sum over ranks of slice `rank` of the symmetric buffer
+void symm_reduce_scatter_t(std::vector<int64_t> buf_ptrs, int64_t multicast_ptr, at::Tensor out, int64_t slice_numel, int64_t row_numel, int64_t out_row_stride,
+                           int64_t dtype_code, double scale, int64_t rank, std::vector<int64_t> pad_ptrs, int64_t slot, int64_t epoch, at::Tensor counter,
+                           int64_t num_ctas) {
+  const int world = buf_ptrs.size();
+  const int esz = dtype_code == 0 ? 4 : 2;
+  TORCH_CHECK(out.is_cuda() && (int)out.element_size() == esz, "symm_reduce_scatter_t: out dtype does not match dtype_code");
+  TORCH_CHECK(row_numel > 0 && slice_numel % row_numel == 0, "symm_reduce_scatter_t: the slice must be whole rows");
+  TORCH_CHECK((row_numel * esz) % 16 == 0 && (out_row_stride * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(out.data_ptr()) % 16 == 0,
+              "symm_reduce_scatter_t: rows, the output row stride and the output base must be multiples of 16 bytes");
+  TORCH_CHECK(out_row_stride >= row_numel);
+  c10::cuda::CUDAGuard guard(counter.device());
+  const size_t slice_vecs = (size_t)slice_numel * esz / 16, row_vecs = (size_t)row_numel * esz / 16, ostride = (size_t)out_row_stride * esz / 16;
+  Peers bp = to_peers(buf_ptrs);
+  Flags pf = to_flags(pad_ptrs);
+  uint32_t* ctr = reinterpret_cast<uint32_t*>(counter.data_ptr());
+  const int grid = grid_for_bytes(slice_vecs * 16, (int)num_ctas);
+  const void* mc = reinterpret_cast<const void*>(multicast_ptr);
+  uint4* outp = reinterpret_cast<uint4*>(out.data_ptr());
+#define VB_RS(T, MODE)                                                                                                                                  \
+  reduce_scatter_kernel<T, MODE><<<grid, 512, 0, cur_stream()>>>(bp, mc, outp, slice_vecs, row_vecs, ostride, world, (int)rank, (float)scale, pf, pf.p[rank], \
+                                                                 (int)slot, (uint32_t)epoch, ctr)
+  if (dtype_code == 0) {
+    if (multicast_ptr != 0) VB_RS(float, 1);
+    else VB_RS(float, 0);
+  } else {
+    if (multicast_ptr != 0) VB_RS(__nv_bfloat16, 1);
+    else VB_RS(__nv_bfloat16, 0);
+  }
+#undef VB_RS
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -378,3 +378,55 @@ def _llama_tp_fused(rank, world):
 @pytest.mark.timeout(300)
 def test_llama_tp_fused_matches_plain():
     run_distributed(_llama_tp_fused, min(torch.cuda.device_count(), 8) // 2 * 2, backend="nccl")
+
+
+def _reduce_scatter_nvls(rank, world):
+    """Tensor-level reduce-scatter kernel (P2P pull and NVLS) against NCCL, strided output, and the gemm_rs built on it."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.comm.fused_tp import FusedTP
+    from vescale_b200.comm.symm_collectives import SymmCollectives
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    dev = torch.device("cuda", rank)
+    mesh = init_device_mesh("cuda", (world,))
+    sc = SymmCollectives(mesh, 0, dev)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for dtype, tol in ((torch.bfloat16, 2e-2), (torch.float32, 1e-5)):
+        for rows, row in ((3, 8), (64, 1024), (257, 4096)):
+            x = torch.randn(world * rows, row, device=dev, generator=g).to(dtype)
+            want = torch.empty(rows, row, device=dev, dtype=dtype)
+            dist.reduce_scatter_tensor(want, x.clone())
+            xs = sc.empty((world * rows, row), dtype)
+            xs.copy_(x)
+            for mm in (False, True):
+                sc.use_multimem = mm
+                for src in (x, xs):  # staged and zero-copy
+                    got = sc.reduce_scatter(src)
+                    torch.testing.assert_close(got.float(), want.float(), rtol=tol, atol=tol * 4)
+            wide = torch.zeros(rows, 2 * row + 8, device=dev, dtype=dtype)
+            sc.reduce_scatter(xs, "avg", out=wide[:, 8 : 8 + row])
+            torch.testing.assert_close(wide[:, 8 : 8 + row].float(), want.float() / world, rtol=tol, atol=tol * 4)
+            assert wide[:, :8].abs().max().item() == 0 and wide[:, 8 + row :].abs().max().item() == 0
+    # back-to-back calls reuse the same buffer without host synchronisation
+    xs = sc.empty((world * 128, 512))
+    for it in range(5):
+        xs.fill_(float(it + rank))
+        got = sc.reduce_scatter(xs)
+        assert torch.all(got.float() == float(sum(it + r for r in range(world)))), it
+    tp = FusedTP(mesh, 0, dev, rs_impl="nvls")
+    M, Kr, N = 256 * world * 2, 512, 1024
+    x = (torch.randn(M, Kr, device=dev, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, Kr, device=dev, generator=g) * 0.05).bfloat16()
+    want = torch.empty(M // world, N, device=dev, dtype=torch.float32)
+    dist.reduce_scatter_tensor(want, x.float() @ w.float().t())
+    for it in range(3):
+        y = tp.gemm_rs(x, w)
+        assert (y.float() - want).abs().max().item() < 0.02 * want.abs().max().item() + 0.05, it
+    torch.cuda.synchronize()
+    dist.barrier()
+
+
+@pytest.mark.timeout(300)
+def test_symm_reduce_scatter_and_nvls_gemm_rs():
+    run_distributed(_reduce_scatter_nvls, min(torch.cuda.device_count(), 8), backend="nccl")

@@ -97,6 +97,16 @@ def test_symmetric_memory_kernels_single_rank(tmp_path):
             xs = sc.empty(n)
             xs.copy_(x)
             torch.testing.assert_close(sc.all_reduce(xs, "avg").float(), x.float(), rtol=1e-2, atol=1e-2)
+        # reduce-scatter with one rank is a (scaled) copy: P2P and NVLS forms, staged and zero-copy, strided output
+        xr = torch.randn(96, 256, device=dev, generator=g).bfloat16()
+        xrs = sc.empty((96, 256))
+        xrs.copy_(xr)
+        for mm in (False, True):
+            sc.use_multimem = mm
+            assert torch.equal(sc.reduce_scatter(xr), xr) and torch.equal(sc.reduce_scatter(xrs), xr)
+        wide = torch.zeros(96, 512, device=dev, dtype=torch.bfloat16)
+        sc.reduce_scatter(xrs, out=wide[:, 128:384])
+        assert torch.equal(wide[:, 128:384], xr) and wide[:, :128].abs().max().item() == 0
         # Shard(i) -> Shard(j) with one rank is the identity; ragged exchange likewise
         t = torch.randn(4, 6, 8, device=dev, generator=g).bfloat16()
         assert torch.equal(sc.all_to_all_permute(t, 0, 2), t) and torch.equal(sc.all_to_all_permute(t, 2, 1), t)
@@ -122,6 +132,8 @@ def test_symmetric_memory_kernels_single_rank(tmp_path):
         assert (y.float() - want).abs().max().item() < 0.02 * want.abs().max().item() + 0.05
         y2 = tp.gemm_rs(x, w)
         assert (y2.float() - want).abs().max().item() < 0.02 * want.abs().max().item() + 0.05
+        y3 = FusedTP(mesh, 0, dev, rs_impl="nvls").gemm_rs(x, w)  # GEMM into symmetric memory + reduce-scatter kernel
+        assert (y3.float() - want).abs().max().item() < 0.02 * want.abs().max().item() + 0.05
         # FSDP all-gather ⊕ first GEMM: the kernel copies the (single) shard into the gathered buffer while multiplying
         from vescale_b200.models import LlamaConfig
         from vescale_b200.models.llama import LlamaBlock

@@ -10,10 +10,13 @@ mesh_broadcast, mesh_reduce_scatter, mesh_all_gather, mesh_all_reduce), referenc
 """
 from __future__ import annotations
 
+import math
 from typing import Callable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
+
+from ..utils.env import flag as _flag
 
 __all__ = [
     "mesh_all_gather",
@@ -179,6 +182,10 @@ def mesh_reduce_scatter(tensor: torch.Tensor, mesh, reduce_op: str = "sum", mesh
         tensor = torch.cat(tensor.chunk(n, dim=scatter_dim), dim=0)
     tensor = tensor.contiguous()
     out_shape = (tensor.shape[0] // n, *tensor.shape[1:])
+    if reduce_op in ("sum", "avg") and tensor.dtype in (torch.float32, torch.bfloat16) and _flag("VESCALE_B200_SYMM_RS"):
+        sc = _symm(group, tensor)
+        if sc is not None and (math.prod(out_shape[1:]) * tensor.element_size()) % 16 == 0:
+            return sc.reduce_scatter(tensor, reduce_op)
     if _backend(group) == "nccl":
         out = tensor.new_empty(out_shape)
         op = _OPS[reduce_op]

@@ -10,12 +10,13 @@ NCCL + cuBLAS for now; the forward kernels never call NCCL.
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 from ..ops import _ext
+from ..utils.env import flag as _flag
 
 __all__ = ["FusedTP", "PlainTP"]
 
@@ -25,8 +26,12 @@ class FusedTP:
     ``gemm_rs(dy, W^T)`` and d(linear_rs)/dx is ``ag_gemm(dy_local, W^T)``; the transposed weight copy is a
     few tens of microseconds per layer."""
 
-    def __init__(self, mesh, mesh_dim=0, device=None, fused_backward: bool = True):
+    def __init__(self, mesh, mesh_dim=0, device=None, fused_backward: bool = True, rs_impl: Optional[str] = None):
         self.fused_backward = fused_backward
+        self.rs_impl = rs_impl or _flag("VESCALE_B200_GEMM_RS")  # "staged" | "nvls"
+        if self.rs_impl not in ("staged", "nvls"):
+            raise ValueError(f"rs_impl must be 'staged' or 'nvls', got {self.rs_impl!r}")
+        self._sc = None
         from ..parallel.fsdp.api import _COMM_CACHE
         from .symm import SymmUnitComm
 
@@ -77,6 +82,8 @@ class FusedTP:
     # ------------------------------------------------------------------ GEMM ⊕ reduce-scatter
     def gemm_rs(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
         """x [M, Kr], w [N, Kr] -> y [M/W, N] (sum over ranks, row-scattered)."""
+        if self.rs_impl == "nvls":
+            return self._gemm_rs_nvls(x, w)
         M, _ = x.shape
         N, W = w.shape[0], self.world
         st = self._site("rs", M, N)
@@ -89,6 +96,25 @@ class FusedTP:
         _ext.count_launch("gemm_rs")
         self.ops.gemm_rs(x, w, y, st["staging_ptrs"], st["done"], st["flag_ptrs"], self.rank, st["epoch"])
         return y
+
+    def _gemm_rs_nvls(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        """``rs_impl="nvls"``: the GEMM writes this rank's partial [M, N] into symmetric memory and the owner of each row block
+        pulls the sum through the switch (``SymmCollectives.reduce_scatter``: one ``multimem.ld_reduce`` per 16 bytes), so a
+        GPU receives M*N/W reduced values instead of (W-1)/W * M*N staged partials.  The staged form wins at W=2, this one is
+        meant for W >= 4 (profiles/roofline_r1.md: staged gemm_rs at 0.82-0.98x of NCCL at W=8)."""
+        from ..ops import functional as F
+        from .symm_collectives import SymmCollectives
+
+        M, N = x.shape[0], w.shape[0]
+        st = self._sites.get(("rs_nvls", M, N))
+        if st is None:
+            st = self._sites[("rs_nvls", M, N)] = {"partial": self.arena.alloc(M * N, torch.bfloat16).view(M, N)}
+        if self._sc is None:
+            self._sc = SymmCollectives(self.mesh, self.md, self.device)
+        F.gemm_nt(x, w, out=st["partial"])
+        # the reduce-scatter kernel retires only after every peer has finished reading my partial (end barrier), so the next
+        # call's GEMM may overwrite it without further synchronisation
+        return self._sc.reduce_scatter(st["partial"])
 
     # ------------------------------------------------------------------ autograd front-ends
     def ag_linear(self, x_local: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

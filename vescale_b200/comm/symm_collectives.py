@@ -2,6 +2,7 @@
 
     sc = SymmCollectives(mesh, "TP")
     sc.all_reduce(x)                               # NVLS two-shot / P2P two-shot / one-shot (small)   — SURVEY §2F C11/C17/C19
+    y = sc.reduce_scatter(x)                       # NVLS / P2P pull of my slice, one kernel           — C5/C10/C18
     y = sc.all_to_all_permute(x, i, j)             # Shard(i) -> Shard(j), both permutes folded in     — C12
     y = sc.ragged_exchange(local, src_rng, dst_rng)  # ragged->ragged / scatter / gather-to-root puts — C2/C3/C21
     loss = sc.vocab_parallel_cross_entropy(logits_shard, target)   # one launch, no all-reduce         — C20
@@ -116,6 +117,47 @@ class SymmCollectives:
             self.ops.symm_all_reduce(ptrs, mc, None, numel_p, _DT[x.dtype], scale, self.rank, self.arena.pad_ptrs, self.slot, self._next(), self.counter, self.num_ctas)
             flat.copy_(st[:nbytes])
         return x
+
+    # ------------------------------------------------------------------ reduce-scatter
+    def reduce_scatter(self, x: torch.Tensor, op: str = "sum", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``x`` [W * rows, ...] (contiguous bf16 / fp32) holds this rank's partial values; returns rows ``[rank * rows,
+        (rank + 1) * rows)`` of the sum (or mean) over the mesh dim as a private tensor.  One kernel: with NVLS the switch adds
+        (``multimem.ld_reduce``), otherwise every peer's copy of my slice is pulled over NVLink.  ``x`` in symmetric memory
+        (``empty``) is read in place; other tensors are staged once.  ``out`` may be a column slice of a wider 2-D tensor."""
+        if x.dtype not in _DT or not x.is_contiguous() or op not in ("sum", "avg"):
+            raise ValueError("symmetric reduce_scatter handles contiguous bf16/fp32 sum/avg")
+        W = self.world
+        if x.ndim == 0 or x.shape[0] % W:
+            raise ValueError("reduce_scatter needs a leading dim divisible by the group size")
+        rows = x.shape[0] // W
+        row = math.prod(x.shape[1:])
+        esz = x.element_size()
+        if out is None:
+            out = torch.empty((rows, *x.shape[1:]), dtype=x.dtype, device=x.device)
+        if out.dtype != x.dtype or tuple(out.shape) != (rows, *x.shape[1:]):
+            raise ValueError("reduce_scatter: out must be [rows, ...] of x's dtype")
+        if rows == 0 or row == 0:
+            return out
+        if out.is_contiguous():
+            ostride = row
+        elif out.ndim == 2 and out.stride(1) == 1:
+            ostride = out.stride(0)
+        else:
+            raise ValueError("reduce_scatter: out must be contiguous or a column slice of a 2-D tensor")
+        if (row * esz) % 16 or (ostride * esz) % 16 or out.data_ptr() % 16:
+            raise ValueError("reduce_scatter: rows, the output row stride and the output base must be multiples of 16 bytes")
+        if x.data_ptr() % 16 == 0 and self._is_symmetric(x):
+            src = x
+        else:
+            nbytes = x.numel() * esz
+            src = self._stage(nbytes)[:nbytes]
+            src.copy_(x.view(-1).view(torch.uint8))
+        scale = 1.0 / W if op == "avg" else 1.0
+        mc = self.arena.multicast_ptr(src) if self.use_multimem else 0
+        _ext.count_launch("symm_reduce_scatter_t")
+        self.ops.symm_reduce_scatter_t(self.arena.peer_ptrs(src), mc, out, rows * row, row, ostride, _DT[x.dtype], scale, self.rank, self.arena.pad_ptrs, self.slot,
+                                       self._next(), self.counter, self.num_ctas)
+        return out
 
     # ------------------------------------------------------------------ Shard(i) -> Shard(j)
     def all_to_all_permute(self, x: torch.Tensor, src_shard_dim: int, dst_shard_dim: int) -> torch.Tensor:
