@@ -49,7 +49,9 @@ def parse():
     p.add_argument("--tp-impl", default="fused", choices=["fused", "plain"], help="fused = ag_gemm/gemm_rs sm_100a kernels; plain = NCCL + library GEMMs")
     p.add_argument("--fused-reduce", action="store_true", help="reduce-scatter ⊕ AdamW in one kernel (no gradient shard is ever stored; implies no global-norm clip; symm backend, N > 1) — the memory-lean optimizer path for 70B-class models")
     p.add_argument("--ac", default="selective", choices=["selective", "full"], help="selective = recompute norm / SwiGLU outputs only (default); full = checkpoint every block (70B-class models)")
-    p.add_argument("--fp8", action="store_true", help="block-scaled e4m3 forward GEMMs in the decoder blocks (BASELINE config 5; use with --model llama3_70b)")
+    p.add_argument("--fp8", nargs="?", const="block128", default=None, choices=["block128", "mx"],
+                   help="block-scaled e4m3 forward GEMMs in the decoder blocks (BASELINE config 5; use with --model llama3_70b): block128 = 1x128 / 128x128 "
+                        "fp32 scales through cuBLASLt, mx = OCP MXFP8 on the hand-written tcgen05 block-scaled kernel (sets VESCALE_B200_MXFP8_NATIVE=1)")
     p.add_argument("--prefetch", type=int, default=1, help="FSDP all-gather prefetch depth (0 = every all-gather exposed: the memory-lean mode)")
     p.add_argument("--fuse-first-gemm", action="store_true", help="exposed all-gathers: the unit's first GEMM gathers its own weight (wag_gemm)")
     p.add_argument("--profile", default=None, help="after the timed regions, run ONE extra step under torch.profiler and write the per-kernel table here")
@@ -189,7 +191,9 @@ def main():
         _ext.load(required=True)
     Fn.set_gemm_backend(args.gemm)
     cfg = getattr(LlamaConfig, args.model)()
-    cfg.fp8 = bool(args.fp8)
+    cfg.fp8 = args.fp8 or False
+    if args.fp8 == "mx":
+        os.environ.setdefault("VESCALE_B200_MXFP8_NATIVE", "1")
     invalid = None
     if args.layers is not None:
         cfg.num_layers = args.layers
@@ -370,7 +374,7 @@ def main():
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "bf16" if not args.fp8 else "fp8 e4m3 block-scaled forward GEMMs (1x128 / 128x128 scales), bf16 backward",
+        "dtype": "bf16" if not args.fp8 else ("fp8 e4m3 block-scaled forward GEMMs (1x128 / 128x128 scales), bf16 backward" if args.fp8 == "block128" else "MXFP8 (e4m3, 1x32 E8M0 scales) forward GEMMs, bf16 backward"),
         "data": "synthetic tokens (uniform random ids), random-init weights of the named architecture",
         "impl": "ours",
         "config": {

@@ -280,3 +280,36 @@ def test_mxfp8_quantisation():
     y = mxfp8_gemm_nt(xq, xs, wq, ws, torch.float32)
     ref = x @ w.t()
     assert (y - ref).norm() / ref.norm() < 0.05
+
+
+def test_mxfp8_scale_atoms_and_recipe():
+    """Scale factors in the tensor core's atom order (512 B = 128 rows x 4 K-blocks; csrc/gemm_mxfp8.cu) round-trip and follow
+    the byte formula; fp8_linear(recipe="mx") and a tiny Llama step under MX numerics track the bf16 model."""
+    from vescale_b200.models import LlamaConfig, LlamaModel
+    from vescale_b200.ops.fp8 import fp8_linear, mx_scale_atoms, mx_scale_from_atoms, quantize_mx
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(300, 512, generator=g)
+    _, s = quantize_mx(x)
+    for mult, atoms_rows in ((128, 3), (256, 4)):
+        a = mx_scale_atoms(s, mult)
+        assert a.dtype == torch.uint8 and a.numel() == atoms_rows * 4 * 512
+        assert torch.equal(mx_scale_from_atoms(a, 300, 16), s)
+        for r, kb in ((0, 0), (31, 3), (32, 4), (200, 9), (299, 15)):
+            off = ((r // 128) * 4 + kb // 4) * 512 + (r % 32) * 16 + (r % 128 // 32) * 4 + kb % 4
+            assert a[off] == s[r, kb]
+        assert (a.view(atoms_rows, 4, 32, 4, 4)[-1, :, :, (300 % 128) // 32 + 1 :, :] == 127).all()  # padding rows: scale 1.0
+    w = torch.randn(96, 512, generator=g) * 0.05
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    y = fp8_linear(xr, wr, recipe="mx")
+    ref = x @ w.t()
+    assert (y - ref).norm() / ref.norm() < 0.06
+    y.sum().backward()
+    torch.testing.assert_close(wr.grad, torch.ones(96, 300) @ x, rtol=1e-4, atol=1e-3)
+    cfg = LlamaConfig.tiny(fp8="mx")
+    m = LlamaModel(cfg).reset_parameters(seed=1)
+    tok = torch.randint(0, cfg.vocab_size, (2, 17), generator=g)
+    loss = m(tok[:, :-1], tok[:, 1:])
+    loss.backward()
+    ref_loss = LlamaModel(LlamaConfig.tiny()).reset_parameters(seed=1)(tok[:, :-1], tok[:, 1:])
+    assert abs(loss.item() - ref_loss.item()) < 0.05 and all(p.grad is not None for p in m.parameters())

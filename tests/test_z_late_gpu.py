@@ -160,3 +160,27 @@ def test_symmetric_memory_kernels_single_rank(tmp_path):
         torch.cuda.synchronize()
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (256, 512, 512), (300, 264, 384), (1024, 768, 2048), (4096, 4096, 4096)])
+def test_mxfp8_native_kernel_matches_emulation(M, N, K):
+    """tcgen05.mma.kind::mxf8f6f4.block_scale kernel (scales staged smem -> TMEM) against the dequantise-and-multiply
+    specification of the same quantised operands: only accumulation order and the bf16 output rounding may differ."""
+    from vescale_b200.ops import _ext, fp8
+
+    _ext.load(required=True)
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    # wide dynamic range across K blocks so that a wrong scale byte / block mapping cannot hide
+    x = torch.randn(M, K, device=dev, generator=g) * torch.exp2(torch.randint(-6, 6, (M, K // 32), device=dev, generator=g).float()).repeat_interleave(32, 1)
+    w = torch.randn(N, K, device=dev, generator=g) * torch.exp2(torch.randint(-6, 6, (N, K // 32), device=dev, generator=g).float()).repeat_interleave(32, 1)
+    xq, xs = fp8.quantize_mx(x)
+    wq, ws = fp8.quantize_mx(w)
+    ref = fp8.dequantize_mx(xq, xs) @ fp8.dequantize_mx(wq, ws).t()
+    got = fp8.mxfp8_gemm_nt_native(xq, fp8.mx_scale_atoms(xs, 128), wq, fp8.mx_scale_atoms(ws, 256)).float()
+    torch.cuda.synchronize()
+    err = ((got - ref).norm() / ref.norm()).item()
+    assert err < 6e-3, err
+    torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2 * ref.abs().max().item())
+    # second call on the same operands is bit-identical (no stale TMEM / barrier state between launches)
+    assert torch.equal(fp8.mxfp8_gemm_nt_native(xq, fp8.mx_scale_atoms(xs, 128), wq, fp8.mx_scale_atoms(ws, 256)).float(), got)

@@ -14,6 +14,7 @@ step kernels 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu
 step late_kernels 600 python -m pytest tests/test_z_late_gpu.py -q -m gpu
 step bench_n1 400 python bench.py --steps 4 --warmup 3
 step gemm_v3 150 python benchmarks/gemm_variant3_check.py
+step mxfp8 200 python benchmarks/mxfp8_check.py
 if [ "$N" -gt 1 ]; then
   T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
   step multigpu_tests 900 python -m pytest tests/test_symm_multigpu.py -x -q -m gpu

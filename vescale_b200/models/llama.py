@@ -38,7 +38,9 @@ class LlamaConfig:
     tie_embeddings: bool = False
     init_std: float = 0.02
     dtype: torch.dtype = torch.bfloat16
-    fp8: bool = False  # block-scaled e4m3 forward GEMMs in the decoder blocks (``ops/fp8.py``); lm-head and backward stay bf16
+    # block-scaled e4m3 forward GEMMs in the decoder blocks (``ops/fp8.py``); lm-head and backward stay bf16.
+    # True / "block128": 1x128 x 128x128 fp32 scales; "mx": OCP MXFP8 (1x32 E8M0 scales, the tcgen05 block-scaled kernel)
+    fp8: object = False
 
     @staticmethod
     def llama3_8b(**kw) -> "LlamaConfig":
@@ -118,8 +120,11 @@ class LlamaBlock(nn.Module):
         B, S, _ = h.shape
         hq, hk, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
         if cfg.fp8:
-            from ..ops.fp8 import fp8_linear
+            from functools import partial
 
+            from ..ops.fp8 import fp8_linear as _fp8_linear
+
+            fp8_linear = partial(_fp8_linear, recipe="mx" if cfg.fp8 == "mx" else "block128")
             h, x = O.add_rms_norm(h, delta, self.attn_norm, cfg.rms_eps)
             qkv = O.rope_qk_(fp8_linear(x, self.wqkv), cos, sin, hq, hk, d)
             a = fp8_linear(O.packed_attention(qkv, hq, hk, d, causal=True), self.wo)

@@ -20,17 +20,22 @@ from typing import Optional, Tuple
 
 import torch
 
-__all__ = ["quantize_blockwise", "dequantize_blockwise", "fp8_linear", "fp8_gemm_nt", "FP8_MAX", "set_fp8_backend", "quantize_mx", "dequantize_mx", "mxfp8_gemm_nt"]
+__all__ = ["quantize_blockwise", "dequantize_blockwise", "fp8_linear", "fp8_gemm_nt", "FP8_MAX", "set_fp8_backend", "quantize_mx", "dequantize_mx", "mxfp8_gemm_nt", "mx_scale_atoms", "mx_scale_from_atoms", "mxfp8_gemm_nt_native"]
 
 FP8 = torch.float8_e4m3fn
 FP8_MAX = 448.0
 _BACKEND = {"mode": "auto", "scaled_mm_ok": None}  # auto | emulate | scaled_mm
 
 
-def set_fp8_backend(mode: str) -> None:
-    assert mode in ("auto", "emulate", "scaled_mm")
-    _BACKEND["mode"] = mode
-    _BACKEND["scaled_mm_ok"] = None
+def set_fp8_backend(mode: Optional[str] = None, *, mx_native: Optional[bool] = None) -> None:
+    """``mode``: block128 recipe backend (auto | emulate | scaled_mm).  ``mx_native``: run MXFP8 GEMMs on the hand-written
+    tcgen05 block-scaled kernel (default: the ``VESCALE_B200_MXFP8_NATIVE`` environment flag)."""
+    if mode is not None:
+        assert mode in ("auto", "emulate", "scaled_mm")
+        _BACKEND["mode"] = mode
+        _BACKEND["scaled_mm_ok"] = None
+    if mx_native is not None:
+        _BACKEND["mx_native"] = bool(mx_native)
 
 
 def _pad_to(x: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
@@ -138,15 +143,18 @@ class _Fp8Linear(torch.autograd.Function):
         return dx, dw
 
 
-def fp8_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+def fp8_linear(x: torch.Tensor, weight: torch.Tensor, recipe: str = "block128") -> torch.Tensor:
+    """``recipe``: "block128" (1x128 activation / 128x128 weight fp32 scales) or "mx" (OCP MXFP8: 1x32 E8M0 scales on both)."""
+    if recipe == "mx":
+        return _MXFp8Linear.apply(x, weight)
     return _Fp8Linear.apply(x, weight)
 
 
 # ------------------------------------------------------------------------------- MXFP8 (the tensor cores' native block scaling)
 # OCP microscaling: 1x32 blocks along K, one power-of-two scale (E8M0, a biased exponent byte) per block, e4m3 elements.  This
-# is the format ``tcgen05.mma.kind::mxf8f6f4.block_scale`` consumes (scale factors staged in TMEM), so the quantiser and the
-# emulated GEMM below are the numerics specification for the hand-written kernel that is still to be written
-# (DESIGN.md "known gaps"); they already let a model be evaluated under MX numerics.
+# is the format ``tcgen05.mma.kind::mxf8f6f4.block_scale`` consumes (scale factors staged in TMEM): the quantiser and the
+# emulated GEMM below are the numerics specification of the hand-written kernel ``csrc/gemm_mxfp8.cu`` (opt-in until it has
+# been validated on hardware: ``set_fp8_backend(mx_native=True)``).
 MX_BLOCK = 32
 
 
@@ -172,6 +180,63 @@ def dequantize_mx(q: torch.Tensor, e8m0: torch.Tensor, dtype=torch.float32) -> t
     return (q.float() * scale).to(dtype)
 
 
+def mx_scale_atoms(e8m0: torch.Tensor, row_multiple: int = 128) -> torch.Tensor:
+    """[R, K/32] E8M0 bytes -> flat uint8 in the tensor core's scale-factor order (``csrc/gemm_mxfp8.cu``): 512-byte atoms of
+    128 rows x 4 K-blocks, byte ``(r % 32) * 16 + (r % 128 // 32) * 4 + k % 4``; the atoms of one 128-row block are consecutive
+    along K.  Rows are padded to ``row_multiple`` (128 for the A operand, 256 for B) with the neutral exponent 127."""
+    R, KB = e8m0.shape
+    if KB % 4:
+        raise ValueError("mx_scale_atoms needs K to be a multiple of 128")
+    pad = (-R) % row_multiple
+    if pad:
+        e8m0 = torch.cat([e8m0, e8m0.new_full((pad, KB), 127)], dim=0)
+    ra = e8m0.shape[0] // 128
+    return e8m0.view(ra, 4, 32, KB // 4, 4).permute(0, 3, 2, 1, 4).contiguous().view(-1)
+
+
+def mx_scale_from_atoms(atoms: torch.Tensor, rows: int, kblocks: int) -> torch.Tensor:
+    """Inverse of ``mx_scale_atoms`` (drops the padding rows)."""
+    ra = atoms.numel() // (kblocks // 4 * 512)
+    return atoms.view(ra, kblocks // 4, 32, 4, 4).permute(0, 3, 2, 1, 4).reshape(ra * 128, kblocks)[:rows].contiguous()
+
+
+def _mx_native_enabled() -> bool:
+    import os
+
+    return _BACKEND.get("mx_native", os.environ.get("VESCALE_B200_MXFP8_NATIVE", "0") == "1")
+
+
+def mxfp8_gemm_nt_native(xq, xs_atoms, wq, ws_atoms, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The hand-written ``tcgen05.mma.kind::mxf8f6f4.block_scale`` kernel; scales already in atom order."""
+    from . import _ext
+
+    if out is None:
+        out = torch.empty(xq.shape[0], wq.shape[0], dtype=torch.bfloat16, device=xq.device)
+    _ext.count_launch("mxfp8_gemm_nt")
+    _ext.ops().mxfp8_gemm_nt(xq.view(torch.uint8), xs_atoms, wq.view(torch.uint8), ws_atoms, out)
+    return out
+
+
 def mxfp8_gemm_nt(xq, xs, wq, ws, out_dtype=torch.bfloat16) -> torch.Tensor:
-    """Emulated MXFP8 GEMM: both operands carry 1x32 scales along K; fp32 accumulation."""
+    """MXFP8 GEMM, both operands with 1x32 E8M0 scales along K, fp32 accumulation.  On CUDA with the native kernel enabled
+    (``set_fp8_backend(mx_native=True)`` or ``VESCALE_B200_MXFP8_NATIVE=1``) and K % 128 == 0, N % 8 == 0: the tcgen05
+    block-scaled kernel; otherwise the emulation (dequantise, multiply in fp32), which is the numerics specification."""
+    if xq.is_cuda and _mx_native_enabled() and xq.shape[1] % 128 == 0 and wq.shape[0] % 8 == 0 and out_dtype == torch.bfloat16:
+        return mxfp8_gemm_nt_native(xq.contiguous(), mx_scale_atoms(xs, 128), wq.contiguous(), mx_scale_atoms(ws, 256))
     return (dequantize_mx(xq, xs) @ dequantize_mx(wq, ws).t()).to(out_dtype)
+
+
+class _MXFp8Linear(torch.autograd.Function):
+    """``recipe="mx"`` twin of ``_Fp8Linear``: forward GEMM on MXFP8 operands, bf16 backward on the saved operands."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x2 = x.reshape(-1, x.shape[-1])
+        xq, xs = quantize_mx(x2)
+        wq, ws = quantize_mx(weight)
+        ctx.save_for_backward(x2, weight)
+        ctx.shape = x.shape
+        y = mxfp8_gemm_nt(xq, xs, wq, ws, torch.bfloat16).to(x.dtype)
+        return y.view(*x.shape[:-1], weight.shape[0]).detach()
+
+    backward = _Fp8Linear.backward
