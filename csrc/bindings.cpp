@@ -17,6 +17,7 @@ void sumsq_accumulate(const at::Tensor& g, at::Tensor out, double scale);
 void fused_adamw_(at::Tensor master, at::Tensor m, at::Tensor v, const at::Tensor& g, at::Tensor p_out, const at::Tensor& wd_table,
                   const at::Tensor& coef, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, double gscale);
 // gemm_sm100.cu
+void mx_quantize(const at::Tensor& x, at::Tensor q, at::Tensor sf);
 void mxfp8_gemm_nt(const at::Tensor& a_q, const at::Tensor& sfa, const at::Tensor& b_q, const at::Tensor& sfb, at::Tensor c);
 void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate, int64_t variant);
 void gemm_nn(const at::Tensor& a, const at::Tensor& b, at::Tensor c);
@@ -86,6 +87,7 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("cross_entropy_fwd_bwd_(Tensor(a!) logits, Tensor target, Tensor n_valid, int ignore_index) -> Tensor");
   m.def("sumsq_accumulate(Tensor g, Tensor(a!) out, float scale) -> ()");
   m.def("fused_adamw_(Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor g, Tensor(d!) p_out, Tensor wd_table, Tensor coef, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) -> ()");
+  m.def("mx_quantize(Tensor x, Tensor(a!) q, Tensor(b!) sf) -> ()");
   m.def("mxfp8_gemm_nt(Tensor a_q, Tensor sfa, Tensor b_q, Tensor sfb, Tensor(a!) c) -> ()");
   m.def("gemm_nt(Tensor a, Tensor b, Tensor(a!) c, bool accumulate, int variant=0) -> ()");
   m.def("gemm_nn(Tensor a, Tensor b, Tensor(a!) c) -> ()");
@@ -133,6 +135,7 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("fused_adamw_", &fused_adamw_);
   m.impl("gemm_nt", &gemm_nt);
   m.impl("mxfp8_gemm_nt", &mxfp8_gemm_nt);
+  m.impl("mx_quantize", &mx_quantize);
   m.impl("gemm_nn", &gemm_nn);
   m.impl("philox_fill_box", &philox_fill_box);
   m.impl("grouped_gemm_nt", &grouped_gemm_nt);

@@ -19,6 +19,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
@@ -212,6 +213,49 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------- bf16 -> MXFP8 quantiser
+// One thread per 1x32 block: amax -> E8M0 exponent floor(log2(amax)) - 8 (the block maximum lands in e4m3's top binade) ->
+// e4m3 elements (round to nearest even, saturating) + the scale byte written straight into the GEMM's atom order.  Same
+// arithmetic as ops/fp8.py::quantize_mx, bit for bit.
+__global__ void __launch_bounds__(256) mx_quantize_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sf, int64_t rows,
+                                                          int kblocks /* K / 32 */) {
+  const int64_t nblk = rows * (int64_t)kblocks;
+  const int katoms = kblocks / 4;
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < nblk; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = b / kblocks;
+    const int kb = (int)(b - r * kblocks);
+    const uint4* src = reinterpret_cast<const uint4*>(x + b * 32);
+    float v[32];
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = ld_stream(src + i);
+      unpack8(*reinterpret_cast<const bf16x8*>(&u), v + 8 * i);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
+    // floor(log2(amax)) for a normal float is its exponent field; anything below 2^-119 (incl. 0 and subnormals) clamps to -127
+    int e = (int)((__float_as_uint(amax) >> 23) & 0xFF) - 127 - 8;
+    if (amax < 1.5046328e-36f /* 2^-119 */) e = -127;
+    const float inv = __uint_as_float((uint32_t)(127 - e) << 23);  // 2^-e, exact (e in [-127, 119] -> exponent field in [8, 254])
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y = fminf(fmaxf(v[4 * i + j] * inv, -448.f), 448.f);
+        packed |= (uint32_t)__nv_cvt_float_to_fp8(y, __NV_SATFINITE, __NV_E4M3) << (8 * j);
+      }
+      w[i] = packed;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(q + b * 32);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    sf[((r >> 7) * katoms + (kb >> 2)) * 512 + (r & 31) * 16 + ((r & 127) >> 5) * 4 + (kb & 3)] = (uint8_t)(e + 127);
+  }
+}
+
 int mxfp8_smem_bytes() { return kFStages * (kFA + kFB + kSFStage) + kFEpi + (2 * kFStages + 2) * 8 + 16 + 1024; }
 
 }  // namespace
@@ -245,5 +289,23 @@ void mxfp8_gemm_nt(const at::Tensor& a_q, const at::Tensor& sfa, const at::Tenso
   const int tiles = (int)(((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN));
   gemm_mxfp8_kernel<<<std::min(tiles, sms), kGemmThreads, smem, at::cuda::getCurrentCUDAStream()>>>(
       ta, tb, tc, reinterpret_cast<const uint8_t*>(sfa.data_ptr()), reinterpret_cast<const uint8_t*>(sfb.data_ptr()), (int)M, (int)N, (int)K);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// x [R, K] bf16 (K % 128 == 0) -> q [R, K] e4m3 bytes, sf: E8M0 bytes in atom order; the caller pre-fills `sf` with 127 (the
+// padding rows keep that neutral scale).
+void mx_quantize(const at::Tensor& x, at::Tensor q, at::Tensor sf) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous(), "mx_quantize: x must be a contiguous 2-D bf16 CUDA tensor");
+  const int64_t R = x.size(0), K = x.size(1);
+  TORCH_CHECK(K % 128 == 0, "mx_quantize: K must be a multiple of 128");
+  TORCH_CHECK(q.is_cuda() && q.element_size() == 1 && q.is_contiguous() && q.numel() == R * K && sf.is_cuda() && sf.element_size() == 1 && sf.is_contiguous());
+  TORCH_CHECK(sf.numel() % 512 == 0 && sf.numel() >= (R + 127) / 128 * (K / 128) * 512, "mx_quantize: sf too small");
+  if (R == 0) return;
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t nblk = R * (K / 32);
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int grid = (int)std::min<int64_t>((nblk + 255) / 256, (int64_t)sms * 16);
+  mx_quantize_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>(reinterpret_cast<const __nv_bfloat16*>(x.data_ptr()), reinterpret_cast<uint8_t*>(q.data_ptr()),
+                                                                        reinterpret_cast<uint8_t*>(sf.data_ptr()), R, (int)(K / 32));
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

@@ -184,3 +184,21 @@ def test_mxfp8_native_kernel_matches_emulation(M, N, K):
     torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2 * ref.abs().max().item())
     # second call on the same operands is bit-identical (no stale TMEM / barrier state between launches)
     assert torch.equal(fp8.mxfp8_gemm_nt_native(xq, fp8.mx_scale_atoms(xs, 128), wq, fp8.mx_scale_atoms(ws, 256)).float(), got)
+
+
+def test_mx_quantize_kernel_matches_specification():
+    """Fused bf16 -> MXFP8 quantiser (elements + E8M0 scales in atom order) is bit-identical to quantize_mx + mx_scale_atoms."""
+    from vescale_b200.ops import _ext, fp8
+
+    _ext.load(required=True)
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(7)
+    for R, K, mult in ((128, 128, 128), (300, 512, 128), (300, 512, 256), (4096, 4096, 256)):
+        x = (torch.randn(R, K, device=dev, generator=g) * torch.exp2(torch.randint(-20, 20, (R, K // 32), device=dev, generator=g).float()).repeat_interleave(32, 1)).bfloat16()
+        x[0, :32] = 0  # an all-zero block
+        x[1, 32:64] = 1e-38  # below the smallest scale
+        q_ref, s_ref = fp8.quantize_mx(x)
+        q, sf = fp8.quantize_mx_fused(x, mult)
+        torch.cuda.synchronize()
+        assert torch.equal(sf, fp8.mx_scale_atoms(s_ref, mult)), (R, K, mult)
+        assert torch.equal(q.view(torch.uint8), q_ref.view(torch.uint8)), (R, K, mult)

@@ -20,7 +20,7 @@ from typing import Optional, Tuple
 
 import torch
 
-__all__ = ["quantize_blockwise", "dequantize_blockwise", "fp8_linear", "fp8_gemm_nt", "FP8_MAX", "set_fp8_backend", "quantize_mx", "dequantize_mx", "mxfp8_gemm_nt", "mx_scale_atoms", "mx_scale_from_atoms", "mxfp8_gemm_nt_native"]
+__all__ = ["quantize_blockwise", "dequantize_blockwise", "fp8_linear", "fp8_gemm_nt", "FP8_MAX", "set_fp8_backend", "quantize_mx", "dequantize_mx", "mxfp8_gemm_nt", "mx_scale_atoms", "mx_scale_from_atoms", "mxfp8_gemm_nt_native", "quantize_mx_fused"]
 
 FP8 = torch.float8_e4m3fn
 FP8_MAX = 448.0
@@ -206,6 +206,20 @@ def _mx_native_enabled() -> bool:
     return _BACKEND.get("mx_native", os.environ.get("VESCALE_B200_MXFP8_NATIVE", "0") == "1")
 
 
+def quantize_mx_fused(x: torch.Tensor, row_multiple: int = 128):
+    """bf16 [R, K] (K % 128 == 0) on CUDA -> (e4m3 [R, K], E8M0 scales already in atom order) in ONE kernel
+    (``csrc/gemm_mxfp8.cu::mx_quantize_kernel``); bit-identical to ``quantize_mx`` + ``mx_scale_atoms``."""
+    from . import _ext
+
+    R, K = x.shape
+    rp = (R + row_multiple - 1) // row_multiple * row_multiple
+    q = torch.empty(R, K, dtype=torch.uint8, device=x.device)
+    sf = torch.full((rp // 128 * (K // 128) * 512,), 127, dtype=torch.uint8, device=x.device)
+    _ext.count_launch("mx_quantize")
+    _ext.ops().mx_quantize(x.contiguous(), q, sf)
+    return q.view(FP8), sf
+
+
 def mxfp8_gemm_nt_native(xq, xs_atoms, wq, ws_atoms, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The hand-written ``tcgen05.mma.kind::mxf8f6f4.block_scale`` kernel; scales already in atom order."""
     from . import _ext
@@ -232,11 +246,17 @@ class _MXFp8Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
         x2 = x.reshape(-1, x.shape[-1])
-        xq, xs = quantize_mx(x2)
-        wq, ws = quantize_mx(weight)
         ctx.save_for_backward(x2, weight)
         ctx.shape = x.shape
-        y = mxfp8_gemm_nt(xq, xs, wq, ws, torch.bfloat16).to(x.dtype)
+        K, N = x2.shape[1], weight.shape[0]
+        if x2.is_cuda and _mx_native_enabled() and x2.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and K % 128 == 0 and N % 8 == 0:
+            xq, xa = quantize_mx_fused(x2, 128)  # one quantise kernel per operand, scales written in the GEMM's atom order
+            wq, wa = quantize_mx_fused(weight, 256)
+            y = mxfp8_gemm_nt_native(xq, xa, wq, wa)
+        else:
+            xq, xs = quantize_mx(x2)
+            wq, ws = quantize_mx(weight)
+            y = mxfp8_gemm_nt(xq, xs, wq, ws, torch.bfloat16).to(x.dtype)
         return y.view(*x.shape[:-1], weight.shape[0]).detach()
 
     backward = _Fp8Linear.backward
