@@ -3,6 +3,7 @@
 # increasing order of risk, each step under its own timeout so a hang costs seconds, not the box.
 #   tools/gpu_validate.sh            # single GPU
 #   tools/gpu_validate.sh 2|4|8      # also the multi-GPU steps on N GPUs
+#   NCU=1 tools/gpu_validate.sh      # also ncu --set full captures of the fused kernels (single GPU)
 # Results land in gpurun_out/validate_*.log / *.json.
 set -uo pipefail
 N="${1:-1}"
@@ -15,6 +16,15 @@ step late_kernels 600 python -m pytest tests/test_z_late_gpu.py -q -m gpu
 step bench_n1 400 python bench.py --steps 4 --warmup 3
 step gemm_v3 150 python benchmarks/gemm_variant3_check.py
 step mxfp8 200 python benchmarks/mxfp8_check.py
+# ncu captures (single GPU, one capture per kernel family; the world-size-1 test drives the fused / symmetric kernels on one GPU,
+# which is the only way to put them under ncu: multi-rank commands must never be wrapped in it).  Read back here with
+#   ncu -i gpurun_out/<name>.ncu-rep --page raw --csv | grep -E 'dram__bytes|sm__pipe_tensor|gpu__dram_throughput|lts__t_sectors'
+if [ "${NCU:-0}" = "1" ]; then
+  NC="ncu --set full --clock-control none --import-source on -c 3"
+  step ncu_fused_tp 300 $NC -k regex:fused_tp_kernel -o gpurun_out/fused_tp python -m pytest "tests/test_z_late_gpu.py::test_symmetric_memory_kernels_single_rank" -q -m gpu
+  step ncu_mxfp8 300 $NC -k regex:gemm_mxfp8_kernel -s 2 -o gpurun_out/mxfp8 python benchmarks/mxfp8_check.py
+  step ncu_vocab_ce 300 $NC -k regex:vocab_ce_kernel -o gpurun_out/vocab_ce python -m pytest "tests/test_z_late_gpu.py::test_symmetric_memory_kernels_single_rank" -q -m gpu
+fi
 if [ "$N" -gt 1 ]; then
   T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
   step multigpu_tests 900 python -m pytest tests/test_symm_multigpu.py -x -q -m gpu
