@@ -251,3 +251,146 @@ def test_emulator_topology_tuning_primitives():
         y = torch.relu(torch.add(sh, 1.0))
     assert isinstance(y, list) and torch.equal(y[1], torch.relu(full[4:] + 1))
     assert torch.equal(torch.add(full, 1.0), full + 1)  # restored
+
+
+def test_reference_import_paths_and_extension_points(tmp_path):
+    """The module paths the reference's own examples / tests import from resolve to the SAME objects as the implementing
+    modules; the class-name keyed auto-plan registry, the torch.distributed-shaped emulator front end, the emulated device
+    mesh and the declared-timer metadata of ndtimeline behave as documented."""
+    import importlib
+    import warnings
+
+    import torch.nn as nn
+
+    import vescale
+    import vescale_b200
+
+    pairs = {
+        "vescale.dtensor.api": ["from_local", "to_local", "distribute_tensor", "redistribute_dtensor", "vescale_all_gather", "vescale_all_reduce", "vescale_reduce_scatter", "normalize_placements"],
+        "vescale.dtensor.placement_types": ["Shard", "Replicate", "Partial", "InterleavedShard", "RaggedShard", "DTensorSpec", "TensorMeta"],
+        "vescale.dtensor.device_mesh": ["DeviceMesh", "init_device_mesh", "mesh_resources"],
+        "vescale.dtensor.dtensor": ["DTensor", "make_dtensor"],
+        "vescale.dtensor.random": ["manual_seed", "init_vescale_rng_tracker", "is_rng_supported_mesh", "OffsetBasedRNGTracker", "ThreadBasedRNGTracker"],
+        "vescale.dtensor.vescale_utils": ["get_ragged_shard", "best_effort_reshape", "retrieve_flattened_index_before_ragged_shard", "cvt_inclusive_to_exclusive"],
+        "vescale.dmodule.api": ["parallelize_module", "is_dmodule", "PlacementsInterface"],
+        "vescale.ddp.distributed_data_parallel": ["DistributedDataParallel"],
+        "vescale.optim.distributed_optimizer": ["DistributedOptimizer"],
+        "vescale.optim.base_optimizer": ["BasicOptimizer", "BasicOptimizerHook"],
+        "vescale.initialize.deferred_init": ["deferred_init", "is_deferred", "materialize_dtensor", "materialize_dparameter"],
+        "vescale.plan": ["PipelineParallelPlan", "PipelineScheduleType", "PipelineSplitMethodType", "ModeType", "TracerType", "PipelineP2PSpec"],
+        "vescale.plan.spec": ["PipelineScheduleType", "PipelineSplitMethodType"],
+        "vescale.pipe": ["PipeModule", "construct_stage_modules", "construct_pipeline_stage", "build_shared_module_group", "build_stage_module_and_dependency", "PipeParser",
+                         "parse_model_graph", "split_pipeline_point", "construct_pipeline_split_graph", "ScheduleEngine", "validate_pipeline_schedule"],
+        "vescale.pipe.pipe_stage": ["PipeModule", "construct_pipeline_stage"],
+        "vescale.pipe._schedules.instruction_base": ["StageDeps", "register_instruction", "Shape"],
+        "vescale.pipe._schedules.pipedream_flush": ["OneFOneBInstrcutionGenerator"],
+        "vescale.engine": ["PipeEngine"],
+        "vescale.moe": ["parallelize_experts", "is_experts_parallized", "MoEOptimizer", "ExpertsAllocator", "TokenDispatcher"],
+        "vescale.dmp": ["auto_parallelize_module", "set_plan_overriding_policy", "get_plan_overriding_policy"],
+        "vescale.dmp.policies": ["REGISTRY"],
+        "vescale.checkpoint": ["save", "load", "CheckpointState"],
+        "vescale.devicemesh_api": ["VESCALE_DEVICE_MESH"],
+        "vescale.model.patch": ["get_all_model_patch"],
+        "vescale.emulator.distributed": ["ProcessGroup", "init_process_group", "new_group", "get_rank", "set_rank", "destroy_process_group"],
+        "vescale.emulator.device_mesh": ["DeviceMesh", "init_device_mesh"],
+        "vescale.emulator.reduce_kernel": ["ReduceOp"],
+        "vescale.emulator.utils": ["flatten_tensors", "restore_tensors"],
+        "vescale.emulator.mesh_collectives": ["mesh_all_gather", "mesh_all_reduce", "mesh_reduce_scatter", "mesh_all_to_all", "mesh_broadcast", "mesh_scatter"],
+        "vescale.ndtimeline": ["init_ndtimers", "flush", "wait", "inc_step", "set_global_step", "ndtimeit", "ndtimer", "WorldInfo", "DeviceTimerMeta", "NDTimerManagerSingleton",
+                               "CudaEventPool", "DefaultEventPool", "get_nccl_coll_stream", "get_nccl_p2p_stream", "encode_package", "serialize_to_package", "SOCK_PATH"],
+        "vescale.ndtimeline.world_info": ["WorldInfo", "TopoInfo", "TrainingInfo"],
+        "vescale.ndtimeline.handlers": ["ChromeTraceNDHandler", "LocalRawNDHandler", "LocalTimelineNDHandler", "LoggingNDHandler", "ParserNDHandler", "DoNothingNDHandler", "SockNDHandler"],
+        "vescale.debug": ["DebugLogger"],
+        "vescale": ["deprecated_function", "switch_dtensor_for_torch_export", "parallelize_module", "DistributedDataParallel", "DistributedOptimizer", "deferred_init"],
+    }
+    for mod, names in pairs.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n}"
+    assert importlib.import_module("vescale.dtensor.api") is importlib.import_module("vescale_b200.dtensor.api")
+    assert importlib.import_module("vescale.emulator.distributed") is vescale_b200.emulator.distributed
+
+    # --- class-name keyed plan providers take precedence over the built-in policy
+    from vescale.dmp.policies import REGISTRY
+    from vescale_b200 import Replicate, Shard
+    from vescale_b200.parallel.dmp.registry import get_policy
+
+    register = REGISTRY.provide_register_for_policy("MEGATRON")
+
+    class MyFancyFFN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(4, 8), nn.Linear(8, 4)
+
+    @register("FancyFFN")
+    def provider(fqn, module):
+        return {"a.weight": [Shard(0)], "b.weight": [Shard(1)]}, {"a.input": [[Replicate()]]}
+
+    plan = get_policy("MEGATRON").provide("blocks.3.ffn", MyFancyFFN(), None)
+    assert plan["parameter"] == {r"blocks\.3\.ffn\.a\.weight": [Shard(0)], r"blocks\.3\.ffn\.b\.weight": [Shard(1)]} and list(plan["forward"]) == [r"blocks\.3\.ffn\.a\.input"]
+    assert REGISTRY.has_module("fancyffn") and REGISTRY.has_policy("megatron")
+    try:
+        register("FancyFFN")(provider)
+        raise AssertionError("a second provider for the same (class, policy) must be rejected")
+    except ValueError:
+        pass
+
+    # --- emulator front end: in-place list semantics, NCCL-ordered sums, emulated mesh
+    import vescale.emulator.distributed as edist
+    from vescale.emulator.device_mesh import init_device_mesh as emu_mesh
+
+    mesh = emu_mesh("cpu", (2, 2), mesh_dim_names=("dp", "tp"))
+    assert [g.ranks for g in mesh.get_dim_groups("tp")] == [[0, 1], [2, 3]] and edist.get_world_size() == 4
+    xs = [torch.randn(33) for _ in range(4)]
+    want = [xs[0] + xs[1], xs[0] + xs[1], xs[2] + xs[3], xs[2] + xs[3]]
+    mesh.all_reduce(xs, "tp")
+    for a, b in zip(xs, want):
+        torch.testing.assert_close(a, b)
+    pg = edist.new_group([0, 1, 2, 3])
+    outs, tl = [None] * 4, [[torch.full((3,), float(10 * i + j)) for j in range(4)] for i in range(4)]
+    pg.reduce_scatter(outs, tl)
+    assert outs[1][0].item() == 1 + 11 + 21 + 31
+    recv = [None] * 4
+    pg.all_to_all(recv, tl)
+    assert recv[1][2][0].item() == 21
+    edist.set_rank(3)
+    assert edist.get_rank(pg) == 3 and edist.get_group_rank(pg, 2) == 2
+    edist.destroy_process_group()
+    assert not edist.is_initialized()
+
+    # --- ndtimeline: declared timers (level / legal tags / enabled), world info reaches the handlers, singleton accessor
+    import vescale.ndtimeline as nd
+
+    p = nd.ParserNDHandler()
+    wi = nd.WorldInfo(rank=0, local_rank=0, tp_rank=1, tp_size=2, world_size=2, run_id=7, cluster="b200")
+    mgr = nd.init_ndtimers(0, 1, [p], world_info=wi, metas=[nd.DeviceTimerMeta(name="declared", legal_tags=["mb"], level=nd.NDMetricLevel.INFO, common_extra={"k": 1}),
+                                                          nd.DeviceTimerMeta(name="off", enabled=False, level=nd.NDMetricLevel.INFO)])
+    assert nd.NDTimerManagerSingleton() is mgr and p.world_info is wi and wi["tp_rank"] == 1 and wi["cluster"] == "b200" and wi["run_id"] == 7
+    with nd.ndtimeit("declared", mb=3):
+        pass
+    with nd.ndtimeit("off"):
+        pass
+    try:
+        with nd.ndtimeit("declared", bogus=1):
+            pass
+        raise AssertionError("undeclared tag must be rejected")
+    except ValueError:
+        pass
+    nd.flush(asynchronous=False)
+    s = p.summary()
+    assert s["declared"]["count"] == 1 and "off" not in s
+    try:
+        nd.TopoInfo(rank=-1)
+        raise AssertionError
+    except ValueError:
+        pass
+    pkg = nd.serialize_to_package([{"a": 1}], rank=2, step=5)
+    assert list(nd.decode_frames(bytearray(pkg))) == [(0, 2, 5, [{"a": 1}])]
+
+    @vescale.deprecated_function
+    def old():
+        return 1
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert old() == 1 and len(w) == 1

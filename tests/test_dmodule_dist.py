@@ -131,3 +131,68 @@ def test_tp_sp_plan():
 
 def test_deferred_init_sharded_equals_single_device():
     run_distributed(_deferred, 4)
+
+
+class _Head(nn.Module):
+    def __init__(self, V=48, h=32):
+        super().__init__()
+        self.emb = nn.Embedding(V, h)
+        self.proj = nn.Linear(h, h)  # row parallel, with bias
+        self.lm = nn.Linear(h, V, bias=False)
+        self.loss = nn.CrossEntropyLoss(ignore_index=-100)
+
+    def forward(self, ids, labels):
+        return self.loss(self.lm(self.proj(self.emb(ids))), labels)
+
+
+def _model_patches(rank, world):
+    """RowParallelLinear / VocabParallelEmbedding / VocabParallelCrossEntropy patches (legacy ``model/patch``): a vocab-parallel
+    embedding, a row-parallel linear with bias and a vocab-parallel LM head + CrossEntropyLoss reproduce the single-device
+    loss and gradients; the patched loss never gathers the logits."""
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200.dtensor import DTensor
+    from vescale_b200.dtensor.debug import CommDebugMode
+    from vescale_b200.model.patch import VocabParallelCrossEntropy, get_all_model_patch
+    from vescale_b200.parallel.dmodule import parallelize_module
+
+    dev = device_type()
+    mesh = init_device_mesh(dev, (world,))
+    torch.manual_seed(0)
+    ref = _Head().to(dev)
+    m = copy.deepcopy(ref)
+    parallelize_module(
+        m, mesh,
+        {"parameter": {r"emb\.weight": [Shard(0)], r"proj\.weight": [Shard(1)], r"proj\.bias": [Replicate()], r"lm\.weight": [Shard(0)]},
+         "forward": {r"proj\.input": [[Shard(1)]], r"lm\.input": [[Replicate()]]}},
+    )
+    for patch in get_all_model_patch():
+        patch(m)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, 48, (24,), generator=g).to(dev)
+    labels = torch.randint(0, 48, (24,), generator=g)
+    labels[::5] = -100
+    labels = labels.to(dev)
+    with CommDebugMode() as comm:
+        loss = m(ids, labels)
+    want = ref(ids, labels)
+    got = loss.full_tensor() if isinstance(loss, DTensor) else loss
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    counts = comm.get_comm_counts()
+    assert not any("all_gather" in str(k) and v for k, v in counts.items() if "logits" in str(k)), counts
+    got.backward() if not isinstance(loss, DTensor) else loss.backward()
+    want.backward()
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        gp = p.grad.full_tensor() if isinstance(p.grad, DTensor) else p.grad
+        torch.testing.assert_close(gp, q.grad, rtol=1e-3, atol=1e-5, msg=lambda s, n=n: f"{n}: {s}")
+    # reductions of the patched loss module on class-sharded logits
+    logits = torch.randn(24, 48, generator=g).to(dev)
+    dl = DTensor.from_local(logits.chunk(world, 1)[rank].contiguous(), mesh, [Shard(1)])
+    for red in ("mean", "sum", "none"):
+        lossmod = nn.CrossEntropyLoss(ignore_index=-100, reduction=red)
+        holder = nn.ModuleDict({"l": lossmod})
+        VocabParallelCrossEntropy.patch(holder)
+        torch.testing.assert_close(lossmod(dl, labels), torch.nn.functional.cross_entropy(logits, labels, ignore_index=-100, reduction=red), rtol=1e-4, atol=1e-5)
+
+
+def test_model_patches():
+    run_distributed(_model_patches, 4)

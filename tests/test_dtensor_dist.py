@@ -46,6 +46,26 @@ def _redistribute_all(rank, world):
         out = distribute_tensor(full, mesh2, a).redistribute(mesh2, b)
         assert torch.equal(out.full_tensor(), full), (a, b)
     assert mesh2["tp"].size() == 2 and mesh2["dp"].get_group() is not None
+    # collective-named API (legacy dtensor/api.py:314-436), also through the `vescale` alias package
+    from vescale.dtensor.api import vescale_all_gather, vescale_all_reduce, vescale_reduce_scatter
+
+    sh = distribute_tensor(full, mesh2, [Shard(0), Shard(1)])
+    g1 = vescale_all_gather(sh, mesh_dims=1)
+    assert g1.placements == (Shard(0), Replicate()) and torch.equal(g1.full_tensor(), full)
+    g2 = vescale_all_gather(sh)
+    assert g2.placements == (Replicate(), Replicate()) and torch.equal(g2.to_local(), full)
+    try:
+        vescale_all_gather(g1, mesh_dims=[1])
+        raise AssertionError("all-gather over an unsharded mesh dim must be rejected")
+    except ValueError:
+        pass
+    part = DTensor.from_local(local, mesh2, [Partial(), Partial()], shape=(8, 12))
+    r1 = vescale_all_reduce(part, mesh_dims="tp")
+    assert r1.placements == (Partial(), Replicate())
+    torch.testing.assert_close(vescale_all_reduce(part).to_local(), want)
+    rs = vescale_reduce_scatter(part, scatter_dims=[0], mesh_dims=[1])
+    assert rs.placements == (Replicate(), Shard(0))
+    torch.testing.assert_close(rs.full_tensor(), want)
 
 
 def _ops(rank, world):

@@ -101,6 +101,25 @@ def test_scheduler_properties():
     bz = bubble_fraction(build_schedule(PipelineParallelPlan(num_stages=4, schedule_type=PipelineScheduleType.ZERO_BUBBLE), 8))
     bv = bubble_fraction(build_schedule(PipelineParallelPlan(num_stages=4, schedule_type=PipelineScheduleType.ZERO_BUBBLE_V), 8))
     assert bv < bz < b1
+    # interleaved 1F1B: fixed Megatron operation order -> the textbook bubble (P-1)(tF+tB) / (M V (tF+tB) + (P-1)(tF+tB)) whenever
+    # P divides M, and no deadlock for long runs (a greedy in-flight window deadlocks at M > 2P)
+    for P, V, M in ((4, 2, 8), (4, 2, 16), (4, 4, 8), (8, 2, 16), (4, 3, 12), (2, 2, 4)):
+        rows = build_schedule(PipelineParallelPlan(num_stages=P, virtual_chunks=V, schedule_type=PipelineScheduleType.INTERLEAVED_1F1B), M)
+        assert all(len(r) == 2 * M * V for r in rows)
+        assert abs(bubble_fraction(rows) - (P - 1) / (M * V + P - 1)) < 1e-9, (P, V, M)
+    for P, V, M in ((4, 2, 6), (2, 2, 5), (2, 3, 7), (4, 2, 64)):
+        rows = build_schedule(PipelineParallelPlan(num_stages=P, virtual_chunks=V, schedule_type=PipelineScheduleType.INTERLEAVED_1F1B), M)
+        assert all(len(r) == 2 * M * V for r in rows)
+    from vescale_b200.parallel.pipe import validate_pipeline_schedule
+    from vescale_b200.parallel.pipe._schedules import InterleavedOneFOneBInstructionGenerator, OneFOneBInstrcutionGenerator, StageDeps
+
+    gen = InterleavedOneFOneBInstructionGenerator(StageDeps(8), [None] * 4, 8)
+    assert len(gen.get_instruction_list(3)) == 32 and gen.bubble_fraction() < OneFOneBInstrcutionGenerator(StageDeps(4), [None] * 4, 8).bubble_fraction()
+    try:
+        validate_pipeline_schedule(PipelineParallelPlan(num_stages=2, virtual_chunks=2, schedule_type=PipelineScheduleType.SIMPLE_1F1B))
+        raise AssertionError("SIMPLE_1F1B with two chunks must be rejected")
+    except ValueError:
+        pass
     m = make_model(10)
     units = list(m.named_children())
     g = split_units(units, PipelineParallelPlan(num_stages=4, split_method=PipelineSplitMethodType.UNIFORM))

@@ -3,6 +3,8 @@
     import vescale; from vescale.dtensor import distribute_tensor, RaggedShard; vescale.checkpoint.save(...)
 """
 import importlib
+import importlib.abc
+import importlib.machinery
 import sys
 
 import vescale_b200 as _impl
@@ -41,8 +43,118 @@ _ALIASES = {
     "vescale.ndtimeline": "vescale_b200.profiler",
     "vescale.debug": "vescale_b200.debug",
     "vescale.model.patch": "vescale_b200.model.patch",
+    # deep module paths the reference's examples and tests import from
+    "vescale.dtensor.api": "vescale_b200.dtensor.api",
+    "vescale.dtensor._api": "vescale_b200.dtensor.api",
+    "vescale.dtensor.dtensor": "vescale_b200.dtensor.api",
+    "vescale.dtensor._utils": "vescale_b200.layout",
+    "vescale.dtensor._collective_utils": "vescale_b200.comm.collectives",
+    "vescale.dtensor.redistribute": "vescale_b200.dtensor.redistribute",
+    "vescale.dtensor.op_schema": "vescale_b200.dtensor.op_schema",
+    "vescale.dtensor.dispatch": "vescale_b200.dtensor.dispatch",
+    "vescale.dtensor.sharding_prop": "vescale_b200.dtensor.sharding_prop",
+    "vescale.dtensor.vescale_utils": "vescale_b200.dtensor.vescale_utils",
+    "vescale.dtensor.vescale_utils.ragged_shard_utils": "vescale_b200.dtensor.vescale_utils",
+    "vescale.dmodule._dmodule": "vescale_b200.parallel.dmodule.api",
+    "vescale.dmodule.placements_interface": "vescale_b200.parallel.dmodule.api",
+    "vescale.ddp.grad_buffer": "vescale_b200.parallel.ddp",
+    "vescale.dmp.policies": "vescale_b200.parallel.dmp.policies",
+    "vescale.dmp.policies.registry": "vescale_b200.parallel.dmp.registry",
+    "vescale.dmp.policies.megatron": "vescale_b200.parallel.dmp.policies.megatron",
+    "vescale.pipe.pipe_stage": "vescale_b200.parallel.pipe.stage",
+    "vescale.pipe.pipe_parser": "vescale_b200.parallel.pipe.stage",
+    "vescale.pipe.tracer": "vescale_b200.parallel.pipe.stage",
+    "vescale.pipe.pipe_emmiter": "vescale_b200.parallel.pipe.engine",
+    "vescale.pipe.p2p_communication": "vescale_b200.parallel.pipe.p2p",
+    "vescale.pipe._schedules": "vescale_b200.parallel.pipe._schedules",
+    "vescale.pipe._schedules.instruction_base": "vescale_b200.parallel.pipe._schedules",
+    "vescale.pipe._schedules.pipedream_flush": "vescale_b200.parallel.pipe._schedules",
+    "vescale.pipe._schedules.looping_bfs": "vescale_b200.parallel.pipe._schedules",
+    "vescale.pipe._schedules.zero_bubble_v": "vescale_b200.parallel.pipe._schedules",
+    "vescale.plan.spec": "vescale_b200.parallel.pipe.plan",
+    "vescale.plan.pipeline_parallel": "vescale_b200.parallel.pipe.plan",
+    "vescale.engine.pipe": "vescale_b200.parallel.pipe.engine",
+    "vescale.moe.experts_allocator": "vescale_b200.parallel.moe.api",
+    "vescale.moe.token_dispatcher": "vescale_b200.parallel.moe.api",
+    "vescale.moe.moe_optimizer": "vescale_b200.parallel.moe.api",
+    "vescale.checkpoint.api": "vescale_b200.checkpoint.api",
+    "vescale.checkpoint.api.meta_type": "vescale_b200.checkpoint.meta_type",
+    "vescale.checkpoint.api.vescale_checkpointer": "vescale_b200.checkpoint.api",
+    "vescale.checkpoint.api.base_checkpointer": "vescale_b200.checkpoint.api",
+    "vescale.checkpoint.utilities.mem_checkpoint": "vescale_b200.checkpoint.mem_server",
+    "vescale.checkpoint.utilities.server.mem_server_lib": "vescale_b200.checkpoint.mem_server",
+    "vescale.devicemesh_api.api": "vescale_b200.devicemesh_api.api",
+    "vescale.debug.debug_log": "vescale_b200.debug.debug_log",
+    "vescale.emulator.distributed": "vescale_b200.emulator.distributed",
+    "vescale.emulator.device_mesh": "vescale_b200.emulator.device_mesh",
+    "vescale.emulator.reduce_kernel": "vescale_b200.emulator.reduce_kernel",
+    "vescale.emulator.utils": "vescale_b200.emulator.utils",
+    "vescale.emulator.mesh_collectives": "vescale_b200.emulator.comm_api",
+    "vescale.emulator.all_reduce": "vescale_b200.emulator.collectives",
+    "vescale.emulator.all_gather": "vescale_b200.emulator.collectives",
+    "vescale.emulator.reduce_scatter": "vescale_b200.emulator.collectives",
+    "vescale.emulator.all_to_all": "vescale_b200.emulator.collectives",
+    "vescale.emulator.calculate_chunk_size": "vescale_b200.emulator.tuning",
+    "vescale.emulator.primitives": "vescale_b200.emulator.comm_primitive",
+    "vescale.ndtimeline.api": "vescale_b200.profiler.timer",
+    "vescale.ndtimeline.timer": "vescale_b200.profiler.timer",
+    "vescale.ndtimeline.pool": "vescale_b200.profiler.pool",
+    "vescale.ndtimeline.stream": "vescale_b200.profiler.stream",
+    "vescale.ndtimeline.world_info": "vescale_b200.profiler.world_info",
+    "vescale.ndtimeline.exceptions": "vescale_b200.profiler.exceptions",
+    "vescale.ndtimeline.logger": "vescale_b200.profiler.logger",
+    "vescale.ndtimeline.predefined": "vescale_b200.profiler.predefined",
+    "vescale.ndtimeline.binary_protocol": "vescale_b200.profiler.sock_streamer",
+    "vescale.ndtimeline.sock_streamer": "vescale_b200.profiler.sock_streamer",
+    "vescale.ndtimeline.variables": "vescale_b200.profiler",
+    "vescale.ndtimeline.handlers": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.handler_base": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.chrome_trace_event": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.local_raw_handler": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.local_timeline_handler": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.logging_handler": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.parser_handler": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.do_nothing_handler": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.sock_handler": "vescale_b200.profiler.sock_streamer",
+    "vescale.optim.utils": "vescale_b200.optim.distributed_optimizer",
+    "vescale.model.patch.linear": "vescale_b200.model.patch.linear",
+    "vescale.model.patch.vp_embedding": "vescale_b200.model.patch.vp_embedding",
+    "vescale.model.patch.vp_cross_entropy": "vescale_b200.model.patch.vp_cross_entropy",
+    "vescale.utils.monkey_patch": "vescale_b200.utils.monkey_patch",
 }
-for _alias, _target in _ALIASES.items():
+def _resolve(fullname: str):
+    """Reference module path -> implementing module path: longest aliased prefix, remainder appended; unaliased names fall
+    through to the same path under ``vescale_b200``."""
+    parts = fullname.split(".")
+    for n in range(len(parts), 1, -1):
+        head = ".".join(parts[:n])
+        if head in _ALIASES:
+            return ".".join([_ALIASES[head]] + parts[n:])
+    return ".".join(["vescale_b200"] + parts[1:])
+
+
+class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """``import vescale.a.b`` yields the SAME module object as the implementing ``vescale_b200...`` module (not a second copy
+    executed under another name, which would break its relative imports and duplicate its state)."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if not fullname.startswith("vescale."):
+            return None
+        try:
+            importlib.import_module(_resolve(fullname))
+        except ImportError:
+            return None
+        return importlib.machinery.ModuleSpec(fullname, self)
+
+    def create_module(self, spec):
+        return sys.modules[_resolve(spec.name)]
+
+    def exec_module(self, module):
+        pass
+
+
+sys.meta_path.insert(0, _AliasFinder())
+for _alias, _target in _ALIASES.items():  # explicit entries first: some alias a module, not a package, under a dotted name
     try:
         sys.modules[_alias] = importlib.import_module(_target)
     except Exception:  # pragma: no cover - optional pieces

@@ -25,6 +25,7 @@ _LAZY = {
     "fully_shard": "parallel.fsdp", "FSDPAdamW": "optim",
     "PipeEngine": "parallel.pipe", "PipelineParallelPlan": "parallel.pipe", "construct_pipeline_stage": "parallel.pipe",
     "parallelize_experts": "parallel.moe",
+    "deprecated_function": "utils", "switch_dtensor_for_torch_export": "utils",
     "checkpoint": None, "emulator": None, "profiler": None, "debug": None, "utils": None, "models": None, "ops": None, "optim": None, "parallel": None, "comm": None,
 }
 __all__ += [k for k in _LAZY]

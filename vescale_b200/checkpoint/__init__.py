@@ -19,4 +19,5 @@ Parity: ``legacy/vescale/checkpoint/__init__.py``, ``api/vescale_checkpointer.py
 """
 from .api import VeScaleCheckpointer, load, save, wait_for_async  # noqa: F401
 from .pinned_pool import PinnedPool  # noqa: F401
+from .meta_type import MODEL_STR, OPTIMIZER_STR, STATE_DICT_TYPE, CheckpointState, Stateful, SupportedStrategy  # noqa: F401
 from .mem_server import MemFileClient, MemFileServer  # noqa: F401

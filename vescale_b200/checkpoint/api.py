@@ -106,7 +106,20 @@ def _async_group():
     return _ASYNC_PG["pg"]
 
 
-class VeScaleCheckpointer:
+class BaseCheckpointer:
+    """Interface of a checkpointer: class-level ``save`` / ``load`` over a checkpoint state (legacy
+    ``checkpoint/api/base_checkpointer.py``)."""
+
+    @classmethod
+    def save(cls, path: str, checkpoint_state: Dict[str, Any]):
+        raise NotImplementedError
+
+    @classmethod
+    def load(cls, path: str, checkpoint_state: Dict[str, Any]):
+        raise NotImplementedError
+
+
+class VeScaleCheckpointer(BaseCheckpointer):
     @classmethod
     def save(cls, path: str, checkpoint_state: Dict[str, Any], async_checkpoint: bool = False) -> Optional[List[Future]]:
         import torch.distributed.checkpoint as dcp

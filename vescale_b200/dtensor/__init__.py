@@ -31,6 +31,9 @@ from .api import (  # noqa: F401
     rand,
     randn,
     redistribute_dtensor,
+    vescale_all_gather,
+    vescale_all_reduce,
+    vescale_reduce_scatter,
     to_local,
     zeros,
 )
@@ -39,11 +42,14 @@ from . import rules  # noqa: F401  (registers sharding rules)
 from . import handlers  # noqa: F401  (registers custom op handlers)
 from .random import manual_seed  # noqa: F401
 from .loss import loss_parallel  # noqa: F401
-from .collective_api import vescale_all_gather, vescale_all_reduce, vescale_reduce_scatter  # noqa: F401
 from .cross_mesh import cross_mesh_redistribute  # noqa: F401
+from ..layout import compute_local_shape, compute_local_shape_and_global_offset  # noqa: F401
+from ..mesh import mesh_resources  # noqa: F401
+from ..placement import normalize_placements  # noqa: F401
+from .api import is_zero_out_local_shard, make_dtensor, normalize_to_torch_size  # noqa: F401
 
 __all__ = [
-    "DTensor", "DeviceMesh", "init_device_mesh", "distribute_tensor", "from_local", "to_local", "redistribute_dtensor",
+    "DTensor", "DeviceMesh", "init_device_mesh", "distribute_tensor", "from_local", "to_local", "redistribute_dtensor", "vescale_all_gather", "vescale_all_reduce", "vescale_reduce_scatter",
     "ones", "empty", "full", "rand", "randn", "zeros", "arange", "equal", "allclose", "DTensorSpec", "TensorMeta", "Placement", "Shard",
     "Replicate", "Partial", "_Partial", "RaggedShard", "_StridedRaggedShard", "_StridedShard", "InterleavedShard",
     "is_ragged_shard", "implicit_replication", "manual_seed", "loss_parallel", "get_sub_spec",

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Any, Optional, Sequence, Tuple
+from typing import Any, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -33,6 +33,9 @@ __all__ = [
     "from_local",
     "to_local",
     "redistribute_dtensor",
+    "vescale_all_gather",
+    "vescale_all_reduce",
+    "vescale_reduce_scatter",
     "zeros",
     "ones",
     "empty",
@@ -294,6 +297,91 @@ def to_local(dt: DTensor, **kw) -> torch.Tensor:
 
 def redistribute_dtensor(dt: DTensor, device_mesh=None, placements=None, **kw) -> DTensor:
     return dt.redistribute(device_mesh, placements, **kw)
+
+
+def make_dtensor(local_tensor: torch.Tensor, device_mesh: DeviceMesh, placements, *, shape, dtype=None, requires_grad: bool = False, stride=None) -> DTensor:
+    """Assemble a DTensor from a local shard and explicit global metadata, no communication, no checks (legacy
+    ``dtensor/dtensor.py:560``)."""
+    from ..spec import contiguous_stride
+
+    shape = tuple(shape)
+    tm = TensorMeta(shape, tuple(stride) if stride is not None else contiguous_stride(shape), dtype or local_tensor.dtype)
+    return DTensor(local_tensor, DTensorSpec(device_mesh, tuple(placements), tm), requires_grad=requires_grad)
+
+
+def normalize_to_torch_size(size) -> torch.Size:
+    """``5`` / ``(2, 3)`` / ``((2, 3),)`` / ``torch.Size`` -> ``torch.Size`` (the forms factory functions accept)."""
+    if isinstance(size, torch.Size):
+        return size
+    if isinstance(size, int):
+        return torch.Size([size])
+    size = tuple(size)
+    if len(size) == 1 and not isinstance(size[0], int):
+        size = tuple(size[0])
+    return torch.Size(size)
+
+
+def is_zero_out_local_shard(mesh: DeviceMesh, placements: Sequence[Placement]) -> bool:
+    """For a factory-made tensor with ``Partial`` placements only the rank at coordinate 0 of every Partial mesh dim holds the
+    value; every other rank must hold zeros so that the pending sum reproduces it (legacy ``dtensor/_utils.py:287``)."""
+    coord = mesh.get_coordinate()
+    if coord is None:
+        return False
+    return any(p.is_partial() and coord[i] != 0 for i, p in enumerate(placements))
+
+
+def _as_mesh_dims(dims, mesh: DeviceMesh) -> List[int]:
+    if dims is None:
+        return []
+    if isinstance(dims, (int, str)):
+        dims = [dims]
+    return [mesh._dim_index(d) if isinstance(d, str) else int(d) % mesh.ndim for d in dims]
+
+
+def vescale_all_gather(dt: DTensor, mesh_dims=None, async_op: bool = True) -> DTensor:
+    """Collective-named view of ``redistribute`` (legacy ``dtensor/api.py:314-351``): the sharded mesh dims in ``mesh_dims``
+    (default: every sharded mesh dim) become ``Replicate``.  Differentiable like any redistribute."""
+    sharded = [i for i, p in enumerate(dt.placements) if p.is_shard()]
+    dims = _as_mesh_dims(mesh_dims, dt.device_mesh) or sharded
+    dst = list(dt.placements)
+    for d in dims:
+        if d not in sharded:
+            raise ValueError(f"mesh dim {d} is not sharded ({dt.placements}); nothing to all-gather")
+        dst[d] = Replicate()
+    return dt.redistribute(dt.device_mesh, dst, async_op=async_op)
+
+
+def vescale_all_reduce(dt: DTensor, mesh_dims=None, async_op: bool = True) -> DTensor:
+    """``Partial`` mesh dims in ``mesh_dims`` (default: all of them) become ``Replicate`` (legacy ``api.py:354-385``)."""
+    partial = [i for i, p in enumerate(dt.placements) if p.is_partial()]
+    dims = _as_mesh_dims(mesh_dims, dt.device_mesh) or partial
+    dst = list(dt.placements)
+    for d in dims:
+        if d not in partial:
+            raise ValueError(f"mesh dim {d} holds no pending reduction ({dt.placements}); nothing to all-reduce")
+        dst[d] = Replicate()
+    return dt.redistribute(dt.device_mesh, dst, async_op=async_op)
+
+
+def vescale_reduce_scatter(dt: DTensor, reduce_mesh_dims=None, scatter_dims=None, mesh_dims=None, async_op: bool = True) -> DTensor:
+    """Every ``Partial`` mesh dim is reduced; mesh dim ``mesh_dims[i]`` ends up ``Shard(scatter_dims[i])`` (a reduce-scatter when
+    it was ``Partial``), the other reduced dims ``Replicate`` (legacy ``api.py:388-436``)."""
+    if scatter_dims is None or mesh_dims is None:
+        raise ValueError("vescale_reduce_scatter needs scatter_dims and mesh_dims")
+    scatter_dims = [scatter_dims] if isinstance(scatter_dims, int) else list(scatter_dims)
+    mdims = _as_mesh_dims(mesh_dims, dt.device_mesh)
+    if len(mdims) != len(scatter_dims):
+        raise ValueError("scatter_dims and mesh_dims must have the same length")
+    partial = [i for i, p in enumerate(dt.placements) if p.is_partial()]
+    for d in _as_mesh_dims(reduce_mesh_dims, dt.device_mesh):
+        if d not in partial:
+            raise ValueError(f"mesh dim {d} holds no pending reduction ({dt.placements})")
+    dst = list(dt.placements)
+    for d in partial:
+        dst[d] = Replicate()
+    for sd, md in zip(scatter_dims, mdims):
+        dst[md] = Shard(sd % dt.ndim)
+    return dt.redistribute(dt.device_mesh, dst, async_op=async_op)
 
 
 # ------------------------------------------------------------------------------- distribute_tensor

@@ -252,6 +252,7 @@ _AUTO_WRAP_OPS = {
     aten.index.Tensor,
     aten.eq.Tensor,
     aten.embedding.default,
+    aten.embedding_dense_backward.default,
     aten.scatter.src,
     aten.scatter_.src,
 }

@@ -312,3 +312,17 @@ def get_rng_tracker() -> RNGStateTracker:
 
 def set_rng_tracker(tracker: Optional[RNGStateTracker]) -> None:
     _TRACKER["t"] = tracker
+
+
+def init_vescale_rng_tracker(device_type: str = "cuda") -> RNGStateTracker:
+    """Create and install the process-wide tracker: thread-based (single-device-equivalent sampling) when
+    ``VESCALE_SINGLE_DEVICE_RAND=1``, offset-based otherwise (legacy ``dtensor/random.py:30``)."""
+    set_rng_tracker(None)
+    return get_rng_tracker()
+
+
+def is_rng_supported_mesh(device_mesh) -> bool:
+    """DTensor random ops work on every mesh here: the Philox stream is evaluated per *global* element index, on the GPU by
+    ``csrc/philox_shard.cu`` and on the CPU by the reference implementation in this module (the reference supports CUDA
+    meshes only, ``dtensor/random.py:37``)."""
+    return device_mesh is not None and device_mesh.device_type in ("cuda", "cpu", "meta")

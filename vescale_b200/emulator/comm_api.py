@@ -13,7 +13,7 @@ from ..mesh import DeviceMesh
 from ..placement import Partial, Placement, Replicate
 from .collectives import EmulatorProcessGroup
 
-__all__ = ["distribute_tensor", "redistribute_dtensor", "full_tensor", "mesh_all_reduce", "mesh_all_gather", "mesh_reduce_scatter"]
+__all__ = ["distribute_tensor", "redistribute_dtensor", "full_tensor", "mesh_all_reduce", "mesh_all_gather", "mesh_reduce_scatter", "mesh_all_to_all", "mesh_broadcast", "mesh_scatter"]
 
 
 def _coords(mesh: DeviceMesh):
@@ -94,3 +94,33 @@ def full_tensor(locals_: List[torch.Tensor], shape: Sequence[int], mesh: DeviceM
 def redistribute_dtensor(locals_: List[torch.Tensor], shape: Sequence[int], mesh: DeviceMesh, src: Sequence[Placement], dst: Sequence[Placement], pg_kw=None) -> List[torch.Tensor]:
     full = full_tensor(locals_, shape, mesh, src, pg_kw)
     return distribute_tensor(full, mesh, dst)
+
+
+def mesh_all_to_all(locals_lists: List[List[torch.Tensor]], mesh: DeviceMesh, mesh_dim: int) -> List[List[torch.Tensor]]:
+    """``locals_lists[r][j]`` = what global rank r sends to the j-th member of its group along ``mesh_dim``; the result has
+    the same indexing on the receiving side (legacy ``emulator/mesh_collectives.py:115``)."""
+    out = [list(x) for x in locals_lists]
+    for ranks in _groups_along(mesh, mesh_dim):
+        for j, dst in enumerate(ranks):
+            out[dst] = [locals_lists[src][j].clone() for src in ranks]
+    return out
+
+
+def mesh_broadcast(locals_: List[torch.Tensor], mesh: DeviceMesh, mesh_dim: int = 0, src_index: int = 0) -> List[torch.Tensor]:
+    """Every group along ``mesh_dim`` copies the tensor of its ``src_index``-th member (legacy ``mesh_collectives.py:142``)."""
+    out = list(locals_)
+    for ranks in _groups_along(mesh, mesh_dim):
+        for r in ranks:
+            out[r] = locals_[ranks[src_index]].clone()
+    return out
+
+
+def mesh_scatter(scatter_lists: List[Optional[List[torch.Tensor]]], mesh: DeviceMesh, mesh_dim: int = 0, src_index: int = 0) -> List[torch.Tensor]:
+    """``scatter_lists[r]`` (needed only for each group's source) holds one tensor per group member; member j receives entry j
+    (legacy ``mesh_collectives.py:178``)."""
+    out: List[Optional[torch.Tensor]] = [None] * len(scatter_lists)
+    for ranks in _groups_along(mesh, mesh_dim):
+        src = scatter_lists[ranks[src_index]]
+        for j, r in enumerate(ranks):
+            out[r] = src[j].clone()
+    return out

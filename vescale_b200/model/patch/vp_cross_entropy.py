@@ -77,3 +77,32 @@ class VocabParallelCrossEntropy:
         per_tok = VocabParallelCrossEntropy.apply(logits, t.clamp(min=0))
         valid = (t != ignore_index).to(per_tok.dtype)
         return (per_tok * valid).sum() / valid.sum().clamp(min=1)
+
+    @staticmethod
+    def patch(root: torch.nn.Module) -> None:
+        """Post-patch every plain ``nn.CrossEntropyLoss`` under ``root`` (no class weights, no label smoothing — those keep the
+        stock forward, with a warning): when its input arrives as a DTensor sharded on the class dim, the loss is computed
+        vocab-parallel instead of gathering the logits (legacy ``model/patch/vp_cross_entropy.py:182-230``)."""
+        import types
+        import warnings
+
+        for path, sub in root.named_modules():
+            if not isinstance(sub, torch.nn.CrossEntropyLoss) or getattr(sub, "_vb_vp_patched", False):
+                continue
+            if sub.weight is not None or sub.label_smoothing != 0.0:
+                warnings.warn(f"CrossEntropyLoss `{path}` has class weights or label smoothing: left unpatched (no vocab-parallel path)", UserWarning)
+                continue
+            stock = sub.forward
+
+            def forward(self, input, target, _stock=stock):
+                if not isinstance(input, DTensor) or input.ndim != 2 or not any(isinstance(p, Shard) and p.dim % input.ndim == 1 for p in input.placements):
+                    return _stock(input, target)
+                t = target._local_tensor if isinstance(target, DTensor) else target
+                if self.reduction == "mean":
+                    return VocabParallelCrossEntropy.mean(input, t, self.ignore_index)
+                valid = t != self.ignore_index
+                per_tok = VocabParallelCrossEntropy.apply(input, t.clamp(min=0)) * valid.to(input.dtype)
+                return per_tok.sum() if self.reduction == "sum" else per_tok
+
+            sub.forward = types.MethodType(forward, sub)
+            sub._vb_vp_patched = True

@@ -57,6 +57,14 @@ def is_moe(module: nn.Module) -> bool:
     return isinstance(module, MoELayer)
 
 
+_TAG_EXPERTS_PARALLELIZED = "_vb_experts_parallelized"
+
+
+def is_experts_parallized(module: nn.Module) -> bool:
+    """True once ``parallelize_experts`` has run on ``module`` (legacy ``moe/_experts.py:39``; spelling kept)."""
+    return bool(getattr(module, _TAG_EXPERTS_PARALLELIZED, False))
+
+
 def parallelize_experts(module: nn.Module, experts_expr: str = r".*moe.*", ep_mesh=None, experts_allocator: Optional[ExpertsAllocator] = None, token_dispatcher: Optional[TokenDispatcher] = None, config: Optional[Dict] = None) -> nn.Module:
     rx = re.compile(experts_expr)
     group = ep_mesh.get_group(0) if ep_mesh is not None and ep_mesh.has_groups() else None
@@ -83,6 +91,7 @@ def parallelize_experts(module: nn.Module, experts_expr: str = r".*moe.*", ep_me
         for p in new.experts.parameters():
             p._is_expert_param = True
     module._ep_group = group
+    setattr(module, _TAG_EXPERTS_PARALLELIZED, True)
     return module
 
 

@@ -21,7 +21,7 @@ import torch
 
 from .p2p import P2PContext
 from .plan import PipelineParallelPlan, PipelineScheduleType
-from .schedule import INSTRUCTION_REGISTRY, Instr, build_schedule, stage_placement
+from .schedule import INSTRUCTION_REGISTRY, Instr, build_schedule, stage_placement, validate_pipeline_schedule
 from .stage import PipeModule
 
 __all__ = ["PipeEngine", "ScheduleEngine"]
@@ -149,6 +149,7 @@ class PipeEngine:
     def __init__(self, module: PipeModule, global_mesh=None, loss_fn: Optional[Callable] = None, plan: Optional[PipelineParallelPlan] = None, *, pp_group=None, pp_rank: Optional[int] = None, device=None):
         self.module = module
         self.plan = plan or module.plan
+        validate_pipeline_schedule(self.plan)
         self.loss_fn = loss_fn
         if global_mesh is not None and pp_rank is None:
             names = global_mesh.mesh_dim_names or ()

@@ -78,6 +78,20 @@ def stage_placement(P: int, V: int, schedule: PipelineScheduleType) -> List[Tupl
     return out
 
 
+def validate_pipeline_schedule(plan: PipelineParallelPlan) -> None:
+    """Consistency of schedule type and virtual chunks (legacy ``pipe_emmiter.py:345``: interleaved needs several chunks,
+    simple 1F1B exactly one) plus ZB-V's fixed two chunks.  GPipe and ZB-H1 run with any chunk count here."""
+    st, V = plan.schedule_type, plan.virtual_chunks
+    if st == PipelineScheduleType.INTERLEAVED_1F1B and V <= 1:
+        raise ValueError("INTERLEAVED_1F1B needs virtual_chunks > 1")
+    if st == PipelineScheduleType.SIMPLE_1F1B and V != 1:
+        raise ValueError(f"SIMPLE_1F1B needs virtual_chunks == 1, got {V}")
+    if st == PipelineScheduleType.ZERO_BUBBLE_V and V != 2:
+        raise ValueError("ZERO_BUBBLE_V needs virtual_chunks == 2")
+    if plan.num_stages < 1 or V < 1:
+        raise ValueError("num_stages and virtual_chunks must be positive")
+
+
 def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[List[Instr]]:
     P, V, M = plan.num_stages, plan.virtual_chunks, num_microbatches
     st = plan.schedule_type
@@ -138,6 +152,8 @@ def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[Li
         t = done.get(("B", m, v))
         return t
 
+    if st == PipelineScheduleType.INTERLEAVED_1F1B and not plan.forward_only and plan.max_inflight is None:
+        return _interleaved_schedule(P, V, M, place, cF, cB, cC)
     now = 0.0
     guard = 0
     while remaining:
@@ -183,6 +199,72 @@ def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[Li
                 raise RuntimeError(f"pipeline schedule deadlock at t={now} with {len(remaining)} ops left (in-flight limit too small?)")
             if future:
                 now = min(future)
+    return rows
+
+
+def _interleaved_schedule(P: int, V: int, M: int, place, cF: float, cB: float, cC: float) -> List[List[Instr]]:
+    """Interleaved 1F1B with the fixed per-rank operation order (legacy ``_schedules/looping_bfs.py``; Megatron's interleaving):
+    forwards go "P micro-batches through chunk 0, the same P through chunk 1, ..., next P micro-batches", backwards the same
+    with the chunks reversed; rank r runs ``2 (P - r - 1) + (V - 1) P`` warm-up forwards, then strictly alternates one
+    forward / one backward, then drains the backwards.  The order is fixed, start times follow from the dependencies.  (A
+    greedy oldest-first choice can fill the in-flight window with chunk-0 forwards whose backwards wait on chunk-1 forwards
+    that the window then blocks: a deadlock for M > 2P.)"""
+    seqs: List[List[Tuple[str, int, int]]] = []
+    for r in range(P):
+        fwd, bwd = [], []
+        for g0 in range(0, M, P):
+            grp = range(g0, min(g0 + P, M))
+            for c in range(V):
+                fwd += [(m, c * P + r) for m in grp]
+            for c in reversed(range(V)):
+                bwd += [(m, c * P + r) for m in grp]
+        n = len(fwd)
+        warm = min(n, 2 * (P - r - 1) + (V - 1) * P)
+        seq = [("F",) + x for x in fwd[:warm]]
+        for k in range(n - warm):
+            seq += [("F",) + fwd[warm + k], ("B",) + bwd[k]]
+        seq += [("B",) + x for x in bwd[n - warm:]]
+        seqs.append(seq)
+    NV = P * V
+    done: Dict[Tuple[str, int, int], float] = {}
+    rows: List[List[Instr]] = [[] for _ in range(P)]
+    free_at, pos = [0.0] * P, [0] * P
+
+    def ready(op, r) -> Optional[float]:
+        k, m, v = op
+        deps = []
+        if k == "F":
+            if v > 0:
+                deps.append((("F", m, v - 1), place[v - 1][0]))
+        else:
+            deps.append((("F", m, v), r))
+            if v < NV - 1:
+                deps.append((("B", m, v + 1), place[v + 1][0]))
+        t = 0.0
+        for d, src in deps:
+            if d not in done:
+                return None
+            t = max(t, done[d] + (cC if src != r else 0.0))
+        return t
+
+    left = sum(len(q) for q in seqs)
+    while left:
+        progressed = False
+        for r in range(P):
+            while pos[r] < len(seqs[r]):
+                op = seqs[r][pos[r]]
+                t = ready(op, r)
+                if t is None:
+                    break
+                start = max(t, free_at[r])
+                cost = cF if op[0] == "F" else cB
+                rows[r].append(Instr(op[0], op[1], op[2], place[op[2]][1], start, start + cost))
+                done[op] = free_at[r] = start + cost
+                pos[r] += 1
+                left -= 1
+                progressed = True
+        if not progressed:
+            raise RuntimeError("interleaved pipeline schedule deadlock (fixed operation order has a dependency cycle)")
     return rows
 
 

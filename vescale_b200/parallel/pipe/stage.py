@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .plan import PipelineParallelPlan, PipelineSplitMethodType, TracerType
+from .plan import PipelineParallelPlan, PipelineScheduleType, PipelineSplitMethodType, TracerType
 from .schedule import stage_placement
 
 __all__ = ["PipeModule", "construct_pipeline_stage", "split_units", "PipeParser"]
@@ -168,32 +168,94 @@ class PipeModule(nn.Module):
                     dist.all_reduce(p.grad, group=group)
 
 
-def construct_pipeline_stage(model: nn.Module, plan: PipelineParallelPlan, device_mesh=None, *, pp_rank: Optional[int] = None, pp_group=None, update_split_points: bool = False) -> PipeModule:
+def parse_model_graph(parser: "PipeParser", model: nn.Module, plan: PipelineParallelPlan):
+    """The model at split granularity: the ordered ``(fqn, module)`` units stages are cut between (legacy
+    ``pipe_parser.py:579`` returns the traced fx graph; here the hierarchy is the graph, tracers only change how the stage
+    modules are materialised)."""
+    return _units(model)
+
+
+def split_pipeline_point(model: nn.Module, plan: PipelineParallelPlan):
+    """Resolve the plan's split method into split-point FQNs (the last unit of every virtual stage but the last), store them
+    in ``plan.split_points`` and return ``(split_points, units, parser)`` (legacy ``pipe_parser.py:612``)."""
+    parser = PipeParser()
+    units = parse_model_graph(parser, model, plan)
+    groups = split_units(units, plan)
+    points = [units[g[-1]][0] for g in groups[:-1]]
+    plan.split_points = points
+    return points, units, parser
+
+
+def construct_pipeline_split_graph(model: nn.Module, plan: PipelineParallelPlan, update_split_points: bool = False) -> List[nn.Module]:
+    """All virtual-stage modules in order (legacy ``pipe_parser.py:632``)."""
+    if update_split_points:
+        method = plan.split_method
+        split_pipeline_point(model, plan)
+        plan.split_method = method
+    return PipeParser().parse(model, plan)
+
+
+def build_stage_module_and_dependency(stages: Sequence[nn.Module], num_stages: int, virtual_chunks: int, stage_id: int,
+                                      schedule_type: PipelineScheduleType = PipelineScheduleType.SIMPLE_1F1B):
+    """``(modules of pipeline rank stage_id keyed by local chunk, StageDeps, p2p input mapping)`` (legacy
+    ``pipe_stage.py:368``).  The mapping lists, per virtual stage, where its inputs come from: all outputs of the previous
+    virtual stage, in order (stage 0 reads the micro-batch)."""
+    from .schedule import StageDeps
+
+    place = stage_placement(num_stages, virtual_chunks, schedule_type)
+    mine = {c: stages[v] for v, (r, c) in enumerate(place) if r == stage_id}
+    deps = StageDeps(len(place))
+    mapping = {v: ([] if deps.prev(v) is None else [(deps.prev(v), None)]) for v in range(len(place))}
+    return mine, deps, mapping
+
+
+def _pp_coords(device_mesh, pp_rank, pp_group):
     if device_mesh is not None and pp_rank is None:
         names = device_mesh.mesh_dim_names or ()
         d = names.index("PP") if "PP" in names else 0
         pp_rank = device_mesh.get_local_rank(d)
         pp_group = device_mesh.get_group(d) if device_mesh.has_groups() else None
-    pp_rank = pp_rank or 0
-    stages = PipeParser().parse(model, plan)
+    return pp_rank or 0, pp_group
+
+
+def construct_stage_modules(model: nn.Module, plan: PipelineParallelPlan, device_mesh=None, update_split_points: bool = False, *, pp_rank: Optional[int] = None):
+    """Ingredients of a PipeModule for this rank: ``(stage modules, StageDeps, p2p input mapping)`` (legacy
+    ``pipe_stage.py:249``)."""
+    pp_rank, _ = _pp_coords(device_mesh, pp_rank, None)
+    stages = construct_pipeline_split_graph(model, plan, update_split_points)
+    return build_stage_module_and_dependency(stages, plan.num_stages, plan.virtual_chunks, pp_rank, plan.schedule_type)
+
+
+def build_shared_module_group(pipe_module: "PipeModule", stages: Sequence[nn.Module], num_stages: int, virtual_chunks: int,
+                              shared_module_path_groups, device_mesh=None, *, pp_group=None, units=None):
+    """One process group per tie (``shared_module_path_groups``: lists of module / parameter FQNs whose values and gradients are
+    kept in sync across stages, e.g. input embedding and LM head) over the pipeline ranks that own a member; appended to
+    ``pipe_module.shared_groups`` (legacy ``pipe_stage.py:311``).  Collective over the PP group."""
+    _, grp = _pp_coords(device_mesh, None, pp_group) if device_mesh is not None else (0, pp_group)
+    pp_group = grp or pipe_module.pp_group
+    if not shared_module_path_groups or pp_group is None:
+        return pipe_module.shared_groups
+    place = stage_placement(num_stages, virtual_chunks, pipe_module.plan.schedule_type)
+    mine = {int(c): m for c, m in pipe_module.stage_modules.items()}
+    for tie in shared_module_path_groups:
+        owners = sorted({place[v][0] for v, st in enumerate(stages) for t in tie if any(t in n or n in t for n in _stage_param_fqns(st, units))})
+        ranks = [dist.get_global_rank(pp_group, r) for r in owners] if len(owners) > 1 else None
+        g = dist.new_group(ranks) if ranks else None
+        if g is not None and pipe_module.pp_rank in owners:
+            ps = [p for c, m in mine.items() for n, p in m.named_parameters() if any(_match_tie(n, m, t) for t in tie)]
+            pipe_module.shared_groups.append((ps, g))
+    return pipe_module.shared_groups
+
+
+def construct_pipeline_stage(model: nn.Module, plan: PipelineParallelPlan, device_mesh=None, *, pp_rank: Optional[int] = None, pp_group=None, update_split_points: bool = False) -> PipeModule:
+    """Raw model -> this rank's ``PipeModule`` (legacy ``pipe_stage.py:285``)."""
+    pp_rank, pp_group = _pp_coords(device_mesh, pp_rank, pp_group)
+    stages = construct_pipeline_split_graph(model, plan, update_split_points)
+    mine, _, _ = build_stage_module_and_dependency(stages, plan.num_stages, plan.virtual_chunks, pp_rank, plan.schedule_type)
     place = stage_placement(plan.num_stages, plan.virtual_chunks, plan.schedule_type)
-    mine, vmap = {}, {}
-    for v, (r, c) in enumerate(place):
-        if r == pp_rank:
-            mine[c] = stages[v]
-            vmap[c] = v
+    vmap = {c: v for v, (r, c) in enumerate(place) if r == pp_rank}
     pm = PipeModule(mine, vmap, plan, pp_rank, pp_group)
-    # tied parameters: create one group per tie over the ranks that own a member
-    if plan.shared_modules and pp_group is not None:
-        all_names = [{n for n, _ in s.named_parameters()} for s in stages]
-        units = _units(model)
-        for tie in plan.shared_modules:
-            owners = sorted({place[v][0] for v, s in enumerate(stages) for t in tie if any(t in n or n in t for n in _stage_param_fqns(s, units))})
-            ranks = [dist.get_global_rank(pp_group, r) for r in owners] if len(owners) > 1 else None
-            grp = dist.new_group(ranks) if ranks else None
-            if grp is not None and pp_rank in owners:
-                ps = [p for c, m in mine.items() for n, p in m.named_parameters() if any(_match_tie(n, m, t) for t in tie)]
-                pm.shared_groups.append((ps, grp))
+    build_shared_module_group(pm, stages, plan.num_stages, plan.virtual_chunks, plan.shared_modules, pp_group=pp_group, units=_units(model))
     return pm
 
 

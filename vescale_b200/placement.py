@@ -312,3 +312,11 @@ def normalize_placements(placements, mesh_ndim: int, tensor_ndim: Optional[int] 
             p = type(p)(**kw)
         out.append(p)
     return tuple(out)
+
+
+def __getattr__(name):  # ``vescale.dtensor.placement_types`` also carries DTensorSpec / TensorMeta in the reference
+    if name in ("DTensorSpec", "TensorMeta"):
+        from . import spec
+
+        return getattr(spec, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

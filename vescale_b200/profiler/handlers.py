@@ -13,6 +13,13 @@ class NDHandler:
         raise NotImplementedError
 
 
+class DoNothingNDHandler(NDHandler):
+    """Accepts and drops records (measuring the timers' own overhead; legacy ``handlers/do_nothing_handler.py``)."""
+
+    def __call__(self, records, rank, step):
+        return None
+
+
 class ChromeTraceNDHandler(NDHandler):
     """One ``chrome://tracing`` / perfetto JSON per rank; timestamps are on the aligned global clock, so files
     from all ranks can be concatenated into one timeline (legacy ``handlers/chrome_trace_event.py``)."""
@@ -85,3 +92,11 @@ class LocalTimelineNDHandler(NDHandler):
         with open(tmp, "w") as f:
             json.dump({"traceEvents": self.events, "displayTimeUnit": "ms"}, f)
         os.replace(tmp, self.path)
+
+
+def __getattr__(name):  # ``handlers.SockNDHandler`` lives with its protocol in sock_streamer.py (which imports this module)
+    if name == "SockNDHandler":
+        from .sock_streamer import SockNDHandler
+
+        return SockNDHandler
+    raise AttributeError(name)

@@ -19,9 +19,14 @@ import struct
 import threading
 from typing import Callable, List, Optional, Sequence
 
+from .exceptions import ProtocolValidationError
 from .handlers import NDHandler
 
-__all__ = ["encode_frame", "decode_frames", "SockNDHandler", "NDtimelineStreamer"]
+__all__ = ["encode_frame", "decode_frames", "SockNDHandler", "NDtimelineStreamer", "dumps_fn", "loads_fn", "encode_package", "serialize_to_package", "SOCK_PARENT_DIR", "SOCK_PATH", "SOCK_TIMEOUT_CLIENT"]
+
+SOCK_PARENT_DIR = os.environ.get("VESCALE_NDTIMELINE_SOCK_DIR", "/tmp/ndtimeline")
+SOCK_PATH = os.path.join(SOCK_PARENT_DIR, "ndtimeline.sock")  # default collector socket of this host
+SOCK_TIMEOUT_CLIENT = 10.0  # seconds a training rank waits for the collector to accept
 
 _MAGIC = b"NDTL"
 _VERSION = 1
@@ -34,12 +39,30 @@ def encode_frame(records: List[dict], rank: int, step: int, kind: int = KIND_REC
     return _HDR.pack(_MAGIC, _VERSION, kind, rank & 0xFFFF, step & 0xFFFFFFFF, len(payload)) + payload
 
 
+# generic payload helpers under the reference's names (legacy ``binary_protocol.py:75-90``, ``sock_streamer.py``)
+def dumps_fn(v) -> bytes:
+    return json.dumps(v, separators=(",", ":")).encode()
+
+
+def loads_fn(b: bytes):
+    return json.loads(b)
+
+
+def encode_package(payload: bytes, rank: int = 0, step: int = 0, kind: int = KIND_RECORDS) -> bytes:
+    """Frame an already serialised payload."""
+    return _HDR.pack(_MAGIC, _VERSION, kind, rank & 0xFFFF, step & 0xFFFFFFFF, len(payload)) + payload
+
+
+def serialize_to_package(v, rank: int = 0, step: int = 0) -> bytes:
+    return encode_package(dumps_fn(v), rank, step)
+
+
 def decode_frames(buf: bytearray):
     """Yield (kind, rank, step, records) for every complete frame at the head of ``buf`` and consume it."""
     while len(buf) >= _HDR.size:
         magic, ver, kind, rank, step, n = _HDR.unpack_from(buf, 0)
         if magic != _MAGIC or ver != _VERSION:
-            raise ValueError("ndtimeline stream: bad frame header")
+            raise ProtocolValidationError("ndtimeline stream: bad frame header")
         if len(buf) < _HDR.size + n:
             return
         payload = bytes(buf[_HDR.size : _HDR.size + n])

@@ -11,18 +11,21 @@ API falls back to ``perf_counter``.  Records are handed to handlers by a backgro
 from __future__ import annotations
 
 import contextlib
+import dataclasses
 import functools
 import threading
 import time
 from enum import IntEnum
-from typing import List, Optional, Sequence
+from typing import Any, Callable, Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 from .handlers import NDHandler
+from .pool import CudaEventPool
+from .world_info import WorldInfo
 
-__all__ = ["NDTimerManager", "NDMetricLevel", "init_ndtimers", "ndtimeit", "ndtimeit_p2p", "ndtimer", "flush", "wait", "inc_step", "set_global_step", "is_initialized"]
+__all__ = ["NDTimerManager", "NDMetricLevel", "init_ndtimers", "ndtimeit", "ndtimeit_p2p", "ndtimer", "flush", "wait", "inc_step", "set_global_step", "is_initialized", "DeviceTimerMeta", "NDTimerManagerSingleton"]
 
 
 class NDMetricLevel(IntEnum):
@@ -38,25 +41,53 @@ class NDMetricLevel(IntEnum):
     TRACE = 104
 
 
-class _EventPool:
-    def __init__(self):
-        self.free: List = []
+@dataclasses.dataclass
+class DeviceTimerMeta:
+    """Declaration of a named timer (legacy ``ndtimeline/timer.py:191-236``): its verbosity level, whether it is enabled, which
+    tag keys a call site may attach, and extra fields merged into every record.  Registered through
+    ``NDTimerManager.register_timers``; undeclared metrics keep working with the level passed at the call site."""
 
-    def get(self):
-        return self.free.pop() if self.free else torch.cuda.Event(enable_timing=True)
+    name: str = ""
+    is_cpu_op: bool = False
+    legal_tags: List[str] = dataclasses.field(default_factory=list)
+    step_getter: Optional[Callable] = None
+    enabled: bool = True
+    level: NDMetricLevel = NDMetricLevel.FRAMEWORK_DEBUG
+    device_id: int = -1
+    dispatch_mode: str = "all"  # "all" handlers, or only those named in dst_names ("selected")
+    dst_names: List[str] = dataclasses.field(default_factory=list)
+    specified_extra: Dict[str, Any] = dataclasses.field(default_factory=dict)
+    common_extra: Dict[str, Any] = dataclasses.field(default_factory=dict)
 
-    def put(self, e):
-        self.free.append(e)
+    def __post_init__(self):
+        if self.dispatch_mode not in ("selected", "all"):
+            raise ValueError(f"invalid dispatch_mode {self.dispatch_mode}")
+        if not isinstance(self.level, NDMetricLevel):
+            raise ValueError(f"invalid type of level {type(self.level)}")
+
+    def copy(self) -> "DeviceTimerMeta":
+        return dataclasses.replace(self, legal_tags=list(self.legal_tags), dst_names=list(self.dst_names), specified_extra=dict(self.specified_extra),
+                                   common_extra=dict(self.common_extra))
 
 
 class NDTimerManager:
     """Pooled CUDA-event timers on a cross-rank aligned clock with asynchronous flush to handlers (legacy ``ndtimeline/timer.py:410-665``)."""
-    def __init__(self, rank: int = 0, world_size: int = 1, handlers: Sequence[NDHandler] = (), level: NDMetricLevel = NDMetricLevel.TRACE, group=None):
+    def __init__(self, rank: int = 0, world_size: int = 1, handlers: Sequence[NDHandler] = (), level: NDMetricLevel = NDMetricLevel.TRACE, group=None,
+                 world_info: Optional[WorldInfo] = None, metas: Sequence[DeviceTimerMeta] = ()):
         self.rank, self.world_size = rank, world_size
         self.handlers = list(handlers)
         self.level = level
+        self.world_info = world_info or WorldInfo(rank=rank, world_size=max(1, world_size))
+        for h in self.handlers:  # handlers may label their output with the producer's coordinates
+            if getattr(h, "world_info", None) is None:
+                try:
+                    h.world_info = self.world_info
+                except AttributeError:
+                    pass
+        self.metas: Dict[str, DeviceTimerMeta] = {}
+        self.register_timers(metas)
         self.cuda = torch.cuda.is_available()
-        self.pool = _EventPool()
+        self.pool = CudaEventPool() if self.cuda else None
         self.open: List[dict] = []
         self.step = 0
         self._lock = threading.Lock()
@@ -83,14 +114,28 @@ class NDTimerManager:
         self.ref_host_us = time.time_ns() / 1e3 - self.clock_offset_us
         self.ref_perf = time.perf_counter()
 
+    def register_timers(self, metas: Sequence[DeviceTimerMeta]) -> None:
+        for m in metas:
+            self.metas[m.name] = m.copy()
+
     # ------------------------------------------------------------------ regions
     @contextlib.contextmanager
     def timeit(self, metric: str, level: NDMetricLevel = NDMetricLevel.INFO, stream=None, tags: Optional[dict] = None):
-        if level > self.level:
+        meta = self.metas.get(metric)
+        if meta is not None:
+            level = meta.level
+            bad = [k for k in (tags or {}) if meta.legal_tags and k not in meta.legal_tags]
+            if bad:
+                raise ValueError(f"timer {metric!r} does not declare tags {bad} (legal: {meta.legal_tags})")
+        if level > self.level or (meta is not None and not meta.enabled):
             yield
             return
-        rec = {"metric": metric, "tags": tags or {}, "step": self.step}
-        if self.cuda:
+        rec = {"metric": metric, "tags": tags or {}, "step": self.step if meta is None or meta.step_getter is None else meta.step_getter()}
+        if meta is not None:
+            rec["tags"] = {**meta.common_extra, **meta.specified_extra, **rec["tags"]}
+            if meta.dispatch_mode == "selected":
+                rec["dst_names"] = list(meta.dst_names)
+        if self.cuda and not (meta is not None and meta.is_cpu_op):
             s = stream or torch.cuda.current_stream()
             e0, e1 = self.pool.get(), self.pool.get()
             e0.record(s)
@@ -131,7 +176,11 @@ class NDTimerManager:
         def work():
             done = self._materialise(recs)
             for h in self.handlers:
-                h(done, self.rank, step)
+                # records of a "selected"-dispatch timer only reach the handlers it names (by class name or `.name`)
+                hn = (getattr(h, "name", None), type(h).__name__)
+                mine = [r for r in done if "dst_names" not in r or any(n in r["dst_names"] for n in hn)]
+                if mine or not done:
+                    h(mine, self.rank, step)
 
         if asynchronous:
             t = threading.Thread(target=work, daemon=True)
@@ -149,10 +198,22 @@ class NDTimerManager:
 _MANAGER: Optional[NDTimerManager] = None
 
 
-def init_ndtimers(rank: int = 0, world_size: int = 1, handlers: Sequence[NDHandler] = (), level: NDMetricLevel = NDMetricLevel.TRACE, group=None, **_kw) -> NDTimerManager:
+def init_ndtimers(rank: int = 0, world_size: int = 1, handlers: Sequence[NDHandler] = (), level: NDMetricLevel = NDMetricLevel.TRACE, group=None,
+                  world_info: Optional[WorldInfo] = None, metas: Sequence[DeviceTimerMeta] = (), **_kw) -> NDTimerManager:
     global _MANAGER
-    _MANAGER = NDTimerManager(rank, world_size, handlers, level, group)
+    _MANAGER = NDTimerManager(rank, world_size, handlers, level, group, world_info=world_info, metas=metas)
     return _MANAGER
+
+
+class NDTimerManagerSingleton:
+    """``NDTimerManagerSingleton()`` is the process-wide manager created by ``init_ndtimers`` (legacy ``timer.py:693``); a
+    default single-rank manager is created on first use when none exists."""
+
+    def __new__(cls, *a, **kw):
+        global _MANAGER
+        if _MANAGER is None:
+            _MANAGER = NDTimerManager(*a, **kw)
+        return _MANAGER
 
 
 def is_initialized() -> bool:

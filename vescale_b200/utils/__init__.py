@@ -3,3 +3,4 @@
 from .env import FLAGS, describe_flags, flag  # noqa: F401
 from .mfu import llama_mfu, mixtral_flops_per_token, model_tflops  # noqa: F401
 from .monkey_patch import patch_method, unpatch_all  # noqa: F401
+from .compat import deprecated_function, switch_dtensor_for_torch_export  # noqa: F401
