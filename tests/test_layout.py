@@ -122,3 +122,44 @@ def test_placement_reprs_and_hash():
     assert p == RaggedShard((0,), [1, 2]) and hash(p) == hash(RaggedShard((0,), (1, 2)))
     assert Shard(1) != _StridedShard(1, split_factor=2)
     assert Replicate() == Replicate() and p.is_ragged_shard() and not Shard(0).is_ragged_shard()
+
+
+def test_general_break_ragged_box_reference_entry_point():
+    """``vescale.dtensor.vescale_utils.checkpoint._break_ragged_box``: any contiguous dim range flattened, the shard an n-d box in
+    that ragged view; the returned boxes tile it exactly (sampled version of the reference's brute-force test
+    ``test/dtensor/cpu_only/test_break_ragged_box.py``, which passes in full against this implementation)."""
+    import itertools
+    import math
+    import random
+
+    import torch
+    from vescale.dtensor.vescale_utils.checkpoint import _break_ragged_box
+
+    rnd = random.Random(7)
+    worst = 0
+    for shape in [(5,), (3, 4), (4, 3, 5), (2, 3, 4, 3), (3, 2, 2, 3, 2)]:
+        n = len(shape)
+        for d0, d1 in itertools.combinations_with_replacement(range(n), 2):
+            rdims = tuple(range(d0, d1 + 1))
+            rshape = shape[:d0] + (math.prod(shape[d0 : d1 + 1]),) + shape[d1 + 1 :]
+            for _ in range(60):
+                rect = []
+                for s in rshape:
+                    a = rnd.randint(0, s - 1)
+                    rect.append((a, rnd.randint(a, s)))
+                sizes, offs = _break_ragged_box(tuple(e - s for s, e in rect), tuple(s for s, _ in rect), rdims, shape, shape, (0,) * n)
+                worst = max(worst, len(sizes))
+                t = torch.zeros(shape, dtype=torch.int64)
+                for sz, of in zip(sizes, offs):
+                    t[tuple(slice(o, o + z) for o, z in zip(of, sz))] += 1
+                want = torch.zeros(rshape, dtype=torch.int64)
+                want[tuple(slice(s, e) for s, e in rect)] = 1
+                assert torch.equal(t.view(rshape), want), (shape, rdims, rect)
+    assert worst <= 2 * 5 - 1
+    # a shard of a row-sharded tensor: ragged offsets are global flat positions, results come back in global coordinates
+    sizes, offs = _break_ragged_box((7,), (4 * 3 + 2,), (0, 1), (4, 3), (8, 3), (4, 0))
+    t = torch.zeros(8, 3, dtype=torch.int64)
+    for sz, of in zip(sizes, offs):
+        t[tuple(slice(o, o + z) for o, z in zip(of, sz))] += 1
+    assert t.view(-1)[14:21].eq(1).all() and t.sum() == 7
+    assert _break_ragged_box((0,), (), (0,), (4,), (4,), (0,)) == ([], [])

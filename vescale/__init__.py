@@ -55,6 +55,7 @@ _ALIASES = {
     "vescale.dtensor.sharding_prop": "vescale_b200.dtensor.sharding_prop",
     "vescale.dtensor.vescale_utils": "vescale_b200.dtensor.vescale_utils",
     "vescale.dtensor.vescale_utils.ragged_shard_utils": "vescale_b200.dtensor.vescale_utils",
+    "vescale.dtensor.vescale_utils.checkpoint": "vescale_b200.dtensor.vescale_utils.checkpoint",
     "vescale.dmodule._dmodule": "vescale_b200.parallel.dmodule.api",
     "vescale.dmodule.placements_interface": "vescale_b200.parallel.dmodule.api",
     "vescale.ddp.grad_buffer": "vescale_b200.parallel.ddp",

@@ -22,7 +22,7 @@ from ..layout import (
     local_boxes,
     shape_and_offset_before_ragged,
 )
-from ..mesh import DeviceMesh, mesh_resources
+from ..mesh import DeviceMesh, as_mesh, mesh_resources
 from ..placement import Partial, Placement, RaggedShard, Replicate, Shard, normalize_placements
 from ..spec import DTensorSpec, TensorMeta, contiguous_stride
 from .redistribute import Redistribute, redistribute_local_tensor
@@ -51,7 +51,7 @@ __all__ = [
 
 
 def _resolve_mesh(mesh: Optional[DeviceMesh]) -> DeviceMesh:
-    return mesh if mesh is not None else mesh_resources.get_current_mesh()
+    return as_mesh(mesh) if mesh is not None else mesh_resources.get_current_mesh()
 
 
 class _FromLocal(torch.autograd.Function):
@@ -229,7 +229,7 @@ class DTensor(torch.Tensor):
         *,
         async_op: bool = False,
     ) -> "DTensor":
-        mesh = device_mesh or self.device_mesh
+        mesh = as_mesh(device_mesh) or self.device_mesh
         if placements is None:
             raise RuntimeError("placements is needed for redistribute")
         placements = normalize_placements(placements, mesh.ndim, self.ndim)

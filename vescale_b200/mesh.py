@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import torch
 import torch.distributed as dist
 
-__all__ = ["DeviceMesh", "init_device_mesh", "mesh_resources"]
+__all__ = ["DeviceMesh", "init_device_mesh", "mesh_resources", "as_mesh"]
 
 
 class _MeshEnv(threading.local):
@@ -287,3 +287,30 @@ def init_device_mesh(
             raise ValueError(f"mesh_shape {tuple(mesh_shape)} does not cover world size {dist.get_world_size()}")
     mesh = torch.arange(n, dtype=torch.int64).reshape(tuple(mesh_shape))
     return DeviceMesh(device_type, mesh, mesh_dim_names=mesh_dim_names, **kw)
+
+
+def as_mesh(mesh):
+    """Accept a ``torch.distributed.device_mesh.DeviceMesh`` wherever a mesh is expected (the reference's new package is built on
+    torch's mesh class, ``vescale/dtensor/_api.py``): it is converted once — same rank grid, dim names and per-dim process
+    groups, no new communicators — and the result is cached on the torch object.  Our own meshes pass through."""
+    if mesh is None or isinstance(mesh, DeviceMesh):
+        return mesh
+    cached = getattr(mesh, "_vb_mesh", None)
+    if cached is not None:
+        return cached
+    if not (hasattr(mesh, "mesh") and hasattr(mesh, "device_type") and hasattr(mesh, "get_group")):
+        raise TypeError(f"expected a DeviceMesh, got {type(mesh).__name__}")
+    grid = mesh.mesh.detach().cpu()
+    groups = None
+    if dist.is_available() and dist.is_initialized():
+        try:
+            groups = [mesh.get_group(i) for i in range(grid.ndim)]
+        except Exception:  # noqa: BLE001  (fake / meta meshes without communicators)
+            groups = None
+    names = getattr(mesh, "mesh_dim_names", None)
+    ours = DeviceMesh(mesh.device_type, grid, mesh_dim_names=tuple(names) if names else None, _dim_groups=groups, _init_process_groups=groups is not None)
+    try:
+        mesh._vb_mesh = ours
+    except AttributeError:
+        pass
+    return ours

@@ -41,6 +41,10 @@ class DTensorSpec:
     __slots__ = ("mesh", "placements", "tensor_meta", "_hash")
 
     def __init__(self, mesh: DeviceMesh, placements: Sequence[Placement], tensor_meta: Optional[TensorMeta] = None):
+        if not isinstance(mesh, DeviceMesh):
+            from .mesh import as_mesh
+
+            mesh = as_mesh(mesh)  # a torch.distributed DeviceMesh (the reference's new package is built on it)
         self.mesh = mesh
         self.placements = tuple(placements)
         self.tensor_meta = tensor_meta
