@@ -83,7 +83,7 @@ class OpDispatcher:
                     raise RuntimeError(f"{op}: DTensor operands live on different meshes")
                 return a._spec, a._local_tensor
             if isinstance(a, torch.Tensor):
-                if a.ndim == 0 or a.numel() == 1 or _IMPLICIT_REPLICATION[0] or op in _AUTO_WRAP_OPS:
+                if a.ndim == 0 or a.numel() == 1 or _IMPLICIT_REPLICATION[0] or op in _AUTO_WRAP_OPS or _torch_implicit_replication():
                     spec = DTensorSpec(mesh, tuple(Replicate() for _ in range(mesh.ndim)), TensorMeta(tuple(a.shape), tuple(a.stride()), a.dtype))
                     return spec, a
                 raise RuntimeError(
@@ -242,6 +242,18 @@ class OpDispatcher:
 
 
 # ops for which plain tensors are silently treated as replicated (reference ``_dispatch.py:281-315``)
+def _torch_implicit_replication() -> bool:
+    """torch's own ``implicit_replication()`` context manager (``torch.distributed.tensor.experimental``) is honoured too: code
+    written against the reference's new package, which rides on torch's dispatcher, uses that one.  Only consulted on the
+    about-to-fail path."""
+    try:
+        from torch.distributed.tensor import DTensor as _TorchDTensor
+
+        return bool(getattr(_TorchDTensor._op_dispatcher, "_allow_implicit_replication", False))
+    except Exception:  # noqa: BLE001
+        return False
+
+
 _AUTO_WRAP_OPS = {
     aten._foreach_mul_.Tensor,
     aten._foreach_norm.Scalar,
