@@ -256,3 +256,58 @@ def test_ops_and_autograd():
 
 def test_factories_and_random():
     run_distributed(_factories_random, 4)
+
+
+def _torch_mesh_strided_ragged_2d(rank, world):
+    """The reference's ``test_ragged_shard_2d`` scenario at CPU-sized tensors (``test/dtensor/ragged_shard/test_redistribute.py:
+    217-300``): meshes are ``torch.distributed.device_mesh`` objects (the reference's new package is built on them), a
+    Shard(s) DTensor's local tensor is ragged-sharded over a second mesh dim, the 2-D spec ``[_StridedRaggedShard | RaggedShard,
+    Shard(s)]`` is assembled by hand with ``DTensorSpec`` / ``DTensor(...)``, and ``full_tensor()`` must reproduce the original."""
+    import math
+
+    import numpy as np
+    from torch.distributed.device_mesh import init_device_mesh as torch_init_device_mesh
+
+    from vescale.dtensor import DTensor, distribute_tensor
+    from vescale.dtensor.placement_types import DTensorSpec, RaggedShard, Shard, TensorMeta, _StridedRaggedShard
+
+    np.random.seed(42)
+    torch.manual_seed(42)
+
+    def units(N, k):
+        if np.random.randint(1, 5) == 1:  # everything on one rank (the Muon gather-to-root layout)
+            rt = np.random.randint(0, k)
+            return tuple(1 if i == rt else 0 for i in range(k))
+        return tuple(int(x) for x in np.random.multinomial(N, np.full(k, 1.0 / k)))
+
+    for mesh_size in [(1, world), (2, world // 2), (world, 1)]:
+        dm = torch_init_device_mesh(device_type(), mesh_size, mesh_dim_names=["ragged", "other"])
+        for _ in range(3):
+            nums = [int(np.random.randint(3, 9)) * mesh_size[1] for _ in range(3)]
+            for input_size in (tuple(nums[:1]), tuple(nums[:2]), tuple(nums[:3])):
+                ndim = len(input_size)
+                g = torch.randn(input_size).to(device_type())
+                for rd, sd in [(d, 0) for d in range(ndim)] + ([(0, 1)] if ndim > 1 else []):
+                    dt_shard = distribute_tensor(g, dm["other"], [Shard(sd)])
+                    st = dt_shard._local_tensor
+                    rdims = tuple(range(rd + 1))
+                    lst = units(math.prod(st.shape[: rd + 1]), dm["ragged"].size())
+                    dt2 = distribute_tensor(st, dm["ragged"], [RaggedShard(rdims, lst)])
+                    first = _StridedRaggedShard(dims=rdims, local_units=lst, split_factor=dm["other"].size()) if sd == 0 else RaggedShard(dims=rdims, local_units=lst)
+                    spec = DTensorSpec(dm, [first, Shard(sd)], tensor_meta=TensorMeta(dt_shard.size(), dt_shard.stride(), dt_shard.dtype))
+                    d = DTensor(dt2._local_tensor, spec, requires_grad=True)
+                    full = d.full_tensor()
+                    assert full.shape == g.shape and torch.equal(full, g), (mesh_size, input_size, rd, sd, lst)
+    # torch's own implicit_replication() context manager is honoured by the dispatcher
+    from torch.distributed.tensor.experimental import implicit_replication as torch_implicit_replication
+
+    mesh1 = torch_init_device_mesh(device_type(), (world,))
+    z = distribute_tensor(torch.zeros(8, 6, dtype=torch.int64).to(device_type()), mesh1, (RaggedShard((0, 1), (0, 1, 5, 2)[:world] if world == 4 else (1,) * world),))
+    add = torch.arange(48).view(8, 6).to(device_type())
+    with torch_implicit_replication():
+        z.add_(add)
+    assert torch.equal(z.full_tensor(), add)
+
+
+def test_torch_device_mesh_and_strided_ragged_2d():
+    run_distributed(_torch_mesh_strided_ragged_2d, 4)

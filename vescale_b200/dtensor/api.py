@@ -156,7 +156,16 @@ class DTensor(torch.Tensor):
     __torch_function__ = torch._C._disabled_torch_function_impl
 
     @staticmethod
-    def __new__(cls, local_tensor: torch.Tensor, spec: DTensorSpec, *, requires_grad: bool = False):
+    def __new__(cls, local_tensor: torch.Tensor, spec, placements=None, *, requires_grad: bool = False, shape=None, dtype=None, stride=None):
+        if not isinstance(spec, DTensorSpec):
+            # legacy constructor form ``DTensor(local, device_mesh, placements, *, shape, dtype, requires_grad, stride)``
+            # (``legacy/vescale/dtensor/dtensor.py:268``); the reference's new package passes a DTensorSpec
+            mesh = as_mesh(spec)
+            if shape is None:
+                raise TypeError("DTensor(local, device_mesh, placements, ...) needs the global `shape`")
+            shape = tuple(shape)
+            pl = normalize_placements(placements, mesh.ndim, len(shape))
+            spec = DTensorSpec(mesh, pl, TensorMeta(shape, tuple(stride) if stride is not None else contiguous_stride(shape), dtype or local_tensor.dtype))
         tm = spec.tensor_meta
         r = torch.Tensor._make_wrapper_subclass(
             cls,
@@ -173,6 +182,10 @@ class DTensor(torch.Tensor):
 
     def __repr__(self, *, tensor_contents=None):
         return f"DTensor(local_tensor={self._local_tensor}, device_mesh={self._spec.mesh}, placements={self._spec.placements})"
+
+    def tolist(self):
+        """Nested list of THIS rank's local shard (legacy ``dtensor/dtensor.py`` ``tolist``); gather first for the full tensor."""
+        return self._local_tensor.tolist()
 
     # -- compile support (flatten protocol)
     def __tensor_flatten__(self):
@@ -208,6 +221,8 @@ class DTensor(torch.Tensor):
         run_check: bool = False,
         shape: Optional[Sequence[int]] = None,
         stride: Optional[Sequence[int]] = None,
+        support_uneven: bool = True,  # legacy knobs (``dtensor/api.py:39-118``): uneven shards are always supported here,
+        async_input: bool = True,  # and inputs need no explicit wait — both accepted and ignored
     ) -> "DTensor":
         mesh = _resolve_mesh(device_mesh)
         placements = normalize_placements(placements, mesh.ndim, len(shape) if shape is not None else local_tensor.ndim)
@@ -215,7 +230,7 @@ class DTensor(torch.Tensor):
             run_check = False
         return _FromLocal.apply(local_tensor, mesh, placements, run_check, tuple(shape) if shape is not None else None, tuple(stride) if stride is not None else None)
 
-    def to_local(self, *, grad_placements: Optional[Sequence[Placement]] = None) -> torch.Tensor:
+    def to_local(self, *, grad_placements: Optional[Sequence[Placement]] = None, async_output: bool = True) -> torch.Tensor:
         if not torch.is_grad_enabled():
             return self._local_tensor
         if grad_placements is not None:
@@ -233,9 +248,8 @@ class DTensor(torch.Tensor):
         if placements is None:
             raise RuntimeError("placements is needed for redistribute")
         placements = normalize_placements(placements, mesh.ndim, self.ndim)
-        for p in placements:
-            if p.is_partial() and not any(q == p for q in self.placements):
-                raise RuntimeError("Can not redistribute to Partial, redistributing to Partial is for internal use only")
+        # -> Partial is allowed, as in the legacy package (R2P keeps the value on coordinate 0 and zeros elsewhere, S2P pads):
+        # ``legacy/vescale/dtensor/redistribute.py``; torch and the reference's new package forbid it
         return Redistribute.apply(self, mesh, placements, async_op)
 
     def full_tensor(self, *, grad_placements: Optional[Sequence[Placement]] = None) -> torch.Tensor:
@@ -431,11 +445,16 @@ def distribute_tensor(
     broadcast over the mesh first); ``None`` skips communication and slices the caller's own tensor
     (reference ``_api.py:589-729``)."""
     mesh = _resolve_mesh(device_mesh)
+    if not tensor.is_leaf:
+        raise RuntimeError("`distribute_tensor` should be used to distribute leaf tensors, but found a non-leaf tensor (detach it, or use DTensor.from_local)")
     if isinstance(tensor, DTensor):
+        # already distributed: only the identity is accepted, as in torch and the reference (legacy ``api.py:206-221``)
         if tensor.device_mesh != mesh:
-            raise ValueError("cannot distribute a DTensor to a different mesh")
+            raise ValueError(f"Cannot distribute a DTensor with device mesh {tensor.device_mesh} to a different device mesh {mesh}.")
         pl = normalize_placements(placements, mesh.ndim, tensor.ndim)
-        return tensor if tensor.placements == pl else tensor.redistribute(mesh, pl)
+        if tensor.placements != pl:
+            raise ValueError(f"Cannot distribute a DTensor with placements {tensor.placements} to a different placements {pl}; call `redistribute` instead.")
+        return tensor
     placements = normalize_placements(placements, mesh.ndim, tensor.ndim)
     dev = mesh.device_type
     if dev not in ("meta",) and tensor.device.type != dev and not tensor.is_meta:
@@ -449,7 +468,7 @@ def distribute_tensor(
         local = torch.empty(compute_local_shape(tensor.shape, mesh, placements), dtype=tensor.dtype, device="meta")
     else:
         src = tensor.detach()
-        if src_data_rank is not None and mesh.has_groups() and mesh.size() > 1:
+        if src_data_rank is not None and mesh.has_groups() and mesh.size() > 1 and mesh.get_coordinate() is not None:
             src = _broadcast_from(src.contiguous().clone(), mesh, src_data_rank)
         if mesh.get_coordinate() is None:
             local = src.new_empty(0)
@@ -469,8 +488,15 @@ def _factory(kind: str, size, *, dtype=None, layout=torch.strided, requires_grad
     dtype = dtype or torch.get_default_dtype()
     dev = mesh.device_type
     local_shape = compute_local_shape(size, mesh, placements)
-    if any(p.is_partial() for p in placements) and kind not in ("empty", "zeros"):
-        raise ValueError(f"factory {kind} with Partial placements is ambiguous")
+    if any(p.is_partial() for p in placements):
+        # a value with a pending sum: the rank at coordinate 0 of every Partial mesh dim holds it, the others hold zeros (legacy
+        # ``dtensor/__init__.py:99``, ``is_zero_out_local_shard``); random factories would need a decomposition, not a fill
+        if kind in ("rand", "randn"):
+            raise ValueError(f"factory {kind} with Partial placements is ambiguous")
+        if any(p.is_partial() and p.reduce_op not in ("sum", "avg") for p in placements):
+            raise ValueError("factories support Partial(sum / avg) only")
+        if is_zero_out_local_shard(mesh, placements) and kind in ("ones", "full"):
+            kind = "zeros"
     if kind == "empty":
         local = torch.empty(local_shape, dtype=dtype, device=dev)
     elif kind == "zeros":
@@ -528,6 +554,8 @@ def _all_ranks_agree(ok: bool, mesh) -> bool:
     """AND of a per-rank boolean over every rank of ``mesh`` (one tiny all-reduce per mesh dim)."""
     from ..comm import collectives as C
 
+    if mesh.get_coordinate() is None or not mesh.has_groups():
+        return ok  # a rank outside the (sub-)mesh, or a mesh without communicators: nothing to agree with
     t = torch.tensor([1.0 if ok else 0.0], device=mesh.device_type if mesh.device_type != "meta" else "cpu")
     for d in range(mesh.ndim):
         if mesh.size(d) > 1:
@@ -535,20 +563,50 @@ def _all_ranks_agree(ok: bool, mesh) -> bool:
     return bool(t.item() > 0.5)
 
 
-def equal(a: DTensor, b: DTensor) -> bool:
-    """True on every rank iff the two DTensors have the same mesh, placements, global shape and bitwise-equal local shards on
-    *all* ranks (legacy ``dtensor/_utils.py:326-411`` ``equal``; a local mismatch anywhere makes every rank return False)."""
+def _same_global_metadata(a, b, exact_device: bool) -> bool:
+    """Everything about two DTensors that is identical on all ranks by construction (legacy ``dtensor/_utils.py:326-352``)."""
     if not (isinstance(a, DTensor) and isinstance(b, DTensor)):
-        raise TypeError("equal() compares two DTensors")
-    if a.device_mesh != b.device_mesh or tuple(a.placements) != tuple(b.placements) or tuple(a.shape) != tuple(b.shape):
         return False
-    return _all_ranks_agree(torch.equal(a._local_tensor, b._local_tensor), a.device_mesh)
+    if exact_device and a.device.type != b.device.type:
+        return False
+    if tuple(a.shape) != tuple(b.shape) or a.dtype != b.dtype or a.layout != b.layout or a.stride() != b.stride() or a.requires_grad != b.requires_grad:
+        return False
+    ma, mb = a._spec.mesh, b._spec.mesh
+    if (ma != mb) if exact_device else (not torch.equal(ma.mesh, mb.mesh)):
+        return False
+    return tuple(a.placements) == tuple(b.placements)
 
 
-def allclose(a: DTensor, b: DTensor, rtol: float = 1e-5, atol: float = 1e-8, equal_nan: bool = False) -> bool:
-    """``torch.allclose`` over all shards of two identically laid out DTensors, agreed on by every rank."""
-    if not (isinstance(a, DTensor) and isinstance(b, DTensor)):
-        raise TypeError("allclose() compares two DTensors")
-    if a.device_mesh != b.device_mesh or tuple(a.placements) != tuple(b.placements) or tuple(a.shape) != tuple(b.shape):
+def _same_local_metadata(t1: torch.Tensor, t2: torch.Tensor, exact_device: bool) -> bool:
+    if exact_device and t1.device.type != t2.device.type:
         return False
-    return _all_ranks_agree(torch.allclose(a._local_tensor, b._local_tensor, rtol=rtol, atol=atol, equal_nan=equal_nan), a.device_mesh)
+    return (t1.shape == t2.shape and t1.dtype == t2.dtype and t1.layout == t2.layout and t1.is_contiguous() == t2.is_contiguous() and t1.stride() == t2.stride()
+            and t1.storage_offset() == t2.storage_offset())
+
+
+def equal(a: DTensor, b: DTensor, exact_device: bool = True) -> bool:
+    """True on every rank iff the two DTensors agree in mesh, placements, global and local metadata (shape, dtype, strides,
+    ``requires_grad``, device type unless ``exact_device=False``) and have bitwise-equal local shards on *all* ranks (legacy
+    ``dtensor/_utils.py:326-385``, which compares the caller's shard only; here a mismatch anywhere makes every rank return
+    False).  Two meta DTensors with equal metadata are equal."""
+    if not _same_global_metadata(a, b, exact_device):
+        return False
+    if a.is_meta and b.is_meta:
+        return True
+    t1, t2 = a._local_tensor, b._local_tensor
+    ok = _same_local_metadata(t1, t2, exact_device) and (torch.equal(t1, t2) if exact_device else torch.equal(t1.cpu(), t2.cpu()))
+    return _all_ranks_agree(ok, a.device_mesh)
+
+
+def allclose(a: DTensor, b: DTensor, rtol: float = 1e-5, atol: float = 1e-8, equal_nan: bool = False, exact_device: bool = True) -> bool:
+    """``torch.allclose`` over all shards of two identically laid out DTensors, agreed on by every rank (metadata rules of
+    ``equal``)."""
+    if not _same_global_metadata(a, b, exact_device):
+        return False
+    if a.is_meta and b.is_meta:
+        return True
+    t1, t2 = a._local_tensor, b._local_tensor
+    if not exact_device:
+        t1, t2 = t1.cpu(), t2.cpu()
+    ok = _same_local_metadata(t1, t2, exact_device) and torch.allclose(t1, t2, rtol=rtol, atol=atol, equal_nan=equal_nan)
+    return _all_ranks_agree(ok, a.device_mesh)

@@ -234,7 +234,11 @@ class OpDispatcher:
         def mk(s):
             if s is None:
                 return None
-            return DTensor(torch.empty(0, dtype=s.dtype, device=s.mesh.device_type if s.mesh.device_type != "meta" else "cpu"), s)
+            dev = s.mesh.device_type if s.mesh.device_type != "meta" else "cpu"
+            # default value on a rank outside the (sub-)mesh: a zero for 0-d results, an empty tensor otherwise (legacy
+            # ``dtensor/dispatch.py`` "default value" contract, ``test_default_value_sub_mesh``)
+            local = torch.zeros((), dtype=s.dtype, device=dev) if len(s.shape) == 0 else torch.empty(0, dtype=s.dtype, device=dev)
+            return DTensor(local, s)
 
         if isinstance(spec, tuple):
             return tuple(mk(s) for s in spec)
@@ -265,6 +269,10 @@ _AUTO_WRAP_OPS = {
     aten.eq.Tensor,
     aten.embedding.default,
     aten.embedding_dense_backward.default,
+    aten.nll_loss_forward.default,
+    aten.nll_loss_backward.default,
+    aten.nll_loss2d_forward.default,
+    aten.nll_loss2d_backward.default,
     aten.scatter.src,
     aten.scatter_.src,
 }

@@ -38,6 +38,10 @@ def _log_softmax_handler(op, args, kwargs):
     half_to_float = args[2]
     md = _class_mesh_dim(x._spec, dim)
     if md is None:
+        if any(p.is_shard() for p in x.placements):
+            # same contract as torch / the reference (legacy ``dtensor/loss.py:105``): inside ``loss_parallel`` the logits must be
+            # sharded on the class dim; anything else is almost certainly a plan mistake (the loss would gather the logits)
+            raise ValueError(f"loss_parallel() only supports logits sharded on the class dimension {dim}, got placements {x.placements}")
         return _fallthrough(op, args, kwargs)
     mesh = x.device_mesh
     lx = x._local_tensor.float() if half_to_float else x._local_tensor

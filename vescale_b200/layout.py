@@ -28,6 +28,7 @@ __all__ = [
     "local_boxes",
     "unravel_index",
     "flatten_index",
+    "gather_local_tensor_shape",
 ]
 
 Interval = Tuple[int, int]  # (start, length)
@@ -121,7 +122,7 @@ def shape_and_offset_before_ragged(
     for d, size in enumerate(global_shape):
         iv = dim_intervals(int(size), d, mesh_shape, placements, coord)
         shape.append(sum(x[1] for x in iv))
-        off.append(iv[0][0] if iv else 0)
+        off.append(iv[0][0] if iv else int(size))  # an empty shard sits at the end of the dim (torch / legacy convention)
     return tuple(shape), tuple(off)
 
 
@@ -177,17 +178,25 @@ def local_numel(global_shape, mesh, placements, coordinate=None) -> int:
     return math.prod(compute_local_shape(global_shape, mesh, placements, coordinate))
 
 
-def compute_global_tensor_info(local_tensor, mesh, placements: Sequence[Placement]) -> Tuple[List[int], List[int]]:
-    """Global size/stride implied by a local tensor (assumes even sharding, as ``from_local`` does)."""
+def compute_global_tensor_info(local_tensor, mesh, placements: Sequence[Placement], meshdim_localtensor_shape=None) -> Tuple[List[int], List[int]]:
+    """Global size/stride implied by a local tensor.  Even sharding is assumed (as ``from_local`` does) unless
+    ``meshdim_localtensor_shape`` — the per-mesh-dim gathered local shapes of ``gather_local_tensor_shape`` — is given, in which
+    case a sharded dim is the sum of its members' extents (legacy ``dtensor/_utils.py:168``).  Mesh dims are folded from the
+    innermost outwards, so nested shards of one tensor dim compose."""
     shape = list(local_tensor.shape)
     stride = list(local_tensor.stride())
     coord = mesh.get_coordinate()
-    for idx, p in enumerate(placements):
+    order = range(len(placements)) if meshdim_localtensor_shape is None else reversed(range(len(placements)))
+    for idx in order:
+        p = placements[idx]
         n = mesh.size(idx)
         if isinstance(p, Shard):  # incl. strided / interleaved
             d = p.dim
             if d >= len(shape):
                 raise ValueError(f"shard dim {d} out of range for local tensor of ndim {len(shape)}")
+            if meshdim_localtensor_shape is not None and idx in meshdim_localtensor_shape:
+                shape[d] = sum(int(s[d]) for s in meshdim_localtensor_shape[idx]) if mesh.size(idx) > 1 else shape[d]
+                continue
             shape[d] = shape[d] * n
             for i in range(len(stride)):
                 if i != d and stride[i] >= stride[d]:
@@ -201,6 +210,10 @@ def compute_global_tensor_info(local_tensor, mesh, placements: Sequence[Placemen
             shape[0] = shape[0] // u * p.total_units
         elif not isinstance(p, (Replicate, Partial)):
             raise RuntimeError(f"unsupported placement {p!r}")
+    if meshdim_localtensor_shape is not None:  # uneven shards: a (possibly empty) local stride says nothing; the global is dense
+        stride, acc = [0] * len(shape), 1
+        for i in reversed(range(len(shape))):
+            stride[i], acc = acc, acc * max(1, shape[i])
     return shape, stride
 
 
@@ -305,3 +318,24 @@ def local_boxes(global_shape, mesh, placements, coordinate=None) -> List[Tuple[T
 
     rec(0, [], [], [])
     return boxes
+
+
+def gather_local_tensor_shape(self_local_tensor, device_mesh, placements: Sequence[Placement], shard_only: bool = False):
+    """All-gather the local shard shapes along every mesh dim (only the sharded ones with ``shard_only``): ``{mesh_dim: [shape of
+    member 0, shape of member 1, ...]}``; ``None`` on ranks outside the mesh (legacy ``dtensor/_utils.py:133``).  The one helper
+    of this module that communicates — used to validate hand-made uneven shards."""
+    import torch
+
+    from .comm import collectives as C
+
+    if device_mesh.get_coordinate() is None:
+        return None
+    shape = tuple(self_local_tensor) if isinstance(self_local_tensor, torch.Size) else tuple(self_local_tensor.shape)
+    dev = device_mesh.device_type if device_mesh.device_type != "meta" else "cpu"
+    mine = torch.tensor([list(shape)], dtype=torch.int64, device=dev)
+    out = {}
+    for d, p in enumerate(placements):
+        if shard_only and not p.is_shard():
+            continue
+        out[d] = C.mesh_all_gather(mine, device_mesh, d, 0).cpu().tolist() if device_mesh.size(d) > 1 else [list(shape)]
+    return out

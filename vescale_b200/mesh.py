@@ -64,6 +64,7 @@ class DeviceMesh:
         _init_process_groups: bool = True,
         _rank: Optional[int] = None,
         _dim_groups: Optional[List[object]] = None,
+        _validate_mesh: bool = True,  # accepted for signature compatibility (legacy ``device_mesh.py:226``); the grid is always checked locally
     ):
         self.device_type = device_type
         m = mesh.detach().cpu().to(torch.int64) if isinstance(mesh, torch.Tensor) else torch.tensor(mesh, dtype=torch.int64)
@@ -95,6 +96,16 @@ class DeviceMesh:
             self._init_groups(pg)
         else:
             self._fill_group_ranks()
+
+    @property
+    def _dim_group_infos(self):
+        """torch-style ``[(tag, ranks, group_name)]`` per mesh dim (what ``torch.distributed._functional_collectives`` accepts as
+        a group); read by code written against torch's / the reference's mesh internals."""
+        out = []
+        for d, g in enumerate(self._dim_groups):
+            ranks = list(self._dim_group_ranks[d]) if d < len(self._dim_group_ranks) else []
+            out.append((f"mesh_dim_{d}", ranks, getattr(g, "group_name", None)))
+        return out
 
     # ------------------------------------------------------------------ groups
     def _ranks_along(self, dim: int) -> List[Tuple[int, ...]]:

@@ -298,8 +298,14 @@ def normalize_placements(placements, mesh_ndim: int, tensor_ndim: Optional[int] 
     if placements is None:
         return tuple(Replicate() for _ in range(mesh_ndim))
     placements = tuple(placements)
-    if len(placements) != mesh_ndim:
-        raise ValueError(f"need one placement per mesh dim ({mesh_ndim}), got {len(placements)}: {placements}")
+    if len(placements) > mesh_ndim:
+        raise ValueError(f"`placements` has {len(placements)} entries, more than the mesh has dims ({mesh_ndim}): {placements}")
+    if len(placements) < mesh_ndim:
+        # as in the legacy package (``dtensor/dtensor.py:60``): the trailing mesh dims are replicated, with a warning
+        import warnings
+
+        warnings.warn(f"`placements` has fewer entries ({len(placements)}) than the mesh has dims ({mesh_ndim}); appending Replicate()", UserWarning, stacklevel=3)
+        placements = placements + tuple(Replicate() for _ in range(mesh_ndim - len(placements)))
     out = []
     for p in placements:
         if not isinstance(p, Placement):
