@@ -78,6 +78,38 @@ class VeDeviceMesh:
     def get_global_tensor_parallel_meshes(self) -> List[DeviceMesh]:
         return self.get().get_all_submesh("TP")
 
+    # ---- reference-named accessors (legacy ``devicemesh_api/api.py:240-435``)
+    @property
+    def _MESH_DIM_NAMES_LOOKUP(self) -> List[str]:
+        return list(self._names)
+
+    def get_coordinate(self) -> Optional[List[int]]:
+        c = self.get().get_coordinate()
+        return None if c is None else list(c)
+
+    def get_local_rank(self) -> int:
+        """Rank within this machine (global rank modulo the local device count; 8 when there is no GPU)."""
+        import torch
+        import torch.distributed as dist
+
+        n = torch.cuda.device_count() if torch.cuda.is_available() else 8
+        return (dist.get_rank() if dist.is_initialized() else 0) % n
+
+    def get_global_pipeline_parallel_meshes(self, device_type: Optional[str] = None) -> List[DeviceMesh]:
+        """One group-less mesh per pipeline stage: the ranks of slice i of the outermost mesh dim."""
+        m = self.get()
+        dev = device_type or m.device_type
+        return [DeviceMesh(dev, m.mesh[i], _init_process_groups=False) for i in range(m.shape[0])]
+
+    def get_data_parallel_dim_groups(self):
+        """Process group of the data-parallel mesh dim: dim 1 of a 3-D (PP, DP, TP) mesh, dim 0 otherwise."""
+        m = self.get()
+        return m.get_dim_groups(1 if m.ndim >= 3 else 0)
+
+    def get_tensor_parallel_dim_groups(self):
+        """Process group of mesh dim 0 (the reference returns the lowest-index dim's group here, ``api.py:427-435``)."""
+        return self.get().get_dim_groups(0)
+
     def is_first_stage(self) -> bool:
         return self.get_pipeline_parallel_rank() == 0
 

@@ -194,6 +194,10 @@ class DeviceMesh:
     def get_all_groups(self):
         return list(self._dim_groups)
 
+    def get_dim_groups(self, mesh_dim: Union[int, str, None] = None):
+        """Legacy spelling (``legacy/vescale/dtensor/device_mesh.py:468``): my group along ``mesh_dim``, or all of them."""
+        return self.get_all_groups() if mesh_dim is None else self.get_group(mesh_dim)
+
     def get_group_ranks(self, mesh_dim: Union[int, str] = 0) -> Tuple[int, ...]:
         """Global ranks of my group along ``mesh_dim`` in mesh-coordinate order."""
         return self._dim_group_ranks[self._dim_index(mesh_dim)]

@@ -24,7 +24,11 @@ Parity: ``legacy/vescale/dmodule/api.py:33-293``, ``_dmodule.py:43-666``, ``_hoo
 from __future__ import annotations
 
 import contextlib
+import dataclasses
+import functools
+import inspect
 import re
+import warnings
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -72,6 +76,20 @@ def _convert(x, pi: Optional[PlacementsInterface], mesh: DeviceMesh):
             return x
         return x.redistribute(mesh, pl, async_op=pi.async_op)
     return DTensor.from_local(x, mesh, pl, run_check=pi.run_check)
+
+
+def _convert_nested(x, spec, mesh: DeviceMesh):
+    """``spec`` mirrors the structure of ``x``: a placement list / ``PlacementsInterface`` for a tensor, a dict for a dict
+    argument, a list of placement lists for a list / tuple argument."""
+    if spec is None:
+        return x
+    if isinstance(spec, dict):
+        if not isinstance(x, dict):
+            return x
+        return type(x)({k: _convert_nested(v, spec[k], mesh) if k in spec else v for k, v in x.items()})
+    if isinstance(spec, (list, tuple)) and spec and not isinstance(spec[0], Placement) and isinstance(x, (list, tuple)):
+        return type(x)(_convert_nested(v, spec[i] if i < len(spec) else None, mesh) for i, v in enumerate(x))
+    return _convert(x, PlacementsInterface.from_placements(spec), mesh)
 
 
 class DModule:
@@ -145,28 +163,78 @@ class DModule:
 
     @staticmethod
     def _make_pre(entry, mesh):
-        if isinstance(entry, dict):
-            kw_pis = {k: PlacementsInterface.from_placements(v) for k, v in entry.items()}
-
-            def pre_kw(mod, args, kwargs):
-                return args, {k: _convert(v, kw_pis.get(k), mesh) for k, v in kwargs.items()}
-
-            return pre_kw
-        pis = _as_pi_list(entry)
+        """Input hook.  The call is bound to ``forward``'s signature first (so a wrong call raises ``TypeError`` before any
+        conversion and defaults are visible), then a sequence plan is laid over the bound arguments in order — positional
+        ones, then keyword ones — and a dict plan is matched by parameter name (a ``*args`` parameter takes a list of
+        placements, a ``**kwargs`` parameter is looked through, container arguments take a nested dict / list).  A plan
+        naming more arguments than the call has warns and the surplus is ignored (legacy ``dmodule/_hook.py:96-170``)."""
+        is_dict = isinstance(entry, dict)
+        pis = None if is_dict else _as_pi_list(entry)
 
         def pre(mod, args, kwargs):
-            new = tuple(_convert(a, pis[i] if i < len(pis) else None, mesh) for i, a in enumerate(args))
-            return new, kwargs
+            sig = inspect.signature(mod.forward)
+            bound = sig.bind(*args, **kwargs)
+            bound.apply_defaults()
+            if not is_dict:
+                pos, kw = bound.args, bound.kwargs
+                n = len(pos) + len(kw)
+                if len(pis) > n:
+                    warnings.warn(f"forward plan lists {len(pis)} placements but the call has {n} arguments; the rest are ignored")
+                full = list(pis[:n]) + [None] * (n - len(pis))
+                return (
+                    tuple(_convert(x, pi, mesh) for x, pi in zip(pos, full)),
+                    {k: _convert(v, pi, mesh) for (k, v), pi in zip(kw.items(), full[len(pos):])},
+                )
+            var_pos = next((q.name for q in sig.parameters.values() if q.kind is q.VAR_POSITIONAL), None)
+            var_kw = next((q.name for q in sig.parameters.values() if q.kind is q.VAR_KEYWORD), None)
+            known = set(bound.arguments) - {var_kw}
+            if var_kw is not None:
+                known |= set(bound.arguments.get(var_kw, {}))
+            unknown = set(entry) - known
+            if unknown:
+                warnings.warn(f"forward plan names arguments the call does not have: {sorted(map(str, unknown))}")
+            for name, val in list(bound.arguments.items()):
+                if name == var_kw:
+                    bound.arguments[name] = {k: _convert_nested(v, entry[k], mesh) if k in entry else v for k, v in val.items()}
+                elif name not in entry:
+                    continue
+                elif name == var_pos:
+                    sub = _as_pi_list(entry[name])
+                    if len(sub) > len(val):
+                        warnings.warn(f"forward plan lists {len(sub)} placements for *{name} but {len(val)} were passed; the rest are ignored")
+                    bound.arguments[name] = tuple(_convert(v, sub[i] if i < len(sub) else None, mesh) for i, v in enumerate(val))
+                else:
+                    bound.arguments[name] = _convert_nested(val, entry[name], mesh)
+            return bound.args, bound.kwargs
 
         return pre
 
     @staticmethod
     def _make_post(entry, mesh):
-        pis = _as_pi_list(entry)
+        """Output hook: a sequence plan over a tensor / tuple / list output, a dict plan (by key / field name) over a dict,
+        dict-like (``ModelOutput``) or dataclass output (legacy ``dmodule/_hook.py:213-256``)."""
+        is_dict = isinstance(entry, dict)
+        pis = None if is_dict else _as_pi_list(entry)
 
         def post(mod, args, output):
+            if is_dict:
+                if dataclasses.is_dataclass(output) and not isinstance(output, type) and not isinstance(output, dict):
+                    vals = {f.name: getattr(output, f.name) for f in dataclasses.fields(output)}
+                    return type(output)(**{k: _convert_nested(v, entry[k], mesh) if k in entry else v for k, v in vals.items()})
+                if isinstance(output, dict):
+                    conv = {k: _convert_nested(v, entry[k], mesh) if k in entry else v for k, v in output.items()}
+                    try:
+                        return type(output)(**conv)
+                    except TypeError:
+                        return type(output)(conv)
+                raise TypeError(f"a dict output plan needs a dict or dataclass output, got {type(output).__name__}")
             if isinstance(output, (tuple, list)):
-                return type(output)(_convert(o, pis[i] if i < len(pis) else None, mesh) for i, o in enumerate(output))
+                if len(output) != len(pis):
+                    raise AssertionError(f"output plan has {len(pis)} entries but the module returned {len(output)} values")
+                conv = [_convert(o, pi, mesh) for o, pi in zip(output, pis)]
+                return type(output)(*conv) if hasattr(output, "_fields") else type(output)(conv)
+            if isinstance(output, dict) or dataclasses.is_dataclass(output):
+                raise TypeError("a sequence output plan cannot be applied to a dict / dataclass output; key it by name")
             return _convert(output, pis[0] if pis else None, mesh)
 
         return post
@@ -266,6 +334,7 @@ def parallelize_module(
     if factory:
         orig_forward = module.forward
 
+        @functools.wraps(orig_forward)
         def fwd(*a, **kw):
             with _factory_mode(device_mesh):
                 return orig_forward(*a, **kw)

@@ -28,6 +28,9 @@ from .logger import NDTimelineLogger, get_logger  # noqa: F401
 
 logger = get_logger()
 
+LOCAL_LOGGING_PATH = SOCK_PARENT_DIR  # default directory of LocalRawNDHandler / LocalTimelineNDHandler output (legacy ``variables.py``)
+DEFAULT_CUDA_EVENT_POOL_SIZE = 20
+NDTIMELINE_FLUSH_SEPCIAL = "special"  # step tag of an out-of-band flush (spelling as in the reference)
 NDTIMELINE_INNER_GLOBAL_STEP_KEY = "_inner_global_step"  # record key of the step counter maintained by inc_step / set_global_step
 NDTIMELINE_STREAM_KEY = "stream_key"  # tag naming the stream a region was timed on
 from . import predefined  # noqa: F401

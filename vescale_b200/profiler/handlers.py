@@ -1,16 +1,77 @@
 """Record handlers: chrome/perfetto trace, raw dump, parser (aggregate stats), logging."""
 from __future__ import annotations
 
+import dataclasses
 import json
 import logging
 import os
 from collections import defaultdict
-from typing import Dict, List
+from typing import Any, Dict, List
+
+
+@dataclasses.dataclass
+class NDRecord:
+    """What a handler returns for a legacy-protocol call: one aggregate per training step."""
+
+    metric: str
+    step: int
+    elapsed: float
+    parts: List[float]
+    since_start: List[float]
+    tags: List[dict]
+    world_info: Any = None
+    extra: Any = None
 
 
 class NDHandler:
+    """Consumer of flushed timeline records.  Two call protocols are accepted by every handler:
+
+    * ``handler(records, rank, step)`` — this framework's batch form (a list of dicts with ``metric`` / ``start_us`` /
+      ``duration_us`` / ``tags`` / ``step``), what ``NDTimerManager.flush`` uses;
+    * ``handler(metric_name, elapsed, recent_elapsed_raw_parts, recent_since_start_raw_parts, tags, step_range, world_info,
+      extra)`` — the reference's per-metric form (legacy ``handlers/handler_base.py``): validated (``NDHandlerError`` on
+      inconsistent lengths), converted to the batch form, and answered with one ``NDRecord`` per step."""
+
+    def __init_subclass__(cls, **kw):
+        super().__init_subclass__(**kw)
+        impl = cls.__dict__.get("__call__")
+        if impl is None:
+            return
+
+        def dual(self, *args, **kwargs):
+            if len(args) == 3 and isinstance(args[0], (list, tuple)) and not kwargs:
+                return impl(self, *args)
+            return NDHandler._legacy_call(self, impl, *args, **kwargs)
+
+        dual.__wrapped__ = impl
+        cls.__call__ = dual
+
     def __call__(self, records: List[dict], rank: int, step: int) -> None:
         raise NotImplementedError
+
+    def _legacy_call(self, impl, metric_name, elapsed, recent_elapsed_raw_parts, recent_since_start_raw_parts, tags, step_range, world_info=None, extra=None):
+        from .exceptions import NDHandlerError
+
+        parts, since, tags = list(recent_elapsed_raw_parts), list(recent_since_start_raw_parts), list(tags)
+        steps = list(step_range)
+        if not (len(parts) == len(since) == len(tags)):
+            raise NDHandlerError(f"{metric_name}: {len(parts)} durations, {len(since)} start times and {len(tags)} tag dicts do not line up")
+        if not steps or len(parts) % len(steps):
+            raise NDHandlerError(f"{metric_name}: {len(parts)} parts cannot be spread over {len(steps)} steps")
+        per = len(parts) // len(steps)
+        rank = 0
+        if world_info is not None:
+            try:
+                rank = int(world_info["rank"])
+            except Exception:  # noqa: BLE001
+                rank = 0
+        out = []
+        for i, st in enumerate(steps):
+            sl = slice(i * per, (i + 1) * per)
+            recs = [{"metric": metric_name, "start_us": s * 1e6, "duration_us": d * 1e3, "tags": dict(t), "step": st, "stream": 0} for d, s, t in zip(parts[sl], since[sl], tags[sl])]
+            impl(self, recs, rank, st)
+            out.append(NDRecord(metric_name, st, float(sum(parts[sl])), parts[sl], since[sl], tags[sl], world_info, extra))
+        return out
 
 
 class DoNothingNDHandler(NDHandler):
