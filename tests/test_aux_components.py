@@ -394,3 +394,38 @@ def test_reference_import_paths_and_extension_points(tmp_path):
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         assert old() == 1 and len(w) == 1
+
+
+def test_hierarchical_double_tree_and_rotating_raw_handler(tmp_path, monkeypatch):
+    """NCCL's node-chain + inter-node double tree (legacy ``test/emulator/test_topo.py``) and the rotating raw-record file
+    (``test/ndtimeline/test_local_raw_handler.py``)."""
+    import os
+
+    from vescale_b200.emulator.topo import DoubleTree
+
+    table = [[n * 8 + i for i in range(8)] for n in range(4)]
+    ranks = [0, 1, 2, 3, 8, 9, 10, 11, 16, 17, 18, 19, 24, 25, 26, 27]
+    dt = DoubleTree(table, ranks, {r: i for i, r in enumerate(ranks)})
+    t0, t1 = dt.tree
+    assert str(t0[1]) == "[Rank 1] up: 0, down: [2, -1, 8].\n" and str(t0[9]) == "[Rank 9] up: 8, down: [10, 4, 12].\n"
+    assert str(t1[5]) == "[Rank 5] up: 4, down: [6, 8, 0].\n" and str(t1[12]) == "[Rank 12] up: -1, down: [13, -1, -1].\n"
+    for t in dt.tree:  # exactly one root; every other rank is reachable from it; chain links are mutual
+        assert sum(n.up == -1 for n in t) == 1
+        for n in t:
+            for d in n.down:
+                assert d == -1 or t[d].up == n.rank
+    for nn_ in (3, 5):  # odd node counts use the shifted second tree; roots of the two trees sit on different nodes
+        d = DoubleTree([[n * 2, n * 2 + 1] for n in range(nn_)], list(range(2 * nn_)))
+        roots = [next(n.rank for n in t if n.up == -1) // 2 for t in d.tree]
+        assert roots[0] != roots[1]
+
+    import vescale_b200.profiler as prof
+    from vescale_b200.profiler.handlers import LocalRawNDHandler, NDRecord
+
+    monkeypatch.setattr(prof, "LOCAL_LOGGING_PATH", str(tmp_path))
+    h = LocalRawNDHandler(run_id=7, chunk_sz=10, backup_cnt=3)
+    for _ in range(6):
+        out = h("m", 1.0, [1.0], [0.5], [{}], range(0, 1), None, {})
+    assert isinstance(out[0], NDRecord) and out[0].metric == "m"
+    base = os.path.join(str(tmp_path), "timeline_run7_raw.log")
+    assert os.path.exists(base) and os.path.exists(base + ".3") and not os.path.exists(base + ".4")

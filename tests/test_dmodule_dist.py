@@ -196,3 +196,87 @@ def _model_patches(rank, world):
 
 def test_model_patches():
     run_distributed(_model_patches, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# forward plans bound to the signature, factory regions per module class (legacy ``test_fwd_plan.py``, ``test_dfactory.py``)
+class _KwOnly(nn.Module):
+    def forward(self, a, *rest, b=None, **extra):
+        return a, rest, b, extra
+
+
+class _InnerZ(nn.Module):
+    def forward(self, x):
+        return torch.zeros(x.shape, dtype=x.dtype)
+
+
+class _OuterZ(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.m = _InnerZ()
+
+    def forward(self, x):
+        return torch.zeros(x.shape), self.m(x), torch.ones(x.shape)
+
+
+def _fwd_plan_and_factory(rank, world):
+    import warnings
+
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200 import dtensor as D
+    from vescale_b200.dtensor import DTensor
+    from vescale_b200.parallel.dmodule import _factory, parallelize_module
+
+    mesh = init_device_mesh(device_type(), (world,))
+    a, b = torch.ones(2, 2), torch.ones(2, 2) * 2
+
+    # sequence plan runs over positional then keyword arguments; dict plan goes by name, *args takes a list, **kwargs is searched
+    m = parallelize_module(_KwOnly(), mesh, {"forward": {".input": [[Shard(0)], None, [Replicate()]]}})
+    o_a, o_rest, o_b, _ = m(a, a, b=b)
+    assert isinstance(o_a, DTensor) and o_a.placements[0] == Shard(0) and tuple(o_a.shape) == (2 * world, 2)
+    assert type(o_rest[0]) is torch.Tensor and isinstance(o_b, DTensor) and o_b.placements[0].is_replicate()
+    m = parallelize_module(_KwOnly(), mesh, {"forward": {".input": {"a": [Shard(1)], "rest": [[Shard(0)]], "z": [Replicate()]}}})
+    o_a, o_rest, o_b, o_extra = m(a, b, z=b)
+    assert o_a.placements[0] == Shard(1) and o_rest[0].placements[0] == Shard(0) and o_b is None and isinstance(o_extra["z"], DTensor)
+    # a wrong call fails as the bare module would; surplus / unknown plan entries warn and are ignored
+    try:
+        m(b=b)
+        raise AssertionError("expected TypeError")
+    except TypeError:
+        pass
+    for plan in ({".input": [[Shard(0)], None, None, None]}, {".input": {"a": [Shard(0)], "nope": None}}):
+        m = parallelize_module(_KwOnly(), mesh, {"forward": plan})
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            m(a)
+        assert any(issubclass(x.category, UserWarning) for x in w), plan
+
+    # factory regions: references to the builtins taken outside still build DTensors; Off inside On inside Off
+    f = torch.zeros
+    adp = _factory._provide_args(mesh, {torch.zeros: [Shard(0)], "full": [Replicate()]})
+    with _factory.FactoryDispatchModeOn(mesh, adp):
+        z = f((2 * world, 3))
+        assert isinstance(z, DTensor) and z.placements[0] == Shard(0) and tuple(z.to_local().shape) == (2, 3)
+        assert D.equal(z, D.zeros((2 * world, 3), device_mesh=mesh, placements=[Shard(0)]))
+        assert torch.full((3,), 2.0).placements[0].is_replicate() and torch.ones(3).placements[0].is_replicate()
+        r = torch.arange(0, 2 * world, 1, dtype=torch.float32)
+        assert isinstance(r, DTensor) and r.full_tensor().tolist() == list(range(2 * world))
+        with _factory.FactoryDispatchModeOff():
+            assert type(torch.zeros(3)) is torch.Tensor
+            with _factory.FactoryDispatchModeOn(mesh, {}):
+                assert isinstance(torch.empty(3), DTensor)
+            assert type(torch.zeros(3)) is torch.Tensor
+        assert isinstance(torch.zeros(3), DTensor)
+    assert type(torch.zeros(3)) is torch.Tensor
+    # per module class: {cls: True | False | {factory: placements}}
+    x = torch.ones(4 * world)
+    o = parallelize_module(_OuterZ(), mesh, {}, factory={_OuterZ: True, _InnerZ: False})(x)
+    assert [isinstance(t, DTensor) for t in o] == [True, False, True]
+    o = parallelize_module(_OuterZ(), mesh, {}, factory={_OuterZ: False, _InnerZ: {torch.zeros: [Shard(0)]}})(x)
+    assert [isinstance(t, DTensor) for t in o] == [False, True, False] and o[1].placements[0] == Shard(0) and o[1].to_local().numel() == 4
+    o = parallelize_module(_OuterZ(), mesh, {"forward": {".input": [[Shard(0)]]}}, factory=True)(torch.ones(4))
+    assert tuple(o[0].shape) == (4 * world,) and isinstance(o[1], DTensor)  # inner module inherits the enclosing region
+
+
+def test_forward_plan_binding_and_factory_regions():
+    run_distributed(_fwd_plan_and_factory, 2)

@@ -47,7 +47,7 @@ _ALIASES = {
     "vescale.dtensor.api": "vescale_b200.dtensor.api",
     "vescale.dtensor._api": "vescale_b200.dtensor.api",
     "vescale.dtensor.dtensor": "vescale_b200.dtensor.api",
-    "vescale.dtensor._utils": "vescale_b200.layout",
+    "vescale.dtensor._utils": "vescale_b200.dtensor._utils",
     "vescale.dtensor._collective_utils": "vescale_b200.comm.collectives",
     "vescale.dtensor.redistribute": "vescale_b200.dtensor.redistribute",
     "vescale.dtensor.op_schema": "vescale_b200.dtensor.op_schema",
@@ -160,5 +160,10 @@ for _alias, _target in _ALIASES.items():  # explicit entries first: some alias a
         sys.modules[_alias] = importlib.import_module(_target)
     except Exception:  # pragma: no cover - optional pieces
         pass
+for _alias in _ALIASES:  # attribute paths too: ``vescale.dtensor.device_mesh.DeviceMesh`` without importing the submodule
+    _parent, _, _leaf = _alias.rpartition(".")
+    _pm, _cm = sys.modules.get(_parent), sys.modules.get(_alias)
+    if _pm is not None and _cm is not None and _parent != "vescale" and not hasattr(_pm, _leaf):
+        setattr(_pm, _leaf, _cm)
 dtensor = sys.modules["vescale.dtensor"]
 checkpoint = sys.modules.get("vescale.checkpoint")

@@ -57,3 +57,4 @@ __all__ = [
 ]
 
 torch.serialization.add_safe_globals([DTensor, DTensorSpec, TensorMeta, DeviceMesh, Shard, Replicate, Partial, RaggedShard, _StridedRaggedShard, _StridedShard, InterleavedShard])
+from . import _utils  # noqa: F401,E402

@@ -7,8 +7,10 @@ full_tensor:515, DCP hooks:542-586, distribute_tensor:589, factories:792-1051) a
 """
 from __future__ import annotations
 
+import functools
 import math
 import os
+import threading
 from typing import Any, List, Optional, Sequence, Tuple
 
 import torch
@@ -479,6 +481,35 @@ def distribute_tensor(
 
 
 # ------------------------------------------------------------------------------- factories
+_factory_tls = threading.local()
+
+
+def _factory_region_stack() -> list:
+    """Per-thread stack of DTensor-factory regions (``parallel/dmodule/_factory.py``): ``(mesh, placements map)`` = ON, None = OFF."""
+    s = getattr(_factory_tls, "stack", None)
+    if s is None:
+        s = _factory_tls.stack = []
+    return s
+
+
+def _plain_torch_factories(fn):
+    """The DTensor factories build their local shards with plain ``torch.zeros`` & co. even inside an ON factory region."""
+
+    @functools.wraps(fn)
+    def run(*a, **kw):
+        st = _factory_region_stack()
+        if not st or st[-1] is None:
+            return fn(*a, **kw)
+        st.append(None)
+        try:
+            return fn(*a, **kw)
+        finally:
+            st.pop()
+
+    return run
+
+
+@_plain_torch_factories
 def _factory(kind: str, size, *, dtype=None, layout=torch.strided, requires_grad=False, device_mesh=None, placements=None, fill_value=None):
     mesh = _resolve_mesh(device_mesh)
     if len(size) == 1 and isinstance(size[0], (list, tuple, torch.Size)):
@@ -541,7 +572,8 @@ def randn(*size, **kw) -> DTensor:
     return _factory("randn", size, **kw)
 
 
-def arange(*args, dtype=None, device_mesh=None, placements=None, requires_grad=False) -> DTensor:
+@_plain_torch_factories
+def arange(*args, dtype=None, layout=torch.strided, device_mesh=None, placements=None, requires_grad=False) -> DTensor:
     mesh = _resolve_mesh(device_mesh)
     full_t = torch.arange(*args, dtype=dtype, device=mesh.device_type if mesh.device_type != "meta" else "cpu")
     placements = normalize_placements(placements, mesh.ndim, 1)

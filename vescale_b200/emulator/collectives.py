@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-__all__ = ["ring_all_reduce", "ring_reduce_scatter", "tree_all_reduce", "double_tree_all_reduce", "all_gather", "all_to_all", "EmulatorProcessGroup", "nccl_chunking"]
+__all__ = ["ring_all_reduce", "ring_reduce_scatter", "tree_all_reduce", "double_tree_all_reduce", "all_gather", "all_to_all", "EmulatorProcessGroup", "nccl_chunking", "expand_tensor_list", "contract_tensor_list"]
 
 
 def nccl_chunking(count: int, nranks: int, nchannels: int = 1, chunk_elems: Optional[int] = None) -> List[Tuple[int, int, int]]:
@@ -178,3 +178,22 @@ class EmulatorProcessGroup:
 
     def broadcast(self, tensors, src: int = 0):
         return [tensors[src].clone() for _ in tensors]
+
+
+def expand_tensor_list(tensor_list: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """The all-gather working buffers of the global view: rank i's buffer is n times its input long, zero everywhere except
+    slot i, which holds its own input (what an in-place NCCL all-gather starts from)."""
+    n, a = len(tensor_list), tensor_list[0].size(0)
+    out = []
+    for i, t in enumerate(tensor_list):
+        buf = t.new_zeros((n * a,) + tuple(t.shape[1:]))
+        buf[i * a:(i + 1) * a] = t
+        out.append(buf)
+    return out
+
+
+def contract_tensor_list(tensor_list: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Inverse view for reduce-scatter: rank i keeps slot i of its n-slot buffer."""
+    n = len(tensor_list)
+    a = tensor_list[0].size(0) // n
+    return [t[i * a:(i + 1) * a] for i, t in enumerate(tensor_list)]

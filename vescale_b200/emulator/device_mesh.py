@@ -10,7 +10,7 @@ import torch
 from ..mesh import DeviceMesh as _RealMesh
 from . import distributed as edist
 
-__all__ = ["DeviceMesh", "init_device_mesh"]
+__all__ = ["DeviceMesh", "init_device_mesh", "dump_nccl_graph_for_mesh", "delete_nccl_graph_for_mesh"]
 
 
 class DeviceMesh(_RealMesh):
@@ -45,3 +45,23 @@ def init_device_mesh(device_type: str, mesh_shape: Sequence[int], *, mesh_dim_na
     for s in mesh_shape:
         n *= int(s)
     return DeviceMesh(device_type, torch.arange(n).view(tuple(mesh_shape)), mesh_dim_names=mesh_dim_names)
+
+
+def dump_nccl_graph_for_mesh(emulator_mesh: DeviceMesh, vescale_mesh) -> List[str]:
+    """For every mesh dim, dump the NCCL graph of MY real group along it (``vescale_mesh``) into the file of the matching
+    emulator group (legacy ``emulator/device_mesh.py:648-670``).  Returns the file names."""
+    me = vescale_mesh.get_rank()
+    files = []
+    for d in range(vescale_mesh.ndim):
+        ranks = sorted(vescale_mesh.get_group_ranks(d))
+        epg = next((g for g in emulator_mesh.get_dim_groups(d) if sorted(g.ranks) == ranks), None)
+        if epg is None:
+            continue
+        files.append(edist.dump_nccl_graph_for_pg(epg, vescale_mesh.get_group(d), me))
+    return files
+
+
+def delete_nccl_graph_for_mesh(emulator_mesh: DeviceMesh) -> None:
+    for groups in emulator_mesh.get_dim_groups():
+        for g in groups:
+            edist.delete_nccl_graph_for_pg(g)

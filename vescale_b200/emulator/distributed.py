@@ -21,7 +21,7 @@ from .collectives import EmulatorProcessGroup, all_gather as _all_gather, all_to
 
 __all__ = [
     "ReduceOp", "ProcessGroup", "GroupMember", "init_process_group", "destroy_process_group", "is_initialized", "new_group", "get_rank", "set_rank", "get_world_size",
-    "get_group_rank", "get_process_group_ranks", "dump_nccl_graph", "get_nccl_graph_xml",
+    "get_group_rank", "get_process_group_ranks", "dump_nccl_graph", "get_nccl_graph_xml", "dump_nccl_graph_for_pg", "delete_nccl_graph_for_pg", "attach_nccl_graph",
 ]
 
 
@@ -45,6 +45,11 @@ class _World:
         self.rank = 0
         self.groups: Dict[tuple, "ProcessGroup"] = {}
         self.graph_xml: Dict[int, str] = {}
+
+    @property
+    def pg_group_ranks(self) -> Dict["ProcessGroup", Dict[int, int]]:
+        """group → {global rank: rank in the group}, in creation order (the c10d ``_world`` field of the same name)."""
+        return {g: {r: i for i, r in enumerate(g.ranks)} for g in self.groups.values()}
 
 
 _world = _World()
@@ -174,14 +179,55 @@ def get_group_rank(group: ProcessGroup, global_rank: int) -> int:
 
 # ------------------------------------------------------------------------------------------------- topology files
 def dump_nccl_graph(xmlfile: str = "./ncclgraph.xml", pg=None, rank: int = 0) -> str:
-    """Ask a REAL NCCL communicator to write its topology graph (``NCCL_GRAPH_DUMP_FILE``) so the emulator can reproduce its
-    rings / trees.  Must be called before the communicator's first collective; returns the file path."""
+    """Ask a REAL NCCL communicator to write its topology graph so the emulator can reproduce its rings / trees: a small
+    ``torch.distributed.all_reduce`` on ``pg`` (a torch group) runs with ``NCCL_GRAPH_DUMP_FILE`` pointing at ``xmlfile``; NCCL
+    writes the file when it initialises that communicator, so ``pg`` must not have communicated yet.  With no NCCL group at hand
+    (gloo, or ``torch.distributed`` not initialised) only the variable is set for the next communicator.  Returns the path."""
+    import torch.distributed as tdist
+
+    prev = os.environ.get("NCCL_GRAPH_DUMP_FILE")
     os.environ["NCCL_GRAPH_DUMP_FILE"] = xmlfile
+    if not (tdist.is_available() and tdist.is_initialized() and torch.cuda.is_available() and tdist.get_backend(pg) == "nccl"):
+        return xmlfile
+    try:
+        probe = torch.ones(1024, device=torch.device("cuda", rank % torch.cuda.device_count()))
+        tdist.all_reduce(probe, group=pg)
+        torch.cuda.synchronize()
+    finally:
+        if prev is None:
+            os.environ.pop("NCCL_GRAPH_DUMP_FILE", None)
+        else:
+            os.environ["NCCL_GRAPH_DUMP_FILE"] = prev
     return xmlfile
 
 
+def _graph_file_of(pg: ProcessGroup) -> str:
+    return "ncclgraph_" + "_".join(map(str, sorted(pg.ranks))) + ".xml"
+
+
+def dump_nccl_graph_for_pg(emulator_pg: ProcessGroup, torch_pg, rank: int) -> str:
+    """Dump the graph of the torch group that ``emulator_pg`` mirrors into ``ncclgraph_<ranks>.xml`` and, when the file appears,
+    attach it so the emulated rings follow the real ones (legacy ``emulator/distributed.py:760-775``)."""
+    xmlfile = dump_nccl_graph(_graph_file_of(emulator_pg), torch_pg, rank)
+    if os.path.exists(xmlfile):
+        try:
+            attach_nccl_graph(emulator_pg, xmlfile)
+        except Exception:  # noqa: BLE001 - a half-written dump from another rank; the default ring order stays
+            pass
+    return xmlfile
+
+
+def delete_nccl_graph_for_pg(emulator_pg: ProcessGroup) -> None:
+    _world.graph_xml.pop(id(emulator_pg), None)
+    f = _graph_file_of(emulator_pg)
+    if os.path.exists(f):
+        os.remove(f)
+
+
 def get_nccl_graph_xml(pg: Optional[ProcessGroup] = None) -> Optional[str]:
-    return (pg or _default()).get_nccl_graph_xml()
+    """The graph file attached to ``pg``; failing that the conventional ``ncclgraph_<ranks>.xml`` name (which may not exist)."""
+    pg = pg or _default()
+    return pg.get_nccl_graph_xml() or _graph_file_of(pg)
 
 
 def attach_nccl_graph(pg: ProcessGroup, xmlfile: str) -> None:

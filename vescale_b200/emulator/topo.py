@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 __all__ = ["Ring", "BinaryTree", "DoubleTree", "btree", "parse_graph_dump"]
 
@@ -71,8 +71,76 @@ def btree(nranks: int) -> BinaryTree:
 
 
 @dataclass
+class TreeNode:
+    """One rank's links in a hierarchical tree: ``up`` is the rank it reduces towards, ``down[0]`` the next rank of its
+    intra-node chain, ``down[1:]`` the (up to two) ranks of child nodes it feeds.  All values are group indices, -1 = none."""
+
+    rank: int
+    up: int = -1
+    down: List[int] = field(default_factory=lambda: [-1, -1, -1])
+
+    def __str__(self) -> str:
+        return f"[Rank {self.rank}] up: {self.up}, down: {self.down}.\n"
+
+
+def _btree_links(n: int, r: int) -> Tuple[int, int, int]:
+    """(parent, child0, child1) of rank ``r`` in ``btree(n)`` with the two child slots kept apart (rank 0 only ever uses slot 1)."""
+    t = btree(n)
+    if r == 0:
+        cs = t.children[0]
+        return -1, -1, (cs[0] if cs else -1)
+    cs = t.children[r]
+    lo = [c for c in cs if c < r]
+    hi = [c for c in cs if c > r]
+    return t.parent[r], (lo[0] if lo else -1), (hi[0] if hi else -1)
+
+
 class DoubleTree:
-    trees: Tuple[BinaryTree, BinaryTree]
+    """Two complementary binary trees (``ncclGetDtree``).  Two forms:
+
+    * ``DoubleTree((t0, t1))`` / ``DoubleTree.build(nranks)`` — flat trees over ``nranks`` ranks (``.trees``);
+    * ``DoubleTree(tree_structure, ranks, mapping)`` — the hierarchical form NCCL really runs (legacy ``emulator/topo.py``):
+      ``tree_structure`` is the node × local-device table of global ranks, ``ranks`` the members of the group and ``mapping``
+      global rank → group index.  The members of one node form a chain; nodes are linked by the binary tree, the first rank of
+      a chain facing the parent node and the second facing the child nodes (NCCL's split-tree pattern).  The second tree is the
+      mirror (even node count) or the shift by one (odd) of the first.  ``.tree[k][i]`` is a ``TreeNode`` per group index."""
+
+    def __init__(self, trees_or_structure, ranks: Optional[Sequence[int]] = None, mapping: Optional[Dict[int, int]] = None):
+        if ranks is None:
+            self.trees: Tuple[BinaryTree, BinaryTree] = tuple(trees_or_structure)  # type: ignore[assignment]
+            self.tree = None
+            return
+        table = [[int(x) for x in row] for row in trees_or_structure]
+        mapping = mapping if mapping is not None else {int(r): i for i, r in enumerate(ranks)}
+        member = set(int(r) for r in ranks)
+        chains = [[mapping[r] for r in row if r in member] for row in table]
+        chains = [c for c in chains if c]
+        nn = len(chains)
+        self.tree = []
+        for k in (0, 1):
+            nodes = [TreeNode(i) for i in range(len(member))]
+            for chain in chains:
+                for a, b in zip(chain, chain[1:]):
+                    nodes[a].down[0] = b
+                    nodes[b].up = a
+            for n, chain in enumerate(chains):
+                if k == 0:
+                    links = _btree_links(nn, n)
+                elif nn % 2 == 0:
+                    links = tuple(-1 if x == -1 else nn - 1 - x for x in _btree_links(nn, nn - 1 - n))
+                else:
+                    links = tuple(-1 if x == -1 else (x + 1) % nn for x in _btree_links(nn, (n - 1) % nn))
+                up, d0, d1 = links
+                head, feeder = chain[0], chain[1] if len(chain) > 1 else chain[0]
+                if up != -1:
+                    par = chains[up]
+                    nodes[head].up = par[1] if len(par) > 1 else par[0]
+                for slot, d in ((1, d0), (2, d1)):
+                    if d != -1:
+                        nodes[feeder].down[slot] = chains[d][0]
+            self.tree.append(nodes)
+        flat = double_tree(nn)
+        self.trees = flat.trees
 
 
 def _relabel(t: BinaryTree, f, nranks: int) -> BinaryTree:

@@ -289,35 +289,6 @@ def is_dmodule(module: nn.Module) -> bool:
     return hasattr(module, "_dmodule")
 
 
-_FACTORY_FNS = ("zeros", "ones", "empty", "full", "randn", "arange")
-
-
-@contextlib.contextmanager
-def _factory_mode(mesh: DeviceMesh):
-    """Inside forward, plain factory calls build replicated DTensors (legacy ``_factory.py:57-117``)."""
-    saved = {n: getattr(torch, n) for n in _FACTORY_FNS}
-
-    from ...dtensor import sharding_prop as _sp
-
-    def wrap(fn):
-        def f(*a, **kw):
-            t = fn(*a, **kw)
-            # never inside the dispatcher's own meta-shape inference, never for meta tensors
-            if _sp.IN_META_PROPAGATION[0] or not isinstance(t, torch.Tensor) or isinstance(t, DTensor) or t.is_meta:
-                return t
-            return DTensor.from_local(t, mesh, [Replicate()] * mesh.ndim)
-
-        return f
-
-    try:
-        for n, fn in saved.items():
-            setattr(torch, n, wrap(fn))
-        yield
-    finally:
-        for n, fn in saved.items():
-            setattr(torch, n, fn)
-
-
 def parallelize_module(
     module: nn.Module,
     device_mesh: DeviceMesh,
@@ -332,15 +303,9 @@ def parallelize_module(
     dm.init_parameters(is_model_sharded)
     dm.init_forward()
     if factory:
-        orig_forward = module.forward
+        from ._factory import wrap_factory_mode
 
-        @functools.wraps(orig_forward)
-        def fwd(*a, **kw):
-            with _factory_mode(device_mesh):
-                return orig_forward(*a, **kw)
-
-        module.forward = fwd
-        dm.factory = True
+        dm.factory = wrap_factory_mode(module, device_mesh, factory) > 0
     module.finish_grad_sync = dm.finish_grad_sync
     module.list_partial_grads = dm.partial_grad_params
     module.get_fqn = lambda: ""

@@ -98,10 +98,32 @@ class ChromeTraceNDHandler(NDHandler):
 
 
 class LocalRawNDHandler(NDHandler):
-    def __init__(self, path: str):
+    """One JSON line per record.  ``LocalRawNDHandler(path)`` appends to ``<path>.rank<r>``; the reference's form
+    ``LocalRawNDHandler(run_id=, chunk_sz=, backup_cnt=)`` writes ``timeline_run<run_id>_raw.log`` under ``LOCAL_LOGGING_PATH``
+    and rotates it every ``chunk_sz`` bytes keeping ``backup_cnt`` older chunks (legacy ``handlers/local_raw_handler.py``)."""
+
+    def __init__(self, path: str = None, *, run_id=None, chunk_sz: int = 0, backup_cnt: int = 0, ranks=None):
         self.path = path
+        self.ranks = None if ranks is None else set(ranks)
+        self._rot = None
+        if path is None:
+            import logging.handlers
+
+            from . import LOCAL_LOGGING_PATH
+
+            os.makedirs(LOCAL_LOGGING_PATH, exist_ok=True)
+            self.file = os.path.join(LOCAL_LOGGING_PATH, f"timeline_run{0 if run_id is None else run_id}_raw.log")
+            self._rot = logging.handlers.RotatingFileHandler(self.file, maxBytes=int(chunk_sz), backupCount=int(backup_cnt))
+            self._rot.setFormatter(logging.Formatter("%(message)s"))
 
     def __call__(self, records, rank, step):
+        if self.ranks is not None and rank not in self.ranks:
+            return
+        if self._rot is not None:
+            for r in records:
+                self._rot.emit(logging.LogRecord("ndtimeline", logging.INFO, "", 0, json.dumps({"rank": rank, "step": step, **r}), None, None))
+            self._rot.flush()
+            return
         with open(f"{self.path}.rank{rank}", "a") as f:
             for r in records:
                 f.write(json.dumps({"rank": rank, "step": step, **r}) + "\n")
