@@ -280,3 +280,49 @@ def _fwd_plan_and_factory(rank, world):
 
 def test_forward_plan_binding_and_factory_regions():
     run_distributed(_fwd_plan_and_factory, 2)
+
+
+class _TwoBranch(nn.Module):
+    def __init__(self, h=16):
+        super().__init__()
+        self.m1 = nn.Sequential(nn.Linear(h, 4 * h, bias=False), nn.Linear(4 * h, h, bias=False))
+        self.m2 = nn.Sequential(nn.Linear(h, 4 * h, bias=False), nn.Linear(4 * h, h, bias=False))
+
+    def forward(self, x):
+        return x + (self.m1(x) + self.m2(x))
+
+
+def _deferred_output_reshard(rank, world):
+    """``PlacementsInterface(defer_reshard=True)`` on two row-parallel outputs: they stay Partial, their sum is all-reduced once
+    (legacy ``test/dtensor/general/test_defer_resharding.py``)."""
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200.dtensor import DTensor
+    from vescale_b200.dtensor.debug import CommDebugMode
+    from vescale_b200.parallel.dmodule import PlacementsInterface as PI
+    from vescale_b200.parallel.dmodule import parallelize_module
+
+    torch.manual_seed(0)
+    mesh = init_device_mesh(device_type(), (world,))
+    m = _TwoBranch().to(device_type())
+    golden = copy.deepcopy(m)
+    x = torch.randn(4, 16, 16, device=device_type())
+    plan = {
+        "parameter": {r"m\d\.0\.weight": [Shard(0)], r"m\d\.1\.weight": [Shard(1)]},
+        "forward": {r"m\d\.input": [[Replicate()]], r"m\d\.output": [PI([Replicate()], defer_reshard=True)]},
+    }
+    dm = parallelize_module(m, mesh, plan)
+    seen = {}
+    dm.m1.register_forward_hook(lambda mod, a, o: seen.update(m1=o.placements[0]))
+    with CommDebugMode() as comm:
+        out = dm(DTensor.from_local(x, mesh, [Replicate()]))
+    assert seen["m1"].is_partial() and out.placements[0].is_replicate()
+    assert comm.get_total_counts() == 1, comm.get_total_counts()
+    ref = golden(x)
+    assert torch.allclose(out.to_local(), ref, atol=1e-5)
+    out.to_local().sum().backward()
+    ref.sum().backward()
+    assert torch.allclose(dm.m1[0].weight.grad.full_tensor(), golden.m1[0].weight.grad, atol=1e-4)
+
+
+def test_deferred_output_reshard_single_allreduce():
+    run_distributed(_deferred_output_reshard, 2)

@@ -145,7 +145,22 @@ class OpDispatcher:
             local_out = op(*local_args, **local_kwargs)
         if out_sh.post is not None:
             local_out = out_sh.post(local_out, local_args, mesh)
-        return self.wrap(op, args, kwargs, local_out, out_sh.output_spec)
+        out = self.wrap(op, args, kwargs, local_out, out_sh.output_spec)
+        if op in _DEFERRED_TARGET_OPS:
+            out = self._apply_deferred_target(args, out)
+        return out
+
+    @staticmethod
+    def _apply_deferred_target(args, out):
+        """An operand whose reshard a DModule output plan deferred (``PlacementsInterface(defer_reshard=True)``) carries the
+        placements it still owes; the sum / difference it enters is resharded there instead — one all-reduce for ``Partial +
+        Partial`` rather than one per operand (legacy ``_dispatch_patch.py:134-143``)."""
+        tgt = next((t for t in (getattr(a, "_deferred_placements", None) for a in args if isinstance(a, DTensor)) if t is not None), None)
+        if tgt is None or not isinstance(out, DTensor) or tuple(out._spec.placements) == tuple(tgt):
+            return out
+        new_spec = DTensorSpec(out._spec.mesh, tuple(tgt), out._spec.tensor_meta)
+        local = redistribute_local_tensor(out._local_tensor, out._spec, new_spec)
+        return DTensor(local, new_spec, requires_grad=False)
 
     def _redistribute_inputs(self, schema, out_sh, local_args, local_kwargs):
         if _disable_redistribute():
@@ -276,6 +291,8 @@ _AUTO_WRAP_OPS = {
     aten.scatter.src,
     aten.scatter_.src,
 }
+
+_DEFERRED_TARGET_OPS = {aten.add.Tensor, aten.sub.Tensor}
 
 _RANDOM_OPS = {
     aten.native_dropout.default,

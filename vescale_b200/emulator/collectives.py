@@ -193,7 +193,7 @@ def expand_tensor_list(tensor_list: Sequence[torch.Tensor]) -> List[torch.Tensor
 
 
 def contract_tensor_list(tensor_list: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-    """Inverse view for reduce-scatter: rank i keeps slot i of its n-slot buffer."""
+    """Inverse view for reduce-scatter: rank i keeps slot i of its n-slot buffer (a flat tensor or a list of n pieces)."""
     n = len(tensor_list)
-    a = tensor_list[0].size(0) // n
+    a = len(tensor_list[0]) // n
     return [t[i * a:(i + 1) * a] for i, t in enumerate(tensor_list)]

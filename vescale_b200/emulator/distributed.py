@@ -91,7 +91,11 @@ class ProcessGroup(EmulatorProcessGroup):
     def all_gather(self, tensors_list: List[List[torch.Tensor]], tensors: List[torch.Tensor], async_op: bool = False):
         """``tensors[i]`` = rank i's contribution; ``tensors_list[i]`` becomes the gathered list seen by rank i."""
         for i in range(self.world_size):
-            tensors_list[i] = [t.clone() for t in tensors]
+            buf = tensors_list[i]
+            if isinstance(buf, torch.Tensor):  # one flat n-slot buffer per rank (``expand_tensor_list``): filled in place
+                buf.view(-1).copy_(torch.cat([t.reshape(-1) for t in tensors]))
+            else:
+                tensors_list[i] = [t.clone() for t in tensors]
 
     def reduce_scatter(self, outputs: List[torch.Tensor], tensors_list: List[List[torch.Tensor]], op=ReduceOp.SUM):
         """``tensors_list[i][j]`` = what rank i contributes to rank j; ``outputs[j]`` becomes the reduction over i."""

@@ -67,12 +67,15 @@ def _as_pi_list(entry) -> List[Optional[PlacementsInterface]]:
     return [None if e is None else PlacementsInterface.from_placements(e) for e in entry]
 
 
-def _convert(x, pi: Optional[PlacementsInterface], mesh: DeviceMesh):
+def _convert(x, pi: Optional[PlacementsInterface], mesh: DeviceMesh, allow_defer: bool = False):
     if pi is None or pi.placements is None or not isinstance(x, torch.Tensor):
         return x
     pl = normalize_placements(pi.placements, mesh.ndim, x.ndim)
     if isinstance(x, DTensor):
         if x.placements == pl:
+            return x
+        if allow_defer and pi.defer_reshard:
+            x._deferred_placements = tuple(pl)  # the sum / difference this output enters pays the reshard (dispatch.py)
             return x
         return x.redistribute(mesh, pl, async_op=pi.async_op)
     return DTensor.from_local(x, mesh, pl, run_check=pi.run_check)
@@ -231,11 +234,11 @@ class DModule:
             if isinstance(output, (tuple, list)):
                 if len(output) != len(pis):
                     raise AssertionError(f"output plan has {len(pis)} entries but the module returned {len(output)} values")
-                conv = [_convert(o, pi, mesh) for o, pi in zip(output, pis)]
+                conv = [_convert(o, pi, mesh, allow_defer=True) for o, pi in zip(output, pis)]
                 return type(output)(*conv) if hasattr(output, "_fields") else type(output)(conv)
             if isinstance(output, dict) or dataclasses.is_dataclass(output):
                 raise TypeError("a sequence output plan cannot be applied to a dict / dataclass output; key it by name")
-            return _convert(output, pis[0] if pis else None, mesh)
+            return _convert(output, pis[0] if pis else None, mesh, allow_defer=True)
 
         return post
 
