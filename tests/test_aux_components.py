@@ -429,3 +429,24 @@ def test_hierarchical_double_tree_and_rotating_raw_handler(tmp_path, monkeypatch
     assert isinstance(out[0], NDRecord) and out[0].metric == "m"
     base = os.path.join(str(tmp_path), "timeline_run7_raw.log")
     assert os.path.exists(base) and os.path.exists(base + ".3") and not os.path.exists(base + ".4")
+
+
+def test_deferred_tensor_factories_and_torchdistx_names():
+    """``deferred_init(torch.empty / full / randn, shape)`` yields one deferred tensor (legacy ``test/initialize/test_defer_init.py``);
+    the ``torchdistx`` entry points the reference's users import forward to the same machinery."""
+    import torch
+    from torchdistx.deferred_init import deferred_init, is_deferred, materialize_module, materialize_tensor
+    from torchdistx.fake import is_fake
+
+    with torch.device("meta"):
+        t = deferred_init(torch.empty, (4, 16, 16))
+    assert is_deferred(t) and is_fake(t) and t.device == torch.device("meta") and tuple(t.shape) == (4, 16, 16)
+    full = materialize_tensor(deferred_init(torch.full, (3, 2), 2.5, device="cpu"))
+    assert full.device.type == "cpu" and torch.equal(full, torch.full((3, 2), 2.5))
+    assert torch.equal(materialize_tensor(deferred_init(torch.ones, (5,))), torch.ones(5))
+    r = materialize_tensor(deferred_init(torch.randn, (64, 64)))
+    assert abs(float(r.mean())) < 0.1 and 0.8 < float(r.std()) < 1.2
+    m = deferred_init(torch.nn.Linear, 8, 8)
+    assert is_deferred(m) and all(is_fake(p) for p in m.parameters())
+    materialize_module(m)
+    assert not is_deferred(m) and float(m.weight.abs().sum()) > 0

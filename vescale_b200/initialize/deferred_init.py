@@ -22,7 +22,7 @@ from ..layout import compute_local_shape
 from ..placement import normalize_placements
 from ..spec import DTensorSpec, TensorMeta, contiguous_stride
 
-__all__ = ["deferred_init", "is_deferred", "materialize_dtensor", "materialize_dparameter", "materialize_module"]
+__all__ = ["deferred_init", "is_deferred", "materialize_dtensor", "materialize_dparameter", "materialize_module", "materialize_plain_tensor"]
 
 _RECORDED = {"normal_", "uniform_", "zero_", "fill_", "ones_", "zeros_", "constant_", "trunc_normal_",
              "kaiming_uniform_", "kaiming_normal_", "xavier_uniform_", "xavier_normal_"}
@@ -74,10 +74,37 @@ class _Recorder(TorchFunctionMode):
         return out
 
 
-def deferred_init(module_fn: Callable[..., nn.Module], *args, **kwargs) -> nn.Module:
-    """Construct ``module_fn(*args, **kwargs)`` on the meta device, recording parameter init ops."""
+_FACTORY_RECORDS = {
+    "ones": lambda a, kw: ("ones_", (), {}),
+    "zeros": lambda a, kw: ("zero_", (), {}),
+    "empty": lambda a, kw: ("empty", (), {}),
+    "randn": lambda a, kw: ("normal_", (0.0, 1.0), {}),
+    "rand": lambda a, kw: ("uniform_", (0.0, 1.0), {}),
+    "full": lambda a, kw: ("fill_", (a[1] if len(a) > 1 else kw.get("fill_value"),), {}),
+}
+
+
+def deferred_init(module_fn: Callable[..., nn.Module], *args, **kwargs):
+    """Construct ``module_fn(*args, **kwargs)`` without allocating it, recording how every parameter is initialised.
+    ``module_fn`` is a module class / builder, or a tensor factory (``torch.empty / zeros / ones / full / randn / rand``): the
+    result is then one deferred tensor (legacy ``initialize/deferred_init.py:38``; the device asked for — argument or
+    ``torch.device`` context — is remembered as ``_deferred_device`` and used when a plain tensor is materialised)."""
+    fname = getattr(module_fn, "__name__", "")
+    if fname in _FACTORY_RECORDS and getattr(torch, fname, None) is module_fn:
+        want = kwargs.pop("device", None)
+        if want is None:
+            want = torch.empty(0).device  # honours an enclosing ``with torch.device(...)``
+        with torch.device("meta"):
+            t = module_fn(*args, **kwargs)
+        t._deferred_init = _FACTORY_RECORDS[fname](args, kwargs)
+        t._deferred_device = torch.device(want)
+        t._is_deferred = True
+        return t
     with torch.device("meta"), _Recorder():
         m = module_fn(*args, **kwargs)
+    if isinstance(m, torch.Tensor):
+        m._is_deferred = True
+        return m
     for p in list(m.parameters()) + list(m.buffers()):
         if not hasattr(p, "_deferred_init"):
             d = getattr(p.data, "_deferred_init", None)
@@ -99,6 +126,8 @@ def _replay(local: torch.Tensor, spec: DTensorSpec, rec) -> torch.Tensor:
     if rec is None:
         return local.zero_()
     name, a, kw = rec
+    if name == "empty":
+        return local
     if name in ("zero_", "zeros_"):
         return local.zero_()
     if name == "ones_":
@@ -159,3 +188,15 @@ def materialize_module(module: nn.Module, device: str = "cpu") -> nn.Module:
             if b is not None and b.is_meta:
                 mod._buffers[n] = materialize_dtensor(b, mesh, [Replicate()])._local_tensor
     return module
+
+
+def materialize_plain_tensor(tensor: torch.Tensor, device=None) -> torch.Tensor:
+    """A deferred tensor in full, as a plain tensor on ``device`` (default: the device it was created for)."""
+    from ..mesh import DeviceMesh
+    from ..placement import Replicate
+
+    dev = torch.device(device if device is not None else getattr(tensor, "_deferred_device", "cpu"))
+    if dev.type == "meta":
+        dev = torch.device("cpu")
+    mesh = DeviceMesh(dev.type, [0], _init_process_groups=False, _rank=0)
+    return materialize_dtensor(tensor, mesh, [Replicate()])._local_tensor
