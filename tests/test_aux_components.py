@@ -450,3 +450,33 @@ def test_deferred_tensor_factories_and_torchdistx_names():
     assert is_deferred(m) and all(is_fake(p) for p in m.parameters())
     materialize_module(m)
     assert not is_deferred(m) and float(m.weight.abs().sum()) > 0
+
+
+def test_emulator_mesh_collectives_reference_call_forms():
+    """``vescale.emulator.mesh_collectives`` argument order (legacy ``emulator/mesh_collectives.py``) over a 2 × 2 emulated mesh."""
+    import torch
+
+    import vescale  # noqa: F401
+    import vescale.emulator.distributed as ed
+    from vescale.emulator.device_mesh import DeviceMesh
+    from vescale.emulator.mesh_collectives import mesh_all_gather, mesh_all_reduce, mesh_all_to_all, mesh_broadcast, mesh_reduce_scatter, mesh_scatter
+    from vescale.emulator.reduce_kernel import ReduceOp
+
+    ed.init_process_group(world_size=4, rank=0)
+    try:
+        mesh = DeviceMesh("cpu", torch.arange(4).view(2, 2))
+        ts = [torch.full((4,), float(r)) for r in range(4)]
+        assert [t[0].item() for t in mesh_all_reduce(ts, mesh, ReduceOp.SUM, 1)] == [1.0, 1.0, 5.0, 5.0]
+        assert [t[0].item() for t in mesh_all_reduce(ts, mesh, ReduceOp.SUM, 0, tree_structure=[[0, 1], [2, 3]])] == [2.0, 4.0, 2.0, 4.0]
+        assert mesh_all_gather(ts, mesh, 0, 1)[2].tolist() == [2.0] * 4 + [3.0] * 4
+        assert mesh_reduce_scatter(ts, mesh, ReduceOp.SUM, 0, 0)[3].tolist() == [4.0, 4.0]
+        outs = [[torch.zeros(4) for _ in range(2)] for _ in range(4)]
+        keep = outs[2][1]
+        mesh_all_to_all(outs, [[torch.full((4,), 10.0 * r + j) for j in range(2)] for r in range(4)], mesh, 1)
+        assert [[o[0].item() for o in row] for row in outs] == [[0.0, 10.0], [1.0, 11.0], [20.0, 30.0], [21.0, 31.0]] and keep[0].item() == 30.0
+        got = mesh_scatter([None] * 4, [[torch.tensor([r, j]) for j in range(2)] for r in range(4)], mesh, 0)
+        assert [x.tolist() for x in got] == [[0, 0], [1, 0], [0, 1], [1, 1]]
+        assert [t[0].item() for t in mesh_broadcast(ts, mesh, 1)] == [0.0, 0.0, 2.0, 2.0]
+        assert list(ed._world.pg_group_ranks.values())[0] == {0: 0, 1: 1, 2: 2, 3: 3}
+    finally:
+        ed.destroy_process_group()

@@ -90,7 +90,8 @@ _ALIASES = {
     "vescale.emulator.device_mesh": "vescale_b200.emulator.device_mesh",
     "vescale.emulator.reduce_kernel": "vescale_b200.emulator.reduce_kernel",
     "vescale.emulator.utils": "vescale_b200.emulator.utils",
-    "vescale.emulator.mesh_collectives": "vescale_b200.emulator.comm_api",
+    "vescale.emulator.mesh_collectives": "vescale_b200.emulator.mesh_collectives",
+    "vescale.emulator.comm_api": "vescale_b200.emulator.comm_api",
     "vescale.emulator.all_reduce": "vescale_b200.emulator.collectives",
     "vescale.emulator.all_gather": "vescale_b200.emulator.collectives",
     "vescale.emulator.reduce_scatter": "vescale_b200.emulator.collectives",
