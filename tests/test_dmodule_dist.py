@@ -326,3 +326,41 @@ def _deferred_output_reshard(rank, world):
 
 def test_deferred_output_reshard_single_allreduce():
     run_distributed(_deferred_output_reshard, 2)
+
+
+def _mixtral_plan_matches_single_device(rank, world):
+    """The sparse-MoE Mixtral of ``examples/mixtral_4D_benchmark`` under its TP+SP sharding plan (data-dependent routing on
+    replicated router outputs, row-parallel experts) reproduces the unparallelised model: output and gradients."""
+    import argparse
+    import importlib.util
+    import os
+
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.dmodule import parallelize_module
+
+    path = os.path.join(os.path.dirname(__file__), "..", "examples", "mixtral_4D_benchmark", "run.py")
+    spec = importlib.util.spec_from_file_location("mixtral_4d_example", path)
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    a = argparse.Namespace(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, num_experts=4, top_k=2)
+    torch.manual_seed(0)
+    dev = device_type()
+    model = ex.Mixtral(a).to(dev)
+    golden = copy.deepcopy(model)
+    ids = torch.randint(0, a.vocab_size, (2, 8), device=dev)
+    probe = torch.randn(2, 8, a.hidden_size, device=dev)
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("TP",))
+    parallelize_module(model, mesh, ex.mixtral_plan)
+    out = model(ids)
+    ref = golden(ids)
+    assert out.placements[0].is_replicate() and torch.allclose(out.to_local(), ref, atol=1e-4), (out.to_local() - ref).abs().max()
+    (out.to_local() * probe).sum().backward()
+    model.finish_grad_sync()
+    (ref * probe).sum().backward()
+    for name in ("layers.0.block_sparse_moe.experts.1.w2.weight", "layers.1.self_attn.q_proj.weight", "layers.0.block_sparse_moe.gate.weight", "embed_tokens.weight", "layers.1.post_attention_layernorm.weight"):
+        g, gg = dict(model.named_parameters())[name].grad, dict(golden.named_parameters())[name].grad
+        assert torch.allclose(g.full_tensor(), gg, atol=1e-3), (name, (g.full_tensor() - gg).abs().max())
+
+
+def test_mixtral_4d_plan_matches_single_device():
+    run_distributed(_mixtral_plan_matches_single_device, 2)
