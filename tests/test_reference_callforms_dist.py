@@ -1,0 +1,46 @@
+"""Reference call forms kept for drop-in use: ``vescale.dtensor._collective_utils`` (legacy ``dtensor/_collective_utils.py``) and
+``VESCALE_DEVICE_MESH`` accessors (legacy ``devicemesh_api/api.py``) on a 2 x 2 mesh."""
+import torch
+
+from common import device_type, run_distributed
+
+
+def _collective_utils(rank, world):
+    torch.set_default_device(device_type())
+    import vescale
+    from vescale.dtensor._collective_utils import mesh_all_gather, mesh_all_reduce, mesh_reduce_scatter, mesh_all_to_all, mesh_all_to_all_single, mesh_broadcast, mesh_scatter, broadcast_across_mesh
+    from vescale.dtensor.device_mesh import DeviceMesh
+    import torch.distributed.distributed_c10d as c10d
+    mesh = DeviceMesh(device_type(), torch.arange(4).view(2, 2))
+    x = torch.full((3, 2), float(rank))
+    assert mesh_all_reduce(x, mesh, c10d.ReduceOp.SUM, 1)[0, 0].item() == [1, 1, 5, 5][rank]
+    assert mesh_all_reduce(x, mesh, c10d.ReduceOp.MAX, 0)[0, 0].item() == [2, 3, 2, 3][rank]
+    g = mesh_all_gather(x, (3, 4), mesh, 1, 1); assert g.shape == (3, 4) and g[0].tolist() == ([0, 0, 1, 1] if rank < 2 else [2, 2, 3, 3])
+    # uneven: global 3 rows over 2 ranks -> 2 + 1
+    c = mesh.get_coordinate()[1]
+    loc = torch.arange(6.).view(3, 2)[[slice(0, 2), slice(2, 3)][c]]
+    assert torch.equal(mesh_all_gather(loc, (3, 2), mesh, 0, 1), torch.arange(6.).view(3, 2))
+    rs = mesh_reduce_scatter(torch.ones(4, 2) * (rank + 1), mesh, c10d.ReduceOp.SUM, 0, 1); assert rs.shape == (2, 2) and rs[0, 0].item() == (3 if rank < 2 else 7)
+    outs = [torch.zeros(2), torch.zeros(2)]
+    mesh_all_to_all(outs, [torch.full((2,), 10. * rank), torch.full((2,), 10. * rank + 1)], mesh, 1)
+    peer = rank ^ 1
+    assert outs[c][0].item() == 10. * rank + c and outs[1 - c][0].item() == 10. * peer + c
+    t = mesh_all_to_all_single(torch.arange(8.).view(2, 4) + 100 * c, mesh, 0, 1, 1); assert t.shape == (4, 2)
+    b = mesh_broadcast(torch.full((2,), float(rank)), mesh, 1); assert b[0].item() == (0 if rank < 2 else 2)
+    o = torch.zeros(2); mesh_scatter(o, [torch.full((2,), 5.), torch.full((2,), 6.)] if c == 0 else None, mesh, 1); assert o[0].item() == 5 + c
+    r = broadcast_across_mesh(torch.arange(3.) if rank == 2 else None, 2, (3,), torch.float32, mesh); assert r.tolist() == [0, 1, 2]
+
+    # VeDeviceMesh: lazy get(**config), strategy size by index or name, coordinates of other ranks
+    from vescale.devicemesh_api import VESCALE_DEVICE_MESH as V
+
+    V._mesh = None
+    m = V.get(device_type=device_type(), mesh_shape=(2, 2), mesh_dim_names=("DP", "TP"))
+    assert m.mesh.tolist() == [[0, 1], [2, 3]] and V.get() is m
+    assert V.get_strategy_size(0) == V.get_strategy_size("DP") == 2 and V.get_strategy_size("PP") == 1
+    assert V.get_strategy_coordinate(local_rank=3) == [1, 1] and V.get_strategy_coordinate() == [rank // 2, rank % 2]
+    assert V.lookup_rank("TP") == rank % 2 and "PP" not in V._MESH_DIM_NAMES_LOOKUP
+    assert [x.mesh.tolist() for x in V.get_global_pipeline_parallel_meshes(device_type())] == [[0, 1], [2, 3]]
+
+
+def test_reference_collective_utils_and_vedevicemesh_call_forms():
+    run_distributed(_collective_utils, 4)

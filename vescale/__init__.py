@@ -48,7 +48,7 @@ _ALIASES = {
     "vescale.dtensor._api": "vescale_b200.dtensor.api",
     "vescale.dtensor.dtensor": "vescale_b200.dtensor.api",
     "vescale.dtensor._utils": "vescale_b200.dtensor._utils",
-    "vescale.dtensor._collective_utils": "vescale_b200.comm.collectives",
+    "vescale.dtensor._collective_utils": "vescale_b200.dtensor._collective_utils",
     "vescale.dtensor.redistribute": "vescale_b200.dtensor.redistribute",
     "vescale.dtensor.op_schema": "vescale_b200.dtensor.op_schema",
     "vescale.dtensor.dispatch": "vescale_b200.dtensor.dispatch",

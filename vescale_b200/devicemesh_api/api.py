@@ -26,8 +26,11 @@ class VeDeviceMesh:
         return self._mesh
 
     def get(self, **kw) -> DeviceMesh:
+        """The global mesh.  Given ``init_device_mesh``'s arguments it initialises one on first use (legacy ``api.py:120-140``)."""
         if self._mesh is None:
-            raise RuntimeError("call VESCALE_DEVICE_MESH.init_device_mesh first")
+            if not kw:
+                raise RuntimeError("call VESCALE_DEVICE_MESH.init_device_mesh first")
+            self.init_device_mesh(kw.pop("device_type"), kw.pop("mesh_shape"), **kw)
         return self._mesh
 
     def __getitem__(self, names) -> DeviceMesh:
@@ -44,11 +47,16 @@ class VeDeviceMesh:
     def size(self, dim=None) -> int:
         return self.get().size(None if dim is None else self.get()._dim_index(dim))
 
-    def get_strategy_size(self, name: str) -> int:
-        return self.get().size(self._names.index(name.upper())) if name.upper() in self._names else 1
+    def get_strategy_size(self, name: Union[int, str]) -> int:
+        """Size of a strategy dim given by index or name (1 for a strategy this mesh does not have)."""
+        if isinstance(name, int):
+            return self.get().size(name)
+        up = [n.upper() for n in self._names]
+        return self.get().size(up.index(name.upper())) if name.upper() in up else 1
 
-    def get_strategy_coordinate(self, rank: Optional[int] = None) -> List[int]:
+    def get_strategy_coordinate(self, local_rank: Optional[int] = None, *, rank: Optional[int] = None) -> List[int]:
         m = self.get()
+        rank = local_rank if local_rank is not None else rank
         if rank is None:
             return list(m.get_coordinate())
         idx = m.mesh.flatten().tolist().index(rank)

@@ -58,3 +58,4 @@ __all__ = [
 
 torch.serialization.add_safe_globals([DTensor, DTensorSpec, TensorMeta, DeviceMesh, Shard, Replicate, Partial, RaggedShard, _StridedRaggedShard, _StridedShard, InterleavedShard])
 from . import _utils  # noqa: F401,E402
+from . import _collective_utils  # noqa: F401,E402
