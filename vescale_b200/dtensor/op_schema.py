@@ -33,17 +33,31 @@ def _freeze(x):
     return x
 
 
+@dataclass
+class RuntimeSchemaInfo:
+    """Which non-tensor arguments matter to sharding propagation (legacy ``op_schema.py:52-69``).  The propagation cache here keys
+    on EVERY argument (frozen once per call), so this record is informational: accepted, stored on the schema, never needed."""
+
+    static_argnum: int = 100
+    static_kwargkey: Optional[List[str]] = None
+    needs_pytree: bool = False
+
+
 class OpSchema:
     """``args_schema`` / ``kwargs_schema`` mirror the call with specs in place of DTensors.
-    Lists of DTensors (foreach ops, cat) become tuples of specs."""
+    Lists of DTensors (foreach ops, cat) become tuples of specs.  The fourth positional argument is the mesh (dispatcher) or a
+    ``RuntimeSchemaInfo`` (the reference's constructor form)."""
 
-    __slots__ = ("op", "args_schema", "kwargs_schema", "_hash", "_key", "mesh")
+    __slots__ = ("op", "args_schema", "kwargs_schema", "_hash", "_key", "mesh", "schema_info")
 
-    def __init__(self, op, args_schema: Tuple[Any, ...], kwargs_schema: Dict[str, Any], mesh=None):
+    def __init__(self, op, args_schema: Tuple[Any, ...], kwargs_schema: Dict[str, Any], mesh=None, schema_info: Optional["RuntimeSchemaInfo"] = None):
+        if isinstance(mesh, RuntimeSchemaInfo):
+            mesh, schema_info = None, mesh
         self.op = op
         self.args_schema = args_schema
         self.kwargs_schema = kwargs_schema
         self.mesh = mesh
+        self.schema_info = schema_info
         self._hash: Optional[int] = None
         self._key = None
 
@@ -62,6 +76,11 @@ class OpSchema:
 
     def __eq__(self, other) -> bool:
         return isinstance(other, OpSchema) and (self is other or self._frozen() == other._frozen())
+
+    @property
+    def args_spec(self) -> Tuple[DTensorSpec, ...]:
+        """Positional specs only (non-tensor arguments dropped)."""
+        return tuple(a for a in self.args_schema if isinstance(a, DTensorSpec))
 
     def tensor_specs(self) -> List[DTensorSpec]:
         """All specs in call order (lists flattened)."""

@@ -95,6 +95,29 @@ class Shard(Placement):
             pads.append(pad)
         return pieces, pads
 
+    # legacy spellings (``legacy/vescale/dtensor/placement_types.py:69-170``; padding on by default there)
+    def _split_tensor(self, tensor: torch.Tensor, num_chunks: int, *, with_padding: bool = True, contiguous: bool = True):
+        return self.split_tensor(tensor, num_chunks, with_padding=with_padding, contiguous=contiguous)
+
+    def _pad_tensor(self, tensor: torch.Tensor, pad_size: int) -> torch.Tensor:
+        """Append ``pad_size`` zeros along the sharded dim."""
+        if pad_size <= 0:
+            return tensor
+        dim = self.dim if self.dim >= 0 else self.dim + tensor.ndim
+        shape = list(tensor.shape)
+        shape[dim] = pad_size
+        return torch.cat([tensor, tensor.new_zeros(shape)], dim=dim)
+
+    def _unpad_tensor(self, tensor: torch.Tensor, pad_size: int) -> torch.Tensor:
+        if pad_size <= 0:
+            return tensor
+        dim = self.dim if self.dim >= 0 else self.dim + tensor.ndim
+        return tensor.narrow(dim, 0, tensor.size(dim) - pad_size)
+
+    def __hash__(self) -> int:
+        # not hash((dim,)): CPython hashes -1 and -2 alike, and Shard(-1) / Shard(-2) key different cache entries
+        return hash((type(self).__name__, self.dim + (1 << 20)))
+
     def __repr__(self) -> str:
         return f"Shard(dim={self.dim})"
 
@@ -109,6 +132,9 @@ class _StridedShard(Shard):
     is the concatenation, over the ``split_factor`` inner pieces, of the ``i``-th sub-chunk."""
 
     split_factor: int = 1
+
+    def __hash__(self) -> int:
+        return hash((type(self).__name__, self.dim + (1 << 20), self.split_factor))
 
     def __repr__(self) -> str:
         return f"_StridedShard(dim={self.dim}, sf={self.split_factor})"
