@@ -11,6 +11,8 @@ Parity: reference re-exports torch's DeviceMesh (``vescale/__init__.py:25-33``);
 """
 from __future__ import annotations
 
+import os
+
 import math
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple, Union
@@ -46,6 +48,10 @@ def _cur_rank() -> int:
     return 0
 
 
+class MeshError(RuntimeError, ValueError):
+    """An ill-formed mesh (the reference raises ``RuntimeError``, torch's own checks ``ValueError``; callers may catch either)."""
+
+
 class DeviceMesh:
     """``DeviceMesh("cuda", [[0,1],[2,3]], mesh_dim_names=("DP","TP"))``.
 
@@ -67,6 +73,12 @@ class DeviceMesh:
         _validate_mesh: bool = True,  # accepted for signature compatibility (legacy ``device_mesh.py:226``); the grid is always checked locally
     ):
         self.device_type = device_type
+        if (_rank is None and _init_process_groups and _dim_groups is None and pg is None and device_type != "meta" and dist.is_available()
+                and not dist.is_initialized() and all(k in os.environ for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"))):
+            # launched by torchrun but nobody created the default group yet: do it here (legacy ``device_mesh.py:258-270``)
+            dist.init_process_group("nccl" if device_type == "cuda" else "gloo")
+            if device_type == "cuda":
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", dist.get_rank() % max(1, torch.cuda.device_count()))))
         m = mesh.detach().cpu().to(torch.int64) if isinstance(mesh, torch.Tensor) else torch.tensor(mesh, dtype=torch.int64)
         if m.ndim == 0:
             m = m.reshape(1)
@@ -76,7 +88,9 @@ class DeviceMesh:
             raise ValueError("mesh_dim_names must have one name per mesh dim")
         flat = m.flatten().tolist()
         if len(set(flat)) != len(flat):
-            raise ValueError(f"DeviceMesh ranks must be unique, got {flat}")
+            raise MeshError(f"DeviceMesh ranks must be unique, found duplicate values in {flat}")
+        if _validate_mesh and _rank is None and _init_process_groups and device_type != "meta" and dist.is_available() and dist.is_initialized() and len(flat) > dist.get_world_size():
+            raise MeshError(f"DeviceMesh has {len(flat)} ranks, bigger than the world size {dist.get_world_size()}")
         self._flat = tuple(flat)
         self._shape = tuple(m.shape)
         self._hash = hash((device_type, self._flat, self._shape, self.mesh_dim_names))
@@ -196,6 +210,8 @@ class DeviceMesh:
 
     def get_dim_groups(self, mesh_dim: Union[int, str, None] = None):
         """Legacy spelling (``legacy/vescale/dtensor/device_mesh.py:468``): my group along ``mesh_dim``, or all of them."""
+        if not self._dim_groups and self.device_type != "meta":
+            raise RuntimeError("DeviceMesh process groups not initialized!")
         return self.get_all_groups() if mesh_dim is None else self.get_group(mesh_dim)
 
     def get_group_ranks(self, mesh_dim: Union[int, str] = 0) -> Tuple[int, ...]:
