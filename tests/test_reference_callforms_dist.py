@@ -44,3 +44,35 @@ def _collective_utils(rank, world):
 
 def test_reference_collective_utils_and_vedevicemesh_call_forms():
     run_distributed(_collective_utils, 4)
+
+
+def _interleaved_through_matmul(rank, world):
+    """A sequence-sharded activation stays sharded through flatten -> mm / addmm -> unflatten: ``Shard(1)`` becomes
+    ``InterleavedShard(0, B)`` and back, with no communication (legacy ``test/dtensor/shard/test_interleaved_shard.py``)."""
+    from vescale_b200 import InterleavedShard, Replicate, Shard, distribute_tensor, init_device_mesh
+    from vescale_b200.dtensor import from_local
+    from vescale_b200.dtensor.debug import CommDebugMode
+
+    torch.set_default_device(device_type())
+    mesh = init_device_mesh(device_type(), (world,))
+    torch.manual_seed(0)
+    lhs, rhs, bias = torch.rand(4, 3 * world, 5), torch.rand(5, 7), torch.rand(7)
+    d, r, b = distribute_tensor(lhs, mesh, [Shard(1)]), distribute_tensor(rhs, mesh, [Replicate()]), distribute_tensor(bias, mesh, [Replicate()])
+    with CommDebugMode() as comm:
+        x = d.reshape((-1, 5))
+        o = torch.mm(x, r)
+        o2 = o.reshape((4, -1, 7))
+        o3 = torch.addmm(b, x, r).reshape((4, -1, 7))
+    assert x.placements[0] == InterleavedShard(0, 4) and o.placements[0] == InterleavedShard(0, 4), (x.placements, o.placements)
+    assert o2.placements[0] == Shard(1) and o3.placements[0] == Shard(1) and comm.get_total_counts() == 0
+    assert torch.allclose(o2.full_tensor(), lhs @ rhs, atol=1e-6) and torch.allclose(o3.full_tensor(), lhs @ rhs + bias, atol=1e-6)
+    assert torch.allclose(x.full_tensor(), lhs.reshape(-1, 5))
+    try:  # a local shard that cannot hold whole sections is rejected
+        from_local(torch.rand(3, 3), mesh, [InterleavedShard(0, 4)])
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass
+
+
+def test_interleaved_shard_through_flatten_matmul_unflatten():
+    run_distributed(_interleaved_through_matmul, 2)

@@ -63,6 +63,10 @@ class _FromLocal(torch.autograd.Function):
         ctx.mesh = mesh
         if shape is not None and stride is None:
             stride = contiguous_stride(shape)
+        for p in placements:
+            n = getattr(p, "interleaved_size", None)
+            if n and p.dim < local.ndim and local.size(p.dim) % n:
+                raise ValueError(f"{p}: the local shard has {local.size(p.dim)} rows on dim {p.dim}, not a multiple of the {n} interleaved sections")
         if shape is None:
             shape, stride = compute_global_tensor_info(local, mesh, placements)
         if mesh.get_coordinate() is None:

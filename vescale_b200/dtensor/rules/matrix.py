@@ -75,9 +75,18 @@ def _pick(mesh, specs: Sequence[DTensorSpec], candidates: Sequence[Tuple[Tuple[P
     return [tuple(x) for x in ins], tuple(out)
 
 
+def _row_interleaved(a: DTensorSpec) -> List[Placement]:
+    """Rows of the left operand sharded section by section (a ``Shard(1)`` activation flattened to 2-D, legacy
+    ``InterleavedShard``): rows are independent, so the product keeps exactly that layout."""
+    from ...placement import InterleavedShard
+
+    return list({p for p in a.placements if isinstance(p, InterleavedShard) and p.dim == 0})
+
+
 def mm_rule(schema: OpSchema) -> RuleResult:
     a, b = schema.args_schema[0], schema.args_schema[1]
     cands = [((Shard(0), R), Shard(0)), ((R, Shard(1)), Shard(1)), ((Shard(1), Shard(0)), P), ((R, R), R), ((P, R), P), ((R, P), P)]
+    cands += [((p, R), p) for p in _row_interleaved(a)]
     ins, out = _pick(schema.mesh, [a, b], cands)
     return RuleResult(out=out, ins=ins)
 
@@ -93,6 +102,7 @@ def addmm_rule(schema: OpSchema) -> RuleResult:
     row = ((P, Shard(1), Shard(0)), P)
     if bias.ndim == 1:
         cands = [((R, Shard(0), R), Shard(0)), ((Shard(0), R, Shard(1)), Shard(1)), row, ((R, R, R), R)]
+        cands += [((R, p, R), p) for p in _row_interleaved(a)]
     else:
         cands = [((Shard(0) if bias.shape[0] != 1 else R, Shard(0), R), Shard(0)), ((Shard(1) if bias.shape[-1] != 1 else R, R, Shard(1)), Shard(1)), row, ((R, R, R), R)]
     ins, out = _pick(schema.mesh, [bias, a, b], cands)

@@ -11,7 +11,7 @@ Parity: legacy ``dtensor/ops/view_ops.py`` (DimSpec algebra) and ``vescale_view_
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -109,10 +109,37 @@ def map_view_placements(spec: DTensorSpec, out_shape: Sequence[int], mesh) -> Tu
         if ok:
             ins.append(p)
             outs.append(shard_with_dim(p, lead_out))
+            continue
+        alt = _interleaved_view(p, gi, gj, in_shape, out_shape, n)
+        if alt is not None:
+            ins.append(p)
+            outs.append(alt)
         else:
             ins.append(R)
             outs.append(R)
     return tuple(ins), tuple(outs)
+
+
+def _interleaved_view(p: Shard, gi: List[int], gj: List[int], in_shape, out_shape, n: int) -> Optional[Placement]:
+    """The two reshapes that keep a sequence-sharded activation sharded through a 2-D matmul (legacy ``InterleavedShard``):
+
+    * ``(B, S, H) Shard(1) -> (B*S, H)``: the dims in front of the sharded one become ``interleaved_size`` sections of the
+      flattened dim, each holding this rank's contiguous ``S/n`` slice — ``InterleavedShard(flat, B)``;
+    * ``(B*S, H) InterleavedShard(0, B) -> (B, S, H)``: the sections become leading dims again and the next dim is ``Shard``."""
+    if type(p) is Shard and len(gj) == 1 and p.dim in gi and in_shape[p.dim] % n == 0:
+        lead = math.prod(in_shape[d] for d in gi if d < p.dim)
+        if lead > 1:
+            return InterleavedShard(gj[0], lead)
+        return None
+    if isinstance(p, InterleavedShard) and gi == [p.dim] and len(gj) > 1:
+        acc = 1
+        for k, d in enumerate(gj):
+            if acc == p.interleaved_size:
+                return Shard(d) if out_shape[d] % n == 0 else None
+            acc *= out_shape[d]
+            if acc > p.interleaved_size:
+                return None
+    return None
 
 
 def _view_rule(size_arg: int = 1):
