@@ -118,3 +118,36 @@ def _tied(rank, world):
 
 def test_ddp_tied_weights():
     run_distributed(_tied, 4)
+
+
+def _clip_model_parallel(rank, world):
+    """the clip norm counts TP-replicated gradients once and TP-sharded ones over the TP mesh."""
+    import torch
+
+    from common import device_type
+    from vescale_b200 import Replicate, Shard, distribute_tensor, init_device_mesh
+    from vescale_b200.optim import clip_grad_norm_fp32, get_grad_norm_fp32
+
+    mesh = init_device_mesh(device_type(), (2, 2), mesh_dim_names=("DP", "TP"))
+    tp = mesh["TP"]
+    g = torch.Generator().manual_seed(7)
+    gw, gn, gp = torch.randn(8, 6, generator=g), torch.randn(6, generator=g), torch.randn(5, generator=g)
+    ref = torch.cat([gw.flatten(), gn, gp]).norm()
+    dw = distribute_tensor(gw.to(device_type()), tp, [Shard(0)], src_data_rank=None)
+    dn = distribute_tensor(gn.to(device_type()), tp, [Replicate()], src_data_rank=None)
+    plain = gp.to(device_type())
+    got = get_grad_norm_fp32([dw, dn, plain])
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-5, atol=1e-5)
+    params = [torch.nn.Parameter(t.clone()) for t in (dw, dn)]
+    for p, t in zip(params, (dw, dn)):
+        p.grad = t.clone()
+    total = clip_grad_norm_fp32(params, max_norm=0.5)
+    expect = torch.cat([gw.flatten(), gn]).norm()
+    torch.testing.assert_close(total.cpu(), expect, rtol=1e-5, atol=1e-5)
+    coef = 0.5 / (expect + 1e-6)
+    torch.testing.assert_close(params[1].grad.full_tensor().cpu(), gn * coef, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(params[0].grad.full_tensor().cpu(), gw * coef, rtol=1e-5, atol=1e-6)
+
+
+def test_clip_grad_norm_model_parallel():
+    run_distributed(_clip_model_parallel, 4)

@@ -250,6 +250,53 @@ def _grads_and_2d(rank, world):
         torch.testing.assert_close(torch.cat([da, db.t()], 1).full_tensor(), torch.cat([a, b.t()], 1))
 
 
+def _view_2d_and_inplace_partial(rank, world):
+    """(B,S,H)->(B*S,H) views under a DP x SP mesh ([Shard(0), Shard(1)]) and in-place ops on Partial tensors."""
+    from vescale_b200 import Partial, Replicate, Shard, distribute_tensor, init_device_mesh
+    from vescale_b200.dtensor import DTensor
+
+    dev = device_type()
+    mesh2 = init_device_mesh(dev, (2, 2), mesh_dim_names=("dp", "sp"))
+    x, w = _t((4, 8, 3), 11), _t((5, 3), 12)
+    y = torch.randint(0, 5, (4, 8), generator=torch.Generator().manual_seed(3)).to(dev)
+    for pl in ([Shard(0), Shard(1)], [Shard(1), Shard(2)], [Replicate(), Shard(1)], [Shard(1), Shard(0)], [Shard(0), Shard(0)]):
+        dx = distribute_tensor(x, mesh2, pl, src_data_rank=None)
+        torch.testing.assert_close(dx.view(32, 3).full_tensor(), x.view(32, 3), msg=lambda m: f"view {pl}: {m}")
+        torch.testing.assert_close(dx.reshape(-1).full_tensor(), x.reshape(-1), msg=lambda m: f"flatten {pl}: {m}")
+        dw = distribute_tensor(w, mesh2, [Replicate(), Replicate()], src_data_rank=None)
+        torch.testing.assert_close(torch.mm(dx.view(32, 3), dw.t()).full_tensor(), x.view(32, 3) @ w.t(), rtol=1e-5, atol=1e-5)
+        xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+        ref = F.cross_entropy(F.linear(xr, wr).view(-1, 5), y.view(-1))
+        ref.backward()
+        dxg = distribute_tensor(x, mesh2, pl, src_data_rank=None).requires_grad_()
+        dwg = distribute_tensor(w, mesh2, [Replicate(), Replicate()], src_data_rank=None).requires_grad_()
+        dy = distribute_tensor(y, mesh2, [Replicate(), Replicate()], src_data_rank=None)
+        loss = F.cross_entropy(F.linear(dxg, dwg).view(-1, 5), dy.view(-1))
+        torch.testing.assert_close(loss.full_tensor(), ref.detach(), rtol=1e-5, atol=1e-5, msg=lambda m: f"loss {pl}: {m}")
+        loss.redistribute(mesh2, [Replicate(), Replicate()]).backward()
+        torch.testing.assert_close(dwg.grad.full_tensor(), wr.grad, rtol=1e-4, atol=1e-5, msg=lambda m: f"dW {pl}: {m}")
+        torch.testing.assert_close(dxg.grad.full_tensor(), xr.grad, rtol=1e-4, atol=1e-5, msg=lambda m: f"dX {pl}: {m}")
+    # in-place ops on a Partial(sum) tensor: non-linear / scalar ops must reduce first (or raise), linear ones may stay Partial
+    mesh = init_device_mesh(dev, (world,))
+    a, b = _t((6, 8), 21), _t((8, 4), 22)
+    ref = a @ b
+    for name, fn in (("relu_", lambda t: t.relu_()), ("add_1", lambda t: t.add_(1.0)), ("clamp_", lambda t: t.clamp_(min=0.1)), ("mul_2", lambda t: t.mul_(2.0)), ("neg_", lambda t: t.neg_())):
+        o = distribute_tensor(a, mesh, [Shard(1)], src_data_rank=None) @ distribute_tensor(b, mesh, [Shard(0)], src_data_rank=None)
+        assert any(isinstance(p, Partial) for p in o.placements)
+        got = fn(o)
+        torch.testing.assert_close(got.full_tensor(), fn(ref.clone()), rtol=1e-5, atol=1e-5, msg=lambda m: f"{name}: {m}")
+        torch.testing.assert_close(o.full_tensor(), fn(ref.clone()), rtol=1e-5, atol=1e-5, msg=lambda m: f"{name} (self): {m}")
+    # neg of Partial(max) must not stay Partial(max)
+    loc = _t((4, 4), 30 + rank)
+    pm = DTensor.from_local(loc, mesh, [Partial("max")], run_check=False)
+    full = pm.full_tensor()
+    torch.testing.assert_close((-pm).full_tensor(), -full)
+
+
+def test_view_2d_mesh_and_inplace_partial():
+    run_distributed(_view_2d_and_inplace_partial, 4)
+
+
 def test_op_sweep_part0():
     run_distributed(_op_sweep, 4, 0, 2)
 

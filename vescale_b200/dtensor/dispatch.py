@@ -201,7 +201,14 @@ class OpDispatcher:
                         # the op needed ``self`` in another layout (e.g. scatter_ along the sharded dim): it ran on a resharded
                         # copy; bring the result back to self's own placements and write it into self's storage
                         res = local_out[0] if isinstance(local_out, (list, tuple)) else local_out
-                        if not isinstance(res, torch.Tensor) or any(p.is_partial() for p in self_arg._spec.placements):
+                        cur = self_arg._spec.placements
+                        if isinstance(res, torch.Tensor) and all(a == b or (a.is_partial() and b.is_replicate()) for a, b in zip(cur, spec.placements)) and res.shape == self_arg._local_tensor.shape:
+                            # ``self`` was Partial and the op does not commute with the pending reduction: it ran on the reduced
+                            # values; they become self's contents and self is Replicate from here on
+                            self_arg._local_tensor.copy_(res)
+                            self_arg._spec = DTensorSpec(spec.mesh, spec.placements, self_arg._spec.tensor_meta)
+                            return self_arg
+                        if not isinstance(res, torch.Tensor) or any(p.is_partial() for p in cur):
                             raise RuntimeError(f"{op}: in-place result would change placements {self_arg._spec.placements} -> {spec.placements}")
                         if _disable_redistribute():
                             raise RuntimeError(f"{op}: in-place update needs a reshard {spec.placements} -> {self_arg._spec.placements} but VESCALE_DISABLE_REDISTRIBUTE=1")

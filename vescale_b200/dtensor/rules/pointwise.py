@@ -153,11 +153,11 @@ def _partial_passthrough(base: str, specs, i, scalar_other: bool = False) -> Opt
     op0 = partials[0]
     if any(p != op0 for p in partials):
         return None
+    if op0.reduce_op not in ("sum", "avg"):
+        # max/min/product commute with monotone maps only (neg flips max<->min): pass through pure copies, nothing else
+        return op0 if base in ("clone", "_to_copy", "detach", "alias", "contiguous") else None
     if base in _LINEAR_UNARY and op0.norm_type is None:
         return op0
-    if op0.reduce_op not in ("sum", "avg"):
-        # max/min commute with monotone maps only; keep it simple
-        return op0 if base in ("clone", "_to_copy", "detach", "alias", "contiguous") else None
     if base in _LINEAR_ADD and len(partials) == len(ps) and not scalar_other:
         return op0
     if base in _LINEAR_SCALE:
@@ -220,11 +220,16 @@ def pointwise_rule(schema: OpSchema) -> RuleResult:
                     elif isinstance(p, RaggedShard):
                         req.append(p if tuple(s.shape) == tuple(specs[0].shape) else R)
                     elif p.is_partial():
-                        req.append(p if s is specs[0] else (p if base in _LINEAR_ADD else R))
+                        # a Partial ``self`` survives only the ops that commute with the pending reduction (``out`` kept it);
+                        # anything else (relu_, add_(scalar), clamp_, ...) reduces ``self`` first — the dispatcher writes the
+                        # result into self's storage and flips its placement to Replicate (torch raises here)
+                        keep = out[len(req)].is_partial() and out[len(req)] == p
+                        req.append((p if (s is specs[0] or base in _LINEAR_ADD) else R) if keep else R)
                     else:
                         req.append(R)
                 new_ins.append(tuple(req))
-            return RuleResult(out=tuple(self_pl), ins=new_ins)
+            out_pl = tuple(p if (not p.is_partial() or (out[k].is_partial() and out[k] == p)) else R for k, p in enumerate(self_pl))
+            return RuleResult(out=out_pl, ins=new_ins)
     return RuleResult(out=out, ins=ins)
 
 

@@ -85,6 +85,13 @@ def map_view_placements(spec: DTensorSpec, out_shape: Sequence[int], mesh) -> Tu
             dim_to_group[d] = (gi, gj)
     ins: List[Placement] = []
     outs: List[Placement] = []
+    # mesh dims that shard some dim of each view group: the interleaved layouts below describe the GLOBAL leading dims, so
+    # they are only valid when no other mesh dim shards a dim of the same group (e.g. [Shard(0), Shard(1)] on a DP x SP mesh)
+    sharders: Dict[int, int] = {}
+    for q in spec.placements:
+        if isinstance(q, Shard) and not isinstance(q, RaggedShard) and q.dim in dim_to_group:
+            k = id(dim_to_group[q.dim][0])
+            sharders[k] = sharders.get(k, 0) + 1
     for i, p in enumerate(spec.placements):
         n = mesh.size(i)
         if isinstance(p, RaggedShard):
@@ -110,7 +117,7 @@ def map_view_placements(spec: DTensorSpec, out_shape: Sequence[int], mesh) -> Tu
             ins.append(p)
             outs.append(shard_with_dim(p, lead_out))
             continue
-        alt = _interleaved_view(p, gi, gj, in_shape, out_shape, n)
+        alt = _interleaved_view(p, gi, gj, in_shape, out_shape, n) if sharders.get(id(gi), 0) <= 1 else None
         if alt is not None:
             ins.append(p)
             outs.append(alt)

@@ -147,7 +147,12 @@ class DistributedOptimizer:
         grads = self._main_grads()
         norm = None
         if self.clip_grad and self.clip_grad > 0:
-            norm = get_grad_norm_fp32(grads, 2.0, [self.group] + self.extra_norm_groups if self.dp > 1 else self.extra_norm_groups)
+            # model-parallel aware: each piece carries the spec of the parameter it belongs to (TP-sharded pieces are summed over
+            # the TP mesh, TP-replicated ones counted once), then the DP group joins the ZeRO shards
+            from .clip_grads import _spec_of
+
+            specs = [_spec_of(mp._orig_param) for plist in self.main_params.values() for mp in plist]
+            norm = get_grad_norm_fp32(grads, 2.0, ([self.group] if self.dp > 1 else []) + self.extra_norm_groups, specs)
             coef = torch.clamp(self.clip_grad / (norm + 1e-6), max=1.0)
             if grads:
                 torch._foreach_mul_(grads, coef)

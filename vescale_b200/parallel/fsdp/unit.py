@@ -264,9 +264,11 @@ class FSDPUnit:
                 self.grad_shard = torch.empty(S, dtype=self.reduce_dtype, device=self.device)
             backend = dist.get_backend(self.group)
             if backend == "nccl":
-                tmp = torch.empty(S, dtype=fg.dtype, device=self.device)
-                dist.reduce_scatter_tensor(tmp, fg, op=dist.ReduceOp.SUM, group=self.group)
-                torch.mul(tmp, scale, out=self.grad_shard) if self.grad_shard.dtype == tmp.dtype else self.grad_shard.copy_(tmp).mul_(scale)
+                # the cross-rank sum runs in ``reduce_dtype`` (MixedPrecisionPolicy default fp32, like FSDP2 and the legacy
+                # fp32 grad buffer ``ddp/grad_buffer.py:132-147``), as the gloo path and the symmetric-memory kernel do
+                red = fg if fg.dtype == self.reduce_dtype else fg.to(self.reduce_dtype)
+                dist.reduce_scatter_tensor(self.grad_shard, red, op=dist.ReduceOp.SUM, group=self.group)
+                self.grad_shard.mul_(scale)
             else:
                 red = fg.to(self.reduce_dtype)
                 dist.all_reduce(red, group=self.group)
