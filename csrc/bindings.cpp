@@ -26,6 +26,8 @@ void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
 // symm_comm.cu
 void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch);
 void symm_wait(int64_t my_pad, int64_t world, int64_t slot, int64_t epoch);
+void symm_all_gather_ce(std::vector<int64_t> shard_ptrs, at::Tensor full, int64_t shard_bytes, int64_t rank, std::vector<int64_t> pad_ptrs, int64_t slot,
+                        int64_t epoch, int64_t lo_bytes, int64_t hi_bytes);
 void symm_all_gather(std::vector<int64_t> shard_ptrs, at::Tensor full, int64_t shard_bytes, int64_t rank, std::vector<int64_t> pad_ptrs,
                      int64_t slot, int64_t epoch, int64_t num_ctas, int64_t range_mode, int64_t range_lo_bytes, int64_t range_hi_bytes);
 void symm_reduce_scatter(std::vector<int64_t> grad_ptrs, at::Tensor out, c10::optional<at::Tensor> sumsq, int64_t shard_elems, int64_t rank,
@@ -104,6 +106,7 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
   m.def("symm_wait(int my_pad, int world, int slot, int epoch) -> ()", &symm_wait);
+  m.def("symm_all_gather_ce(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int lo_bytes=0, int hi_bytes=0) -> ()");
   m.def("symm_all_gather(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int num_ctas, int range_mode=0, int range_lo_bytes=0, int range_hi_bytes=0) -> ()");
   m.def("symm_reduce_scatter(int[] grad_ptrs, Tensor(a!) out, Tensor(b!)? sumsq, int shard_elems, int rank, float scale, int[] pad_ptrs, int slot, int epoch, int multicast_ptr, int num_ctas) -> ()");
   m.def("symm_rs_adamw(int[] grad_ptrs, Tensor(a!) master, Tensor(b!) m, Tensor(c!) v, Tensor(d!) p_out, Tensor wd_table, Tensor coef, Tensor(e!)? sumsq, int rank, float scale, int[] pad_ptrs, int slot, int epoch, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int num_ctas) -> ()");
@@ -147,6 +150,7 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("ag_gemm", &ag_gemm);
   m.impl("gemm_rs", &gemm_rs);
   m.impl("symm_all_gather", &symm_all_gather);
+  m.impl("symm_all_gather_ce", &symm_all_gather_ce);
   m.impl("symm_reduce_scatter", &symm_reduce_scatter);
   m.impl("symm_rs_adamw", &symm_rs_adamw);
 }

@@ -34,7 +34,7 @@ constexpr int kFB = kBN * kFBK;             // 32 KB
 constexpr int kSFAtom = 512;                // 128 rows x 4 scales
 constexpr int kSFStage = 3 * kSFAtom;       // SFA atom + 2 SFB atoms
 constexpr int kFStages = 4;
-constexpr int kFEpi = 4 * 2 * 4096;         // 4 warps x 2 buffers x (32 rows x 128 B)
+constexpr int kFEpi = 4 * 4096;             // 4 warps x one staging buffer of 32 rows x 128 B (two would push the CTA past 227 KB)
 constexpr uint32_t kSfaCol = 256, kSfbCol = 260;
 
 VB_DEVICE void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -191,8 +191,8 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       aph ^= 1;
 #pragma unroll
       for (int c = 0; c < kBN / 64; ++c) {
-        uint8_t* buf = smem_epi + (ew * 2 + (c & 1)) * 4096;
-        if (lane == 0) tma_store_wait_read<1>();
+        uint8_t* buf = smem_epi + ew * 4096;
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         epi_write_row_swizzled_packed(buf, lane, packed + c * 32);
         fence_proxy_async();
@@ -244,7 +244,11 @@ __global__ void __launch_bounds__(256) mx_quantize_kernel(const __nv_bfloat16* _
       uint32_t packed = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float y = fminf(fmaxf(v[4 * i + j] * inv, -448.f), 448.f);
+        // mul.rn.f32 WITHOUT .ftz: the build uses --use_fast_math (ftz), which would flush subnormal inputs (blocks below 2^-126)
+        // to zero here while the specification (ops/fp8.py::quantize_mx) scales them up into range
+        float y;
+        asm("mul.rn.f32 %0, %1, %2;" : "=f"(y) : "f"(v[4 * i + j]), "f"(inv));
+        y = fminf(fmaxf(y, -448.f), 448.f);
         packed |= (uint32_t)__nv_cvt_float_to_fp8(y, __NV_SATFINITE, __NV_E4M3) << (8 * j);
       }
       w[i] = packed;
@@ -256,7 +260,9 @@ __global__ void __launch_bounds__(256) mx_quantize_kernel(const __nv_bfloat16* _
   }
 }
 
-int mxfp8_smem_bytes() { return kFStages * (kFA + kFB + kSFStage) + kFEpi + (2 * kFStages + 2) * 8 + 16 + 1024; }
+constexpr int kMxSmemBytes = kFStages * (kFA + kFB + kSFStage) + kFEpi + (2 * kFStages + 2) * 8 + 16 + 1024;
+static_assert(kMxSmemBytes <= 232448, "gemm_mxfp8_kernel: dynamic shared memory exceeds the 227 KB per-CTA limit of sm_100");
+int mxfp8_smem_bytes() { return kMxSmemBytes; }
 
 }  // namespace
 

@@ -261,3 +261,41 @@ def _act_ckpt(rank, world):
 
 def test_fsdp_with_activation_checkpointing():
     run_distributed(_act_ckpt, 4)
+
+
+def _fsdp_timeline(rank, world):
+    """ndtimeline is wired into the engine: UNSHARD_AG / GRAD_RS on the communication streams, OPTIMIZER_STEP around the update
+    (legacy predefined metrics ``ndtimeline/predefined.py:17-30``; the reference's FSDP patch is a stub, ``fsdp_patch.py:17-28``)."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200 import profiler as ndt
+    from vescale_b200.models import LlamaConfig, LlamaModel
+    from vescale_b200.optim import FSDPAdamW
+    from vescale_b200.parallel.fsdp import MixedPrecisionPolicy, fully_shard
+
+    seen = []
+
+    class Capture(ndt.NDHandler):
+        def __call__(self, records, rank_, step):
+            seen.extend((r["metric"], r["tags"].get("unit")) for r in records)
+
+    ndt.init_ndtimers(rank=rank, world_size=world, handlers=[Capture()])
+    dev = device_type()
+    cfg = LlamaConfig.tiny()
+    mesh = init_device_mesh(dev, (world,))
+    model = LlamaModel(cfg).reset_parameters(seed=1).to(dev)
+    mp = MixedPrecisionPolicy(param_dtype=torch.float32, reduce_dtype=torch.float32)
+    for blk in model.layers:
+        fully_shard(blk, mesh, mp_policy=mp)
+    fully_shard(model, mesh, mp_policy=mp)
+    opt = FSDPAdamW(model, lr=1e-3)
+    tok = torch.randint(0, cfg.vocab_size, (2, 16)).to(dev)
+    model(tok, tok).backward()
+    opt.step()
+    ndt.flush(asynchronous=False)
+    metrics = {m for m, _ in seen}
+    assert {"unshard-all-gather", "grad-reduce-scatter", "optimizer-step"} <= metrics, metrics
+    assert sum(1 for m, _ in seen if m == "grad-reduce-scatter") == cfg.num_layers + 1
+
+
+def test_fsdp_ndtimeline_regions():
+    run_distributed(_fsdp_timeline, 2)

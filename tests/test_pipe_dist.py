@@ -70,6 +70,57 @@ def test_pipeline_schedules_match_single_process(sched):
     run_distributed(_pp, 4, sched, "STRUCTURAL")
 
 
+def _pp_overlap(rank, world, batch):
+    """p2p is overlapped: receives are prefetched from the pair order, the shape record travels once, sends + following
+    receives form one batch group when the plan asks for it, and every op shows up on the ndtimeline."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200 import profiler as ndt
+    from vescale_b200.parallel.pipe import PipeEngine, PipelineParallelPlan, PipelineScheduleType, construct_pipeline_stage
+
+    dev = device_type()
+    seen = []
+
+    class Capture(ndt.NDHandler):
+        def __call__(self, records, rank_, step):
+            seen.extend(r["metric"] for r in records)
+
+    ndt.init_ndtimers(rank=rank, world_size=world, handlers=[Capture()])
+    ref = make_model().to(dev)
+    model = copy.deepcopy(ref)
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("PP",))
+    plan = PipelineParallelPlan(num_stages=world, schedule_type=PipelineScheduleType.SIMPLE_1F1B, batch_p2p_comm=batch)
+    pm = construct_pipeline_stage(model, plan, mesh)
+    M = 8
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(3, 16, generator=g).to(dev) for _ in range(M)]
+    ys = [torch.randn(3, 16, generator=g).to(dev) for _ in range(M)]
+    loss_fn = lambda out, y: torch.nn.functional.mse_loss(out, y)
+    engine = PipeEngine(pm, mesh, loss_fn, plan)
+    engine(xs, ys)
+    first = dict(engine.schedule_engine.last_p2p.stats)
+    loss, _ = engine(xs, ys)
+    st = engine.schedule_engine.last_p2p.stats
+    assert first["meta_messages"] > 0 and st["meta_messages"] == 0, (first, st)  # shapes handshaken once, then reused
+    n_recv = (M if rank > 0 else 0) + (M if rank < world - 1 else 0)
+    assert st["prefetched_recvs"] >= n_recv - 2, (st, n_recv)  # all but the very first receive of each direction were posted early
+    if batch and 0 < rank < world - 1:
+        assert st["batched_groups"] > 0, st
+    ref_loss = sum(loss_fn(ref(x), y) / M for x, y in zip(xs, ys))
+    if engine.is_last_rank:
+        torch.testing.assert_close(loss, ref_loss.detach(), rtol=1e-5, atol=1e-6)
+    ndt.flush(asynchronous=False)
+    assert "forward-compute" in seen and "backward-compute" in seen, set(seen)
+    if rank < world - 1:
+        assert "send-forward" in seen and "recv-backward" in seen, set(seen)
+    if rank > 0:
+        assert "recv-forward" in seen and "send-backward" in seen, set(seen)
+
+
+@pytest.mark.parametrize("batch", [False, True])
+def test_pipeline_p2p_overlap_and_timeline(batch):
+    run_distributed(_pp_overlap, 4, batch)
+
+
 def test_pipeline_fx_tracer():
     run_distributed(_pp, 2, "SIMPLE_1F1B", "FX")
 

@@ -156,6 +156,50 @@ def test_symmetric_memory_kernels_single_rank(tmp_path):
         assert torch.equal(full[slot.offset : slot.end].view(slot.shape), wq)
         wantq = xin.float() @ wq.float().t()
         assert (yq.float() - wantq).abs().max().item() < 0.02 * wantq.abs().max().item() + 0.05
+        # ---- FSDP default-path kernels with one rank: all-gather (SM pull and copy-engine forms, whole
+        # unit / only-range / skip-range), reduce-scatter ⊕ scale ⊕ fp32 ⊕ sum-of-squares (P2P and NVLS forms), reduce-scatter ⊕ AdamW
+        S = unit.S
+        shard = unit.param_shard
+        ref_shard = shard.clone()
+        lo, hi = slot.offset, slot.end
+        for impl in ("pull", "ce"):
+            comm.ag_impl = impl
+            full2 = torch.full((S,), float("nan"), dtype=torch.bfloat16, device=dev)
+            comm.all_gather(shard, full2, unit)
+            torch.cuda.synchronize()
+            assert torch.equal(full2, ref_shard), impl
+            full3 = torch.zeros(S, dtype=torch.bfloat16, device=dev)
+            comm.all_gather(shard, full3, unit, only=(lo, hi))
+            torch.cuda.synchronize()
+            assert torch.equal(full3[lo:hi], ref_shard[lo:hi]) and full3[:lo].abs().sum().item() == 0 and full3[hi:].abs().sum().item() == 0, impl
+            full4 = torch.zeros(S, dtype=torch.bfloat16, device=dev)
+            comm.all_gather(shard, full4, unit, skip=(lo, hi))
+            torch.cuda.synchronize()
+            assert torch.equal(full4[:lo], ref_shard[:lo]) and torch.equal(full4[hi:], ref_shard[hi:]) and full4[lo:hi].abs().sum().item() == 0, impl
+        fg = unit._alloc_full(torch.bfloat16, symmetric=True)
+        fg.copy_((torch.randn(S, device=dev, generator=g) * 0.1).bfloat16())
+        want_g = fg.float() * 0.5
+        for mm in (False, True):
+            comm.use_multimem = mm
+            out = torch.zeros(S, dtype=torch.float32, device=dev)
+            comm.reduce_scatter(fg, out, 0.5, unit)
+            torch.cuda.synchronize()
+            torch.testing.assert_close(out, want_g, rtol=1e-2, atol=1e-3)
+            torch.testing.assert_close(unit.sumsq[0], want_g.pow(2).sum(), rtol=2e-2, atol=1e-3)
+        comm.use_multimem = True
+        # reduce-scatter ⊕ AdamW against torch.optim.AdamW on the same fp32 master
+        unit.exp_avg = torch.zeros(S, dtype=torch.float32, device=dev)
+        unit.exp_avg_sq = torch.zeros(S, dtype=torch.float32, device=dev)
+        unit.wd_table = torch.tensor([[0, S, 1]], dtype=torch.int64, device=dev)
+        ref_p = torch.nn.Parameter(unit.master.clone())
+        ref_p.grad = want_g.clone()
+        opt = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+        opt.step()
+        hp = dict(coef=torch.ones(1, device=dev), lr=1e-2, b1=0.9, b2=0.95, eps=1e-8, wd=0.1, bc1=1.0 - 0.9, bc2=1.0 - 0.95)
+        comm.reduce_scatter_adamw(fg, unit, 0.5, hp)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(unit.master, ref_p.detach(), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(unit.param_shard.float(), ref_p.detach().bfloat16().float(), rtol=1e-2, atol=1e-3)
     finally:
         torch.cuda.synchronize()
         if created:

@@ -146,6 +146,8 @@ class SymmUnitComm:
         self._unit_slots: Dict[int, Tuple[int, int, int]] = {}
         self._fused_sites: Dict[Tuple[int, str], dict] = {}
         self._epochs: Dict[Tuple[int, str], int] = {}
+        # all-gather transport: "ce" = peer cudaMemcpyAsync on the copy engines (default: zero SMs), "pull" = SM pull kernel
+        self.ag_impl = os.environ.get("VESCALE_B200_AG_IMPL", "ce")
         self.ag_ctas = int(os.environ.get("VESCALE_B200_AG_CTAS", "0"))
         self.rs_ctas = int(os.environ.get("VESCALE_B200_RS_CTAS", "0"))
 
@@ -180,6 +182,22 @@ class SymmUnitComm:
             raise ValueError("skip range must start on a 16-byte boundary")
         if mode == 2:
             hi = hi * esz // 16 * 16 // esz  # never skip a partially covered vector
+        if self.ag_impl == "ce":
+            # copy engines (peer cudaMemcpyAsync): no SM is taken from the GEMMs the gather overlaps
+            _ext.count_launch("symm_all_gather_ce")
+            args = (self.arena.peer_ptrs(shard), full, shard.numel() * esz, self.rank)
+            pads = self.arena.pad_ptrs if handshake else []
+            if mode == 0:
+                self.ops.symm_all_gather_ce(*args, pads, ag_slot, epoch, 0, 0)
+            elif mode == 1:
+                self.ops.symm_all_gather_ce(*args, pads, ag_slot, epoch, lo * esz, hi * esz)
+            else:
+                total = full.numel() * esz
+                # [0, lo) with the handshake (an empty range, lo == hi == 1, still exchanges the flags), then [hi, total)
+                self.ops.symm_all_gather_ce(*args, pads, ag_slot, epoch, 0 if lo > 0 else 1, lo * esz if lo > 0 else 1)
+                if hi * esz < total:
+                    self.ops.symm_all_gather_ce(*args, [], ag_slot, epoch, hi * esz, total)
+            return
         _ext.count_launch("symm_all_gather")
         self.ops.symm_all_gather(
             self.arena.peer_ptrs(shard), full, shard.numel() * esz, self.rank, self.arena.pad_ptrs if handshake else [], ag_slot, epoch, self.ag_ctas, mode,

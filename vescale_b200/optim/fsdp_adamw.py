@@ -18,6 +18,7 @@ import torch
 import torch.distributed as dist
 
 from ..ops import _ext
+from ..profiler import ndtimeit, predefined
 from ..parallel.fsdp.api import FSDPState, get_fsdp_state
 from ..parallel.fsdp.unit import FSDPUnit
 
@@ -189,6 +190,10 @@ class FSDPAdamW:
 
     @torch.no_grad()
     def step(self) -> Optional[torch.Tensor]:
+        with ndtimeit(predefined.OPTIMIZER_STEP):
+            return self._step()
+
+    def _step(self) -> Optional[torch.Tensor]:
         st = self.state
         st.wait_grads()
         self.step_count += 1

@@ -31,6 +31,8 @@ from .unit import FSDPUnit, MixedPrecisionPolicy, make_event, _NullStream
 __all__ = ["checkpoint_module", "fully_shard", "FSDPState", "MixedPrecisionPolicy", "get_fsdp_state", "fsdp_units"]
 
 
+from ...profiler import ndtimeit, predefined  # ndtimeline: UNSHARD_AG / GRAD_RS regions on the communication streams
+
 class _BufferPool:
     """Recycles gathered-parameter / gradient buffers.  A buffer handed back is tagged with the event
     after which its contents are dead; the next user makes its stream wait for that event."""
@@ -164,7 +166,7 @@ class FSDPState:
         # the shard may have just been written by the optimizer on the compute stream
         self.ag_stream.wait_stream(self.cur_stream())
         hs = self._need_handshake()
-        with self.on(self.ag_stream):
+        with self.on(self.ag_stream), ndtimeit(predefined.UNSHARD_AG, stream=self.ag_stream if self.cuda else None, unit=u.name):
             u.all_gather(full, handshake=hs)
             evt = make_event(self.device)
             evt.record(self.ag_stream if self.cuda else None)
@@ -338,7 +340,7 @@ class FSDPState:
             u.detach_grad_buffer()  # grad_shard keeps aliasing the persistent bf16 buffer
             return
         self.rs_stream.wait_stream(self.cur_stream())
-        with self.on(self.rs_stream):
+        with self.on(self.rs_stream), ndtimeit(predefined.GRAD_RS, stream=self.rs_stream if self.cuda else None, unit=u.name):
             fused = getattr(self, "fused_optimizer", None)
             if fused is not None and self.comm is not None and getattr(self.comm, "symmetric", False):
                 fused.fused_update(u, scale)  # reduce-scatter ⊕ AdamW ⊕ bf16 cast in one kernel

@@ -19,6 +19,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from ...profiler import ndtimeit, predefined
 from .p2p import P2PContext
 from .plan import PipelineParallelPlan, PipelineScheduleType
 from .schedule import INSTRUCTION_REGISTRY, Instr, build_schedule, stage_placement, validate_pipeline_schedule
@@ -55,24 +56,35 @@ class ScheduleEngine:
                     f.write("\n".join(repr(i) for i in self._sched_cache[M][self.rank]))
         return self._sched_cache[M]
 
-    def _incoming_order(self, rows: List[List[Instr]]) -> Dict[int, List[Tuple[str, int, int]]]:
-        """For every peer: the messages it sends me, in its send order."""
-        order: Dict[int, List] = {}
+    def _pair_ops(self, rows: List[List[Instr]]) -> Dict[int, List[Tuple[str, Tuple[str, int, int]]]]:
+        """For every peer: all messages between us, both directions, in *pair order* — sorted by the simulated time at which the
+        producing instruction ends (ties: lower sender rank first).  Both ends compute the same list (see ``p2p.py``)."""
+        msgs: Dict[int, List] = {}
         for r, row in enumerate(rows):
-            if r == self.rank:
-                continue
             for ins in row:
-                if ins.kind == "F" and ins.vstage + 1 < self.NV and self.place[ins.vstage + 1][0] == self.rank:
-                    order.setdefault(r, []).append(("F", ins.microbatch, ins.vstage))
-                if ins.kind == "B" and ins.vstage > 0 and self.place[ins.vstage - 1][0] == self.rank:
-                    order.setdefault(r, []).append(("B", ins.microbatch, ins.vstage))
-        return order
+                if ins.kind == "F" and ins.vstage + 1 < self.NV:
+                    dst = self.place[ins.vstage + 1][0]
+                elif ins.kind == "B" and ins.vstage > 0:
+                    dst = self.place[ins.vstage - 1][0]
+                else:
+                    continue
+                if dst == r or self.rank not in (r, dst):
+                    continue
+                peer = dst if r == self.rank else r
+                msgs.setdefault(peer, []).append((ins.end, r, ins.kind, ins.microbatch, ins.vstage))
+        out = {}
+        for peer, lst in msgs.items():
+            lst.sort()
+            out[peer] = [("S" if src == self.rank else "R", (kind, m, v)) for _, src, kind, m, v in lst]
+        return out
 
     def execute(self, inputs: Sequence, labels: Optional[Sequence], forward_only: bool = False):
         M = len(inputs)
         rows = self.schedule(M)
-        p2p = P2PContext(self.group, self.rank, self._incoming_order(rows), self.device, self.plan.p2p_tensor_dtype, self.plan.reuse_p2p_tensor_shape)
+        p2p = P2PContext(self.group, self.rank, self._pair_ops(rows), self.device, self.plan.p2p_tensor_dtype, self.plan.reuse_p2p_tensor_shape,
+                         prefetch=getattr(self.plan, "overlap_p2p_comm", True), batch=getattr(self.plan, "batch_p2p_comm", True))
         p2p.shapes = self._shape_cache
+        self.last_p2p = p2p
         acts: Dict[Tuple[int, int], Tuple] = {}  # (m, v) -> (stage_inputs, stage_outputs)
         local_fwd: Dict[Tuple[int, int], Tuple] = {}
         local_bwd: Dict[Tuple[int, int], Tuple] = {}
@@ -92,7 +104,7 @@ class ScheduleEngine:
                 else:
                     xs = p2p.recv(("F", m, v - 1), self.place[v - 1][0])
                 xs = tuple(x.detach().requires_grad_(x.is_floating_point() and not forward_only) if isinstance(x, torch.Tensor) else x for x in xs)
-                with torch.set_grad_enabled(not forward_only):
+                with torch.set_grad_enabled(not forward_only), ndtimeit(predefined.FORWARD_COMPUTE, microbatch=m, vstage=v):
                     out = self.module(*xs, chunk_id=c)
                     outs = _as_tuple(out)
                     if v == self.NV - 1:
@@ -118,13 +130,15 @@ class ScheduleEngine:
                 pairs = [(o, g) for o, g in zip(outs, gouts) if isinstance(o, torch.Tensor) and o.requires_grad]
                 o_t, g_t = [p[0] for p in pairs], [p[1] for p in pairs]
                 grad_inputs = [x for x in xs if isinstance(x, torch.Tensor) and x.requires_grad]
-                if self.split_w:
-                    gi = torch.autograd.grad(o_t, grad_inputs, g_t, retain_graph=True, allow_unused=True) if grad_inputs else ()
-                    pending_w[(m, v)] = (o_t, g_t)
-                else:
-                    torch.autograd.backward(o_t, g_t)
-                    gi = tuple(x.grad for x in grad_inputs)
-                    del acts[(m, v)]
+                with ndtimeit(predefined.BACKWARD_COMPUTE, microbatch=m, vstage=v):
+                    if self.split_w:
+                        gi = torch.autograd.grad(o_t, grad_inputs, g_t, retain_graph=True, allow_unused=True) if grad_inputs else ()
+                        pending_w[(m, v)] = (o_t, g_t)
+                    else:
+                        torch.autograd.backward(o_t, g_t)
+                        gi = tuple(x.grad for x in grad_inputs)
+                        del acts[(m, v)]
+                p2p.drain_sends(keep=2 * self.V)  # retire old sends so their buffers are freed while the pipeline keeps running
                 if v > 0:
                     gi = tuple(g if g is not None else torch.zeros_like(x) for g, x in zip(gi, grad_inputs))
                     if self.place[v - 1][0] == self.rank:
@@ -134,7 +148,8 @@ class ScheduleEngine:
             elif ins.kind == "W":
                 o_t, g_t = pending_w.pop((m, v))
                 params = [p for p in self.module.chunk(c).parameters() if p.requires_grad]
-                gs = torch.autograd.grad(o_t, params, g_t, allow_unused=True)
+                with ndtimeit(predefined.BACKWARD_COMPUTE, microbatch=m, vstage=v, part="weight-grad"):
+                    gs = torch.autograd.grad(o_t, params, g_t, allow_unused=True)
                 for p, g in zip(params, gs):
                     if g is not None:
                         p.grad = g if p.grad is None else p.grad + g
