@@ -24,6 +24,8 @@ void gemm_nn(const at::Tensor& a, const at::Tensor& b, at::Tensor c);
 void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate);
 
 // symm_comm.cu
+void gemm_set_sched(int64_t mode);
+int64_t gemm_get_sched();
 void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch);
 void symm_wait(int64_t my_pad, int64_t world, int64_t slot, int64_t epoch);
 void symm_all_gather_ce(std::vector<int64_t> shard_ptrs, at::Tensor full, int64_t shard_bytes, int64_t rank, std::vector<int64_t> pad_ptrs, int64_t slot,
@@ -104,6 +106,8 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("gemm_tn(Tensor a, Tensor b, Tensor(a!) c, bool accumulate) -> ()");
   m.def("ag_gemm(Tensor x_local, int[] x_ptrs, Tensor w, Tensor(a!) x_full, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
+  m.def("gemm_set_sched(int mode) -> ()", &gemm_set_sched);
+  m.def("gemm_get_sched() -> int", &gemm_get_sched);
   m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
   m.def("symm_wait(int my_pad, int world, int slot, int epoch) -> ()", &symm_wait);
   m.def("symm_all_gather_ce(int[] shard_ptrs, Tensor(a!) full, int shard_bytes, int rank, int[] pad_ptrs, int slot, int epoch, int lo_bytes=0, int hi_bytes=0) -> ()");

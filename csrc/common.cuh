@@ -316,6 +316,29 @@ VB_DEVICE void umma_commit_2cta_mc(uint64_t* bar, uint16_t mask) {
 }
 
 // ---- system-scope signalling for cross-GPU flags in peer-mapped memory
+// ---- cluster launch control (sm_100): a running cluster asks the hardware for the index of a not-yet-launched cluster and runs
+// its work itself -- a dynamic tile scheduler with no global counter.  The 16-byte response is written (async proxy) to the same
+// shared-memory offset in every CTA of the cluster and completes 16 bytes on each CTA's mbarrier at the same offset.
+VB_DEVICE void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+VB_DEVICE void clc_try_cancel_mc(uint32_t resp_smem, uint32_t bar_smem) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];" ::"r"(resp_smem),
+               "r"(bar_smem)
+               : "memory");
+}
+// -> first ctaid.x of the cancelled cluster, or -1 when nothing was left to cancel
+VB_DEVICE int clc_read(uint32_t resp_smem) {
+  uint32_t valid, x;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\tld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\tselp.u32 %1, 1, 0, p1;\n\tmov.u32 %0, 0;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}\n"
+      : "=r"(x), "=r"(valid)
+      : "r"(resp_smem)
+      : "memory");
+  return valid ? (int)x : -1;
+}
 VB_DEVICE void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 VB_DEVICE uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;

@@ -12,6 +12,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda.h>
+#include <string>
 #include <cudaTypedefs.h>
 
 #include <mutex>
@@ -219,7 +220,12 @@ constexpr int kB2Bytes = (kBN / 2) * kBK * 2;  // half B tile per CTA
 constexpr int kStage2 = kABytes + kB2Bytes;    // 32 KB
 constexpr int kEpiBytes = 4 * 2 * 4096;         // epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B)
 
-template <int STAGES, bool A_MN, bool B_MN>
+// CLC = true: tile scheduling by cluster launch control.  The grid has one cluster per tile; a cluster that finishes its tile
+// cancels a not-yet-launched cluster and runs that tile itself, so tiles flow to whichever SM pairs are making progress.  The
+// static `tile += num_pairs` schedule makes every GEMM as slow as its slowest CTA pair, which hurts exactly when a communication
+// kernel shares some of the SMs.  Roles: warp 3 of the leader CTA is the scheduler; the TMA producer, the
+// MMA issuer and the four epilogue warps of both CTAs consume every response, in order, through a 2-slot ring.
+template <int STAGES, bool A_MN, bool B_MN, bool CLC = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
                     __nv_bfloat16* __restrict__ C, int M, int N, int K, int ldc, int accumulate, int group_m, const int* __restrict__ tile_expert,
@@ -236,6 +242,10 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  constexpr int kClcSlots = 2;
+  uint64_t* clc_full = tempty_bar + 4;   // [kClcSlots]  (tmem_holder occupies the 16 bytes in between)
+  uint64_t* clc_empty = clc_full + kClcSlots;
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(clc_empty + kClcSlots);  // kClcSlots x 16 B, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,6 +281,14 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * kEpilogueThreads);  // both CTAs' epilogue threads release the pair's accumulator
     }
+    if (CLC) {
+      for (int s = 0; s < kClcSlots; ++s) {
+        mbar_init(&clc_full[s], 1);
+        // consumers of one response (arrive on the leader's barrier): leader = producer + MMA + 4 epilogue warps + scheduler,
+        // peer = producer + 4 epilogue warps
+        mbar_init(&clc_empty[s], 12);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -282,12 +300,28 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // next tile of this cluster.  Static: stride by the number of resident pairs.  CLC: the next response of the ring.
+  int sslot = 0;
+  uint32_t sph = 0;
+  auto next_tile = [&](int cur, bool arrive) -> int {
+    if (!CLC) return cur + num_pairs;
+    mbar_wait(&clc_full[sslot], sph);
+    const int x = clc_read(smem_u32(clc_resp + sslot * 16));
+    fence_proxy_async();  // this generic-proxy read is ordered before the async-proxy write of the next response into the slot
+    if (arrive) mbar_arrive_cluster(mapa(smem_u32(&clc_empty[sslot]), 0));
+    if (++sslot == kClcSlots) {
+      sslot = 0;
+      sph ^= 1;
+    }
+    return x >= 0 ? (x >> 1) : num_tiles;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer (both CTAs; bytes land on the leader's full barrier) =====================
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int tile = pair; tile < num_tiles; tile = next_tile(tile, true)) {
         int m_blk, n_blk;
         tile_coord(tile, m_blk, n_blk);
         const int ex = tile_expert ? tile_expert[m_blk] : 0;
@@ -325,7 +359,7 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int tile = pair; tile < num_tiles; tile = next_tile(tile, true)) {
         if (tile_expert) {
           int m_blk, n_blk;
           tile_coord(tile, m_blk, n_blk);
@@ -357,12 +391,33 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
       }
     }
+  } else if (CLC && warp == 3) {
+    if (lane == 0 && leader) {
+      // ===================== tile scheduler (cluster launch control) =====================
+      int slot = 0;
+      uint32_t ph = 0;
+      while (true) {
+        mbar_wait(&clc_empty[slot], ph ^ 1);  // every consumer of both CTAs has read the previous response in this slot
+        mbar_expect_tx(&clc_full[slot], 16);
+        mbar_expect_tx_cluster(mapa(smem_u32(&clc_full[slot]), 1), 16);
+        clc_try_cancel_mc(smem_u32(clc_resp + slot * 16), smem_u32(&clc_full[slot]));
+        mbar_wait(&clc_full[slot], ph);
+        const int x = clc_read(smem_u32(clc_resp + slot * 16));
+        fence_proxy_async();
+        mbar_arrive(&clc_empty[slot]);
+        if (x < 0) break;  // nothing left to cancel: the consumers see the same response and stop too
+        if (++slot == kClcSlots) {
+          slot = 0;
+          ph ^= 1;
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
     const int ew = warp - 4;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int tile = pair; tile < num_tiles; tile = (__syncwarp(), next_tile(tile, lane == 0))) {
       int m_blk, n_blk;
       tile_coord(tile, m_blk, n_blk);
       if (tile_expert && tile_expert[m_blk] < 0) continue;
@@ -659,9 +714,19 @@ const CUtensorMap& cached_tmap_store_bf16(const void* p, int64_t rows, int64_t c
   return it->second;
 }
 
+// tile scheduling of the 2-CTA kernels: 0 = static persistent grid, 1 = cluster launch control (one cluster per tile, running
+// clusters pull the remaining tiles).  VESCALE_B200_GEMM_SCHED=clc|static, or gemm_set_sched() at run time.
+int g_gemm_sched = [] {
+  const char* e = getenv("VESCALE_B200_GEMM_SCHED");
+  return (e && std::string(e) == "clc") ? 1 : 0;
+}();
+
 int gemm_smem_bytes(int stages) { return stages * (kABytes + kBBytes) + (2 * stages + 4) * 8 + 16 + 1024; }
 
 }  // namespace vb
+
+void gemm_set_sched(int64_t mode) { vb::g_gemm_sched = (int)mode; }
+int64_t gemm_get_sched() { return vb::g_gemm_sched; }
 
 void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate, int64_t variant_arg) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && c.is_cuda(), "gemm_nt: CUDA tensors required");
@@ -718,7 +783,7 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
     constexpr int STAGES2 = 6;
     const CUtensorMap& ta2 = cached_tmap_bf16(a.data_ptr(), M, K, a.stride(0), kBM);
     const CUtensorMap& tb2 = cached_tmap_bf16(b.data_ptr(), N, K, b.stride(0), kBN / 2);
-    const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+    const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 96 + 1024;
     const CUtensorMap& tc2 = cached_tmap_store_bf16(c.data_ptr(), M, N, c.stride(0));
     static bool attr2 = false;
     if (!attr2) {
@@ -731,8 +796,18 @@ void gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
       const char* e = getenv("VESCALE_B200_GEMM_GROUP_M");
       return e ? atoi(e) : 8;
     }();
-    gemm_nt_2cta_kernel<STAGES2, false, false><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
-        ta2, tb2, tc2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m, nullptr, 0);
+    if (vb::g_gemm_sched == 1) {
+      static bool attr2c = false;
+      if (!attr2c) {
+        C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        attr2c = true;
+      }
+      gemm_nt_2cta_kernel<STAGES2, false, false, true><<<tiles2 * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+          ta2, tb2, tc2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m, nullptr, 0);
+    } else {
+      gemm_nt_2cta_kernel<STAGES2, false, false><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+          ta2, tb2, tc2, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, group_m, nullptr, 0);
+    }
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return;
   }
@@ -762,7 +837,7 @@ void launch_2cta_major(const void* a, const void* b, at::Tensor& c, int64_t M, i
   const CUtensorMap ta = A_MN ? make_tmap_2d(a, K, M, lda * 2, 64, 64, 2, true) : make_tmap_2d(a, M, K, lda * 2, kBM, kBK, 2, true);
   const CUtensorMap tb = B_MN ? make_tmap_2d(b, K, N, ldb * 2, 64, 64, 2, true) : make_tmap_2d(b, N, K, ldb * 2, kBN / 2, kBK, 2, true);
   const CUtensorMap& tc = cached_tmap_store_bf16(c.data_ptr(), M, N, c.stride(0));
-  const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+  const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 96 + 1024;
   static bool attr = false;
   if (!attr) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -771,8 +846,18 @@ void launch_2cta_major(const void* a, const void* b, at::Tensor& c, int64_t M, i
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   const int tiles2 = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN);
   const int pairs = std::max(1, std::min(sms / 2, tiles2));
-  gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
-      ta, tb, tc, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, 8, nullptr, 0);
+  if (vb::g_gemm_sched == 1) {
+    static bool attrc = false;
+    if (!attrc) {
+      C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attrc = true;
+    }
+    gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN, true><<<tiles2 * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+        ta, tb, tc, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, 8, nullptr, 0);
+  } else {
+    gemm_nt_2cta_kernel<STAGES2, A_MN, B_MN><<<pairs * 2, kGemmThreads, smem2, at::cuda::getCurrentCUDAStream()>>>(
+        ta, tb, tc, (__nv_bfloat16*)c.data_ptr(), (int)M, (int)N, (int)K, (int)c.stride(0), accumulate ? 1 : 0, 8, nullptr, 0);
+  }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 }  // namespace
@@ -814,7 +899,7 @@ void grouped_gemm_nt(const at::Tensor& a, const at::Tensor& b, at::Tensor c, con
   const CUtensorMap ta = make_tmap_2d(a.data_ptr(), M, K, a.stride(0) * 2, kBM, kBK, 2, true);
   const CUtensorMap tb = make_tmap_2d(b.data_ptr(), b.size(0), K, b.stride(0) * 2, kBN / 2, kBK, 2, true);
   const CUtensorMap tcm = make_tmap_2d(c.data_ptr(), M, N, c.stride(0) * 2, 32, 64, 2, true);
-  const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 1024;
+  const int smem2 = STAGES2 * kStage2 + kEpiBytes + (2 * STAGES2 + 4) * 8 + 16 + 96 + 1024;
   C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_2cta_kernel<STAGES2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   const int tiles2 = (M / (2 * kBM)) * ((N + kBN - 1) / kBN);

@@ -150,13 +150,9 @@ __global__ void __launch_bounds__(512) reduce_scatter_fused_kernel(PeerPtrs grad
   }
   float ss = 0.f;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    uint4 v[WORLD];
-#pragma unroll
-    for (int pi = 0; pi < WORLD; ++pi) {
-      const int p = (rank + pi) % WORLD;
-      v[pi] = ld_stream(reinterpret_cast<const uint4*>(grads.p[p]) + shard_off_vec + i);
-    }
+  // requests in flight per thread: WORLD peers x U iterations (>= 8 x 16 B), see reduce_scatter_multimem_kernel
+  constexpr int U = WORLD >= 8 ? 1 : (WORLD >= 4 ? 2 : (WORLD >= 2 ? 4 : 8));
+  auto process = [&](size_t i, const uint4* v) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int pi = 0; pi < WORLD; ++pi) acc8(acc, v[pi]);
@@ -198,6 +194,28 @@ __global__ void __launch_bounds__(512) reduce_scatter_fused_kernel(PeerPtrs grad
       reinterpret_cast<float4*>(ad.v + e)[1] = *reinterpret_cast<float4*>(vv + 4);
       st8(ad.p_out + e, pack8(pm));
     }
+  };
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    uint4 v[U][WORLD];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int pi = 0; pi < WORLD; ++pi) {
+        const int p = (rank + pi) % WORLD;
+        v[u][pi] = ld_stream(reinterpret_cast<const uint4*>(grads.p[p]) + shard_off_vec + i + u * stride);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) process(i + u * stride, v[u]);
+  }
+  for (; i < nvec; i += stride) {
+    uint4 v[WORLD];
+#pragma unroll
+    for (int pi = 0; pi < WORLD; ++pi) {
+      const int p = (rank + pi) % WORLD;
+      v[pi] = ld_stream(reinterpret_cast<const uint4*>(grads.p[p]) + shard_off_vec + i);
+    }
+    process(i, v);
   }
   ss = block_sum<512>(ss, red);
   if (threadIdx.x == 0 && sumsq != nullptr) atomicAdd(sumsq, ss);
@@ -212,12 +230,10 @@ __global__ void __launch_bounds__(512) reduce_scatter_multimem_kernel(const void
   float ss = 0.f;
   const uint4* src = reinterpret_cast<const uint4*>(mc_base) + shard_off_vec;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    uint4 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(src + i)
-                 : "memory");
+  // A switch-reduced load has ~3 us of latency: with one 16 B request per thread the kernel moved ~180 GB/s on half the SMs
+  // (profiles/step_profile_n2_ce_r2.txt).  UNROLL requests in flight per thread let a quarter of the CTAs saturate the links.
+  constexpr int UNROLL = 8;
+  auto consume = [&](size_t i, const uint4& v) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     acc8(acc, v);
 #pragma unroll
@@ -228,6 +244,26 @@ __global__ void __launch_bounds__(512) reduce_scatter_multimem_kernel(const void
     float4* o = reinterpret_cast<float4*>(out + i * 8);
     o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  };
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + (UNROLL - 1) * stride < nvec; i += UNROLL * stride) {
+    uint4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                   : "l"(src + i + u * stride)
+                   : "memory");
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) consume(i + u * stride, v[u]);
+  }
+  for (; i < nvec; i += stride) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(src + i)
+                 : "memory");
+    consume(i, v);
   }
   ss = block_sum<512>(ss, red);
   if (threadIdx.x == 0 && sumsq != nullptr) atomicAdd(sumsq, ss);
@@ -331,7 +367,9 @@ void symm_reduce_scatter(std::vector<int64_t> grad_ptrs, at::Tensor out, c10::op
   const int world = grad_ptrs.size();
   c10::cuda::CUDAGuard guard(out.device());
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  const int grid = num_ctas > 0 ? (int)num_ctas : comm_grid(sms, 1, 2);
+  // 8 requests in flight per thread (see the kernels): 32 CTAs keep > 2 MB outstanding on the NVLS path, a third of the SMs on
+  // the P2P path — the reduce-scatter overlaps the next unit's backward GEMMs and every SM it holds slows them down
+  const int grid = num_ctas > 0 ? (int)num_ctas : (multicast_ptr != 0 ? 32 : comm_grid(sms, 1, 3));
   const size_t nvec = shard_elems / 8, off_vec = (size_t)rank * nvec;
   float* outp = out.data_ptr<float>();
   float* ssp = sumsq.has_value() ? sumsq->data_ptr<float>() : nullptr;

@@ -222,3 +222,33 @@ def test_sharded_philox_matches_cpu_specification():
                 assert torch.equal(local.cpu().reshape(-1), want.reshape(-1)), (world, pl, kind)
             else:
                 torch.testing.assert_close(local.cpu().reshape(-1), want.reshape(-1), rtol=1e-5, atol=1e-6)
+
+
+def test_gemm_clc_scheduler_matches_static_schedule():
+    """Cluster-launch-control tile scheduling (one cluster per tile, running clusters pull the rest) computes the same tiles with the
+    same math as the static persistent schedule: results must be bit-identical (NT / NN / TN, edge tiles)."""
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    ops = torch.ops.vescale_b200
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    try:
+        for M, N, K in ((512, 256, 64), (1000, 264, 192), (2048, 1536, 1024), (4096, 4096, 512)):
+            a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+            b = (torch.randn(N, K, device=dev, generator=g) * 0.5).bfloat16()
+            bt = b.t().contiguous()
+            outs = []
+            for sched in (0, 1):
+                ops.gemm_set_sched(sched)
+                c = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+                ops.gemm_nt(a, b, c, False, 2)
+                d = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+                ops.gemm_nn(a, bt, d)
+                outs.append((c, d))
+            torch.cuda.synchronize()
+            ref = a.float() @ b.float().t()
+            assert (outs[0][0].float() - ref).abs().max().item() <= 0.02 * ref.abs().max().item() + 0.05
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (M, N, K)
+    finally:
+        ops.gemm_set_sched(0)

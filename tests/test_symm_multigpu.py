@@ -430,3 +430,49 @@ def _reduce_scatter_nvls(rank, world):
 @pytest.mark.timeout(300)
 def test_symm_reduce_scatter_and_nvls_gemm_rs():
     run_distributed(_reduce_scatter_nvls, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+def _dtensor_fusion(rank, world):
+    """``redistribute(Shard -> Replicate) -> mm`` and ``mm(Partial) -> redistribute(-> Shard)`` issued as plain DTensor ops hit the
+    fused sm_100a kernels (dtensor/fusion.py) and match the unfused DTensor path."""
+    import os
+
+    from vescale_b200 import Shard, distribute_tensor, init_device_mesh
+    from vescale_b200.dtensor import fusion
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    dev = torch.device("cuda", rank)
+    mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("TP",))
+    g = torch.Generator(device=dev).manual_seed(0)
+    M, H, Fd = 512 * world, 1024, 512 * world
+    x = (torch.randn(M, H, device=dev, generator=g) * 0.5).bfloat16()
+    w1 = (torch.randn(Fd, H, device=dev, generator=g) * 0.05).bfloat16()
+    w2 = (torch.randn(H, Fd, device=dev, generator=g) * 0.05).bfloat16()
+    dist.broadcast(x, 0), dist.broadcast(w1, 0), dist.broadcast(w2, 0)
+    outs = {}
+    for mode in ("auto", "off"):
+        os.environ["VESCALE_B200_FUSE_TP"] = mode
+        dx = distribute_tensor(x, mesh, [Shard(0)], src_data_rank=None)
+        d1 = distribute_tensor(w1, mesh, [Shard(0)], src_data_rank=None)
+        d2 = distribute_tensor(w2, mesh, [Shard(1)], src_data_rank=None)
+        fusion.reset_stats()
+        h = torch.relu(dx @ d1.t())
+        with fusion.fuse_reshard(mesh, [Shard(0)]):
+            y = h @ d2.t()
+        y = y.redistribute(mesh, [Shard(0)])
+        torch.cuda.synchronize()
+        if mode == "auto":
+            assert fusion.stats["ag_gemm"] == 1 and fusion.stats["gemm_rs"] == 1, fusion.stats
+        else:
+            assert fusion.stats["ag_gemm"] == 0 and fusion.stats["gemm_rs"] == 0, fusion.stats
+        outs[mode] = y.full_tensor().float()
+    os.environ["VESCALE_B200_FUSE_TP"] = "auto"
+    ref = torch.relu(x.float() @ w1.float().t()).bfloat16().float() @ w2.float().t()
+    for mode, o in outs.items():
+        assert (o - ref).abs().max().item() < 0.03 * ref.abs().max().item() + 0.05, mode
+
+
+@pytest.mark.timeout(200)
+def test_dtensor_level_fusion_hits_fused_kernels():
+    run_distributed(_dtensor_fusion, min(torch.cuda.device_count(), 8), backend="nccl")

@@ -23,6 +23,7 @@ from .redistribute import redistribute_local_tensor
 from .sharding_prop import propagator
 
 aten = torch.ops.aten
+_MM = aten.mm.default
 
 __all__ = ["OpDispatcher", "dispatcher", "register_op_handler"]
 
@@ -114,6 +115,13 @@ class OpDispatcher:
         h = self._custom.get(op)
         if h is not None:
             return h(op, args, kwargs)
+        if op is _MM:
+            # redistribute(Shard -> Replicate) -> mm  and  mm(Partial) -> redistribute(-> Shard): one fused kernel (fusion.py)
+            from .fusion import mm_fusion_handler
+
+            r = mm_fusion_handler(self, op, args, kwargs)
+            if r is not NotImplemented:
+                return r
         mesh, schema, local_args, local_kwargs = self.unwrap(op, args, kwargs)
         out_sh = self.sharding_propagator.propagate(schema)
         for hook in self._hooks:

@@ -162,7 +162,12 @@ class DModule:
                     if kind == "input":
                         self.handles.append(mod.register_forward_pre_hook(self._make_pre(entry, mesh), with_kwargs=True))
                     else:
-                        self.handles.append(mod.register_forward_hook(self._make_post(entry, mesh)))
+                        hint = self._reshard_hint(entry, mesh)
+                        if hint is not None:
+                            # the output plan reshards this module's result: a row-parallel matmul inside may produce the target
+                            # layout directly (GEMM ⊕ reduce-scatter, dtensor/fusion.py) instead of Partial + reduce-scatter
+                            self.handles.append(mod.register_forward_pre_hook(self._make_hint_push(hint, mesh)))
+                        self.handles.append(mod.register_forward_hook(self._make_post(entry, mesh, pop_hint=hint is not None)))
 
     @staticmethod
     def _make_pre(entry, mesh):
@@ -213,13 +218,39 @@ class DModule:
         return pre
 
     @staticmethod
-    def _make_post(entry, mesh):
+    def _reshard_hint(entry, mesh):
+        """Placements of the (single / first) tensor output if the plan shards it, else None."""
+        if isinstance(entry, dict):
+            return None
+        pis = _as_pi_list(entry)
+        if not pis or pis[0] is None or pis[0].placements is None:
+            return None
+        pl = list(pis[0].placements)
+        return pl if any(isinstance(p, Shard) for p in pl) else None
+
+    @staticmethod
+    def _make_hint_push(placements, mesh):
+        from ...dtensor.fusion import push_hint
+
+        def push(mod, args):
+            # a Shard(1) target on a (B, S, H) output is a contiguous row shard of the token matrix only when B == 1
+            batch1 = all(a.shape[0] == 1 for a in args if isinstance(a, torch.Tensor) and a.ndim == 3)
+            push_hint(id(mod), mesh, placements, rows_contiguous=batch1)
+
+        return push
+
+    @staticmethod
+    def _make_post(entry, mesh, pop_hint: bool = False):
         """Output hook: a sequence plan over a tensor / tuple / list output, a dict plan (by key / field name) over a dict,
         dict-like (``ModelOutput``) or dataclass output (legacy ``dmodule/_hook.py:213-256``)."""
         is_dict = isinstance(entry, dict)
         pis = None if is_dict else _as_pi_list(entry)
 
         def post(mod, args, output):
+            if pop_hint:
+                from ...dtensor.fusion import pop_hint as _pop
+
+                _pop(id(mod))
             if is_dict:
                 if dataclasses.is_dataclass(output) and not isinstance(output, type) and not isinstance(output, dict):
                     vals = {f.name: getattr(output, f.name) for f in dataclasses.fields(output)}

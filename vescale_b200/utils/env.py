@@ -25,11 +25,14 @@ FLAGS: Dict[str, Tuple[str, str]] = {
     "VESCALE_B200_GEMM_VARIANT": ("2", "read by csrc/gemm_sm100.cu: 1 = 1-CTA tcgen05 kernel, 2 = CTA pairs (default), 3 = experimental 2x2 cluster with TMA multicast of B"),
     "VESCALE_B200_GEMM_GROUP_M": ("8", "read by csrc/gemm_sm100.cu: M-tiles per rasterisation group (L2 locality)"),
     "VESCALE_B200_AG_CTAS": ("0", "CTAs of the FSDP pull all-gather kernel (0 = a quarter of the SMs)"),
-    "VESCALE_B200_RS_CTAS": ("0", "CTAs of the fused reduce-scatter kernels (0 = half of the SMs)"),
+    "VESCALE_B200_RS_CTAS": ("0", "CTAs of the fused reduce-scatter kernels (0 = 32 on the NVLS path, a third of the SMs on the P2P path)"),
     "VESCALE_NDTIMELINE_LOG_LEVEL": ("INFO", "level of the ndtimeline logger (unknown names fall back to WARNING)"),
     "VESCALE_NDTIMELINE_SOCK_DIR": ("/tmp/ndtimeline", "directory of the default collector socket of the ndtimeline streamer"),
     "VESCALE_B200_MXFP8_NATIVE": ("0", "1 = MXFP8 GEMMs (ops.fp8.mxfp8_gemm_nt, fp8_linear(recipe='mx')) run on the tcgen05 block-scaled kernel csrc/gemm_mxfp8.cu instead of the emulation"),
     "VESCALE_B200_SYMM_RS": ("0", "1 = mesh_reduce_scatter (DTensor Partial -> Shard) uses the symmetric-memory reduce-scatter kernel (NVLS / P2P) instead of NCCL"),
+    "VESCALE_B200_FUSE_TP": ("auto", "DTensor-level fusion of redistribute -> mm / mm -> redistribute onto ag_gemm / gemm_rs (dtensor/fusion.py): auto = fused sm_100a kernels on CUDA, c10d = same pattern match on ordinary collectives (CPU tests, baseline), off = generic path"),
+    "VESCALE_B200_AG_IMPL": ("ce", "FSDP all-gather transport: ce = peer cudaMemcpyAsync on the copy engines (no SM), pull = SM pull kernel"),
+    "VESCALE_B200_GEMM_SCHED": ("static", "read by csrc/gemm_sm100.cu: static = persistent grid, tile += grid; clc = cluster launch control (one cluster per tile, running clusters pull the remaining tiles)"),
     "VESCALE_B200_GEMM_RS": ("staged", "FusedTP.gemm_rs implementation: staged = partial tiles pushed into the owner's staging slots by the GEMM epilogue; nvls = GEMM into a symmetric buffer + switch-reduced pull of the owner's rows"),
 }
 
