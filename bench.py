@@ -92,7 +92,54 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
+    def _start_nvml(self) -> bool:
+        """In-process NVML sampling (nvidia_ml_py): one nvmlInit, then three cheap queries per 200 ms sample.  Preferred over a
+        `nvidia-smi -lms` child process: nvidia-smi re-enumerates every GPU of the host for each sample and was the prime suspect
+        for the sporadic 150-550 ms stall of ONE step inside the device-timed region (it only ever appeared
+        while the sampler ran)."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {
+                "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+            }
+            self._stop = threading.Event()
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        r = int(reasons_fn(h))
+                        flags = ", ".join("Active" if r & bits[n] else "Not Active" for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                        self.lines.append((time.time(), f"{self.idx}, {sm}, {mx}, {pw:.2f}, {flags}"))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.2)
+
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+            self.nvml = True
+            return True
+        except Exception:
+            return False
+
     def start(self):
+        if os.environ.get("VESCALE_B200_CLOCK_SAMPLER", "nvml") == "nvml" and self._start_nvml():
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
@@ -114,13 +161,17 @@ class ClockSampler:
         self.t_end = time.time()
 
     def stop(self):
-        if self.proc is None:
+        if getattr(self, "nvml", False):
+            self._stop.set()
+            self.t.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         t0, t1 = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
@@ -143,6 +194,7 @@ class ClockSampler:
             "sm_max_mhz": max(mx) if mx else None,
             "power_w_max": max(pw) if pw else None,
             "samples": len(sm),
+            "sampler": "nvml (in-process, 200 ms)" if getattr(self, "nvml", False) else "nvidia-smi -lms 200",
             "reasons": sorted(reasons),
         }
 
@@ -300,6 +352,14 @@ def main():
         step_device(i)
     barrier()
     mem_gb = torch.cuda.max_memory_allocated() / 2**30 if cuda else 0.0
+    # A generation-2 garbage collection over the ~10^5 live Python objects of the model takes 150-250 ms of host time and showed up
+    # as one slow step in some runs (551 ms in a 400 ms series).  Training loops collect at a point of their
+    # choosing (Megatron's --manual-gc); here: collect now, freeze the survivors, and keep the collector off in the timed regions.
+    import gc
+
+    gc.collect()
+    gc.freeze()
+    gc.disable()
 
     # ---- timed region 1: device-timed
     sampler.mark_begin()
@@ -392,6 +452,7 @@ def main():
             "fuse_first_gemm": bool(args.fuse_first_gemm),
             "optimizer": ("AdamW fp32 master/m/v, global-norm clip 1.0" if args.max_grad_norm else "AdamW fp32 master/m/v, no clip") + (", fused into the reduce-scatter kernel" if fused_reduce else ""),
             "activation_memory": "selective recompute (norm and SwiGLU outputs recomputed)" if args.ac == "selective" else "full activation checkpointing per block",
+            "host_gc": "manual: gc.collect() + gc.freeze() after warm-up, automatic collection off during the timed regions",
             "l2_policy": "no explicit flush: per-step working set (>100 GB of weights/optimizer state/activations) is ~1000x the 126 MB L2",
         },
         "mfu_of_measured_cublas_sustained": tps / world * flops_tok / peak,

@@ -1,0 +1,92 @@
+"""Bring-up + timing of the hand-written tcgen05 flash-attention kernels (csrc/attention_sm100.cu) against SDPA.
+
+    timeout 200 python benchmarks/attn_check.py [--bwd]
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def ref_attention(qkv, hq, hk, d):
+    B, S, _ = qkv.shape
+    q = qkv[..., : hq * d].view(B, S, hq, d).transpose(1, 2).float()
+    k = qkv[..., hq * d : (hq + hk) * d].view(B, S, hk, d).transpose(1, 2).float()
+    v = qkv[..., (hq + hk) * d :].view(B, S, hk, d).transpose(1, 2).float()
+    o = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=hq != hk)
+    return o.transpose(1, 2).reshape(B, S, hq * d)
+
+
+def main():
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    ops = torch.ops.vescale_b200
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(0)
+    d = 128
+    out = {"numerics": [], "timing": []}
+    ok_all = True
+    for B, S, hq, hk in ((1, 128, 1, 1), (1, 256, 2, 1), (1, 512, 4, 2), (2, 1024, 8, 2), (1, 4096, 4, 1)):
+        qkv = (torch.randn(B, S, (hq + 2 * hk) * d, device=dev, generator=g) * 1.0).bfloat16()
+        o = torch.full((B, S, hq * d), float("nan"), device=dev, dtype=torch.bfloat16)
+        lse = torch.full((B, hq, S), float("nan"), device=dev, dtype=torch.float32)
+        ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d))
+        torch.cuda.synchronize()
+        ref = ref_attention(qkv, hq, hk, d)
+        err = (o.float() - ref).abs().max().item()
+        # reference lse
+        q = qkv[..., : hq * d].view(B, S, hq, d).transpose(1, 2).float()
+        k = qkv[..., hq * d : (hq + hk) * d].view(B, S, hk, d).transpose(1, 2).float().repeat_interleave(hq // hk, 1)
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+        sc = sc.masked_fill(torch.triu(torch.ones(S, S, device=dev, dtype=torch.bool), 1), float("-inf"))
+        lse_ref = torch.logsumexp(sc, -1)
+        lerr = (lse - lse_ref).abs().max().item()
+        ok = bool(torch.isfinite(o.float()).all()) and err < 0.02 and lerr < 0.02
+        ok_all &= ok
+        out["numerics"].append({"shape": [B, S, hq, hk], "max_abs_err": err, "lse_err": lerr, "ok": ok})
+        print(f"attn_fwd B{B} S{S} Hq{hq} Hkv{hk}: out err {err:.4f} lse err {lerr:.4f} {'ok' if ok else 'MISMATCH'}", flush=True)
+    if not ok_all:
+        print(json.dumps(out))
+        sys.exit(1)
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    for B, S, hq, hk in ((1, 8192, 32, 8), (2, 4096, 32, 8)):
+        qkv = torch.randn(B, S, (hq + 2 * hk) * d, device=dev, generator=g).bfloat16()
+        o = torch.empty(B, S, hq * d, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
+        fl = 4.0 * B * hq * S * S * d / 2  # causal
+        ms = timeit(lambda: ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d)))
+        q = qkv[..., : hq * d].view(B, S, hq, d).transpose(1, 2)
+        k = qkv[..., hq * d : (hq + hk) * d].view(B, S, hk, d).transpose(1, 2)
+        v = qkv[..., (hq + hk) * d :].view(B, S, hk, d).transpose(1, 2)
+        with sdpa_kernel([SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION], set_priority=True):
+            ms_c = timeit(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True))
+        row = {"shape": [B, S, hq, hk], "ours_fwd_ms": ms, "ours_fwd_tflops": fl / ms / 1e9, "cudnn_fwd_ms": ms_c, "cudnn_fwd_tflops": fl / ms_c / 1e9}
+        out["timing"].append(row)
+        print(json.dumps(row), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/attn_check.json", "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

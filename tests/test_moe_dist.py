@@ -1,5 +1,7 @@
 """Expert parallelism: EP=4 Mixtral-tiny must match the same model with all experts on one device
 (legacy ``test/parallel/ddp_optim/test_moe.py`` / ``test/model/mixtral`` strategy)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -92,3 +94,198 @@ def _realloc(rank, world):
 
 def test_dynamic_expert_reallocation():
     run_distributed(_realloc, 4)
+
+
+def _hijack_hf_mixtral(rank, world):
+    """``parallelize_experts`` on an UNMODIFIED HuggingFace ``MixtralSparseMoeBlock`` (legacy ``moe/_moe_tensor.py:42-99``): the
+    block keeps its class, router and signature; its expert container is swapped for the EP dispatch -> grouped GEMM -> combine
+    path.  Output and expert gradients equal the single-process block (each rank routes different tokens)."""
+    import copy
+
+    from common import device_type
+    from transformers import MixtralConfig
+    from transformers.models.mixtral import modeling_mixtral as mm
+
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.moe import is_experts_parallized, parallelize_experts
+
+    cfg = MixtralConfig(hidden_size=32, intermediate_size=64, num_local_experts=4, num_experts_per_tok=2, num_hidden_layers=1, num_attention_heads=4,
+                        num_key_value_heads=2, vocab_size=64)
+    torch.manual_seed(0)
+    blk = mm.MixtralSparseMoeBlock(cfg)
+    for p in blk.parameters():
+        torch.nn.init.normal_(p, 0, 0.1)
+    ref = copy.deepcopy(blk)
+    mesh = init_device_mesh(device_type(), (world,), mesh_dim_names=("EP",))
+    holder = torch.nn.ModuleDict({"moe": blk})
+    parallelize_experts(holder, r"moe", ep_mesh=mesh)
+    assert is_experts_parallized(holder) and type(holder["moe"]) is mm.MixtralSparseMoeBlock
+    per = 4 // world
+    lay = holder["moe"]._vb_moe_layer
+    assert lay.experts.w_gate_up.shape[0] == per and all(getattr(p, "_is_expert_param", False) for p in lay.experts.parameters())
+    x = torch.randn(2, 8, 32, generator=torch.Generator().manual_seed(10 + rank))
+    out = holder["moe"](x.clone())
+    want = ref(x.clone())
+    torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-5)
+    out.sum().backward()
+    want.sum().backward()
+    for mine, full in ((lay.experts.w_gate_up.grad, ref.experts.gate_up_proj.grad), (lay.experts.w_down.grad, ref.experts.down_proj.grad)):
+        g = full.clone()
+        dist.all_reduce(g)  # an expert's gradient sums the tokens every rank sent to it
+        torch.testing.assert_close(mine, g[rank * per : (rank + 1) * per], rtol=1e-4, atol=1e-5)
+
+
+class _OldStyleExpert(torch.nn.Module):
+    def __init__(self, h, f):
+        super().__init__()
+        self.w1, self.w2, self.w3 = torch.nn.Linear(h, f, bias=False), torch.nn.Linear(f, h, bias=False), torch.nn.Linear(h, f, bias=False)
+
+    def forward(self, x):
+        return self.w2(torch.nn.functional.silu(self.w1(x)) * self.w3(x))
+
+
+class _OldStyleBlock(torch.nn.Module):
+    """transformers-4.x ``MixtralSparseMoeBlock``: per-expert loop with ``index_add_`` in the block's forward."""
+
+    def __init__(self, h=16, f=32, e=4, k=2):
+        super().__init__()
+        self.top_k, self.num_experts = k, e
+        self.gate = torch.nn.Linear(h, e, bias=False)
+        self.experts = torch.nn.ModuleList([_OldStyleExpert(h, f) for _ in range(e)])
+
+    def forward(self, hidden_states):
+        b, s, h = hidden_states.shape
+        x = hidden_states.view(-1, h)
+        logits = self.gate(x)
+        w = torch.softmax(logits, dim=1, dtype=torch.float)
+        w, sel = torch.topk(w, self.top_k, dim=-1)
+        w = (w / w.sum(-1, keepdim=True)).to(x.dtype)
+        final = torch.zeros_like(x)
+        mask = torch.nn.functional.one_hot(sel, self.num_experts).permute(2, 1, 0)
+        for e in range(self.num_experts):
+            idx, top_x = torch.where(mask[e])
+            final.index_add_(0, top_x, self.experts[e](x[top_x]) * w[top_x, idx, None])
+        return final.view(b, s, h), logits
+
+
+def _hijack_modulelist(rank, world):
+    import copy
+
+    from common import device_type
+
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.moe import parallelize_experts
+
+    torch.manual_seed(1)
+    blk = _OldStyleBlock()
+    ref = copy.deepcopy(blk)
+    mesh = init_device_mesh(device_type(), (world,), mesh_dim_names=("EP",))
+    holder = torch.nn.ModuleDict({"block_sparse_moe": blk})
+    parallelize_experts(holder, r"block_sparse_moe", ep_mesh=mesh)
+    assert len(holder["block_sparse_moe"].experts) == 0  # remote experts' weights were released
+    x = torch.randn(2, 6, 16, generator=torch.Generator().manual_seed(20 + rank))
+    out, logits = holder["block_sparse_moe"](x.clone())
+    want, want_logits = ref(x.clone())
+    torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(logits, want_logits)
+
+
+def test_hijack_unmodified_hf_mixtral_block():
+    run_distributed(_hijack_hf_mixtral, 2)
+
+
+def test_hijack_modulelist_style_block():
+    run_distributed(_hijack_modulelist, 2)
+
+
+def _param_buffer(rank, world):
+    """``MoELayerParamBuffer`` on an EP=2 x DP=2 mesh: expert buffers sharded over DP (FSDP units sharing one state), gathered a
+    layer ahead, gradients reduce-scattered from the backward hook; ``refresh_buffer`` moves experts with master weights and
+    AdamW moments.  Golden = the same layers with un-sharded experts on the EP group only."""
+    import copy
+
+    from common import device_type
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.optim import FSDPAdamW
+    from vescale_b200.parallel.fsdp import MixedPrecisionPolicy
+    from vescale_b200.parallel.moe import MoEConfig, MoELayer, MoELayerParamBuffer
+
+    dev = device_type()
+    mesh = init_device_mesh(dev, (2, 2), mesh_dim_names=("DP", "EP"))
+    ep_group, dp = mesh.get_group("EP"), mesh.get_local_rank("DP")
+    cfg = MoEConfig(16, 32, 4, 2, dtype=torch.float32)
+    def build():
+        g = torch.Generator().manual_seed(3)
+        ls = torch.nn.ModuleList([MoELayer(cfg, ep_group, device=dev) for _ in range(2)])
+        for l in ls:
+            l.reset_parameters(g)
+        return ls
+
+    layers, golden = build(), build()
+    buf = MoELayerParamBuffer(layers, mesh, mesh_dim="DP", mp_policy=MixedPrecisionPolicy(param_dtype=torch.float32, reduce_dtype=torch.float32), prefetch=1)
+    assert len(buf.units) == 2 and buf.units[0]._state is buf.units[1]._state
+    assert all(u.S * 2 >= sum(p.numel() for p in gl.experts.parameters()) for u, gl in zip(buf.units, golden))
+
+    def run(ls, x):
+        h = x
+        for l in ls:
+            h = h + l(h)
+        return h.pow(2).mean()
+
+    x = torch.randn(12, 16, generator=torch.Generator().manual_seed(50 + rank)).to(dev)
+    loss = run(layers, x)
+    ref = run(golden, x)
+    torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-6)
+    loss.backward()
+    ref.backward()
+    buf.state.wait_grads()
+    for u, gl in zip(buf.units, golden):
+        flat = torch.cat([gl.experts.w_gate_up.grad.reshape(-1), gl.experts.w_down.grad.reshape(-1)])
+        dist.all_reduce(flat, group=mesh.get_group("DP"))
+        flat /= 2  # the reduce-scatter averages over the DP replicas
+        got = torch.zeros(u.S * 2)
+        mine = u.grad_shard.float() * getattr(u, "grad_scale_pending", 1.0)
+        for slot in u.layout.slots:
+            lo, hi = u.layout.rank_range(slot, u.rank)
+            if hi > lo:
+                got[u.rank * u.S + lo : u.rank * u.S + hi] = mine[lo:hi]
+        want = torch.zeros(u.S * 2)
+        off = 0
+        for slot, p in zip(u.layout.slots, (gl.experts.w_gate_up.grad, gl.experts.w_down.grad)):
+            want[slot.offset : slot.end] = flat[off : off + p.numel()]
+            off += p.numel()
+        sl = slice(u.rank * u.S, (u.rank + 1) * u.S)
+        if os.environ.get("DBG"):
+            print(rank, "got", got[sl][:4], got[sl].norm(), "want", want[sl][:4], want[sl].norm(), "ratio", (got[sl] / want[sl])[:6], flush=True)
+        torch.testing.assert_close(got[sl], want[sl], rtol=1e-4, atol=1e-6)
+    # ---- re-allocation: swap the homes of experts 0 and 3; forward is unchanged, moments travel with their expert
+    holder = torch.nn.Module()
+    holder.layers = layers
+    opt = FSDPAdamW(holder, lr=1e-2, max_grad_norm=None)  # finds the buffer's FSDP state through the expert units
+    u0 = buf.units[0]
+    El = 2
+    for slot in u0.layout.slots:  # tag the first moment of every element with the id of the expert it belongs to
+        lo, hi = u0.layout.rank_range(slot, u0.rank)
+        per = slot.end - slot.offset
+        per //= El
+        idx = torch.arange(u0.rank * u0.S + lo, u0.rank * u0.S + hi)
+        local_slot = (idx - slot.offset) // per
+        ep = mesh.get_local_rank("EP")
+        u0.exp_avg[lo:hi] = (ep * El + local_slot).float()
+    before = run(layers, x).detach()
+    buf.refresh_buffer(0, [3, 1, 2, 0], optimizer=opt)
+    after = run(layers, x).detach()
+    torch.testing.assert_close(after, before, rtol=1e-5, atol=1e-6)
+    ep = mesh.get_local_rank("EP")
+    owner = {0: 3, 1: 1, 2: 2, 3: 0}  # slot -> expert now living there
+    for slot in u0.layout.slots:
+        lo, hi = u0.layout.rank_range(slot, u0.rank)
+        per = (slot.end - slot.offset) // El
+        idx = torch.arange(u0.rank * u0.S + lo, u0.rank * u0.S + hi)
+        local_slot = (idx - slot.offset) // per
+        want = torch.tensor([float(owner[ep * El + int(s)]) for s in local_slot])
+        torch.testing.assert_close(u0.exp_avg[lo:hi].cpu(), want)
+
+
+def test_moe_layer_param_buffer():
+    run_distributed(_param_buffer, 4)

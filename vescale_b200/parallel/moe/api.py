@@ -70,8 +70,19 @@ def parallelize_experts(module: nn.Module, experts_expr: str = r".*moe.*", ep_me
     group = ep_mesh.get_group(0) if ep_mesh is not None and ep_mesh.has_groups() else None
     W = dist.get_world_size(group) if group is not None else 1
     rank = dist.get_rank(group) if group is not None else 0
+    from .hijack import hijack_moe_block, is_hijackable
+
     for fqn, sub in list(module.named_modules()):
-        if not rx.fullmatch(fqn) or not isinstance(sub, MoELayer) or sub.ep_size == W:
+        if not rx.fullmatch(fqn):
+            continue
+        if not isinstance(sub, MoELayer) and is_hijackable(sub) and not hasattr(sub, "_vb_moe_layer"):
+            # an unmodified third-party block (HF Mixtral style): its expert container is swapped for the EP path (hijack.py)
+            ex = sub.experts
+            E = ex.gate_up_proj.shape[0] if hasattr(ex, "gate_up_proj") else len(ex)
+            alloc = (experts_allocator or BasicExpertsAllocator(E, W)).allocate()
+            hijack_moe_block(sub, group, placement=alloc, top_k=(config or {}).get("top_k"), comm_backend=(config or {}).get("comm_backend", "nccl"))
+            continue
+        if not isinstance(sub, MoELayer) or sub.ep_size == W:
             continue
         cfg = sub.cfg
         alloc = (experts_allocator or BasicExpertsAllocator(cfg.num_experts, W)).allocate()
@@ -146,12 +157,9 @@ def balanced_allocation(load_per_expert, ep_size: int) -> List[int]:
     return slot
 
 
-@torch.no_grad()
-def reallocate_experts(layer: MoELayer, new_slot_of_expert, optimizer: Optional[torch.optim.Optimizer] = None) -> None:
-    """Move experts between EP ranks while training: weights *and* the optimizer state of every moved expert migrate to the
-    new owner, and the layer's routing table is updated (legacy ``MoELayerParamBuffer.refresh_buffer``,
-    ``_moe_param_buffer.py:183-337``).  ``new_slot_of_expert[e]`` is the global slot (rank * E/W + local index) expert ``e``
-    moves to; it must be a permutation of ``range(E)``.  One all-to-all per tensor; collective over the EP group."""
+def _expert_move_plan(layer: MoELayer, new_slot_of_expert):
+    """(new slot list, ``move(t)``): ``move`` permutes a ``[E_local, ...]`` tensor of per-slot data across the EP group in place
+    according to the re-allocation (one all-to-all)."""
     from ...comm.collectives import _p2p_all_to_all
 
     E, W, El, me, group = layer.cfg.num_experts, layer.ep_size, layer.num_local, layer.ep_rank, layer.ep_group
@@ -186,6 +194,16 @@ def reallocate_experts(layer: MoELayer, new_slot_of_expert, optimizer: Optional[
             for k, j in enumerate(sorted(recv[s])):
                 t[j].copy_(outs[s][k])
 
+    return new, move
+
+
+@torch.no_grad()
+def reallocate_experts(layer: MoELayer, new_slot_of_expert, optimizer: Optional[torch.optim.Optimizer] = None) -> None:
+    """Move experts between EP ranks while training: weights *and* the optimizer state of every moved expert migrate to the
+    new owner, and the layer's routing table is updated (legacy ``MoELayerParamBuffer.refresh_buffer``,
+    ``_moe_param_buffer.py:183-337``).  ``new_slot_of_expert[e]`` is the global slot (rank * E/W + local index) expert ``e``
+    moves to; it must be a permutation of ``range(E)``.  One all-to-all per tensor; collective over the EP group."""
+    new, move = _expert_move_plan(layer, new_slot_of_expert)
     for p in (layer.experts.w_gate_up, layer.experts.w_down):
         move(p.data)
         if optimizer is not None:

@@ -99,18 +99,72 @@ class GroupedExperts(nn.Module):
         self.w_down._is_expert_param = True
 
     def forward(self, x: torch.Tensor, rows_per_expert: List[int]) -> torch.Tensor:
-        outs = []
-        pos = 0
-        for e, n in enumerate(rows_per_expert):
+        if sum(rows_per_expert) == 0:
+            return x.new_zeros((0, self.cfg.hidden_size)) + 0.0 * (self.w_gate_up.sum() + self.w_down.sum())  # keep the graph connected
+        return _GroupedSwiGLUFFN.apply(x, self.w_gate_up, self.w_down, tuple(int(n) for n in rows_per_expert))
+
+
+class _GroupedSwiGLUFFN(torch.autograd.Function):
+    """All local experts' SwiGLU FFNs over rows grouped by expert, as ONE autograd node that saves the *stacked parameters
+    themselves* (not per-expert slices of them).  Under FSDP the parameters' storage is re-pointed at the freshly gathered unit
+    buffer before backward (``reshard_after_forward``); a slice view taken in forward would still alias the recycled buffer of
+    the forward pass, so backward re-slices the live parameter.  Weight gradients go straight into ``main_grad`` (a view of the
+    unit's flat gradient buffer) when the wrapper provides one; the gate|up activation is kept, its SwiGLU product recomputed."""
+
+    @staticmethod
+    def forward(ctx, x, w_gate_up, w_down, rows):
+        Fn = O.functional
+        outs, gus, pos = [], [], 0
+        for e, n in enumerate(rows):
             if n == 0:
                 continue
-            xe = x[pos : pos + n]
+            xe = x[pos : pos + n].contiguous()
             pos += n
-            gu = O.linear(xe, self.w_gate_up[e])
-            outs.append(O.functional.swiglu_linear(gu, self.w_down[e]))
-        if not outs:
-            return x.new_zeros((0, self.cfg.hidden_size))
+            gu = Fn.gemm_nt(xe, w_gate_up[e])
+            gus.append(gu)
+            outs.append(Fn.gemm_nt(Fn._swiglu_fwd(gu), w_down[e]))
+        ctx.save_for_backward(x, torch.cat(gus, 0), w_gate_up, w_down)
+        ctx.rows = rows
         return torch.cat(outs, 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        Fn = O.functional
+        x, gu_all, w_gate_up, w_down = ctx.saved_tensors
+        dy = dy.contiguous()
+        grads = []
+        for w in (w_gate_up, w_down):
+            mg = getattr(w, "main_grad", None)
+            if mg is not None:
+                if not getattr(w, "_main_grad_initialised", False):
+                    mg.zero_()  # experts that received no token keep a zero gradient
+                    w._main_grad_initialised = True
+                grads.append(mg)
+            else:
+                grads.append(torch.zeros_like(w))
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        pos = 0
+        for e, n in enumerate(ctx.rows):
+            if n == 0:
+                continue
+            sl = slice(pos, pos + n)
+            pos += n
+            ge, dye, xe = gu_all[sl], dy[sl], x[sl].contiguous()
+            act = Fn._swiglu_fwd(ge)
+            grads[1][e].add_(Fn.gemm_tn(dye, act).to(grads[1].dtype))
+            dact = Fn.gemm_nn(dye, w_down[e])
+            if Fn._use_kernels(dact) and dact.dtype == torch.bfloat16:
+                dgu = Fn._ext.ops().swiglu_bwd(dact, ge.contiguous())
+            else:
+                dgu = Fn._swiglu_bwd_ref(dact, ge)
+            grads[0][e].add_(Fn.gemm_tn(dgu, xe).to(grads[0].dtype))
+            if dx is not None:
+                dx[sl] = Fn.gemm_nn(dgu, w_gate_up[e])
+        for w in (w_gate_up, w_down):
+            hook = getattr(w, "_post_main_grad_hook", None)
+            if hook is not None and getattr(w, "main_grad", None) is not None:
+                hook(w)
+        return dx, (None if getattr(w_gate_up, "main_grad", None) is not None else grads[0]), (None if getattr(w_down, "main_grad", None) is not None else grads[1]), None
 
 
 class MoELayer(nn.Module):
@@ -155,15 +209,23 @@ class MoELayer(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
-        T, k, E, W, El = x2.shape[0], self.cfg.top_k, self.cfg.num_experts, self.ep_size, self.num_local
         topv, topi, probs = self.router(x2)
+        return self.experts_forward(x2, topv, topi, probs).view(shape)
+
+    def experts_forward(self, x2: torch.Tensor, topv: torch.Tensor, topi: torch.Tensor, probs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Everything after routing: dispatch the ``[T, H]`` token rows to the ranks hosting their ``top_k`` experts, run the
+        grouped expert FFN, combine with the gate weights.  Also the entry point of hijacked third-party MoE blocks, whose own
+        router produced ``topv`` / ``topi`` (``hijack.py``)."""
+        shape = x2.shape
+        T, k, E, W, El = x2.shape[0], topi.shape[-1], self.cfg.num_experts, self.ep_size, self.num_local
         slots = self.slot_of_expert[topi]  # where each chosen expert lives now
         if self.symm_dispatcher is not None and x2.is_cuda and W > 1:
             from .symm_dispatch import symm_moe_forward
 
             out = symm_moe_forward(x2.contiguous(), topv, slots, self.experts.w_gate_up, self.experts.w_down, self.symm_dispatcher)
             return out.view(shape)
-        if self.cfg.aux_loss_coef > 0:
+        x = x2
+        if self.cfg.aux_loss_coef > 0 and probs is not None:
             frac = torch.zeros(E, device=x.device).index_add_(0, topi.reshape(-1), torch.ones(T * k, device=x.device)) / (T * k)
             self.last_aux_loss = self.cfg.aux_loss_coef * E * (frac * probs.mean(0)).sum()
         flat_e = slots.reshape(-1)
