@@ -42,6 +42,7 @@ def parse():
     p.add_argument("--comm", default="auto", choices=["auto", "nccl", "symm"])
     p.add_argument("--gemm", default="auto", choices=["auto", "tcgen05", "cublas"])
     p.add_argument("--reshard", default="auto", choices=["auto", "yes", "no"])
+    p.add_argument("--attn", default="auto", choices=["auto", "tcgen05", "cudnn"], help="attention back end: hand-written tcgen05 flash attention, library SDPA (cuDNN), or the faster of the two")
     p.add_argument("--max-grad-norm", type=float, default=1.0)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--device", default="cuda", choices=["cuda", "cpu"], help="cpu = control-flow smoke test of this script on gloo (marks the record invalid)")
@@ -242,6 +243,7 @@ def main():
     if cuda:
         _ext.load(required=True)
     Fn.set_gemm_backend(args.gemm)
+    Fn.set_attention_backend(args.attn)
     cfg = getattr(LlamaConfig, args.model)()
     cfg.fp8 = args.fp8 or False
     if args.fp8 == "mx":
@@ -447,6 +449,7 @@ def main():
             "parallelism": f"fsdp{world}" if tp is None else f"fsdp{dp_size}xtp{tp_size}({type(tp).__name__})",
             "comm_backend": comm_name,
             "gemm_backend": args.gemm,
+            "attention_backend": args.attn,
             "reshard_after_forward": bool(reshard),
             "prefetch": args.prefetch,
             "fuse_first_gemm": bool(args.fuse_first_gemm),

@@ -55,6 +55,33 @@ def main():
         print(json.dumps(out))
         sys.exit(1)
 
+    # ---- backward: dqkv against autograd through the fp32 reference
+    for B, S, hq, hk in ((1, 128, 1, 1), (1, 256, 2, 1), (1, 512, 4, 2), (2, 1024, 8, 2)):
+        qkv = (torch.randn(B, S, (hq + 2 * hk) * d, device=dev, generator=g) * 1.0).bfloat16()
+        do = (torch.randn(B, S, hq * d, device=dev, generator=g) * 1.0).bfloat16()
+        o = torch.empty(B, S, hq * d, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
+        ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d))
+        dqkv = torch.full_like(qkv, float("nan"))
+        dvec = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
+        dq_acc = torch.empty(B, S, hq * d, device=dev, dtype=torch.float32)
+        ops.attn_bwd(qkv, o, do, lse, dqkv, dvec, dq_acc, hq, hk, 1.0 / math.sqrt(d))
+        torch.cuda.synchronize()
+        x = qkv.float().requires_grad_()
+        ref_attention(x, hq, hk, d).backward(do.float())
+        gref = x.grad
+        errs = {}
+        for name, lo, hi in (("dq", 0, hq * d), ("dk", hq * d, (hq + hk) * d), ("dv", (hq + hk) * d, (hq + 2 * hk) * d)):
+            a, r_ = dqkv[..., lo:hi].float(), gref[..., lo:hi]
+            errs[name] = ((a - r_).abs().max() / (r_.abs().max() + 1e-6)).item()
+        ok = bool(torch.isfinite(dqkv.float()).all()) and max(errs.values()) < 0.03
+        ok_all &= ok
+        out["numerics"].append({"bwd_shape": [B, S, hq, hk], **errs, "ok": ok})
+        print(f"attn_bwd B{B} S{S} Hq{hq} Hkv{hk}: rel err dq {errs['dq']:.4f} dk {errs['dk']:.4f} dv {errs['dv']:.4f} {'ok' if ok else 'MISMATCH'}", flush=True)
+    if not ok_all:
+        print(json.dumps(out))
+        sys.exit(1)
+
     def timeit(fn, n=10):
         for _ in range(3):
             fn()
@@ -80,7 +107,17 @@ def main():
         v = qkv[..., (hq + hk) * d :].view(B, S, hk, d).transpose(1, 2)
         with sdpa_kernel([SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION], set_priority=True):
             ms_c = timeit(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True))
-        row = {"shape": [B, S, hq, hk], "ours_fwd_ms": ms, "ours_fwd_tflops": fl / ms / 1e9, "cudnn_fwd_ms": ms_c, "cudnn_fwd_tflops": fl / ms_c / 1e9}
+        do = torch.randn(B, S, hq * d, device=dev, generator=g).bfloat16()
+        dqkv = torch.empty_like(qkv)
+        dvec = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
+        dq_acc = torch.empty(B, S, hq * d, device=dev, dtype=torch.float32)
+        ms_b = timeit(lambda: ops.attn_bwd(qkv, o, do, lse, dqkv, dvec, dq_acc, hq, hk, 1.0 / math.sqrt(d)))
+        qg, kg, vg = (t.detach().clone().requires_grad_() for t in (q, k, v))
+        with sdpa_kernel([SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION], set_priority=True):
+            oc = F.scaled_dot_product_attention(qg, kg, vg, is_causal=True, enable_gqa=True)
+            do4 = do.view(B, S, hq, d).transpose(1, 2)
+            ms_cb = timeit(lambda: torch.autograd.grad(oc, (qg, kg, vg), do4, retain_graph=True))
+        row = {"shape": [B, S, hq, hk], "ours_bwd_ms": ms_b, "ours_bwd_tflops": 2.5 * fl / ms_b / 1e9, "cudnn_bwd_ms": ms_cb, "cudnn_bwd_tflops": 2.5 * fl / ms_cb / 1e9, "ours_fwd_ms": ms, "ours_fwd_tflops": fl / ms / 1e9, "cudnn_fwd_ms": ms_c, "cudnn_fwd_tflops": fl / ms_c / 1e9}
         out["timing"].append(row)
         print(json.dumps(row), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

@@ -314,3 +314,386 @@ void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q
   attn_fwd_kernel<<<grid, kAThreads, kAttnFwdSmem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
+
+// =====================================================================================================================
+// Backward.  One CTA = one 128-key tile j of one KV head; it loops over the G query heads sharing that KV head and over the
+// query blocks i >= j (causal), accumulating dK_j and dV_j in TMEM and adding each dQ_i contribution to an fp32 accumulator in
+// global memory.  Everything is computed TRANSPOSED (keys on the TMEM lanes) so that the probabilities never leave tensor
+// memory on their way into the dV / dK products:
+//     S^T  = K_j Q_i^T                     (lanes = keys, columns = queries)      -> TMEM R0
+//     dP^T = V_j dO_i^T                                                            -> TMEM R1
+//     softmax threads (one per key row):  P^T = exp2(S^T * c - lse_i),  dS^T = P^T o (dP^T - D_i)
+//         P^T  (bf16) -> TMEM R0[0,64)    : A operand (from TMEM) of  dV_j += P^T dO_i
+//         dS^T (bf16) -> TMEM R1[64,128)  : A operand (from TMEM) of  dK_j += dS^T Q_i
+//         dS^T (bf16) -> shared memory     : MN-major A operand of     dQ_i  = dS K_j      -> TMEM columns [64,192) (dead halves of R0/R1)
+//     dQ_i tile: tcgen05.ld -> red.global.add.v4.f32 into dq_acc[B, S, Hq, 128]
+// Q_i and dO_i tiles are TMA-loaded into a two-deep ring (the same bytes serve as K-major A/B of the first two products and as
+// MN-major B of dV / dK), lse_i and D_i = rowsum(dO o O) ride along as 512-byte bulk copies.
+// Pre-pass: attn_bwd_prep_kernel (D, zero dq_acc).  Post-pass: attn_bwd_dq_kernel (dq_acc * scale -> bf16 into the packed dqkv).
+// =====================================================================================================================
+namespace {
+
+struct BwdBars {
+  uint64_t kv_full;
+  uint64_t q_full[2], q_empty[2];   // Q_i + lse_i + D_i (one stage) ; released when S^T and dK have consumed it
+  uint64_t do_full[2], do_empty[2];
+  uint64_t sp_full;                 // S^T and dP^T ready                 (MMA -> softmax)
+  uint64_t pds_full;                // P^T, dS^T (TMEM + smem) written     (softmax -> MMA), count 4
+  uint64_t dq_full;                 // dQ tile ready                        (MMA -> softmax)
+  uint64_t dq_free;                 // dQ tile drained, R0/R1 reusable      (softmax -> MMA), count 4
+  uint64_t acc_full;                // dK / dV complete                     (MMA -> epilogue)
+  uint32_t tmem_holder;
+  uint32_t pad;
+};
+
+constexpr uint32_t kR0 = 0, kR1 = 128, kRdV = 256, kRdK = 384, kRdQ = 64;
+constexpr int kBwdSmemTiles = 7;  // K, V, Q x2, dO x2, dS^T
+constexpr int kBwdVecBytes = 2 * 2 * 512;  // (lse, D) x 2 stages x 128 floats
+// no slack for manual alignment here (7 tiles + vectors + barriers = 226.1 KB): the dynamic shared memory window is declared
+// __align__(1024) and the kernel traps if the base is not 1024-byte aligned (128B-swizzled TMA boxes need it)
+constexpr int kAttnBwdSmem = kBwdSmemTiles * kATile + kBwdVecBytes + (int)sizeof(BwdBars);
+static_assert(kAttnBwdSmem <= 232448, "attn_bwd_kernel: shared memory over the 227 KB CTA limit");
+
+VB_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+VB_DEVICE void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// one 128-element bf16 row (row r of a [128 x 128] tile made of two [128 x 64] 128B-swizzled boxes), from 64 packed bf16x2 words
+VB_DEVICE void write_row_sw128(uint8_t* tile, int r, const uint32_t* pk /*64*/) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t base = smem_u32(tile + half * kAHalf) + r * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(base + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4), pk[half * 32 + 4 * j], pk[half * 32 + 4 * j + 1], pk[half * 32 + 4 * j + 2], pk[half * 32 + 4 * j + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(kAThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv,
+                const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dq_acc, int B, int S, int Hq, int Hkv, float scale_log2,
+                float scale) {
+  extern __shared__ __align__(1024) uint8_t smem_bwd[];
+  uint8_t* smem = smem_bwd;
+  if (smem_u32(smem) & 1023u) {
+    if (threadIdx.x == 0) printf("[vescale_b200] attn_bwd_kernel: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
+    __trap();
+  }
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kATile;
+  uint8_t* sQ = smem + 2 * kATile;   // 2 stages
+  uint8_t* sDO = smem + 4 * kATile;  // 2 stages
+  uint8_t* sDS = smem + 6 * kATile;
+  float* sVec = reinterpret_cast<float*>(smem + 7 * kATile);  // [stage][lse 128 | D 128]
+  BwdBars* bars = reinterpret_cast<BwdBars*>(smem + 7 * kATile + kBwdVecBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = Hq / Hkv, nq = S / kAQ;
+  int idx = blockIdx.x;
+  const int j = idx % nq;  // early key tiles first: they see the most query blocks
+  idx /= nq;
+  const int kvh = idx % Hkv, b = idx / Hkv;
+  const int n_i = nq - j;          // query blocks j .. nq-1
+  const int n_iter = G * n_i;      // iteration t -> (g = t / n_i, i = j + t % n_i)
+  const int krow = b * S + j * kAKV;
+  const int col_k = (Hq + kvh) * kAD, col_v = (Hq + Hkv + kvh) * kAD;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_do);
+    prefetch_tmap(&tm_dqkv);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bars->kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->q_full[s], 1);
+      mbar_init(&bars->q_empty[s], 1);
+      mbar_init(&bars->do_full[s], 1);
+      mbar_init(&bars->do_empty[s], 1);
+    }
+    mbar_init(&bars->sp_full, 1);
+    mbar_init(&bars->pds_full, 4);
+    mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dq_free, 4);
+    mbar_init(&bars->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(&bars->kv_full, 2 * kATile);
+      tma_load_2d(sK, &tm_qkv, &bars->kv_full, col_k, krow);
+      tma_load_2d(sK + kAHalf, &tm_qkv, &bars->kv_full, col_k + 64, krow);
+      tma_load_2d(sV, &tm_qkv, &bars->kv_full, col_v, krow);
+      tma_load_2d(sV + kAHalf, &tm_qkv, &bars->kv_full, col_v + 64, krow);
+      for (int t = 0; t < n_iter; ++t) {
+        const int s = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        const int g = t / n_i, i = j + t % n_i;
+        const int h = kvh * G + g;
+        const int qrow = b * S + i * kAQ;
+        const size_t vec_off = ((size_t)b * Hq + h) * S + (size_t)i * kAQ;
+        mbar_wait(&bars->q_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->q_full[s], kATile + 1024);
+        tma_load_2d(sQ + s * kATile, &tm_qkv, &bars->q_full[s], h * kAD, qrow);
+        tma_load_2d(sQ + s * kATile + kAHalf, &tm_qkv, &bars->q_full[s], h * kAD + 64, qrow);
+        bulk_load_1d(sVec + s * 256, lse + vec_off, 512, &bars->q_full[s]);
+        bulk_load_1d(sVec + s * 256 + 128, dvec + vec_off, 512, &bars->q_full[s]);
+        mbar_wait(&bars->do_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->do_full[s], kATile);
+        tma_load_2d(sDO + s * kATile, &tm_do, &bars->do_full[s], h * kAD, qrow);
+        tma_load_2d(sDO + s * kATile + kAHalf, &tm_do, &bars->do_full[s], h * kAD + 64, qrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_kk = make_idesc_bf16_major(128, 128, false, false);  // both K-major
+      constexpr uint32_t idesc_tb = make_idesc_bf16_major(128, 128, false, true);   // A from TMEM (K-major), B MN-major
+      constexpr uint32_t idesc_mm = make_idesc_bf16_major(128, 128, true, true);    // A and B MN-major
+      mbar_wait(&bars->kv_full, 0);
+      for (int t = 0; t < n_iter; ++t) {
+        const int s = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        uint8_t* q = sQ + s * kATile;
+        uint8_t* dO = sDO + s * kATile;
+        mbar_wait(&bars->q_full[s], ph);
+        mbar_wait(&bars->do_full[s], ph);
+        if (t >= 1) mbar_wait(&bars->dq_free, (t - 1) & 1);  // R0 / R1 (previous dQ tile) drained by the softmax warps
+        tc_fence_after();
+        // S^T = K_j Q_i^T -> R0 ; dP^T = V_j dO_i^T -> R1
+#pragma unroll
+        for (int k = 0; k < kAD / 16; ++k) {
+          const uint64_t a = make_sw128_desc(smem_u32(sK + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          const uint64_t bb = make_sw128_desc(smem_u32(q + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem + kR0, a, bb, idesc_kk, k ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < kAD / 16; ++k) {
+          const uint64_t a = make_sw128_desc(smem_u32(sV + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          const uint64_t bb = make_sw128_desc(smem_u32(dO + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem + kR1, a, bb, idesc_kk, k ? 1u : 0u);
+        }
+        umma_commit(&bars->sp_full);
+        mbar_wait(&bars->pds_full, t & 1);
+        tc_fence_after();
+        // dV_j += P^T dO_i : A = P^T (TMEM R0[0,64)), B = dO_i as MN-major [q rows x d]
+        const uint64_t do_mn = make_sw128_desc_mn_lbo(smem_u32(dO), kAHalf);
+        const uint64_t q_mn = make_sw128_desc_mn_lbo(smem_u32(q), kAHalf);
+        const uint64_t k_mn = make_sw128_desc_mn_lbo(smem_u32(sK), kAHalf);
+        const uint64_t ds_mn = make_sw128_desc_mn_lbo(smem_u32(sDS), kAHalf);
+#pragma unroll
+        for (int k = 0; k < kAQ / 16; ++k) umma_bf16_ts(tmem + kRdV, tmem + kR0 + k * 8, do_mn + (uint64_t)(k * 128), idesc_tb, (t | k) ? 1u : 0u);
+        umma_commit(&bars->do_empty[s]);
+        // dK_j += dS^T Q_i : A = dS^T (TMEM R1[64,128)), B = Q_i as MN-major
+#pragma unroll
+        for (int k = 0; k < kAQ / 16; ++k) umma_bf16_ts(tmem + kRdK, tmem + kR1 + 64 + k * 8, q_mn + (uint64_t)(k * 128), idesc_tb, (t | k) ? 1u : 0u);
+        umma_commit(&bars->q_empty[s]);
+        // dQ_i = dS K_j : A = dS^T in smem read MN-major ([key rows x query cols] -> A[q][key]), B = K_j MN-major
+#pragma unroll
+        for (int k = 0; k < kAKV / 16; ++k) umma_bf16(tmem + kRdQ, ds_mn + (uint64_t)(k * 128), k_mn + (uint64_t)(k * 128), idesc_mm, k ? 1u : 0u);
+        umma_commit(&bars->dq_full);
+      }
+      umma_commit(&bars->acc_full);
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax / dS / dQ drain: one thread per key row =====================
+    const int qd = warp - 4;
+    const int row = qd * 32 + lane;  // key index inside the tile
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const float log2e = 1.4426950408889634f;
+    for (int t = 0; t < n_iter; ++t) {
+      const int s = t & 1;
+      const int g = t / n_i, i = j + t % n_i;
+      const int h = kvh * G + g;
+      const bool diag = i == j;
+      const float* vl = sVec + s * 256;
+      const float* vd = vl + 128;
+      mbar_wait(&bars->sp_full, t & 1);
+      tc_fence_after();
+      uint32_t pp[64];  // P^T row, packed bf16x2 (query 2c, 2c+1 in word c)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_base + kR0 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const int q0 = c * 32 + 2 * w;
+          float p0 = exp2f(__uint_as_float(r[2 * w]) * scale_log2 - vl[q0] * log2e);
+          float p1 = exp2f(__uint_as_float(r[2 * w + 1]) * scale_log2 - vl[q0 + 1] * log2e);
+          if (diag) {  // causal inside the diagonal block: key `row` is visible to query q iff row <= q
+            if (row > q0) p0 = 0.f;
+            if (row > q0 + 1) p1 = 0.f;
+          }
+          pp[c * 16 + w] = pack_bf16x2(p0, p1);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st_32x32_x16(tmem + lane_base + kR0 + c * 16, pp + c * 16);
+      uint32_t ds[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_base + kR1 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const int q0 = c * 32 + 2 * w;
+          const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pp[c * 16 + w]);
+          const float d0 = __bfloat162float(pb.x) * (__uint_as_float(r[2 * w]) - vd[q0]);
+          const float d1 = __bfloat162float(pb.y) * (__uint_as_float(r[2 * w + 1]) - vd[q0 + 1]);
+          ds[c * 16 + w] = pack_bf16x2(d0, d1);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st_32x32_x16(tmem + lane_base + kR1 + 64 + c * 16, ds + c * 16);
+      write_row_sw128(sDS, row, ds);
+      tmem_st_wait();
+      fence_proxy_async();  // the dS^T tile in shared memory is read by the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->pds_full);
+      // ---- drain dQ_i (lanes = queries of block i, columns = head dim) into the fp32 accumulator
+      mbar_wait(&bars->dq_full, t & 1);
+      tc_fence_after();
+      float* dst = dq_acc + (((size_t)(b * S + i * kAQ + row)) * Hq + h) * kAD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_base + kRdQ + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+          red_add_v4(dst + c * 32 + 4 * w, __uint_as_float(r[4 * w]), __uint_as_float(r[4 * w + 1]), __uint_as_float(r[4 * w + 2]), __uint_as_float(r[4 * w + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->dq_free);
+    }
+    // ---- epilogue: dK_j * scale and dV_j -> bf16 -> packed dqkv (the Q / dO rings are dead: reuse sQ as staging)
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t reg = which == 0 ? kRdK : kRdV;
+      const float mul = which == 0 ? scale : 1.f;
+      const int col = which == 0 ? col_k : col_v;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float v[64];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem + lane_base + reg + c * 64 + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) v[cc * 32 + x] = __uint_as_float(r[x]) * mul;
+        }
+        uint8_t* buf = sQ + (qd * 2 + (c & 1)) * 4096;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        epi_write_row_swizzled(buf, lane, v);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_dqkv, buf, col + c * 64, krow + qd * 32);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// D[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d] (fp32) ; dq_acc zeroed.  One warp per (b, s, h) row of 128 elements.
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, float* __restrict__ dvec,
+                                                            float* __restrict__ dq_acc, int B, int S, int Hq) {
+  const int64_t nrow = (int64_t)B * S * Hq;
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrow; r += (int64_t)gridDim.x * 8) {
+    const uint2 a = *reinterpret_cast<const uint2*>(o + r * kAD + lane * 4);
+    const uint2 c = *reinterpret_cast<const uint2*>(dO + r * kAD + lane * 4);
+    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* ch = reinterpret_cast<const __nv_bfloat162*>(&c);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float2 x = __bfloat1622float2(ah[k]), y = __bfloat1622float2(ch[k]);
+      sum += x.x * y.x + x.y * y.y;
+    }
+    sum = warp_sum(sum);
+    const int64_t bs = r / Hq;
+    const int h = (int)(r - bs * Hq);
+    const int64_t bb = bs / S, ss = bs - bb * S;
+    if (lane == 0) dvec[(bb * Hq + h) * S + ss] = sum;
+    *reinterpret_cast<float4*>(dq_acc + r * kAD + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// dq_acc [B*S, Hq*128] fp32 * scale -> bf16 into the first Hq*128 columns of dqkv [B*S, C]
+__global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, int64_t rows, int qcols, int C, float scale) {
+  const int64_t n8 = rows * (qcols / 8);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / (qcols / 8);
+    const int c8 = (int)(e - r * (qcols / 8));
+    const float4 a = *reinterpret_cast<const float4*>(dq_acc + r * qcols + c8 * 8);
+    const float4 b = *reinterpret_cast<const float4*>(dq_acc + r * qcols + c8 * 8 + 4);
+    float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+    st8(dqkv + r * C + c8 * 8, pack8(f));
+  }
+}
+
+}  // namespace
+
+// qkv, out, dout as in attn_fwd; lse [B, Hq, S]; dqkv [B, S, C] bf16 (fully written); scratch: dvec [B, Hq, S] fp32, dq_acc [B, S, Hq*128] fp32
+void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse, at::Tensor dqkv, at::Tensor dvec, at::Tensor dq_acc,
+              int64_t n_q, int64_t n_kv, double softmax_scale) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == at::kBFloat16 && qkv.dim() == 3 && qkv.is_contiguous());
+  const int64_t B = qkv.size(0), S = qkv.size(1), C = qkv.size(2);
+  TORCH_CHECK(C == (n_q + 2 * n_kv) * kAD && S % kAQ == 0 && n_q % n_kv == 0);
+  TORCH_CHECK(out.is_contiguous() && dout.is_contiguous() && out.scalar_type() == at::kBFloat16 && dout.scalar_type() == at::kBFloat16 && out.numel() == B * S * n_q * kAD &&
+              dout.numel() == out.numel());
+  TORCH_CHECK(dqkv.is_contiguous() && dqkv.scalar_type() == at::kBFloat16 && dqkv.numel() == qkv.numel());
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == B * n_q * S && dvec.scalar_type() == at::kFloat && dvec.numel() == lse.numel() &&
+              dq_acc.scalar_type() == at::kFloat && dq_acc.is_contiguous() && dq_acc.numel() == B * S * n_q * kAD);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  attn_bwd_prep_kernel<<<sms * 8, 256, 0, stream>>>((const __nv_bfloat16*)out.data_ptr(), (const __nv_bfloat16*)dout.data_ptr(), dvec.data_ptr<float>(),
+                                                    dq_acc.data_ptr<float>(), (int)B, (int)S, (int)n_q);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  const CUtensorMap tq = make_tmap_2d(qkv.data_ptr(), B * S, C, C * 2, 128, 64, 2, true);
+  const CUtensorMap tdo = make_tmap_2d(dout.data_ptr(), B * S, n_q * kAD, n_q * kAD * 2, 128, 64, 2, true);
+  const CUtensorMap tdqkv = make_tmap_2d(dqkv.data_ptr(), B * S, C, C * 2, 32, 64, 2, true);
+  static bool attr = false;
+  if (!attr) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
+    attr = true;
+  }
+  const int grid = (int)(B * n_kv * (S / kAQ));
+  attn_bwd_kernel<<<grid, kAThreads, kAttnBwdSmem, stream>>>(tq, tdo, tdqkv, lse.data_ptr<float>(), dvec.data_ptr<float>(), dq_acc.data_ptr<float>(), (int)B, (int)S,
+                                                            (int)n_q, (int)n_kv, (float)(softmax_scale * 1.4426950408889634), (float)softmax_scale);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  attn_bwd_dq_kernel<<<sms * 4, 256, 0, stream>>>(dq_acc.data_ptr<float>(), (__nv_bfloat16*)dqkv.data_ptr(), B * S, (int)(n_q * kAD), (int)C, (float)softmax_scale);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}

@@ -307,3 +307,34 @@ def test_op_sweep_part1():
 
 def test_autograd_and_2d_mesh():
     run_distributed(_grads_and_2d, 4)
+
+
+def _conv_rules(rank, world):
+    """Convolution rules (legacy ``ops/conv_ops.py``): batch-parallel and output-channel-parallel conv2d keep their shards,
+    weight gradients of the batch-parallel form are Partial, everything matches single-device forward and backward."""
+    from vescale_b200 import Replicate, Shard, distribute_tensor, init_device_mesh
+
+    mesh = init_device_mesh(device_type(), (world,))
+    g = torch.Generator().manual_seed(0)
+    x, w, b = torch.randn(8, 3, 10, 10, generator=g).to(device_type()), torch.randn(2 * world, 3, 3, 3, generator=g).to(device_type()), torch.randn(2 * world, generator=g).to(device_type())
+    xr, wr, br = (t.clone().requires_grad_() for t in (x, w, b))
+    yr = F.conv2d(xr, wr, br, stride=1, padding=1)
+    yr.square().sum().backward()
+    for px, pw, want in (([Shard(0)], [Replicate()], Shard(0)), ([Replicate()], [Shard(0)], Shard(1)), ([Replicate()], [Replicate()], Replicate()), ([Shard(2)], [Replicate()], None)):
+        dx = distribute_tensor(x, mesh, px, src_data_rank=None).requires_grad_()
+        dw = distribute_tensor(w, mesh, pw, src_data_rank=None).requires_grad_()
+        db = distribute_tensor(b, mesh, pw, src_data_rank=None).requires_grad_()
+        y = F.conv2d(dx, dw, db, stride=1, padding=1)
+        if want is not None:
+            assert y.placements == (want,), (px, pw, y.placements)
+        torch.testing.assert_close(y.full_tensor(), yr.detach(), rtol=1e-4, atol=1e-5)
+        y.square().sum().redistribute(mesh, [Replicate()]).backward()
+        torch.testing.assert_close(dx.grad.full_tensor(), xr.grad, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(dw.grad.full_tensor(), wr.grad, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(db.grad.full_tensor(), br.grad, rtol=1e-4, atol=1e-4)
+        if px == [Shard(0)]:
+            assert dw.grad.placements[0].is_partial(), dw.grad.placements
+
+
+def test_conv_rules():
+    run_distributed(_conv_rules, 2)

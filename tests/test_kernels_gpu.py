@@ -252,3 +252,37 @@ def test_gemm_clc_scheduler_matches_static_schedule():
             assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (M, N, K)
     finally:
         ops.gemm_set_sched(0)
+
+
+@pytest.mark.parametrize("B,S,hq,hk", [(1, 256, 2, 1), (2, 512, 4, 2), (1, 1024, 8, 2)])
+def test_native_flash_attention_matches_fp32_reference(B, S, hq, hk):
+    """Hand-written tcgen05 causal GQA flash attention (csrc/attention_sm100.cu), forward and backward through the packed-qkv
+    autograd op, against plain fp32 attention."""
+    import math
+
+    from vescale_b200.ops import _ext
+    from vescale_b200.ops import functional as Fn
+
+    _ext.load(required=True)
+    dev = torch.device("cuda")
+    d = 128
+    g = torch.Generator(device=dev).manual_seed(S + hq)
+    qkv = torch.randn(B, S, (hq + 2 * hk) * d, device=dev, generator=g).bfloat16().requires_grad_()
+    do = torch.randn(B, S, hq * d, device=dev, generator=g).bfloat16()
+    Fn.set_attention_backend("tcgen05")
+    try:
+        out = Fn.packed_attention(qkv, hq, hk, d, causal=True)
+        out.backward(do)
+    finally:
+        Fn.set_attention_backend("auto")
+    x = qkv.detach().float().requires_grad_()
+    q = x[..., : hq * d].view(B, S, hq, d).transpose(1, 2)
+    k = x[..., hq * d : (hq + hk) * d].view(B, S, hk, d).transpose(1, 2).repeat_interleave(hq // hk, 1)
+    v = x[..., (hq + hk) * d :].view(B, S, hk, d).transpose(1, 2).repeat_interleave(hq // hk, 1)
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+    sc = sc.masked_fill(torch.triu(torch.ones(S, S, device=dev, dtype=torch.bool), 1), float("-inf"))
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B, S, hq * d)
+    ref.backward(do.float())
+    assert (out.float() - ref).abs().max().item() < 0.03
+    rel = ((qkv.grad.float() - x.grad).abs().max() / x.grad.abs().max()).item()
+    assert rel < 0.03, rel

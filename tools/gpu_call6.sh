@@ -1,0 +1,7 @@
+#!/usr/bin/env bash
+set -uo pipefail
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+step() { local name="$1" t="$2"; shift 2; echo "== $name"; local t0=$SECONDS; timeout "$t" "$@" > "gpurun_out/c6_$name.log" 2>&1; echo "   rc=$? ($((SECONDS-t0))s)"; tail -14 "gpurun_out/c6_$name.log" | cut -c1-500; }
+step attn 150 python benchmarks/attn_check.py
+step bench_n1 300 python bench.py --gpus 1 --steps 6 --warmup 3 --no-e2e

@@ -23,6 +23,7 @@ __all__ = [
     "rope_qk_",
     "attention",
     "packed_attention",
+    "set_attention_backend",
     "cross_entropy",
     "set_gemm_backend",
 ]
@@ -446,8 +447,94 @@ class _PackedAttention(torch.autograd.Function):
         return dqkv, None, None, None, None
 
 
+# attention back end: "cudnn" = library SDPA (cuDNN's Blackwell kernels), "tcgen05" = the hand-written sm_100a kernels of
+# csrc/attention_sm100.cu (forward + backward, head dim 128, causal, S % 128 == 0), "auto" = whichever is faster for the shape
+# (timed once, like the GEMM back ends).  VESCALE_B200_ATTN / set_attention_backend().
+_ATTN = {"backend": None}
+_ATTN_TUNE: dict = {}
+
+
+def set_attention_backend(name: str) -> None:
+    assert name in ("auto", "cudnn", "tcgen05")
+    _ATTN["backend"] = name
+
+
+def _attn_backend() -> str:
+    if _ATTN["backend"] is None:
+        import os
+
+        _ATTN["backend"] = os.environ.get("VESCALE_B200_ATTN", "auto")
+    return _ATTN["backend"]
+
+
+def _native_attn_ok(qkv: torch.Tensor, n_q: int, n_kv: int, head_dim: int, causal: bool) -> bool:
+    return (causal and head_dim == 128 and qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.dim() == 3 and qkv.shape[1] % 128 == 0 and n_q % n_kv == 0
+            and _ext.available() and hasattr(_ext.ops(), "attn_bwd"))
+
+
+class _NativeAttention(torch.autograd.Function):
+    """Causal GQA flash attention on the hand-written tcgen05 kernels, straight from / to the packed qkv activation: the forward
+    keeps only the output and the per-row log-sum-exp, the backward writes dq | dk | dv into one packed gradient."""
+
+    @staticmethod
+    def forward(ctx, qkv, n_q, n_kv, head_dim):
+        B, S, _ = qkv.shape
+        qkv = qkv.contiguous()
+        out = torch.empty(B, S, n_q * head_dim, dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty(B, n_q, S, dtype=torch.float32, device=qkv.device)
+        _ext.count_launch("attn_fwd")
+        _ext.ops().attn_fwd(qkv, out, lse, n_q, n_kv, 1.0 / math.sqrt(head_dim))
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (n_q, n_kv, head_dim)
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, out, lse = ctx.saved_tensors
+        n_q, n_kv, head_dim = ctx.cfg
+        B, S, _ = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        dvec = torch.empty_like(lse)
+        dq_acc = torch.empty(B, S, n_q * head_dim, dtype=torch.float32, device=qkv.device)
+        _ext.count_launch("attn_bwd")
+        _ext.ops().attn_bwd(qkv, out, do.contiguous(), lse, dqkv, dvec, dq_acc, n_q, n_kv, 1.0 / math.sqrt(head_dim))
+        return dqkv, None, None, None
+
+
+def _attn_pick_native(qkv, n_q, n_kv, head_dim) -> bool:
+    """auto: time forward + backward of both back ends once per (B, S, Hq, Hkv) and keep the faster."""
+    key = (tuple(qkv.shape), n_q, n_kv)
+    hit = _ATTN_TUNE.get(key)
+    if hit is not None:
+        return hit
+    if torch.cuda.is_current_stream_capturing():
+        return False
+
+    def t(fn):
+        src = qkv.detach().clone().requires_grad_(True)
+        for _ in range(2):
+            fn(src).sum().backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn(src).sum().backward()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    with torch.enable_grad():
+        ours = t(lambda x: _NativeAttention.apply(x, n_q, n_kv, head_dim))
+        lib = t(lambda x: _PackedAttention.apply(x, n_q, n_kv, head_dim, True))
+    _ATTN_TUNE[key] = ours <= lib
+    return _ATTN_TUNE[key]
+
+
 def packed_attention(qkv: torch.Tensor, n_q: int, n_kv: int, head_dim: int, causal: bool = True) -> torch.Tensor:
     """qkv [B, S, (Hq+2Hk)*D] (RoPE already applied) -> attention output [B, S, Hq*D]."""
+    be = _attn_backend()
+    if be != "cudnn" and _native_attn_ok(qkv, n_q, n_kv, head_dim, causal):
+        if be == "tcgen05" or _attn_pick_native(qkv, n_q, n_kv, head_dim):
+            return _NativeAttention.apply(qkv, n_q, n_kv, head_dim)
     return _PackedAttention.apply(qkv, n_q, n_kv, head_dim, causal)
 
 

@@ -33,6 +33,8 @@ FLAGS: Dict[str, Tuple[str, str]] = {
     "VESCALE_B200_FUSE_TP": ("auto", "DTensor-level fusion of redistribute -> mm / mm -> redistribute onto ag_gemm / gemm_rs (dtensor/fusion.py): auto = fused sm_100a kernels on CUDA, c10d = same pattern match on ordinary collectives (CPU tests, baseline), off = generic path"),
     "VESCALE_B200_AG_IMPL": ("ce", "FSDP all-gather transport: ce = peer cudaMemcpyAsync on the copy engines (no SM), pull = SM pull kernel"),
     "VESCALE_B200_GEMM_SCHED": ("static", "read by csrc/gemm_sm100.cu: static = persistent grid, tile += grid; clc = cluster launch control (one cluster per tile, running clusters pull the remaining tiles)"),
+    "VESCALE_B200_ATTN": ("auto", "attention back end of ops.packed_attention: tcgen05 = hand-written sm_100a flash attention (csrc/attention_sm100.cu), cudnn = library SDPA, auto = faster of the two per shape"),
+    "VESCALE_B200_CLOCK_SAMPLER": ("nvml", "bench.py clock / throttle sampler: nvml = in-process NVML thread, smi = nvidia-smi -lms child process"),
     "VESCALE_B200_GEMM_RS": ("staged", "FusedTP.gemm_rs implementation: staged = partial tiles pushed into the owner's staging slots by the GEMM epilogue; nvls = GEMM into a symmetric buffer + switch-reduced pull of the owner's rows"),
 }
 
