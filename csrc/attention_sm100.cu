@@ -288,13 +288,255 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward, variant 2: EIGHT softmax warps.  Warps w and w+4 share a TMEM lane quadrant and split every row's columns in halves
+// (S columns / head-dim columns [64 hf, 64 hf + 64)), so the per-row exp2 / convert / accumulate work — the forward's bottleneck
+// on Blackwell (16 ex2 per clock per SM against 8192 tensor FLOP per clock) — is spread over 256 threads and each thread keeps
+// only 64 output accumulators.  The row maximum is agreed on through shared memory (one 64-thread named barrier per quadrant
+// per tile).  P gets its own TMEM columns (no aliasing with S, which the partner thread may still be reading):
+//     S0 [0,128) S1 [128,256) | P0 [256,320) P1 [320,384) | O_tile [384,512)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kA2Threads = 384;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 spare, w4-11 softmax (quadrant = w % 4, half = (w - 4) / 4)
+constexpr uint32_t k2ColP = 256, k2ColOT = 384;
+
+struct Attn2Bars {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], p_full[2], s_free[2], ot_full, ot_free;
+  uint32_t tmem_holder;
+  uint32_t pad;
+  float xmax[2][2][128];  // [tile parity][half][row]
+  float xsum[2][128];
+};
+
+VB_DEVICE void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o, float* __restrict__ lse, int B, int S, int Hq, int Hkv,
+                 float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kATile;
+  uint8_t* sV = smem + 3 * kATile;
+  Attn2Bars* bars = reinterpret_cast<Attn2Bars*>(smem + 5 * kATile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = Hq / Hkv, nq = S / kAQ;
+  int idx = blockIdx.x;
+  const int g = idx % G;
+  idx /= G;
+  const int qblk = nq - 1 - idx % nq;
+  idx /= nq;
+  const int kvh = idx % Hkv, b = idx / Hkv;
+  const int h = kvh * G + g;
+  const int n_tiles = qblk + 1;
+  const int row0 = b * S + qblk * kAQ;
+  const int col_q = h * kAD, col_k = (Hq + kvh) * kAD, col_v = (Hq + Hkv + kvh) * kAD;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_o);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->k_full[s], 1);
+      mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->v_full[s], 1);
+      mbar_init(&bars->v_empty[s], 1);
+      mbar_init(&bars->s_full[s], 1);
+      mbar_init(&bars->p_full[s], 8);
+      mbar_init(&bars->s_free[s], 1);
+    }
+    mbar_init(&bars->ot_full, 1);
+    mbar_init(&bars->ot_free, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars->q_full, kATile);
+      tma_load_2d(sQ, &tm_qkv, &bars->q_full, col_q, row0);
+      tma_load_2d(sQ + kAHalf, &tm_qkv, &bars->q_full, col_q + 64, row0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int krow = b * S + j * kAKV;
+        mbar_wait(&bars->k_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->k_full[s], kATile);
+        tma_load_2d(sK + s * kATile, &tm_qkv, &bars->k_full[s], col_k, krow);
+        tma_load_2d(sK + s * kATile + kAHalf, &tm_qkv, &bars->k_full[s], col_k + 64, krow);
+        mbar_wait(&bars->v_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->v_full[s], kATile);
+        tma_load_2d(sV + s * kATile, &tm_qkv, &bars->v_full[s], col_v, krow);
+        tma_load_2d(sV + s * kATile + kAHalf, &tm_qkv, &bars->v_full[s], col_v + 64, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_major(kAQ, kAKV, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16_major(kAQ, kAD, false, true);
+      mbar_wait(&bars->q_full, 0);
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&bars->k_full[s], (j >> 1) & 1);
+        if (j >= 2) mbar_wait(&bars->s_free[s], ((j >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + kColS + s * 128;
+#pragma unroll
+        for (int k = 0; k < kAD / 16; ++k) {
+          const uint64_t a = make_sw128_desc(smem_u32(sQ + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          const uint64_t bb = make_sw128_desc(smem_u32(sK + s * kATile + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(d, a, bb, idesc_qk, k ? 1u : 0u);
+        }
+        umma_commit(&bars->k_empty[s]);
+        umma_commit(&bars->s_full[s]);
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->p_full[s], ph);
+        mbar_wait(&bars->v_full[s], ph);
+        if (j >= 1) mbar_wait(&bars->ot_free, (j - 1) & 1);  // O_tile(j-1) folded into the running output
+        tc_fence_after();
+        const uint32_t p = tmem + k2ColP + s * 64;
+        const uint64_t vdesc = make_sw128_desc_mn_lbo(smem_u32(sV + s * kATile), kAHalf);
+#pragma unroll
+        for (int k = 0; k < kAKV / 16; ++k) umma_bf16_ts(tmem + k2ColOT, p + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, k ? 1u : 0u);
+        umma_commit(&bars->v_empty[s]);
+        umma_commit(&bars->s_free[s]);
+        umma_commit(&bars->ot_full);
+      }
+    }
+  } else if (warp >= 4) {
+    const int qd = warp & 3, hf = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
+    const int c0 = hf * 64;  // first S / head-dim column of this thread
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    float m = -INFINITY, l = 0.f, alpha_pending = 0.f;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+
+    auto accumulate = [&](int t, float a) {
+      mbar_wait(&bars->ot_full, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_base + k2ColOT + c0 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * a + __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->ot_free);
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const bool diag = j == qblk;
+      mbar_wait(&bars->s_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t sb = tmem + lane_base + kColS + s * 128 + c0;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(sb + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (!diag || c0 + c * 32 + i <= row) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      // agree on the row maximum with the thread that owns the other half of this row
+      bars->xmax[j & 1][hf][row] = mx;
+      named_bar_sync(1 + qd, 64);
+      mx = fmaxf(mx, bars->xmax[j & 1][hf ^ 1][row]);
+      const float m_new = fmaxf(m, mx * scale_log2);
+      const float alpha = exp2f(m - m_new);
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(sb + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = exp2f(__uint_as_float(r[2 * i]) * scale_log2 - m_new);
+          float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * scale_log2 - m_new);
+          if (diag) {
+            if (c0 + c * 32 + 2 * i > row) p0 = 0.f;
+            if (c0 + c * 32 + 2 * i + 1 > row) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32_x16(tmem + lane_base + k2ColP + s * 64 + hf * 32 + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[s]);
+      l = l * alpha + rs;
+      m = m_new;
+      if (j >= 1) accumulate(j - 1, alpha_pending);
+      alpha_pending = alpha;
+    }
+    accumulate(n_tiles - 1, alpha_pending);
+
+    // row sum: add the partner's half
+    bars->xsum[hf][row] = l;
+    named_bar_sync(1 + qd, 64);
+    l += bars->xsum[hf ^ 1][row];
+    const float inv_l = 1.f / l;
+    if (hf == 0 && lse != nullptr) lse[((size_t)b * Hq + h) * S + qblk * kAQ + row] = (m + log2f(l)) * 0.6931471805599453f;
+    {
+      float v[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = o[i] * inv_l;
+      uint8_t* buf = sQ + (qd * 2 + hf) * 4096;
+      epi_write_row_swizzled(buf, lane, v);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tm_o, buf, h * kAD + c0, row0 + qd * 32);
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+constexpr int kAttnFwd2Smem = 5 * kATile + (int)sizeof(Attn2Bars) + 1024;
+static_assert(kAttnFwd2Smem <= 232448, "attn_fwd2_kernel: shared memory over the 227 KB CTA limit");
+
 constexpr int kAttnFwdSmem = 5 * kATile + (int)sizeof(AttnBars) + 1024;
 static_assert(kAttnFwdSmem <= 232448, "attn_fwd_kernel: shared memory over the 227 KB CTA limit");
 
 }  // namespace
 
 // qkv [B, S, (Hq + 2 Hkv) * 128] bf16 contiguous (RoPE already applied) -> out [B, S, Hq * 128] bf16, lse [B, Hq, S] fp32
-void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q, int64_t n_kv, double softmax_scale) {
+void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q, int64_t n_kv, double softmax_scale, int64_t variant) {
   TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == at::kBFloat16 && qkv.dim() == 3 && qkv.is_contiguous(), "attn_fwd: qkv must be a contiguous bf16 [B, S, C] CUDA tensor");
   const int64_t B = qkv.size(0), S = qkv.size(1), C = qkv.size(2);
   TORCH_CHECK(C == (n_q + 2 * n_kv) * kAD, "attn_fwd: head dim must be 128 and C == (Hq + 2 Hkv) * 128");
@@ -311,7 +553,20 @@ void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q
   }
   const int grid = (int)(B * n_kv * (S / kAQ) * (n_q / n_kv));
   const float scale_log2 = (float)(softmax_scale * 1.4426950408889634);
-  attn_fwd_kernel<<<grid, kAThreads, kAttnFwdSmem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
+  static const int env_variant = [] {
+    const char* e = getenv("VESCALE_B200_ATTN_FWD");
+    return e ? atoi(e) : 2;
+  }();
+  if ((variant > 0 ? (int)variant : env_variant) == 1) {
+    attn_fwd_kernel<<<grid, kAThreads, kAttnFwdSmem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
+  } else {
+    static bool attr2 = false;
+    if (!attr2) {
+      C10_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwd2Smem));
+      attr2 = true;
+    }
+    attn_fwd2_kernel<<<grid, kA2Threads, kAttnFwd2Smem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
+  }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -24,7 +24,7 @@ void gemm_nn(const at::Tensor& a, const at::Tensor& b, at::Tensor c);
 void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumulate);
 
 // symm_comm.cu
-void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q, int64_t n_kv, double softmax_scale);
+void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q, int64_t n_kv, double softmax_scale, int64_t variant);
 void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse, at::Tensor dqkv, at::Tensor dvec, at::Tensor dq_acc,
               int64_t n_q, int64_t n_kv, double softmax_scale);
 void gemm_set_sched(int64_t mode);
@@ -109,7 +109,7 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("gemm_tn(Tensor a, Tensor b, Tensor(a!) c, bool accumulate) -> ()");
   m.def("ag_gemm(Tensor x_local, int[] x_ptrs, Tensor w, Tensor(a!) x_full, Tensor(b!) y, Tensor(c!) arrive, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
-  m.def("attn_fwd(Tensor qkv, Tensor(a!) out, Tensor(b!) lse, int n_q, int n_kv, float softmax_scale) -> ()");
+  m.def("attn_fwd(Tensor qkv, Tensor(a!) out, Tensor(b!) lse, int n_q, int n_kv, float softmax_scale, int variant=0) -> ()");
   m.def("attn_bwd(Tensor qkv, Tensor out, Tensor dout, Tensor lse, Tensor(a!) dqkv, Tensor(b!) dvec, Tensor(c!) dq_acc, int n_q, int n_kv, float softmax_scale) -> ()");
   m.def("gemm_set_sched(int mode) -> ()", &gemm_set_sched);
   m.def("gemm_get_sched() -> int", &gemm_get_sched);

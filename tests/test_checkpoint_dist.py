@@ -380,3 +380,34 @@ def test_dmodule_checkpoint_reshards_across_tp_degrees(tmp_path):
     (legacy ``dmodule/test_saveload.py`` + ``checkpoint/open_llama/test_open_llama_tp_reshard.py``)."""
     run_distributed(_tp_save, 4, str(tmp_path))
     run_distributed(_tp_load, 2, str(tmp_path))
+
+
+def _pp_layout_and_workers(rank, world, path):
+    """Optimizer state of a pipelined model: one DCP checkpoint per stage under ``optimizer/pp_{rank}`` saved within the stage's
+    process group (legacy layout, ``api/vescale_checkpointer.py:71-249``); files are serialised by worker processes
+    (``storage.ProcessPoolWriter``, legacy ``storage/filesystem.py:401-460``) and reshard on load."""
+    import vescale_b200.checkpoint as ckpt
+    from vescale_b200 import Shard, distribute_tensor, init_device_mesh
+
+    pp_rank = rank // 2
+    groups = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+    from vescale_b200.mesh import DeviceMesh
+
+    meshes = [DeviceMesh(device_type(), [0, 1]), DeviceMesh(device_type(), [2, 3])]  # every rank builds both (group creation is collective)
+    mesh = meshes[pp_rank]
+    w = torch.arange(48.0).view(6, 8) + 1000 * pp_rank  # every stage owns different optimizer state
+    st = {"exp_avg": distribute_tensor(w.to(device_type()), mesh, [Shard(0)], src_data_rank=None), "step": 7 + pp_rank}
+    ckpt.save(path, {"optimizer": st}, async_checkpoint=True, workers=2, pp_rank=pp_rank, pp_group=groups[pp_rank])
+    ckpt.wait_for_async()
+    dist.barrier()
+    d = os.path.join(path, "optimizer", f"pp_{pp_rank}")
+    files = sorted(os.listdir(d))
+    assert ".metadata" in files and sum(f.endswith(".distcp") for f in files) >= 2, files
+    assert sorted(os.listdir(os.path.join(path, "optimizer"))) == ["pp_0", "pp_1"]
+    tgt = {"exp_avg": distribute_tensor(torch.zeros(6, 8).to(device_type()), mesh, [Shard(1)], src_data_rank=None), "step": 0}
+    ckpt.load(path, {"optimizer": tgt}, pp_rank=pp_rank, pp_group=groups[pp_rank])
+    torch.testing.assert_close(tgt["exp_avg"].full_tensor().cpu(), w)
+
+
+def test_pp_optimizer_layout_and_process_pool_writer(tmp_path):
+    run_distributed(_pp_layout_and_workers, 4, str(tmp_path))

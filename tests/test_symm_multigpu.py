@@ -476,3 +476,48 @@ def _dtensor_fusion(rank, world):
 @pytest.mark.timeout(200)
 def test_dtensor_level_fusion_hits_fused_kernels():
     run_distributed(_dtensor_fusion, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+def _emulator_vs_nccl(rank, world):
+    """The emulator against LIVE NCCL (legacy ``test/emulator/test_distributed.py:72-101`` asserts ``torch.equal`` between the
+    two): ring all-reduce / reduce-scatter with the Simple protocol on one channel.  The ring order NCCL chose on this box is
+    discovered once (the reference reads it from a graph dump, ``emulator/distributed.py:741-809``): the same candidate must
+    reproduce every message size bit for bit."""
+    import itertools
+
+    from vescale_b200.emulator.collectives import ring_all_reduce, ring_reduce_scatter
+
+    dev = torch.device("cuda", rank)
+    g = torch.Generator(device=dev)
+    cases = []
+    for n_per in (1024, 4096, 65536):
+        count = n_per * world
+        g.manual_seed(1234 + rank + n_per)
+        x = (torch.randn(count, device=dev, generator=g) * 3.0).float()
+        gathered = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(gathered, x)
+        y = x.clone()
+        dist.all_reduce(y)
+        rs = torch.empty(n_per, device=dev)
+        dist.reduce_scatter_tensor(rs, x.clone())
+        cases.append((n_per, [t.cpu() for t in gathered], y.cpu(), rs.cpu()))
+    if rank != 0:
+        return
+    rings = [[0] + list(p) for p in itertools.permutations(range(1, world))] if world <= 5 else [list(range(world)), list(range(world - 1, -1, -1))]
+    good = None
+    for ring in rings:
+        if all(torch.equal(ring_all_reduce(ins, "sum", ring=ring, nchannels=1, chunk_elems=n_per)[0], y) for n_per, ins, y, _ in cases):
+            good = ring
+            break
+    assert good is not None, "no ring order reproduces NCCL's all-reduce bit for bit"
+    for n_per, ins, _, rs in cases:
+        assert torch.equal(ring_reduce_scatter(ins, "sum", ring=good)[0], rs), ("reduce_scatter", n_per, good)
+    print(f"[emulator] NCCL ring order on this box: {good}; all_reduce / reduce_scatter bit-identical for {[c[0] * world for c in cases]} fp32 elements", flush=True)
+
+
+@pytest.mark.timeout(240)
+def test_emulator_bitwise_equals_live_nccl(monkeypatch):
+    # one channel, ring, Simple protocol: the configuration whose schedule the emulator reproduces
+    for k, v in (("NCCL_ALGO", "Ring"), ("NCCL_PROTO", "Simple"), ("NCCL_MAX_NCHANNELS", "1"), ("NCCL_MIN_NCHANNELS", "1"), ("NCCL_NVLS_ENABLE", "0")):
+        monkeypatch.setenv(k, v)
+    run_distributed(_emulator_vs_nccl, min(torch.cuda.device_count(), 4), backend="nccl")

@@ -15,7 +15,7 @@ from .pinned_pool import PinnedPool
 
 __all__ = ["save", "load", "VeScaleCheckpointer", "wait_for_async"]
 
-_POOL = PinnedPool()
+_POOL = PinnedPool(shared=True)  # shared-memory + cudaHostRegister: worker processes serialise the staged shards without a copy
 _PENDING: List[Future] = []
 _ASYNC_PG = {"pg": None}
 _PLANNERS: Dict[str, Any] = {}
@@ -37,17 +37,61 @@ def _save_planner(key: str):
     return pl
 
 
-def _storage(sub: str, write: bool):
-    """``mem://host:port/dir`` checkpoints go to the in-memory file server (``mem_server.py``); anything else is a path."""
+def _storage(sub: str, write: bool, workers: int = 0):
+    """``mem://host:port/dir`` checkpoints go to the in-memory file server (``mem_server.py``); anything else is a path.
+    ``workers > 0`` (writes): files are serialised and written by that many worker processes (``storage.ProcessPoolWriter``)."""
     from .mem_server import make_mem_reader, make_mem_writer, parse_mem_uri
 
     if parse_mem_uri(sub) is None:
+        if write and workers > 0:
+            from .storage import ProcessPoolWriter
+
+            return {"storage_writer": ProcessPoolWriter(sub, workers=workers)}
         return {"checkpoint_id": sub}
     return {"storage_writer": make_mem_writer(sub)} if write else {"storage_reader": make_mem_reader(sub)}
 
 
 def _join(path: str, key: str) -> str:
     return f"{path.rstrip('/')}/{key}" if path.startswith("mem://") else os.path.join(path, key)
+
+
+def _pp_scope(key: str, pp_rank: Optional[int], pp_group):
+    """Optimizer state of a pipeline-parallel model differs per stage: each stage saves its own DCP checkpoint under
+    ``optimizer/pp_{rank}`` within the process group of that stage (legacy layout ``path/optimizer/pp_{pp_rank}``,
+    ``api/vescale_checkpointer.py:71-249``).  Returns (sub-directory suffix, process group) — ("", None) when not pipelined.
+    The stage group defaults to the DP x TP ranks of this stage taken from the global ``VESCALE_DEVICE_MESH``."""
+    if key != "optimizer":
+        return "", None
+    if pp_rank is None:
+        try:
+            from ..devicemesh_api import VESCALE_DEVICE_MESH as vdm
+
+            if "PP" in (vdm._MESH_DIM_NAMES_LOOKUP or []) and vdm.get_strategy_size("PP") > 1:
+                pp_rank = vdm.get_pipeline_parallel_rank()
+        except Exception:  # noqa: BLE001 — no global mesh: not pipelined
+            return "", None
+    if pp_rank is None:
+        return "", None
+    if pp_group is None:
+        pp_group = _stage_group(pp_rank)
+    return f"pp_{pp_rank}", pp_group
+
+
+_STAGE_GROUPS: Dict[int, Any] = {}
+
+
+def _stage_group(pp_rank: int):
+    """Process group of all ranks in pipeline stage ``pp_rank`` (every rank must call this for every stage: new_group is
+    collective)."""
+    if not _STAGE_GROUPS:
+        from ..devicemesh_api import VESCALE_DEVICE_MESH as vdm
+
+        mesh = vdm.get()
+        d = list(mesh.mesh_dim_names).index("PP")
+        t = mesh.mesh.movedim(d, 0).reshape(mesh.mesh.shape[d], -1)
+        for r in range(t.shape[0]):
+            _STAGE_GROUPS[r] = dist.new_group([int(x) for x in t[r].tolist()], backend="gloo" if dist.get_backend() == "gloo" else None)
+    return _STAGE_GROUPS[pp_rank]
 
 
 def _flatten(prefix: str, obj, out: Dict[str, Any]) -> None:
@@ -121,13 +165,21 @@ class BaseCheckpointer:
 
 class VeScaleCheckpointer(BaseCheckpointer):
     @classmethod
-    def save(cls, path: str, checkpoint_state: Dict[str, Any], async_checkpoint: bool = False) -> Optional[List[Future]]:
+    def save(cls, path: str, checkpoint_state: Dict[str, Any], async_checkpoint: bool = False, *, workers: Optional[int] = None, pp_rank: Optional[int] = None,
+             pp_group=None) -> Optional[List[Future]]:
+        """``workers``: writer processes per rank for the file serialisation (default: 2 for asynchronous saves, 0 = in-process
+        writer threads for synchronous ones; ``VESCALE_CHECKPOINT_WORKERS`` overrides)."""
         import torch.distributed.checkpoint as dcp
 
+        if workers is None:
+            workers = int(os.environ.get("VESCALE_CHECKPOINT_WORKERS", "2" if async_checkpoint else "0"))
         futures = []
         for key, obj in checkpoint_state.items():
             sub = _join(path, key)
-            if not path.startswith("mem://") and (not dist.is_initialized() or dist.get_rank() == 0):
+            suffix, stage_pg = _pp_scope(key, pp_rank, pp_group)
+            if suffix:
+                sub = _join(sub, suffix)
+            if not path.startswith("mem://"):
                 os.makedirs(sub, exist_ok=True)
             sd = _state_of(obj)
             tensors = {k: v for k, v in sd.items() if isinstance(v, torch.Tensor)}
@@ -136,12 +188,14 @@ class VeScaleCheckpointer(BaseCheckpointer):
                 tensors["__extras__"] = extras  # small python state (step counters, hyper-parameters) via DCP bytes
             if async_checkpoint:
                 host = _stage_to_host(tensors)
-                pg = _async_group()
+                pg = stage_pg if stage_pg is not None else _async_group()
                 fut: Future = Future()
 
                 def work(host=host, sub=sub, pg=pg, fut=fut):
                     try:
-                        dcp.save(host, process_group=pg, planner=_save_planner("async/" + key), **_storage(sub, True))
+                        # planning (a few small collectives) runs on this thread; serialisation + file writes run in worker
+                        # PROCESSES on the shared pinned staging buffers, so the training loop's GIL is left alone
+                        dcp.save(host, process_group=pg, planner=_save_planner("async/" + key), **_storage(sub, True, workers))
                         fut.set_result(sub)
                     except Exception as e:  # noqa: BLE001
                         fut.set_exception(e)
@@ -155,15 +209,18 @@ class VeScaleCheckpointer(BaseCheckpointer):
                 _PENDING.append(fut)
                 futures.append(fut)
             else:
-                dcp.save(tensors, planner=_save_planner(key), **_storage(sub, True))
+                dcp.save(tensors, planner=_save_planner(key), process_group=stage_pg, **_storage(sub, True, workers))
         return futures or None
 
     @classmethod
-    def load(cls, path: str, checkpoint_state: Dict[str, Any], broadcast_checkpoint: bool = False) -> None:
+    def load(cls, path: str, checkpoint_state: Dict[str, Any], broadcast_checkpoint: bool = False, *, pp_rank: Optional[int] = None, pp_group=None) -> None:
         import torch.distributed.checkpoint as dcp
 
         for key, obj in checkpoint_state.items():
             sub = _join(path, key)
+            suffix, stage_pg = _pp_scope(key, pp_rank, pp_group)
+            if suffix:
+                sub = _join(sub, suffix)
             sd = _state_of(obj)
             tensors = {k: v for k, v in sd.items() if isinstance(v, torch.Tensor)}
             extras_keys = [k for k, v in sd.items() if not isinstance(v, torch.Tensor)]
@@ -193,7 +250,7 @@ class VeScaleCheckpointer(BaseCheckpointer):
                         else:
                             dist.broadcast(t, src=0)
             else:
-                dcp.load(req, **_storage(sub, False))  # in place: DTensor / tensor storages are filled with the resharded data
+                dcp.load(req, process_group=stage_pg, **_storage(sub, False))  # in place: DTensor / tensor storages are filled with the resharded data
             if isinstance(obj, nn.Module):
                 pass  # state_dict tensors alias the module's parameters/buffers
             elif hasattr(obj, "load_checkpoint_state"):
@@ -239,9 +296,9 @@ def wait_for_async() -> None:
 atexit.register(lambda: [f.result() for f in list(_PENDING) if not f.done()] if _PENDING else None)
 
 
-def save(path: str, checkpoint_state: Dict[str, Any], async_checkpoint: bool = False):
-    return VeScaleCheckpointer.save(path, checkpoint_state, async_checkpoint)
+def save(path: str, checkpoint_state: Dict[str, Any], async_checkpoint: bool = False, **kw):
+    return VeScaleCheckpointer.save(path, checkpoint_state, async_checkpoint, **kw)
 
 
-def load(path: str, checkpoint_state: Dict[str, Any], broadcast_checkpoint: bool = False):
-    return VeScaleCheckpointer.load(path, checkpoint_state, broadcast_checkpoint)
+def load(path: str, checkpoint_state: Dict[str, Any], broadcast_checkpoint: bool = False, **kw):
+    return VeScaleCheckpointer.load(path, checkpoint_state, broadcast_checkpoint, **kw)

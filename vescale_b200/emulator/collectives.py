@@ -18,22 +18,30 @@ import torch
 __all__ = ["ring_all_reduce", "ring_reduce_scatter", "tree_all_reduce", "double_tree_all_reduce", "all_gather", "all_to_all", "EmulatorProcessGroup", "nccl_chunking", "expand_tensor_list", "contract_tensor_list"]
 
 
-def nccl_chunking(count: int, nranks: int, nchannels: int = 1, chunk_elems: Optional[int] = None) -> List[Tuple[int, int, int]]:
-    """[(channel, loop_offset, chunk_size)]: each entry is one ring loop covering ``nranks * chunk_size`` elements
-    (the last loop of a channel may be shorter; its chunk size shrinks, aligned to 4 elements as NCCL does for 16 B)."""
-    per_channel = (count + nchannels - 1) // nchannels
-    out = []
-    for ch in range(nchannels):
-        lo, hi = ch * per_channel, min(count, (ch + 1) * per_channel)
-        pos = lo
-        while pos < hi:
-            remaining = hi - pos
-            cs = chunk_elems if chunk_elems is not None else max(1, (remaining + nranks - 1) // nranks)
-            if remaining < nranks * cs:
-                cs = max(1, (remaining + nranks - 1) // nranks)
-                cs = (cs + 3) // 4 * 4 if remaining >= 4 * nranks else cs
-            out.append((ch, pos, cs))
-            pos += nranks * cs
+def nccl_chunking(count: int, nranks: int, nchannels: int = 1, chunk_elems: Optional[int] = None, align: int = 4) -> List[Tuple[int, int, int]]:
+    """[(channel, offset, chunk_size)] — one entry per (loop, channel), in NCCL's order (``all_reduce.h::runRing``, Simple
+    protocol): the buffer is walked in loops of ``nchannels * nranks * chunk`` elements; inside a loop channel ``b`` owns the
+    ``nranks`` chunks starting at ``loop_offset + b * nranks * real_chunk``, and ``real_chunk`` shrinks in the last loop to
+    ``ceil(remaining / (nchannels * nranks))`` rounded up to ``align`` elements (NCCL aligns to the thread-block vector width;
+    pass the value of the run you compare against, ``legacy/vescale/emulator/calculate_chunk_size.py``).  Which element falls
+    into which chunk decides its summation chain, so this — with the ring order — is all that bit-exactness depends on."""
+    out: List[Tuple[int, int, int]] = []
+    if count <= 0:
+        return out
+    chunk = chunk_elems if chunk_elems is not None else max(1, (count + nchannels * nranks - 1) // (nchannels * nranks))
+    loop = nchannels * nranks * chunk
+    off = 0
+    while off < count:
+        remaining = count - off
+        real = min(chunk, (remaining + nchannels * nranks - 1) // (nchannels * nranks))
+        if align > 1 and remaining >= align * nchannels * nranks:
+            real = (real + align - 1) // align * align
+        real = max(1, real)
+        for ch in range(nchannels):
+            base = off + ch * nranks * real
+            if base < count:
+                out.append((ch, base, real))
+        off += loop if remaining > loop else nchannels * nranks * real
     return out
 
 
