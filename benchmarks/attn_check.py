@@ -67,7 +67,7 @@ def main():
         lse = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
         ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d))
         dqkv = torch.full_like(qkv, float("nan"))
-        dvec = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
+        dvec = torch.empty(2, B, hq, S, device=dev, dtype=torch.float32)
         dq_acc = torch.empty(B, S, hq * d, device=dev, dtype=torch.float32)
         ops.attn_bwd(qkv, o, do, lse, dqkv, dvec, dq_acc, hq, hk, 1.0 / math.sqrt(d))
         torch.cuda.synchronize()
@@ -114,7 +114,7 @@ def main():
             ms_c = timeit(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True))
         do = torch.randn(B, S, hq * d, device=dev, generator=g).bfloat16()
         dqkv = torch.empty_like(qkv)
-        dvec = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
+        dvec = torch.empty(2, B, hq, S, device=dev, dtype=torch.float32)
         dq_acc = torch.empty(B, S, hq * d, device=dev, dtype=torch.float32)
         ms_b = timeit(lambda: ops.attn_bwd(qkv, o, do, lse, dqkv, dvec, dq_acc, hq, hk, 1.0 / math.sqrt(d)))
         qg, kg, vg = (t.detach().clone().requires_grad_() for t in (q, k, v))

@@ -25,7 +25,7 @@ def main():
         o = torch.empty(B, S, hq * d, device=dev, dtype=torch.bfloat16)
         lse = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
         do = torch.randn(B, S, hq * d, device=dev, generator=g).bfloat16()
-        dqkv, dvec, dq = torch.empty_like(qkv), torch.empty_like(lse), torch.empty(B, S, hq * d, device=dev, dtype=torch.float32)
+        dqkv, dvec, dq = torch.empty_like(qkv), torch.empty(2, B, hq, S, device=dev, dtype=torch.float32), torch.empty(B, S, hq * d, device=dev, dtype=torch.float32)
         for _ in range(2):
             ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d), 2)
             ops.attn_bwd(qkv, o, do, lse, dqkv, dvec, dq, hq, hk, 1.0 / math.sqrt(d))

@@ -20,6 +20,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
@@ -445,9 +446,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       if (lane == 0) mbar_arrive(&bars->ot_free);
     };
 
-    for (int j = 0; j < n_tiles; ++j) {
+    auto tile = [&](int j, auto diag_tag) {
+      constexpr bool diag = decltype(diag_tag)::value;  // compare-and-select code only in the diagonal-tile instantiation
       const int s = j & 1;
-      const bool diag = j == qblk;
       mbar_wait(&bars->s_full[s], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t sb = tmem + lane_base + kColS + s * 128 + c0;
@@ -495,6 +496,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       m = m_new;
       if (j >= 1) accumulate(j - 1, alpha_pending);
       alpha_pending = alpha;
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j == qblk) tile(j, std::true_type{});
+      else tile(j, std::false_type{});
     }
     accumulate(n_tiles - 1, alpha_pending);
 
@@ -628,9 +633,9 @@ VB_DEVICE void write_row_sw128(uint8_t* tile, int r, const uint32_t* pk /*64*/) 
   }
 }
 
-__global__ void __launch_bounds__(kAThreads, 1)
+__global__ void __launch_bounds__(kA2Threads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv,
-                const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dq_acc, int B, int S, int Hq, int Hkv, float scale_log2,
+                const __grid_constant__ CUtensorMap tm_dq, const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dq_acc, int B, int S, int Hq, int Hkv, float scale_log2,
                 float scale) {
   extern __shared__ __align__(1024) uint8_t smem_bwd[];
   uint8_t* smem = smem_bwd;
@@ -661,6 +666,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     prefetch_tmap(&tm_qkv);
     prefetch_tmap(&tm_do);
     prefetch_tmap(&tm_dqkv);
+    prefetch_tmap(&tm_dq);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(&bars->kv_full, 1);
@@ -671,9 +677,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_init(&bars->do_empty[s], 1);
     }
     mbar_init(&bars->sp_full, 1);
-    mbar_init(&bars->pds_full, 4);
+    mbar_init(&bars->pds_full, 8);
     mbar_init(&bars->dq_full, 1);
-    mbar_init(&bars->dq_free, 4);
+    mbar_init(&bars->dq_free, 8);
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
   }
@@ -705,7 +711,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         mbar_expect_tx(&bars->q_full[s], kATile + 1024);
         tma_load_2d(sQ + s * kATile, &tm_qkv, &bars->q_full[s], h * kAD, qrow);
         tma_load_2d(sQ + s * kATile + kAHalf, &tm_qkv, &bars->q_full[s], h * kAD + 64, qrow);
-        bulk_load_1d(sVec + s * 256, lse + vec_off, 512, &bars->q_full[s]);
+        bulk_load_1d(sVec + s * 256, lse + vec_off, 512, &bars->q_full[s]);  // `lse` here = lse * log2(e), written by the pre-pass
         bulk_load_1d(sVec + s * 256 + 128, dvec + vec_off, 512, &bars->q_full[s]);
         mbar_wait(&bars->do_empty[s], ph ^ 1);
         mbar_expect_tx(&bars->do_full[s], kATile);
@@ -765,79 +771,114 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       umma_commit(&bars->acc_full);
     }
   } else if (warp >= 4) {
-    // ===================== softmax / dS / dQ drain: one thread per key row =====================
-    const int qd = warp - 4;
-    const int row = qd * 32 + lane;  // key index inside the tile
+    // ===================== softmax / dS / dQ drain: EIGHT warps, two threads per key row (query / head-dim columns split in halves) ====
+    // Instruction issue of these warps is what bounds the kernel (ncu: ALU pipe highest, tensor pipe < 40 %), so per element the
+    // inner loops are kept to FFMA + EX2 (+ 1/2 convert) for P and FADD + FMUL (+ 1/2 convert) for dS; lse arrives pre-multiplied by
+    // log2(e), the lse / D vectors are read as float4, and the causal compare-and-select code exists only in the diagonal-tile
+    // instantiation.
+    const int qd = warp & 3, hf = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;  // key index inside the tile (S^T / dP^T lanes); query index for the dQ drain
+    const int c0 = hf * 64;          // first query column (S^T, dP^T) / head-dim column (dQ, dK, dV) of this thread
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    const float log2e = 1.4426950408889634f;
-    for (int t = 0; t < n_iter; ++t) {
+    auto tile = [&](int t, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       const int s = t & 1;
       const int g = t / n_i, i = j + t % n_i;
       const int h = kvh * G + g;
-      const bool diag = i == j;
-      const float* vl = sVec + s * 256;
-      const float* vd = vl + 128;
+      const float4* vl4 = reinterpret_cast<const float4*>(sVec + s * 256 + c0);        // lse * log2(e)
+      const float4* vd4 = reinterpret_cast<const float4*>(sVec + s * 256 + 128 + c0);  // D
       mbar_wait(&bars->sp_full, t & 1);
       tc_fence_after();
-      uint32_t pp[64];  // P^T row, packed bf16x2 (query 2c, 2c+1 in word c)
+      float p[64];
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem + lane_base + kR0 + c * 32, r);
+        tmem_ld_32x32(tmem + lane_base + kR0 + c0 + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int w = 0; w < 16; ++w) {
-          const int q0 = c * 32 + 2 * w;
-          float p0 = exp2f(__uint_as_float(r[2 * w]) * scale_log2 - vl[q0] * log2e);
-          float p1 = exp2f(__uint_as_float(r[2 * w + 1]) * scale_log2 - vl[q0 + 1] * log2e);
-          if (diag) {  // causal inside the diagonal block: key `row` is visible to query q iff row <= q
-            if (row > q0) p0 = 0.f;
-            if (row > q0 + 1) p1 = 0.f;
+        for (int w = 0; w < 8; ++w) {
+          const float4 l4 = vl4[c * 8 + w];
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int q = c * 32 + 4 * w + e;
+            float v = exp2f(__uint_as_float(r[4 * w + e]) * scale_log2 - lv[e]);
+            if (DIAG && row > c0 + q) v = 0.f;  // key `row` is visible to query q iff row <= q
+            p[q] = v;
           }
-          pp[c * 16 + w] = pack_bf16x2(p0, p1);
         }
+#pragma unroll
+        for (int w = 0; w < 16; ++w) pk[c * 16 + w] = pack_bf16x2(p[c * 32 + 2 * w], p[c * 32 + 2 * w + 1]);
       }
+      // P^T (bf16) overwrites S^T columns [0,64) of the row: the partner thread must have finished READING its half first
+      named_bar_sync(1 + qd, 64);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st_32x32_x16(tmem + lane_base + kR0 + c * 16, pp + c * 16);
-      uint32_t ds[64];
+      for (int c = 0; c < 2; ++c) tmem_st_32x32_x16(tmem + lane_base + kR0 + hf * 32 + c * 16, pk + c * 16);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem + lane_base + kR1 + c * 32, r);
+        tmem_ld_32x32(tmem + lane_base + kR1 + c0 + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int w = 0; w < 16; ++w) {
-          const int q0 = c * 32 + 2 * w;
-          const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pp[c * 16 + w]);
-          const float d0 = __bfloat162float(pb.x) * (__uint_as_float(r[2 * w]) - vd[q0]);
-          const float d1 = __bfloat162float(pb.y) * (__uint_as_float(r[2 * w + 1]) - vd[q0 + 1]);
-          ds[c * 16 + w] = pack_bf16x2(d0, d1);
+        for (int w = 0; w < 8; ++w) {
+          const float4 d4 = vd4[c * 8 + w];
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          float ds4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ds4[e] = p[c * 32 + 4 * w + e] * (__uint_as_float(r[4 * w + e]) - dv[e]);
+          pk[c * 16 + 2 * w] = pack_bf16x2(ds4[0], ds4[1]);
+          pk[c * 16 + 2 * w + 1] = pack_bf16x2(ds4[2], ds4[3]);
         }
       }
+      named_bar_sync(1 + qd, 64);  // dS^T overwrites dP^T columns [64,128): same rule
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st_32x32_x16(tmem + lane_base + kR1 + 64 + c * 16, ds + c * 16);
-      write_row_sw128(sDS, row, ds);
+      for (int c = 0; c < 2; ++c) tmem_st_32x32_x16(tmem + lane_base + kR1 + 64 + hf * 32 + c * 16, pk + c * 16);
+      if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dQ reduce no longer reads this warp's slice of the tile
+      __syncwarp();
+      {  // the same dS^T half-row into shared memory (box `hf` of the [128 keys x 128 queries] tile, 128B swizzle)
+        const uint32_t base = smem_u32(sDS + hf * kAHalf) + row * 128;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) st_shared_v4(base + (((uint32_t)jj ^ ((uint32_t)row & 7u)) << 4), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+      }
       tmem_st_wait();
-      fence_proxy_async();  // the dS^T tile in shared memory is read by the tensor core (async proxy)
+      fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->pds_full);
-      // ---- drain dQ_i (lanes = queries of block i, columns = head dim) into the fp32 accumulator
+      // ---- drain dQ_i (lanes = queries of block i, columns = head dim: this thread's half) into the fp32 accumulator.
+      // 16K scalar reductions per tile from the SMs saturated the L2 atomic units (the first version spent most of its time
+      // here); instead each warp stages its [32 queries x 32 dims] fp32 block in shared memory — the 4 KB slice of the dS^T
+      // tile it owns, dead once the dQ product has completed — and ONE bulk tensor reduce-add (TMA) adds it to dq_acc.
       mbar_wait(&bars->dq_full, t & 1);
       tc_fence_after();
-      float* dst = dq_acc + (((size_t)(b * S + i * kAQ + row)) * Hq + h) * kAD;
+      uint8_t* stage = sDS + hf * kAHalf + qd * 4096;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem + lane_base + kRdQ + c * 32, r);
+        tmem_ld_32x32(tmem + lane_base + kRdQ + c0 + c * 32, r);
         tmem_ld_wait();
+        if (c == 1) {  // R0 / R1 are free for the next tile's S^T / dP^T as soon as the last TMEM read has landed
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->dq_free);
+        }
+        if (lane == 0) tma_store_wait_read<0>();  // the previous reduce has finished reading the staging block
+        __syncwarp();
+        const uint32_t base = smem_u32(stage) + lane * 128;
 #pragma unroll
-        for (int w = 0; w < 8; ++w)
-          red_add_v4(dst + c * 32 + 4 * w, __uint_as_float(r[4 * w]), __uint_as_float(r[4 * w + 1]), __uint_as_float(r[4 * w + 2]), __uint_as_float(r[4 * w + 3]));
+        for (int jj = 0; jj < 8; ++jj) st_shared_v4(base + (((uint32_t)jj ^ ((uint32_t)lane & 7u)) << 4), r[4 * jj], r[4 * jj + 1], r[4 * jj + 2], r[4 * jj + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tm_dq, stage, h * kAD + c0 + c * 32, b * S + i * kAQ + qd * 32);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->dq_free);
+    };
+    for (int t = 0; t < n_iter; ++t) {
+      if (t % n_i == 0) tile(t, std::true_type{});  // i == j: the diagonal block
+      else tile(t, std::false_type{});
     }
     // ---- epilogue: dK_j * scale and dV_j -> bf16 -> packed dqkv (the Q / dO rings are dead: reuse sQ as staging)
     mbar_wait(&bars->acc_full, 0);
@@ -847,27 +888,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const uint32_t reg = which == 0 ? kRdK : kRdV;
       const float mul = which == 0 ? scale : 1.f;
       const int col = which == 0 ? col_k : col_v;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float v[64];
+      float v[64];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem + lane_base + reg + c * 64 + cc * 32, r);
-          tmem_ld_wait();
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_base + reg + c0 + cc * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int x = 0; x < 32; ++x) v[cc * 32 + x] = __uint_as_float(r[x]) * mul;
-        }
-        uint8_t* buf = sQ + (qd * 2 + (c & 1)) * 4096;
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
-        epi_write_row_swizzled(buf, lane, v);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tm_dqkv, buf, col + c * 64, krow + qd * 32);
-          tma_store_commit();
-        }
+        for (int x = 0; x < 32; ++x) v[cc * 32 + x] = __uint_as_float(r[x]) * mul;
+      }
+      uint8_t* buf = sQ + ((warp - 4) * 2 + which) * 4096;
+      epi_write_row_swizzled(buf, lane, v);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tm_dqkv, buf, col + c0, krow + qd * 32);
+        tma_store_commit();
       }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -881,8 +917,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 }
 
 // D[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d] (fp32) ; dq_acc zeroed.  One warp per (b, s, h) row of 128 elements.
-__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, float* __restrict__ dvec,
-                                                            float* __restrict__ dq_acc, int B, int S, int Hq) {
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
+                                                            float* __restrict__ dvec, float* __restrict__ lse2, float* __restrict__ dq_acc, int B, int S, int Hq) {
   const int64_t nrow = (int64_t)B * S * Hq;
   const int lane = threadIdx.x & 31;
   for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrow; r += (int64_t)gridDim.x * 8) {
@@ -900,7 +936,10 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
     const int64_t bs = r / Hq;
     const int h = (int)(r - bs * Hq);
     const int64_t bb = bs / S, ss = bs - bb * S;
-    if (lane == 0) dvec[(bb * Hq + h) * S + ss] = sum;
+    if (lane == 0) {
+      dvec[(bb * Hq + h) * S + ss] = sum;
+      lse2[(bb * Hq + h) * S + ss] = lse[(bb * Hq + h) * S + ss] * 1.4426950408889634f;
+    }
     *reinterpret_cast<float4*>(dq_acc + r * kAD + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
@@ -920,7 +959,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restric
 
 }  // namespace
 
-// qkv, out, dout as in attn_fwd; lse [B, Hq, S]; dqkv [B, S, C] bf16 (fully written); scratch: dvec [B, Hq, S] fp32, dq_acc [B, S, Hq*128] fp32
+// qkv, out, dout as in attn_fwd; lse [B, Hq, S]; dqkv [B, S, C] bf16 (fully written); scratch: dvec [2, B, Hq, S] fp32 (D | lse*log2e), dq_acc [B, S, Hq*128] fp32
 void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse, at::Tensor dqkv, at::Tensor dvec, at::Tensor dq_acc,
               int64_t n_q, int64_t n_kv, double softmax_scale) {
   TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == at::kBFloat16 && qkv.dim() == 3 && qkv.is_contiguous());
@@ -929,24 +968,26 @@ void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& do
   TORCH_CHECK(out.is_contiguous() && dout.is_contiguous() && out.scalar_type() == at::kBFloat16 && dout.scalar_type() == at::kBFloat16 && out.numel() == B * S * n_q * kAD &&
               dout.numel() == out.numel());
   TORCH_CHECK(dqkv.is_contiguous() && dqkv.scalar_type() == at::kBFloat16 && dqkv.numel() == qkv.numel());
-  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == B * n_q * S && dvec.scalar_type() == at::kFloat && dvec.numel() == lse.numel() &&
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == B * n_q * S && dvec.scalar_type() == at::kFloat && dvec.numel() == 2 * lse.numel() &&
               dq_acc.scalar_type() == at::kFloat && dq_acc.is_contiguous() && dq_acc.numel() == B * S * n_q * kAD);
   c10::cuda::CUDAGuard guard(qkv.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  attn_bwd_prep_kernel<<<sms * 8, 256, 0, stream>>>((const __nv_bfloat16*)out.data_ptr(), (const __nv_bfloat16*)dout.data_ptr(), dvec.data_ptr<float>(),
+  float* lse2 = dvec.data_ptr<float>() + lse.numel();  // second half of the scratch vector: lse * log2(e)
+  attn_bwd_prep_kernel<<<sms * 8, 256, 0, stream>>>((const __nv_bfloat16*)out.data_ptr(), (const __nv_bfloat16*)dout.data_ptr(), lse.data_ptr<float>(), dvec.data_ptr<float>(), lse2,
                                                     dq_acc.data_ptr<float>(), (int)B, (int)S, (int)n_q);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   const CUtensorMap tq = make_tmap_2d(qkv.data_ptr(), B * S, C, C * 2, 128, 64, 2, true);
   const CUtensorMap tdo = make_tmap_2d(dout.data_ptr(), B * S, n_q * kAD, n_q * kAD * 2, 128, 64, 2, true);
   const CUtensorMap tdqkv = make_tmap_2d(dqkv.data_ptr(), B * S, C, C * 2, 32, 64, 2, true);
+  const CUtensorMap tdq = make_tmap_2d(dq_acc.data_ptr(), B * S, n_q * kAD, n_q * kAD * 4, 32, 32, 4, true);  // fp32 reduce-add target, [32 x 32] boxes
   static bool attr = false;
   if (!attr) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
     attr = true;
   }
   const int grid = (int)(B * n_kv * (S / kAQ));
-  attn_bwd_kernel<<<grid, kAThreads, kAttnBwdSmem, stream>>>(tq, tdo, tdqkv, lse.data_ptr<float>(), dvec.data_ptr<float>(), dq_acc.data_ptr<float>(), (int)B, (int)S,
+  attn_bwd_kernel<<<grid, kA2Threads, kAttnBwdSmem, stream>>>(tq, tdo, tdqkv, tdq, lse2, dvec.data_ptr<float>(), dq_acc.data_ptr<float>(), (int)B, (int)S,
                                                             (int)n_q, (int)n_kv, (float)(softmax_scale * 1.4426950408889634), (float)softmax_scale);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   attn_bwd_dq_kernel<<<sms * 4, 256, 0, stream>>>(dq_acc.data_ptr<float>(), (__nv_bfloat16*)dqkv.data_ptr(), B * S, (int)(n_q * kAD), (int)C, (float)softmax_scale);

@@ -121,6 +121,48 @@ def test_pipeline_p2p_overlap_and_timeline(batch):
     run_distributed(_pp_overlap, 4, batch)
 
 
+def _pp_hf_graph(rank, world):
+    """Graph tracer (torch.export + liveness pass, ``pipe/trace.py``) on an UNMODIFIED HuggingFace Llama: rotary tables and the
+    mask skip over stages, the stages still form a chain; 1F1B over 2 ranks reproduces the single-process loss and gradients."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.pipe import PipeEngine, PipelineParallelPlan, PipelineScheduleType, TracerType, construct_pipeline_stage
+
+    dev = device_type()
+    cfg = LlamaConfig(vocab_size=128, hidden_size=32, intermediate_size=64, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2,
+                      max_position_embeddings=64, attn_implementation="sdpa", use_cache=False, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    ref = LlamaForCausalLM(cfg).to(dev)
+    model = copy.deepcopy(ref)
+    g = torch.Generator().manual_seed(9)
+    M = 4
+    xs = [torch.randint(0, 128, (2, 16), generator=g).to(dev) for _ in range(M)]
+    ys = [torch.randint(0, 128, (2, 16), generator=g).to(dev) for _ in range(M)]
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("PP",))
+    plan = PipelineParallelPlan(num_stages=world, schedule_type=PipelineScheduleType.SIMPLE_1F1B, tracer_type=TracerType.GRAPH, example_inputs=(xs[0],))
+    pm = construct_pipeline_stage(model, plan, mesh)
+    loss_fn = lambda out, y: torch.nn.functional.cross_entropy((out[0] if isinstance(out, tuple) else out).reshape(-1, 128), y.reshape(-1))
+    engine = PipeEngine(pm, mesh, loss_fn, plan)
+    loss, _ = engine(xs, ys)
+    ref_loss = sum(loss_fn(ref(x).logits, y) / M for x, y in zip(xs, ys))
+    ref_loss.backward()
+    if engine.is_last_rank:
+        torch.testing.assert_close(loss, ref_loss.detach(), rtol=1e-5, atol=1e-6)
+    ref_params = dict(ref.named_parameters())
+    checked = 0
+    for c in range(pm.num_chunks):
+        st = pm.chunk(c)
+        for key, p in st.weights.items():
+            torch.testing.assert_close(p.grad, ref_params[st.names[key]].grad, rtol=1e-4, atol=1e-6, msg=st.names[key])
+            checked += 1
+    assert checked > 0
+
+
+def test_pipeline_graph_tracer_hf_llama():
+    run_distributed(_pp_hf_graph, 2)
+
+
 def test_pipeline_fx_tracer():
     run_distributed(_pp, 2, "SIMPLE_1F1B", "FX")
 

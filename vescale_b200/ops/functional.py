@@ -494,7 +494,7 @@ class _NativeAttention(torch.autograd.Function):
         n_q, n_kv, head_dim = ctx.cfg
         B, S, _ = qkv.shape
         dqkv = torch.empty_like(qkv)
-        dvec = torch.empty_like(lse)
+        dvec = torch.empty(2 * lse.numel(), dtype=torch.float32, device=qkv.device)  # D | lse * log2(e)
         dq_acc = torch.empty(B, S, n_q * head_dim, dtype=torch.float32, device=qkv.device)
         _ext.count_launch("attn_bwd")
         _ext.ops().attn_bwd(qkv, out, do.contiguous(), lse, dqkv, dvec, dq_acc, n_q, n_kv, 1.0 / math.sqrt(head_dim))

@@ -34,6 +34,7 @@ class TracerType(Enum):
     STRUCTURAL = "structural"  # split along the model's declared unit list
     FX = "fx"  # torch.fx symbolic trace + split_module
     EXPORT = "export"  # torch.export (dynamo) graph capture, unflattened back to the module hierarchy, split on unit boundaries
+    GRAPH = "graph"  # torch.export capture split at graph level with a liveness pass (HuggingFace models, skip connections): trace.py
 
 
 @dataclass

@@ -87,6 +87,10 @@ class PipeParser:
     """Splits a model into virtual-stage modules (all of them; the caller keeps its own)."""
 
     def parse(self, model: nn.Module, plan: PipelineParallelPlan) -> List[nn.Module]:
+        if plan.tracer_type == TracerType.GRAPH:
+            from .trace import trace_and_split
+
+            return trace_and_split(model, plan)
         units = _units(model)
         groups = split_units(units, plan)
         if plan.tracer_type == TracerType.FX:
