@@ -27,6 +27,7 @@ void gemm_tn(const at::Tensor& a, const at::Tensor& b, at::Tensor c, bool accumu
 void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q, int64_t n_kv, double softmax_scale, int64_t variant);
 void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse, at::Tensor dqkv, at::Tensor dvec, at::Tensor dq_acc,
               int64_t n_q, int64_t n_kv, double softmax_scale);
+void ragged_norm_partial(const at::Tensor& x, at::Tensor out, int64_t rows, int64_t C, int64_t mode, int64_t p);
 void gemm_set_sched(int64_t mode);
 int64_t gemm_get_sched();
 void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch);
@@ -111,6 +112,7 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("gemm_rs(Tensor x, Tensor w, Tensor(a!) y, int[] staging_ptrs, Tensor(b!) done, int[] flag_ptrs, int rank, int epoch) -> ()");
   m.def("attn_fwd(Tensor qkv, Tensor(a!) out, Tensor(b!) lse, int n_q, int n_kv, float softmax_scale, int variant=0) -> ()");
   m.def("attn_bwd(Tensor qkv, Tensor out, Tensor dout, Tensor lse, Tensor(a!) dqkv, Tensor(b!) dvec, Tensor(c!) dq_acc, int n_q, int n_kv, float softmax_scale) -> ()");
+  m.def("ragged_norm_partial(Tensor x, Tensor(a!) out, int rows, int C, int mode, int p) -> ()");
   m.def("gemm_set_sched(int mode) -> ()", &gemm_set_sched);
   m.def("gemm_get_sched() -> int", &gemm_get_sched);
   m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
@@ -158,6 +160,7 @@ TORCH_LIBRARY_IMPL(vescale_b200, CUDA, m) {
   m.impl("gemm_tn", &gemm_tn);
   m.impl("ag_gemm", &ag_gemm);
   m.impl("gemm_rs", &gemm_rs);
+  m.impl("ragged_norm_partial", &ragged_norm_partial);
   m.impl("attn_fwd", &attn_fwd);
   m.impl("attn_bwd", &attn_bwd);
   m.impl("symm_all_gather", &symm_all_gather);

@@ -286,3 +286,33 @@ def test_native_flash_attention_matches_fp32_reference(B, S, hq, hk):
     assert (out.float() - ref).abs().max().item() < 0.03
     rel = ((qkv.grad.float() - x.grad).abs().max() / x.grad.abs().max()).item()
     assert rel < 0.03, rel
+
+
+def test_ragged_norm_kernel_matches_eager_formulation():
+    """csrc/ragged_norm.cu (per-row / per-column p-norm partials of a RaggedShard's local rows, one pass in the storage dtype)
+    against the eager torch formulation of ``handlers.ragged_norm_local`` on a fake 4-rank mesh."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.dtensor import DTensor, RaggedShard
+    from vescale_b200.dtensor import handlers as H
+    from vescale_b200.ops import _ext
+
+    _ext.load(required=True)
+    dev = torch.device("cuda")
+    full = torch.randn(96, 40, 8, device=dev).bfloat16()
+    units = (1, 3, 0, 2)
+    for rank in range(4):
+        mesh = init_device_mesh("cuda", (4,), _rank=rank, _init_process_groups=False)
+        pl = RaggedShard((0,), units)
+        lo = sum(units[:rank]) * 96 // sum(units) * 320
+        n = units[rank] * 96 // sum(units) * 320
+        local = full.reshape(-1)[lo : lo + n].contiguous()
+        spec = DTensor.from_local(local, mesh, [pl], run_check=False, shape=full.shape, stride=full.stride())._spec
+        for ord_ in (2.0, 1.0, float("inf")):
+            for dims in ((1, 2), (0,)):
+                got = H.ragged_norm_local(local, spec, ord_, dims, False)
+                orig, H._ragged_norm_kernel = H._ragged_norm_kernel, lambda *a, **k: None
+                try:
+                    want = H.ragged_norm_local(local, spec, ord_, dims, False)
+                finally:
+                    H._ragged_norm_kernel = orig
+                torch.testing.assert_close(got, want.float(), rtol=2e-3, atol=2e-3, msg=lambda m: f"rank {rank} ord {ord_} dims {dims}: {m}")

@@ -118,8 +118,11 @@ def ragged_norm_local(local: torch.Tensor, spec: DTensorSpec, ord_: float, dims,
     lo, hi = rp.flat_range(math.prod(before), coord[ridx])
     rows = (hi - lo) // row_elems
     row0 = lo // row_elems
-    x = local.reshape(rows, *trail).to(dtype or (torch.float32 if local.dtype in (torch.float16, torch.bfloat16) else local.dtype))
     red = set(dims)
+    fast = _ragged_norm_kernel(local, rows, row_elems, lead, trail, k, red, ord_, row0, before, keepdim, dtype)
+    if fast is not None:
+        return fast
+    x = local.reshape(rows, *trail).to(dtype or (torch.float32 if local.dtype in (torch.float16, torch.bfloat16) else local.dtype))
     # power-sum elementwise
     if math.isinf(ord_):
         pw = x.abs()
@@ -171,6 +174,36 @@ def ragged_norm_local(local: torch.Tensor, spec: DTensorSpec, ord_: float, dims,
     if math.isinf(ord_) or ord_ in (0, 1):
         return acc
     return acc.pow(1.0 / ord_)
+
+
+def _ragged_norm_kernel(local, rows, row_elems, lead, trail, k, red, ord_, row0, before, keepdim, dtype):
+    """sm_100a fast path (``csrc/ragged_norm.cu``): one pass over the shard in its storage dtype when the reduced dims are exactly
+    the trailing dims (per-row partials) or exactly the leading dims (per-column partials) and p is 1, 2 or inf."""
+    from ..ops import _ext
+
+    if not (local.is_cuda and local.dtype in (torch.bfloat16, torch.float32) and local.is_contiguous() and _ext.available()):
+        return None
+    if not (math.isinf(ord_) or ord_ in (1.0, 2.0)) or (dtype is not None and dtype != torch.float32) or not hasattr(_ext.ops(), "ragged_norm_partial"):
+        return None
+    nd = len(before)
+    trailing, leading = set(range(k, nd)), set(range(k))
+    p = 0 if math.isinf(ord_) else int(ord_)
+    if red == trailing and k == 1:
+        out = torch.zeros(max(1, lead[0]), dtype=torch.float32, device=local.device)
+        if rows:
+            _ext.count_launch("ragged_norm")
+            _ext.ops().ragged_norm_partial(local, out[row0 : row0 + rows], rows, row_elems, 0, p)
+        shape = [lead[0]] + ([1] * len(trail) if keepdim else [])
+    elif red == leading and nd > k:
+        out = torch.zeros(row_elems, dtype=torch.float32, device=local.device)
+        if rows:
+            _ext.count_launch("ragged_norm")
+            _ext.ops().ragged_norm_partial(local, out, rows, row_elems, 1, p)
+        shape = ([1] * k if keepdim else []) + list(trail)
+    else:
+        return None
+    out = out.reshape(shape)
+    return out if p != 2 else out.sqrt()
 
 
 def _ragged_norm_cond(args, kwargs) -> bool:

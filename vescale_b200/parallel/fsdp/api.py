@@ -84,6 +84,10 @@ class FSDPState:
         if self.cuda:
             self.ag_stream = torch.cuda.Stream(priority=-1)
             self.rs_stream = torch.cuda.Stream(priority=-1)
+            from ...profiler.stream import register_comm_stream
+
+            register_comm_stream("fsdp-ag", self.ag_stream)  # ndtimeline looks communication streams up by name / group
+            register_comm_stream("fsdp-rs", self.rs_stream)
         else:
             self.ag_stream = self.rs_stream = _NullStream()
         self.pool = _BufferPool(device)

@@ -28,8 +28,24 @@ def _lookup(name: str) -> Optional["torch.cuda.Stream"]:
 
 
 def get_nccl_coll_stream(name: str, nccl_pg=None, nccl_tensor: Optional[torch.Tensor] = None):
-    return _lookup(name)
+    """Stream a collective named ``name`` runs on.  Resolution order: a stream registered under ``name``; a stream registered for
+    the process group (``register_comm_stream(pg.group_name, s)`` — FSDP registers its all-gather / reduce-scatter streams as
+    ``"fsdp-ag" / "fsdp-rs"`` and per group); the current stream of the tensor's device (c10d collectives issued with
+    ``async_op=False`` are ordered with it)."""
+    s = _STREAMS.get(name)
+    if s is None and nccl_pg is not None:
+        s = _STREAMS.get(getattr(nccl_pg, "group_name", None) or str(id(nccl_pg)))
+    if s is None and nccl_tensor is not None and nccl_tensor.is_cuda:
+        s = torch.cuda.current_stream(nccl_tensor.device)
+    return s if s is not None else _lookup(name)
 
 
 def get_nccl_p2p_stream(name: str, nccl_pg=None, peer=None, is_batched: bool = False):
-    return _lookup(name)
+    """Stream of a pipeline p2p operation: per (group, peer) registration first (``register_comm_stream(f"p2p:{peer}", s)``), then
+    the group's, then the current stream (torch's NCCL p2p kernels are enqueued behind the current stream's work)."""
+    s = _STREAMS.get(name)
+    if s is None and peer is not None:
+        s = _STREAMS.get(f"p2p:{peer}")
+    if s is None and nccl_pg is not None:
+        s = _STREAMS.get(getattr(nccl_pg, "group_name", None) or str(id(nccl_pg)))
+    return s if s is not None else _lookup(name)
