@@ -35,7 +35,7 @@ def main():
     for B, S, hq, hk in ((1, 128, 1, 1), (1, 256, 2, 1), (1, 512, 4, 2), (2, 1024, 8, 2), (1, 4096, 4, 1)):
         qkv = (torch.randn(B, S, (hq + 2 * hk) * d, device=dev, generator=g) * 1.0).bfloat16()
         ref = ref_attention(qkv, hq, hk, d)
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             o = torch.full((B, S, hq * d), float("nan"), device=dev, dtype=torch.bfloat16)
             lse = torch.full((B, hq, S), float("nan"), device=dev, dtype=torch.float32)
             ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d), variant)
@@ -106,7 +106,8 @@ def main():
         lse = torch.empty(B, hq, S, device=dev, dtype=torch.float32)
         fl = 4.0 * B * hq * S * S * d / 2  # causal
         ms1 = timeit(lambda: ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d), 1))
-        ms = timeit(lambda: ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d), 2))
+        ms2 = timeit(lambda: ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d), 2))
+        ms = timeit(lambda: ops.attn_fwd(qkv, o, lse, hq, hk, 1.0 / math.sqrt(d), 3))
         q = qkv[..., : hq * d].view(B, S, hq, d).transpose(1, 2)
         k = qkv[..., hq * d : (hq + hk) * d].view(B, S, hk, d).transpose(1, 2)
         v = qkv[..., (hq + hk) * d :].view(B, S, hk, d).transpose(1, 2)
@@ -122,7 +123,7 @@ def main():
             oc = F.scaled_dot_product_attention(qg, kg, vg, is_causal=True, enable_gqa=True)
             do4 = do.view(B, S, hq, d).transpose(1, 2)
             ms_cb = timeit(lambda: torch.autograd.grad(oc, (qg, kg, vg), do4, retain_graph=True))
-        row = {"shape": [B, S, hq, hk], "ours_bwd_ms": ms_b, "ours_bwd_tflops": 2.5 * fl / ms_b / 1e9, "cudnn_bwd_ms": ms_cb, "cudnn_bwd_tflops": 2.5 * fl / ms_cb / 1e9, "ours_fwd_v1_ms": ms1, "ours_fwd_ms": ms, "ours_fwd_tflops": fl / ms / 1e9, "cudnn_fwd_ms": ms_c, "cudnn_fwd_tflops": fl / ms_c / 1e9}
+        row = {"shape": [B, S, hq, hk], "ours_bwd_ms": ms_b, "ours_bwd_tflops": 2.5 * fl / ms_b / 1e9, "cudnn_bwd_ms": ms_cb, "cudnn_bwd_tflops": 2.5 * fl / ms_cb / 1e9, "ours_fwd_v1_ms": ms1, "ours_fwd_v2_ms": ms2, "ours_fwd_ms": ms, "ours_fwd_tflops": fl / ms / 1e9, "cudnn_fwd_ms": ms_c, "cudnn_fwd_tflops": fl / ms_c / 1e9}
         out["timing"].append(row)
         print(json.dumps(row), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

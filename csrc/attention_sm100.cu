@@ -45,6 +45,29 @@ VB_DEVICE void tmem_st_32x32_x16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 VB_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 lanes x 64 columns in ONE request (one wait instead of two: the softmax warps are bound by tcgen05.ld round trips)
+VB_DEVICE void tmem_ld_32x64(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+        "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+        "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]),
+        "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr));
+}
+VB_DEVICE void tmem_st_32x32_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+      "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (P, packed bf16, one query row per lane) never leaves tensor memory
 VB_DEVICE void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -312,6 +335,7 @@ struct Attn2Bars {
 
 VB_DEVICE void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+template <bool X64>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o, float* __restrict__ lse, int B, int S, int Hq, int Hkv,
                  float scale_log2) {
@@ -433,13 +457,21 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     auto accumulate = [&](int t, float a) {
       mbar_wait(&bars->ot_full, t & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem + lane_base + k2ColOT + c0 + c * 32, r);
+      if (X64) {
+        uint32_t r[64];
+        tmem_ld_32x64(tmem + lane_base + k2ColOT + c0, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * a + __uint_as_float(r[i]);
+        for (int i = 0; i < 64; ++i) o[i] = o[i] * a + __uint_as_float(r[i]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem + lane_base + k2ColOT + c0 + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * a + __uint_as_float(r[i]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -452,7 +484,34 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       mbar_wait(&bars->s_full[s], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t sb = tmem + lane_base + kColS + s * 128 + c0;
-      float mx = -INFINITY;
+      float mx = -INFINITY, m_new, alpha, rs = 0.f;
+      if (X64) {
+        // one TMEM round trip per tile: the 64 S values of this thread stay in registers between the max and the exp2 pass
+        uint32_t r[64];
+        tmem_ld_32x64(sb, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (!diag || c0 + i <= row) mx = fmaxf(mx, __uint_as_float(r[i]));
+        bars->xmax[j & 1][hf][row] = mx;
+        named_bar_sync(1 + qd, 64);
+        mx = fmaxf(mx, bars->xmax[j & 1][hf ^ 1][row]);
+        m_new = fmaxf(m, mx * scale_log2);
+        alpha = exp2f(m - m_new);
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float p0 = exp2f(__uint_as_float(r[2 * i]) * scale_log2 - m_new);
+          float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * scale_log2 - m_new);
+          if (diag) {
+            if (c0 + 2 * i > row) p0 = 0.f;
+            if (c0 + 2 * i + 1 > row) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32_x32(tmem + lane_base + k2ColP + s * 64 + hf * 32, pk);
+      } else {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
@@ -466,9 +525,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       bars->xmax[j & 1][hf][row] = mx;
       named_bar_sync(1 + qd, 64);
       mx = fmaxf(mx, bars->xmax[j & 1][hf ^ 1][row]);
-      const float m_new = fmaxf(m, mx * scale_log2);
-      const float alpha = exp2f(m - m_new);
-      float rs = 0.f;
+      m_new = fmaxf(m, mx * scale_log2);
+      alpha = exp2f(m - m_new);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
@@ -487,6 +545,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           pk[i] = pack_bf16x2(p0, p1);
         }
         tmem_st_32x32_x16(tmem + lane_base + k2ColP + s * 64 + hf * 32 + c * 16, pk);
+      }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -560,17 +619,21 @@ void attn_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor lse, int64_t n_q
   const float scale_log2 = (float)(softmax_scale * 1.4426950408889634);
   static const int env_variant = [] {
     const char* e = getenv("VESCALE_B200_ATTN_FWD");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 3;
   }();
   if ((variant > 0 ? (int)variant : env_variant) == 1) {
     attn_fwd_kernel<<<grid, kAThreads, kAttnFwdSmem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
   } else {
     static bool attr2 = false;
     if (!attr2) {
-      C10_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwd2Smem));
+      C10_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwd2Smem));
+      C10_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwd2Smem));
       attr2 = true;
     }
-    attn_fwd2_kernel<<<grid, kA2Threads, kAttnFwd2Smem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
+    if ((variant > 0 ? (int)variant : env_variant) == 2)
+      attn_fwd2_kernel<false><<<grid, kA2Threads, kAttnFwd2Smem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
+    else  // 3: single TMEM round trip per tile (x64 loads)
+      attn_fwd2_kernel<true><<<grid, kA2Threads, kAttnFwd2Smem, at::cuda::getCurrentCUDAStream()>>>(tq, to, lse.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv, scale_log2);
   }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

@@ -480,3 +480,28 @@ def test_emulator_mesh_collectives_reference_call_forms():
         assert list(ed._world.pg_group_ranks.values())[0] == {0: 0, 1: 1, 2: 2, 3: 3}
     finally:
         ed.destroy_process_group()
+
+
+def test_emulator_dtensor_list_front_end():
+    """List-of-DTensors front end (legacy ``test/emulator/test_dtensor.py``): one process holds every rank's DTensor, ops go through
+    the real rules rank by rank, redistributions through the emulated collectives (ring order of the Partial reduction)."""
+    import torch
+
+    from vescale_b200 import Replicate, Shard
+    from vescale_b200.emulator.collectives import ring_all_reduce
+    from vescale_b200.emulator.dtensor_api import EmuMesh, distribute_tensor, emu_call, redistribute_dtensor
+
+    mesh = EmuMesh("cpu", (4,))
+    torch.manual_seed(0)
+    t1, t2 = torch.randn(12, 8), torch.randn(8, 12)
+    expect = {(Shard(0), Replicate()): Shard(0), (Shard(1), Shard(0)): None, (Replicate(), Shard(1)): Shard(1), (Replicate(), Replicate()): Replicate(), (Shard(0), Shard(0)): Shard(0)}
+    for (p1, p2), want in expect.items():
+        a, b = distribute_tensor([t1] * 4, mesh, [p1]), distribute_tensor([t2] * 4, mesh, [p2])
+        y = emu_call(torch.mm, a, b)
+        assert (y[0].placements[0].is_partial() if want is None else y[0].placements == (want,)), (p1, p2, y[0].placements)
+        y = redistribute_dtensor(y, mesh, [Replicate()])
+        for d in y:
+            torch.testing.assert_close(d.to_local(), t1 @ t2, rtol=1e-5, atol=1e-5)
+        if want is None:  # the Partial result was reduced in NCCL's ring association order, bit for bit
+            parts = [t1[:, 2 * r : 2 * r + 2] @ t2[2 * r : 2 * r + 2] for r in range(4)]
+            assert torch.equal(y[0].to_local(), ring_all_reduce(parts)[0])
