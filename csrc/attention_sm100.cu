@@ -59,6 +59,18 @@ VB_DEVICE void tmem_ld_32x64(uint32_t taddr, uint32_t* r) {
         "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
       : "r"(taddr));
 }
+VB_DEVICE void tmem_st_32x64(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,"
+      "%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63,%64};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+      "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(r[32]), "r"(r[33]), "r"(r[34]), "r"(r[35]), "r"(r[36]), "r"(r[37]), "r"(r[38]), "r"(r[39]),
+      "r"(r[40]), "r"(r[41]), "r"(r[42]), "r"(r[43]), "r"(r[44]), "r"(r[45]), "r"(r[46]), "r"(r[47]), "r"(r[48]), "r"(r[49]), "r"(r[50]), "r"(r[51]), "r"(r[52]),
+      "r"(r[53]), "r"(r[54]), "r"(r[55]), "r"(r[56]), "r"(r[57]), "r"(r[58]), "r"(r[59]), "r"(r[60]), "r"(r[61]), "r"(r[62]), "r"(r[63])
+      : "memory");
+}
 VB_DEVICE void tmem_st_32x32_x32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -433,12 +445,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&bars->p_full[s], ph);
         mbar_wait(&bars->v_full[s], ph);
-        if (j >= 1) mbar_wait(&bars->ot_free, (j - 1) & 1);  // O_tile(j-1) folded into the running output
+        if (!X64 && j >= 1) mbar_wait(&bars->ot_free, (j - 1) & 1);  // O_tile(j-1) folded into the running output
         tc_fence_after();
         const uint32_t p = tmem + k2ColP + s * 64;
         const uint64_t vdesc = make_sw128_desc_mn_lbo(smem_u32(sV + s * kATile), kAHalf);
+        // X64 (lazy rescaling): the output accumulates IN TMEM across all key tiles; the softmax warps rescale it in place only
+        // when a row maximum grew by more than 2^8 (p_full(j) is signalled after any such rescale, so it is ordered before PV(j))
 #pragma unroll
-        for (int k = 0; k < kAKV / 16; ++k) umma_bf16_ts(tmem + k2ColOT, p + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, k ? 1u : 0u);
+        for (int k = 0; k < kAKV / 16; ++k) umma_bf16_ts(tmem + k2ColOT, p + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, (X64 ? (j | k) : k) ? 1u : 0u);
         umma_commit(&bars->v_empty[s]);
         umma_commit(&bars->s_free[s]);
         umma_commit(&bars->ot_full);
@@ -496,8 +510,30 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         bars->xmax[j & 1][hf][row] = mx;
         named_bar_sync(1 + qd, 64);
         mx = fmaxf(mx, bars->xmax[j & 1][hf ^ 1][row]);
+        // Lazy rescaling: `m` is the REFERENCE maximum of the row, not necessarily the running one.  It is raised — and the
+        // output accumulator in TMEM rescaled — only when the true maximum exceeds it by more than 8 (a factor 256, far inside
+        // bf16 / fp32 range for P and O); until then P = exp2(s - m) may exceed 1.  The decision is warp-uniform (TMEM loads and
+        // stores are warp-collective) and identical in the partner warp, which sees the same maxima.
         m_new = fmaxf(m, mx * scale_log2);
-        alpha = exp2f(m - m_new);
+        const bool grow = m_new > m + 8.f;
+        alpha = 1.f;
+        if (j == 0) {
+          m = m_new;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          if (grow) {
+            alpha = exp2f(m - m_new);
+            m = m_new;
+          }
+          mbar_wait(&bars->ot_full, (j - 1) & 1);  // PV(j-1) has landed in the accumulator
+          tc_fence_after();
+          uint32_t oo[64];
+          tmem_ld_32x64(tmem + lane_base + k2ColOT + c0, oo);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 64; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+          tmem_st_32x64(tmem + lane_base + k2ColOT + c0, oo);
+        }
+        m_new = m;
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -553,14 +589,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       if (lane == 0) mbar_arrive(&bars->p_full[s]);
       l = l * alpha + rs;
       m = m_new;
-      if (j >= 1) accumulate(j - 1, alpha_pending);
-      alpha_pending = alpha;
+      if (!X64) {
+        if (j >= 1) accumulate(j - 1, alpha_pending);
+        alpha_pending = alpha;
+      }
     };
     for (int j = 0; j < n_tiles; ++j) {
       if (j == qblk) tile(j, std::true_type{});
       else tile(j, std::false_type{});
     }
-    accumulate(n_tiles - 1, alpha_pending);
+    if (X64) accumulate(n_tiles - 1, 0.f);  // o = 0 * 0 + accumulator: the finished output comes out of TMEM once
+    else accumulate(n_tiles - 1, alpha_pending);
 
     // row sum: add the partner's half
     bars->xsum[hf][row] = l;
@@ -660,16 +699,18 @@ struct BwdBars {
   uint64_t kv_full;
   uint64_t q_full[2], q_empty[2];   // Q_i + lse_i + D_i (one stage) ; released when S^T and dK have consumed it
   uint64_t do_full[2], do_empty[2];
-  uint64_t sp_full;                 // S^T and dP^T ready                 (MMA -> softmax)
-  uint64_t pds_full;                // P^T, dS^T (TMEM + smem) written     (softmax -> MMA), count 4
-  uint64_t dq_full;                 // dQ tile ready                        (MMA -> softmax)
-  uint64_t dq_free;                 // dQ tile drained, R0/R1 reusable      (softmax -> MMA), count 4
+  uint64_t s_full;                  // S^T ready                             (MMA -> softmax)
+  uint64_t dp_full;                 // dP^T ready                            (MMA -> softmax)
+  uint64_t p_full;                  // P^T written to TMEM                   (softmax -> MMA), count 8
+  uint64_t ds_full;                 // dS^T written to shared memory         (softmax -> MMA), count 8
+  uint64_t dq_full;                 // dQ tile ready                         (MMA -> softmax)
+  uint64_t dq_free;                 // dQ tile drained, R1 reusable          (softmax -> MMA), count 8
   uint64_t acc_full;                // dK / dV complete                     (MMA -> epilogue)
   uint32_t tmem_holder;
   uint32_t pad;
 };
 
-constexpr uint32_t kR0 = 0, kR1 = 128, kRdV = 256, kRdK = 384, kRdQ = 64;
+constexpr uint32_t kR0 = 0, kR1 = 128, kRdV = 256, kRdK = 384, kRdQ = 128;  // dQ reuses R1 once dP^T has been read
 constexpr int kBwdSmemTiles = 7;  // K, V, Q x2, dO x2, dS^T
 constexpr int kBwdVecBytes = 2 * 2 * 512;  // (lse, D) x 2 stages x 128 floats
 // no slack for manual alignment here (7 tiles + vectors + barriers = 226.1 KB): the dynamic shared memory window is declared
@@ -739,8 +780,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_init(&bars->do_full[s], 1);
       mbar_init(&bars->do_empty[s], 1);
     }
-    mbar_init(&bars->sp_full, 1);
-    mbar_init(&bars->pds_full, 8);
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->dp_full, 1);
+    mbar_init(&bars->p_full, 8);
+    mbar_init(&bars->ds_full, 8);
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_free, 8);
     mbar_init(&bars->acc_full, 1);
@@ -788,45 +831,55 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       constexpr uint32_t idesc_kk = make_idesc_bf16_major(128, 128, false, false);  // both K-major
       constexpr uint32_t idesc_tb = make_idesc_bf16_major(128, 128, false, true);   // A from TMEM (K-major), B MN-major
       constexpr uint32_t idesc_mm = make_idesc_bf16_major(128, 128, true, true);    // A and B MN-major
+      constexpr uint32_t idesc_kb = make_idesc_bf16_major(128, 128, false, true);   // A K-major (smem), B MN-major
       mbar_wait(&bars->kv_full, 0);
+      const uint64_t k_mn = make_sw128_desc_mn_lbo(smem_u32(sK), kAHalf);
+      const uint64_t ds_mn = make_sw128_desc_mn_lbo(smem_u32(sDS), kAHalf);
       for (int t = 0; t < n_iter; ++t) {
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         uint8_t* q = sQ + s * kATile;
         uint8_t* dO = sDO + s * kATile;
+        // ---- S^T = K_j Q_i^T -> R0.  tcgen05.mma executes in issue order, so this may follow dV(t-1) (the reader of P^T(t-1) in
+        // R0) directly: the tensor core starts the next tile's scores while the softmax warps still drain dQ(t-1)
         mbar_wait(&bars->q_full[s], ph);
-        mbar_wait(&bars->do_full[s], ph);
-        if (t >= 1) mbar_wait(&bars->dq_free, (t - 1) & 1);  // R0 / R1 (previous dQ tile) drained by the softmax warps
         tc_fence_after();
-        // S^T = K_j Q_i^T -> R0 ; dP^T = V_j dO_i^T -> R1
 #pragma unroll
         for (int k = 0; k < kAD / 16; ++k) {
           const uint64_t a = make_sw128_desc(smem_u32(sK + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
           const uint64_t bb = make_sw128_desc(smem_u32(q + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
           umma_bf16(tmem + kR0, a, bb, idesc_kk, k ? 1u : 0u);
         }
+        umma_commit(&bars->s_full);
+        // ---- dP^T = V_j dO_i^T -> R1 (holds dQ(t-1) until the softmax warps have drained it)
+        mbar_wait(&bars->do_full[s], ph);
+        if (t >= 1) mbar_wait(&bars->dq_free, (t - 1) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < kAD / 16; ++k) {
           const uint64_t a = make_sw128_desc(smem_u32(sV + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
           const uint64_t bb = make_sw128_desc(smem_u32(dO + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
           umma_bf16(tmem + kR1, a, bb, idesc_kk, k ? 1u : 0u);
         }
-        umma_commit(&bars->sp_full);
-        mbar_wait(&bars->pds_full, t & 1);
+        umma_commit(&bars->dp_full);
+        // ---- dV_j += P^T dO_i : A = P^T (TMEM R0[0,64)), B = dO_i as MN-major [q rows x d]; runs while the softmax warps compute dS
+        mbar_wait(&bars->p_full, t & 1);
         tc_fence_after();
-        // dV_j += P^T dO_i : A = P^T (TMEM R0[0,64)), B = dO_i as MN-major [q rows x d]
         const uint64_t do_mn = make_sw128_desc_mn_lbo(smem_u32(dO), kAHalf);
         const uint64_t q_mn = make_sw128_desc_mn_lbo(smem_u32(q), kAHalf);
-        const uint64_t k_mn = make_sw128_desc_mn_lbo(smem_u32(sK), kAHalf);
-        const uint64_t ds_mn = make_sw128_desc_mn_lbo(smem_u32(sDS), kAHalf);
 #pragma unroll
         for (int k = 0; k < kAQ / 16; ++k) umma_bf16_ts(tmem + kRdV, tmem + kR0 + k * 8, do_mn + (uint64_t)(k * 128), idesc_tb, (t | k) ? 1u : 0u);
         umma_commit(&bars->do_empty[s]);
-        // dK_j += dS^T Q_i : A = dS^T (TMEM R1[64,128)), B = Q_i as MN-major
+        // ---- dK_j += dS^T Q_i : A = dS^T from shared memory, K-major ([key rows x query cols]: rows = M, queries = K); B = Q_i MN-major
+        mbar_wait(&bars->ds_full, t & 1);
+        tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < kAQ / 16; ++k) umma_bf16_ts(tmem + kRdK, tmem + kR1 + 64 + k * 8, q_mn + (uint64_t)(k * 128), idesc_tb, (t | k) ? 1u : 0u);
+        for (int k = 0; k < kAQ / 16; ++k) {
+          const uint64_t a = make_sw128_desc(smem_u32(sDS + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem + kRdK, a, q_mn + (uint64_t)(k * 128), idesc_kb, (t | k) ? 1u : 0u);
+        }
         umma_commit(&bars->q_empty[s]);
-        // dQ_i = dS K_j : A = dS^T in smem read MN-major ([key rows x query cols] -> A[q][key]), B = K_j MN-major
+        // ---- dQ_i = dS K_j -> R1 : A = the same dS^T tile read MN-major (A[q][key]), B = K_j MN-major
 #pragma unroll
         for (int k = 0; k < kAKV / 16; ++k) umma_bf16(tmem + kRdQ, ds_mn + (uint64_t)(k * 128), k_mn + (uint64_t)(k * 128), idesc_mm, k ? 1u : 0u);
         umma_commit(&bars->dq_full);
@@ -850,34 +903,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int h = kvh * G + g;
       const float4* vl4 = reinterpret_cast<const float4*>(sVec + s * 256 + c0);        // lse * log2(e)
       const float4* vd4 = reinterpret_cast<const float4*>(sVec + s * 256 + 128 + c0);  // D
-      mbar_wait(&bars->sp_full, t & 1);
+      mbar_wait(&bars->s_full, t & 1);
       tc_fence_after();
       float p[64];
       uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem + lane_base + kR0 + c0 + c * 32, r);
+      {
+        uint32_t r[64];
+        tmem_ld_32x64(tmem + lane_base + kR0 + c0, r);  // one TMEM round trip for the thread's 64 scores
         tmem_ld_wait();
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const float4 l4 = vl4[c * 8 + w];
+        for (int w = 0; w < 16; ++w) {
+          const float4 l4 = vl4[w];
           const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int q = c * 32 + 4 * w + e;
-            float v = exp2f(__uint_as_float(r[4 * w + e]) * scale_log2 - lv[e]);
+            const int q = 4 * w + e;
+            float v = exp2f(__uint_as_float(r[q]) * scale_log2 - lv[e]);
             if (DIAG && row > c0 + q) v = 0.f;  // key `row` is visible to query q iff row <= q
             p[q] = v;
           }
         }
-#pragma unroll
-        for (int w = 0; w < 16; ++w) pk[c * 16 + w] = pack_bf16x2(p[c * 32 + 2 * w], p[c * 32 + 2 * w + 1]);
       }
+#pragma unroll
+      for (int w = 0; w < 32; ++w) pk[w] = pack_bf16x2(p[2 * w], p[2 * w + 1]);
       // P^T (bf16) overwrites S^T columns [0,64) of the row: the partner thread must have finished READING its half first
       named_bar_sync(1 + qd, 64);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_st_32x32_x16(tmem + lane_base + kR0 + hf * 32 + c * 16, pk + c * 16);
+      tmem_st_32x32_x32(tmem + lane_base + kR0 + hf * 32, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full);  // the dV product starts now, under the dS computation below
+      mbar_wait(&bars->dp_full, t & 1);
+      tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
@@ -894,21 +951,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           pk[c * 16 + 2 * w + 1] = pack_bf16x2(ds4[2], ds4[3]);
         }
       }
-      named_bar_sync(1 + qd, 64);  // dS^T overwrites dP^T columns [64,128): same rule
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_st_32x32_x16(tmem + lane_base + kR1 + 64 + hf * 32 + c * 16, pk + c * 16);
       if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dQ reduce no longer reads this warp's slice of the tile
       __syncwarp();
-      {  // the same dS^T half-row into shared memory (box `hf` of the [128 keys x 128 queries] tile, 128B swizzle)
+      {  // dS^T half-row into shared memory (box `hf` of the [128 keys x 128 queries] tile, 128B swizzle): operand of dK and dQ
         const uint32_t base = smem_u32(sDS + hf * kAHalf) + row * 128;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) st_shared_v4(base + (((uint32_t)jj ^ ((uint32_t)row & 7u)) << 4), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
       }
-      tmem_st_wait();
       fence_proxy_async();
-      tc_fence_before();
+      tc_fence_before();  // the dP^T reads above are ordered before the dQ product that overwrites R1
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->pds_full);
+      if (lane == 0) mbar_arrive(&bars->ds_full);
       // ---- drain dQ_i (lanes = queries of block i, columns = head dim: this thread's half) into the fp32 accumulator.
       // 16K scalar reductions per tile from the SMs saturated the L2 atomic units (the first version spent most of its time
       // here); instead each warp stages its [32 queries x 32 dims] fp32 block in shared memory — the 4 KB slice of the dS^T
