@@ -78,25 +78,44 @@ def main():
     model = GPT().to(dev)
     over = {"parameter": {r"h\.\d+\.c_proj2\.weight": [Shard(1)], r"wpe\.weight": [Replicate()]},
             "forward": {r"input": [[Replicate()]], r"h\.\d+\.attn\.input": [[Replicate()]], r"h\.\d+\.c_fc\.input": [[Replicate()]], r"ln_f\.input": [[Replicate()]], r"wte\.output": [[Replicate()]], r"h\.\d+\.ln_\d\.input": [[Replicate()]]}}
-    auto_parallelize_module(model, VESCALE_DEVICE_MESH["TP"], "MEGATRON", plan_override=over, factory=True)
-    ddp = DDP(model, VESCALE_DEVICE_MESH.get_data_parallel_group(), overlap_grad_reduce=True)
-    opt = BasicOptimizer(torch.optim.AdamW(model.parameters(), lr=1e-3), [ddp], clip_grad=1.0)
-    g = torch.Generator().manual_seed(VESCALE_DEVICE_MESH.get_data_parallel_rank())
-    for step in range(args.steps):
+    def build():
+        torch.manual_seed(0)
+        m = GPT().to(dev)
+        auto_parallelize_module(m, VESCALE_DEVICE_MESH["TP"], "MEGATRON", plan_override=over, factory=True)
+        d = DDP(m, VESCALE_DEVICE_MESH.get_data_parallel_group(), overlap_grad_reduce=True)
+        o = BasicOptimizer(torch.optim.AdamW(m.parameters(), lr=1e-3), [d], clip_grad=1.0)
+        return m, d, o
+
+    def train_step(d, o, step):
+        g = torch.Generator().manual_seed(1000 * step + VESCALE_DEVICE_MESH.get_data_parallel_rank())
         ids = torch.randint(0, 512, (4, 33), generator=g).to(dev)
-        opt.zero_grad()
-        logits = ddp(ids[:, :-1])
+        o.zero_grad()
+        logits = d(ids[:, :-1])
         loss = F.cross_entropy(logits.full_tensor().view(-1, 512), ids[:, 1:].reshape(-1))
         loss.backward()
-        opt.step()
+        o.step()
+        return loss.item()
+
+    del model
+    model, ddp, opt = build()
+    for step in range(args.steps):
+        loss = train_step(ddp, opt, step)
         if dist.get_rank() == 0:
-            print(f"step {step} loss {loss.item():.4f}")
+            print(f"step {step} loss {loss:.4f}")
+    # ---- checkpoint (model + optimizer, asynchronous: pinned staging + worker processes), then RESUME into a fresh model /
+    # optimizer and check that training continues exactly where it stopped (reference: finetune_4D.py:355,390 save / load)
     box = [tempfile.mkdtemp() if dist.get_rank() == 0 else None]
     dist.broadcast_object_list(box, 0)
-    ckpt.save(box[0], {"model": model})
-    ckpt.load(box[0], {"model": model})
+    ckpt.save(box[0], {"model": model, "optimizer": opt}, async_checkpoint=True)
+    ckpt.wait_for_async()
+    cont = train_step(ddp, opt, args.steps)  # the original run, one step further
+    model2, ddp2, opt2 = build()  # fresh weights and optimizer state ...
+    train_step(ddp2, opt2, 12345)  # ... moved away from the initial state, so a silent no-op load would be caught
+    ckpt.load(box[0], {"model": model2, "optimizer": opt2})
+    resumed = train_step(ddp2, opt2, args.steps)
+    assert abs(resumed - cont) < 1e-5, (resumed, cont)
     if dist.get_rank() == 0:
-        print("checkpoint round trip ok:", box[0])
+        print(f"checkpoint resume ok: next-step loss {resumed:.6f} == {cont:.6f} ({box[0]})")
     dist.destroy_process_group()
 
 
