@@ -20,6 +20,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda.h>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -706,6 +707,7 @@ struct BwdBars {
   uint64_t dq_full;                 // dQ tile ready                         (MMA -> softmax)
   uint64_t dq_free;                 // dQ tile drained, R1 reusable          (softmax -> MMA), count 8
   uint64_t acc_full;                // dK / dV complete                     (MMA -> epilogue)
+  uint64_t stage_free;              // attn_bwd2: dQ reduces have read the staging slices (drain -> softmax), count 4
   uint32_t tmem_holder;
   uint32_t pad;
 };
@@ -1032,6 +1034,344 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// attn_bwd2_kernel: the same algorithm and memory layout as attn_bwd_kernel with the critical chain of one (key tile, query
+// block) pair shortened.  ncu on the first kernel: tensor pipe < 40 %, the eight softmax warps do P, dS AND the dQ drain one
+// after the other and then sit idle while dK / dQ / the next S^T run.  Changes:
+//   * a fourth warpgroup (w12-15) owns the dQ drain (TMEM -> shared staging -> TMA reduce-add), so the softmax warps go straight
+//     from dS(t) to P(t+1);
+//   * the MMA issue order is software-pipelined: S^T(t+1) is issued right after dV(t), BEFORE waiting for dS(t), so the scores of
+//     the next pair are ready when the softmax warps come back;
+//   * P^T is stored in the thread's OWN column range of R0 (half 0 -> cols [0,32), half 1 -> cols [64,96)): no partner thread
+//     reads those columns, which removes the named barrier between the S^T read and the P^T store;
+//   * 512 threads, registers re-balanced with setmaxnreg (TMA/MMA group 80, drain group 96, softmax groups 168).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBwd2Threads = 512;
+template <int N>
+VB_DEVICE void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+VB_DEVICE void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+__global__ void __launch_bounds__(kBwd2Threads, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv,
+                 const __grid_constant__ CUtensorMap tm_dq, const float* __restrict__ lse, const float* __restrict__ dvec, int B, int S, int Hq, int Hkv, float scale_log2, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem_bwd[];
+  uint8_t* smem = smem_bwd;
+  if (smem_u32(smem) & 1023u) {
+    if (threadIdx.x == 0) printf("[vescale_b200] attn_bwd2_kernel: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
+    __trap();
+  }
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kATile;
+  uint8_t* sQ = smem + 2 * kATile;   // 2 stages
+  uint8_t* sDO = smem + 4 * kATile;  // 2 stages
+  uint8_t* sDS = smem + 6 * kATile;
+  float* sVec = reinterpret_cast<float*>(smem + 7 * kATile);  // [stage][lse 128 | D 128]
+  BwdBars* bars = reinterpret_cast<BwdBars*>(smem + 7 * kATile + kBwdVecBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = Hq / Hkv, nq = S / kAQ;
+  int idx = blockIdx.x;
+  const int j = idx % nq;
+  idx /= nq;
+  const int kvh = idx % Hkv, b = idx / Hkv;
+  const int n_i = nq - j;
+  const int n_iter = G * n_i;
+  const int krow = b * S + j * kAKV;
+  const int col_k = (Hq + kvh) * kAD, col_v = (Hq + Hkv + kvh) * kAD;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_do);
+    prefetch_tmap(&tm_dqkv);
+    prefetch_tmap(&tm_dq);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bars->kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->q_full[s], 1);
+      mbar_init(&bars->q_empty[s], 1);
+      mbar_init(&bars->do_full[s], 1);
+      mbar_init(&bars->do_empty[s], 1);
+    }
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->dp_full, 1);
+    mbar_init(&bars->p_full, 8);
+    mbar_init(&bars->ds_full, 8);
+    mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dq_free, 4);
+    mbar_init(&bars->acc_full, 1);
+    mbar_init(&bars->stage_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_holder;
+
+  if (warp < 4) {
+    reg_dec<80>();
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(&bars->kv_full, 2 * kATile);
+      tma_load_2d(sK, &tm_qkv, &bars->kv_full, col_k, krow);
+      tma_load_2d(sK + kAHalf, &tm_qkv, &bars->kv_full, col_k + 64, krow);
+      tma_load_2d(sV, &tm_qkv, &bars->kv_full, col_v, krow);
+      tma_load_2d(sV + kAHalf, &tm_qkv, &bars->kv_full, col_v + 64, krow);
+      for (int t = 0; t < n_iter; ++t) {
+        const int s = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        const int g = t / n_i, i = j + t % n_i;
+        const int h = kvh * G + g;
+        const int qrow = b * S + i * kAQ;
+        const size_t vec_off = ((size_t)b * Hq + h) * S + (size_t)i * kAQ;
+        mbar_wait(&bars->q_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->q_full[s], kATile + 1024);
+        tma_load_2d(sQ + s * kATile, &tm_qkv, &bars->q_full[s], h * kAD, qrow);
+        tma_load_2d(sQ + s * kATile + kAHalf, &tm_qkv, &bars->q_full[s], h * kAD + 64, qrow);
+        bulk_load_1d(sVec + s * 256, lse + vec_off, 512, &bars->q_full[s]);
+        bulk_load_1d(sVec + s * 256 + 128, dvec + vec_off, 512, &bars->q_full[s]);
+        mbar_wait(&bars->do_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->do_full[s], kATile);
+        tma_load_2d(sDO + s * kATile, &tm_do, &bars->do_full[s], h * kAD, qrow);
+        tma_load_2d(sDO + s * kATile + kAHalf, &tm_do, &bars->do_full[s], h * kAD + 64, qrow);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer (software-pipelined: S^T(t+1) goes out before dS(t) is waited for) =====================
+      constexpr uint32_t idesc_kk = make_idesc_bf16_major(128, 128, false, false);
+      constexpr uint32_t idesc_tb = make_idesc_bf16_major(128, 128, false, true);
+      constexpr uint32_t idesc_mm = make_idesc_bf16_major(128, 128, true, true);
+      constexpr uint32_t idesc_kb = make_idesc_bf16_major(128, 128, false, true);
+      mbar_wait(&bars->kv_full, 0);
+      const uint64_t k_mn = make_sw128_desc_mn_lbo(smem_u32(sK), kAHalf);
+      const uint64_t ds_mn = make_sw128_desc_mn_lbo(smem_u32(sDS), kAHalf);
+      auto issue_s = [&](int t) {  // S^T(t) = K_j Q_i^T -> R0
+        const int s = t & 1;
+        uint8_t* q = sQ + s * kATile;
+        mbar_wait(&bars->q_full[s], (t >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kAD / 16; ++k) {
+          const uint64_t a = make_sw128_desc(smem_u32(sK + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          const uint64_t bb = make_sw128_desc(smem_u32(q + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem + kR0, a, bb, idesc_kk, k ? 1u : 0u);
+        }
+        umma_commit(&bars->s_full);
+      };
+      auto issue_dp = [&](int t) {  // dP^T(t) = V_j dO_i^T -> R1 (holds dQ(t-1) until the drain warps have read it)
+        const int s = t & 1;
+        uint8_t* dO = sDO + s * kATile;
+        mbar_wait(&bars->do_full[s], (t >> 1) & 1);
+        if (t >= 1) mbar_wait(&bars->dq_free, (t - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kAD / 16; ++k) {
+          const uint64_t a = make_sw128_desc(smem_u32(sV + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          const uint64_t bb = make_sw128_desc(smem_u32(dO + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem + kR1, a, bb, idesc_kk, k ? 1u : 0u);
+        }
+        umma_commit(&bars->dp_full);
+      };
+      issue_s(0);
+      issue_dp(0);
+      for (int t = 0; t < n_iter; ++t) {
+        const int s = t & 1;
+        uint8_t* q = sQ + s * kATile;
+        uint8_t* dO = sDO + s * kATile;
+        const uint64_t do_mn = make_sw128_desc_mn_lbo(smem_u32(dO), kAHalf);
+        const uint64_t q_mn = make_sw128_desc_mn_lbo(smem_u32(q), kAHalf);
+        // ---- dV_j += P^T dO_i : A = P^T from TMEM (queries 16k..16k+15 -> 8 packed columns at (k / 4) * 64 + (k % 4) * 8)
+        mbar_wait(&bars->p_full, t & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kAQ / 16; ++k)
+          umma_bf16_ts(tmem + kRdV, tmem + kR0 + (uint32_t)((k >> 2) * 64 + (k & 3) * 8), do_mn + (uint64_t)(k * 128), idesc_tb, (t | k) ? 1u : 0u);
+        umma_commit(&bars->do_empty[s]);
+        // ---- next pair's scores: R0 is free (every S^T(t) read precedes p_full; P^T(t) is consumed by the dV product above, in order)
+        if (t + 1 < n_iter) issue_s(t + 1);
+        // ---- dK_j += dS^T Q_i
+        mbar_wait(&bars->ds_full, t & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kAQ / 16; ++k) {
+          const uint64_t a = make_sw128_desc(smem_u32(sDS + (k >> 2) * kAHalf)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem + kRdK, a, q_mn + (uint64_t)(k * 128), idesc_kb, (t | k) ? 1u : 0u);
+        }
+        umma_commit(&bars->q_empty[s]);
+        // ---- dQ_i = dS K_j -> R1
+#pragma unroll
+        for (int k = 0; k < kAKV / 16; ++k) umma_bf16(tmem + kRdQ, ds_mn + (uint64_t)(k * 128), k_mn + (uint64_t)(k * 128), idesc_mm, k ? 1u : 0u);
+        umma_commit(&bars->dq_full);
+        if (t + 1 < n_iter) issue_dp(t + 1);
+      }
+      umma_commit(&bars->acc_full);
+    }
+  } else if (warp >= 12) {
+    // ===================== dQ drain: four warps, one thread per query row, all 128 head-dim columns in four [32 x 32] fp32 blocks.
+    // Each warp stages through its two 4 KB slices of the dS^T tile (dead once the dQ product has completed) and adds every block
+    // to dq_acc with ONE bulk tensor reduce (TMA); stage_free tells the softmax warps when the slices may hold dS^T again.
+    reg_dec<96>();
+    const int qd = warp & 3;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    uint8_t* stage = sDS + qd * 8192;
+    for (int t = 0; t < n_iter; ++t) {
+      const int g = t / n_i, i = j + t % n_i;
+      const int h = kvh * G + g;
+      mbar_wait(&bars->dq_full, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cp = 0; cp < 2; ++cp) {
+        uint32_t r[64];
+        tmem_ld_32x64(tmem + lane_base + kRdQ + cp * 64, r);
+        tmem_ld_wait();
+        if (cp == 1) {  // R1 is free for the next pair's dP^T as soon as the last TMEM read has landed
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bars->dq_free);
+            tma_store_wait_read<0>();  // the two reduces of the first half have finished reading the staging slices
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t base = smem_u32(stage + c * 4096) + lane * 128;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            st_shared_v4(base + (((uint32_t)jj ^ ((uint32_t)lane & 7u)) << 4), r[c * 32 + 4 * jj], r[c * 32 + 4 * jj + 1], r[c * 32 + 4 * jj + 2], r[c * 32 + 4 * jj + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tm_dq, stage, h * kAD + cp * 64, b * S + i * kAQ + qd * 32);
+          tma_reduce_add_2d(&tm_dq, stage + 4096, h * kAD + cp * 64 + 32, b * S + i * kAQ + qd * 32);
+          tma_store_commit();
+        }
+      }
+      if (lane == 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&bars->stage_free);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tma_store_wait<0>();
+  } else {
+    // ===================== softmax / dS: EIGHT warps, two threads per key row (query columns split in halves) =====================
+    reg_inc<168>();
+    const int qd = warp & 3, hf = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
+    const int c0 = hf * 64;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    auto tile = [&](int t, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
+      const int s = t & 1;
+      const float4* vl4 = reinterpret_cast<const float4*>(sVec + s * 256 + c0);        // lse * log2(e)
+      const float4* vd4 = reinterpret_cast<const float4*>(sVec + s * 256 + 128 + c0);  // D
+      mbar_wait(&bars->s_full, t & 1);
+      tc_fence_after();
+      float p[64];
+      uint32_t pk[32];
+      {
+        uint32_t r[64];
+        tmem_ld_32x64(tmem + lane_base + kR0 + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const float4 l4 = vl4[w];
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int q = 4 * w + e;
+            float v = exp2f(__uint_as_float(r[q]) * scale_log2 - lv[e]);
+            if (DIAG && row > c0 + q) v = 0.f;
+            p[q] = v;
+          }
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < 32; ++w) pk[w] = pack_bf16x2(p[2 * w], p[2 * w + 1]);
+      tmem_st_32x32_x32(tmem + lane_base + kR0 + c0, pk);  // own columns: [c0, c0 + 32)
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full);
+      mbar_wait(&bars->dp_full, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_base + kR1 + c0 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float4 d4 = vd4[c * 8 + w];
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          float ds4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ds4[e] = p[c * 32 + 4 * w + e] * (__uint_as_float(r[4 * w + e]) - dv[e]);
+          pk[c * 16 + 2 * w] = pack_bf16x2(ds4[0], ds4[1]);
+          pk[c * 16 + 2 * w + 1] = pack_bf16x2(ds4[2], ds4[3]);
+        }
+      }
+      if (t >= 1) mbar_wait(&bars->stage_free, (t - 1) & 1);  // the previous pair's dQ reduces no longer read the dS^T tile
+      {
+        const uint32_t base = smem_u32(sDS + hf * kAHalf) + row * 128;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) st_shared_v4(base + (((uint32_t)jj ^ ((uint32_t)row & 7u)) << 4), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();  // the dP^T reads above are ordered before the dQ product that overwrites R1
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->ds_full);
+    };
+    for (int t = 0; t < n_iter; ++t) {
+      if (t % n_i == 0) tile(t, std::true_type{});
+      else tile(t, std::false_type{});
+    }
+    // ---- epilogue: dK_j * scale and dV_j -> bf16 -> packed dqkv (the Q / dO rings are dead: reuse sQ as staging)
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t reg = which == 0 ? kRdK : kRdV;
+      const float mul = which == 0 ? scale : 1.f;
+      const int col = which == 0 ? col_k : col_v;
+      float v[64];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_base + reg + c0 + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; ++x) v[cc * 32 + x] = __uint_as_float(r[x]) * mul;
+      }
+      uint8_t* buf = sQ + ((warp - 4) * 2 + which) * 4096;
+      epi_write_row_swizzled(buf, lane, v);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tm_dqkv, buf, col + c0, krow + qd * 32);
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // D[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d] (fp32) ; dq_acc zeroed.  One warp per (b, s, h) row of 128 elements.
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
                                                             float* __restrict__ dvec, float* __restrict__ lse2, float* __restrict__ dq_acc, int B, int S, int Hq) {
@@ -1100,11 +1440,21 @@ void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& do
   static bool attr = false;
   if (!attr) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
     attr = true;
   }
   const int grid = (int)(B * n_kv * (S / kAQ));
-  attn_bwd_kernel<<<grid, kA2Threads, kAttnBwdSmem, stream>>>(tq, tdo, tdqkv, tdq, lse2, dvec.data_ptr<float>(), dq_acc.data_ptr<float>(), (int)B, (int)S,
-                                                            (int)n_q, (int)n_kv, (float)(softmax_scale * 1.4426950408889634), (float)softmax_scale);
+  static const int bwd_variant = [] {
+    const char* e = std::getenv("VESCALE_B200_ATTN_BWD");
+    return e ? std::atoi(e) : 1;  // 2 = attn_bwd2_kernel
+  }();
+  if (bwd_variant == 1) {
+    attn_bwd_kernel<<<grid, kA2Threads, kAttnBwdSmem, stream>>>(tq, tdo, tdqkv, tdq, lse2, dvec.data_ptr<float>(), dq_acc.data_ptr<float>(), (int)B, (int)S,
+                                                              (int)n_q, (int)n_kv, (float)(softmax_scale * 1.4426950408889634), (float)softmax_scale);
+  } else {
+    attn_bwd2_kernel<<<grid, kBwd2Threads, kAttnBwdSmem, stream>>>(tq, tdo, tdqkv, tdq, lse2, dvec.data_ptr<float>(), (int)B, (int)S, (int)n_q, (int)n_kv,
+                                                                 (float)(softmax_scale * 1.4426950408889634), (float)softmax_scale);
+  }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   attn_bwd_dq_kernel<<<sms * 4, 256, 0, stream>>>(dq_acc.data_ptr<float>(), (__nv_bfloat16*)dqkv.data_ptr(), B * S, (int)(n_q * kAD), (int)C, (float)softmax_scale);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
