@@ -21,11 +21,23 @@ def _worker(rank, world_size, fn, init_file, backend, args):
     try:
         if backend == "nccl":
             torch.cuda.set_device(rank)
+            # a rank that is still inside the test after this long prints where it is (a spin in a kernel, a collective a failed
+            # peer never joined); the per-test pytest timeout then shows it with the captured output
+            import faulthandler
+
+            faulthandler.dump_traceback_later(int(os.environ.get("VESCALE_TEST_HANG_DUMP_S", "150")), exit=False)
         dist.init_process_group(backend, init_method=f"file://{init_file}", rank=rank, world_size=world_size)
         fn(rank, world_size, *args)
         dist.barrier()
     except Exception:
         traceback.print_exc()
+        if backend == "nccl":
+            # Do NOT tear the NCCL group down after a failure: the peers are blocked in (or about to enter) a collective this rank
+            # will never join, and destroy_process_group() would wait for them — the failure would turn into a hang of all ranks.
+            # Exiting makes mp.spawn see the failure and terminate the peers.
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(1)
         raise
     finally:
         if dist.is_initialized():

@@ -115,15 +115,17 @@ def _fsdp_backends(rank, world):
         assert rel < 2e-3, (a, b, rel.item())
 
 
+@pytest.mark.timeout(240)
 def test_symm_collectives_match_nccl():
     run_distributed(_collectives, min(torch.cuda.device_count(), 8), backend="nccl")
 
 
+@pytest.mark.timeout(300)
 def test_fsdp_symm_matches_nccl():
     run_distributed(_fsdp_backends, min(torch.cuda.device_count(), 8), backend="nccl")
 
 
-def _fused_tp(rank, world):
+def _fused_tp_setup(rank, world):
     from vescale_b200 import init_device_mesh
     from vescale_b200.comm.fused_tp import FusedTP
     from vescale_b200.ops import _ext
@@ -131,8 +133,11 @@ def _fused_tp(rank, world):
     _ext.load(required=True)
     dev = torch.device("cuda", rank)
     mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("TP",))
-    tp = FusedTP(mesh, "TP", dev)
-    g = torch.Generator(device=dev)
+    return FusedTP(mesh, "TP", dev), dev, torch.Generator(device=dev)
+
+
+def _fused_tp_ag(rank, world):
+    tp, dev, g = _fused_tp_setup(rank, world)
     for (Ml, K, Nr) in ((256, 512, 256), (1024, 4096, 3072 // world * 2), (512, 1024, 264)):
         M = Ml * world
         for it in range(3):
@@ -147,6 +152,12 @@ def _fused_tp(rank, world):
             assert torch.equal(x_full, torch.cat(xs)), f"ag_gemm gathered buffer mismatch {Ml,K,Nr} it{it}"
             err = (y.float() - ref).abs().max().item()
             assert err < 0.02 * ref.abs().max().item() + 0.05, ("ag_gemm", Ml, K, Nr, it, err)
+        if rank == 0:
+            print(f"[fused_tp] ag_gemm {Ml, K, Nr} ok", flush=True)
+
+
+def _fused_tp_rs(rank, world):
+    tp, dev, g = _fused_tp_setup(rank, world)
     for (M, Kr, N) in ((256 * world, 512, 256), (2048 * world // 2, 2048, 4096), (512 * world, 1024, 264)):
         for it in range(3):
             g.manual_seed(77 * it + rank)
@@ -161,9 +172,13 @@ def _fused_tp(rank, world):
             err = (y.float() - ref).abs().max().item()
             assert err < 0.03 * ref.abs().max().item() + 0.05, ("gemm_rs", M, Kr, N, it, err)
             dist.barrier()
-    # autograd: column-parallel then row-parallel MLP under SP equals the single-device MLP
-    if rank == 0:
-        print("[fused_tp] kernels ok; autograd section", flush=True)
+        if rank == 0:
+            print(f"[fused_tp] gemm_rs {M, Kr, N} ok", flush=True)
+
+
+def _fused_tp_autograd(rank, world):
+    # column-parallel then row-parallel MLP under SP equals the single-device MLP
+    tp, dev, g = _fused_tp_setup(rank, world)
     H, F, Ml = 512, 1024, 256
     g.manual_seed(5)
     w1 = (torch.randn(F, H, device=dev, generator=g) * 0.05).bfloat16()
@@ -192,8 +207,19 @@ def _fused_tp(rank, world):
     assert (w1s.grad.float() - w1f.grad[rank * F // world : (rank + 1) * F // world]).abs().max().item() < 0.08 * w1f.grad.abs().max().item() + 0.05
 
 
-def test_fused_tp_kernels():
-    run_distributed(_fused_tp, min(torch.cuda.device_count(), 8), backend="nccl")
+@pytest.mark.timeout(240)
+def test_fused_tp_ag_gemm():
+    run_distributed(_fused_tp_ag, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+@pytest.mark.timeout(240)
+def test_fused_tp_gemm_rs():
+    run_distributed(_fused_tp_rs, min(torch.cuda.device_count(), 8), backend="nccl")
+
+
+@pytest.mark.timeout(240)
+def test_fused_tp_autograd():
+    run_distributed(_fused_tp_autograd, min(torch.cuda.device_count(), 8), backend="nccl")
 
 
 def _symm_moe(rank, world):

@@ -106,6 +106,7 @@ class FSDPState:
         # by two timing events; their elapsed time is the stall (≈ 0 when the collective had already finished)
         self.measure_exposed = False
         self._exposed_events: List[Tuple[Any, Any]] = []
+        self._event_pool: List[Tuple[Any, Any]] = []  # pre-created timing events (prepare_exposed_measure)
 
     # ------------------------------------------------------------------ exposed communication
     def wait_comm_event(self, event) -> None:
@@ -116,11 +117,30 @@ class FSDPState:
         if not self.measure_exposed:
             s.wait_event(event)
             return
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pool = self._event_pool
+        if pool:
+            a, b = pool.pop()
+        else:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(s)
         s.wait_event(event)
         b.record(s)
         self._exposed_events.append((a, b))
+
+    def prepare_exposed_measure(self, n_pairs: int) -> None:
+        """Create ``n_pairs`` timing-event pairs NOW and record each once, so that a measured region never creates a CUDA event.
+        ``cudaEventCreate`` is lazy in torch (first ``record``) and the driver grows its event pools in chunks; with peer access
+        enabled between all GPUs of a node a pool growth maps new memory into every peer and synchronises the device.  That was
+        the one-step stall (150-330 ms, always the SECOND measured step, only while ``measure_exposed`` was on) in the round-1 and
+        early round-2 bench records: the host blocked in the driver until the GPU drained, then had to re-fill the launch queue."""
+        if not self.cuda:
+            return
+        s = self.cur_stream()
+        pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(int(n_pairs))]
+        for x, y in pool:
+            x.record(s)
+            y.record(s)
+        self._event_pool = pool
 
     def exposed_comm_ms(self, reset: bool = True) -> float:
         """Device time the compute stream spent stalled on all-gather / reduce-scatter completion since the last reset
