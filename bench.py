@@ -350,6 +350,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    elif cuda and os.environ.get("VESCALE_B200_CLOCK_SAMPLER", "nvml") == "nvml":
+        sampler._start_nvml()  # the other ranks sample their own GPU in-process too (per-rank diagnostics); never a child process
     waits_per_step = 0
     for i in range(args.warmup):
         if i == args.warmup - 1:  # count the compute-stream waits of one step: the measured region draws its timing events from a pool
@@ -402,7 +404,7 @@ def main():
     by_op = dict(_ext.LAUNCH_COUNTER["by_op"])
     _ext.LAUNCH_COUNTER["enabled"] = False
     sampler.mark_end()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 or getattr(sampler, "nvml", False)) else None
     final_loss = float(last.item()) * tp_size  # TP: the model returns this rank's share (local mean / tp)
 
     # ---- timed region 2: end to end through the public API (pinned H2D of the batch + D2H of the loss every step)
@@ -429,8 +431,18 @@ def main():
         step_device(0)
 
     t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0, mem_gb, exposed_ms], device=dev, dtype=torch.float64)
+    # per-rank diagnostics: the rank whose compute stream never waits for a collective is the straggler the others wait for, and
+    # under the 1 kW power cap the GPUs of one box settle at different SM clocks (the step time of the job is the slowest GPU's)
+    per_rank = torch.tensor([exposed_ms, float((clocks or {}).get("sm_mhz") or 0.0), float((clocks or {}).get("power_w_max") or 0.0)], device=dev, dtype=torch.float64)
+    per_rank_all = [per_rank.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank_all, per_rank)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_rank_diag = {
+        "exposed_comm_ms_per_step": [round(float(x[0]), 2) for x in per_rank_all],
+        "sm_mhz": [float(x[1]) for x in per_rank_all],
+        "power_w_max": [round(float(x[2]), 1) for x in per_rank_all],
+    }
     ms, e2e_ms_max, mem_gb, exposed_ms = t.tolist()
     tokens_per_step = dp_size * B * S
     tps = tokens_per_step * args.steps / (ms / 1e3)
@@ -481,6 +493,7 @@ def main():
         "final_loss": final_loss,
         "step_ms": step_ms,
         "host_enqueue_ms": host_ms,
+        "per_rank": per_rank_diag,
         "gpu_launches": launches,
         "gpu_launches_by_op": by_op,
         "clocks": clocks,

@@ -1416,6 +1416,13 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restric
 }  // namespace
 
 // qkv, out, dout as in attn_fwd; lse [B, Hq, S]; dqkv [B, S, C] bf16 (fully written); scratch: dvec [2, B, Hq, S] fp32 (D | lse*log2e), dq_acc [B, S, Hq*128] fp32
+static int g_attn_bwd_variant = [] {
+  const char* e = std::getenv("VESCALE_B200_ATTN_BWD");
+  return e ? std::atoi(e) : 2;
+}();
+void attn_set_bwd_variant(int64_t v) { g_attn_bwd_variant = (int)v; }
+int64_t attn_get_bwd_variant() { return g_attn_bwd_variant; }
+
 void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse, at::Tensor dqkv, at::Tensor dvec, at::Tensor dq_acc,
               int64_t n_q, int64_t n_kv, double softmax_scale) {
   TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == at::kBFloat16 && qkv.dim() == 3 && qkv.is_contiguous());
@@ -1444,10 +1451,7 @@ void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& do
     attr = true;
   }
   const int grid = (int)(B * n_kv * (S / kAQ));
-  static const int bwd_variant = [] {
-    const char* e = std::getenv("VESCALE_B200_ATTN_BWD");
-    return e ? std::atoi(e) : 1;  // 2 = attn_bwd2_kernel
-  }();
+  const int bwd_variant = g_attn_bwd_variant;  // 2 = attn_bwd2_kernel (default), 1 = attn_bwd_kernel
   if (bwd_variant == 1) {
     attn_bwd_kernel<<<grid, kA2Threads, kAttnBwdSmem, stream>>>(tq, tdo, tdqkv, tdq, lse2, dvec.data_ptr<float>(), dq_acc.data_ptr<float>(), (int)B, (int)S,
                                                               (int)n_q, (int)n_kv, (float)(softmax_scale * 1.4426950408889634), (float)softmax_scale);

@@ -29,6 +29,8 @@ void attn_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& do
               int64_t n_q, int64_t n_kv, double softmax_scale);
 void ragged_norm_partial(const at::Tensor& x, at::Tensor out, int64_t rows, int64_t C, int64_t mode, int64_t p);
 void gemm_set_sched(int64_t mode);
+void attn_set_bwd_variant(int64_t v);
+int64_t attn_get_bwd_variant();
 int64_t gemm_get_sched();
 void symm_signal(std::vector<int64_t> pad_ptrs, int64_t rank, int64_t slot, int64_t epoch);
 void symm_wait(int64_t my_pad, int64_t world, int64_t slot, int64_t epoch);
@@ -114,6 +116,8 @@ TORCH_LIBRARY(vescale_b200, m) {
   m.def("attn_bwd(Tensor qkv, Tensor out, Tensor dout, Tensor lse, Tensor(a!) dqkv, Tensor(b!) dvec, Tensor(c!) dq_acc, int n_q, int n_kv, float softmax_scale) -> ()");
   m.def("ragged_norm_partial(Tensor x, Tensor(a!) out, int rows, int C, int mode, int p) -> ()");
   m.def("gemm_set_sched(int mode) -> ()", &gemm_set_sched);
+  m.def("attn_set_bwd_variant(int v) -> ()", &attn_set_bwd_variant);
+  m.def("attn_get_bwd_variant() -> int", &attn_get_bwd_variant);
   m.def("gemm_get_sched() -> int", &gemm_get_sched);
   m.def("symm_signal(int[] pad_ptrs, int rank, int slot, int epoch) -> ()", &symm_signal);
   m.def("symm_wait(int my_pad, int world, int slot, int epoch) -> ()", &symm_wait);

@@ -254,8 +254,9 @@ def test_gemm_clc_scheduler_matches_static_schedule():
         ops.gemm_set_sched(0)
 
 
+@pytest.mark.parametrize("bwd_variant", [2, 1])
 @pytest.mark.parametrize("B,S,hq,hk", [(1, 256, 2, 1), (2, 512, 4, 2), (1, 1024, 8, 2)])
-def test_native_flash_attention_matches_fp32_reference(B, S, hq, hk):
+def test_native_flash_attention_matches_fp32_reference(B, S, hq, hk, bwd_variant):
     """Hand-written tcgen05 causal GQA flash attention (csrc/attention_sm100.cu), forward and backward through the packed-qkv
     autograd op, against plain fp32 attention."""
     import math
@@ -270,11 +271,14 @@ def test_native_flash_attention_matches_fp32_reference(B, S, hq, hk):
     qkv = torch.randn(B, S, (hq + 2 * hk) * d, device=dev, generator=g).bfloat16().requires_grad_()
     do = torch.randn(B, S, hq * d, device=dev, generator=g).bfloat16()
     Fn.set_attention_backend("tcgen05")
+    prev = torch.ops.vescale_b200.attn_get_bwd_variant()
+    torch.ops.vescale_b200.attn_set_bwd_variant(bwd_variant)  # 2 = drain-warpgroup kernel (default), 1 = first kernel
     try:
         out = Fn.packed_attention(qkv, hq, hk, d, causal=True)
         out.backward(do)
     finally:
         Fn.set_attention_backend("auto")
+        torch.ops.vescale_b200.attn_set_bwd_variant(prev)
     x = qkv.detach().float().requires_grad_()
     q = x[..., : hq * d].view(B, S, hq, d).transpose(1, 2)
     k = x[..., hq * d : (hq + hk) * d].view(B, S, hk, d).transpose(1, 2).repeat_interleave(hq // hk, 1)

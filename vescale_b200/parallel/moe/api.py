@@ -25,32 +25,78 @@ __all__ = ["parallelize_experts", "ExpertsAllocator", "BasicExpertsAllocator", "
 
 
 class ExpertsAllocator:
-    """expert id -> EP rank(s).  Replicas allow hot experts on several ranks."""
+    """Where the experts of each MoE layer live.  Two levels of contract:
 
-    def __init__(self, num_experts: int, ep_size: int):
+    * the reference's (``legacy/vescale/moe/experts_allocator.py:26-62``): ``allocate_experts(layer_id, iter)`` returns one
+      ``[DP, TP]`` mesh per expert (a DeviceMesh, a tensor or nested lists of EP ranks: ``DP`` replicas, each sharded ``TP`` ways)
+      or ``None`` = keep the current allocation; ``collect_performance(perf, iter)`` receives the loads of every layer run.  Layers
+      built from such an allocator are :class:`~.scheduler.ScheduledMoELayer` s driven by a :class:`~.scheduler.MoEScheduler`;
+    * the simple one: ``allocate()`` returns, per expert, the list of ranks hosting it (whole experts, plain EP).
+
+    The default ``allocate_experts`` lifts ``allocate()`` (each hosting rank = one unsharded replica) the first time a layer asks."""
+
+    def __init__(self, num_experts: Optional[int] = None, ep_size: Optional[int] = None, model_config=None, env_config=None):
         self.num_experts, self.ep_size = num_experts, ep_size
+        self.model_config, self.env_config = model_config, env_config
+        self._visited = set()
 
     def allocate(self) -> List[List[int]]:
         raise NotImplementedError
 
+    def collect_performance(self, perf, iter=-1) -> None:
+        pass
+
+    def allocate_experts(self, layer_id, iter=-1):
+        if layer_id in self._visited:
+            return None
+        self._visited.add(layer_id)
+        return [[[r] for r in ranks] for ranks in self.allocate()]
+
+    def allocate_experts_internal(self, layer_id, iter=-1) -> Optional[Dict]:
+        """``{"experts_alloc", "dp_size", "tp_size"}`` for the dispatcher, or ``None`` when nothing changes."""
+        from .scheduler import ExpertsAllocation
+
+        got = self.allocate_experts(layer_id, iter)
+        if got is None:
+            return None
+        alloc = got if isinstance(got, ExpertsAllocation) else ExpertsAllocation(got, self.ep_size or (dist.get_world_size() if dist.is_initialized() else 1))
+        return alloc.info()
+
 
 class BasicExpertsAllocator(ExpertsAllocator):
+    """Plain expert parallelism: expert ``e`` whole on rank ``e // (E / W)``."""
+
     def allocate(self) -> List[List[int]]:
-        per = self.num_experts // self.ep_size
-        return [[e // per] for e in range(self.num_experts)]
+        per = max(1, self.num_experts // self.ep_size)
+        return [[min(e // per, self.ep_size - 1)] for e in range(self.num_experts)]
 
 
 class TokenDispatcher:
-    def dispatch_token(self, expert_id: torch.Tensor, placement: List[List[int]]) -> torch.Tensor:
+    """Chooses the replica every routed token copy goes to (reference ``token_dispatcher.py:26-70``): the scheduler calls
+    ``set_experts_alloc(info)`` when the allocation changes, ``assign_task(layer_id, token_id, expert_id, hidden_state, token_weight)``
+    with the routed copies of the layer, then ``dispatch_token(layer_id) -> (expert_id, replica_id)``; ``collect_performance`` as
+    for the allocator."""
+
+    def set_experts_alloc(self, experts_alloc_info: Dict) -> None:
+        self.experts_alloc = experts_alloc_info["experts_alloc"]
+        self.num_replicate = experts_alloc_info["dp_size"]
+
+    def assign_task(self, layer_id, token_id, expert_id, hidden_state, token_weight) -> None:
+        self.expert_id, self.token_id = expert_id, token_id
+
+    def collect_performance(self, perf, iter=-1) -> None:
+        pass
+
+    def dispatch_token(self, layer_id: int):
         raise NotImplementedError
 
 
 class BasicTokenDispatcher(TokenDispatcher):
-    """Random replica among the ranks hosting the expert (legacy ``token_dispatcher.py:46``)."""
+    """Uniformly random replica among the ones hosting the expert (legacy ``token_dispatcher.py:46-70``)."""
 
-    def dispatch_token(self, expert_id, placement):
-        table = torch.tensor([p[0] for p in placement], device=expert_id.device)
-        return table[expert_id]
+    def dispatch_token(self, layer_id: int):
+        n = self.num_replicate.to(self.expert_id.device)[self.expert_id]
+        return self.expert_id, torch.randint_like(n, 65535) % n
 
 
 def is_moe(module: nn.Module) -> bool:
@@ -72,6 +118,7 @@ def parallelize_experts(module: nn.Module, experts_expr: str = r".*moe.*", ep_me
     rank = dist.get_rank(group) if group is not None else 0
     from .hijack import hijack_moe_block, is_hijackable
 
+    scheduled: List[nn.Module] = []
     for fqn, sub in list(module.named_modules()):
         if not rx.fullmatch(fqn):
             continue
@@ -85,6 +132,18 @@ def parallelize_experts(module: nn.Module, experts_expr: str = r".*moe.*", ep_me
         if not isinstance(sub, MoELayer) or sub.ep_size == W:
             continue
         cfg = sub.cfg
+        meshes = _reference_shaped_allocation(experts_allocator, len(scheduled), W)
+        if meshes is not None:
+            # per-expert DP x TP meshes (replicated / sharded experts): the layer becomes a ScheduledMoELayer
+            from .scheduler import ExpertsAllocation, ScheduledMoELayer
+
+            alloc_obj = meshes if isinstance(meshes, ExpertsAllocation) else ExpertsAllocation(meshes, W)
+            new = ScheduledMoELayer(cfg, alloc_obj, group, device=sub.router.weight.device, layer_id=len(scheduled))
+            new.router.weight.data.copy_(sub.router.weight.data)
+            new.load_full_experts(sub.experts.w_gate_up.data, sub.experts.w_down.data)
+            _replace_module(module, fqn, new)
+            scheduled.append(new)
+            continue
         alloc = (experts_allocator or BasicExpertsAllocator(cfg.num_experts, W)).allocate()
         new = MoELayer(cfg, group, device=sub.router.weight.device)
         new.router.weight.data.copy_(sub.router.weight.data)
@@ -94,16 +153,35 @@ def parallelize_experts(module: nn.Module, experts_expr: str = r".*moe.*", ep_me
             for le, e in enumerate(mine):
                 new.experts.w_gate_up[le].copy_(sub.experts.w_gate_up[e])
                 new.experts.w_down[le].copy_(sub.experts.w_down[e])
-        parent = module
-        parts = fqn.split(".")
-        for p in parts[:-1]:
-            parent = getattr(parent, p)
-        setattr(parent, parts[-1], new)
+        _replace_module(module, fqn, new)
         for p in new.experts.parameters():
             p._is_expert_param = True
     module._ep_group = group
+    if scheduled:
+        from .scheduler import MoEScheduler
+
+        module._moe_scheduler = MoEScheduler(experts_allocator, token_dispatcher, config, optimizer=(config or {}).get("optimizer")).register(module)
     setattr(module, _TAG_EXPERTS_PARALLELIZED, True)
     return module
+
+
+def _replace_module(root: nn.Module, fqn: str, new: nn.Module) -> None:
+    parent = root
+    parts = fqn.split(".")
+    for p in parts[:-1]:
+        parent = getattr(parent, p)
+    setattr(parent, parts[-1], new)
+
+
+def _reference_shaped_allocation(allocator, layer_id: int, world: int):
+    """The per-expert meshes of a reference-shaped allocator (one that overrides ``allocate_experts``), or ``None`` for the simple
+    ``allocate()`` kind / no allocator."""
+    if allocator is None:
+        return None
+    fn = getattr(type(allocator), "allocate_experts", None)
+    if fn is None or fn is ExpertsAllocator.allocate_experts:
+        return None
+    return allocator.allocate_experts(layer_id, 0)
 
 
 class MoEOptimizer:
