@@ -352,35 +352,44 @@ def main():
         sampler.start()
     elif cuda and os.environ.get("VESCALE_B200_CLOCK_SAMPLER", "nvml") == "nvml":
         sampler._start_nvml()  # the other ranks sample their own GPU in-process too (per-rank diagnostics); never a child process
-    waits_per_step = 0
-    for i in range(args.warmup):
-        if i == args.warmup - 1:  # count the compute-stream waits of one step: the measured region draws its timing events from a pool
-            state.measure_exposed, state._exposed_events = True, []
-        step_device(i)
-        if i == args.warmup - 1:
-            waits_per_step = len(state._exposed_events)
-            state.measure_exposed, state._exposed_events = False, []
-    barrier()
-    mem_gb = torch.cuda.max_memory_allocated() / 2**30 if cuda else 0.0
-    # A generation-2 garbage collection over the ~10^5 live Python objects of the model takes 150-250 ms of host time and showed up
-    # as one slow step in some runs (551 ms in a 400 ms series).  Training loops collect at a point of their
-    # choosing (Megatron's --manual-gc); here: collect now, freeze the survivors, and keep the collector off in the timed regions.
     import gc
 
-    gc.collect()
-    gc.freeze()
-    gc.disable()
-
-    # ---- timed region 1: device-timed.  No CUDA event is CREATED inside it: torch creates events lazily at their first record, and
-    # an event-pool growth in the driver (peer-mapped on a multi-GPU node) synchronises the device — the one-step stall of the earlier
-    # records (always the second timed step).  The exposed-communication events come from a pre-recorded pool, the step marks are
-    # recorded once here.
-    state.prepare_exposed_measure((waits_per_step + 8) * args.steps)
     e0, e1 = Event(enable_timing=True), Event(enable_timing=True)
     marks = [Event(enable_timing=True) for _ in range(args.steps)]
-    if cuda:
-        for ev in [e0, e1] + marks:
-            ev.record()
+
+    def housekeeping(waits_per_step: int) -> None:
+        """Everything slow that has to happen before the timed region, done BEFORE THE LAST WARM-UP STEP so that the GPU goes from a
+        full training step straight into the timed steps.  (a) A generation-2 garbage collection over the ~10^5 live Python objects
+        of the model takes 150-250 ms: collect now, freeze the survivors, keep the collector off in the timed regions (Megatron's
+        --manual-gc).  (b) No CUDA event is CREATED inside the timed region: torch creates events lazily at their first record and an
+        event-pool growth in the driver synchronises the device; the exposed-communication events come from a pre-recorded pool,
+        the step marks are recorded once here.  (c) The GPU must not sit idle right before the region: under the 1 kW cap the power
+        controller lets the first step after an idle gap run fast (390-399 ms against 403-409 steady) and then over-corrects on
+        the second one — the one slow step of the earlier records (464 ms at N=2, 644 ms at N=8, always the SECOND timed step,
+        never in the end-to-end region, which starts without such a gap)."""
+        gc.collect()
+        gc.freeze()
+        gc.disable()
+        state.prepare_exposed_measure((waits_per_step + 8) * args.steps)
+        if cuda:
+            for ev in [e0, e1] + marks:
+                ev.record()
+
+    waits_per_step = 0
+    for i in range(args.warmup):
+        if i == 0:  # count the compute-stream waits of one step: the measured region draws its timing events from a pool
+            state.measure_exposed, state._exposed_events = True, []
+        if i == args.warmup - 1 and i > 0:
+            housekeeping(waits_per_step)
+        step_device(i)
+        if i == 0:
+            waits_per_step = len(state._exposed_events)
+            state.measure_exposed, state._exposed_events = False, []
+    if args.warmup <= 1:
+        housekeeping(waits_per_step)
+    mem_gb = torch.cuda.max_memory_allocated() / 2**30 if cuda else 0.0
+
+    # ---- timed region 1: device-timed (barrier + synchronize on both sides; nothing else between the last warm-up step and it)
     sampler.mark_begin()
     state.measure_exposed = True
     state._exposed_events = []

@@ -11,6 +11,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from ..dtensor.api import DTensor
+from .flat_piece import FlatPiece
 from .pinned_pool import PinnedPool
 
 __all__ = ["save", "load", "VeScaleCheckpointer", "wait_for_async"]
@@ -129,6 +130,8 @@ def _stage_to_host(sd: Dict[str, Any]) -> Dict[str, Any]:
     for k, v in sd.items():
         if isinstance(v, DTensor):
             out[k] = DTensor(_POOL.stage(v._local_tensor), v._spec)
+        elif isinstance(v, FlatPiece):
+            out[k] = v.with_local(_POOL.stage(v._local_tensor))
         elif isinstance(v, torch.Tensor):
             out[k] = _POOL.stage(v)
         else:
@@ -139,7 +142,7 @@ def _stage_to_host(sd: Dict[str, Any]) -> Dict[str, Any]:
 
 def _release(sd: Dict[str, Any]) -> None:
     for v in sd.values():
-        t = v._local_tensor if isinstance(v, DTensor) else v
+        t = v._local_tensor if isinstance(v, (DTensor, FlatPiece)) else v
         if isinstance(t, torch.Tensor) and hasattr(t, "_pool_base"):
             _POOL.release(t)
 
@@ -230,8 +233,8 @@ class VeScaleCheckpointer(BaseCheckpointer):
             if broadcast_checkpoint and dist.is_initialized() and dist.get_world_size() > 1:
                 # replicated (non-DTensor) entries: one rank reads the files, everyone else gets them over the network
                 # (legacy ``storage/filesystem.py:817-865`` read_data_with_broadcast); sharded entries are read by their owners
-                plain = {k: v for k, v in req.items() if not isinstance(v, DTensor)}
-                sharded = {k: v for k, v in req.items() if isinstance(v, DTensor)}
+                plain = {k: v for k, v in req.items() if not isinstance(v, (DTensor, FlatPiece))}
+                sharded = {k: v for k, v in req.items() if isinstance(v, (DTensor, FlatPiece))}
                 if sharded:
                     dcp.load(sharded, **_storage(sub, False))
                 if plain:

@@ -92,7 +92,12 @@ class DistributedOptimizer:
                     lp = _local(p)
                     pbuf[s:e].copy_(lp.detach().reshape(-1))
                     view = pbuf[s:e].view(lp.shape)
-                    if isinstance(p.data, DTensor):
+                    # a DModule parameter IS a DTensor (wrapper subclass): its local shard is re-pointed on the parameter object
+                    # itself — ``p.data`` of a wrapper subclass is a fresh alias object, assigning to it would be lost and the
+                    # optimizer would update a buffer the model never reads
+                    if isinstance(p, DTensor):
+                        p._local_tensor = view
+                    elif isinstance(p.data, DTensor):
                         p.data._local_tensor = view
                     else:
                         p.data = view
@@ -243,23 +248,50 @@ class DistributedOptimizer:
                         spec_of = lambda dtype: DTensorSpec(mesh, (RaggedShard((0,), units),), TensorMeta((numel,), (1,), dtype))  # noqa: E731
                         mine = [mp for mp in self.main_params.get(id(p), [])]
                         fq = names.get(id(p), str(id(p)))
+                        geom = self._model_parallel_geometry(p)
+                        if geom is None:
+                            wrap = lambda t, lo, hi: DTensor(t, spec_of(t.dtype))  # noqa: E731
+                        else:
+                            # the parameter is itself sharded over a model-parallel mesh: this rank's range of the LOCAL shard is
+                            # saved as boxes of the GLOBAL tensor (checkpoint/flat_piece.py) — every (DP, TP) rank writes disjoint
+                            # boxes under one key, reloadable under another DP size, bucket size or TP degree
+                            from ..checkpoint.flat_piece import FlatPiece
+
+                            wrap = lambda t, lo, hi: FlatPiece(t.reshape(-1), geom[0], lo, hi, geom[1], geom[2])  # noqa: E731
                         if mine:
                             mp = mine[0]
                             st = self._ensure_state(mp)
-                            out[f"{fq}.main"] = DTensor(mp.data, spec_of(mp.dtype))
+                            lo, hi = mp._piece
+                            out[f"{fq}.main"] = wrap(mp.data, lo, hi)
                             for k, v in st.items():
                                 if torch.is_tensor(v) and v.numel() == mp.numel() and v.dim() >= 1:
-                                    out[f"{fq}.{k}"] = DTensor(v, spec_of(v.dtype))
+                                    out[f"{fq}.{k}"] = wrap(v, lo, hi)
                                 elif k == "step":
                                     steps[fq] = float(v)
                         elif id(p) in self._opt_param_ids:
                             # this rank owns no element of the parameter: empty local shards keep the key set identical on all ranks
                             ref_dtype = torch.float32
-                            out[f"{fq}.main"] = DTensor(torch.empty(0, dtype=ref_dtype, device=b.data.device), spec_of(ref_dtype))
+                            out[f"{fq}.main"] = wrap(torch.empty(0, dtype=ref_dtype, device=b.data.device), 0, 0)
                             for k in self._state_keys():
-                                out[f"{fq}.{k}"] = DTensor(torch.empty(0, dtype=ref_dtype, device=b.data.device), spec_of(ref_dtype))
+                                out[f"{fq}.{k}"] = wrap(torch.empty(0, dtype=ref_dtype, device=b.data.device), 0, 0)
         out["__steps__"] = steps
         return out
+
+    @staticmethod
+    def _model_parallel_geometry(p):
+        """``(local shape, global shape, global offset of the local shard)`` of a parameter that is a DTensor sharded over a
+        model-parallel mesh, ``None`` for plain / fully replicated parameters (their flat ranges are saved as 1-D RaggedShard
+        DTensors over the DP group).  Layouts whose local shard is not one box of the global tensor (``InterleavedShard``) are not
+        expressible this way and raise."""
+        if not isinstance(p, DTensor) or all(pl.is_replicate() for pl in p.placements):
+            return None
+        from ..layout import local_boxes
+
+        boxes = list(local_boxes(p.shape, p.device_mesh, p.placements))
+        local_shape = tuple(p._local_tensor.shape)
+        if len(boxes) != 1 or tuple(boxes[0][1]) != local_shape:
+            raise NotImplementedError(f"DistributedOptimizer.checkpoint_state: parameter with placements {p.placements} has a local shard that is not one box of the global tensor")
+        return local_shape, tuple(p.shape), tuple(boxes[0][0])
 
     def _state_keys(self):
         name = type(self.optimizer).__name__.lower()
