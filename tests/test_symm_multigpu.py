@@ -547,3 +547,21 @@ def test_emulator_bitwise_equals_live_nccl(monkeypatch):
     for k, v in (("NCCL_ALGO", "Ring"), ("NCCL_PROTO", "Simple"), ("NCCL_MAX_NCHANNELS", "1"), ("NCCL_MIN_NCHANNELS", "1"), ("NCCL_NVLS_ENABLE", "0")):
         monkeypatch.setenv(k, v)
     run_distributed(_emulator_vs_nccl, min(torch.cuda.device_count(), 4), backend="nccl")
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("batch", [False, True])
+def test_pipeline_engine_on_gpus_overlapped_nccl_p2p(batch):
+    """The pipeline engine on real GPUs: 1F1B over NCCL p2p with receives posted ahead (and batched send+recv groups), loss equal to
+    the single-device model, every instruction on the ndtimeline (CUDA-event timers).  Same body as the gloo test."""
+    from test_pipe_dist import _pp_overlap
+
+    run_distributed(_pp_overlap, min(torch.cuda.device_count(), 4), batch, backend="nccl")
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("sched", ["ZERO_BUBBLE", "INTERLEAVED_1F1B"])
+def test_pipeline_schedules_on_gpus(sched):
+    from test_pipe_dist import _pp
+
+    run_distributed(_pp, min(torch.cuda.device_count(), 4) // 2 * 2, sched, "STRUCTURAL", backend="nccl")
