@@ -549,6 +549,15 @@ def test_emulator_bitwise_equals_live_nccl(monkeypatch):
     run_distributed(_emulator_vs_nccl, min(torch.cuda.device_count(), 4), backend="nccl")
 
 
+# Written after this round's GPU budget was spent: these bodies have only ever run on gloo.  A test nobody has seen pass on NCCL is not
+# evidence, so it is opt-in until it has been (VESCALE_B200_RUN_UNVALIDATED_GPU_TESTS=1 on a >= 2 GPU box).
+_unvalidated = pytest.mark.skipif(
+    __import__("os").environ.get("VESCALE_B200_RUN_UNVALIDATED_GPU_TESTS", "0") != "1",
+    reason="never run on NCCL yet (added after the GPU budget was spent); set VESCALE_B200_RUN_UNVALIDATED_GPU_TESTS=1",
+)
+
+
+@_unvalidated
 @pytest.mark.timeout(240)
 @pytest.mark.parametrize("batch", [False, True])
 def test_pipeline_engine_on_gpus_overlapped_nccl_p2p(batch):
@@ -559,6 +568,7 @@ def test_pipeline_engine_on_gpus_overlapped_nccl_p2p(batch):
     run_distributed(_pp_overlap, min(torch.cuda.device_count(), 4), batch, backend="nccl")
 
 
+@_unvalidated
 @pytest.mark.timeout(240)
 @pytest.mark.parametrize("sched", ["ZERO_BUBBLE", "INTERLEAVED_1F1B"])
 def test_pipeline_schedules_on_gpus(sched):
