@@ -76,9 +76,38 @@ def _auto_plan(rank, world):
     x = torch.randn(2, 4, 32, generator=torch.Generator().manual_seed(1)).to(dev)
     y = model(x)
     torch.testing.assert_close(y.full_tensor(), ref(x), rtol=1e-4, atol=1e-5)
+    summary = DebugLogger.summary()
     set_vescale_debug_mode(False)
     if rank == 0:
         assert any("[comm]" in r for r in DebugLogger.records) and any("[op]" in r for r in DebugLogger.records)
+        # ops are attributed to the module whose forward dispatched them, with operand / output specs spelled out
+        assert any("[op] Linear forward()" in r and "in  = [" in r and "Shard(" in r for r in DebugLogger.records), DebugLogger.records[:5]
+        # collectives name the user line that injected them (this file), and the summary aggregates bytes per site
+        assert any("[comm]" in r and "test_aux_components.py:" in r for r in DebugLogger.records)
+        assert "communication by call site" in summary and "MiB" in summary and "Linear.forward" in summary
+    else:
+        assert not DebugLogger.records  # rank filter
+    DebugLogger.reset()
+    # the manual / decorator forms and the environment switch (with a rank list after ':')
+    import os
+
+    os.environ["VESCALE_DEBUG_MODE"] = "1:-1"
+    from vescale_b200.debug import update_vescale_debug_mode_from_env
+
+    assert update_vescale_debug_mode_from_env() and DebugLogger.IS_DEBUG_MODE and DebugLogger.ranks == (-1,)
+
+    @DebugLogger.log_communication_decorator()
+    def my_all_reduce(t, tag=None):
+        return t
+
+    my_all_reduce(torch.ones(4, 2), tag="x")
+    assert any("my_all_reduce(float32[4, 2], tag=x)" in r for r in DebugLogger.records), DebugLogger.records
+    os.environ["VESCALE_DEBUG_MODE"] = "0"
+    assert not update_vescale_debug_mode_from_env() and not DebugLogger.IS_DEBUG_MODE
+    n = len(DebugLogger.records)
+    (model(x)).full_tensor()
+    assert len(DebugLogger.records) == n  # hooks are gone
+    DebugLogger.reset()
 
 
 def test_auto_plan_devicemesh_debuglog():

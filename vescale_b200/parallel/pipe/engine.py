@@ -91,11 +91,14 @@ class ScheduleEngine:
         pending_w: Dict[Tuple[int, int], Tuple] = {}
         losses: List[Optional[torch.Tensor]] = [None] * M
         outputs: List = [None] * M
+        timing = self._timing
         for ins in rows[self.rank]:
             h = INSTRUCTION_REGISTRY.get(ins.kind)
             if h is not None and h(self, ins) is not None:
                 continue
             m, v, c = ins.microbatch, ins.vstage, ins.chunk
+            if timing is not None:
+                self._tick(timing, ins.kind)
             if ins.kind == "F":
                 if v == 0:
                     xs = _as_tuple(inputs[m])
@@ -154,8 +157,26 @@ class ScheduleEngine:
                     if g is not None:
                         p.grad = g if p.grad is None else p.grad + g
                 del acts[(m, v)]
+        if timing is not None:
+            self._tick(timing, None)
         p2p.drain()
         return losses, outputs
+
+    # ---- cost calibration (feeds the cost-driven schedule search, auto_schedule.py)
+    _timing: Optional[Dict] = None
+
+    def _tick(self, timing: Dict, kind: Optional[str]) -> None:
+        """Close the running instruction's interval and open one for ``kind``.  Intervals include the p2p waits in front of the
+        compute of an instruction on purpose: a schedule is better when what it measures shrinks."""
+        import time
+
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        now = time.perf_counter()
+        if timing.get("open") is not None:
+            k0, t0 = timing["open"]
+            timing.setdefault(k0, []).append(now - t0)
+        timing["open"] = None if kind is None else (kind, now)
 
 
 class PipeEngine:
@@ -197,6 +218,41 @@ class PipeEngine:
         return loss, outputs
 
     __call__ = forward_backward
+
+    def calibrate(self, minibatch, labels=None, num_microbatches: Optional[int] = None, comm: Optional[float] = None, warmup: int = 1, search: bool = True):
+        """Measure F / B / W on this pipeline (median per instruction kind, MAX over the pipeline ranks, normalised so that F = 1),
+        store them in ``plan.costs`` and — with ``search`` — switch the plan to the cost-driven schedule search for the following
+        mini-batches (``plan.auto_schedule``; legacy ``zero_bubble_v.py:198-600`` takes the same four costs as constructor arguments
+        and leaves measuring them to the user).  ``comm`` (same unit: multiples of one F) is taken as given; gradients produced by
+        the calibration mini-batches are discarded.  Returns the cost dict."""
+        import statistics
+
+        import torch.distributed as dist
+
+        se = self.schedule_engine
+        for _ in range(max(0, warmup)):
+            self.forward_backward(minibatch, labels, num_microbatches=num_microbatches)
+        se._timing = {}
+        try:
+            self.forward_backward(minibatch, labels, num_microbatches=num_microbatches)
+            t = se._timing
+        finally:
+            se._timing = None
+        self.zero_grad()
+        med = torch.tensor([statistics.median(t[k]) if t.get(k) else 0.0 for k in ("F", "B", "W")], dtype=torch.float64)
+        if self.pp_group is not None and dist.is_initialized():
+            med = med.to(self.device) if dist.get_backend(self.pp_group) == "nccl" else med
+            dist.all_reduce(med, op=dist.ReduceOp.MAX, group=self.pp_group)
+            med = med.cpu()
+        f = float(med[0]) or 1.0
+        costs = {"F": 1.0, "B": float(med[1]) / f, "W": float(med[2]) / f if se.split_w else 0.0, "comm": float(comm if comm is not None else self.plan.costs.get("comm", 0.0))}
+        if not se.split_w:
+            costs["B"], costs["W"] = costs["B"], 0.0  # un-split backward: all of it is measured as B
+        self.plan.costs = costs
+        self.plan.auto_schedule = bool(search)
+        se._sched_cache.clear()
+        self.measured_seconds = {"F": float(med[0]), "B": float(med[1]), "W": float(med[2])}
+        return costs
 
     def sync_shared_params(self, share_params: bool = True):
         self.module.sync_shared_params(share_params)

@@ -61,6 +61,10 @@ class PipelineParallelPlan:
     shared_modules: List[List[str]] = field(default_factory=list)  # groups of parameter fqns tied across stages
     costs: Dict[str, float] = field(default_factory=lambda: {"F": 1.0, "B": 1.0, "W": 1.0, "comm": 0.0})
     max_inflight: Optional[int] = None
+    # cost-driven schedule search (auto_schedule.py; legacy zero_bubble_v.py:198-600): activation-memory model per op kind and bound
+    auto_schedule: bool = False
+    mem_costs: Dict[str, float] = field(default_factory=lambda: {"F": 1.0, "B": -0.5, "W": -0.5})
+    max_mem: Optional[float] = None  # in units of mem_costs; None = the schedule type's classic in-flight rule only
     forward_only: bool = False
     uniform_split_ops: bool = False
 

@@ -23,7 +23,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 from .plan import PipelineParallelPlan, PipelineScheduleType
 
-__all__ = ["Instr", "build_schedule", "stage_placement", "register_instruction", "INSTRUCTION_REGISTRY", "StageDeps"]
+__all__ = ["Instr", "build_schedule", "stage_placement", "register_instruction", "INSTRUCTION_REGISTRY", "StageDeps", "ScheduleKnobs", "peak_memory", "makespan", "bubble_fraction"]
 
 
 @dataclass(frozen=True)
@@ -92,7 +92,45 @@ def validate_pipeline_schedule(plan: PipelineParallelPlan) -> None:
         raise ValueError("num_stages and virtual_chunks must be positive")
 
 
-def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[List[Instr]]:
+@dataclass(frozen=True)
+class ScheduleKnobs:
+    """Free choices of the list scheduler that the cost-driven search (``auto_schedule.search_schedule``) enumerates; the defaults are
+    the classic schedules.  ``prio``: rank of each op kind when several are ready (lower first).  ``inflight``: forwards a rank may
+    hold before their backward ran (None = the schedule type's rule).  ``deep_first``: among ready forwards prefer the deeper chunk
+    (drains a V / interleave) or the shallower one (fills the pipeline sooner).  ``mem`` / ``max_mem``: activation-memory model —
+    an F adds ``mem["F"]``, a B adds ``mem["B"]`` (negative: it frees what only the input gradient needed), a W adds ``mem["W"]``
+    (negative: the rest); an F is not started while it would push the rank above ``max_mem``.  ``w_when_blocked``: run a ready W
+    ahead of forwards whenever the memory bound (not a dependency) is what blocks the next F."""
+
+    prio: Optional[Tuple[Tuple[str, int], ...]] = None
+    inflight: Optional[int] = None
+    deep_first: bool = True
+    mem: Optional[Tuple[Tuple[str, float], ...]] = None
+    max_mem: Optional[float] = None
+    w_when_blocked: bool = True
+
+
+def peak_memory(rows: List[List[Instr]], mem: Dict[str, float]) -> List[float]:
+    """Per-rank peak of the activation-memory model along the rank's instruction order."""
+    out = []
+    for row in rows:
+        cur = peak = 0.0
+        for ins in row:
+            cur += mem.get(ins.kind, 0.0)
+            peak = max(peak, cur)
+        out.append(peak)
+    return out
+
+
+def makespan(rows: List[List[Instr]]) -> float:
+    return max((r[-1].end for r in rows if r), default=0.0)
+
+
+def build_schedule(plan: PipelineParallelPlan, num_microbatches: int, knobs: Optional[ScheduleKnobs] = None) -> List[List[Instr]]:
+    if knobs is None and getattr(plan, "auto_schedule", False):
+        from .auto_schedule import search_schedule
+
+        return search_schedule(plan, num_microbatches).rows
     P, V, M = plan.num_stages, plan.virtual_chunks, num_microbatches
     st = plan.schedule_type
     NV = P * V
@@ -102,8 +140,18 @@ def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[Li
     if not split_w:
         cB = cB + cW
     prio = {"F": 1, "B": 0, "W": 2} if st != PipelineScheduleType.GPIPE else {"F": 0, "B": 1, "W": 2}
+    kn = knobs or ScheduleKnobs()
+    if kn.prio is not None:
+        prio = dict(kn.prio)
+    mem_model = dict(kn.mem) if kn.mem is not None else None
+    if mem_model is not None and not split_w:
+        mem_model = {"F": mem_model.get("F", 0.0), "B": mem_model.get("B", 0.0) + mem_model.get("W", 0.0), "W": 0.0}
+    max_mem = kn.max_mem if mem_model is not None else None
+    mem_now = [0.0] * P
 
     def limit(rank: int) -> int:
+        if kn.inflight is not None:
+            return kn.inflight
         if plan.max_inflight is not None:
             return plan.max_inflight
         if st == PipelineScheduleType.GPIPE or plan.forward_only:
@@ -152,7 +200,21 @@ def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[Li
         t = done.get(("B", m, v))
         return t
 
-    if st == PipelineScheduleType.INTERLEAVED_1F1B and not plan.forward_only and plan.max_inflight is None:
+    owned = [[v for v in range(NV) if place[v][0] == r] for r in range(P)]
+    next_w = [0] * NV  # W's of a virtual stage run in micro-batch order too (their B's do)
+
+    def frontier(r: int):
+        """The only ops of rank ``r`` that can be ready: per owned virtual stage the next forward, the next backward, the next W."""
+        for v in owned[r]:
+            if next_f[v] < M:
+                yield ("F", next_f[v], v)
+            if not plan.forward_only:
+                if next_b[v] < M:
+                    yield ("B", next_b[v], v)
+                if split_w and next_w[v] < next_b[v]:
+                    yield ("W", next_w[v], v)
+
+    if st == PipelineScheduleType.INTERLEAVED_1F1B and not plan.forward_only and plan.max_inflight is None and knobs is None:
         return _interleaved_schedule(P, V, M, place, cF, cB, cC)
     now = 0.0
     guard = 0
@@ -165,20 +227,30 @@ def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[Li
             if free_at[r] > now + 1e-12:
                 continue
             cands = []
-            for op in remaining:
-                if place[op[2]][0] != r:
-                    continue
+            mem_blocked = False
+            for op in frontier(r):
                 rt = ready_time(op)
                 if rt is None or rt > now + 1e-12:
                     continue
-                if op[0] == "F" and inflight[r] >= limit(r):
+                # the window is admission control: it holds back NEW micro-batches (chunk 0).  A deeper chunk's forward belongs to a
+                # micro-batch that is already in flight, and holding it back can starve the backward that would open the window
+                # (seen with ZB-V once p2p latency delays the second chunk's arrivals)
+                if op[0] == "F" and place[op[2]][1] == 0 and inflight[r] >= limit(r):
+                    continue
+                if op[0] == "F" and max_mem is not None and mem_now[r] + mem_model["F"] > max_mem + 1e-9:
+                    mem_blocked = True
                     continue
                 cands.append(op)
             if not cands:
                 continue
+            if mem_blocked and kn.w_when_blocked and any(o[0] == "W" for o in cands) and not any(o[0] == "B" for o in cands):
+                cands = [o for o in cands if o[0] == "W"]  # free memory first: the blocked F is worth more than the ready one
             # priority, then older micro-batch, then (for F) deeper chunk first so the V/interleave drains
-            op = min(cands, key=lambda o: (prio[o[0]], o[1], -o[2] if o[0] == "F" else o[2]))
+            sgn = -1 if kn.deep_first else 1
+            op = min(cands, key=lambda o: (prio[o[0]], o[1], sgn * o[2] if o[0] == "F" else o[2]))
             k, m, v = op
+            if mem_model is not None:
+                mem_now[r] += mem_model.get(k, 0.0)
             cost = cF if k == "F" else (cB if k == "B" else cW)
             rows[r].append(Instr(k, m, v, place[v][1], now, now + cost))
             done[op] = now + cost
@@ -190,6 +262,8 @@ def build_schedule(plan: PipelineParallelPlan, num_microbatches: int) -> List[Li
             elif k == "B":
                 inflight[r] -= 1
                 next_b[v] += 1
+            else:
+                next_w[v] += 1
             progressed = True
         if remaining:
             # advance to the next time anything can change
