@@ -7,3 +7,4 @@ from .stage import (  # noqa: F401
 )
 from .p2p import P2PContext  # noqa: F401
 from .engine import PipeEngine, ScheduleEngine  # noqa: F401
+from .graph_emitter import GraphPipeProgram, PPCollectiveOpEmitter, infer_stage_meta  # noqa: F401

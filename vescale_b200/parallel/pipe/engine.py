@@ -21,7 +21,7 @@ import torch
 
 from ...profiler import ndtimeit, predefined
 from .p2p import P2PContext
-from .plan import PipelineParallelPlan, PipelineScheduleType
+from .plan import ModeType, PipelineParallelPlan, PipelineScheduleType
 from .schedule import INSTRUCTION_REGISTRY, Instr, build_schedule, stage_placement, validate_pipeline_schedule
 from .stage import PipeModule
 
@@ -211,13 +211,37 @@ class PipeEngine:
             n = num_microbatches or self.plan.num_stages
             minibatch = list(minibatch.chunk(n))
             labels = list(labels.chunk(n)) if isinstance(labels, torch.Tensor) else labels
-        losses, outputs = self.schedule_engine.execute(minibatch, labels, forward_only or self.plan.forward_only)
+        if self.plan.mode == ModeType.GRAPH_EAGER:
+            losses, outputs = self._run_graph_program(minibatch, labels, forward_only or self.plan.forward_only)
+        else:
+            losses, outputs = self.schedule_engine.execute(minibatch, labels, forward_only or self.plan.forward_only)
         loss = None
         if any(l is not None for l in losses):
             loss = torch.stack([l for l in losses if l is not None]).sum()
         return loss, outputs
 
     __call__ = forward_backward
+
+    # ---- graph mode (plan.mode = GRAPH_EAGER): this rank's emitted fx program, p2p inside the graph (graph_emitter.py)
+    def graph_program(self, minibatch, with_labels: bool = True):
+        """The emitted program for ``len(minibatch)`` micro-batches (built once per micro-batch count and label use)."""
+        from .graph_emitter import PPCollectiveOpEmitter, infer_stage_meta
+
+        key = (len(minibatch), bool(with_labels))
+        cache = self.__dict__.setdefault("_graph_programs", {})
+        if key not in cache:
+            ex = minibatch[0] if isinstance(minibatch[0], (tuple, list)) else (minibatch[0],)
+            if "_graph_metas" not in self.__dict__:
+                self._graph_metas = infer_stage_meta(self.module, self.plan, self.pp_rank, self.pp_group, ex, self.device)
+            em = PPCollectiveOpEmitter(self.module, self.plan, self.pp_rank, self.pp_group, self.loss_fn)
+            cache[key] = em.emit(len(minibatch), self._graph_metas, self.device, n_inputs=len(ex), with_labels=with_labels)
+        return cache[key]
+
+    def _run_graph_program(self, minibatch, labels, forward_only: bool):
+        prog = self.graph_program(minibatch, with_labels=labels is not None and self.loss_fn is not None)
+        losses, outs = prog.run(minibatch if prog.takes_inputs else None, labels if prog.takes_labels else None, forward_only=forward_only)
+        M = len(minibatch)
+        return (losses + [None] * (M - len(losses))), (outs + [None] * (M - len(outs)))
 
     def calibrate(self, minibatch, labels=None, num_microbatches: Optional[int] = None, comm: Optional[float] = None, warmup: int = 1, search: bool = True):
         """Measure F / B / W on this pipeline (median per instruction kind, MAX over the pipeline ranks, normalised so that F = 1),
