@@ -1,5 +1,5 @@
 """PP x DP Llama training with the pipeline engine (1F1B / interleaved / zero-bubble) over FSDP-free stages.
-    torchrun --nproc-per-node 4 examples/llama_4D_finetune/train.py --pp 2 --dp 2 --schedule ZERO_BUBBLE
+    torchrun --nproc-per-node 4 examples/llama_4D_finetune/pp_train.py --pp 2 --dp 2 --schedule ZERO_BUBBLE
 (reference: ``legacy/examples/llama2_4D_finetune/llama_train.py``)."""
 import argparse
 import os

@@ -116,7 +116,7 @@ def main():
         from vescale_b200.dtensor import loss_parallel
 
         with loss_parallel():
-            loss = F.cross_entropy(logits.view(-1, args.vocab), torch.nn.Parameter(ids[:, 1:].reshape(-1).float(), requires_grad=False).long() if False else ids[:, 1:].reshape(-1))
+            loss = F.cross_entropy(logits.view(-1, args.vocab), ids[:, 1:].reshape(-1))
             loss.backward()
         opt.step()
         if cuda:
