@@ -52,3 +52,10 @@ def test_llama_4d_finetune_hf_model_curves_and_resume(tmp_path):
     assert sorted(resumed) == [4, 5, 6, 7], resumed
     for k, v in resumed.items():
         assert abs(v - full[k]) < 2e-3, (k, v, full[k])
+
+
+def test_mixtral_ep_training_hf_model_matches_single_device():
+    """Unmodified HF MixtralForCausalLM, experts hijacked onto EP=4 (one expert per rank per layer, so ranks regularly receive no
+    token for a layer), MoEOptimizer: the loss curve equals the unparallelised twin on the global batch."""
+    out = _torchrun(4, "examples/mixtral_EP_training/mixtral_train.py", "--max_iters", "8", "--compare-single", port=29715)
+    assert "loss curves agree" in out, out[-2000:]

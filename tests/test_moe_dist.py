@@ -46,6 +46,44 @@ def test_expert_parallel_matches_local_experts():
     run_distributed(_ep, 4)
 
 
+def _ep_starved_rank(rank, world):
+    """A rank whose experts receive NO token must still take part in the backward of the dispatch all-to-all (its peers run theirs):
+    the router is biased so that every token goes to the experts of the last rank.  Outputs and gradients equal the dense layer."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.moe import MoEConfig, MoELayer
+
+    dev = device_type()
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("EP",))
+    cfg = MoEConfig(16, 32, 2 * world, 2, dtype=torch.float32)
+    ep, dense = MoELayer(cfg, mesh.get_group(0), device=dev), MoELayer(MoEConfig(16, 32, 2 * world, 2, dtype=torch.float32), None, device=dev)
+    for l in (ep, dense):
+        l.reset_parameters(torch.Generator().manual_seed(4))
+        with torch.no_grad():
+            l.router.weight.zero_()
+            l.router.weight[-2:, 0] = 50.0  # with x[:, 0] = 1 below, the last two experts win every token
+    for it in range(2):
+        xs = [torch.randn(6, 16, generator=torch.Generator().manual_seed(10 * it + r)).to(dev) for r in range(world)]
+        for x in xs:
+            x[:, 0] = 1.0
+        x = xs[rank].clone().requires_grad_(True)
+        y = ep(x)
+        assert sum(ep.last_tokens_per_rank) == (6 * 2 * world if rank == world - 1 else 0)
+        y.pow(2).sum().backward()
+        xd = [t.clone().requires_grad_(True) for t in xs]
+        sum(dense(t).pow(2).sum() for t in xd).backward()
+        torch.testing.assert_close(y.detach(), dense(xs[rank]).detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(x.grad, xd[rank].grad, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(ep.experts.w_down.grad, dense.experts.w_down.grad[2 * rank : 2 * rank + 2], rtol=1e-5, atol=1e-6)
+        assert ep.experts.w_gate_up.grad is not None and (rank == world - 1 or float(ep.experts.w_gate_up.grad.abs().sum()) == 0.0)
+        for l in (ep, dense):
+            for p in l.parameters():
+                p.grad = None
+
+
+def test_expert_parallel_rank_without_tokens():
+    run_distributed(_ep_starved_rank, 3)
+
+
 def _realloc(rank, world):
     """Experts (weights + Adam state) migrate between EP ranks mid-training; the function computed and the optimizer
     trajectory are unchanged (legacy ``_moe_param_buffer.py:183-337`` dynamic re-allocation)."""

@@ -100,7 +100,10 @@ class GroupedExperts(nn.Module):
 
     def forward(self, x: torch.Tensor, rows_per_expert: List[int]) -> torch.Tensor:
         if sum(rows_per_expert) == 0:
-            return x.new_zeros((0, self.cfg.hidden_size)) + 0.0 * (self.w_gate_up.sum() + self.w_down.sum())  # keep the graph connected
+            # no token for any local expert.  The (empty) result must still depend on BOTH the input rows and the weights: the rows
+            # came out of the dispatch all-to-all, and a graph that does not reach it makes this rank skip that collective's backward
+            # while its peers run theirs (hang on NCCL, size mismatch on gloo); the weights must get (zero) gradients for the optimizer.
+            return x[:, : self.cfg.hidden_size] * 1.0 + 0.0 * (self.w_gate_up.sum() + self.w_down.sum()).to(x.dtype)
         return _GroupedSwiGLUFFN.apply(x, self.w_gate_up, self.w_down, tuple(int(n) for n in rows_per_expert))
 
 
