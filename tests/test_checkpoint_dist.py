@@ -411,3 +411,93 @@ def _pp_layout_and_workers(rank, world, path):
 
 def test_pp_optimizer_layout_and_process_pool_writer(tmp_path):
     run_distributed(_pp_layout_and_workers, 4, str(tmp_path))
+
+
+def test_bfile_schemes_recorder_and_logger(tmp_path, monkeypatch):
+    """``bfile``: one file API over local paths, the in-memory file server (``mem://``) and registered schemes, atomic writes;
+    ``TorchCheckpointRecorder`` turns ``torch.save`` calls asynchronous; checkpoint logger level from the environment
+    (legacy ``checkpoint/utilities/{bfile,mem_checkpoint,logger}.py``)."""
+    import logging
+
+    from vescale_b200.checkpoint import MemFileServer, TorchCheckpointRecorder, bfile, get_vescale_checkpoint_logger
+
+    # local
+    p = str(tmp_path / "a" / "b" / "f.bin")
+    bfile.safe_atomic_write(p, b"hello")
+    assert bfile.exists(p) and bfile.read_bytes(p) == b"hello" and bfile.is_local_path(p) and bfile.get_schema(p) == bfile.FileType.LOCAL
+    assert bfile.listdir(str(tmp_path / "a" / "b")) == ["f.bin"]  # no temporary file left behind
+    bfile.rename(p, p + "2")
+    assert not bfile.exists(p) and bfile.local_list_folder(str(tmp_path / "a"), recursive=True) == [p + "2"]
+    bfile.remove(str(tmp_path / "a"))
+    assert not bfile.exists(str(tmp_path / "a"))
+    # in-memory file server
+    srv = MemFileServer().start()
+    try:
+        root = f"mem://{srv.address}/ck"
+        bfile.safe_atomic_write(root + "/x.bin", b"abc")
+        with bfile.BFile(root + "/t.txt", "w") as f:
+            f.write("text")
+        assert bfile.get_schema(root) == bfile.FileType.LOCAL_MEM and sorted(bfile.listdir(root)) == ["t.txt", "x.bin"]
+        assert bfile.read_bytes(root + "/x.bin") == b"abc"
+        with bfile.BFile(root + "/t.txt", "r") as f:
+            assert f.read() == "text"
+        bfile.remove(root)
+        assert not bfile.exists(root + "/x.bin")
+    finally:
+        srv.stop()
+    # a deployment's own object store
+    store = {}
+
+    class Dict:
+        def open(self, path, mode="r"):
+            import io
+
+            if "r" in mode:
+                return io.BytesIO(store[path])
+            b = io.BytesIO()
+            close = b.close
+            b.close = lambda: (store.__setitem__(path, b.getvalue()), close())[1]
+            return b
+
+        def exists(self, path):
+            return path in store
+
+        def listdir(self, path):
+            return [k[len(path) + 1 :] for k in store if k.startswith(path + "/")]
+
+        def remove(self, path):
+            store.pop(path, None)
+
+        def rename(self, src, dst, overwrite=False):
+            store[dst] = store.pop(src)
+
+        def makedirs(self, path):
+            pass
+
+    bfile.register_scheme("objstore", Dict())
+    bfile.safe_atomic_write("objstore://bucket/ck/meta", b"m")
+    assert store == {"objstore://bucket/ck/meta": b"m"} and bfile.get_schema("objstore://bucket") == bfile.FileType.REMOTE and not bfile.is_local_path("objstore://x")
+    try:
+        bfile.exists("nosuch://x")
+        raise AssertionError("unknown scheme must raise")
+    except ValueError:
+        pass
+    # torch.save recorder
+    sd = {"w": torch.arange(12.0).view(3, 4), "step": 3, "nested": [torch.ones(2), ("a", torch.zeros(1))]}
+    rec = TorchCheckpointRecorder()
+    with rec:
+        torch.save(sd, str(tmp_path / "r" / "model.pt"))
+        sd["w"].mul_(0)  # the training loop moves on; the recorded copy must not see it
+        torch.save({"x": torch.ones(1)}, str(tmp_path / "r" / "model.pt"))  # same path again: waits for the first write
+        torch.save(sd, str(tmp_path / "r" / "second.pt"))
+    assert torch.save.__module__.startswith("torch")  # restored
+    written = rec.wait()
+    assert set(written) == {str(tmp_path / "r" / "model.pt"), str(tmp_path / "r" / "second.pt")} and all(v > 0 for v in written.values())
+    assert torch.equal(torch.load(str(tmp_path / "r" / "model.pt"))["x"], torch.ones(1))
+    assert float(torch.load(str(tmp_path / "r" / "second.pt"))["w"].abs().sum()) == 0.0
+    rec.close()
+    # logger level from the environment
+    monkeypatch.setenv("VESCALE_CHECKPOINT_LOGGING_LEVEL", "DEBUG")
+    assert get_vescale_checkpoint_logger().level == logging.DEBUG
+    monkeypatch.setenv("VESCALE_CHECKPOINT_LOGGING_LEVEL", "35")
+    assert get_vescale_checkpoint_logger().level == 35

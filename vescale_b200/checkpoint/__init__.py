@@ -21,3 +21,6 @@ from .api import VeScaleCheckpointer, load, save, wait_for_async  # noqa: F401
 from .pinned_pool import PinnedPool  # noqa: F401
 from .meta_type import MODEL_STR, OPTIMIZER_STR, STATE_DICT_TYPE, CheckpointState, Stateful, SupportedStrategy  # noqa: F401
 from .mem_server import MemFileClient, MemFileServer  # noqa: F401
+from . import bfile  # noqa: F401
+from .logger import get_vescale_checkpoint_logger  # noqa: F401
+from .recorder import TorchCheckpointRecorder  # noqa: F401

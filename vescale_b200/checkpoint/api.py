@@ -11,7 +11,9 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from ..dtensor.api import DTensor
+from . import bfile
 from .flat_piece import FlatPiece
+from .logger import timed
 from .pinned_pool import PinnedPool
 
 __all__ = ["save", "load", "VeScaleCheckpointer", "wait_for_async"]
@@ -182,15 +184,15 @@ class VeScaleCheckpointer(BaseCheckpointer):
             suffix, stage_pg = _pp_scope(key, pp_rank, pp_group)
             if suffix:
                 sub = _join(sub, suffix)
-            if not path.startswith("mem://"):
-                os.makedirs(sub, exist_ok=True)
+            bfile.makedirs(sub)  # a no-op for back ends with implicit directories (mem://)
             sd = _state_of(obj)
             tensors = {k: v for k, v in sd.items() if isinstance(v, torch.Tensor)}
             extras = {k: v for k, v in sd.items() if not isinstance(v, torch.Tensor)}
             if extras:
                 tensors["__extras__"] = extras  # small python state (step counters, hyper-parameters) via DCP bytes
             if async_checkpoint:
-                host = _stage_to_host(tensors)
+                with timed(f"save {key}: device -> pinned staging"):
+                    host = _stage_to_host(tensors)
                 pg = stage_pg if stage_pg is not None else _async_group()
                 fut: Future = Future()
 
@@ -198,7 +200,8 @@ class VeScaleCheckpointer(BaseCheckpointer):
                     try:
                         # planning (a few small collectives) runs on this thread; serialisation + file writes run in worker
                         # PROCESSES on the shared pinned staging buffers, so the training loop's GIL is left alone
-                        dcp.save(host, process_group=pg, planner=_save_planner("async/" + key), **_storage(sub, True, workers))
+                        with timed(f"save {key}: plan + serialise + write (background, {workers} worker processes)"):
+                            dcp.save(host, process_group=pg, planner=_save_planner("async/" + key), **_storage(sub, True, workers))
                         fut.set_result(sub)
                     except Exception as e:  # noqa: BLE001
                         fut.set_exception(e)
@@ -212,7 +215,8 @@ class VeScaleCheckpointer(BaseCheckpointer):
                 _PENDING.append(fut)
                 futures.append(fut)
             else:
-                dcp.save(tensors, planner=_save_planner(key), process_group=stage_pg, **_storage(sub, True, workers))
+                with timed(f"save {key}: synchronous"):
+                    dcp.save(tensors, planner=_save_planner(key), process_group=stage_pg, **_storage(sub, True, workers))
         return futures or None
 
     @classmethod
@@ -253,7 +257,8 @@ class VeScaleCheckpointer(BaseCheckpointer):
                         else:
                             dist.broadcast(t, src=0)
             else:
-                dcp.load(req, process_group=stage_pg, **_storage(sub, False))  # in place: DTensor / tensor storages are filled with the resharded data
+                with timed(f"load {key}"):
+                    dcp.load(req, process_group=stage_pg, **_storage(sub, False))  # in place: DTensor / tensor storages are filled with the resharded data
             if isinstance(obj, nn.Module):
                 pass  # state_dict tensors alias the module's parameters/buffers
             elif hasattr(obj, "load_checkpoint_state"):
