@@ -30,7 +30,7 @@ def test_emulator_ring_order_and_dtensor_api():
     # different association than a naive sum (that is the point of the emulator)
     torch.testing.assert_close(out[0], sum(xs), rtol=1e-5, atol=1e-3)
     t = tree_all_reduce(xs)
-    assert torch.equal(t[0], ((xs[3] + xs[1]) + xs[2]) + xs[0])
+    assert torch.equal(t[0], (xs[0] + (xs[1] + xs[3])) + xs[2])  # a node's own buffer is source 0, then its children in order (NCCL reduceCopy)
     mesh = DeviceMesh("meta", torch.arange(4).reshape(2, 2), mesh_dim_names=("dp", "tp"), _rank=0)
     full = torch.randn(8, 6)
     shards = distribute_tensor(full, mesh, [Shard(0), Shard(1)])

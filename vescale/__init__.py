@@ -92,12 +92,22 @@ _ALIASES = {
     "vescale.emulator.utils": "vescale_b200.emulator.utils",
     "vescale.emulator.mesh_collectives": "vescale_b200.emulator.mesh_collectives",
     "vescale.emulator.comm_api": "vescale_b200.emulator.comm_api",
-    "vescale.emulator.all_reduce": "vescale_b200.emulator.collectives",
-    "vescale.emulator.all_gather": "vescale_b200.emulator.collectives",
-    "vescale.emulator.reduce_scatter": "vescale_b200.emulator.collectives",
-    "vescale.emulator.all_to_all": "vescale_b200.emulator.collectives",
-    "vescale.emulator.calculate_chunk_size": "vescale_b200.emulator.tuning",
-    "vescale.emulator.primitives": "vescale_b200.emulator.comm_primitive",
+    "vescale.emulator.all_reduce": "vescale_b200.emulator.algorithms",
+    "vescale.emulator.all_gather": "vescale_b200.emulator.algorithms",
+    "vescale.emulator.reduce_scatter": "vescale_b200.emulator.algorithms",
+    "vescale.emulator.all_to_all": "vescale_b200.emulator.algorithms",
+    "vescale.emulator.calculate_chunk_size": "vescale_b200.emulator.chunk_math",
+    "vescale.emulator.primitives": "vescale_b200.emulator.primitives",
+    "vescale.emulator.nccl": "vescale_b200.emulator.nccl",
+    "vescale.emulator.nccl.constants": "vescale_b200.emulator.nccl.constants",
+    "vescale.emulator.nccl.init": "vescale_b200.emulator.nccl.comm",
+    "vescale.emulator.nccl.include": "vescale_b200.emulator.nccl.comm",
+    "vescale.emulator.nccl.include.comm": "vescale_b200.emulator.nccl.comm",
+    "vescale.emulator.nccl.include.graph": "vescale_b200.emulator.nccl.comm",
+    "vescale.emulator.nccl.include.info": "vescale_b200.emulator.nccl.comm",
+    "vescale.emulator.nccl.graph": "vescale_b200.emulator.nccl.tuning",
+    "vescale.emulator.nccl.graph.tuning": "vescale_b200.emulator.nccl.tuning",
+    "vescale.emulator.nccl.nccl_profiler_result": "vescale_b200.emulator.nccl.profiler_result",
     "vescale.ndtimeline.api": "vescale_b200.profiler.timer",
     "vescale.ndtimeline.timer": "vescale_b200.profiler.timer",
     "vescale.ndtimeline.pool": "vescale_b200.profiler.pool",

@@ -11,3 +11,6 @@ from .comm_primitive import P2R, P2S, R2P, R2R, R2S, S2R, S2S  # noqa: F401
 from .emulator_instrumentation import EmulatorInstrumentation, map_over_ranks  # noqa: F401
 from .topo import BinaryTree, DoubleTree, Ring, btree, double_tree, parse_graph_dump  # noqa: F401
 from .tuning import Tuning, calculate_chunk_size, select_algorithm  # noqa: F401
+from . import algorithms, chunk_math, nccl, primitives  # noqa: F401,E402
+from .algorithms import chunk_layout, run_all_to_all, run_broadcast, run_ring_all_gather, run_ring_all_reduce, run_ring_reduce_scatter, run_tree_all_reduce  # noqa: F401,E402
+from .primitives import Point2PointPrimitive, RingPrimitive, Traffic, TreePrimitive  # noqa: F401,E402

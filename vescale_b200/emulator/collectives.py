@@ -94,17 +94,17 @@ def ring_reduce_scatter(inputs: Sequence[torch.Tensor], op: str = "sum", ring: O
 
 
 def tree_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum") -> List[torch.Tensor]:
-    """Binary-tree reduce (rank 0 root, children 2i+1 / 2i+2: child partial sums arrive first, the local value is
-    added last) followed by a broadcast."""
+    """Binary-tree reduce (rank 0 root, children 2i+1 / 2i+2) followed by a broadcast.  A node accumulates like NCCL's
+    ``reduceCopy``: its own buffer is source 0, then the children's partial sums in connection order —
+    ``(local + child0) + child1``."""
     n = len(inputs)
 
     def up(i):
-        acc = None
+        acc = inputs[i].clone()
         for c in (2 * i + 1, 2 * i + 2):
             if c < n:
-                v = up(c)
-                acc = v if acc is None else _op(acc, v, op)
-        return inputs[i].clone() if acc is None else _op(acc, inputs[i], op)
+                acc = _op(acc, up(c), op)
+        return acc
 
     total = up(0)
     return [total.clone() for _ in range(n)]
@@ -112,8 +112,8 @@ def tree_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum") -> List[tor
 
 def double_tree_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum", chunk_elems: Optional[int] = None) -> List[torch.Tensor]:
     """NCCL's tree all-reduce: the buffer alternates between the two trees of ``topo.double_tree`` chunk by chunk; within a
-    tree a node receives its children's partial results in child order, adds its own value last (``reduce`` up), and the
-    root's total is broadcast down.  The association order therefore depends on (tree, position) — which is exactly what
+    tree a node starts from its own value and adds its children's partial results in child order (``reduceCopy`` source
+    order: local buffer, then the receive connections), and the root's total is broadcast down.  The association order therefore depends on (tree, position) — which is exactly what
     differs from a ring and what this function reproduces."""
     from .topo import double_tree
 
@@ -125,12 +125,10 @@ def double_tree_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum", chun
     result = torch.empty_like(flat[0])
 
     def up(tree, r, lo, hi):
-        acc = None
+        acc = flat[r][lo:hi].clone()  # source 0 of reduceCopy is the local buffer, the receive connections follow in order
         for c in tree.children.get(r, []):
-            v = up(tree, c, lo, hi)
-            acc = v if acc is None else _op(acc, v, op)
-        mine = flat[r][lo:hi]
-        return mine.clone() if acc is None else _op(acc, mine, op)
+            acc = _op(acc, up(tree, c, lo, hi), op)
+        return acc
 
     pos, k = 0, 0
     while pos < count:
@@ -166,6 +164,8 @@ class EmulatorProcessGroup:
             return tree_all_reduce(tensors, op)
         if self.algo == "double_tree":
             return double_tree_all_reduce(tensors, op, self.chunk_elems)
+        if self.algo == "nccl":  # the full host-side model (nccl/tuning.py) + step-level kernels with the protocol's own chunk geometry
+            return self._all_reduce_nccl_model(tensors, op)
         if self.algo == "auto":  # let the tuning model pick, as NCCL would for this message size
             from .tuning import select_algorithm
 
@@ -174,6 +174,29 @@ class EmulatorProcessGroup:
                 return double_tree_all_reduce(tensors, op, max(1, t.chunk_bytes // tensors[0].element_size()))
             return ring_all_reduce(tensors, op, self.ring, t.nchannels, max(1, t.chunk_bytes // tensors[0].element_size()))
         return ring_all_reduce(tensors, op, self.ring, self.nchannels, self.chunk_elems)
+
+    def _all_reduce_nccl_model(self, tensors, op):
+        """``algo="nccl"``: ``nccl.get_algo_info`` decides (algorithm, protocol, channels, threads, chunk) for this message on
+        ``self.comm`` (an ``nccl.NcclComm``; default: one NVSwitch node of ``world_size`` Blackwell GPUs without NVLS, whose in-switch
+        reduction has no software order to emulate), and the step-level kernels of ``algorithms.py`` run it.  ``self.last_info`` /
+        ``self.last_traffic`` keep the decision and the per-link byte counts."""
+        from .algorithms import chunk_layout, run_ring_all_reduce, run_tree_all_reduce
+        from .nccl import Algo, CollInfo, Func, get_algo_info, init_comm
+        from .primitives import Traffic
+
+        comm = getattr(self, "comm", None)
+        if comm is None:
+            comm = self.comm = init_comm(self.world_size, nvls=False)
+        es = tensors[0].element_size()
+        info = get_algo_info(comm, CollInfo(int(Func.ALL_REDUCE), tensors[0].numel(), es), force=getattr(self, "force_algo_proto", None))
+        self.last_info, self.last_traffic = info, Traffic()
+        if info.algo == int(Algo.TREE):
+            return run_tree_all_reduce(tensors, op, getattr(self, "trees", None), max(1, info.last_chunk_size), info.n_channels, self.last_traffic)
+        step_elems = max(1, info.chunk_size // es) if info.proto == 2 else max(1, (info.chunk_size // (2 if info.proto == 0 else 1)) // es)
+        if info.proto == 1:
+            step_elems = max(1, info.chunk_size // 16 * 15 // es)
+        layout = chunk_layout(tensors[0].numel(), self.world_size, info.n_channels, step_elems, info.proto, info.n_threads, es)
+        return run_ring_all_reduce(tensors, op, self.ring, layout=layout, traffic=self.last_traffic)
 
     def reduce_scatter(self, tensors, op: str = "sum"):
         return ring_reduce_scatter(tensors, op, self.ring)

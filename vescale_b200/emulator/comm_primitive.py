@@ -19,7 +19,7 @@ import torch
 from ..mesh import DeviceMesh
 from .comm_api import _groups_along, mesh_all_gather, mesh_all_reduce, mesh_reduce_scatter
 
-__all__ = ["R2R", "R2S", "S2R", "P2R", "P2S", "S2S", "R2P"]
+__all__ = ["R2R", "R2S", "S2R", "P2R", "P2S", "S2S", "R2P", "get_redistribute_fn", "TRANSITIONS"]
 
 
 def R2R(locals_: List[torch.Tensor], mesh: DeviceMesh, mesh_dim: int) -> List[torch.Tensor]:  # noqa: N802
@@ -63,3 +63,38 @@ def R2P(locals_: List[torch.Tensor], mesh: DeviceMesh, mesh_dim: int) -> List[to
         for i, r in enumerate(ranks):
             out[r] = locals_[r].clone() if i == 0 else torch.zeros_like(locals_[r])
     return out
+
+
+def _kind(p) -> str:
+    if p.is_replicate():
+        return "R"
+    if p.is_partial():
+        return "P"
+    return "S"
+
+
+TRANSITIONS = {("R", "R"): R2R, ("R", "S"): R2S, ("S", "R"): S2R, ("P", "R"): P2R, ("P", "S"): P2S, ("S", "S"): S2S, ("R", "P"): R2P}
+
+
+def get_redistribute_fn(src, dst):
+    """The transition primitive for one mesh dim going from placement ``src`` to ``dst``, with the placement-specific arguments
+    (shard dims, reduce op) already bound: call it as ``fn(locals_, mesh, mesh_dim)``."""
+    import functools
+
+    key = (_kind(src), _kind(dst))
+    if key not in TRANSITIONS:
+        raise NotImplementedError(f"no single-step transition {src} -> {dst}; go through Replicate")
+    fn = TRANSITIONS[key]
+    if key == ("R", "S"):
+        return functools.partial(fn, shard_dim=dst.dim)
+    if key == ("S", "R"):
+        return functools.partial(fn, shard_dim=src.dim)
+    if key == ("P", "R"):
+        return functools.partial(fn, op=getattr(src, "reduce_op", "sum"))
+    if key == ("P", "S"):
+        return functools.partial(fn, shard_dim=dst.dim, op=getattr(src, "reduce_op", "sum"))
+    if key == ("S", "S"):
+        if src.dim == dst.dim:
+            return R2R
+        return functools.partial(fn, src_dim=src.dim, dst_dim=dst.dim)
+    return fn

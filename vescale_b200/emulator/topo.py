@@ -12,7 +12,7 @@ import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
-__all__ = ["Ring", "BinaryTree", "DoubleTree", "btree", "parse_graph_dump"]
+__all__ = ["Ring", "BinaryTree", "DoubleTree", "btree", "parse_graph_dump", "global_rank_to_group_rank", "filter_tree_structure", "tree_structure_from_graph_dump"]
 
 
 @dataclass
@@ -173,3 +173,25 @@ def parse_graph_dump(xml_text: str) -> Dict[str, List[List[int]]]:
             if order:
                 out[kind].append(order)
     return out
+
+
+def global_rank_to_group_rank(global_ranks: Sequence[int], mapping: Dict[int, int]) -> List[int]:
+    """Indices inside a group for a list of global ranks (``mapping``: global rank -> group index)."""
+    return [mapping[int(r)] for r in global_ranks]
+
+
+def filter_tree_structure(tree_structure: Sequence[Sequence[int]], selected_ranks: Sequence[int], mapping: Optional[Dict[int, int]] = None) -> List[List[int]]:
+    """The node x local-device table restricted to a group: rows keep only member ranks (translated through ``mapping`` when
+    given), rows without members disappear — what a sub-communicator's tree is built over."""
+    member = set(int(r) for r in selected_ranks)
+    rows = [[(mapping[int(r)] if mapping is not None else int(r)) for r in row if int(r) in member] for row in tree_structure]
+    return [r for r in rows if r]
+
+
+def tree_structure_from_graph_dump(xml_text: str, ranks_per_node: Optional[int] = None, n_nodes: int = 1) -> List[List[int]]:
+    """Node x local-device table of global ranks from the tree graph of an ``NCCL_GRAPH_DUMP_FILE`` (channel 0's device order is
+    the intra-node chain every node uses); falls back to the ring graph's order."""
+    g = parse_graph_dump(xml_text)
+    order = (g["tree"] or g["ring"] or [[]])[0]
+    per = ranks_per_node or len(order)
+    return [[n * per + d for d in order] for n in range(n_nodes)]

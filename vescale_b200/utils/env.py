@@ -17,6 +17,7 @@ FLAGS: Dict[str, Tuple[str, str]] = {
     "VESCALE_DEBUG_MODE": ("", "non-empty = DebugLogger prints every dispatched op and mesh collective (rank filter after ':')"),
     "VESCALE_DUMMY_P2P": ("0", "1 = pipeline p2p ops are logged, not executed (schedule dry run)"),
     "VESCALE_DUMP_INSTRUCTION": ("0", "1 = the pipeline engine dumps each rank's instruction list to a file"),
+    "VESCALE_CHECKPOINT_LOGGING_LEVEL": ("", "level of the checkpoint logger: a logging level name (DEBUG, INFO, ...) or number; empty = WARNING"),
     "VESCALE_DEVICE_MESH": ("", "internal: name of the global VeDeviceMesh registry entry"),
     "VESCALE_B200_ALLOW_FALLBACK": ("0", "1 = allow PyTorch fallbacks on a CUDA device when vescale_b200/_C.so is missing (default: fail loudly)"),
     "VESCALE_B200_SYMM_DEBUG": ("0", "1 = poison symmetric buffers when they return to a pool and validate signal epochs (comm/symm_debug.py)"),
