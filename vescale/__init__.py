@@ -64,11 +64,12 @@ _ALIASES = {
     "vescale.dmp.policies.megatron": "vescale_b200.parallel.dmp.policies.megatron",
     "vescale.pipe.pipe_stage": "vescale_b200.parallel.pipe.stage",
     "vescale.pipe.pipe_parser": "vescale_b200.parallel.pipe.stage",
-    "vescale.pipe.tracer": "vescale_b200.parallel.pipe.stage",
+    "vescale.pipe.tracer": "vescale_b200.parallel.pipe.tracer",
     "vescale.pipe.pipe_emmiter": "vescale_b200.parallel.pipe.engine",
-    "vescale.pipe.p2p_communication": "vescale_b200.parallel.pipe.p2p",
+    "vescale.pipe.p2p_communication": "vescale_b200.parallel.pipe.p2p_communication",
     "vescale.pipe._schedules": "vescale_b200.parallel.pipe._schedules",
-    "vescale.pipe._schedules.instruction_base": "vescale_b200.parallel.pipe._schedules",
+    "vescale.pipe._schedules.instruction_base": "vescale_b200.parallel.pipe.instruction_base",
+    "vescale.pipe._schedules.pp_collective_emitter": "vescale_b200.parallel.pipe.graph_emitter",
     "vescale.pipe._schedules.pipedream_flush": "vescale_b200.parallel.pipe._schedules",
     "vescale.pipe._schedules.looping_bfs": "vescale_b200.parallel.pipe._schedules",
     "vescale.pipe._schedules.zero_bubble_v": "vescale_b200.parallel.pipe._schedules",

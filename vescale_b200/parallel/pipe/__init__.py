@@ -8,3 +8,5 @@ from .stage import (  # noqa: F401
 from .p2p import P2PContext  # noqa: F401
 from .engine import PipeEngine, ScheduleEngine  # noqa: F401
 from .graph_emitter import GraphPipeProgram, PPCollectiveOpEmitter, infer_stage_meta  # noqa: F401
+from . import instruction_base, p2p_communication  # noqa: F401,E402
+from .instruction_base import BaseInstruction, CommPacket, InstructionBuilder, InstructionVM, PipelineSchema, StageLink, Status  # noqa: F401,E402

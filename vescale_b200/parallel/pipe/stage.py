@@ -123,7 +123,9 @@ class PipeParser:
         for s, g in enumerate(groups):
             for i in g:
                 unit_stage[units[i][0]] = s
-        gm = fx.symbolic_trace(model)
+        from .tracer import trace_model
+
+        gm = trace_model(model, partition_units=[n for n, _ in units])  # units stay opaque call_module nodes (tracer.py)
         cur = [0]
 
         def part(node):
