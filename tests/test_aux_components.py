@@ -132,8 +132,50 @@ def test_profiler_chrome_trace(tmp_path):
         nd.flush(asynchronous=True)
     nd.wait()
     ev = json.load(open(tmp_path / "ndtimeline_rank0.json"))["traceEvents"]
-    assert {e["name"] for e in ev} == {"decorated", "forward-compute"} and all(e["dur"] >= 0 for e in ev)
+    slices = [e for e in ev if e["ph"] == "X"]
+    assert {e["name"] for e in slices} == {"decorated", "forward-compute"} and all(e["dur"] >= 0 for e in slices)
+    assert [e for e in ev if e["ph"] == "M"][0]["args"]["name"].startswith("rank 0")
     assert p.summary()["decorated"]["count"] == 2
+    # typed records of the parser handler: ordered, on the global clock, tags preserved
+    assert len(p.records) == 4 and all(isinstance(r, nd.DeviceTimerStreamRecord) for r in p.records) and p.records[0].end_ts >= p.records[0].ts
+    assert {r.tags.get("microbatch") for r in p.records if r.metric == "forward-compute"} == {0, 1}
+
+
+def test_chrome_trace_events_flows_and_host_timeline(tmp_path):
+    """Typed trace events, stable thread ids, send -> recv flow arrows across ranks, merged host timeline (legacy
+    ``handlers/chrome_trace_event.py``, ``local_timeline_handler.py``)."""
+    import vescale_b200.profiler as nd
+    from vescale_b200.profiler.chrome_trace_event import (BeginEvent, CombinedEvents, CompleteEvent, CounterEvent, DummyEvent, EndEvent, FlowEvent, ThreadMetadataEvent,
+                                                          build_thread_index_table, link_p2p_flows)
+
+    doc = CombinedEvents([CompleteEvent(name="k", ts=1.0, dur=2.0, pid=0, tid=1, args={"a": 1}), BeginEvent(name="b", ts=1.0), EndEvent(name="b", ts=2.0),
+                          CounterEvent(name="bytes", ts=1.5, args={"in_flight": 3}), DummyEvent(), ThreadMetadataEvent(pid=0, tid=1, args={"name": "comm"})])
+    d = json.loads(doc.to_json())
+    assert [e["ph"] for e in d["traceEvents"]] == ["X", "B", "E", "C", "M"] and d["traceEvents"][0]["dur"] == 2.0 and "args" not in d["traceEvents"][1]
+    table = build_thread_index_table([(0, 77), (0, 0), (1, 5), (0, 77), (1, 0)])
+    assert table[(0, 0)] == 0 and table[(0, 77)] == 1 and table[(1, 0)] == 0 and table[(1, 5)] == 1
+    # two ranks of a pipeline: rank 0 sends forward twice to rank 1, rank 1 sends one gradient back
+    def rec(metric, start, peer, **tags):
+        return {"metric": metric, "start_us": start, "duration_us": 10.0, "tags": {"peer": peer, **tags}, "stream": 0}
+    h = nd.LocalTimelineNDHandler(str(tmp_path / "host.json"))
+    h([rec("send-forward", 100.0, 1, microbatch=0), rec("send-forward", 200.0, 1, microbatch=1), rec("recv-backward", 400.0, 1, microbatch=0)], 0, 0)
+    h([rec("recv-forward", 120.0, 0, microbatch=0), rec("recv-forward", 230.0, 0, microbatch=1), rec("send-backward", 380.0, 0, microbatch=0),
+       {"metric": "grad-reduce-scatter", "start_us": 300.0, "duration_us": 50.0, "tags": {}, "stream": 9}], 1, 0)
+    ev = json.load(open(tmp_path / "host.json"))["traceEvents"]
+    flows = [e for e in ev if e["ph"] in ("s", "f")]
+    assert len(flows) == 6 and {e["id"] for e in flows} == {1, 2, 3}
+    starts = {e["id"]: e for e in flows if e["ph"] == "s"}
+    ends = {e["id"]: e for e in flows if e["ph"] == "f"}
+    assert all(ends[i]["bp"] == "e" and ends[i]["ts"] >= starts[i]["ts"] and ends[i]["pid"] != starts[i]["pid"] for i in starts)
+    names = {(e["pid"], e["tid"]): e["args"]["name"] for e in ev if e["ph"] == "M" and e["name"] == "thread_name"}
+    assert names[(1, 0)] == "compute" and names[(1, 1)] == "stream 9"
+    # per-rank files merged after the fact get the same arrows
+    for rk, recs in ((0, [rec("send-forward", 100.0, 1)]), (1, [rec("recv-forward", 130.0, 0)])):
+        nd.ChromeTraceNDHandler(str(tmp_path), prefix="m")(recs, rk, 0)
+    n = nd.ChromeTraceNDHandler.merge([str(tmp_path / "m_rank0.json"), str(tmp_path / "m_rank1.json")], str(tmp_path / "merged.json"))
+    merged = json.load(open(tmp_path / "merged.json"))["traceEvents"]
+    assert n == len(merged) and sum(1 for e in merged if e["ph"] in ("s", "f")) == 2
+    assert isinstance(link_p2p_flows([])[0:0], list) and FlowEvent(ph="f", bp="e", id=3).to_dict()["bp"] == "e"
 
 
 def test_vescale_alias_package():
@@ -177,7 +219,8 @@ def test_profiler_socket_streamer(tmp_path):
     streamer.join(30)
     ev = json.load(open(out))["traceEvents"]
     spans = [e for e in ev if e["ph"] == "X"]
-    assert len(spans) == 6 and {e["pid"] for e in spans} == {0, 1} and all(e["tid"] == 7 for e in spans)
+    assert len(spans) == 6 and {e["pid"] for e in spans} == {0, 1} and all(e["tid"] == 0 for e in spans)  # small stable thread ids ...
+    assert {e["args"]["name"] for e in ev if e["ph"] == "M" and e["name"] == "thread_name"} == {"stream 7"}  # ... named after the CUDA stream
 
 
 def _emulator_vs_real(rank, world):

@@ -122,7 +122,7 @@ _ALIASES = {
     "vescale.ndtimeline.variables": "vescale_b200.profiler",
     "vescale.ndtimeline.handlers": "vescale_b200.profiler.handlers",
     "vescale.ndtimeline.handlers.handler_base": "vescale_b200.profiler.handlers",
-    "vescale.ndtimeline.handlers.chrome_trace_event": "vescale_b200.profiler.handlers",
+    "vescale.ndtimeline.handlers.chrome_trace_event": "vescale_b200.profiler.chrome_trace_event",
     "vescale.ndtimeline.handlers.local_raw_handler": "vescale_b200.profiler.handlers",
     "vescale.ndtimeline.handlers.local_timeline_handler": "vescale_b200.profiler.handlers",
     "vescale.ndtimeline.handlers.logging_handler": "vescale_b200.profiler.handlers",

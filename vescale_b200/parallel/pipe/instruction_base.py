@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import enum
 from dataclasses import dataclass, field
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
 import torch.distributed as dist
@@ -31,7 +31,9 @@ from ...profiler import ndtimeit, ndtimeit_p2p, predefined
 from .plan import PipelineParallelPlan, PipelineScheduleType
 from .schedule import INSTRUCTION_REGISTRY, Instr, StageDeps, build_schedule, register_instruction, stage_placement
 
-__all__ = ["Status", "CommPacket", "BaseInstruction", "PipelineSchema", "InstructionBuilder", "InstructionVM", "StageLink", "INSTRUCTION_SET", "get_linear_pp_module_dep2",
+Shape = Union[List[int], torch.Size]  # a p2p tensor shape as schedules pass it around
+
+__all__ = ["Shape", "register_instruction", "StageDeps", "Status", "CommPacket", "BaseInstruction", "PipelineSchema", "InstructionBuilder", "InstructionVM", "StageLink", "INSTRUCTION_SET", "get_linear_pp_module_dep2",
            "RECV_FORWARD", "RECV_BACKWARD", "SEND_FORWARD", "SEND_BACKWARD", "SEND_FORWARD_RECV_BACKWARD", "SEND_BACKWARD_RECV_FORWARD", "FORWARD_STEP", "BACKWARD_STEP",
            "WEIGHT_GRAD_STEP", "DRAIN_SEND_REQS", "DEALLOCATE_OUTPUT_TENSOR", "BUBBLE"]
 

@@ -10,12 +10,13 @@ from .timer import (  # noqa: F401
     init_ndtimers,
     is_initialized,
     ndtimeit,
+    ndtimeit_coll,
     ndtimeit_p2p,
     ndtimer,
     set_global_step,
     wait,
 )
-from .handlers import ChromeTraceNDHandler, DoNothingNDHandler, LocalRawNDHandler, LocalTimelineNDHandler, LoggingNDHandler, NDHandler, ParserNDHandler  # noqa: F401
+from .handlers import DeviceTimerStreamRecord, parse_record, ChromeTraceNDHandler, DoNothingNDHandler, LocalRawNDHandler, LocalTimelineNDHandler, LoggingNDHandler, NDHandler, ParserNDHandler  # noqa: F401
 from .sock_streamer import (  # noqa: F401
     SOCK_PARENT_DIR, SOCK_PATH, SOCK_TIMEOUT_CLIENT, NDtimelineStreamer, SockNDHandler, decode_frames, dumps_fn, encode_frame, encode_package, loads_fn,
     serialize_to_package,
@@ -34,3 +35,4 @@ NDTIMELINE_FLUSH_SEPCIAL = "special"  # step tag of an out-of-band flush (spelli
 NDTIMELINE_INNER_GLOBAL_STEP_KEY = "_inner_global_step"  # record key of the step counter maintained by inc_step / set_global_step
 NDTIMELINE_STREAM_KEY = "stream_key"  # tag naming the stream a region was timed on
 from . import predefined  # noqa: F401
+from . import chrome_trace_event  # noqa: F401,E402

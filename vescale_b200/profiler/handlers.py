@@ -83,18 +83,51 @@ class DoNothingNDHandler(NDHandler):
 
 class ChromeTraceNDHandler(NDHandler):
     """One ``chrome://tracing`` / perfetto JSON per rank; timestamps are on the aligned global clock, so files
-    from all ranks can be concatenated into one timeline (legacy ``handlers/chrome_trace_event.py``)."""
+    from all ranks can be concatenated into one timeline (legacy ``handlers/chrome_trace_event.py``).  Rows are labelled with
+    the rank's mesh coordinates (``world_info``) and stream names; ``merge(paths, out)`` joins per-rank files and draws p2p
+    flow arrows between them."""
 
     def __init__(self, out_dir: str = ".", prefix: str = "ndtimeline"):
         self.out_dir, self.prefix = out_dir, prefix
         self.events: List[dict] = []
+        self._named = set()
 
     def __call__(self, records, rank, step):
-        for r in records:
-            self.events.append({"name": r["metric"], "ph": "X", "ts": r["start_us"], "dur": r["duration_us"], "pid": rank, "tid": r.get("stream", 0), "args": {"step": step, **r.get("tags", {})}})
+        from .chrome_trace_event import ProcessMetadataEvent, records_to_events
+
+        if rank not in self._named:
+            self._named.add(rank)
+            self.events.append(ProcessMetadataEvent(pid=rank, args={"name": _rank_label(rank, getattr(self, "world_info", None))}).to_dict())
+        self.events.extend(e.to_dict() for e in records_to_events(records, rank, step))
         os.makedirs(self.out_dir, exist_ok=True)
         with open(os.path.join(self.out_dir, f"{self.prefix}_rank{rank}.json"), "w") as f:
             json.dump({"traceEvents": self.events}, f)
+
+    @staticmethod
+    def merge(paths, out_path: str, flows: bool = True) -> int:
+        """Concatenate per-rank trace files into one and (optionally) add send -> recv flow arrows; returns the event count."""
+        from .chrome_trace_event import CombinedEvents, CompleteEvent, link_p2p_flows
+
+        raw: List[dict] = []
+        for p in paths:
+            with open(p) as f:
+                raw.extend(json.load(f)["traceEvents"])
+        typed = [CompleteEvent(name=e["name"], ts=e["ts"], dur=e.get("dur", 0.0), pid=e["pid"], tid=e.get("tid", 0), args=e.get("args", {})) for e in raw if e.get("ph") == "X"]
+        extra = [f.to_dict() for f in link_p2p_flows(typed)] if flows else []
+        with open(out_path, "w") as f:
+            json.dump({"traceEvents": raw + extra, "displayTimeUnit": "ms"}, f)
+        return len(raw) + len(extra)
+
+
+def _rank_label(rank: int, world_info) -> str:
+    if world_info is None:
+        return f"rank {rank}"
+    try:
+        t = world_info["topo_info"] if not hasattr(world_info, "topo_info") else world_info.topo_info
+        coords = " ".join(f"{k}{getattr(t, k + '_rank')}" for k in ("pp", "dp", "tp") if getattr(t, k + "_rank", None) is not None)
+        return f"rank {rank} ({coords})" if coords else f"rank {rank}"
+    except Exception:  # noqa: BLE001
+        return f"rank {rank}"
 
 
 class LocalRawNDHandler(NDHandler):
@@ -129,15 +162,48 @@ class LocalRawNDHandler(NDHandler):
                 f.write(json.dumps({"rank": rank, "step": step, **r}) + "\n")
 
 
-class ParserNDHandler(NDHandler):
-    """Aggregates per-metric count / total / mean durations (legacy ``handlers/parser_handler.py``)."""
+@dataclasses.dataclass
+class DeviceTimerStreamRecord:
+    """One timed region in typed form (legacy ``handlers/parser_handler.py``): timestamps in seconds on the aligned global clock,
+    duration in milliseconds, plus where it ran."""
 
-    def __init__(self):
+    ts: float
+    rank: int
+    step: int
+    metric: str
+    duration: float
+    stream: Any = 0
+    tags: Dict[str, Any] = dataclasses.field(default_factory=dict)
+    world_info: Any = None
+
+    @property
+    def end_ts(self) -> float:
+        return self.ts + self.duration / 1e3
+
+
+def parse_record(records: List[dict], rank: int = 0, step: int = 0, world_info: Any = None) -> List[DeviceTimerStreamRecord]:
+    """Batch-form dict records -> typed records, ordered by start time."""
+    out = [DeviceTimerStreamRecord(ts=r["start_us"] / 1e6, rank=r.get("rank", rank), step=r.get("step", step), metric=r["metric"], duration=r["duration_us"] / 1e3,
+                                   stream=r.get("tags", {}).get("stream_key", r.get("stream", 0)), tags=dict(r.get("tags", {})), world_info=world_info) for r in records]
+    return sorted(out, key=lambda x: x.ts)
+
+
+class ParserNDHandler(NDHandler):
+    """Turns flushed records into typed ``DeviceTimerStreamRecord`` s (returned from the call, kept in ``.records``) and aggregates
+    per-metric count / total / mean durations (legacy ``handlers/parser_handler.py``)."""
+
+    def __init__(self, keep: bool = True):
         self.stats: Dict[str, List[float]] = defaultdict(list)
+        self.records: List[DeviceTimerStreamRecord] = []
+        self.keep = keep
 
     def __call__(self, records, rank, step):
         for r in records:
             self.stats[r["metric"]].append(r["duration_us"])
+        typed = parse_record(records, rank, step, getattr(self, "world_info", None))
+        if self.keep:
+            self.records.extend(typed)
+        return typed
 
     def summary(self) -> Dict[str, dict]:
         return {k: {"count": len(v), "total_us": sum(v), "mean_us": sum(v) / len(v)} for k, v in self.stats.items()}
@@ -158,23 +224,28 @@ class LocalTimelineNDHandler(NDHandler):
     (legacy ``handlers/local_timeline_handler.py``).  Meant to run inside the ``NDtimelineStreamer`` collector, where records
     of all local ranks arrive; rewrites the file atomically on every flush."""
 
-    def __init__(self, path: str = "ndtimeline_host.json"):
-        self.path = path
-        self.events: List[dict] = []
-        self._named = set()
+    def __init__(self, path: str = "ndtimeline_host.json", flows: bool = True):
+        self.path, self.flows = path, flows
+        self.records: List[tuple] = []  # (rank, step, record)
 
     def __call__(self, records, rank, step):
-        if rank not in self._named:
-            self._named.add(rank)
-            self.events.append({"name": "process_name", "ph": "M", "pid": rank, "args": {"name": f"rank {rank}"}})
-        for r in records:
-            self.events.append({"name": r["metric"], "cat": "ndtimeline", "ph": "X", "ts": r["start_us"], "dur": r["duration_us"], "pid": rank,
-                                "tid": r.get("stream", 0), "args": {"step": step, **r.get("tags", {})}})
-        tmp = self.path + ".tmp"
-        os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
-        with open(tmp, "w") as f:
-            json.dump({"traceEvents": self.events, "displayTimeUnit": "ms"}, f)
-        os.replace(tmp, self.path)
+        from .chrome_trace_event import CombinedEvents, ProcessMetadataEvent, ThreadMetadataEvent, build_thread_index_table, link_p2p_flows, records_to_events
+
+        self.records.extend((rank, step, r) for r in records)
+        key = lambda r: r.get("tags", {}).get("stream_key", r.get("stream", 0))  # noqa: E731
+        table = build_thread_index_table((rk, key(r)) for rk, _, r in self.records)
+        doc = CombinedEvents()
+        for rk in sorted({rk for rk, _, _ in self.records}):
+            doc.append(ProcessMetadataEvent(pid=rk, args={"name": _rank_label(rk, getattr(self, "world_info", None) if rk == rank else None)}))
+        for (rk, stream), tid in table.items():
+            doc.append(ThreadMetadataEvent(pid=rk, tid=tid, args={"name": f"stream {stream}" if stream not in (0, "compute", "main") else "compute"}))
+        slices = []
+        for rk, st, r in self.records:
+            slices.extend(records_to_events([r], rk, st, table))
+        doc.extend(slices)
+        if self.flows:
+            doc.extend(link_p2p_flows(slices))
+        doc.dump(self.path)
 
 
 def __getattr__(name):  # ``handlers.SockNDHandler`` lives with its protocol in sock_streamer.py (which imports this module)

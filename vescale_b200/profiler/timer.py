@@ -25,7 +25,7 @@ from .handlers import NDHandler
 from .pool import CudaEventPool
 from .world_info import WorldInfo
 
-__all__ = ["NDTimerManager", "NDMetricLevel", "init_ndtimers", "ndtimeit", "ndtimeit_p2p", "ndtimer", "flush", "wait", "inc_step", "set_global_step", "is_initialized", "DeviceTimerMeta", "NDTimerManagerSingleton"]
+__all__ = ["NDTimerManager", "NDMetricLevel", "init_ndtimers", "ndtimeit", "ndtimeit_p2p", "ndtimeit_coll", "ndtimer", "flush", "wait", "inc_step", "set_global_step", "is_initialized", "DeviceTimerMeta", "NDTimerManagerSingleton"]
 
 
 class NDMetricLevel(IntEnum):
@@ -228,6 +228,17 @@ def ndtimeit(metric: str, level: NDMetricLevel = NDMetricLevel.INFO, stream=None
 
 def ndtimeit_p2p(metric: str, group=None, peer: Optional[int] = None, **tags):
     return ndtimeit(metric, NDMetricLevel.INFO, None, peer=peer, **tags)
+
+
+def ndtimeit_coll(metric: str, group=None, tensor: Optional[torch.Tensor] = None, **tags):
+    """Time a collective on the stream it runs on: the stream registered for this metric / group (``profiler.stream``), else the
+    current stream; the payload size goes into the tags."""
+    from .stream import get_nccl_coll_stream
+
+    stream = get_nccl_coll_stream(metric, group, tensor) if torch.cuda.is_available() else None
+    if tensor is not None:
+        tags.setdefault("bytes", tensor.numel() * tensor.element_size())
+    return ndtimeit(metric, NDMetricLevel.INFO, stream, **tags)
 
 
 def ndtimer(metric: str, level: NDMetricLevel = NDMetricLevel.INFO):
