@@ -207,7 +207,7 @@ def test_scheduler_properties():
     from vescale_b200.parallel.pipe._schedules import InterleavedOneFOneBInstructionGenerator, OneFOneBInstrcutionGenerator, StageDeps
 
     gen = InterleavedOneFOneBInstructionGenerator(StageDeps(8), [None] * 4, 8)
-    assert len(gen.get_instruction_list(3)) == 32 and gen.bubble_fraction() < OneFOneBInstrcutionGenerator(StageDeps(4), [None] * 4, 8).bubble_fraction()
+    assert len(gen.schema.rows[3]) == 32 and sum(i.name in ('FWD', 'BWD') for i in gen.get_instruction_list(3)) == 32 and gen.bubble_fraction() < OneFOneBInstrcutionGenerator(StageDeps(4), [None] * 4, 8).bubble_fraction()
     try:
         validate_pipeline_schedule(PipelineParallelPlan(num_stages=2, virtual_chunks=2, schedule_type=PipelineScheduleType.SIMPLE_1F1B))
         raise AssertionError("SIMPLE_1F1B with two chunks must be rejected")

@@ -247,3 +247,139 @@ def test_fx_tracers_keep_partition_units_opaque():
     o = g(ids) if hasattr(g, "fx_error") else g(input_ids=ids)
     torch.testing.assert_close(o.logits if hasattr(o, "logits") else o[0], hf(input_ids=ids).logits, rtol=1e-4, atol=1e-5)
     assert g.class_for_deserialization is LlamaForCausalLM and g.config is hf.config
+
+
+def _closed_form(rank, world, which):
+    """The three explicit instruction programs (closed-form 1F1B, interleaved with posted receives, cost-driven ZB-V) run on the VM
+    and reproduce the single-process loss and gradients; their registered bodies are the override points."""
+    from vescale_b200 import init_device_mesh
+    from vescale_b200.parallel.pipe import construct_pipeline_stage
+    from vescale_b200.parallel.pipe._schedules import InterleavedOneFOneBInstructionGenerator, OneFOneBInstrcutionGenerator, StageDeps, ZeroBubbleVInstrcutionGenerator
+    from vescale_b200.parallel.pipe.auto_schedule import check_schedule
+    from vescale_b200.parallel.pipe.instruction_base import InstructionBuilder
+    from vescale_b200.parallel.pipe.schedule import INSTRUCTION_REGISTRY, register_instruction
+
+    dev = device_type()
+    ref = make_model().to(dev)
+    model = copy.deepcopy(ref)
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("PP",))
+    M = 8
+    if which == "1f1b":
+        gen = OneFOneBInstrcutionGenerator(StageDeps(world), [None] * world, M)
+        body, marker = "vescale_1f1b_forward_step", "POP_INPUT"
+    elif which == "interleaved":
+        gen = InterleavedOneFOneBInstructionGenerator(StageDeps(2 * world), [None] * world, M)
+        body, marker = "vescale_interleavd_1f1b_forward", "WAIT_FWD"
+    else:
+        gen = ZeroBubbleVInstrcutionGenerator(StageDeps(2 * world), [None] * world, M, f_cost=1.0, b_cost=1.0, w_cost=0.8, c_cost=0.1, post_validation=True)
+        body, marker = "vescale_zbv_forward", "WEIGHT_GRAD_STEP"
+    plan = gen.plan
+    check_schedule(gen.schema.rows, plan, M)
+    progs = gen.gen_instruction()
+    InstructionBuilder.check_streams(gen.programs)
+    assert marker in gen.gen_instruction_str_list()[rank] or marker in ",".join(i.name for i in progs[rank])
+    pm = construct_pipeline_stage(model, plan, mesh)
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(3, 16, generator=g).to(dev) for _ in range(M)]
+    ys = [torch.randn(3, 16, generator=g).to(dev) for _ in range(M)]
+    loss_fn = lambda out, y: torch.nn.functional.mse_loss(out, y)  # noqa: E731
+    calls = []
+    stock = INSTRUCTION_REGISTRY[body]
+
+    @register_instruction(body)
+    def counted(vm, ins):  # replace one step of every program of this schedule, delegate to the stock body
+        calls.append((ins.microbatch, ins.vstage))
+        return stock(vm, ins)
+
+    try:
+        loss, outs = gen.execute(rank, pm, xs, ys, pp_group=mesh.get_group("PP"), loss_fn=loss_fn, device=dev)
+    finally:
+        INSTRUCTION_REGISTRY[body] = stock
+    assert len(calls) == M * plan.virtual_chunks
+    ref_loss = sum(loss_fn(ref(x), y) / M for x, y in zip(xs, ys))
+    ref_loss.backward()
+    owner_of_last = 0 if which == "zbv" else world - 1
+    if rank == owner_of_last:
+        torch.testing.assert_close(loss, ref_loss.detach(), rtol=1e-5, atol=1e-6)
+    else:
+        assert loss is None
+    ref_params = dict(ref.named_parameters())
+    checked = 0
+    for c in range(pm.num_chunks):
+        stage = pm.chunk(c)
+        names = getattr(stage, "names", None)
+        for n, p in stage.named_parameters():
+            fq = n
+            if names is not None:
+                _, idx, rest = n.split(".", 2)
+                fq = f"{names[int(idx)]}.{rest}"
+            torch.testing.assert_close(p.grad, ref_params[fq].grad, rtol=1e-4, atol=1e-6)
+            checked += 1
+    assert checked == 2 * (8 // world)
+    if which == "1f1b":  # the FIFO instructions enforce the 1F1B retirement order: a program that breaks it fails loudly
+        from vescale_b200.parallel.pipe._schedules.pipedream_flush import BACKWARD_STEP, POP_INPUT
+
+        bad = list(progs[rank])
+        k = next(i for i, ins in enumerate(bad) if isinstance(ins, POP_INPUT))
+        j = next(i for i, ins in enumerate(bad) if isinstance(ins, BACKWARD_STEP))
+        assert bad[j].microbatch == bad[k].microbatch == 0
+        assert gen.schema.warmup_batches == [min(world - 1 - s, M) for s in range(world)]
+        assert gen.schema.phase(0, gen.schema.rows[0][0]) == "WUp"
+
+
+@pytest.mark.parametrize("which", ["1f1b", "interleaved", "zbv"])
+def test_closed_form_schedule_programs(which):
+    run_distributed(_closed_form, 4, which)
+
+
+def test_user_written_programs_and_compile_operators():
+    """``build_from_dict`` / ``run`` (functions by name, state on the builder), compile operators, ``CostGraph`` node lists."""
+    from vescale_b200.parallel.pipe._schedules import CostGraph
+    from vescale_b200.parallel.pipe._schedules.common import timestamp_orders
+    from vescale_b200.parallel.pipe._schedules.pipedream_flush import PipeDream, one_f_one_b_order
+    from vescale_b200.parallel.pipe.instruction_base import (VESCALE_INTRUCTION_BUILDER as builder, CompilePPCollectiveKind, CompilePPCollectiveOperator, register_instruction)
+    from vescale_b200.parallel.pipe.plan import PipelineParallelPlan, PipelineScheduleType
+
+    @register_instruction("t_load")
+    def _load():
+        return builder.dataloader[builder.pos // 2]
+
+    @register_instruction("t_double")
+    def _double():
+        return builder.last * 2
+
+    builder.dataloader = [torch.ones(2), torch.full((2,), 3.0)]
+    builder.build_from_dict({0: "t_load,t_double,t_load,t_double", 1: ["t_load"]})
+    out = builder.run(0)
+    assert [float(o[0]) for o in out] == [1.0, 2.0, 3.0, 6.0] and builder.pos == 3
+    assert "t_double" in builder.draw_user_instructions()
+    with pytest.raises(KeyError):
+        builder.build_from_dict({0: "no_such_instruction"})
+
+    a, b = CompilePPCollectiveOperator(CompilePPCollectiveKind.SEND, dst=1), CompilePPCollectiveOperator(CompilePPCollectiveKind.SEND, dst=1)
+    assert a == b and len({a, b, CompilePPCollectiveOperator(CompilePPCollectiveKind.RECV, src=0, is_backward=True)}) == 2
+    CompilePPCollectiveOperator(CompilePPCollectiveKind.BORADCAST, src=0, dst=[0, 1, 2])
+    with pytest.raises(ValueError):
+        CompilePPCollectiveOperator(CompilePPCollectiveKind.BORADCAST, src=3, dst=[0, 1])
+
+    # closed-form 1F1B == the list scheduler's 1F1B (same makespan with unit costs); a cyclic order is reported, not hung on
+    from vescale_b200.parallel.pipe.schedule import build_schedule, makespan
+
+    for P, M in ((4, 8), (4, 2), (3, 7)):
+        sc = PipeDream(P, M)
+        assert makespan(sc.rows) == 3 * (M + P - 1) == makespan(build_schedule(sc.plan, M))  # F = 1, unsplit B = B + W = 2
+    plan = PipelineParallelPlan(num_stages=2, schedule_type=PipelineScheduleType.SIMPLE_1F1B)
+    with pytest.raises(RuntimeError, match="deadlock"):
+        timestamp_orders([[("B", 0, 0), ("F", 0, 0)], [("F", 0, 1), ("B", 0, 1)]], plan)
+    assert one_f_one_b_order(0, 4, 8)[:4] == [("F", 0, 0), ("F", 1, 0), ("F", 2, 0), ("F", 3, 0)]
+
+    cg = CostGraph(4, 8, 1.0, 1.0, 1.0, 0.0)
+    nodes = cg.get_v_schedule()
+    assert len(nodes) == 4 and sum(n.type in "FBW" for n in nodes[0]) == 8 * 2 * 3
+    sends = sum(n.type.startswith("SEND") for st in nodes for n in st)
+    recvs = sum(n.type.startswith("RECV") for st in nodes for n in st)
+    assert sends == recvs > 0
+    f0 = next(n for n in nodes[0] if n.type == "F" and n.chunk == 0)
+    assert [p.peer_stage for p in f0.get_send_comms(4)] == [1] and f0.get_recv_comms(4) == []
+    assert cg.get_v_schedule(only_run_time=True) <= cg.try_v_schedule(fill_f=False)[1] + 1e-9
+    assert "stage 3" in cg.print_details()

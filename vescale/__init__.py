@@ -70,9 +70,6 @@ _ALIASES = {
     "vescale.pipe._schedules": "vescale_b200.parallel.pipe._schedules",
     "vescale.pipe._schedules.instruction_base": "vescale_b200.parallel.pipe.instruction_base",
     "vescale.pipe._schedules.pp_collective_emitter": "vescale_b200.parallel.pipe.graph_emitter",
-    "vescale.pipe._schedules.pipedream_flush": "vescale_b200.parallel.pipe._schedules",
-    "vescale.pipe._schedules.looping_bfs": "vescale_b200.parallel.pipe._schedules",
-    "vescale.pipe._schedules.zero_bubble_v": "vescale_b200.parallel.pipe._schedules",
     "vescale.plan.spec": "vescale_b200.parallel.pipe.plan",
     "vescale.plan.pipeline_parallel": "vescale_b200.parallel.pipe.plan",
     "vescale.engine.pipe": "vescale_b200.parallel.pipe.engine",

@@ -2,17 +2,19 @@
 Generator``, ``InterleavedOneFOneBInstructionGenerator``, ``ZeroBubbleVInstrcutionGenerator`` — the reference's spellings are
 kept so that user code importing them keeps working).
 
-Every schedule here is one instance of the same event-driven list scheduler (``schedule.build_schedule``); a generator only
-fixes the schedule type / chunk count and exposes the per-stage instruction lists the way the reference's generators do
-(``gen_instruction()``, ``get_instruction_list(stage)``).  Execution is the engine's job (``PipeEngine`` / ``ScheduleEngine``)."""
+``InstructionGenerator`` (and the GPipe / ZB-H1 generators) expose the rows of the event-driven list scheduler
+(``schedule.build_schedule``) the way the reference's generators do (``gen_instruction()``, ``get_instruction_list(stage)``);
+executing those rows is the engine's job (``PipeEngine`` / ``ScheduleEngine``).  1F1B, interleaved 1F1B and ZB-V additionally have
+explicit instruction PROGRAMS with communication spelled out (``pipedream_flush.py``, ``looping_bfs.py``, ``zero_bubble_v.py``); those
+generators ``execute`` on the ``InstructionVM``."""
 from __future__ import annotations
 
 from typing import List, Optional, Sequence, Union
 
 import torch
 
-from .plan import PipelineParallelPlan, PipelineScheduleType
-from .schedule import Instr, StageDeps, bubble_fraction, build_schedule, register_instruction
+from ..plan import PipelineParallelPlan, PipelineScheduleType
+from ..schedule import Instr, StageDeps, bubble_fraction, build_schedule, register_instruction
 
 __all__ = ["Shape", "StageDeps", "register_instruction", "InstructionGenerator", "OneFOneBInstrcutionGenerator", "InterleavedOneFOneBInstructionGenerator",
            "ZeroBubbleVInstrcutionGenerator", "ZeroBubbleInstructionGenerator", "GPipeInstructionGenerator"]
@@ -71,19 +73,14 @@ class GPipeInstructionGenerator(InstructionGenerator):
     schedule_type = PipelineScheduleType.GPIPE
 
 
-class OneFOneBInstrcutionGenerator(InstructionGenerator):
-    schedule_type = PipelineScheduleType.SIMPLE_1F1B
-
-
-class InterleavedOneFOneBInstructionGenerator(InstructionGenerator):
-    schedule_type = PipelineScheduleType.INTERLEAVED_1F1B
-    default_chunks = 2
-
-
 class ZeroBubbleInstructionGenerator(InstructionGenerator):
     schedule_type = PipelineScheduleType.ZERO_BUBBLE
 
 
-class ZeroBubbleVInstrcutionGenerator(InstructionGenerator):
-    schedule_type = PipelineScheduleType.ZERO_BUBBLE_V
-    default_chunks = 2
+# The three schedules the reference spells out as instruction programs live in modules of their own (closed-form order, their own
+# instruction sets, registered bodies, ``execute`` on the InstructionVM); they subclass ``InstructionGenerator`` above.
+from .pipedream_flush import OneFOneBInstrcutionGenerator, PipeDream  # noqa: E402
+from .looping_bfs import InterleavedOneFOneBInstructionGenerator, InterleavedPipeDreramFlush  # noqa: E402
+from .zero_bubble_v import CostGraph, ScheduledNode, ZeroBubbleVInstrcutionGenerator  # noqa: E402
+
+__all__ += ["PipeDream", "InterleavedPipeDreramFlush", "CostGraph", "ScheduledNode"]

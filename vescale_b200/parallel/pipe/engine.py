@@ -25,7 +25,7 @@ from .plan import ModeType, PipelineParallelPlan, PipelineScheduleType
 from .schedule import INSTRUCTION_REGISTRY, Instr, build_schedule, stage_placement, validate_pipeline_schedule
 from .stage import PipeModule
 
-__all__ = ["PipeEngine", "ScheduleEngine"]
+__all__ = ["PipeEngine", "ScheduleEngine", "PipelineEmitter"]
 
 
 def _as_tuple(x):
@@ -177,6 +177,43 @@ class ScheduleEngine:
             k0, t0 = timing["open"]
             timing.setdefault(k0, []).append(now - t0)
         timing["open"] = None if kind is None else (kind, now)
+
+
+class PipelineEmitter:
+    """Schedule type -> the generator that writes its instruction programs (legacy ``pipe/pipe_emmiter.py:43-129``).  1F1B, interleaved
+    1F1B and ZB-V have explicit programs (``_schedules/{pipedream_flush,looping_bfs,zero_bubble_v}.py``); GPipe and ZB-H1 expose the
+    list scheduler's rows.  ``meshes``: one entry per pipeline stage."""
+
+    def __init__(self, deps, meshes: Sequence, schedule, batches: int, tensor_shape=None, dtype: Optional[torch.dtype] = None, num_chunks: int = 1, input_shapes=None,
+                 input_shapes_unpad=None, forward_only: bool = False, overlap_p2p_comm: bool = False, batch_p2p_comm: bool = True, param_sync_overlap: bool = False,
+                 grad_sync_overlap: bool = False, **kwargs):
+        from . import _schedules as S
+
+        schedule = PipelineScheduleType(schedule) if not isinstance(schedule, PipelineScheduleType) else schedule
+        self.deps, self.meshes, self.batches, self.num_chunks, self.forward_only = deps, meshes, batches, num_chunks, forward_only
+        self.num_stage = len(meshes)
+        self.overlap_p2p_comm, self.batch_p2p_comm, self.param_sync_overlap, self.grad_sync_overlap = overlap_p2p_comm, batch_p2p_comm, param_sync_overlap, grad_sync_overlap
+        common = dict(deps=deps, meshes=meshes, batches=batches, default_shape=tensor_shape, default_dtype=dtype)
+        if schedule == PipelineScheduleType.SIMPLE_1F1B:
+            self.instruction_generator = S.OneFOneBInstrcutionGenerator(forward_only=forward_only, batch_p2p_comm=batch_p2p_comm, overlap_p2p_comm=overlap_p2p_comm, **common)
+        elif schedule == PipelineScheduleType.INTERLEAVED_1F1B:
+            self.instruction_generator = S.InterleavedOneFOneBInstructionGenerator(forward_only=forward_only, num_chunk=max(2, num_chunks), batch_shape_lists=input_shapes,
+                                                                                   batch_p2p_comm=batch_p2p_comm, overlap_p2p_comm=overlap_p2p_comm, **common)
+        elif schedule in (PipelineScheduleType.ZERO_BUBBLE_V,):
+            self.instruction_generator = S.ZeroBubbleVInstrcutionGenerator(**common, **kwargs)
+        elif schedule == PipelineScheduleType.ZERO_BUBBLE:
+            self.instruction_generator = S.ZeroBubbleInstructionGenerator(forward_only=forward_only, num_chunk=num_chunks, **common)
+        elif schedule == PipelineScheduleType.GPIPE:
+            self.instruction_generator = S.GPipeInstructionGenerator(forward_only=forward_only, num_chunk=num_chunks, **common)
+        else:
+            raise NotImplementedError(f"unsupported schedule type {schedule}")
+        self.instruction_list = self.gen_instruction()
+
+    def gen_instruction(self):
+        return self.instruction_generator.gen_instruction()
+
+    def get_instruction_list(self, stage: int):
+        return self.instruction_generator.get_instruction_list(stage)
 
 
 class PipeEngine:

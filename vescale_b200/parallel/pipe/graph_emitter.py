@@ -42,7 +42,7 @@ from ...comm import functional_p2p as fp2p
 from .plan import PipelineParallelPlan
 from .schedule import stage_placement
 
-__all__ = ["PPCollectiveOpEmitter", "GraphPipeProgram", "infer_stage_meta"]
+__all__ = ["PPCollectiveOpEmitter", "GraphPipeProgram", "infer_stage_meta", "read_fg"]
 
 Meta = Tuple[Tuple[int, ...], torch.dtype]
 
@@ -91,6 +91,19 @@ def infer_stage_meta(pipe_module, plan: PipelineParallelPlan, pp_rank: int, pp_g
     return metas
 
 
+def read_fg(fg: fx.GraphModule):
+    """(number of placeholders, number of outputs) of a captured graph — what an emitter needs to know to splice communication
+    nodes around it (legacy ``pp_collective_emitter.py:35-43``).  A graph that returns a single value counts one output."""
+    n_in, n_out = 0, None
+    for node in fg.graph.nodes:
+        if node.op == "placeholder":
+            n_in += 1
+        elif node.op == "output":
+            ret = node.args[0]
+            n_out = len(ret) if isinstance(ret, (tuple, list)) else 1
+    return n_in, n_out
+
+
 class PPCollectiveOpEmitter:
     """Emits this rank's forward program.  ``gen_pp_collective_topo`` exposes the peers per chunk the way the reference's emitter
     does (``fwd_recv_srcs / fwd_send_dsts``; the backward peers are the same lists mirrored, and are never needed explicitly)."""
@@ -115,6 +128,20 @@ class PPCollectiveOpEmitter:
             self.fwd_send_dsts[c] = None if dst == self.rank else dst
         return {"fwd_recv_srcs": dict(self.fwd_recv_srcs), "fwd_send_dsts": dict(self.fwd_send_dsts),
                 "bwd_recv_srcs": dict(self.fwd_send_dsts), "bwd_send_dsts": dict(self.fwd_recv_srcs)}
+
+    def gen_pp_collective_topo_from_schedule_engine(self, engine_or_programs):
+        """The same peer sets derived from what a schedule actually does rather than from the placement: walk this rank's instruction
+        program (a generator / emitter with ``get_instruction_list``, or ``{rank: program}``) and collect every operator its
+        communication instructions compile to (legacy ``pp_collective_emitter.py:57-101``)."""
+        prog = engine_or_programs[self.rank] if isinstance(engine_or_programs, dict) else engine_or_programs.get_instruction_list(self.rank)
+        from .instruction_base import CompilePPCollectiveKind
+
+        sets = {"fwd_recv_srcs": set(), "fwd_send_dsts": set(), "bwd_recv_srcs": set(), "bwd_send_dsts": set()}
+        for ins in prog:
+            for op in ins.compile():
+                send = op.kind is CompilePPCollectiveKind.SEND
+                sets[("bwd_" if op.is_backward else "fwd_") + ("send_dsts" if send else "recv_srcs")].add(op.dst if send else op.src)
+        return {k: sorted(v) for k, v in sets.items()}
 
     # ------------------------------------------------------------------ emission
     def emit(self, num_microbatches: int, metas: Dict[int, List[Meta]], device, n_inputs: int = 1, with_labels: bool = True) -> "GraphPipeProgram":

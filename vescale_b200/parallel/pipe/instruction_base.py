@@ -34,6 +34,7 @@ from .schedule import INSTRUCTION_REGISTRY, Instr, StageDeps, build_schedule, re
 Shape = Union[List[int], torch.Size]  # a p2p tensor shape as schedules pass it around
 
 __all__ = ["Shape", "register_instruction", "StageDeps", "Status", "CommPacket", "BaseInstruction", "PipelineSchema", "InstructionBuilder", "InstructionVM", "StageLink", "INSTRUCTION_SET", "get_linear_pp_module_dep2",
+           "CompilePPCollectiveKind", "CompilePPCollectiveOperator", "VESCALE_INTRUCTION_BUILDER", "switch_dtensor", "registed_functions", "InstructionGenerator",
            "RECV_FORWARD", "RECV_BACKWARD", "SEND_FORWARD", "SEND_BACKWARD", "SEND_FORWARD_RECV_BACKWARD", "SEND_BACKWARD_RECV_FORWARD", "FORWARD_STEP", "BACKWARD_STEP",
            "WEIGHT_GRAD_STEP", "DRAIN_SEND_REQS", "DEALLOCATE_OUTPUT_TENSOR", "BUBBLE"]
 
@@ -48,12 +49,21 @@ class Status(enum.Enum):
 
 @dataclass(frozen=True)
 class CommPacket:
-    """One tensor bundle in flight: who produces it, who consumes it, under which key."""
-    kind: str  # "F" activation / "B" gradient
-    microbatch: int
-    vstage: int  # virtual stage that PRODUCED it
-    src: int
-    dst: int
+    """One tensor bundle in flight: who produces it, who consumes it, under which key.  The optional fields describe a stage boundary
+    whose two sides live on different (tensor-parallel) meshes (legacy ``instruction_base.py:75-83``): which input slot of the consumer it
+    feeds, and the placements on either side — ``cross_mesh_send`` / ``cross_mesh_recv`` (``_schedules/common.py``) use them."""
+    kind: str = "F"  # "F" activation / "B" gradient
+    microbatch: int = -1
+    vstage: int = -1  # virtual stage that PRODUCED it
+    src: int = -1
+    dst: int = -1
+    cur_mesh: object = None
+    peer_mesh: object = None
+    input_id: int = 0
+    peer_stage: int = -1
+    peer_sharding: Optional[tuple] = None
+    cur_sharding: Optional[tuple] = None
+    is_kwargs: bool = False
 
     @property
     def key(self) -> Tuple[str, int, int]:
@@ -81,12 +91,26 @@ class BaseInstruction:
 
     name = "BASE"
 
+    handler = None  # class-level: name of the registered function that does the work (schedule-specific instruction sets)
+
     def __init_subclass__(cls, **kw):
         super().__init_subclass__(**kw)
-        INSTRUCTION_SET[cls.name] = cls
+        INSTRUCTION_SET.setdefault(cls.name, cls)  # the first definition of a name is the canonical one (schedule modules refine, not replace)
 
     def run(self, vm: "InstructionVM") -> None:
-        raise NotImplementedError
+        """Schedule-specific instruction sets name the registered function that implements them (``handler``): re-registering that
+        name (``register_instruction("vescale_1f1b_forward_step")``) swaps the behaviour for every program of that schedule."""
+        h = type(self).handler
+        if h is None:
+            raise NotImplementedError
+        return INSTRUCTION_REGISTRY[h](vm, self)
+
+    def compile(self) -> List["CompilePPCollectiveOperator"]:
+        """The p2p operators this instruction stands for, as the graph emitter wants them (legacy ``BaseInstruction.compile``)."""
+        out = []
+        for kind, m, v, peer, is_send in _wire_ops(self):
+            out.append(CompilePPCollectiveOperator(CompilePPCollectiveKind.SEND if is_send else CompilePPCollectiveKind.RECV, src=None if is_send else peer, dst=peer if is_send else None, is_backward=(kind == "B")))
+        return out
 
     def dump(self) -> str:
         where = f" peer={self.peer}" if self.peer >= 0 else ""
@@ -211,6 +235,75 @@ class BUBBLE(BaseInstruction):  # noqa: N801
 
     def run(self, vm):
         pass
+
+
+# ---- p2p operators for graph mode ----------------------------------------------------------------------------------------------------------
+class CompilePPCollectiveKind(enum.Enum):
+    SEND = 1
+    RECV = 2
+    BORADCAST = 3  # (sic, the reference's spelling) one source, several destinations: a stage boundary that fans out across meshes
+    UNKNOWN = 4
+
+
+class CompilePPCollectiveOperator:
+    """What a communication instruction turns into when a rank's program is compiled to a graph (``graph_emitter.py``): a send to
+    ``dst``, a receive from ``src``, or a broadcast from ``src`` to the ranks ``dst`` (which contain ``src``).  Hashable, so an emitter
+    can de-duplicate the process groups / buffers it creates per distinct operator."""
+
+    def __init__(self, kind: CompilePPCollectiveKind, src: Optional[int] = None, dst: Union[int, Sequence[int], None] = None, is_backward: bool = False):
+        if kind is CompilePPCollectiveKind.SEND:
+            if not isinstance(dst, int):
+                raise ValueError("a SEND names one destination rank")
+        elif kind is CompilePPCollectiveKind.RECV:
+            if not isinstance(src, int):
+                raise ValueError("a RECV names one source rank")
+        elif kind is CompilePPCollectiveKind.BORADCAST:
+            if not isinstance(src, int) or isinstance(dst, int) or dst is None or src not in list(dst):
+                raise ValueError("a BORADCAST names a source rank and a list of ranks that contains it")
+            dst = tuple(dst)
+        else:
+            raise ValueError(f"cannot compile a collective of kind {kind}")
+        self.kind, self.src, self.dst, self.is_backward = kind, src, dst, bool(is_backward)
+
+    def _key(self):
+        return (self.kind, self.src, self.dst, self.is_backward)
+
+    def __hash__(self) -> int:
+        return hash(self._key())
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, CompilePPCollectiveOperator) and self._key() == other._key()
+
+    def __repr__(self):
+        arrow = f"-> {self.dst}" if self.kind is CompilePPCollectiveKind.SEND else (f"<- {self.src}" if self.kind is CompilePPCollectiveKind.RECV else f"{self.src} => {self.dst}")
+        return f"{self.kind.name}{'(bwd)' if self.is_backward else ''} {arrow}"
+
+
+def switch_dtensor(fn: Callable) -> Callable:
+    """Decorator for instruction bodies that move tensors over the wire: DTensor arguments go in as their local shards, and a result
+    that corresponds to a DTensor argument comes back wrapped with that argument's mesh and placements (legacy
+    ``instruction_base.py:42-55``)."""
+    import functools
+
+    from ...dtensor.api import DTensor
+
+    @functools.wraps(fn)
+    def wrap(*args, **kwargs):
+        specs = [(a.device_mesh, a.placements) if isinstance(a, DTensor) else None for a in args]
+        out = fn(*[a.to_local() if isinstance(a, DTensor) else a for a in args], **{k: (v.to_local() if isinstance(v, DTensor) else v) for k, v in kwargs.items()})
+        live = [s for s in specs if s is not None]
+        if not live or out is None:
+            return out
+        def rewrap(t, spec):
+            return DTensor.from_local(t, spec[0], spec[1], run_check=False) if isinstance(t, torch.Tensor) and not isinstance(t, DTensor) else t
+        if isinstance(out, (tuple, list)):
+            return type(out)(rewrap(t, live[min(i, len(live) - 1)]) for i, t in enumerate(out))
+        return rewrap(out, live[0])
+
+    return wrap
+
+
+registed_functions = INSTRUCTION_REGISTRY  # the reference's name (and spelling) for the registry dict
 
 
 # ---- schedule grid ---------------------------------------------------------------------------------------------------------------------------
@@ -343,6 +436,84 @@ class InstructionBuilder:
                 i += 1
         return out
 
+
+    # -- user-written programs (legacy ``instruction_base.py:436-520``) ------------------------------------------------------------------------
+    # A power user can skip schedules altogether: register plain functions under names, give every stage a comma-separated list of
+    # those names, and ``run(stage_id)`` calls them in order.  The functions take no arguments; they talk to each other through the
+    # builder: ``builder.last`` is what the previous function returned, ``builder.pos`` its own index, and anything else the user hangs
+    # on the builder (``builder.model``, ``builder.dataloader``, ``builder.topo``, ``builder.stage_id`` ...).
+    def build_from_dict(self, instructions: Dict) -> None:
+        if not isinstance(instructions, dict):
+            raise TypeError("instructions: {stage_id: 'name,name,...' | [names]}")
+        self.global_instructions_funcs, self.global_instructions_str = getattr(self, "global_instructions_funcs", {}), getattr(self, "global_instructions_str", {})
+        for stage_id, names in instructions.items():
+            names = [n.strip() for n in names.split(",")] if isinstance(names, str) else list(names)
+            missing = [n for n in names if n not in INSTRUCTION_REGISTRY]
+            if missing:
+                raise KeyError(f"stage {stage_id}: instructions {missing} are not registered (register_instruction(name))")
+            self.global_instructions_funcs[stage_id] = [INSTRUCTION_REGISTRY[n] for n in names]
+            self.global_instructions_str[stage_id] = names
+
+    @property
+    def pos(self) -> int:
+        return getattr(self, "_pos", 0)
+
+    @property
+    def last(self):
+        return getattr(self, "_stack", None)
+
+    def run(self, stage_id: int) -> List:
+        """Call stage ``stage_id``'s functions in order; returns every function's result."""
+        out = []
+        for pos, fn in enumerate(getattr(self, "global_instructions_funcs", {}).get(stage_id, [])):
+            self._pos = pos
+            self._stack = fn()
+            out.append(self._stack)
+        return out
+
+    def export(self, stage_id: int, *args, **kwargs):
+        """``torch.export`` of one stage's user program: the functions run in order on (args, kwargs); the one called ``forward``
+        is the stage module (``builder.model``)."""
+        funcs, model = list(self.global_instructions_funcs[stage_id]), self.model
+
+        class _Program(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.model = model
+
+            def forward(self, *a, **kw):
+                for f in funcs:
+                    if getattr(f, "__name__", "") == "forward":
+                        a, kw = (self.model(*a, **kw),), {}
+                    else:
+                        a, kw = f(*a, **kw)
+                return a, kw
+
+        return torch.export.export(_Program(), args, kwargs or None)
+
+    def draw_user_instructions(self, path: Optional[str] = None) -> str:
+        """The user programs as a text table (one row per stage); with ``path`` also as a picture when matplotlib is installed."""
+        rows = getattr(self, "global_instructions_str", {})
+        w = max((len(n) for names in rows.values() for n in names), default=1)
+        text = "\n".join(f"stage {s}: " + " | ".join(n.ljust(w) for n in names) for s, names in sorted(rows.items()))
+        if path is not None:
+            try:
+                from matplotlib import pyplot as plt
+            except ImportError:
+                return text
+            fig, ax = plt.subplots()
+            for s, names in sorted(rows.items()):
+                for k, n in enumerate(names):
+                    ax.add_patch(plt.Rectangle((k, -s), 1, 1, fill=False, edgecolor="black", lw=2))
+                    ax.text(k + 0.5, -s + 0.5, n, ha="center", va="center")
+                ax.text(-0.5, -s + 0.5, str(s), ha="center", va="center")
+            ax.set_xlim(0, max(len(n) for n in rows.values()))
+            ax.set_ylim(-len(rows) + 1, 1)
+            ax.axis("off")
+            fig.savefig(path)
+            plt.close(fig)
+        return text
+
     # -- inspection ------------------------------------------------------------------------------------------------------------------------
     def dump_instructions(self, rank: Optional[int] = None) -> str:
         ranks = [rank] if rank is not None else sorted(self.programs)
@@ -350,7 +521,9 @@ class InstructionBuilder:
 
     def draw_instructions(self, width: int = 6) -> str:
         """One line per rank, one cell per instruction, compute steps only (F3 / B3 / W3): the classic pipeline diagram."""
-        sym = {"FORWARD_STEP": "F", "BACKWARD_STEP": "B", "WEIGHT_GRAD_STEP": "W"}
+        if not self.programs and getattr(self, "global_instructions_str", None):
+            return self.draw_user_instructions()
+        sym = {"FORWARD_STEP": "F", "BACKWARD_STEP": "B", "WEIGHT_GRAD_STEP": "W", "FWD": "F", "BWD": "B"}
         return "\n".join(f"rank {r}: " + " ".join(f"{sym[i.name]}{i.microbatch}".ljust(width) for i in self.programs[r] if i.name in sym) for r in sorted(self.programs))
 
     @staticmethod
@@ -369,7 +542,10 @@ class InstructionBuilder:
 
 
 def _wire_ops(ins: BaseInstruction):
-    if isinstance(ins, SEND_FORWARD):
+    own = getattr(ins, "wire_ops", None)
+    if own is not None:
+        yield from own()
+    elif isinstance(ins, SEND_FORWARD):
         yield ("F", ins.microbatch, ins.vstage, ins.peer, True)
     elif isinstance(ins, SEND_BACKWARD):
         yield ("B", ins.microbatch, ins.vstage, ins.peer, True)
@@ -596,3 +772,14 @@ class InstructionVM:
         for o in outs:
             if isinstance(o, torch.Tensor) and o._base is None and o.grad_fn is not None and o.numel() > 1:
                 o.data = torch.empty((1,), device=o.device, dtype=o.dtype)
+
+
+VESCALE_INTRUCTION_BUILDER = InstructionBuilder()  # the process-wide builder user programs hang their state on (the reference's spelling)
+
+
+def __getattr__(name):  # ``InstructionGenerator`` lives with the generators; importing it here eagerly would be a cycle
+    if name == "InstructionGenerator":
+        from ._schedules import InstructionGenerator
+
+        return InstructionGenerator
+    raise AttributeError(name)
