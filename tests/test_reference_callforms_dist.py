@@ -76,3 +76,113 @@ def _interleaved_through_matmul(rank, world):
 
 def test_interleaved_shard_through_flatten_matmul_unflatten():
     run_distributed(_interleaved_through_matmul, 2)
+
+
+def _custom_rules(rank, world):
+    """A user's custom op gets its sharding behaviour through the reference's two registration contracts."""
+    import torch
+    from vescale_b200 import DTensor, Replicate, Shard, distribute_tensor, init_device_mesh
+    from vescale_b200.dtensor.op_schema import OpSchema, OpStrategy, OutputSharding, PlacementStrategy
+    from vescale_b200.dtensor.ops.basic_strategy import gen_einsum_strategies
+    from vescale_b200.dtensor.ops.common_rules import einop_rule, pointwise_rule
+    from vescale_b200.dtensor.ops.utils import generate_redistribute_costs, is_tensor_partial, register_op_strategy, register_prop_rule
+    from vescale_b200.placement import Partial
+    from vescale_b200.spec import DTensorSpec
+
+    lib = torch.library.Library("vb_test", "FRAGMENT")  # noqa: TOR901
+    lib.define("scaled_mm(Tensor a, Tensor b, float s) -> Tensor")
+    lib.define("shift(Tensor a, Tensor b) -> Tensor")
+    lib.impl("scaled_mm", lambda a, b, s: (a @ b) * s, "CompositeExplicitAutograd")
+    lib.impl("shift", lambda a, b: a + b, "CompositeExplicitAutograd")
+    mm_op, shift_op = torch.ops.vb_test.scaled_mm.default, torch.ops.vb_test.shift.default
+
+    @register_prop_rule(mm_op)
+    def _mm_rule(schema: OpSchema) -> OutputSharding:
+        return einop_rule("mk,kn->mn", schema, linearity=False)
+
+    seen = {}
+
+    @register_op_strategy(shift_op)
+    def _shift_strategy(mesh, schema):
+        a, b = schema.args_schema
+        assert isinstance(a, OpStrategy) and isinstance(b, OpStrategy)
+        seen["cur"] = (a.strategies[0].output_spec.placements, b.strategies[0].output_spec.placements)
+        alts = []
+        for pl in ([Shard(0)], [Replicate()]):
+            spec = DTensorSpec(mesh, tuple(pl))
+            alts.append(PlacementStrategy(output_spec=spec, input_specs=[spec, spec], redistribute_cost=[generate_redistribute_costs(a, spec), generate_redistribute_costs(b, spec)]))
+        return OpStrategy(alts)
+
+    mesh = init_device_mesh("cpu", (world,), mesh_dim_names=("TP",))
+    torch.manual_seed(0)
+    A, B = torch.randn(8, 12), torch.randn(12, 6)
+    # row-parallel: contraction sharded -> the einop rule leaves the output Partial; the product is right after reduction
+    dA, dB = distribute_tensor(A, mesh, [Shard(1)]), distribute_tensor(B, mesh, [Shard(0)])
+    out = mm_op(dA, dB, 0.5)
+    assert isinstance(out, DTensor) and out.placements[0].is_partial()
+    torch.testing.assert_close(out.full_tensor(), (A @ B) * 0.5, rtol=1e-5, atol=1e-5)
+    # conflicting layouts (both operands sharded along the SAME mesh dim on m and n): the rule answers with a suggestion, inputs are resharded
+    out = mm_op(distribute_tensor(A, mesh, [Shard(0)]), distribute_tensor(B, mesh, [Shard(1)]), 2.0)
+    torch.testing.assert_close(out.full_tensor(), (A @ B) * 2.0, rtol=1e-5, atol=1e-5)
+    # a Partial operand into a non-linear rule is reduced first
+    P = DTensor.from_local(A / world, mesh, [Partial("sum")], run_check=False)
+    out = mm_op(P, distribute_tensor(B, mesh, [Replicate()]), 1.0)
+    torch.testing.assert_close(out.full_tensor(), A @ B, rtol=1e-5, atol=1e-5)
+    # strategy contract: the cheapest alternative given the current layouts wins (both sharded -> stays sharded, no communication)
+    X, Y = torch.randn(8, 4), torch.randn(8, 4)
+    out = shift_op(distribute_tensor(X, mesh, [Shard(0)]), distribute_tensor(Y, mesh, [Shard(0)]))
+    assert out.placements == (Shard(0),) and seen["cur"] == ((Shard(0),), (Shard(0),))
+    torch.testing.assert_close(out.full_tensor(), X + Y)
+    out = shift_op(distribute_tensor(X, mesh, [Replicate()]), distribute_tensor(Y, mesh, [Shard(0)]))
+    torch.testing.assert_close(out.full_tensor(), X + Y)
+
+    # the building blocks on their own
+    sa = DTensorSpec(mesh, (Shard(0),), dA._spec.tensor_meta)
+    sb = DTensorSpec(mesh, (Replicate(),), dB._spec.tensor_meta)
+    r = einop_rule("mk,kn->mn", OpSchema(mm_op, (sa, sb, 1.0), {}, mesh))
+    assert r.output_spec.placements == (Shard(0),) and not is_tensor_partial(r.output_spec)
+    r = einop_rule("mk,kn->mn", OpSchema(mm_op, (sa, sb, 1.0), {}, mesh), enforce_sharding={"m": -1})
+    assert r.output_spec is None and r.schema_suggestions[0].args_spec[0].placements == (Replicate(),)
+    from vescale_b200.spec import TensorMeta
+    bias = DTensorSpec(mesh, (Shard(0),), TensorMeta((6,), (1,), torch.float32))
+    act = DTensorSpec(mesh, (Shard(1),), TensorMeta((8, 6), (6, 1), torch.float32))
+    r = pointwise_rule(OpSchema(shift_op, (act, bias), {}, mesh))
+    assert r.output_spec.placements == (Shard(1),)  # the bias' dim 0 IS the activation's dim 1 after right-alignment
+    one = DTensorSpec(mesh, (Replicate(),), TensorMeta((8, 1), (1, 1), torch.float32))
+    assert pointwise_rule(OpSchema(shift_op, (act, one), {}, mesh)).output_spec.placements == (Shard(1),)
+    strat = gen_einsum_strategies("bmk,bkn->bmn", mesh)
+    outs = {s.output_spec.placements for s in strat.strategies}
+    assert outs == {(Replicate(),), (Shard(0),), (Shard(1),), (Shard(2),), (Partial("sum"),)}
+    assert len(gen_einsum_strategies("mk,kn->mn", mesh, linearity=True).strategies) == 5
+    lib._destroy()
+
+
+def test_custom_op_rules_through_reference_registration_contracts():
+    run_distributed(_custom_rules, 4)
+
+
+def _cross_mesh_autograd(rank, world):
+    import torch
+    from vescale_b200 import DeviceMesh, DTensor, Replicate, Shard, distribute_tensor
+    from vescale_b200.dtensor.cross_mesh import CrossMeshRedistribute, cross_mesh_anchor
+
+    src, dst = DeviceMesh("cpu", [0, 1], _validate_mesh=False), DeviceMesh("cpu", [2, 3], _validate_mesh=False)
+    torch.manual_seed(3)
+    full = torch.randn(6, 4)
+    w = torch.arange(24.0).reshape(6, 4)
+    if rank < 2:
+        x = distribute_tensor(full, src, [Shard(0)]).detach().requires_grad_(True)
+        stub = CrossMeshRedistribute.apply(x, src, [Shard(0)], dst, [Shard(1)])
+        assert not isinstance(stub, DTensor)
+        stub.backward()  # joins the backward: receives d(loss)/dx from the target mesh
+        torch.testing.assert_close(x.grad.full_tensor(), w)
+        assert x.grad.placements == (Shard(0),)
+    else:
+        y = CrossMeshRedistribute.apply(None, src, [Shard(0)], dst, [Shard(1)], cross_mesh_anchor())
+        assert isinstance(y, DTensor) and y.placements == (Shard(1),) and y.requires_grad
+        torch.testing.assert_close(y.full_tensor(), full)
+        (y * distribute_tensor(w, dst, [Shard(1)])).sum().backward()
+
+
+def test_cross_mesh_redistribute_is_differentiable():
+    run_distributed(_cross_mesh_autograd, 4)

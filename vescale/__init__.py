@@ -51,6 +51,30 @@ _ALIASES = {
     "vescale.dtensor._collective_utils": "vescale_b200.dtensor._collective_utils",
     "vescale.dtensor.redistribute": "vescale_b200.dtensor.redistribute",
     "vescale.dtensor.op_schema": "vescale_b200.dtensor.op_schema",
+    "vescale.dtensor._op_schema": "vescale_b200.dtensor.op_schema",
+    "vescale.dtensor._dispatch": "vescale_b200.dtensor.dispatch",
+    "vescale.dtensor._sharding_prop": "vescale_b200.dtensor.sharding_prop",
+    "vescale.dtensor._redistribute": "vescale_b200.dtensor.redistribute",
+    # rule-author API: registration contracts, einop / einsum building blocks, predicates (real modules); the per-family rule files
+    # resolve to this framework's rule modules (same ops covered, RuleResult-style functions under their own names)
+    "vescale.dtensor.ops": "vescale_b200.dtensor.ops",
+    "vescale.dtensor.ops.math_ops": "vescale_b200.dtensor.rules.math",
+    "vescale.dtensor.ops.matrix_ops": "vescale_b200.dtensor.rules.matrix",
+    "vescale.dtensor.ops.pointwise_ops": "vescale_b200.dtensor.rules.pointwise",
+    "vescale.dtensor.ops.tensor_ops": "vescale_b200.dtensor.rules.tensor",
+    "vescale.dtensor.ops.view_ops": "vescale_b200.dtensor.rules.view",
+    "vescale.dtensor.ops.vescale_view_ops": "vescale_b200.dtensor.rules.view",
+    "vescale.dtensor.ops.conv_ops": "vescale_b200.dtensor.rules.conv",
+    "vescale.dtensor.ops.embedding_ops": "vescale_b200.dtensor.rules.tensor",
+    "vescale.dtensor.ops.random_ops": "vescale_b200.dtensor.rules.pointwise",
+    "vescale.dtensor.ops.experimental_ops": "vescale_b200.dtensor.rules.math",
+    "vescale.dtensor._ops": "vescale_b200.dtensor.ops",
+    "vescale.dtensor._ops._common_rules": "vescale_b200.dtensor.ops.common_rules",
+    "vescale.dtensor._ops.utils": "vescale_b200.dtensor.ops.utils",
+    "vescale.dtensor._ops._math_ops": "vescale_b200.dtensor.rules.math",
+    "vescale.dtensor._ops._matrix_ops": "vescale_b200.dtensor.rules.matrix",
+    "vescale.dtensor._ops._pointwise_ops": "vescale_b200.dtensor.rules.pointwise",
+    "vescale.dtensor._ops._tensor_ops": "vescale_b200.dtensor.rules.tensor",
     "vescale.dtensor.dispatch": "vescale_b200.dtensor.dispatch",
     "vescale.dtensor.sharding_prop": "vescale_b200.dtensor.sharding_prop",
     "vescale.dtensor.vescale_utils": "vescale_b200.dtensor.vescale_utils",

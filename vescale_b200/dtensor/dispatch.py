@@ -330,3 +330,54 @@ def register_op_handler(ops, fn=None):
         return f
 
     return deco(fn) if fn is not None else deco
+
+
+# ---- function-level entry points (legacy ``dispatch.py``: ``operator_dispatch`` / ``unwrap_to_op_info`` / ``redistribute_local_args`` / ``wrap``) ----
+# Tools built on the reference call these directly (tracers, debuggers, the emulator's DTensor front end): each is one stage of
+# ``OpDispatcher.dispatch`` on the process-wide dispatcher.
+def unwrap_to_op_info(op_call, args, kwargs):
+    """Stage 1: DTensor arguments -> (schema of specs, local tensors), packed as ``OpInfo``."""
+    from .op_schema import OpInfo
+
+    mesh, schema, local_args, local_kwargs = dispatcher.unwrap(op_call, args, kwargs or {})
+    flat = []
+    for a in list(schema.args_schema) + list(schema.kwargs_schema.values()):
+        flat.extend(a) if isinstance(a, tuple) and a and any(isinstance(x, DTensorSpec) for x in a) else flat.append(a)
+    return OpInfo(mesh, schema, flat, local_args, local_kwargs)
+
+
+def redistribute_local_args(op_info, suggested_input_schema=None) -> None:
+    """Stage 3: bring the local arguments of ``op_info`` to the placements propagation asked for (``op_info.output_sharding``, or an
+    explicit suggested schema whose specs name the targets).  In place."""
+    out_sh = op_info.output_sharding
+    if suggested_input_schema is not None:
+        from .op_schema import OutputSharding
+
+        have, want = op_info.schema.tensor_specs(), suggested_input_schema.tensor_specs()
+        out_sh = OutputSharding(None, [None if h.placements == w.placements else h.with_placements(w.placements) for h, w in zip(have, want)])
+    if out_sh is None or out_sh.redistribute_specs is None:
+        return
+    dispatcher._redistribute_inputs(op_info.schema, out_sh, op_info.local_args, op_info.local_kwargs)
+
+
+def wrap(res, spec):
+    """Stage 5: local result(s) + output spec(s) -> DTensor(s); non-tensor results pass through."""
+    if isinstance(res, torch.Tensor):
+        if spec is None:
+            return res
+        return DTensor(res, spec, requires_grad=res.requires_grad)
+    if isinstance(res, (list, tuple)):
+        specs = spec if isinstance(spec, (list, tuple)) else [spec] * len(res)
+        return type(res)(wrap(r, s) for r, s in zip(res, specs))
+    return res
+
+
+def operator_dispatch(op_call, args, kwargs, sharding_propagator=None):
+    """All stages.  ``sharding_propagator``: use this propagator instead of the process-wide one for this call."""
+    if sharding_propagator is None or sharding_propagator is dispatcher.sharding_propagator:
+        return dispatcher.dispatch(op_call, args, kwargs or {})
+    saved, dispatcher.sharding_propagator = dispatcher.sharding_propagator, sharding_propagator
+    try:
+        return dispatcher.dispatch(op_call, args, kwargs or {})
+    finally:
+        dispatcher.sharding_propagator = saved

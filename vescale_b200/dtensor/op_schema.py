@@ -17,7 +17,7 @@ import torch
 from ..placement import Placement
 from ..spec import DTensorSpec
 
-__all__ = ["OpSchema", "OutputSharding", "RuleResult", "PlacementList"]
+__all__ = ["OpSchema", "OutputSharding", "RuleResult", "PlacementList", "RuntimeSchemaInfo", "PlacementStrategy", "OpStrategy", "TupleStrategy", "StrategyType", "OpInfo"]
 
 PlacementList = Tuple[Placement, ...]
 
@@ -121,7 +121,12 @@ class RuleResult:
 
 @dataclass
 class OutputSharding:
-    """Propagation result: output spec(s), and the input specs to redistribute to (if any)."""
+    """Propagation result: output spec(s), and the input specs to redistribute to (if any).
+
+    Rules written against the reference's contract (``dtensor/ops/utils.py::register_prop_rule``) return
+    ``OutputSharding(output_spec, schema_suggestions=[OpSchema], failed_reason=...)``: "I cannot produce an output for these input
+    placements; with the suggested ones I can".  The second positional slot takes either form; ``ops.utils`` converts a suggestion
+    into ``redistribute_specs`` by re-running the rule on the suggested schema."""
 
     output_spec: Any
     redistribute_specs: Optional[List[Optional[DTensorSpec]]] = None
@@ -129,3 +134,102 @@ class OutputSharding:
     local_kwargs: Optional[Dict[str, Any]] = None
     post: Optional[Callable] = None
     pre: Optional[Callable] = None
+    schema_suggestions: Optional[List["OpSchema"]] = None
+    failed_reason: Optional[str] = None
+    needs_redistribute: bool = False
+
+    def __post_init__(self):
+        rs = self.redistribute_specs
+        if rs and all(isinstance(x, OpSchema) for x in rs):  # the reference's positional form
+            self.schema_suggestions, self.redistribute_specs = list(rs), None
+        if self.schema_suggestions:
+            self.needs_redistribute = True
+
+
+# ---- strategy-style rules (legacy ``op_schema.py:303-400``) --------------------------------------------------------------------------------
+class StrategyType:
+    """Base of what a strategy function may return / receive: one op's alternatives (``OpStrategy``) or a tuple of them."""
+
+
+@dataclass
+class PlacementStrategy:
+    """One way to run an op: the output spec it produces given these input specs; ``redistribute_cost[i][j]`` is the cost of
+    bringing input ``i`` from its ``j``-th current alternative to ``input_specs[i]``."""
+
+    output_spec: Any = None
+    input_specs: Optional[Sequence[DTensorSpec]] = None
+    redistribute_cost: Optional[List[List[float]]] = None
+    output_specs: Any = None  # newer spelling
+
+    def __post_init__(self):
+        if self.output_spec is None and self.output_specs is not None:
+            self.output_spec = self.output_specs
+        self.output_specs = self.output_spec
+
+    @property
+    def out_spec(self) -> DTensorSpec:
+        return self.output_spec
+
+    def cost(self) -> float:
+        return sum(min(c) if c else 0.0 for c in (self.redistribute_cost or []))
+
+    def pretty_print_placements(self, placements) -> str:
+        return "".join(str(p) for p in placements)
+
+    def __str__(self) -> str:
+        ins = ", ".join(self.pretty_print_placements(s.placements) for s in (self.input_specs or []))
+        out = self.output_spec
+        outs = ", ".join(self.pretty_print_placements(o.placements) for o in out) if isinstance(out, (tuple, list)) else (self.pretty_print_placements(out.placements) if out is not None else "None")
+        return f"({ins}) -> ({outs}) @ mesh {getattr(out if not isinstance(out, (tuple, list)) else out[0], 'mesh', None)}"
+
+
+class OpStrategy(StrategyType):
+    """The alternatives of one op (or, for an op's ARGUMENT, the single placement it currently has)."""
+
+    def __init__(self, strategies: List[PlacementStrategy]):
+        self.strategies: List[PlacementStrategy] = list(strategies)
+
+    def __str__(self) -> str:
+        return "OpStrategy:[" + ", ".join(str(s) for s in self.strategies) + "]"
+
+    def max_num_shards(self) -> int:
+        return max(s.output_spec.num_shards for s in self.strategies)
+
+    @property
+    def output_mesh_shape(self):
+        return tuple(self.strategies[0].output_spec.mesh.shape)
+
+    @property
+    def output_ndim(self) -> int:
+        return self.strategies[0].output_spec.ndim
+
+    @property
+    def output_shape(self):
+        return self.strategies[0].output_spec.shape
+
+    def best(self) -> PlacementStrategy:
+        """Least total redistribution cost; first wins ties (strategy functions list their preferred alternative first)."""
+        return min(self.strategies, key=lambda s: s.cost())
+
+
+class TupleStrategy(StrategyType):
+    """Strategies of an op whose argument / result is a list of tensors (foreach ops, ``cat``): one child per element."""
+
+    def __init__(self, childs: Sequence[StrategyType]):
+        self.childs: Sequence[StrategyType] = childs
+
+    def __str__(self) -> str:
+        return "TupleStrategy(" + ", ".join(str(c) for c in self.childs) + ")"
+
+
+@dataclass
+class OpInfo:
+    """Everything the dispatcher knows about one call after unwrapping (legacy ``op_schema.py:381-401``)."""
+
+    mesh: Any
+    schema: "OpSchema"
+    flat_args_schema: List[object]
+    local_args: Sequence[object]
+    local_kwargs: Dict[str, object]
+    args_tree_spec: Optional[object] = None
+    output_sharding: Optional[OutputSharding] = None

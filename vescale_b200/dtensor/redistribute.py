@@ -327,3 +327,11 @@ class Redistribute(torch.autograd.Function):
         # dgrad) is reduced here — Partial -> Shard is the reduce-scatter of Megatron SP
         local = redistribute_local_tensor(grad._local_tensor, g_cur, g_tgt)
         return DTensor(local, g_tgt, requires_grad=grad.requires_grad), None, None, None
+
+
+def __getattr__(name):  # ``CrossMeshRedistribute`` lives with the cross-mesh transport (import cycle otherwise)
+    if name == "CrossMeshRedistribute":
+        from .cross_mesh import CrossMeshRedistribute
+
+        return CrossMeshRedistribute
+    raise AttributeError(name)
