@@ -577,3 +577,144 @@ def test_emulator_dtensor_list_front_end():
         if want is None:  # the Partial result was reduced in NCCL's ring association order, bit for bit
             parts = [t1[:, 2 * r : 2 * r + 2] @ t2[2 * r : 2 * r + 2] for r in range(4)]
             assert torch.equal(y[0].to_local(), ring_all_reduce(parts)[0])
+
+
+def test_checkpoint_planner_dedup_balance_cache_and_single_process_io(tmp_path):
+    """Load-balanced dedup, plan fingerprints / LRU cache, and the save / load drivers without a process group."""
+    import pytest
+    import torch
+    from torch.distributed.checkpoint.metadata import ChunkStorageMetadata, MetadataIndex, TensorProperties
+    from torch.distributed.checkpoint.planner import SavePlan, TensorWriteData, WriteItem, WriteItemType
+
+    from vescale_b200.checkpoint.planner import PlanLRUCache, VeScaleLoadPlanner, VeScaleSavePlanner, custom_dedup_tensors, item_bytes, plan_fingerprint
+    from vescale_b200.checkpoint.state_dict_io import CheckpointException, load_state_dict, save_state_dict
+
+    def item(name, n, off=0):
+        return WriteItem(MetadataIndex(name, torch.Size([off])), WriteItemType.TENSOR,
+                         tensor_data=TensorWriteData(ChunkStorageMetadata(torch.Size([off]), torch.Size([n])), TensorProperties(dtype=torch.float32), torch.Size([n + off])))
+
+    # four ranks all offer the replicated tensors r0..r5 (sizes 6..1 MB-ish); rank 2 also owns a big private shard
+    sizes = [600, 500, 400, 300, 200, 100]
+    plans = [SavePlan([item(f"r{i}", n) for i, n in enumerate(sizes)] + ([item("private", 900)] if r == 2 else [])) for r in range(4)]
+    out = custom_dedup_tensors(plans)
+    names = [sorted(it.index.fqn for it in p.items) for p in out]
+    assert sorted(n for ns in names for n in ns) == sorted([f"r{i}" for i in range(6)] + ["private"])  # every piece exactly once
+    load = [sum(item_bytes(it) for it in p.items) for p in out]
+    assert max(load) - min(load) <= 4 * 600 and "private" in names[2] and len(names[2]) == 1  # the loaded rank gets nothing extra
+    lowest = [sum(item_bytes(it) for it in p.items) for p in [SavePlan(plans[0].items)] + [SavePlan([i for i in p.items if i.index.fqn == "private"]) for p in plans[1:]]]
+    assert max(load) < max(lowest)  # better than "lowest rank writes everything"
+    assert plan_fingerprint(plans[0]) == plan_fingerprint(plans[1]) != plan_fingerprint(plans[2])
+
+    cache = PlanLRUCache(capacity=2)
+    for k in "abc":
+        cache.put(k, plans[0], None)
+    assert cache.get("a") is None and cache.get("c") is not None and len(cache) == 2 and (cache.hits, cache.misses) == (1, 1)
+
+    sd = {"layer": {"w": torch.arange(12.0).reshape(3, 4), "b": torch.ones(4)}, "step": 7}
+    pl = VeScaleSavePlanner()
+    for k in range(2):
+        save_state_dict(sd, str(tmp_path / f"ck{k}"), no_dist=True, planner=pl)
+    assert pl.global_plan_runs == 1 and pl.cache.hits == 1  # second save: cached plan + metadata
+    dst = {"layer": {"w": torch.zeros(3, 4), "b": torch.zeros(4)}, "step": 0}
+    load_state_dict(dst, str(tmp_path / "ck1"), no_dist=True)
+    assert torch.equal(dst["layer"]["w"], sd["layer"]["w"]) and dst["step"] == 7
+    with pytest.raises(CheckpointException, match="rank"):
+        load_state_dict({"missing": torch.zeros(2)}, str(tmp_path / "ck1"), no_dist=True)
+    load_state_dict({"missing": torch.zeros(2), "step": 0}, str(tmp_path / "ck1"), no_dist=True, planner=VeScaleLoadPlanner(allow_partial_load=True))
+
+
+def test_checkpoint_report_service_gather_broadcast_barrier():
+    """The out-of-band coordination channel of asynchronous saves: rendezvous by tag, status of a stuck rendezvous, time-outs."""
+    import threading
+
+    import pytest
+
+    from vescale_b200.checkpoint import server_lib as sl
+
+    W = 4
+    server, addr = sl.serve(sl.ReportServicer(W))
+    try:
+        results = [None] * W
+
+        def rank_main(r):
+            stub = sl.get_stub(addr)
+            got = sl.gather(stub, 2, r, {"rank": r, "bytes": 10 * r}, tag="plans")
+            cfg = sl.broadcast(stub, 1, r, obj=("final-plan", r) if r == 1 else None, tag="final")
+            sl.barrier(stub, r, tag="done")
+            results[r] = (got, cfg)
+            stub.close()
+
+        ts = [threading.Thread(target=rank_main, args=(r,)) for r in range(W)]
+        [t.start() for t in ts]
+        [t.join(30) for t in ts]
+        assert all(not t.is_alive() for t in ts)
+        assert results[2][0] == [{"rank": r, "bytes": 10 * r} for r in range(W)] and all(results[r][0] is None for r in (0, 1, 3))
+        assert all(results[r][1] == ("final-plan", 1) for r in range(W))
+        stub = sl.get_stub(addr)
+        st = sl.get_server_status(stub)
+        assert st["waiting"] == {} and st["completed"] == 3
+        # a rendezvous nobody else joins: visible in the status while it waits, then a time-out naming the missing ranks
+        box = {}
+        t = threading.Thread(target=lambda: box.setdefault("err", _raises(lambda: sl.barrier(sl.get_stub(addr), 0, tag="lonely", timeout=1.0))))
+        t.start()
+        import time
+
+        time.sleep(0.3)
+        st = sl.get_server_status(stub)
+        assert st["waiting"]["barrier/lonely"]["missing"] == [1, 2, 3]
+        t.join(10)
+        assert "ranks [1, 2, 3]" in box["err"]
+        with pytest.raises(RuntimeError, match="twice"):
+            s2 = sl.get_stub(addr)
+            threading.Thread(target=lambda: _raises(lambda: sl.barrier(s2, 0, tag="dup", timeout=1.0)), daemon=True).start()
+            time.sleep(0.2)
+            sl.barrier(s2, 0, tag="dup", timeout=1.0)
+    finally:
+        server.stop(0)
+
+
+def _raises(fn):
+    try:
+        fn()
+    except Exception as e:  # noqa: BLE001
+        return str(e)
+    return ""
+
+
+def test_named_mem_file_server_path_api_and_pinned_pool_functions():
+    """``/local_mem/<name>/...`` file API over named servers (legacy ``mem_server_lib``), pool function forms (``mem_checkpoint``)."""
+    import pytest
+    import torch
+
+    import vescale_b200.checkpoint.mem_server as m
+    from vescale_b200.checkpoint.pinned_pool import GLOBAL_POOL, copy_gpu_tensor_to_cpu_pinned_mem_pool, deallocate_cpu_tensor_in_pinned_mem_pool
+
+    name = f"pytest_{os.getpid()}"
+    srv = m.start_server(name, force=True)
+    try:
+        assert m.wait_until_fs_ready(name, 5) and open(m.get_mem_server_sock_file(name)).read() == srv.address
+        p = m.get_prefix(name)
+        with m.open(p + "ck/step1/a.bin", "wb") as f:
+            f.write(b"abc")
+        with m.open(p + "ck/step1/a.bin", "ab") as f:
+            f.write(b"def")
+        assert m.open(p + "ck/step1/a.bin", "rb").read() == b"abcdef" and m.listdir(p + "ck") == ["step1"] and m.listdir(p + "ck/step1") == ["a.bin"]
+        m.rename(p + "ck/step1/a.bin", p + "ck/step1/b.bin")
+        with pytest.raises(FileExistsError):
+            with m.open(p + "ck/step1/c.bin", "wb") as f:
+                f.write(b"x")
+            m.rename(p + "ck/step1/c.bin", p + "ck/step1/b.bin")
+        m.remove(p + "ck/step1/b.bin")
+        assert not m.exists(p + "ck/step1/b.bin") and m.exists(p + "ck/step1/c.bin")
+        with pytest.raises(RuntimeError, match="already running"):
+            m.start_server(name)
+        with pytest.raises(ValueError):
+            m.exists("/tmp/not_local_mem")
+    finally:
+        srv.stop(0)
+        os.remove(m.get_mem_server_sock_file(name))
+    t = torch.arange(6.0).reshape(2, 3)
+    h = copy_gpu_tensor_to_cpu_pinned_mem_pool(t)
+    assert torch.equal(h, t) and h.data_ptr() != t.data_ptr()
+    deallocate_cpu_tensor_in_pinned_mem_pool(h)
+    assert GLOBAL_POOL is not None

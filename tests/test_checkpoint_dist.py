@@ -160,7 +160,13 @@ def _mem_ckpt(rank, world):
         ckpt.save(f"mem://{addr}/run/step{step}", {"model": make_state(float(step))})
     dist.barrier()
     pl = _PLANNERS["model"]
-    assert getattr(pl, "_enable_plan_caching", True)
+    # the second save found its local plan in the cache on every rank and skipped the global planning step; the replicated "b"
+    # (offered by all four ranks) was written by exactly one of them
+    assert pl.cache.hits >= 1 and pl.global_plan_runs == (1 if dist.get_rank() == 0 else 0), (pl.cache.hits, pl.global_plan_runs)
+    assert sum(1 for it in pl.plan.items if it.index.fqn == "b") in (0, 1)
+    owners = [None] * world
+    dist.all_gather_object(owners, sum(1 for it in pl.plan.items if it.index.fqn == "b"))
+    assert sum(owners) == 1, owners
     client = MemFileClient(addr)
     names = client.listdir("run/step2/model")
     assert any(n.endswith(".metadata") for n in names) and sum(n.endswith(".distcp") for n in names) >= 1
@@ -397,9 +403,19 @@ def _pp_layout_and_workers(rank, world, path):
     mesh = meshes[pp_rank]
     w = torch.arange(48.0).view(6, 8) + 1000 * pp_rank  # every stage owns different optimizer state
     st = {"exp_avg": distribute_tensor(w.to(device_type()), mesh, [Shard(0)], src_data_rank=None), "step": 7 + pp_rank}
-    ckpt.save(path, {"optimizer": st}, async_checkpoint=True, workers=2, pp_rank=pp_rank, pp_group=groups[pp_rank])
+    # the background half of the save coordinates over the report service (no collective on any process group from that thread)
+    from vescale_b200.checkpoint import server_lib
+
+    box = [server_lib.start_server_in_new_process(world) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ckpt.save(path, {"optimizer": st}, async_checkpoint=True, workers=2, pp_rank=pp_rank, pp_group=groups[pp_rank], coordinator_address=box[0])
     ckpt.wait_for_async()
     dist.barrier()
+    if rank == 0:
+        status = server_lib.get_server_status(server_lib.get_stub(box[0]))
+        assert status["waiting"] == {} and status["completed"] >= 2 * 6, status  # both stages ran their rendezvous through it
+        for p in server_lib.start_server_in_new_process.processes:
+            p.terminate()
     d = os.path.join(path, "optimizer", f"pp_{pp_rank}")
     files = sorted(os.listdir(d))
     assert ".metadata" in files and sum(f.endswith(".distcp") for f in files) >= 2, files

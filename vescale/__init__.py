@@ -104,8 +104,24 @@ _ALIASES = {
     "vescale.checkpoint.api.meta_type": "vescale_b200.checkpoint.meta_type",
     "vescale.checkpoint.api.vescale_checkpointer": "vescale_b200.checkpoint.api",
     "vescale.checkpoint.api.base_checkpointer": "vescale_b200.checkpoint.api",
-    "vescale.checkpoint.utilities.mem_checkpoint": "vescale_b200.checkpoint.mem_server",
+    "vescale.checkpoint.save_state_dict": "vescale_b200.checkpoint.state_dict_io",
+    "vescale.checkpoint.load_state_dict": "vescale_b200.checkpoint.state_dict_io",
+    "vescale.checkpoint.planner": "vescale_b200.checkpoint.planner",
+    "vescale.checkpoint.planner.common": "vescale_b200.checkpoint.planner",
+    "vescale.checkpoint.planner.vescale": "vescale_b200.checkpoint.planner",
+    "vescale.checkpoint.planner.vescale.vescale_planner": "vescale_b200.checkpoint.planner",
+    "vescale.checkpoint.planner.vescale.vescale_planner_helpers": "vescale_b200.checkpoint.planner",
+    "vescale.checkpoint.storage.filesystem": "vescale_b200.checkpoint.storage",
+    "vescale.checkpoint.utilities": "vescale_b200.checkpoint",
+    "vescale.checkpoint.utilities.bfile": "vescale_b200.checkpoint.bfile",
+    "vescale.checkpoint.utilities.logger": "vescale_b200.checkpoint.logger",
+    "vescale.checkpoint.utilities.sync_queue": "vescale_b200.checkpoint.sync_queue",
+    "vescale.checkpoint.utilities.mem_checkpoint": "vescale_b200.checkpoint.recorder",
+    "vescale.checkpoint.utilities.server": "vescale_b200.checkpoint.server_lib",
+    "vescale.checkpoint.utilities.server.server_lib": "vescale_b200.checkpoint.server_lib",
     "vescale.checkpoint.utilities.server.mem_server_lib": "vescale_b200.checkpoint.mem_server",
+    "vescale.checkpoint.utilities.server.detached_mem_server": "vescale_b200.checkpoint.mem_server",
+    "vescale.checkpoint.utilities.server.server_status_client": "vescale_b200.checkpoint.server_lib",
     "vescale.devicemesh_api.api": "vescale_b200.devicemesh_api.api",
     "vescale.debug.debug_log": "vescale_b200.debug.debug_log",
     "vescale.emulator.distributed": "vescale_b200.emulator.distributed",

@@ -24,3 +24,7 @@ from .mem_server import MemFileClient, MemFileServer  # noqa: F401
 from . import bfile  # noqa: F401
 from .logger import get_vescale_checkpoint_logger  # noqa: F401
 from .recorder import TorchCheckpointRecorder  # noqa: F401
+from .planner import PlanLRUCache, VeScaleLoadPlanner, VeScaleSavePlanner, custom_dedup_tensors  # noqa: F401
+from .state_dict_io import CheckpointException, ServiceComm, load_state_dict, save_state_dict  # noqa: F401
+from .sync_queue import SynchronizedQueue  # noqa: F401
+from .version import __version__ as CHECKPOINT_FORMAT_VERSION  # noqa: F401

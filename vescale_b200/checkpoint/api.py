@@ -16,7 +16,7 @@ from .flat_piece import FlatPiece
 from .logger import timed
 from .pinned_pool import PinnedPool
 
-__all__ = ["save", "load", "VeScaleCheckpointer", "wait_for_async"]
+__all__ = ["save", "load", "VeScaleCheckpointer", "wait_for_async", "deduplicate_2d_list", "get_optim_ckpt_process_group", "BaseCheckpointer"]
 
 _POOL = PinnedPool(shared=True)  # shared-memory + cudaHostRegister: worker processes serialise the staged shards without a copy
 _PENDING: List[Future] = []
@@ -25,19 +25,32 @@ _PLANNERS: Dict[str, Any] = {}
 
 
 def _save_planner(key: str):
-    """One planner per checkpoint key, kept across saves: torch DCP caches the local/global plan and the metadata when the
-    state-dict structure is unchanged (the legacy plan LRU cache, ``planner/common.py:65-89``) and spreads replicated items
-    over the ranks by accumulated bytes instead of writing them all from rank 0 (load-balanced dedup, ``:92-132``)."""
-    import torch.distributed.checkpoint as dcp
+    """One planner per checkpoint key, kept across saves: its plan cache (``planner.PlanLRUCache``) lets a save whose structure is
+    unchanged skip the plan gather / scatter, and its dedup spreads replicated items over the ranks by accumulated bytes instead of
+    writing them all from rank 0 (legacy ``planner/common.py:65-132``)."""
+    from .planner import VeScaleSavePlanner
 
     pl = _PLANNERS.get(key)
     if pl is None:
-        try:
-            pl = dcp.DefaultSavePlanner(dedup_save_to_lowest_rank=False, enable_plan_caching=True)
-        except TypeError:  # older torch: no plan caching switch
-            pl = dcp.DefaultSavePlanner()
-        _PLANNERS[key] = pl
+        pl = _PLANNERS[key] = VeScaleSavePlanner()
     return pl
+
+
+def _dcp_save(sd: Dict[str, Any], sub: str, pg, planner_key: str, workers: int, coordinator_address: Optional[str] = None) -> None:
+    from .state_dict_io import ServiceComm, save_state_dict
+
+    st = _storage(sub, True, workers)
+    comm = None
+    if coordinator_address and dist.is_initialized():  # coordinate over the report service: no collective on any process group
+        comm = ServiceComm(coordinator_address, dist.get_rank(pg), dist.get_world_size(pg), tag=sub)
+    save_state_dict(sd, st.get("checkpoint_id"), process_group=pg, planner=_save_planner(planner_key), storage_writer=st.get("storage_writer"), comm=comm)
+
+
+def _dcp_load(sd: Dict[str, Any], sub: str, pg=None, no_dist: bool = False) -> None:
+    from .state_dict_io import load_state_dict
+
+    st = _storage(sub, False)
+    load_state_dict(sd, st.get("checkpoint_id"), process_group=pg, no_dist=no_dist, storage_reader=st.get("storage_reader"))
 
 
 def _storage(sub: str, write: bool, workers: int = 0):
@@ -171,9 +184,12 @@ class BaseCheckpointer:
 class VeScaleCheckpointer(BaseCheckpointer):
     @classmethod
     def save(cls, path: str, checkpoint_state: Dict[str, Any], async_checkpoint: bool = False, *, workers: Optional[int] = None, pp_rank: Optional[int] = None,
-             pp_group=None) -> Optional[List[Future]]:
+             pp_group=None, coordinator_address: Optional[str] = None) -> Optional[List[Future]]:
         """``workers``: writer processes per rank for the file serialisation (default: 2 for asynchronous saves, 0 = in-process
-        writer threads for synchronous ones; ``VESCALE_CHECKPOINT_WORKERS`` overrides)."""
+        writer threads for synchronous ones; ``VESCALE_CHECKPOINT_WORKERS`` overrides).  ``coordinator_address``: address of a
+        report service (``server_lib.start_server_in_new_process``): the ranks agree on plans / results through it instead of through
+        collectives (``VESCALE_CHECKPOINT_COORDINATOR`` sets it for the job)."""
+        coordinator_address = coordinator_address or os.environ.get("VESCALE_CHECKPOINT_COORDINATOR") or None
         import torch.distributed.checkpoint as dcp
 
         if workers is None:
@@ -201,7 +217,7 @@ class VeScaleCheckpointer(BaseCheckpointer):
                         # planning (a few small collectives) runs on this thread; serialisation + file writes run in worker
                         # PROCESSES on the shared pinned staging buffers, so the training loop's GIL is left alone
                         with timed(f"save {key}: plan + serialise + write (background, {workers} worker processes)"):
-                            dcp.save(host, process_group=pg, planner=_save_planner("async/" + key), **_storage(sub, True, workers))
+                            _dcp_save(host, sub, pg, "async/" + key, workers, coordinator_address)
                         fut.set_result(sub)
                     except Exception as e:  # noqa: BLE001
                         fut.set_exception(e)
@@ -216,7 +232,7 @@ class VeScaleCheckpointer(BaseCheckpointer):
                 futures.append(fut)
             else:
                 with timed(f"save {key}: synchronous"):
-                    dcp.save(tensors, planner=_save_planner(key), process_group=stage_pg, **_storage(sub, True, workers))
+                    _dcp_save(tensors, sub, stage_pg, key, workers, coordinator_address)
         return futures or None
 
     @classmethod
@@ -240,10 +256,10 @@ class VeScaleCheckpointer(BaseCheckpointer):
                 plain = {k: v for k, v in req.items() if not isinstance(v, (DTensor, FlatPiece))}
                 sharded = {k: v for k, v in req.items() if isinstance(v, (DTensor, FlatPiece))}
                 if sharded:
-                    dcp.load(sharded, **_storage(sub, False))
+                    _dcp_load(sharded, sub)
                 if plain:
                     if dist.get_rank() == 0:
-                        dcp.load(plain, no_dist=True, **_storage(sub, False))
+                        _dcp_load(plain, sub, no_dist=True)
                     box = [plain.get("__extras__")]
                     dist.broadcast_object_list(box, src=0)
                     if "__extras__" in plain:
@@ -258,7 +274,7 @@ class VeScaleCheckpointer(BaseCheckpointer):
                             dist.broadcast(t, src=0)
             else:
                 with timed(f"load {key}"):
-                    dcp.load(req, process_group=stage_pg, **_storage(sub, False))  # in place: DTensor / tensor storages are filled with the resharded data
+                    _dcp_load(req, sub, stage_pg)  # in place: DTensor / tensor storages are filled with the resharded data
             if isinstance(obj, nn.Module):
                 pass  # state_dict tensors alias the module's parameters/buffers
             elif hasattr(obj, "load_checkpoint_state"):
@@ -310,3 +326,22 @@ def save(path: str, checkpoint_state: Dict[str, Any], async_checkpoint: bool = F
 
 def load(path: str, checkpoint_state: Dict[str, Any], broadcast_checkpoint: bool = False, **kw):
     return VeScaleCheckpointer.load(path, checkpoint_state, broadcast_checkpoint, **kw)
+
+
+def deduplicate_2d_list(lst: List[List[Any]]) -> List[List[Any]]:
+    """Rows of a 2-D list without repetitions, first occurrences kept in order (legacy ``vescale_checkpointer.py:38-48``; used on the
+    rank lists of per-stage process groups, where several mesh slices name the same set of ranks)."""
+    seen, out = set(), []
+    for row in lst:
+        key = tuple(row)
+        if key not in seen:
+            seen.add(key)
+            out.append(list(row))
+    return out
+
+
+def get_optim_ckpt_process_group():
+    """The process group within which THIS rank's optimizer state is saved: its pipeline stage's DP x TP ranks when the global mesh
+    has a PP dimension of size > 1, the default group otherwise (legacy ``vescale_checkpointer.py:51-68``)."""
+    suffix, pg = _pp_scope("optimizer", None, None)
+    return pg if suffix else None

@@ -46,3 +46,13 @@ def timed(phase: str, level: int = logging.INFO):
         dt = time.perf_counter() - t0
         PHASE_SECONDS[phase] = dt
         get_vescale_checkpoint_logger().log(level, f"{phase}: {dt * 1e3:.1f} ms")
+
+
+class VeScaleCheckpointLogger:
+    """Holder form (legacy ``utilities/logger.py:229-251``): ``VeScaleCheckpointLogger().logger`` is the shared logger."""
+
+    def __new__(cls):
+        if not hasattr(cls, "_inst"):
+            cls._inst = super().__new__(cls)
+            cls._inst.logger = get_vescale_checkpoint_logger()
+        return cls._inst

@@ -21,7 +21,8 @@ from concurrent import futures
 from contextlib import contextmanager
 from typing import Dict, Iterable, Iterator, List, Optional, Tuple
 
-__all__ = ["MemFileServer", "MemFileClient", "MemFileSystem", "parse_mem_uri", "make_mem_writer", "make_mem_reader"]
+__all__ = ["MemFileServer", "MemFileClient", "MemFileSystem", "parse_mem_uri", "make_mem_writer", "make_mem_reader", "MemFileServicer", "get_mem_server_sock_file", "get_prefix",
+           "start_server", "start_server_in_new_process", "wait_until_fs_ready", "mem_open", "rename", "remove", "listdir", "exists"]
 
 _SERVICE = "vescale_b200.MemFile"
 _CHUNK = 4 << 20
@@ -121,7 +122,7 @@ class MemFileServer:
                 st.dirs.add(hdr["name"].rstrip("/"))
                 return _pack({"ok": True})
             if op == "listdir":
-                pre = hdr["name"].rstrip("/") + "/"
+                pre = (hdr["name"].rstrip("/") + "/") if hdr["name"].strip("/") else ""
                 return _pack({"ok": True, "names": sorted(k for k in st.files if k.startswith(pre))})
             if op == "report":  # report service: ranks post status, anyone can read the table
                 if "status" in hdr:
@@ -300,3 +301,167 @@ def make_mem_reader(uri: str):
     r.fs = MemFileSystem(client)
     r.path = r.fs.init_path(path)
     return r
+
+
+# ---- named servers + a file API on ``/local_mem/<name>/...`` paths (legacy ``mem_server_lib.py:48-307``) ------------------------------------------
+# The reference addresses a node-local server by NAME (a unix socket under /var/tmp) and files as ``/local_mem/<name>/<path>``.
+# Same model here: ``start_server(name)`` writes the server's TCP address to a small rendezvous file; the module-level ``open`` /
+# ``rename`` / ``remove`` / ``listdir`` / ``exists`` resolve the name through it.
+MemFileServicer = MemFileServer  # the reference's name for the service implementation
+_PREFIX = "/local_mem"
+_NAMED: Dict[str, MemFileServer] = {}
+_CLIENTS: Dict[str, MemFileClient] = {}
+
+
+def get_mem_server_sock_file(name: str) -> str:
+    """The rendezvous file of server ``name`` (holds ``host:port``)."""
+    import tempfile
+
+    return os.path.join(tempfile.gettempdir(), f"vescale_b200_mem_server_{os.getuid()}_{name}.addr")
+
+
+def get_prefix(name: str) -> str:
+    return f"{_PREFIX}/{name}/"
+
+
+def start_server(name: str, force: bool = False) -> MemFileServer:
+    """Serve ``name`` from this process.  A live server of that name (this process or another) is an error unless ``force``."""
+    sock = get_mem_server_sock_file(name)
+    if os.path.exists(sock) and not force:
+        try:
+            MemFileClient(open_text(sock), timeout=2.0).exists("__probe__")
+            raise RuntimeError(f"a mem file server named {name!r} is already running at {open_text(sock)}")
+        except RuntimeError:
+            raise
+        except Exception:  # noqa: BLE001  stale rendezvous file of a dead server
+            pass
+    srv = MemFileServer().start()
+    tmp = sock + f".{os.getpid()}"
+    with io.open(tmp, "w") as f:
+        f.write(srv.address)
+    os.replace(tmp, sock)
+    _NAMED[name] = srv
+    _CLIENTS.pop(name, None)
+    return srv
+
+
+def open_text(path: str) -> str:
+    with io.open(path) as f:
+        return f.read().strip()
+
+
+def _serve_named(name: str, conn) -> None:
+    srv = start_server(name, force=True)
+    conn.send(srv.address)
+    conn.close()
+    srv.server.wait_for_termination()
+
+
+def start_server_in_new_process(name: str):
+    """Serve ``name`` from a daemon child process (checkpoints then survive a crash of the training process, which is the point of
+    a detached in-memory server); returns the ``multiprocessing.Process``."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe()
+    p = ctx.Process(target=_serve_named, args=(name, child), daemon=True)
+    p.start()
+    _recv_or_die(parent, p, f"mem file server {name!r}")
+    parent.close()
+    _CLIENTS.pop(name, None)
+    return p
+
+
+def _recv_or_die(conn, proc, what: str, timeout: float = 120.0):
+    """First message of a freshly spawned server process — or a clear error if the child died before sending it (e.g. the parent's
+    ``__main__`` cannot be re-imported by ``spawn``), instead of blocking forever on the pipe."""
+    end = time.time() + timeout
+    while time.time() < end:
+        if conn.poll(0.2):
+            return conn.recv()
+        if not proc.is_alive():
+            raise RuntimeError(f"{what}: the server process exited with code {proc.exitcode} before it came up")
+    proc.terminate()
+    raise TimeoutError(f"{what}: the server process did not come up within {timeout} s")
+
+
+def wait_until_fs_ready(name: str, timeout: float = 120.0) -> bool:
+    end = time.time() + timeout
+    while time.time() < end:
+        try:
+            _client(name).exists("__probe__")
+            return True
+        except Exception:  # noqa: BLE001
+            _CLIENTS.pop(name, None)
+            time.sleep(0.1)
+    return False
+
+
+def _client(name: str) -> MemFileClient:
+    c = _CLIENTS.get(name)
+    if c is None:
+        sock = get_mem_server_sock_file(name)
+        if not os.path.exists(sock):
+            raise FileNotFoundError(f"no mem file server named {name!r} (start_server / start_server_in_new_process)")
+        c = _CLIENTS[name] = MemFileClient(open_text(sock))
+    return c
+
+
+def _split(path: str) -> Tuple[MemFileClient, str]:
+    if not path.startswith(_PREFIX + "/"):
+        raise ValueError(f"{path!r} is not under {_PREFIX}/<server name>/")
+    name, _, rest = path[len(_PREFIX) + 1:].partition("/")
+    return _client(name), rest
+
+
+class _Upload(io.BytesIO):
+    def __init__(self, client: MemFileClient, name: str, initial: bytes = b""):
+        super().__init__()
+        self._client, self._name = client, name
+        if initial:
+            self.write(initial)
+
+    def close(self):
+        if not self.closed:
+            self._client.write(self._name, self.getvalue())
+        super().close()
+
+
+def mem_open(name: str, mode: str = "rb"):
+    """A binary file object on the named server: ``rb`` downloads, ``wb`` uploads on close, ``ab`` appends (download + upload)."""
+    client, rest = _split(name)
+    if "r" in mode:
+        return io.BytesIO(client.read(rest))
+    if "a" in mode:
+        return _Upload(client, rest, client.read(rest) if client.exists(rest) else b"")
+    return _Upload(client, rest)
+
+
+def rename(src: str, dst: str, overwrite: bool = False) -> None:
+    client, a = _split(src)
+    _, b = _split(dst)
+    if not overwrite and client.exists(b):
+        raise FileExistsError(dst)
+    client.rename(a, b)
+
+
+def remove(name: str) -> None:
+    client, rest = _split(name)
+    client.remove(rest)
+
+
+def listdir(name: str) -> List[str]:
+    client, rest = _split(name.rstrip("/") + "/")
+    rest = rest.rstrip("/")
+    return sorted({n[len(rest) + 1:].split("/", 1)[0] if rest and n.startswith(rest + "/") else n.split("/", 1)[0] for n in client.listdir(rest)})
+
+
+def exists(name: str) -> bool:
+    client, rest = _split(name)
+    return client.exists(rest)
+
+
+def __getattr__(attr):  # ``mem_server.open(...)`` is the reference's spelling; a module-level ``open`` would shadow the builtin in here
+    if attr == "open":
+        return mem_open
+    raise AttributeError(attr)

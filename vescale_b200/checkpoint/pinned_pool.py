@@ -9,7 +9,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-__all__ = ["PinnedPool"]
+__all__ = ["PinnedPool", "PinnedStoragePool", "GLOBAL_POOL", "copy_gpu_tensor_to_cpu_pinned_mem_pool", "deallocate_cpu_tensor_in_pinned_mem_pool"]
 
 
 class PinnedPool:
@@ -76,3 +76,23 @@ class PinnedPool:
     def synchronize(self) -> None:
         if self._stream is not None:
             self._stream.synchronize()
+
+
+# ---- function form over one process-wide pool (legacy ``mem_checkpoint.py:66-151``) -------------------------------------------------------------
+PinnedStoragePool = PinnedPool  # the reference's class name
+GLOBAL_POOL = PinnedPool()
+
+
+def copy_gpu_tensor_to_cpu_pinned_mem_pool(tensor: torch.Tensor, non_blocking: bool = False) -> torch.Tensor:
+    """Device tensor -> pinned host tensor from the process-wide pool (same shape / dtype).  ``non_blocking``: return as soon as the
+    copy is enqueued on the pool's side stream — call ``GLOBAL_POOL.synchronize()`` (or any stream sync) before reading the result."""
+    host = GLOBAL_POOL.stage(tensor)
+    if not non_blocking:
+        GLOBAL_POOL.synchronize()
+    return host
+
+
+def deallocate_cpu_tensor_in_pinned_mem_pool(tensor: torch.Tensor) -> None:
+    """Hand a staged tensor's buffer back to the pool for the next save (tensors that did not come from the pool are ignored)."""
+    if hasattr(tensor, "_pool_base"):
+        GLOBAL_POOL.release(tensor)

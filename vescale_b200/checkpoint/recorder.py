@@ -88,3 +88,6 @@ class TorchCheckpointRecorder:
     def close(self):
         self.wait()
         self._ex.shutdown(wait=True)
+
+
+from .pinned_pool import PinnedStoragePool, copy_gpu_tensor_to_cpu_pinned_mem_pool, deallocate_cpu_tensor_in_pinned_mem_pool  # noqa: E402,F401  (legacy ``mem_checkpoint`` exports all four)

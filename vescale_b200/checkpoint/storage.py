@@ -26,7 +26,7 @@ from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tupl
 
 import torch
 
-__all__ = ["ProcessPoolWriter", "OverlappingLoader", "shutdown_workers"]
+__all__ = ["ProcessPoolWriter", "OverlappingLoader", "shutdown_workers", "FileSystemWriter", "FileSystemReader"]
 
 _EXECUTORS: Dict[int, ProcessPoolExecutor] = {}
 
@@ -179,3 +179,15 @@ class OverlappingLoader:
                 pending.put((nxt, self.pool.submit(self.fetch, nxt)))
             yield k, f.result()
         self.pool.shutdown(wait=False)
+
+
+# the reference's names for "the" file-system back ends (legacy ``storage/filesystem.py:540,749``)
+FileSystemWriter = ProcessPoolWriter
+
+
+def __getattr__(name):
+    if name == "FileSystemReader":
+        from torch.distributed.checkpoint import FileSystemReader
+
+        return FileSystemReader
+    raise AttributeError(name)
