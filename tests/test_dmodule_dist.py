@@ -364,3 +364,71 @@ def _mixtral_plan_matches_single_device(rank, world):
 
 def test_mixtral_4d_plan_matches_single_device():
     run_distributed(_mixtral_plan_matches_single_device, 2)
+
+
+class _FFNBlock(nn.Module):
+    def __init__(self, d=16):
+        super().__init__()
+        self.up, self.gate, self.down = nn.Linear(d, 4 * d), nn.Linear(d, 4 * d), nn.Linear(4 * d, d)
+
+    def forward(self, x):
+        return self.down(torch.nn.functional.silu(self.gate(x)) * self.up(x))
+
+
+class _TwoBlocks(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a, self.b = _FFNBlock(), _FFNBlock()
+
+    def forward(self, x):
+        return self.b(self.a(x))
+
+
+def _dmp_pinned(rank, world):
+    """Policy plans from a class-level provider, overridden for one subtree by a pinned plan (legacy ``dmp.py:37-184``)."""
+    import copy
+
+    from vescale_b200 import Replicate, Shard, distribute_tensor, init_device_mesh
+    from vescale_b200.dtensor.api import DTensor
+    from vescale_b200.parallel.dmp import PlanGenerator, auto_parallelize_module, get_plan_overriding_policy, set_plan_overriding_policy
+    from vescale_b200.parallel.dmp.policies import REGISTRY
+    from vescale_b200.parallel.dmp.policies.megatron import mlp_plan_provider
+    from vescale_b200.parallel.dmp.policies.utils import validate_single_input
+
+    if not REGISTRY.has_module("_FFNBLOCK"):
+        REGISTRY.provide_register_for_policy("MEGATRON")(["_FFNBlock"])(mlp_plan_provider)
+    dev = device_type()
+    mesh = init_device_mesh(dev, (world,), mesh_dim_names=("TP",))
+    torch.manual_seed(0)
+    ref = _TwoBlocks().to(dev)
+    model = copy.deepcopy(ref)
+    assert validate_single_input(model.a) == "x"
+    # pin block b: keep it entirely replicated (e.g. too small to be worth sharding); the policy still shards block a
+    set_plan_overriding_policy(model.b, param_sharding_plan={r".*": [Replicate()]}, fwd_resharding_plan={"input": [[Replicate()]], "output": [[Replicate()]]})
+    assert get_plan_overriding_policy(model.b)[0] is not None and get_plan_overriding_policy(model.a) == (None, None)
+    try:
+        set_plan_overriding_policy(model, {})
+        raise AssertionError("pinning above a pinned subtree must be rejected")
+    except NotImplementedError:
+        pass
+    p, f, pin_p, pin_f, pol_p, pol_f = PlanGenerator(model, "megatron").generate()
+    assert any(k.startswith("b") for k in pol_p) and not any(k.startswith(r"b\.") and v != [Replicate()] for k, v in p.items())
+    assert p[r"a\.up\.weight"] == [Shard(0)] and p[r"a\.down\.weight"] == [Shard(1)] and p[r"b\..*"] == [Replicate()]
+    assert f[r"a\.input"] == [[Replicate()]] and f[r"b\.output"] == [[Replicate()]] and r"b\.input" in pin_f
+    saved = {}
+    auto_parallelize_module(model, mesh, "MEGATRON", plan_to_save=saved)
+    assert saved["param_sharding_plan"] == p
+    assert model.a.up.weight.placements == (Shard(0),) and model.a.down.weight.placements == (Shard(1),) and model.b.up.weight.placements == (Replicate(),)
+    x = torch.randn(2, 8, 16).to(dev)
+    out = model(distribute_tensor(x, mesh, [Replicate()]))
+    out = out.full_tensor() if isinstance(out, DTensor) else out
+    torch.testing.assert_close(out, ref(x), rtol=1e-4, atol=1e-5)
+    try:
+        PlanGenerator(model, "no_such_policy")
+        raise AssertionError
+    except ValueError:
+        pass
+
+
+def test_dmp_pinned_plans_and_class_level_providers():
+    run_distributed(_dmp_pinned, 2)

@@ -166,7 +166,8 @@ _ALIASES = {
     "vescale.ndtimeline.handlers.parser_handler": "vescale_b200.profiler.handlers",
     "vescale.ndtimeline.handlers.do_nothing_handler": "vescale_b200.profiler.handlers",
     "vescale.ndtimeline.handlers.sock_handler": "vescale_b200.profiler.sock_streamer",
-    "vescale.optim.utils": "vescale_b200.optim.distributed_optimizer",
+    "vescale.optim.utils": "vescale_b200.optim.utils",
+    "vescale.optim.checkpoint_helper": "vescale_b200.optim.distributed_optimizer",
     "vescale.model.patch.linear": "vescale_b200.model.patch.linear",
     "vescale.model.patch.vp_embedding": "vescale_b200.model.patch.vp_embedding",
     "vescale.model.patch.vp_cross_entropy": "vescale_b200.model.patch.vp_cross_entropy",

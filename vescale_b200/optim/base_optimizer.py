@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from ..dtensor.api import DTensor
 
-__all__ = ["BasicOptimizer", "GradOptimizerHookBase", "BasicOptimizerHook"]
+__all__ = ["BasicOptimizer", "GradOptimizerHookBase", "BasicOptimizerHook", "OptimizerBase"]
 
 
 class GradOptimizerHookBase:
@@ -44,7 +44,40 @@ class BasicOptimizerHook(GradOptimizerHookBase):
         return None
 
 
-class BasicOptimizer:
+class OptimizerBase:
+    """What every optimizer wrapper of this package provides (legacy ``base_optimizer.py:26-113``): a ``step`` that first finishes
+    gradient synchronisation, ``zero_grad`` that also clears gradient buffers, ``state_dict`` / ``load_state_dict``, and the
+    ``param_groups`` of the wrapped optimizer.  ``BasicOptimizer`` and ``DistributedOptimizer`` are its two implementations."""
+
+    optimizer: torch.optim.Optimizer
+
+    def step(self, closure=None):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def zero_grad(self, set_to_none: bool = True):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def state_dict(self):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def load_state_dict(self, state_dict):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def get_loss_scale(self) -> float:
+        """bf16 / fp32 training does not scale the loss."""
+        return 1.0
+
+    # ``optimizer.state`` / ``optimizer.param_groups`` read and written through the wrapper (learning-rate schedulers do both)
+    @property
+    def state(self):
+        return self.optimizer.state
+
+    @state.setter
+    def state(self, value):
+        self.optimizer.state = value
+
+
+class BasicOptimizer(OptimizerBase):
     """Thin wrapper that finishes DModule / DDP gradient synchronisation, exposes ``main_grad`` as ``.grad``, clips, and steps the
     inner ``torch.optim`` optimizer (legacy ``optim/base_optimizer.py:116-206``)."""
     def __init__(self, optimizer: torch.optim.Optimizer, models: Union[nn.Module, Sequence[nn.Module]], grad_hook: Optional[GradOptimizerHookBase] = None, clip_grad: float = 0.0):

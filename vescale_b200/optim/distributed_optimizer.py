@@ -28,9 +28,10 @@ import torch.nn as nn
 
 from ..dtensor.api import DTensor
 from ..parallel.ddp import DistributedDataParallel, GradBuffer, _local
+from .base_optimizer import OptimizerBase
 from .clip_grads import get_grad_norm_fp32
 
-__all__ = ["DistributedOptimizer", "OptimizerStateSpec"]
+__all__ = ["DistributedOptimizer", "OptimizerStateSpec", "Range", "convert_dict_with_sharded", "convert_dict_sharded_to_tensor", "initialize_optimizer_state"]
 
 
 @dataclass
@@ -40,6 +41,66 @@ class OptimizerStateSpec:
     global_offset: Tuple[int, ...]
     local_tensor: torch.Tensor
     dp_ranks_ranges: Optional[Dict[int, Tuple[int, int]]] = None
+
+
+class Range:
+    """Half-open index range ``[start, end)`` of a shard inside a flat buffer (legacy ``distributed_optimizer.py:26-48``)."""
+
+    __slots__ = ("start", "end", "size")
+
+    def __init__(self, start: int, end: int):
+        if end < start:
+            raise ValueError(f"empty-negative range [{start}, {end})")
+        self.start, self.end, self.size = int(start), int(end), int(end) - int(start)
+
+    def normalize(self, start: int = 0) -> "Range":
+        """The same length re-based at ``start`` (world offset -> offset inside a bucket / a parameter)."""
+        return Range(start, start + self.size)
+
+    def intersect(self, other: "Range") -> Optional["Range"]:
+        lo, hi = max(self.start, other.start), min(self.end, other.end)
+        return Range(lo, hi) if hi > lo else None
+
+    def __len__(self) -> int:
+        return self.size
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, Range) and (self.start, self.end) == (other.start, other.end)
+
+    def __hash__(self) -> int:
+        return hash((self.start, self.end))
+
+    def __repr__(self) -> str:
+        return f"Range({self.start},{self.end} [{self.size}])"
+
+    __str__ = __repr__
+
+
+def convert_dict_with_sharded(param_state: dict, global_shape: Tuple[int, ...], local_shape: Tuple[int, ...], global_offset: Tuple[int, ...], dp_ranks_ranges: Optional[Dict[int, "Range"]] = None) -> dict:
+    """One parameter's optimizer state for saving: every tensor entry (``exp_avg`` ...) is wrapped in an ``OptimizerStateSpec`` that
+    says where the flat piece sits in the global tensor; scalars (``step``) pass through.  Without ``dp_ranks_ranges`` the piece must
+    be the whole model-parallel shard."""
+    import math
+
+    out = {}
+    for k, v in param_state.items():
+        if isinstance(v, torch.Tensor) and v.dim() >= 1:
+            if not dp_ranks_ranges and math.prod(local_shape) != v.numel():
+                raise ValueError(f"state {k!r}: {v.numel()} elements do not fill the local shard {tuple(local_shape)} of global {tuple(global_shape)} at {tuple(global_offset)}")
+            out[k] = OptimizerStateSpec(tuple(global_shape), tuple(local_shape), tuple(global_offset), v, dp_ranks_ranges)
+        else:
+            out[k] = v
+    return out
+
+
+def convert_dict_sharded_to_tensor(param_state: dict, range_1d: Optional["Range"] = None) -> dict:
+    """The inverse after loading: specs back to flat tensors, cut to this rank's ``range_1d`` of the shard when the state is spread
+    over several DP ranks.  In place; returns the dict."""
+    for k, v in param_state.items():
+        if isinstance(v, OptimizerStateSpec):
+            flat = v.local_tensor.flatten()
+            param_state[k] = flat[range_1d.start:range_1d.end] if range_1d is not None else flat
+    return param_state
 
 
 class _BucketShard:
@@ -52,7 +113,7 @@ class _BucketShard:
         self.n = n
 
 
-class DistributedOptimizer:
+class DistributedOptimizer(OptimizerBase):
     """ZeRO-2+ wrapper: every DDP bucket is sharded evenly over the DP group, fp32 main-parameter shards are updated by the inner
     optimizer and all-gathered back into the (aliased) parameter buffer, optionally overlapped with the next forward; the state
     dict is expressed as ``OptimizerStateSpec``s so it reshards on load.  Parity: legacy ``optim/distributed_optimizer.py:131-1296``."""
@@ -370,3 +431,11 @@ class DistributedOptimizer:
                         dst[lo - mp._piece[0] : hi - mp._piece[0]].copy_(src[lo - s_lo : hi - s_lo])
         for sh in self.shards:
             sh.pbuf[sh.lo : sh.hi].copy_(self.main_shards[id(sh)])
+
+
+def initialize_optimizer_state(optimizer: "DistributedOptimizer") -> None:
+    """Create the inner optimizer's per-parameter state (``exp_avg`` ...) without taking a step, so that a freshly built optimizer
+    has something to load a checkpoint INTO (legacy ``distributed_optimizer.py:1289-1296`` / ``checkpoint_helper.py``)."""
+    for g in optimizer.optimizer.param_groups:
+        for mp in g["params"]:
+            optimizer._ensure_state(mp)

@@ -68,3 +68,87 @@ def conv_provider(fqn, module, root):
     if "conv" in type(module).__name__.lower():
         return {"parameter": {}, "forward": {}}
     return None
+
+
+# ---- class-level providers (legacy ``megatron.py:32-219``) --------------------------------------------------------------------------------------
+# ``provider(fqn, module) -> (param_plan, fwd_plan)`` with keys RELATIVE to ``module`` (literal names such as ``fc1.weight``; the registry escapes them): what one registers through
+# ``REGISTRY.provide_register_for_policy("MEGATRON")`` for a model's own block classes.  They read the block's structure (which
+# children are Linear, in which order) instead of relying on child names; the leaf providers above remain the fallback for modules no
+# class-level provider claims.
+def _linears(module: nn.Module):
+    return [(n, m) for n, m in module.named_children() if isinstance(m, nn.Linear)]
+
+
+def _col(name: str, m: nn.Linear, param: dict) -> None:
+    param[name + ".weight"] = [Shard(0)]
+    if m.bias is not None:
+        param[name + ".bias"] = [Shard(0)]
+
+
+def _row(name: str, m: nn.Linear, param: dict) -> None:
+    param[name + ".weight"] = [Shard(1)]
+    if m.bias is not None:
+        param[name + ".bias"] = [Replicate()]
+
+
+def mlp_plan_provider(fqn: str, module: nn.Module, *, sync_dropout: bool = True):
+    """A feed-forward block: every Linear but the last is column-parallel, the last row-parallel (gated MLPs have two or three
+    column-parallel projections).  The block's input is gathered along the sequence, its output goes back to sequence-sharded."""
+    lin = _linears(module)
+    if len(lin) < 2:
+        return {}, {}
+    param: dict = {}
+    for n, m in lin[:-1]:
+        _col(n, m, param)
+    _row(lin[-1][0], lin[-1][1], param)
+    fwd = {"input": [[Replicate()]], "output": [[Shard(1)]]}
+    if not sync_dropout:  # dropout right after the row-parallel matmul draws per-shard masks unless it sees the resharded activation
+        fwd[lin[-1][0] + ".output"] = [[Shard(1)]]
+    return param, fwd
+
+
+def attention_plan_provider(fqn: str, module: nn.Module):
+    """Self-attention: q / k / v (or one fused qkv) column-parallel = heads split across ranks, the output projection row-parallel.
+    The last Linear child is taken as the output projection."""
+    lin = _linears(module)
+    if len(lin) < 2:
+        return {}, {}
+    param: dict = {}
+    for n, m in lin[:-1]:
+        _col(n, m, param)
+    _row(lin[-1][0], lin[-1][1], param)
+    return param, {"input": [[Replicate()]], "output": [[Shard(1)]]}
+
+
+def layernorm_plan_provider(fqn: str, module: nn.Module, *, seq_dim: int = 1):
+    """Norms run sequence-parallel: replicated affine parameters, activations sharded along ``seq_dim``."""
+    param = {n: [Replicate()] for n, _ in module.named_parameters(recurse=False)}
+    return param, {"input": [[Shard(seq_dim)]]}
+
+
+def embedding_plan_provider(fqn: str, module: nn.Module):
+    """Token embeddings are vocab-parallel (rows split; the lookup's masked partial results are reduce-scattered to the sequence
+    dim), positional ones replicated."""
+    if isinstance(module, nn.Embedding) and module.num_embeddings >= 4 * module.embedding_dim:
+        return {"weight": [Shard(0)]}, {"input": [[Replicate()]], "output": [[Shard(1)]]}
+    return {n: [Replicate()] for n, _ in module.named_parameters(recurse=False)}, {"output": [[Shard(1)]]}
+
+
+def lm_linear_plan_provider(fqn: str, module: nn.Module):
+    """A stand-alone Linear is treated as the LM head: vocab (output features) split, input gathered; logits stay vocab-sharded for a
+    vocab-parallel loss."""
+    if not isinstance(module, nn.Linear):
+        return {}, {}
+    param = {"weight": [Shard(0)]}
+    if module.bias is not None:
+        param["bias"] = [Shard(0)]
+    return param, {"input": [[Replicate()]]}
+
+
+def dropout_plan_provider(fqn: str, module: nn.Module):
+    return {}, {}
+
+
+def conv_plan_provider(fqn: str, module: nn.Module):
+    """Convolutions stay replicated under this policy."""
+    return {n: [Replicate()] for n, _ in module.named_parameters(recurse=False)}, {}
