@@ -36,6 +36,7 @@ FLAGS: Dict[str, Tuple[str, str]] = {
     "VESCALE_B200_GEMM_SCHED": ("static", "read by csrc/gemm_sm100.cu: static = persistent grid, tile += grid; clc = cluster launch control (one cluster per tile, running clusters pull the remaining tiles)"),
     "VESCALE_B200_ATTN": ("auto", "attention back end of ops.packed_attention: tcgen05 = hand-written sm_100a flash attention (csrc/attention_sm100.cu), cudnn = library SDPA, auto = faster of the two per shape"),
     "VESCALE_B200_CLOCK_SAMPLER": ("nvml", "bench.py clock / throttle sampler: nvml = in-process NVML thread, smi = nvidia-smi -lms child process"),
+    "VESCALE_CHECKPOINT_COORDINATOR": ("", "host:port of a checkpoint report service (checkpoint/server_lib.py): saves coordinate plans / results through it instead of process-group collectives"),
     "VESCALE_CHECKPOINT_WORKERS": ("2", "writer processes per rank that serialise and write checkpoint files (checkpoint/storage.py); 0 = in-process writer"),
     "VESCALE_B200_ATTN_FWD": ("3", "read by csrc/attention_sm100.cu: forward kernel variant (1 = four softmax warps, 2 = eight softmax warps splitting each row in halves, 3 = 2 with one 64-column TMEM load per tile)"),
     "VESCALE_B200_GEMM_RS": ("staged", "FusedTP.gemm_rs implementation: staged = partial tiles pushed into the owner's staging slots by the GEMM epilogue; nvls = GEMM into a symmetric buffer + switch-reduced pull of the owner's rows"),
