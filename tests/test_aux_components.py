@@ -221,6 +221,28 @@ def test_profiler_socket_streamer(tmp_path):
     spans = [e for e in ev if e["ph"] == "X"]
     assert len(spans) == 6 and {e["pid"] for e in spans} == {0, 1} and all(e["tid"] == 0 for e in spans)  # small stable thread ids ...
     assert {e["args"]["name"] for e in ev if e["ph"] == "M" and e["name"] == "thread_name"} == {"stream 7"}  # ... named after the CUDA stream
+    # the receiving side on its own: frames off a byte stream through a bare recv(), carry-over between calls, validation
+    import io
+
+    import pytest
+
+    from vescale_b200.profiler.binary_protocol import dumps, loads, read_or_recv, recv_and_validate
+    from vescale_b200.profiler.exceptions import ProtocolValidationError
+
+    stream = io.BytesIO(encode_frame(recs, 3, 42) + encode_frame([], 5, 1))
+    recv = lambda n: stream.read(min(n, 7))  # noqa: E731  a peer that trickles 7 bytes at a time
+    carry = bytearray()
+    kind, rank, step, payload = recv_and_validate(recv, carry)
+    assert (kind, rank, step, loads(payload)) == (0, 3, 42, recs)
+    assert recv_and_validate(recv, carry)[1:3] == (5, 1) and loads(dumps({"a": [1, 2]})) == {"a": [1, 2]}
+    with pytest.raises(EOFError):
+        recv_and_validate(recv, carry)
+    with pytest.raises(ProtocolValidationError, match="magic"):
+        recv_and_validate(io.BytesIO(b"XXXX" + bytes(20)).read, bytearray())
+    with pytest.raises(BrokenPipeError):
+        recv_and_validate(io.BytesIO(encode_frame(recs, 0, 0)[:-3]).read, bytearray())
+    pre = bytearray(b"abcdef")
+    assert read_or_recv(4, None, pre) == b"abcd" and pre == bytearray(b"ef")
 
 
 def _emulator_vs_real(rank, world):
@@ -718,3 +740,33 @@ def test_named_mem_file_server_path_api_and_pinned_pool_functions():
     assert torch.equal(h, t) and h.data_ptr() != t.data_ptr()
     deallocate_cpu_tensor_in_pinned_mem_pool(h)
     assert GLOBAL_POOL is not None
+
+
+def test_profiler_device_timer_global_clock_and_singleton():
+    import time
+
+    import pytest
+
+    from vescale_b200.profiler.timer import DeviceTimer, GlobalReferenceTime, Singleton
+
+    class Once(metaclass=Singleton):
+        def __init__(self, v=0):
+            self.v = v
+
+    assert Once(1) is Once(2) and Once().v == 1
+    GlobalReferenceTime.sync_events()
+    t0 = time.time_ns() / 1e3
+    assert GlobalReferenceTime.initialized and abs(GlobalReferenceTime.host_time(time.perf_counter()) - t0) < 5e4
+    assert GlobalReferenceTime.calibrate() == 1.0  # no GPU: nothing to drift against
+    t = DeviceTimer("step", is_host=True)
+    for _ in range(2):
+        with t:
+            time.sleep(0.01)
+    with pytest.raises(RuntimeError, match="not started"):
+        t.stop()
+    iv = t.intervals(reset=False)
+    assert len(iv) == 2 and iv[0][0] < iv[1][0] and all(9e3 < d < 2e5 for _, d in iv) and abs(iv[0][0] - t0) < 1e6
+    assert 18 < t.elapsed() < 400 and t.elapsed() == 0.0
+    t.disable()
+    t.start(); t.stop()  # noqa: E702  a disabled timer ignores both
+    assert t.intervals() == [] and not t.is_enabled()

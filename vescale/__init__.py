@@ -154,7 +154,7 @@ _ALIASES = {
     "vescale.ndtimeline.exceptions": "vescale_b200.profiler.exceptions",
     "vescale.ndtimeline.logger": "vescale_b200.profiler.logger",
     "vescale.ndtimeline.predefined": "vescale_b200.profiler.predefined",
-    "vescale.ndtimeline.binary_protocol": "vescale_b200.profiler.sock_streamer",
+    "vescale.ndtimeline.binary_protocol": "vescale_b200.profiler.binary_protocol",
     "vescale.ndtimeline.sock_streamer": "vescale_b200.profiler.sock_streamer",
     "vescale.ndtimeline.variables": "vescale_b200.profiler",
     "vescale.ndtimeline.handlers": "vescale_b200.profiler.handlers",

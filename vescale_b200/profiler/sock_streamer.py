@@ -14,7 +14,9 @@ from __future__ import annotations
 import json
 import multiprocessing as mp
 import os
+import queue
 import socket
+import socketserver
 import struct
 import threading
 from typing import Callable, List, Optional, Sequence
@@ -22,7 +24,7 @@ from typing import Callable, List, Optional, Sequence
 from .exceptions import ProtocolValidationError
 from .handlers import NDHandler
 
-__all__ = ["encode_frame", "decode_frames", "SockNDHandler", "NDtimelineStreamer", "dumps_fn", "loads_fn", "encode_package", "serialize_to_package", "SOCK_PARENT_DIR", "SOCK_PATH", "SOCK_TIMEOUT_CLIENT"]
+__all__ = ["encode_frame", "decode_frames", "SockNDHandler", "NDtimelineStreamer", "dumps_fn", "loads_fn", "encode_package", "serialize_to_package", "SOCK_PARENT_DIR", "SOCK_PATH", "SOCK_TIMEOUT_CLIENT", "MsgHandler", "internal_queue_consume"]
 
 SOCK_PARENT_DIR = os.environ.get("VESCALE_NDTIMELINE_SOCK_DIR", "/tmp/ndtimeline")
 SOCK_PATH = os.path.join(SOCK_PARENT_DIR, "ndtimeline.sock")  # default collector socket of this host
@@ -92,47 +94,75 @@ class SockNDHandler(NDHandler):
                 self.sock.close()
 
 
+class MsgHandler(socketserver.BaseRequestHandler):
+    """One connection of the collector (one training rank): read frames, validate, queue them.  Nothing else happens on this thread —
+    the NDHandlers (file writes, trace merging) run on the consumer thread, so a slow handler fills the queue, not the socket, and the
+    training rank's ``sendall`` keeps returning immediately."""
+
+    def handle(self) -> None:
+        from .binary_protocol import loads_fn as _loads, recv_and_validate
+
+        carry = bytearray()
+        try:
+            while True:
+                try:
+                    kind, rank, step, payload = recv_and_validate(self.request.recv, carry)
+                except (EOFError, BrokenPipeError):
+                    return
+                if kind == KIND_CLOSE:
+                    return
+                self.server.queue.put((rank, step, _loads(payload)))
+        except ProtocolValidationError as e:
+            self.server.queue.put(e)
+        finally:
+            self.server.queue.put(_CLIENT_DONE)
+
+
+_CLIENT_DONE = object()
+
+
+def internal_queue_consume(q: "queue.Queue", handlers: Sequence[NDHandler], expected_clients: int) -> int:
+    """Consumer loop: hand queued record batches to the handlers until ``expected_clients`` connections have finished.  Returns the
+    number of batches processed.  A protocol error from a connection is re-raised here, after that connection was counted."""
+    done = n = 0
+    err = None
+    while done < expected_clients:
+        item = q.get()
+        if item is _CLIENT_DONE:
+            done += 1
+        elif isinstance(item, Exception):
+            err = item
+        else:
+            rank, step, recs = item
+            for h in handlers:
+                h(recs, rank, step)
+            n += 1
+    if err is not None:
+        raise err
+    return n
+
+
+class _Collector(socketserver.ThreadingMixIn, socketserver.UnixStreamServer):
+    daemon_threads = True
+    request_queue_size = 128
+
+
 def _serve(sock_path: str, make_handlers: Callable[[], Sequence[NDHandler]], expected_clients: int, ready) -> None:
     handlers = list(make_handlers())
     if os.path.exists(sock_path):
         os.unlink(sock_path)
-    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    srv.bind(sock_path)
-    srv.listen(max(8, expected_clients))
+    srv = _Collector(sock_path, MsgHandler)
+    srv.queue = queue.Queue()
+    t = threading.Thread(target=srv.serve_forever, kwargs={"poll_interval": 0.05}, daemon=True)
+    t.start()
     ready.set()
-    lock = threading.Lock()
-    closed = [0]
-
-    def client(conn):
-        buf = bytearray()
-        try:
-            while True:
-                chunk = conn.recv(1 << 16)
-                if not chunk:
-                    break
-                buf += chunk
-                for kind, rank, step, recs in decode_frames(buf):
-                    if kind == KIND_CLOSE:
-                        return
-                    with lock:
-                        for h in handlers:
-                            h(recs, rank, step)
-        finally:
-            conn.close()
-            with lock:
-                closed[0] += 1
-
-    threads = []
-    for _ in range(expected_clients):
-        conn, _addr = srv.accept()
-        t = threading.Thread(target=client, args=(conn,), daemon=True)
-        t.start()
-        threads.append(t)
-    for t in threads:
-        t.join()
-    srv.close()
-    if os.path.exists(sock_path):
-        os.unlink(sock_path)
+    try:
+        internal_queue_consume(srv.queue, handlers, expected_clients)
+    finally:
+        srv.shutdown()
+        srv.server_close()
+        if os.path.exists(sock_path):
+            os.unlink(sock_path)
 
 
 class NDtimelineStreamer:

@@ -25,7 +25,7 @@ from .handlers import NDHandler
 from .pool import CudaEventPool
 from .world_info import WorldInfo
 
-__all__ = ["NDTimerManager", "NDMetricLevel", "init_ndtimers", "ndtimeit", "ndtimeit_p2p", "ndtimeit_coll", "ndtimer", "flush", "wait", "inc_step", "set_global_step", "is_initialized", "DeviceTimerMeta", "NDTimerManagerSingleton"]
+__all__ = ["NDTimerManager", "NDMetricLevel", "init_ndtimers", "ndtimeit", "ndtimeit_p2p", "ndtimeit_coll", "ndtimer", "flush", "wait", "inc_step", "set_global_step", "is_initialized", "DeviceTimerMeta", "NDTimerManagerSingleton", "Singleton", "GlobalReferenceTime", "DeviceTimer"]
 
 
 class NDMetricLevel(IntEnum):
@@ -70,6 +70,175 @@ class DeviceTimerMeta:
                                    common_extra=dict(self.common_extra))
 
 
+class Singleton(type):
+    """Metaclass: one instance per class, constructed on first call (legacy ``ndtimeline/timer.py:37-45``)."""
+
+    _instances: Dict[type, Any] = {}
+    _lock = threading.Lock()
+
+    def __call__(cls, *args, **kwargs):
+        if cls not in Singleton._instances:
+            with Singleton._lock:
+                if cls not in Singleton._instances:
+                    Singleton._instances[cls] = super().__call__(*args, **kwargs)
+        return Singleton._instances[cls]
+
+
+class GlobalReferenceTime:
+    """The process-wide clock every record is stamped on (legacy ``ndtimeline/timer.py:48-151``).
+
+    * ``sync_events`` — the reference point: a CUDA event recorded at a known host time, with the host time shifted by this rank's
+      lead over the earliest rank at a barrier (``all_gather`` of ``time_ns``), so that timelines of different ranks line up.
+    * ``elapsed_time(event)`` — absolute micro-seconds of a CUDA event: reference host time + GPU time since the reference event,
+      the latter scaled by ``drift`` because the GPU's event clock and the host clock do not tick at exactly the same rate
+      (tens of ppm: milliseconds over a long run).
+    * ``calibrate`` — re-estimates ``drift`` from how far the two clocks have moved since the reference; cheap, called from ``flush``
+      every few seconds."""
+
+    initialized = False
+    cuda = False
+    ref_event = None
+    ref_host_us = 0.0
+    ref_perf = 0.0
+    clock_offset_us = 0.0
+    drift = 1.0
+    last_calibrated = 0.0
+    _lock = threading.Lock()
+
+    @classmethod
+    def sync_events(cls, group=None, world_size: int = 1) -> None:
+        with cls._lock:
+            cls.cuda = torch.cuda.is_available()
+            cls.clock_offset_us = 0.0
+            if dist.is_available() and dist.is_initialized() and world_size > 1:
+                dist.barrier(group=group)
+                t = torch.tensor([time.time_ns()], dtype=torch.int64)
+                if dist.get_backend(group) == "nccl":
+                    t = t.cuda()
+                ts = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
+                dist.all_gather(ts, t, group=group)
+                cls.clock_offset_us = (int(t.item()) - min(int(x.item()) for x in ts)) / 1e3  # my lead over the earliest rank at the barrier
+            if cls.cuda:
+                cls.ref_event = torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                cls.ref_event.record()
+                torch.cuda.synchronize()
+            cls.ref_host_us = time.time_ns() / 1e3 - cls.clock_offset_us
+            cls.ref_perf = time.perf_counter()
+            cls.drift, cls.last_calibrated, cls.initialized = 1.0, cls.ref_perf, True
+
+    @classmethod
+    def elapsed_time(cls, event) -> float:
+        """Absolute time (us on the aligned clock) at which ``event`` completed."""
+        return cls.ref_host_us + cls.ref_event.elapsed_time(event) * 1e3 * cls.drift
+
+    @classmethod
+    def host_time(cls, perf_counter_value: float) -> float:
+        return cls.ref_host_us + (perf_counter_value - cls.ref_perf) * 1e6
+
+    @classmethod
+    def calibrate(cls, min_interval_s: float = 0.0) -> float:
+        """Re-estimate ``drift`` (host micro-seconds per GPU micro-second since the reference).  Needs at least 100 ms of distance to
+        the reference for a meaningful ratio; returns the current value."""
+        now = time.perf_counter()
+        if not cls.initialized or not cls.cuda or now - cls.last_calibrated < min_interval_s:
+            return cls.drift
+        with cls._lock:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            e.synchronize()
+            host_us = (time.perf_counter() - cls.ref_perf) * 1e6
+            gpu_us = cls.ref_event.elapsed_time(e) * 1e3
+            if gpu_us > 1e5:
+                ratio = host_us / gpu_us
+                if 0.99 < ratio < 1.01:  # anything else is a measurement glitch (a stalled host thread), not clock drift
+                    cls.drift = ratio
+            cls.last_calibrated = now
+        return cls.drift
+
+
+class DeviceTimer:
+    """A named stopwatch on a CUDA stream (or on the host with ``is_host=True``), usable on its own: ``start()`` / ``stop()`` may be
+    called repeatedly; ``elapsed()`` returns the summed duration in milliseconds and resets; ``intervals()`` the individual
+    ``(absolute start us, duration us)`` pairs on the aligned clock (legacy ``ndtimeline/timer.py:239-407``).  ``NDTimerManager``
+    is the pooled, flushed, many-timers version of this."""
+
+    def __init__(self, name: str, is_host: bool = False, stream=None, meta: Optional[DeviceTimerMeta] = None):
+        self.name = name
+        self.meta = meta or DeviceTimerMeta(name=name, is_cpu_op=is_host)
+        self.is_host = is_host or not torch.cuda.is_available()
+        self.stream = stream
+        self._started = False
+        self._pairs: List[tuple] = []
+        self._t0 = None
+        if not GlobalReferenceTime.initialized:
+            GlobalReferenceTime.sync_events()
+
+    def is_enabled(self) -> bool:
+        return self.meta.enabled
+
+    def enable(self) -> None:
+        self.meta.enabled = True
+
+    def disable(self) -> None:
+        self.meta.enabled = False
+
+    def start(self, stream=None) -> None:
+        if not self.meta.enabled:
+            return
+        if self._started:
+            raise RuntimeError(f"timer {self.name!r} has already been started")
+        self._started = True
+        if self.is_host:
+            self._t0 = time.perf_counter()
+        else:
+            s = stream or self.stream or torch.cuda.current_stream()
+            self._t0 = (torch.cuda.Event(enable_timing=True), s)
+            self._t0[0].record(s)
+
+    def stop(self) -> None:
+        if not self.meta.enabled:
+            return
+        if not self._started:
+            raise RuntimeError(f"timer {self.name!r} is not started")
+        self._started = False
+        if self.is_host:
+            self._pairs.append((self._t0, time.perf_counter()))
+        else:
+            e0, s = self._t0
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(s)
+            self._pairs.append((e0, e1))
+
+    def intervals(self, reset: bool = True) -> List[tuple]:
+        out = []
+        for a, b in self._pairs:
+            if self.is_host:
+                out.append((GlobalReferenceTime.host_time(a), (b - a) * 1e6))
+            else:
+                b.synchronize()
+                out.append((GlobalReferenceTime.elapsed_time(a), a.elapsed_time(b) * 1e3))
+        if reset:
+            self._pairs = []
+        return out
+
+    def elapsed(self, reset: bool = True) -> float:
+        if self._started:
+            raise RuntimeError(f"timer {self.name!r} is still running")
+        return sum(d for _, d in self.intervals(reset)) / 1e3
+
+    def reset(self) -> None:
+        self._pairs, self._started = [], False
+
+    def __enter__(self):
+        self.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop()
+        return False
+
+
 class NDTimerManager:
     """Pooled CUDA-event timers on a cross-rank aligned clock with asynchronous flush to handlers (legacy ``ndtimeline/timer.py:410-665``)."""
     def __init__(self, rank: int = 0, world_size: int = 1, handlers: Sequence[NDHandler] = (), level: NDMetricLevel = NDMetricLevel.TRACE, group=None,
@@ -96,23 +265,11 @@ class NDTimerManager:
         self._calibrate(group)
 
     def _calibrate(self, group=None):
-        """Cross-rank clock alignment + GPU reference event."""
-        if dist.is_available() and dist.is_initialized() and self.world_size > 1:
-            dist.barrier(group=group)
-            t = torch.tensor([time.time_ns()], dtype=torch.int64)
-            if dist.get_backend(group) == "nccl":
-                t = t.cuda()
-            ts = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
-            dist.all_gather(ts, t, group=group)
-            base = min(int(x.item()) for x in ts)
-            self.clock_offset_us = (int(t.item()) - base) / 1e3  # my lead over the earliest rank at the barrier
-        if self.cuda:
-            self.ref_event = torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            self.ref_event.record()
-            torch.cuda.synchronize()
-        self.ref_host_us = time.time_ns() / 1e3 - self.clock_offset_us
-        self.ref_perf = time.perf_counter()
+        """Cross-rank clock alignment + GPU reference event: delegated to the process-wide ``GlobalReferenceTime``."""
+        GlobalReferenceTime.sync_events(group, self.world_size)
+        self.clock_offset_us = GlobalReferenceTime.clock_offset_us
+        self.ref_event = GlobalReferenceTime.ref_event
+        self.ref_host_us, self.ref_perf = GlobalReferenceTime.ref_host_us, GlobalReferenceTime.ref_perf
 
     def register_timers(self, metas: Sequence[DeviceTimerMeta]) -> None:
         for m in metas:
@@ -160,7 +317,7 @@ class NDTimerManager:
         for r in recs:
             if "e0" in r:
                 r["e1"].synchronize()
-                start = self.ref_host_us + self.ref_event.elapsed_time(r["e0"]) * 1e3
+                start = GlobalReferenceTime.elapsed_time(r["e0"])
                 dur = r["e0"].elapsed_time(r["e1"]) * 1e3
                 self.pool.put(r.pop("e0"))
                 self.pool.put(r.pop("e1"))
@@ -174,6 +331,7 @@ class NDTimerManager:
         step = self.step
 
         def work():
+            GlobalReferenceTime.calibrate(min_interval_s=5.0)
             done = self._materialise(recs)
             for h in self.handlers:
                 # records of a "selected"-dispatch timer only reach the handlers it names (by class name or `.name`)
