@@ -165,3 +165,48 @@ host:1:2 [0] NCCL INFO 2097152 Bytes -> Algo 1 proto 2 time 41.5
         p2p.assert_drained()
     with pytest.raises(AssertionError):
         RingPrimitive([torch.zeros(4), torch.zeros(4)]).recv(0, 0, 4)  # nothing was sent
+
+
+def test_emulator_per_dim_redistribute_and_nccl_named_helpers():
+    """Redistribution as the real planner does it (one collective per differing mesh dim), transition objects, NCCL-named helpers."""
+    import torch
+
+    from vescale_b200.emulator import comm_api as ca
+    from vescale_b200.emulator.algorithms import contract_tensor_list, expand_tensor_list
+    from vescale_b200.emulator.comm_primitive import BaseRedistributeFunc
+    from vescale_b200.emulator.nccl import comm, constants as c, profiler_result as pr, tuning
+    from vescale_b200.mesh import DeviceMesh
+    from vescale_b200.placement import Partial, Replicate, Shard
+
+    mesh = DeviceMesh("cpu", torch.arange(4).reshape(2, 2), _rank=0)
+    full = torch.arange(48.0).reshape(8, 6)
+    cases = [([Shard(0), Shard(1)], [Replicate(), Shard(0)], ["all_gather", "all_to_all"]), ([Partial(), Shard(1)], [Shard(0), Shard(1)], ["reduce_scatter"]),
+             ([Partial(), Partial()], [Replicate(), Shard(0)], ["all_reduce", "reduce_scatter"]), ([Shard(0), Shard(0)], [Replicate(), Replicate()], None)]
+    for src, dst, want in cases:
+        loc = ca.distribute_tensor(full, mesh, src)
+        tr = []
+        out = ca.DTensorRedistribute.apply(loc, full.shape, mesh, src, dst, trace=tr)
+        assert torch.equal(ca.full_tensor(out, full.shape, mesh, dst), ca.full_tensor(loc, full.shape, mesh, src))
+        if want is not None:
+            assert [t[2] for t in tr] == want
+        else:
+            assert tr == []  # two mesh dims on one tensor dim: no single-step path, full-tensor route
+    f = BaseRedistributeFunc.of(Partial("sum"), Shard(1))
+    assert (f.name, f.collective, f.bound["shard_dim"]) == ("P2S", "reduce_scatter", 1) and "P2S" in repr(f)
+    e = expand_tensor_list([torch.full((2,), float(i)) for i in range(3)])
+    assert e[1].tolist() == [0, 0, 1, 1, 0, 0] and contract_tensor_list(e)[2].tolist() == [2, 2]
+
+    assert (c.div_up(7, 2), c.round_up(7, 4), c.align_up(5000, 4096), c.log2i(9), c.NcclFunc.ALL_REDUCE) == (4, 8, 8192, 3, c.Func.ALL_REDUCE)
+    cm = comm.init(8)
+    assert comm.compute_buff_sizes(cm, {"NCCL_BUFFSIZE": "8388608"})[int(c.Proto.SIMPLE)] == 8388608
+    assert comm.compute_buff_sizes(cm, {})[int(c.Proto.SIMPLE)] == c.DEFAULT_BUFFSIZE[c.Proto.SIMPLE]
+    assert (tuning.get_nthreads("t", 100, 64, 512, 256), tuning.get_nthreads("t", -2, 64, 512, 256), tuning.get_nthreads("t", 32, 64, 512, 256)) == (512, 256, 64)
+    assert tuning.nccl_topo_get_algo_time is tuning.algo_time and tuning.DIVUP(9, 4) == 3 and tuning.get_cpu_info()[0] in (1, 2, 3)
+    topo = ('<system version="1"><cpu numaid="0" arch="x86_64" vendor="AuthenticAMD"><pci><gpu dev="0" sm="100" rank="0"><nvlink target="x" count="18" tclass="0x068000"/></gpu>'
+            '<gpu dev="1" sm="90" rank="1"/></pci><nic><net name="mlx5_0" speed="400000" gdr="1"/></nic></cpu></system>')
+    t = pr.parse_nccl_topo(topo)
+    assert t["cpu_arch_amd"] and t["nvswitch"] and pr.get_default_min_max_compcap(t) == (90, 100) and pr.get_default_min_max_compcap() == (100, 100)
+    g = pr.parse_graph_xml('<graphs version="1"><graph id="0" pattern="4" nchannels="2" speedintra="40" speedinter="40" typeintra="NVL" typeinter="PIX">'
+                           '<channel><gpu dev="0"/><gpu dev="1"/></channel><channel><gpu dev="1"/><gpu dev="0"/></channel></graph></graphs>')
+    assert g[0].channels == [[0, 1], [1, 0]] and g[0].bw_intra == 40.0
+    assert comm.nccl_info_set_derived(comm.CollInfo(func=int(c.Func.ALL_GATHER), count=1024), 8).total_bytes == 8 * 4096

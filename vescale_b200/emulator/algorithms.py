@@ -254,3 +254,27 @@ def split_tensors(t: torch.Tensor, sizes: Sequence[int]) -> List[torch.Tensor]:
 
 def concatenate_tensors(ts: Sequence[torch.Tensor]) -> torch.Tensor:
     return torch.cat([t.reshape(-1) for t in ts])
+
+
+def expand_tensor_list(tensor_list: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """All-gather as an in-place ring algorithm wants its buffers: rank ``i``'s 1-D contribution of ``a`` elements becomes a zero
+    buffer of ``n * a`` with the contribution sitting in slot ``i`` (the slot it will still occupy when the gather is done)."""
+    n, a = len(tensor_list), tensor_list[0].numel()
+    out = []
+    for i, t in enumerate(tensor_list):
+        if t.numel() != a:
+            raise ValueError("expand_tensor_list: all contributions must have the same number of elements")
+        buf = torch.zeros(n * a, dtype=t.dtype, device=t.device)
+        buf[i * a:(i + 1) * a] = t.reshape(-1)
+        out.append(buf)
+    return out
+
+
+def contract_tensor_list(tensor_list: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """The inverse view for reduce-scatter: of rank ``i``'s full-length buffer only slot ``i`` is its result."""
+    n = len(tensor_list)
+    a = tensor_list[0].numel() // n
+    return [t.reshape(-1)[i * a:(i + 1) * a] for i, t in enumerate(tensor_list)]
+
+
+__all__ += ["expand_tensor_list", "contract_tensor_list"]

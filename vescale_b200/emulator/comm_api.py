@@ -124,3 +124,46 @@ def mesh_scatter(scatter_lists: List[Optional[List[torch.Tensor]]], mesh: Device
         for j, r in enumerate(ranks):
             out[r] = src[j].clone()
     return out
+
+
+def redistribute_local_tensor(locals_: List[torch.Tensor], shape: Sequence[int], mesh: DeviceMesh, src: Sequence[Placement], dst: Sequence[Placement], pg_kw=None, trace: Optional[list] = None) -> List[torch.Tensor]:
+    """Redistribute the way the real planner does it — mesh dim by mesh dim with ONE collective per differing dim (Partial -> Shard is
+    a reduce-scatter, Shard(i) -> Shard(j) an all-to-all, ...) — so that the emulated result carries the same summation order as the
+    real run, instead of going through the full tensor (``redistribute_dtensor``).  Falls back to the full-tensor route when a
+    transition has no single-step primitive (interleaved / ragged placements, or several mesh dims sharding the same tensor dim).
+    ``trace``: a list that receives ``(mesh_dim, transition name, collective)`` per step."""
+    from .comm_primitive import BaseRedistributeFunc
+
+    src, dst = list(src), list(dst)
+    plain = all(type(p).__name__ in ("Shard", "Replicate", "Partial") for p in src + dst)
+    shard_dims = [p.dim for p in src + dst if type(p).__name__ == "Shard"]
+    multi = any(sum(1 for p in pl if type(p).__name__ == "Shard" and p.dim == d) > 1 for pl in (src, dst) for d in set(shard_dims))
+    if not plain or multi:
+        return redistribute_dtensor(locals_, shape, mesh, src, dst, pg_kw)
+    cur = list(locals_)
+    # replicate-producing steps innermost mesh dim first, shard-producing steps outermost first (the real planner's order)
+    order = [i for i in reversed(range(mesh.ndim)) if dst[i].is_replicate()] + [i for i in range(mesh.ndim) if not dst[i].is_replicate()]
+    for i in order:
+        if src[i] == dst[i]:
+            continue
+        try:
+            step = BaseRedistributeFunc.of(src[i], dst[i])
+        except NotImplementedError:
+            return redistribute_dtensor(locals_, shape, mesh, list(src), dst, pg_kw)
+        if step.name in ("P2R", "P2S") and pg_kw:
+            step.bound["pg_kw"] = pg_kw
+        cur = step(cur, mesh, i)
+        if trace is not None:
+            trace.append((i, step.name, step.collective))
+    return cur
+
+
+class DTensorRedistribute:
+    """Function-object form (legacy ``comm_api.py::DTensorRedistribute``): ``DTensorRedistribute.apply(locals_, shape, mesh, src, dst)``."""
+
+    @staticmethod
+    def apply(locals_, shape, mesh, src, dst, pg_kw=None, trace=None):
+        return redistribute_local_tensor(locals_, shape, mesh, src, dst, pg_kw, trace)
+
+
+__all__ += ["redistribute_local_tensor", "DTensorRedistribute"]

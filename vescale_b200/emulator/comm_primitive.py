@@ -98,3 +98,36 @@ def get_redistribute_fn(src, dst):
             return R2R
         return functools.partial(fn, src_dim=src.dim, dst_dim=dst.dim)
     return fn
+
+
+class BaseRedistributeFunc:
+    """A per-mesh-dim transition as an object (legacy ``comm_primitive.py:40-60``): ``name`` such as ``"P2S"``, the placement-specific
+    arguments bound at construction, ``__call__(locals_, mesh, mesh_dim)`` runs it on the global view.  ``BaseRedistributeFunc.of(src,
+    dst)`` picks the transition for a pair of placements; ``collective`` names what it costs on the wire."""
+
+    COLLECTIVE = {"R2R": None, "R2S": None, "R2P": None, "S2R": "all_gather", "P2R": "all_reduce", "P2S": "reduce_scatter", "S2S": "all_to_all"}
+
+    def __init__(self, name: str, **bound):
+        if name not in self.COLLECTIVE:
+            raise KeyError(f"unknown transition {name!r}")
+        self.name, self.bound = name, bound
+        self.fn = globals()[name]
+
+    @classmethod
+    def of(cls, src, dst) -> "BaseRedistributeFunc":
+        fn = get_redistribute_fn(src, dst)
+        base = getattr(fn, "func", fn)
+        return cls(base.__name__, **getattr(fn, "keywords", {}))
+
+    @property
+    def collective(self) -> Optional[str]:
+        return self.COLLECTIVE[self.name]
+
+    def __call__(self, locals_: List[torch.Tensor], mesh: DeviceMesh, mesh_dim: int) -> List[torch.Tensor]:
+        return self.fn(locals_, mesh, mesh_dim, **self.bound)
+
+    def __repr__(self) -> str:
+        return f"{self.name}({', '.join(f'{k}={v}' for k, v in self.bound.items())})"
+
+
+__all__ += ["BaseRedistributeFunc"]

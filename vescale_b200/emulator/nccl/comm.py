@@ -165,3 +165,38 @@ def init_comm(n_ranks: int, n_nodes: int = 1, compcap: int = 100, xml: Optional[
     comm.tree_depth = max(1, (n_ranks // n_nodes - 1) + (int(math.log2(n_nodes)) if n_nodes > 1 else 0))
     tune_model(comm)
     return comm
+
+
+# ---- NCCL-named entry points (``init.cc`` / ``info.h`` / ``enqueue.cc``) ------------------------------------------------------------------------
+NcclTopoGraph, NcclInfo = TopoGraph, CollInfo
+
+
+def compute_buff_sizes(comm: NcclComm, env: Optional[Dict[str, str]] = None) -> Dict[int, int]:
+    """``computeBuffSizes``: per-protocol FIFO sizes — the defaults unless ``NCCL_BUFFSIZE`` / ``NCCL_LL_BUFFSIZE`` /
+    ``NCCL_LL128_BUFFSIZE`` override them (``env``: a mapping to read them from, default the process environment)."""
+    import os
+
+    from .constants import Proto
+
+    env = os.environ if env is None else env
+    names = {int(Proto.LL): "NCCL_LL_BUFFSIZE", int(Proto.LL128): "NCCL_LL128_BUFFSIZE", int(Proto.SIMPLE): "NCCL_BUFFSIZE"}
+    for p, default in DEFAULT_BUFFSIZE.items():
+        raw = env.get(names[int(p)], "")
+        v = int(raw) if str(raw).lstrip("-").isdigit() else -2
+        comm.buff_sizes[int(p)] = v if v > 0 else default
+    return comm.buff_sizes
+
+
+def init(n_ranks: int, n_nodes: int = 1, compcap: int = 100, xml: Optional[str] = None, **kw) -> NcclComm:
+    """``ncclCommInitRank`` as far as the model is concerned: topology graphs, buffer sizes, tuning tables."""
+    comm = init_comm(n_ranks, n_nodes, compcap, xml, **kw)
+    compute_buff_sizes(comm)
+    return comm
+
+
+def nccl_info_set_derived(info: CollInfo, n_ranks: int) -> CollInfo:
+    """``ncclInfoSetDerived``: byte counts of a call.  For all-gather / reduce-scatter ``count`` is per rank; the algorithms move
+    ``count * n_ranks`` elements, which is what tuning looks at (``info.n_bytes`` stays per-rank; the total lands in ``total_bytes``)."""
+    per_rank = Func(info.func) in (Func.ALL_GATHER, Func.REDUCE_SCATTER)
+    info.total_bytes = info.n_bytes * (n_ranks if per_rank else 1)
+    return info

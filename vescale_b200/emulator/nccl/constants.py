@@ -110,3 +110,31 @@ def compcap_index(compcap: int) -> int:
 
 
 TYPE_SIZE = {"int8": 1, "uint8": 1, "float8_e4m3fn": 1, "float8_e5m2": 1, "float16": 2, "bfloat16": 2, "int32": 4, "float32": 4, "int64": 8, "float64": 8}
+
+
+# ---- NCCL's own spellings and integer helpers (``devcomm.h`` / ``align.h``) ------------------------------------------------------------------
+NcclFunc, NcclAlgo, NcclProto, NcclPattern = Func, Algo, Proto, Pattern
+ALIGN_SIZE = 4096  # buffers are carved out of one allocation on page boundaries
+
+
+def div_up(x: int, y: int) -> int:
+    return (x + y - 1) // y
+
+
+def round_up(x: int, y: int) -> int:
+    return (x + y - 1) // y * y
+
+
+def align_up(x: int, a: int) -> int:
+    """``a`` a power of two."""
+    if a & (a - 1):
+        raise ValueError("align_up: the alignment must be a power of two")
+    return (x + a - 1) & ~(a - 1)
+
+
+def log2i(n: int) -> int:
+    """floor(log2(n)); 0 for n <= 1."""
+    return max(0, int(n).bit_length() - 1)
+
+
+__all__ += ["NcclFunc", "NcclAlgo", "NcclProto", "NcclPattern", "ALIGN_SIZE", "div_up", "round_up", "align_up", "log2i"]

@@ -90,3 +90,42 @@ def parse_nccl_debug_log(text: str, rank: Optional[int] = None) -> NcclProfilerR
         if m:
             res.n_channels = int(m.group(1))
     return res
+
+
+# ---- topology / graph dumps (legacy ``nccl_profiler_result.py``: ``parse_nccl_topo`` / ``parse_graph_xml``) --------------------------------------
+def parse_graph_xml(text_or_path: str) -> Dict[int, "TopoGraph"]:
+    """An ``NCCL_GRAPH_DUMP_FILE``: graph id (0 ring, 1 tree, 2 collnet, 3 nvls) -> ``TopoGraph`` (channels' GPU orders, per-channel
+    intra / inter bandwidth, path types)."""
+    import os
+    import xml.etree.ElementTree as ET
+
+    from .comm import _graph_from_xml
+
+    text = open(text_or_path).read() if os.path.exists(text_or_path) else text_or_path
+    root = ET.fromstring(text)
+    return {int(g.get("id", i)): _graph_from_xml(g) for i, g in enumerate(root.iter("graph"))}
+
+
+def parse_nccl_topo(text_or_path: str) -> Dict[str, object]:
+    """An ``NCCL_TOPO_DUMP_FILE``: what the tuning model needs from it — the GPUs (device index, ``sm`` compute capability, rank),
+    the CPU (arch / vendor, AMD doubles the network overhead), NVLink fan-out per GPU and whether an NVSwitch is in the path."""
+    import os
+    import xml.etree.ElementTree as ET
+
+    text = open(text_or_path).read() if os.path.exists(text_or_path) else text_or_path
+    root = ET.fromstring(text)
+    gpus = [{"dev": int(g.get("dev", -1)), "sm": int(g.get("sm", 0)), "rank": int(g.get("rank", -1)), "nvlinks": sum(int(l.get("count", 1)) for l in g.iter("nvlink")),
+             "nvswitch": any(l.get("tclass", "").startswith("0x068000") for l in g.iter("nvlink"))} for g in root.iter("gpu")]
+    cpus = [{"arch": c.get("arch", ""), "vendor": c.get("vendor", ""), "numaid": int(c.get("numaid", 0))} for c in root.iter("cpu")]
+    nics = [{"name": n.get("name", ""), "speed": int(n.get("speed", 0)), "gdr": int(n.get("gdr", 0))} for n in root.iter("net")]
+    return {"gpus": gpus, "cpus": cpus, "nets": nics, "cpu_arch_amd": any(c["vendor"] == "AuthenticAMD" for c in cpus), "nvswitch": any(g["nvswitch"] for g in gpus)}
+
+
+def get_default_min_max_compcap(topo: Optional[Dict[str, object]] = None, default: int = 100) -> Tuple[int, int]:
+    """(min, max) compute capability over the GPUs of a parsed topology (tuning uses the minimum); ``(default, default)`` — Blackwell
+    — when no topology is given."""
+    sms = [g["sm"] for g in (topo or {}).get("gpus", []) if g.get("sm")]
+    return (min(sms), max(sms)) if sms else (default, default)
+
+
+__all__ += ["parse_graph_xml", "parse_nccl_topo", "get_default_min_max_compcap"]

@@ -277,3 +277,54 @@ def get_algo_info(comm: NcclComm, info: CollInfo, num_pipe_ops: int = 1, force: 
     nt = 3 * WARP_SIZE if nt // WARP_SIZE < 3 else nt
     info.n_channels, info.n_threads = nc, nt
     return compute_coll(comm, info)
+
+
+# ---- tuning.cc's own names ------------------------------------------------------------------------------------------------------------------------
+nccl_topo_tune_model, nccl_topo_get_algo_time = tune_model, algo_time
+getNetOverhead = _net_overhead  # noqa: N816
+
+
+def DIVUP(x: int, y: int) -> int:  # noqa: N802
+    return (x + y - 1) // y
+
+
+class ncclTopoCpuType:  # noqa: N801
+    """(arch, vendor, model) of the host CPU as ``ncclTopoCpuType`` reports it: the tuning model only distinguishes AMD x86 (twice
+    the network overhead) from everything else."""
+    ARCH_X86, ARCH_POWER, ARCH_ARM = 1, 2, 3
+    VENDOR_INTEL, VENDOR_AMD, VENDOR_ZHAOXIN = 1, 2, 3
+
+
+def get_cpu_info():
+    """``(arch, vendor)`` of this host (from ``/proc/cpuinfo`` / ``platform``)."""
+    import platform
+
+    m = platform.machine().lower()
+    arch = ncclTopoCpuType.ARCH_X86 if m in ("x86_64", "amd64", "i686") else ncclTopoCpuType.ARCH_ARM if m.startswith(("aarch", "arm")) else ncclTopoCpuType.ARCH_POWER
+    vendor = 0
+    try:
+        with open("/proc/cpuinfo") as f:
+            text = f.read(8192)
+        vendor = ncclTopoCpuType.VENDOR_AMD if "AuthenticAMD" in text else ncclTopoCpuType.VENDOR_INTEL if "GenuineIntel" in text else ncclTopoCpuType.VENDOR_ZHAOXIN if "Shanghai" in text else 0
+    except OSError:
+        pass
+    return arch, vendor
+
+
+def get_nthreads(name: str, env_value: int, min_threads: int, max_threads: int, default: int) -> int:
+    """``getNthreads``: an ``NCCL_*NTHREADS`` override is honoured only if it is a multiple of the warp size inside
+    ``[min_threads, max_threads]``; otherwise (or when unset: -2) the default applies."""
+    nt = env_value
+    if nt > 0:
+        if nt % WARP_SIZE != 0:
+            nt = max_threads
+        elif nt > max_threads:
+            nt = max_threads
+        elif nt < min_threads:
+            nt = min_threads
+    else:
+        nt = default
+    return nt
+
+
+__all__ += ["nccl_topo_tune_model", "nccl_topo_get_algo_time", "getNetOverhead", "DIVUP", "ncclTopoCpuType", "get_cpu_info", "get_nthreads"]
