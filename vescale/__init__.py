@@ -97,6 +97,11 @@ _ALIASES = {
     "vescale.plan.spec": "vescale_b200.parallel.pipe.plan",
     "vescale.plan.pipeline_parallel": "vescale_b200.parallel.pipe.plan",
     "vescale.engine.pipe": "vescale_b200.parallel.pipe.engine",
+    "vescale.moe._scheduler": "vescale_b200.parallel.moe.scheduler",
+    "vescale.moe._moe_param_buffer": "vescale_b200.parallel.moe.param_buffer",
+    "vescale.moe._moe_tensor": "vescale_b200.parallel.moe.hijack",
+    "vescale.moe._experts": "vescale_b200.parallel.moe.hijack",
+    "vescale.moe._utils": "vescale_b200.parallel.moe.layer",
     "vescale.moe.experts_allocator": "vescale_b200.parallel.moe.api",
     "vescale.moe.token_dispatcher": "vescale_b200.parallel.moe.api",
     "vescale.moe.moe_optimizer": "vescale_b200.parallel.moe.api",
@@ -169,6 +174,7 @@ _ALIASES = {
     "vescale.optim.utils": "vescale_b200.optim.utils",
     "vescale.optim.checkpoint_helper": "vescale_b200.optim.distributed_optimizer",
     "vescale.model.patch.linear": "vescale_b200.model.patch.linear",
+    "vescale.model.patch.utils": "vescale_b200.model.patch.utils",
     "vescale.model.patch.vp_embedding": "vescale_b200.model.patch.vp_embedding",
     "vescale.model.patch.vp_cross_entropy": "vescale_b200.model.patch.vp_cross_entropy",
     "vescale.utils.monkey_patch": "vescale_b200.utils.monkey_patch",

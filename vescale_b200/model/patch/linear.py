@@ -10,11 +10,30 @@ import torch.nn as nn
 from ...dtensor.api import DTensor
 
 
+def make_new_row_parallel_linear_forward(module: nn.Linear, output_placements=None):
+    """The replacement ``forward`` of one row-parallel ``nn.Linear`` (legacy ``linear.py:32-54``): matmul on the sharded operands,
+    THEN reduce (to ``output_placements``, default: every ``Partial`` -> ``Replicate``), THEN add the bias once."""
+
+    def forward(x):
+        y = torch.matmul(x, module.weight.t())
+        if output_placements is not None:
+            y = y.redistribute(y.device_mesh, output_placements)
+        elif isinstance(y, DTensor) and any(p.is_partial() for p in y.placements):
+            from ...placement import Replicate
+
+            y = y.redistribute(y.device_mesh, [Replicate() if p.is_partial() else p for p in y.placements])
+        return y + module.bias if module.bias is not None else y
+
+    return forward
+
+
 class RowParallelLinear:
     @staticmethod
     def patch(module: nn.Module, output_placements=None) -> None:
+        from .utils import is_patched, set_patched
+
         for m in module.modules():
-            if not isinstance(m, nn.Linear):
+            if not isinstance(m, nn.Linear) or is_patched(m):
                 continue
             w = m.weight
             if not isinstance(w, DTensor) and not isinstance(getattr(w, "data", None), DTensor):
@@ -23,14 +42,5 @@ class RowParallelLinear:
             if not any(p.is_shard(1) for p in pl):
                 continue
 
-            def forward(x, _m=m, _out=output_placements):
-                y = torch.matmul(x, _m.weight.t())
-                if _out is not None:
-                    y = y.redistribute(y.device_mesh, _out)
-                elif isinstance(y, DTensor) and any(p.is_partial() for p in y.placements):
-                    from ...placement import Replicate
-
-                    y = y.redistribute(y.device_mesh, [Replicate() if p.is_partial() else p for p in y.placements])
-                return y + _m.bias if _m.bias is not None else y
-
-            m.forward = forward
+            m.forward = make_new_row_parallel_linear_forward(m, output_placements)
+            set_patched(m)

@@ -265,3 +265,20 @@ def _gloo_a2a_counts(recv, send, group):
 
     outs = list(recv.unbind(0))
     _p2p_all_to_all(outs, list(send.unbind(0)), group)
+
+
+def global_all_to_all_single(tensor: torch.Tensor, input_split_sizes: Optional[List[int]] = None, output_split_sizes: Optional[List[int]] = None, async_op: bool = False, group=None) -> torch.Tensor:
+    """Differentiable ``all_to_all_single`` along dim 0 (legacy ``moe/_utils.py:26-67``): even split when no sizes are given.  The
+    gradient is the all-to-all with the split lists swapped."""
+    n = dist.get_world_size(group) if dist.is_initialized() else 1
+    if input_split_sizes is None:
+        if tensor.shape[0] % n:
+            raise ValueError(f"an even all-to-all needs dim 0 ({tensor.shape[0]}) divisible by the group size ({n})")
+        input_split_sizes = [tensor.shape[0] // n] * n
+    if output_split_sizes is None:
+        output_split_sizes = list(input_split_sizes)
+    return _AllToAll.apply(tensor, list(input_split_sizes), list(output_split_sizes), group)
+
+
+_AllToAllSingle = _AllToAll  # the reference's name for the autograd function
+__all__ += ["global_all_to_all_single"]
