@@ -412,9 +412,10 @@ def _dmp_pinned(rank, world):
     except NotImplementedError:
         pass
     p, f, pin_p, pin_f, pol_p, pol_f = PlanGenerator(model, "megatron").generate()
-    assert any(k.startswith("b") for k in pol_p) and not any(k.startswith(r"b\.") and v != [Replicate()] for k, v in p.items())
-    assert p[r"a\.up\.weight"] == [Shard(0)] and p[r"a\.down\.weight"] == [Shard(1)] and p[r"b\..*"] == [Replicate()]
-    assert f[r"a\.input"] == [[Replicate()]] and f[r"b\.output"] == [[Replicate()]] and r"b\.input" in pin_f
+    assert any(k.startswith("b") for k in pol_p) and not any(k.startswith("b.") and v != [Replicate()] for k, v in p.items())
+    assert p["a.up.weight"] == [Shard(0)] and p["a.down.weight"] == [Shard(1)] and p["b..*"] == [Replicate()]
+    assert f["a.input"] == [[Replicate()]] and f["b.output"] == [[Replicate()]] and "b.input" in pin_f
+    assert auto_parallelize_module(copy.deepcopy(ref), None, "MEGATRON", plan_only=True)[2]["parameter"]["a.up.weight"] == [Shard(0)]
     saved = {}
     auto_parallelize_module(model, mesh, "MEGATRON", plan_to_save=saved)
     assert saved["param_sharding_plan"] == p

@@ -51,7 +51,10 @@ class EinsumDims:
         return cls(contracting, batch, lhs_only, rhs_only)
 
 
-def gen_einsum_strategies(equation: str, mesh, *, linearity: bool = False) -> OpStrategy:
+def gen_einsum_strategies(equation: str, mesh, mat1: "OpStrategy" = None, mat2: "OpStrategy" = None, *, linearity: bool = False) -> OpStrategy:
+    """Without operands: every strategy of the einsum over ``mesh``.  With the operands' current strategies (``mat1`` / ``mat2``, one
+    placement strategy each): the ONE strategy that keeps those placements — per mesh dim the admissible choice whose operand
+    placements are exactly the current ones (all-replicate where none matches, i.e. the operands would have to be gathered)."""
     ins, out = EinsumDims.parse_equation(equation)
     dims = EinsumDims.parse_dims(ins, out)
 
@@ -69,6 +72,19 @@ def gen_einsum_strategies(equation: str, mesh, *, linearity: bool = False) -> Op
             per_mesh_dim.append(place(ch))
     if linearity:
         per_mesh_dim.append([Partial("sum")] * (len(ins) + 1))
+    current = [m for m in (mat1, mat2) if m is not None]
+    if current:
+        if len(current) != len(ins):
+            raise ValueError(f"{equation!r} has {len(ins)} operands, {len(current)} strategies were given")
+        cur_specs = [m.strategies[0].output_spec for m in current]
+        combo = []
+        for md in range(mesh.ndim):
+            have = [s.placements[md] if md < len(s.placements) else None for s in cur_specs]  # a spec may say nothing about a mesh dim
+            combo.append(next((row for row in per_mesh_dim if all(h is None or h == w for h, w in zip(have, row[1:]))), per_mesh_dim[0]))
+        cols = list(zip(*combo))
+        out_spec = DTensorSpec(mesh, tuple(cols[0]))
+        in_specs = [DTensorSpec(mesh, tuple(c[: len(s.placements)])) for c, s in zip(cols[1:], cur_specs)]
+        return OpStrategy([PlacementStrategy(output_spec=out_spec, input_specs=in_specs)])
     strategies = []
     for combo in itertools.product(per_mesh_dim, repeat=mesh.ndim):
         cols = list(zip(*combo))  # cols[0]: output placements over mesh dims, cols[1:]: operands

@@ -48,7 +48,13 @@ def get_plan_overriding_policy(module: nn.Module) -> Tuple[Optional[Dict], Optio
 
 
 def _prefix(fqn: str, key: str) -> str:
-    return key if not fqn else re.escape(fqn) + r"\." + key
+    """Root-relative plan key.  Keys are regular expressions matched against fully qualified names; module paths are written with
+    plain dots (``blocks.0.fc1.weight`` — a dot matches a dot), which keeps generated plans readable and comparable."""
+    return key if not fqn else fqn + "." + key
+
+
+def _plain(key: str) -> str:
+    return key.replace(r"\.", ".")
 
 
 class PlanGenerator:
@@ -89,8 +95,8 @@ class PlanGenerator:
                 continue
             if _DEBUG:
                 print(f"[dmp] {fqn or '<root>'} : {type(sub).__name__} --{self.policy}--> {r}")
-            root_p.update(r.get("parameter", {}))
-            root_f.update(r.get("forward", {}))
+            root_p.update({_plain(k): v for k, v in r.get("parameter", {}).items()})
+            root_f.update({_plain(k): v for k, v in r.get("forward", {}).items()})
         return root_p, root_f
 
     @staticmethod
@@ -98,7 +104,7 @@ class PlanGenerator:
         """``low`` without the entries that live under a claimed subtree, then ``high`` on top."""
         out = copy.copy(low)
         for fqn in claims:
-            pre = re.escape(fqn) + r"\." if fqn else ""
+            pre = fqn + "." if fqn else ""
             for k in [k for k in out if k.startswith(pre)]:
                 del out[k]
         out.update(high)
@@ -117,14 +123,19 @@ def generate_plan(module: nn.Module, policy: str = "MEGATRON") -> Dict[str, Dict
     return {"parameter": p, "forward": f}
 
 
-def auto_parallelize_module(module: nn.Module, device_mesh, policy: str = "MEGATRON", *, plan_override: Optional[Dict[str, Dict]] = None, plan_to_save: Optional[Dict] = None, **kw) -> nn.Module:
-    """``plan_override``: extra root-relative entries laid over the generated plan (a one-call alternative to pinning).
-    ``plan_to_save``: a dict that receives the final plans under ``"param_sharding_plan"`` / ``"fwd_resharding_plan"``."""
+def auto_parallelize_module(module: nn.Module, device_mesh=None, policy: str = "MEGATRON", plan_only: bool = False, *, plan_override: Optional[Dict[str, Dict]] = None,
+                            plan_to_save: Optional[Dict] = None, **kw):
+    """``device_mesh=None``: the mesh of the enclosing ``with DeviceMesh(...):`` block.  ``plan_only``: generate, do not parallelize —
+    returns ``(module, device_mesh, {"parameter": ..., "forward": ...})``.  ``plan_override``: extra root-relative entries laid over
+    the generated plan (a one-call alternative to pinning).  ``plan_to_save``: a dict that receives the final plans under
+    ``"param_sharding_plan"`` / ``"fwd_resharding_plan"``."""
     plan = generate_plan(module, policy)
     if plan_override:
         plan["parameter"].update(plan_override.get("parameter", {}))
         plan["forward"].update(plan_override.get("forward", {}))
     if plan_to_save is not None:
         plan_to_save["param_sharding_plan"], plan_to_save["fwd_resharding_plan"] = dict(plan["parameter"]), dict(plan["forward"])
+    if plan_only:
+        return module, device_mesh, plan
     module._auto_plan = plan
     return parallelize_module(module, device_mesh, plan, **kw)
