@@ -97,6 +97,7 @@ class GlobalReferenceTime:
 
     initialized = False
     cuda = False
+    device = 0
     ref_event = None
     ref_host_us = 0.0
     ref_perf = 0.0
@@ -119,6 +120,7 @@ class GlobalReferenceTime:
                 dist.all_gather(ts, t, group=group)
                 cls.clock_offset_us = (int(t.item()) - min(int(x.item()) for x in ts)) / 1e3  # my lead over the earliest rank at the barrier
             if cls.cuda:
+                cls.device = torch.cuda.current_device()  # flush threads start on device 0: calibrate() must come back here
                 cls.ref_event = torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 cls.ref_event.record()
@@ -144,15 +146,19 @@ class GlobalReferenceTime:
         if not cls.initialized or not cls.cuda or now - cls.last_calibrated < min_interval_s:
             return cls.drift
         with cls._lock:
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
-            e.synchronize()
-            host_us = (time.perf_counter() - cls.ref_perf) * 1e6
-            gpu_us = cls.ref_event.elapsed_time(e) * 1e3
-            if gpu_us > 1e5:
-                ratio = host_us / gpu_us
-                if 0.99 < ratio < 1.01:  # anything else is a measurement glitch (a stalled host thread), not clock drift
-                    cls.drift = ratio
+            try:
+                with torch.cuda.device(cls.device):  # the reference event lives on this device; elapsed_time cannot cross devices
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    e.synchronize()
+                    host_us = (time.perf_counter() - cls.ref_perf) * 1e6
+                    gpu_us = cls.ref_event.elapsed_time(e) * 1e3
+                if gpu_us > 1e5:
+                    ratio = host_us / gpu_us
+                    if 0.99 < ratio < 1.01:  # anything else is a measurement glitch (a stalled host thread), not clock drift
+                        cls.drift = ratio
+            except RuntimeError:  # calibration is best effort: a failed attempt keeps the previous coefficient
+                pass
             cls.last_calibrated = now
         return cls.drift
 
