@@ -383,3 +383,37 @@ def test_user_written_programs_and_compile_operators():
     assert [p.peer_stage for p in f0.get_send_comms(4)] == [1] and f0.get_recv_comms(4) == []
     assert cg.get_v_schedule(only_run_time=True) <= cg.try_v_schedule(fill_f=False)[1] + 1e-9
     assert "stage 3" in cg.print_details()
+
+
+def test_diff_switches_dummy_p2p_and_instruction_dump(tmp_path, monkeypatch):
+    from vescale_b200.dtensor._diff import DeferReshardMode, dummy_p2p, get_counter, set_counter
+    from vescale_b200.parallel.pipe._schedules import OneFOneBInstrcutionGenerator, StageDeps
+
+    monkeypatch.chdir(tmp_path)
+
+    @dummy_p2p
+    def recv_forward(tensor_shape=None, recv_dtype=None):
+        raise AssertionError("must not communicate in a dry run")
+
+    @dummy_p2p
+    def send_forward(t):
+        return "sent"
+
+    assert send_forward(torch.ones(2)) == "sent"  # flag off: the function itself
+    monkeypatch.setenv("VESCALE_DUMMY_P2P", "1")
+    monkeypatch.setenv("STAGE_ID", "3")
+    set_counter(0)
+    x = recv_forward(tensor_shape=(2, 3), recv_dtype=torch.bfloat16)
+    assert x.shape == (2, 3) and x.dtype == torch.bfloat16 and send_forward(torch.ones(4, 5)) is None and get_counter() == 2
+    log = open(tmp_path / "dummy_p2p_rank3.txt").read().splitlines()
+    assert log[0].startswith("0: recv_forward") and "(4, 5)" in log[1]
+    # instruction dump: what a stage is about to execute is on disk before it runs (here the run itself fails: no module given)
+    monkeypatch.setenv("VESCALE_DUMP_INSTRUCTION", "1")
+    gen = OneFOneBInstrcutionGenerator(StageDeps(4), [None] * 4, 4)
+    with pytest.raises(ValueError, match="PipeModule"):
+        gen.execute(1)
+    text = open(tmp_path / "instruction_dump_stage1.txt").read()
+    assert "SEND_FORWARD_RECV_BACKWARD" in text and "[rank 1]" in text
+    with DeferReshardMode(False):
+        assert not DeferReshardMode.is_enabled()
+    assert DeferReshardMode.is_enabled()

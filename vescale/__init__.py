@@ -53,6 +53,9 @@ _ALIASES = {
     "vescale.dtensor.op_schema": "vescale_b200.dtensor.op_schema",
     "vescale.dtensor._op_schema": "vescale_b200.dtensor.op_schema",
     "vescale.dtensor._dispatch": "vescale_b200.dtensor.dispatch",
+    "vescale.dtensor._diff": "vescale_b200.dtensor._diff",
+    "vescale.dtensor._dispatch_bypass": "vescale_b200.dtensor.handlers",
+    "vescale.dtensor._dispatch_patch": "vescale_b200.dtensor.dispatch",
     "vescale.dtensor._sharding_prop": "vescale_b200.dtensor.sharding_prop",
     "vescale.dtensor._redistribute": "vescale_b200.dtensor.redistribute",
     # rule-author API: registration contracts, einop / einsum building blocks, predicates (real modules); the per-family rule files

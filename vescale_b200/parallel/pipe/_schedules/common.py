@@ -11,6 +11,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from ....dtensor._diff import manage_dump_file
 from ....profiler import ndtimeit, predefined
 from ..instruction_base import BaseInstruction, CommPacket, InstructionBuilder, InstructionVM
 from ..plan import PipelineParallelPlan, PipelineScheduleType
@@ -217,6 +218,7 @@ class ProgramGenerator:
         ranks = [rank] if rank is not None else range(self.num_stages)
         return "\n".join(f"[rank {r}] {k:3d}: {ins.dump()}" for r in ranks for k, ins in enumerate(self.instruction_list[r]))
 
+    @manage_dump_file
     def execute(self, stage_id: int, module=None, inputs: Sequence = (), labels: Optional[Sequence] = None, *, pp_group=None, loss_fn: Optional[Callable] = None, device=None,
                 pp_ranks: Optional[Sequence[int]] = None, forward_only: Optional[bool] = None, vm: Optional[InstructionVM] = None):
         """Run stage ``stage_id``'s program on its ``PipeModule`` (legacy ``InstructionGenerator.execute``): returns ``(loss, outputs)``
