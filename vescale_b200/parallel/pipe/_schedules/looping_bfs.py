@@ -48,7 +48,9 @@ Msg = Optional[Tuple[int, int, int]]  # (micro-batch, virtual stage, peer rank) 
 class InterleavedPipeDreramFlush(PipelineSchema):  # (sic) the reference's spelling
     """Clock table of the interleaved schedule.  ``warmup_batches[r]``: forwards rank ``r`` runs before its first backward."""
 
-    def __init__(self, plan_or_stages, num_microbatches: int, knobs=None, *, num_chunks: int = 2):
+    def __init__(self, plan_or_stages, num_microbatches, knobs=None, *, num_chunks: int = 2):
+        if isinstance(num_microbatches, (list, tuple)):  # the reference's form: InterleavedPipeDreramFlush(num_chunks, meshes, batches)
+            num_chunks, plan_or_stages, num_microbatches, knobs = int(plan_or_stages), len(num_microbatches), knobs, None
         plan = plan_or_stages if isinstance(plan_or_stages, PipelineParallelPlan) else PipelineParallelPlan(num_stages=int(plan_or_stages), virtual_chunks=num_chunks, schedule_type=PipelineScheduleType.INTERLEAVED_1F1B)
         P, V, M = plan.num_stages, plan.virtual_chunks, int(num_microbatches)
         self.warmup_batches = [min(M * V, 2 * (P - r - 1) + (V - 1) * P) for r in range(P)]

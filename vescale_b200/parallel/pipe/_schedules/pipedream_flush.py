@@ -53,7 +53,9 @@ class PipeDream(PipelineSchema):
     """The 1F1B clock table.  ``warmup_batches[s]`` / ``remain_batches[s]`` are the phase lengths of stage ``s``; with forward cost f and backward cost b
     the table spans ``(f + b) (M + P - 1)`` — the flush-bounded optimum for a schedule that holds at most ``P - s`` activations."""
 
-    def __init__(self, plan_or_stages, num_microbatches: int, knobs=None, *, forward_only: bool = False):
+    def __init__(self, plan_or_stages, num_microbatches, knobs=None, *, forward_only: bool = False):
+        if isinstance(num_microbatches, (list, tuple)):  # the reference's form: PipeDream(num_chunks, meshes, batches)
+            plan_or_stages, num_microbatches, knobs = len(num_microbatches), knobs, None
         plan = plan_or_stages if isinstance(plan_or_stages, PipelineParallelPlan) else PipelineParallelPlan(num_stages=int(plan_or_stages), schedule_type=PipelineScheduleType.SIMPLE_1F1B, forward_only=forward_only)
         if plan.virtual_chunks != 1:
             raise ValueError("1F1B runs one model chunk per stage; use the interleaved schedule for more")
