@@ -283,39 +283,14 @@ class DModule:
         return out
 
     def finish_grad_sync(self, bucket_bytes: int = 40 * 2**20) -> int:
-        """All-reduce every ``Partial`` gradient on its mesh dims, flattened into buckets per (mesh dim, dtype)
-        (legacy ``_grad_sync.py:60-126``: 40 MB flat buckets).  Returns the number of collectives issued."""
-        groups: Dict[Tuple[int, torch.dtype, str], List[Tuple[nn.Parameter, torch.Tensor]]] = {}
-        for p in self.partial_grad_params():
-            g: DTensor = p.grad
-            for i, pl in enumerate(g.placements):
-                if pl.is_partial():
-                    groups.setdefault((i, g.dtype, pl.reduce_op), []).append((p, g._local_tensor))
-        n_coll = 0
-        for (md, dtype, op), items in groups.items():
-            bucket, size = [], 0
-            def flush():
-                nonlocal n_coll, bucket, size
-                if not bucket:
-                    return
-                flat = torch.cat([t.reshape(-1) for _, t in bucket])
-                red = C.mesh_all_reduce(flat, self.mesh, op, md, inplace=True)
-                off = 0
-                for _, t in bucket:
-                    t.copy_(red[off : off + t.numel()].view_as(t))
-                    off += t.numel()
-                n_coll += 1
-                bucket, size = [], 0
-            for p, t in items:
-                bucket.append((p, t))
-                size += t.numel() * t.element_size()
-                if size >= bucket_bytes:
-                    flush()
-            flush()
-            for p, _ in items:
-                g = p.grad
-                pl = tuple(Replicate() if (i == md and q.is_partial()) else q for i, q in enumerate(g.placements))
-                p.grad = DTensor(g._local_tensor, g._spec.with_placements(pl))
+        """All-reduce every ``Partial`` gradient on its mesh dims, flattened into buckets per (mesh dim, dtype, reduce op)
+        (``_grad_sync.sync_gradients``; legacy ``_grad_sync.py:60-126``: 40 MB flat buckets).  Returns the number of collectives issued."""
+        from ._grad_sync import sync_gradients
+
+        params = list(self.partial_grad_params())
+        reduced, n_coll = sync_gradients([p.grad for p in params], self.mesh, bucket_bytes)
+        for p, g in zip(params, reduced):
+            p.grad = g
         return n_coll
 
 
