@@ -45,16 +45,7 @@ def nccl_chunking(count: int, nranks: int, nchannels: int = 1, chunk_elems: Opti
     return out
 
 
-def _op(a: torch.Tensor, b: torch.Tensor, op: str) -> torch.Tensor:
-    if op == "sum":
-        return a + b
-    if op == "max":
-        return torch.maximum(a, b)
-    if op == "min":
-        return torch.minimum(a, b)
-    if op == "product":
-        return a * b
-    raise ValueError(op)
+from .reduce_kernel import reduce_pair as _op  # noqa: E402  (one reduction kernel for the whole emulator)
 
 
 def ring_all_reduce(inputs: Sequence[torch.Tensor], op: str = "sum", ring: Optional[Sequence[int]] = None, nchannels: int = 1, chunk_elems: Optional[int] = None) -> List[torch.Tensor]:

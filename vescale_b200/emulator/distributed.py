@@ -25,17 +25,7 @@ __all__ = [
 ]
 
 
-class ReduceOp:
-    """Reduction selector (legacy ``emulator/reduce_kernel.py``)."""
-
-    SUM, PRODUCT, MAX, MIN, AVG = "sum", "product", "max", "min", "avg"
-
-
-def _op_name(op) -> str:
-    if isinstance(op, str):
-        return op.lower()
-    name = getattr(op, "name", None) or str(op)  # torch.distributed.ReduceOp members
-    return {"SUM": "sum", "PRODUCT": "product", "MAX": "max", "MIN": "min", "AVG": "avg"}.get(name.split(".")[-1].upper(), "sum")
+from .reduce_kernel import ReduceOp, op_name as _op_name  # noqa: E402
 
 
 class _World:

@@ -20,24 +20,7 @@ from .topo import BinaryTree
 __all__ = ["Traffic", "RingPrimitive", "TreePrimitive", "Point2PointPrimitive", "reduce_sources"]
 
 
-def _bin(a: torch.Tensor, b: torch.Tensor, op: str) -> torch.Tensor:
-    if op in ("sum", "avg"):
-        return a + b
-    if op == "max":
-        return torch.maximum(a, b)
-    if op == "min":
-        return torch.minimum(a, b)
-    if op == "product":
-        return a * b
-    raise ValueError(op)
-
-
-def reduce_sources(srcs: Sequence[torch.Tensor], op: str) -> torch.Tensor:
-    """Left-to-right accumulation over the sources of one primitive call."""
-    acc = srcs[0].clone()
-    for s in srcs[1:]:
-        acc = _bin(acc, s, op)
-    return acc
+from .reduce_kernel import reduce_pair as _bin, reduce_sources  # noqa: E402  (one reduction kernel for the whole emulator)
 
 
 @dataclass
