@@ -6,6 +6,8 @@
 # Round-1 result on CPU (gloo): dtensor/general/test_api 5/5, test_equal 2/2 (+1 skip), test_utils 5/5, test_defer_resharding 2/2,
 # dtensor/loss 1/1, ndtimeline parser 2/2 + local_raw 1/1 + metric_level 1/1, emulator/test_topo 1/1, dmodule/test_plans 2/2 (+3 skip),
 # test_fwd_plan 23/23, test_obj_return 3/3, test_dfactory 6/6.  NCCL-only by construction (bitwise comparison with a real NCCL
+# Round 2 adds: dtensor/ops/test_common_rules 11/11, test_basic_strategy 10/10 (the rule-author API), parallel/pipeline/instruction/
+# test_zerobubble 1/1, test_pipe_instruction_register 2/2, parallel/dmp/test_dmp TestSetPlan 3/3 (+7 GPU-only skipped).
 # communicator / CUDA memory counters): emulator/test_distributed, test_mesh_collectives, test_dtensor, initialize/test_defer_init.
 set -uo pipefail
 REPO="$(cd "$(dirname "$0")/.." && pwd)"
@@ -27,7 +29,8 @@ if [ ${#FILES[@]} -eq 0 ]; then
   FILES=(dtensor/general/test_api.py dtensor/general/test_equal.py dtensor/general/test_utils.py dtensor/general/test_defer_resharding.py
          dtensor/loss/test_loss.py ndtimeline/test_parser_handler.py ndtimeline/test_local_raw_handler.py ndtimeline/test_metric_level.py
          emulator/test_topo.py dmodule/test_plans.py dmodule/test_fwd_plan.py dmodule/test_obj_return.py dmodule/test_dfactory.py
-         parallel/devicemesh_api/test_api.py)
+         parallel/devicemesh_api/test_api.py dtensor/ops/test_common_rules.py dtensor/ops/test_basic_strategy.py
+         parallel/pipeline/instruction/test_zerobubble.py parallel/pipeline/instruction/test_pipe_instruction_register.py parallel/dmp/test_dmp.py)
 fi
 for f in "${FILES[@]}"; do
   echo "== $f"
