@@ -65,7 +65,7 @@ _ALIASES = {
     "vescale.dtensor.ops.matrix_ops": "vescale_b200.dtensor.rules.matrix",
     "vescale.dtensor.ops.pointwise_ops": "vescale_b200.dtensor.rules.pointwise",
     "vescale.dtensor.ops.tensor_ops": "vescale_b200.dtensor.rules.tensor",
-    "vescale.dtensor.ops.view_ops": "vescale_b200.dtensor.rules.view",
+    "vescale.dtensor.ops.view_ops": "vescale_b200.dtensor.rules.dim_maps",
     "vescale.dtensor.ops.vescale_view_ops": "vescale_b200.dtensor.rules.view",
     "vescale.dtensor.ops.conv_ops": "vescale_b200.dtensor.rules.conv",
     "vescale.dtensor.ops.embedding_ops": "vescale_b200.dtensor.rules.tensor",
