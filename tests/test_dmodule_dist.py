@@ -433,3 +433,71 @@ def _dmp_pinned(rank, world):
 
 def test_dmp_pinned_plans_and_class_level_providers():
     run_distributed(_dmp_pinned, 2)
+
+
+def _w_weight_forward_plan(rank, world):
+    """A forward plan on a PARAMETER: fc1 is stored column-sharded (ZeRO-3 style), computes with a replicated weight, and the
+    gradient comes back in the parameter's own layout; ``grad=`` re-labels the gradient (legacy ``_hook.py:178-273``)."""
+    from vescale_b200 import Replicate, Shard, init_device_mesh
+    from vescale_b200.dtensor.api import DTensor
+    from vescale_b200.parallel.dmodule import parallelize_module
+    from vescale_b200.parallel.dmodule.api import PlacementsInterface as PI
+    from vescale_b200.parallel.dmodule._hook import PostHookGrad, get_sig
+
+    torch.manual_seed(0)
+    mesh = init_device_mesh(device_type(), (world,))
+    golden = Block().to(device_type())
+    model = copy.deepcopy(golden)
+    plan = {
+        "parameter": {r"fc1\.weight": [Shard(0)], r"fc1\.bias": [Shard(0)]},
+        "forward": {
+            r"fc1\.weight": [Replicate()],
+            r"fc1\.bias": PI([Replicate()]),
+            r"input": [[Replicate()]],
+            r"output": [[Replicate()]],
+        },
+    }
+    model = parallelize_module(model, mesh, plan)
+    w = model.fc1.weight
+    assert isinstance(w, nn.Parameter) and w.placements == (Shard(0),)
+    x = torch.randn(4, 8, 32, device=device_type())
+    seen = {}
+    model.fc1.register_forward_pre_hook(lambda m, a: seen.update(in_fwd=(m.weight.placements, m.bias.placements)))
+    out = model(x)
+    assert seen["in_fwd"] == ((Replicate(),), (Replicate(),))
+    assert model.fc1.weight is w and model.fc1._parameters["weight"] is w  # the parameter is back in its slot
+    ref = golden(x)
+    assert torch.allclose(out.to_local(), ref, atol=1e-5)
+    out.to_local().sum().backward()
+    ref.sum().backward()
+    assert w.grad.placements == (Shard(0),)
+    assert torch.allclose(w.grad.full_tensor(), golden.fc1.weight.grad, atol=1e-5)
+    assert torch.allclose(model.fc1.bias.grad.full_tensor(), golden.fc1.bias.grad, atol=1e-5)
+    # a second step goes through the same hooks
+    out2 = model(x)
+    assert torch.allclose(out2.to_local(), ref, atol=1e-5) and model.fc1._parameters["weight"] is w
+    # grad re-labelling
+    from vescale_b200 import Partial
+
+    g = DTensor.from_local(torch.ones(4, 4), mesh, [Partial()])
+    relabelled = PostHookGrad.get_hook(mesh, [Replicate()])(g)
+    assert relabelled.placements == (Replicate(),) and relabelled.to_local().data_ptr() == g.to_local().data_ptr()
+    try:
+        PostHookGrad.get_hook(mesh, [Shard(0)])(g)  # would claim a (4, 4) local piece of a (4, 4) tensor split two ways
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass
+    assert list(get_sig(model).parameters) == ["x"]
+
+    # through a plan: fc2's weight gradient is declared Replicate although the matmul with a sharded activation leaves it Partial
+    m2 = copy.deepcopy(golden)
+    m2 = parallelize_module(
+        m2, mesh, {"parameter": {}, "forward": {r"fc2\.weight": PI(None, grad=[Replicate()]), r"input": [[Shard(0)]], r"output": [[Shard(0)]]}}
+    )
+    m2(x).to_local().sum().backward()
+    assert m2.fc2.weight.grad.placements == (Replicate(),)
+    assert any(p.is_partial() for p in m2.fc1.weight.grad.placements)  # the un-planned sibling keeps what autograd produced
+
+
+def test_weight_forward_plan_and_grad_placements():
+    run_distributed(_w_weight_forward_plan, 2)

@@ -85,7 +85,7 @@ _ALIASES = {
     "vescale.dtensor.vescale_utils.checkpoint": "vescale_b200.dtensor.vescale_utils.checkpoint",
     "vescale.dmodule._dmodule": "vescale_b200.parallel.dmodule.api",
     "vescale.dmodule._grad_sync": "vescale_b200.parallel.dmodule._grad_sync",
-    "vescale.dmodule._hook": "vescale_b200.parallel.dmodule.api",
+    "vescale.dmodule._hook": "vescale_b200.parallel.dmodule._hook",
     "vescale.dmodule.placements_interface": "vescale_b200.parallel.dmodule.api",
     "vescale.ddp.grad_buffer": "vescale_b200.parallel.ddp",
     "vescale.dmp.policies": "vescale_b200.parallel.dmp.policies",

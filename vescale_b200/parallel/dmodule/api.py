@@ -39,60 +39,11 @@ from ...comm import collectives as C
 from ...dtensor.api import DTensor, distribute_tensor
 from ...mesh import DeviceMesh
 from ...placement import Partial, Placement, Replicate, Shard, normalize_placements
+from ._hook import (  # noqa: F401
+    PlacementsInterface, PostHookGrad, PostHookOutput, PostHookWeight, PreHookInput, PreHookWeight, _as_pi_list, _convert, _convert_nested,
+)
 
 __all__ = ["parallelize_module", "is_dmodule", "PlacementsInterface", "DModule"]
-
-
-@dataclass
-class PlacementsInterface:
-    placements: Optional[Sequence[Placement]]
-    async_op: bool = True
-    defer_reshard: bool = False
-    run_check: bool = False
-    support_uneven: bool = True
-    grad: Optional[Sequence[Placement]] = None
-
-    @classmethod
-    def from_placements(cls, p) -> "PlacementsInterface":
-        if isinstance(p, cls):
-            return p
-        return cls(None if p is None else list(p))
-
-
-def _as_pi_list(entry) -> List[Optional[PlacementsInterface]]:
-    if entry is None:
-        return []
-    if isinstance(entry, PlacementsInterface) or (entry and isinstance(entry[0], Placement)):
-        entry = [entry]
-    return [None if e is None else PlacementsInterface.from_placements(e) for e in entry]
-
-
-def _convert(x, pi: Optional[PlacementsInterface], mesh: DeviceMesh, allow_defer: bool = False):
-    if pi is None or pi.placements is None or not isinstance(x, torch.Tensor):
-        return x
-    pl = normalize_placements(pi.placements, mesh.ndim, x.ndim)
-    if isinstance(x, DTensor):
-        if x.placements == pl:
-            return x
-        if allow_defer and pi.defer_reshard:
-            x._deferred_placements = tuple(pl)  # the sum / difference this output enters pays the reshard (dispatch.py)
-            return x
-        return x.redistribute(mesh, pl, async_op=pi.async_op)
-    return DTensor.from_local(x, mesh, pl, run_check=pi.run_check)
-
-
-def _convert_nested(x, spec, mesh: DeviceMesh):
-    """``spec`` mirrors the structure of ``x``: a placement list / ``PlacementsInterface`` for a tensor, a dict for a dict
-    argument, a list of placement lists for a list / tuple argument."""
-    if spec is None:
-        return x
-    if isinstance(spec, dict):
-        if not isinstance(x, dict):
-            return x
-        return type(x)({k: _convert_nested(v, spec[k], mesh) if k in spec else v for k, v in x.items()})
-    if isinstance(spec, (list, tuple)) and spec and not isinstance(spec[0], Placement) and isinstance(x, (list, tuple)):
-        return type(x)(_convert_nested(v, spec[i] if i < len(spec) else None, mesh) for i, v in enumerate(x))
-    return _convert(x, PlacementsInterface.from_placements(spec), mesh)
 
 
 class DModule:
@@ -160,62 +111,43 @@ class DModule:
                     if not mod_rx.fullmatch(fqn):
                         continue
                     if kind == "input":
-                        self.handles.append(mod.register_forward_pre_hook(self._make_pre(entry, mesh), with_kwargs=True))
+                        self.handles.append(mod.register_forward_pre_hook(PreHookInput.get_hook(mesh, entry), with_kwargs=True))
                     else:
                         hint = self._reshard_hint(entry, mesh)
                         if hint is not None:
                             # the output plan reshards this module's result: a row-parallel matmul inside may produce the target
                             # layout directly (GEMM ⊕ reduce-scatter, dtensor/fusion.py) instead of Partial + reduce-scatter
-                            self.handles.append(mod.register_forward_pre_hook(self._make_hint_push(hint, mesh)))
-                        self.handles.append(mod.register_forward_hook(self._make_post(entry, mesh, pop_hint=hint is not None)))
+                            self.handles.append(mod.register_forward_pre_hook(PostHookOutput.get_hint_push(mesh, hint)))
+                        self.handles.append(mod.register_forward_hook(PostHookOutput.get_hook(mesh, entry, pop_hint=hint is not None)))
+        self._init_weight_plans(names)
 
-    @staticmethod
-    def _make_pre(entry, mesh):
-        """Input hook.  The call is bound to ``forward``'s signature first (so a wrong call raises ``TypeError`` before any
-        conversion and defaults are visible), then a sequence plan is laid over the bound arguments in order — positional
-        ones, then keyword ones — and a dict plan is matched by parameter name (a ``*args`` parameter takes a list of
-        placements, a ``**kwargs`` parameter is looked through, container arguments take a nested dict / list).  A plan
-        naming more arguments than the call has warns and the surplus is ignored (legacy ``dmodule/_hook.py:96-170``)."""
-        is_dict = isinstance(entry, dict)
-        pis = None if is_dict else _as_pi_list(entry)
-
-        def pre(mod, args, kwargs):
-            sig = inspect.signature(mod.forward)
-            bound = sig.bind(*args, **kwargs)
-            bound.apply_defaults()
-            if not is_dict:
-                pos, kw = bound.args, bound.kwargs
-                n = len(pos) + len(kw)
-                if len(pis) > n:
-                    warnings.warn(f"forward plan lists {len(pis)} placements but the call has {n} arguments; the rest are ignored")
-                full = list(pis[:n]) + [None] * (n - len(pis))
-                return (
-                    tuple(_convert(x, pi, mesh) for x, pi in zip(pos, full)),
-                    {k: _convert(v, pi, mesh) for (k, v), pi in zip(kw.items(), full[len(pos):])},
-                )
-            var_pos = next((q.name for q in sig.parameters.values() if q.kind is q.VAR_POSITIONAL), None)
-            var_kw = next((q.name for q in sig.parameters.values() if q.kind is q.VAR_KEYWORD), None)
-            known = set(bound.arguments) - {var_kw}
-            if var_kw is not None:
-                known |= set(bound.arguments.get(var_kw, {}))
-            unknown = set(entry) - known
-            if unknown:
-                warnings.warn(f"forward plan names arguments the call does not have: {sorted(map(str, unknown))}")
-            for name, val in list(bound.arguments.items()):
-                if name == var_kw:
-                    bound.arguments[name] = {k: _convert_nested(v, entry[k], mesh) if k in entry else v for k, v in val.items()}
-                elif name not in entry:
-                    continue
-                elif name == var_pos:
-                    sub = _as_pi_list(entry[name])
-                    if len(sub) > len(val):
-                        warnings.warn(f"forward plan lists {len(sub)} placements for *{name} but {len(val)} were passed; the rest are ignored")
-                    bound.arguments[name] = tuple(_convert(v, sub[i] if i < len(sub) else None, mesh) for i, v in enumerate(val))
-                else:
-                    bound.arguments[name] = _convert_nested(val, entry[name], mesh)
-            return bound.args, bound.kwargs
-
-        return pre
+    def _init_weight_plans(self, names: Dict[str, nn.Module]) -> None:
+        """Forward-plan keys that name a PARAMETER (``r"fc1\\.weight": [Replicate()]`` or ``PlacementsInterface(..., grad=[...])``;
+        legacy ``_dmodule.py:330-348``): the owning module computes with the parameter in that layout (``PreHookWeight`` /
+        ``PostHookWeight`` swap a differentiable redistributed view in and out), and ``grad=`` re-labels the gradient that
+        reaches the parameter (``PostHookGrad``)."""
+        mesh = self.mesh
+        per_module: Dict[str, Dict[str, PlacementsInterface]] = {}
+        for rx, entry in self.fwd_plan.items():
+            pat = rx.pattern
+            if pat in ("input", "output") or pat.endswith((".input", ".output")):
+                continue
+            for mod_name, mod in names.items():
+                for pname, p in mod._parameters.items():
+                    if p is None:
+                        continue
+                    fqn = f"{mod_name}.{pname}" if mod_name else pname
+                    if rx.fullmatch(fqn):
+                        pi = entry if isinstance(entry, PlacementsInterface) else PlacementsInterface.from_placements(entry)
+                        per_module.setdefault(mod_name, {})[pname] = pi
+        for mod_name, pis in per_module.items():
+            mod = names[mod_name]
+            if any(pi.placements for pi in pis.values()):
+                self.handles.append(mod.register_forward_pre_hook(PreHookWeight.get_hook(mesh, pis)))
+                self.handles.append(mod.register_forward_hook(PostHookWeight.get_hook(mesh, pis), always_call=True))
+            for pname, pi in pis.items():
+                if pi.grad:
+                    self.handles.append(mod._parameters[pname].register_hook(PostHookGrad.get_hook(mesh, pi.grad)))
 
     @staticmethod
     def _reshard_hint(entry, mesh):
@@ -227,51 +159,6 @@ class DModule:
             return None
         pl = list(pis[0].placements)
         return pl if any(isinstance(p, Shard) for p in pl) else None
-
-    @staticmethod
-    def _make_hint_push(placements, mesh):
-        from ...dtensor.fusion import push_hint
-
-        def push(mod, args):
-            # a Shard(1) target on a (B, S, H) output is a contiguous row shard of the token matrix only when B == 1
-            batch1 = all(a.shape[0] == 1 for a in args if isinstance(a, torch.Tensor) and a.ndim == 3)
-            push_hint(id(mod), mesh, placements, rows_contiguous=batch1)
-
-        return push
-
-    @staticmethod
-    def _make_post(entry, mesh, pop_hint: bool = False):
-        """Output hook: a sequence plan over a tensor / tuple / list output, a dict plan (by key / field name) over a dict,
-        dict-like (``ModelOutput``) or dataclass output (legacy ``dmodule/_hook.py:213-256``)."""
-        is_dict = isinstance(entry, dict)
-        pis = None if is_dict else _as_pi_list(entry)
-
-        def post(mod, args, output):
-            if pop_hint:
-                from ...dtensor.fusion import pop_hint as _pop
-
-                _pop(id(mod))
-            if is_dict:
-                if dataclasses.is_dataclass(output) and not isinstance(output, type) and not isinstance(output, dict):
-                    vals = {f.name: getattr(output, f.name) for f in dataclasses.fields(output)}
-                    return type(output)(**{k: _convert_nested(v, entry[k], mesh) if k in entry else v for k, v in vals.items()})
-                if isinstance(output, dict):
-                    conv = {k: _convert_nested(v, entry[k], mesh) if k in entry else v for k, v in output.items()}
-                    try:
-                        return type(output)(**conv)
-                    except TypeError:
-                        return type(output)(conv)
-                raise TypeError(f"a dict output plan needs a dict or dataclass output, got {type(output).__name__}")
-            if isinstance(output, (tuple, list)):
-                if len(output) != len(pis):
-                    raise AssertionError(f"output plan has {len(pis)} entries but the module returned {len(output)} values")
-                conv = [_convert(o, pi, mesh, allow_defer=True) for o, pi in zip(output, pis)]
-                return type(output)(*conv) if hasattr(output, "_fields") else type(output)(conv)
-            if isinstance(output, dict) or dataclasses.is_dataclass(output):
-                raise TypeError("a sequence output plan cannot be applied to a dict / dataclass output; key it by name")
-            return _convert(output, pis[0] if pis else None, mesh, allow_defer=True)
-
-        return post
 
     # ------------------------------------------------------------------ gradient sync
     def partial_grad_params(self) -> List[nn.Parameter]:
