@@ -313,3 +313,29 @@ def test_mxfp8_scale_atoms_and_recipe():
     loss.backward()
     ref_loss = LlamaModel(LlamaConfig.tiny()).reset_parameters(seed=1)(tok[:, :-1], tok[:, 1:])
     assert abs(loss.item() - ref_loss.item()) < 0.05 and all(p.grad is not None for p in m.parameters())
+
+
+def test_new_package_dispatch_names_and_bypass_table():
+    """The new package's handler names and the bypass table object resolve to the functions the dispatcher runs
+    (``vescale/dtensor/_dispatch.py``, ``legacy/vescale/dtensor/_dispatch_bypass.py:26``)."""
+    import torch
+
+    from vescale.dtensor._dispatch import found_inf_reduce_handler, fused_adamw_sgd_op_handler, is_contiguous, ragged_norm_op_handler
+    from vescale.dtensor._dispatch_bypass import BypassOpDispatch
+    from vescale.dtensor._dtensor_spec import is_ragged_shard
+    from vescale.dtensor._redistribute import substitute_ragged_spec
+    from vescale_b200 import DTensor, Replicate, init_device_mesh
+    from vescale_b200.dtensor import handlers
+    from vescale_b200.placement import RaggedShard
+    from vescale_b200.spec import DTensorSpec, TensorMeta
+
+    assert ragged_norm_op_handler is handlers.ragged_norm_handler and found_inf_reduce_handler is handlers.found_inf_handler
+    assert fused_adamw_sgd_op_handler is handlers.fused_optimizer_handler
+    mesh = init_device_mesh("cpu", (2,), _rank=0, _init_process_groups=False)
+    sp = DTensorSpec(mesh, (RaggedShard((0,), (1, 3)),), TensorMeta((4, 4), (4, 1), torch.float32))
+    assert is_ragged_shard(sp) and substitute_ragged_spec(sp).placements == (Replicate(),) and is_contiguous(sp)
+    assert not is_contiguous(DTensorSpec(mesh, (Replicate(),), TensorMeta((4, 4), (1, 4), torch.float32)))
+    a = DTensor.from_local(torch.ones(4, 4), mesh, [Replicate()])
+    hit, same = BypassOpDispatch.apply(torch.ops.aten.is_same_size.default, (a, a), {})
+    assert hit and same is True
+    assert BypassOpDispatch.apply(torch.ops.aten.mm.default, (a, a), {}) == (False, None)

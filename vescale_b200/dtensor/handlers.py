@@ -267,3 +267,50 @@ def _dispatch_with_cond(op, args, kwargs):
 
 
 dispatcher.dispatch = _dispatch_with_cond
+
+
+# ------------------------------------------------------------------------------- bypass table as an object
+class BypassOpDispatch:
+    """The ops that never reach sharding propagation because their result is not a tensor layout question — scalar extraction,
+    size comparison, equality (legacy ``_dispatch_bypass.py:26-158``: ``BypassOpDispatch.apply(op, args, kwargs)`` answers
+    ``(handled, result)``).  Backed by the same functions the dispatcher's handler table holds, so registering one here is
+    registering it there."""
+
+    op_handlers = {
+        aten._local_scalar_dense.default: local_scalar_handler,
+        aten.is_same_size.default: same_size_handler,
+        aten.equal.default: equal_handler,
+    }
+
+    @classmethod
+    def register(cls, op, fn) -> None:
+        cls.op_handlers[op] = fn
+        register_op_handler([op], fn)
+
+    @classmethod
+    def apply(cls, op_call, args, kwargs=None):
+        h = cls.op_handlers.get(op_call)
+        if h is None:
+            return False, None
+        return True, h(op_call, args, kwargs or {})
+
+
+def is_contiguous(spec: DTensorSpec) -> bool:
+    """Whether the global tensor the spec describes is laid out row-major (the ragged handlers address the flat storage)."""
+    expect = 1
+    for size, stride in zip(reversed(spec.tensor_meta.shape), reversed(spec.tensor_meta.stride)):
+        if size != 1 and stride != expect:
+            return False
+        expect *= size
+    return True
+
+
+# the new package's names for the custom handlers (``vescale/dtensor/_dispatch.py:31-250``)
+found_inf_reduce_handler = found_inf_handler
+fused_adamw_sgd_op_handler = fused_optimizer_handler
+ragged_norm_op_handler = ragged_norm_handler
+ragged_norm_kernel = _ragged_norm_kernel
+from . import dispatch as _dispatch_mod  # noqa: E402
+
+for _n in ("found_inf_reduce_handler", "fused_adamw_sgd_op_handler", "ragged_norm_op_handler", "ragged_norm_kernel", "is_contiguous", "BypassOpDispatch"):
+    setattr(_dispatch_mod, _n, globals()[_n])

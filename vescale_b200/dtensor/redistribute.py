@@ -335,3 +335,11 @@ def __getattr__(name):  # ``CrossMeshRedistribute`` lives with the cross-mesh tr
 
         return CrossMeshRedistribute
     raise AttributeError(name)
+
+
+def substitute_ragged_spec(spec: DTensorSpec) -> DTensorSpec:
+    """The spec with every ragged placement replaced by ``Replicate`` — the layout a ragged tensor is gathered to before an op
+    without a ragged rule runs (``vescale/dtensor/_redistribute.py:44-45``)."""
+    from ..layout import substitute_ragged_with_replicate
+
+    return DTensorSpec(spec.mesh, substitute_ragged_with_replicate(spec.placements), spec.tensor_meta)

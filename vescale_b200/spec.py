@@ -157,3 +157,8 @@ def get_sub_spec(spec: DTensorSpec, include: Optional[Sequence[str]] = None, exc
     sub_mesh = spec.mesh[tuple(keep)]
     placements = tuple(spec.placements[names.index(n)] for n in keep)
     return DTensorSpec(sub_mesh, placements, spec.tensor_meta)
+
+
+def is_ragged_shard(spec: "DTensorSpec") -> bool:
+    """Function form of :meth:`DTensorSpec.is_ragged_shard`."""
+    return spec.is_ragged_shard()
