@@ -10,7 +10,7 @@ import torch
 
 from ..layout import local_boxes
 from ..mesh import DeviceMesh
-from ..placement import Partial, Placement, Replicate
+from ..placement import Partial, Placement, Replicate, normalize_placements
 from .collectives import EmulatorProcessGroup
 
 __all__ = ["distribute_tensor", "redistribute_dtensor", "full_tensor", "mesh_all_reduce", "mesh_all_gather", "mesh_reduce_scatter", "mesh_all_to_all", "mesh_broadcast", "mesh_scatter"]
@@ -28,9 +28,33 @@ def _groups_along(mesh: DeviceMesh, mesh_dim: int) -> List[List[int]]:
     return [list(r) for r in mesh._ranks_along(mesh_dim)]
 
 
-def distribute_tensor(tensor: torch.Tensor, mesh: DeviceMesh, placements: Sequence[Placement]) -> List[torch.Tensor]:
-    """Full tensor -> list of local shards indexed by global rank."""
+def _is_dtensor_list(x) -> bool:
+    from ..dtensor.api import DTensor
+
+    return isinstance(x, (list, tuple)) and len(x) > 0 and isinstance(x[0], DTensor)
+
+
+def distribute_tensor(tensor, mesh: DeviceMesh, placements: Sequence[Placement]):
+    """Full tensor -> list of local shards indexed by global rank.
+
+    A LIST of full tensors (one per rank, the reference's front end: ``legacy/emulator/comm_api.py::distribute_tensor`` as
+    driven by ``legacy/test/emulator/test_dtensor.py:84-96``) gives a list of DTensors instead — element r is rank r's DTensor on
+    a view of ``mesh`` pinned to rank r, sliced from ``tensor[r]`` — which instrumented torch functions and
+    :func:`redistribute_dtensor` take as they are."""
     from ..dtensor.api import slice_local
+
+    if isinstance(tensor, (list, tuple)):
+        from . import dtensor_api as _D
+
+        emesh = _D.EmuMesh.from_mesh(mesh)
+        assert len(tensor) == emesh.world, f"{len(tensor)} tensors for a world of {emesh.world}"
+        pl = tuple(normalize_placements(placements, emesh.ndim, tensor[0].ndim))
+        locs = []
+        for c in _coords(emesh.global_view):
+            r = _rank_of(emesh.global_view, c)
+            locs.append((r, slice_local(tensor[r].detach(), emesh.global_view, pl, c)))
+        locs.sort(key=lambda x: x[0])
+        return _D._wrap([t for _, t in locs], tensor[0].shape, emesh, pl)
 
     out: List[Optional[torch.Tensor]] = [None] * mesh.size()
     for c in _coords(mesh):
@@ -91,7 +115,17 @@ def full_tensor(locals_: List[torch.Tensor], shape: Sequence[int], mesh: DeviceM
     return out
 
 
-def redistribute_dtensor(locals_: List[torch.Tensor], shape: Sequence[int], mesh: DeviceMesh, src: Sequence[Placement], dst: Sequence[Placement], pg_kw=None) -> List[torch.Tensor]:
+def redistribute_dtensor(locals_, shape=None, mesh=None, src=None, dst=None, pg_kw=None):
+    """``(locals, shape, mesh, src, dst)`` on plain local tensors, or ``(dtensors, mesh, placements)`` on a list of DTensors
+    (every reduction / gather on the emulated collectives either way)."""
+    if _is_dtensor_list(locals_):
+        from . import dtensor_api as _D
+
+        target = src if src is not None else mesh  # (dts, mesh, placements) arrives as (locals_, shape=mesh, mesh=placements)
+        the_mesh = shape
+        if isinstance(the_mesh, (list, tuple)) or the_mesh is None:
+            raise TypeError("redistribute_dtensor(dtensors, mesh, placements)")
+        return _D.redistribute_dtensor(locals_, _D.EmuMesh.from_mesh(the_mesh, pg_kw), target)
     full = full_tensor(locals_, shape, mesh, src, pg_kw)
     return distribute_tensor(full, mesh, dst)
 

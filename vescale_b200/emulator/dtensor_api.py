@@ -40,15 +40,44 @@ class EmuMesh:
             n *= s
         self.world = n
         self.views = [init_device_mesh(device_type, self.shape, mesh_dim_names=mesh_dim_names, _rank=r, _init_process_groups=False) for r in range(n)]
+        _pin(self.views)
         self.global_view = self.views[0]
         self.ndim = len(self.shape)
         self.pg_kw = pg_kw or {}
+
+    @classmethod
+    def from_mesh(cls, mesh: DeviceMesh, pg_kw: Optional[dict] = None) -> "EmuMesh":
+        """All ranks' views of an existing (emulator or ordinary) mesh object, cached on it."""
+        if isinstance(mesh, cls):
+            return mesh
+        cached = mesh.__dict__.get("_emu_views")
+        if cached is None:
+            cached = cls.__new__(cls)
+            cached.shape = tuple(mesh.shape)
+            cached.world = mesh.size()
+            cached.ndim = mesh.ndim
+            cached.pg_kw = pg_kw or {}
+            cached.views = [
+                DeviceMesh(mesh.device_type, mesh.mesh, mesh_dim_names=mesh.mesh_dim_names, _init_process_groups=False, _rank=r) for r in range(cached.world)
+            ]
+            _pin(cached.views)
+            cached.global_view = cached.views[0]
+            mesh.__dict__["_emu_views"] = cached
+        return cached
 
     def of(self, rank: int) -> DeviceMesh:
         return self.views[rank]
 
     def size(self) -> int:
         return self.world
+
+
+def _pin(views: List[DeviceMesh]) -> None:
+    """A rank-pinned view is a mesh of its own: it must not compare (or hash) equal to the live mesh with the same grid, or to
+    another rank's view — the propagation cache is keyed by specs, and a cached answer carries the mesh (and, for view ops, the
+    per-rank local sizes) of whoever asked first."""
+    for r, v in enumerate(views):
+        v._hash = hash((v._hash, "emulated-rank-view", r))
 
 
 def _wrap(locals_: List[torch.Tensor], shape, mesh: EmuMesh, placements) -> List[DTensor]:
