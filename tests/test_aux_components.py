@@ -811,3 +811,50 @@ def _emulator_dtensor_lists(rank, world):
 
 def test_emulator_list_of_dtensors_front_end():
     run_distributed(_emulator_dtensor_lists, 4)
+
+
+def _fsdp2_patch(rank, world):
+    """``ndtimeline.fsdp_patch``: torch's own ``fully_shard`` emits UNSHARD_AG / GRAD_RS regions once patched; unpatching restores
+    the originals; numerics are untouched."""
+    from torch.distributed.fsdp import fully_shard
+
+    import vescale_b200.profiler.fsdp_patch as fp
+    from vescale.ndtimeline.fsdp_patch import is_fsdp_patched, patch_fsdp
+    from vescale_b200.profiler import predefined
+
+    seen = []
+    real = fp.ndtimeit
+
+    def spy(metric, *a, **kw):
+        seen.append((metric, kw.get("unit")))
+        return real(metric, *a, **kw)
+
+    fp.ndtimeit = spy
+    try:
+        assert not is_fsdp_patched()
+        patch_fsdp()
+        patch_fsdp()  # idempotent
+        assert is_fsdp_patched()
+        torch.manual_seed(0)
+        ref = nn.Sequential(nn.Linear(8, 8), nn.Linear(8, 4)).to(device_type())
+        import copy
+
+        m = copy.deepcopy(ref)
+        for layer in m:
+            fully_shard(layer)
+        fully_shard(m)
+        x = torch.randn(4, 8, device=device_type())
+        m(x).sum().backward()
+        ref(x).sum().backward()
+        metrics = [s[0] for s in seen]
+        assert metrics.count(predefined.UNSHARD_AG) >= 2 and metrics.count(predefined.GRAD_RS) >= 2, metrics
+        assert torch.allclose(m[0].weight.grad.full_tensor(), ref[0].weight.grad, atol=1e-6)
+        fp.unpatch_fsdp()
+        assert not is_fsdp_patched()
+    finally:
+        fp.ndtimeit = real
+        fp.unpatch_fsdp()
+
+
+def test_ndtimeline_patch_for_torch_fsdp2():
+    run_distributed(_fsdp2_patch, 2)

@@ -157,6 +157,7 @@ _ALIASES = {
     "vescale.emulator.nccl.graph.tuning": "vescale_b200.emulator.nccl.tuning",
     "vescale.emulator.nccl.nccl_profiler_result": "vescale_b200.emulator.nccl.profiler_result",
     "vescale.ndtimeline.api": "vescale_b200.profiler.timer",
+    "vescale.ndtimeline.fsdp_patch": "vescale_b200.profiler.fsdp_patch",
     "vescale.ndtimeline.timer": "vescale_b200.profiler.timer",
     "vescale.ndtimeline.pool": "vescale_b200.profiler.pool",
     "vescale.ndtimeline.stream": "vescale_b200.profiler.stream",
